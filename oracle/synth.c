@@ -1,0 +1,202 @@
+/* CPU ORACLE (test infrastructure) -- SYNTH-CELT/1 frame decode and the CPU baseline loop.
+ *
+ * The reference's CeltDecoder::decode is a stub (src/celt/decoder.rs:47-56 is `todo!()`), so
+ * there is no reference frame format to follow.  SYNTH-CELT/1
+ * is a frame layout built only from operations the reference implements, chained the way
+ * src/decoder.rs:700-711 would chain them:
+ *   RangeDecoder::new -> flags / post-filter parameters / Laplace energies / raw fine bits ->
+ *   decode_pulses per band part -> (synthetic unit-norm "denormalise") -> Mdct::backward with the
+ *   60-sample carry -> comb_filter_inplace on the rolling history -> interleaved f32 PCM.
+ * This file is the straight-line CPU composition of the oracle primitives; the CUDA path must
+ * reproduce it bit-exactly for every integer and within 1e-5 max-abs for PCM. */
+#include "oracle.h"
+#include "oracle_tables.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define HIST 1024
+static const uint8_t TAPSET_ICDF[3] = {2, 1, 0};
+
+void orc_synth_state_init(orc_synth_state *s) { memset(s, 0, sizeof(*s)); }
+
+static void decode_symbols(orc_dec *d, int lm, int channels, orc_synth_side *side, int32_t *y_out,
+                           float *coef)
+{
+    int nf = 120 << lm;
+    memset(side, 0, sizeof(*side));
+    memset(coef, 0, sizeof(float) * (size_t)nf * (size_t)channels);
+    if (y_out) memset(y_out, 0, sizeof(int32_t) * (size_t)nf * (size_t)channels);
+
+    side->silence = orc_dec_bit_logp(d, 15);
+    if (!side->silence) {
+        side->postfilter = orc_dec_bit_logp(d, 1);
+        if (side->postfilter) {
+            side->octave = (int32_t)orc_dec_uint(d, 6);
+            side->period = (16 << side->octave) + (int32_t)orc_dec_bits(d, 4 + (uint32_t)side->octave) - 1;
+            side->gain_idx = (int32_t)orc_dec_bits(d, 3);
+            side->tapset = (int32_t)orc_dec_icdf(d, TAPSET_ICDF, 2);
+        }
+        side->transient = orc_dec_bit_logp(d, 3);
+        side->intra = orc_dec_bit_logp(d, 3);
+        for (int b = 0; b < 21; b++)
+            for (int c = 0; c < channels; c++) {
+                uint32_t decay = 6000u + 400u * (uint32_t)b;
+                side->coarse[c][b] = orc_dec_laplace(d, orc_laplace_start_freq(decay), decay);
+            }
+        for (int b = 0; b < 21; b++)
+            for (int c = 0; c < channels; c++) side->fine[c][b] = (int32_t)orc_dec_bits(d, 2);
+        int32_t y[176];
+        for (int b = 0; b < 21; b++)
+            for (int c = 0; c < channels; c++) {
+                int n = ORC_SYNTH_SCHED[lm][b][0], parts = ORC_SYNTH_SCHED[lm][b][1],
+                    k = ORC_SYNTH_SCHED[lm][b][2];
+                int base = c * nf + ((int)ORC_E_BANDS[b] << lm);
+                if (n == 1) {
+                    uint32_t sign = orc_dec_bits(d, 1);
+                    coef[base] = sign ? -0.03125f : 0.03125f;
+                    if (y_out) y_out[base] = sign ? -1 : 1;
+                    side->n_pulses += 1;
+                    continue;
+                }
+                for (int p = 0; p < parts; p++) {
+                    float yy = orc_decode_pulses(d, y, (uint32_t)n, (uint32_t)k);
+                    float g = 0.03125f / sqrtf(yy);
+                    for (int j = 0; j < n; j++) {
+                        coef[base + p * n + j] = (float)y[j] * g;
+                        if (y_out) y_out[base + p * n + j] = y[j];
+                    }
+                    side->n_pulses += (uint32_t)k;
+                }
+            }
+    }
+    side->final_rng = d->rng;
+    side->tell_frac = orc_dec_tell_frac(d);
+}
+
+int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm,
+                           int channels, int apply_comb, orc_synth_side *side, int32_t *y_out,
+                           float *coef_out, float *pcm_out)
+{
+    if (lm < 0 || lm > 3 || channels < 1 || channels > 2) return ORC_ERR_BAD_ARG;
+    int nf = 120 << lm;
+    float coef_local[2 * 960];
+    float *coef = coef_out ? coef_out : coef_local;
+    orc_synth_side side_local;
+    if (!side) side = &side_local;
+
+    int lost = len == 0;
+    if (lost) {
+        memset(side, 0, sizeof(*side));
+        memset(coef, 0, sizeof(float) * (size_t)nf * (size_t)channels);
+        if (y_out) memset(y_out, 0, sizeof(int32_t) * (size_t)nf * (size_t)channels);
+    } else {
+        orc_dec d;
+        orc_dec_init(&d, payload, len);
+        decode_symbols(&d, lm, channels, side, y_out, coef);
+    }
+
+    int t1 = st->pf_period, tap1 = st->pf_tapset;
+    float g1 = st->pf_gain;
+    if (!lost) {
+        t1 = side->postfilter ? side->period : 0;
+        g1 = side->postfilter ? 0.09375f * (float)(side->gain_idx + 1) : 0.0f;
+        tap1 = side->postfilter ? side->tapset : 0;
+    }
+
+    int blocks = side->transient ? (1 << lm) : 1;
+    int shift = side->transient ? 3 : 3 - lm;
+    float work[HIST + 960 + 60];
+    for (int c = 0; c < channels; c++) {
+        memcpy(work, st->hist[c], sizeof(float) * HIST);
+        memcpy(work + HIST, st->carry[c], sizeof(float) * 60);
+        memset(work + HIST + 60, 0, sizeof(float) * (size_t)nf);
+        for (int b = 0; b < blocks; b++)
+            orc_mdct_backward(coef + c * nf + b, work + HIST + 120 * b * (blocks > 1), ORC_WINDOW,
+                              ORC_OVERLAP, shift, blocks);
+        if (apply_comb)
+            orc_comb_filter_inplace(work, HIST, (size_t)st->pf_period, (size_t)t1, (size_t)nf,
+                                    st->pf_gain, g1, (size_t)st->pf_tapset, (size_t)tap1, ORC_OVERLAP);
+        for (int i = 0; i < nf; i++) pcm_out[i * channels + c] = work[HIST + i];
+        memcpy(st->carry[c], work + HIST + nf, sizeof(float) * 60);
+        memcpy(st->hist[c], work + nf, sizeof(float) * HIST);
+    }
+    st->pf_period = t1;
+    st->pf_gain = g1;
+    st->pf_tapset = tap1;
+    return nf;
+}
+
+/* ------------------------------------------------------------------ CPU baseline */
+typedef struct {
+    const uint8_t *packets;
+    uint32_t n_streams, n_frames, pkt_bytes, s0, s1;
+    int lm, channels, apply_comb;
+    float *pcm_last;
+    uint32_t rng_xor;
+} bench_job;
+
+static void *bench_thread(void *arg)
+{
+    bench_job *j = (bench_job *)arg;
+    int nf = 120 << j->lm;
+    orc_synth_state *st = (orc_synth_state *)malloc(sizeof(orc_synth_state));
+    float pcm[2 * 960];
+    orc_synth_side side;
+    uint32_t x = 0;
+    for (uint32_t s = j->s0; s < j->s1; s++) {
+        orc_synth_state_init(st);
+        for (uint32_t f = 0; f < j->n_frames; f++) {
+            const uint8_t *pkt = j->packets + ((size_t)f * j->n_streams + s) * j->pkt_bytes;
+            /* byte 0 is the TOC */
+            orc_synth_decode_frame(st, pkt + 1, j->pkt_bytes - 1, j->lm, j->channels, j->apply_comb,
+                                   &side, NULL, NULL, pcm);
+            x ^= side.final_rng;
+        }
+        if (j->pcm_last)
+            memcpy(j->pcm_last + (size_t)s * (size_t)nf * (size_t)j->channels, pcm,
+                   sizeof(float) * (size_t)nf * (size_t)j->channels);
+    }
+    j->rng_xor = x;
+    free(st);
+    return NULL;
+}
+
+double orc_synth_bench(const uint8_t *packets, uint32_t n_streams, uint32_t n_frames,
+                       uint32_t pkt_bytes, int lm, int channels, int apply_comb, int n_threads,
+                       float *pcm_last, uint32_t *final_rng_xor)
+{
+    if (n_threads < 1) n_threads = 1;
+    if ((uint32_t)n_threads > n_streams) n_threads = (int)n_streams;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    bench_job *jobs = (bench_job *)calloc((size_t)n_threads, sizeof(bench_job));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < n_threads; t++) {
+        bench_job *j = &jobs[t];
+        j->packets = packets;
+        j->n_streams = n_streams;
+        j->n_frames = n_frames;
+        j->pkt_bytes = pkt_bytes;
+        j->s0 = (uint32_t)((uint64_t)n_streams * (uint64_t)t / (uint64_t)n_threads);
+        j->s1 = (uint32_t)((uint64_t)n_streams * (uint64_t)(t + 1) / (uint64_t)n_threads);
+        j->lm = lm;
+        j->channels = channels;
+        j->apply_comb = apply_comb;
+        j->pcm_last = pcm_last;
+        pthread_create(&th[t], NULL, bench_thread, j);
+    }
+    uint32_t x = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        x ^= jobs[t].rng_xor;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (final_rng_xor) *final_rng_xor = x;
+    free(th);
+    free(jobs);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

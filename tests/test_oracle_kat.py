@@ -1,0 +1,327 @@
+"""Pins the CPU oracle to the reference crate's own known-answer tests.
+Every test names the reference test it restates.  CPU only."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+L = O.lib()
+
+
+# ---- range_coder/mod.rs:155-188 test_tell / test_tell_frac / test_tell_frac_limits
+def test_tell_kats():
+    assert len(KATS["tell"]) == 13 and len(KATS["tell_frac"]) == 9
+    for bits_total, rng, want in KATS["tell"]:
+        assert L.orc_tell(bits_total, rng) == want
+    for bits_total, rng, want in KATS["tell_frac"]:
+        assert L.orc_tell_frac(bits_total, rng) == want
+
+
+# ---- range_coder/mod.rs:191-263 test_simple_uint_bits
+def test_simple_uint_bits():
+    ops, vals, entropy = [], [], 0.0
+    for ft in range(2, 1024):
+        for i in range(ft):
+            entropy += math.log(ft) * math.log2(math.e)
+            ops.append((O.OP_UINT, ft, 0))
+            vals.append(i)
+    for ftb in range(1, 16):
+        for i in range(1 << ftb):
+            entropy += ftb
+            ops.append((O.OP_BITS, ftb, 0))
+            vals.append(i)
+    ops = np.array(ops, dtype=O.OP_DTYPE)
+    vals = np.array(vals, dtype=np.uint32)
+    buf, tf, range_bytes, final_tf, err = O.enc_run_script(10 * 1024 * 1024, ops, vals)
+    assert err == 0
+    k = KATS["simple_uint_bits"]
+    assert abs(entropy - k["entropy"]) < 2.3e-10  # f64::EPSILON in the reference; sum order differs
+    assert final_tf / 8.0 == k["tell_frac_over_8"]
+    assert range_bytes == k["range_bytes"] == 497192
+    # raw bits cost exactly ftb bits each (mod.rs:209-219): tell_frac rises by 8*ftb
+    nb = (1 << 16) - 2
+    raw_tf = tf[-nb:].astype(np.int64)
+    raw_bits = ops["a"][-nb:].astype(np.int64)
+    assert np.all(np.diff(np.concatenate([[tf[-nb - 1]], raw_tf])) == 8 * raw_bits)
+    out, _ = O.dec_run_script(buf, ops)
+    assert np.array_equal(out["value"], vals)
+    assert out["tell_frac"][-1] == final_tf
+    assert np.array_equal(out["tell_frac"], tf)  # per-symbol enc/dec agreement (mod.rs:367-374)
+
+
+# ---- range_coder/mod.rs:271-298 test_encoder_prefers_range_coder_data
+def test_encoder_prefers_range_coder_data():
+    buf = np.zeros(2, np.uint8)
+    e = O.Enc()
+    L.orc_enc_init(C.byref(e), O.ptr(buf), 2)
+    L.orc_enc_bits(C.byref(e), 0x55, 7)
+    for v, ft in [(1, 2), (1, 3), (1, 4), (1, 5), (2, 6), (6, 7)]:
+        L.orc_enc_uint(C.byref(e), v, ft)
+    L.orc_enc_done(C.byref(e))  # busts: the reference unwraps Ok here too
+    d = O.Dec()
+    L.orc_dec_init(C.byref(d), O.ptr(buf), 2)
+    assert L.orc_dec_bits(C.byref(d), 7) == 0x05
+    assert [L.orc_dec_uint(C.byref(d), ft) for ft in (2, 3, 4, 5, 6, 7)] == [1, 1, 1, 1, 2, 6]
+
+
+# ---- range_coder/mod.rs:498-516 test_patch_initial_bits
+def test_patch_initial_bits():
+    buf = np.zeros(10000, np.uint8)
+    e = O.Enc()
+    L.orc_enc_init(C.byref(e), O.ptr(buf), len(buf))
+    for v, lp in [(0, 1), (0, 1), (1, 6), (0, 2)]:
+        assert L.orc_enc_bit_logp(C.byref(e), v, lp) == 0
+    assert L.orc_enc_patch_initial_bits(C.byref(e), 0, 2) == 0
+    assert L.orc_enc_done(C.byref(e)) == 0
+    assert L.orc_enc_range_bytes(C.byref(e)) == 2
+    assert buf[0] == 63
+
+
+# ---- range_coder/mod.rs:519-528 test_shrink
+def test_shrink():
+    buf = np.zeros(10000, np.uint8)
+    e = O.Enc()
+    L.orc_enc_init(C.byref(e), O.ptr(buf), len(buf))
+    for v in (1, 2, 3, 4):
+        L.orc_enc_uint(C.byref(e), v, 255)
+    L.orc_enc_done(C.byref(e))
+    L.orc_enc_shrink(C.byref(e), 5)
+    d = O.Dec()
+    L.orc_dec_init(C.byref(d), O.ptr(buf), 5)
+    assert [L.orc_dec_uint(C.byref(d), 255) for _ in range(4)] == [1, 2, 3, 4]
+
+
+# ---- range_coder/mod.rs:301-377 test_random_data (property; numpy RNG replaces nanorand)
+def test_random_data_roundtrip_and_tell():
+    rnd = np.random.default_rng(42)
+    for _ in range(256):
+        ft = int(rnd.integers(2, 1024))
+        sz = int(rnd.integers(128, 512))
+        zeros = rnd.integers(0, 14) == 0
+        data = np.zeros(sz, np.uint32) if zeros else rnd.integers(0, ft, sz).astype(np.uint32)
+        ops = np.array([(O.OP_UINT, ft, 0)] * sz, dtype=O.OP_DTYPE)
+        buf, tf, rb, ftf, err = O.enc_run_script(10000, ops, data)
+        assert err == 0
+        out, _ = O.dec_run_script(buf, ops)
+        assert np.array_equal(out["value"], data)
+        assert np.array_equal(out["tell_frac"], tf)
+        assert (ftf // 8 + 7) // 8 + 1 >= rb
+
+
+# ---- range_coder/mod.rs:381-495 test_compatibility: 4 encode x 4 decode methods for binary symbols
+def test_compatibility():
+    rnd = np.random.default_rng(42)
+    meth = [O.OP_BIT_VIA_DECODE, O.OP_BIT_VIA_DECODE_BIN, O.OP_BIT_LOGP, O.OP_ICDF]
+    pool = np.array([1, 0], np.uint8)
+    for _ in range(256):
+        sz = int(rnd.integers(128, 512))
+        data = rnd.integers(0, 2, sz).astype(np.uint32)
+        logp = rnd.integers(1, 17, sz)
+
+        def mk(methods):
+            return np.array([(meth[m], 0, lp) if meth[m] == O.OP_ICDF else (meth[m], lp, 0) for m, lp in zip(methods, logp)], dtype=O.OP_DTYPE)
+
+        eops, dops = mk(rnd.integers(0, 4, sz)), mk(rnd.integers(0, 4, sz))
+        buf, tf, rb, ftf, err = O.enc_run_script(10000, eops, data, icdf_pool=pool)
+        assert err == 0
+        out, _ = O.dec_run_script(buf, dops, icdf_pool=pool)
+        assert np.array_equal(out["value"], data)
+        assert np.array_equal(out["tell_frac"], tf)
+
+
+# ---- range_coder/mod.rs:537-570 test_laplace
+def test_laplace():
+    rnd = np.random.default_rng(42)
+    val = (rnd.integers(0, 16, 10000) - 7).astype(np.int32)
+    decay = rnd.integers(5000, 16000, 10000).astype(np.uint32)
+    val[:3] = [3, 0, -1]
+    decay[:3] = [6000, 5800, 5600]
+    ops = np.array([(O.OP_LAPLACE, L.orc_laplace_start_freq(int(d)), int(d)) for d in decay], dtype=O.OP_DTYPE)
+    buf, tf, rb, ftf, err = O.enc_run_script(40000, ops, val.view(np.uint32))
+    assert err == 0
+    out, _ = O.dec_run_script(buf, ops)
+    assert np.array_equal(out["value"].view(np.int32), val)
+    assert np.array_equal(out["tell_frac"], tf)
+
+
+# ---- celt/pvc.rs:439-451 test_pvq_v
+def test_pvq_v_kats():
+    assert len(KATS["pvq_v"]) == 11
+    for n, k, want in KATS["pvq_v"]:
+        assert L.orc_pvq_v(n, k) == want
+
+
+# ---- celt/pvc.rs:453-503 test_pvc
+def test_pvc_roundtrip():
+    def get_pulses(i):
+        return i if i < 8 else (8 + (i & 7)) << ((i >> 3) - 1)
+
+    for n, kmax in zip(KATS["pvc_pn"], KATS["pvc_pk_max"]):
+        for pseudo in range(1, 41):
+            k = get_pulses(pseudo)
+            if k > kmax:
+                break
+            nc = L.orc_pvq_v(n, k)
+            inc = max(nc // 2000, 1)  # reference uses nc/20000; thinned to keep the CPU suite short
+            y = np.zeros(n, np.int32)
+            for i in range(0, nc, inc):
+                yy = L.orc_cwrsi(O.ptr(y), n, k, i)
+                assert int(np.abs(y).sum()) == k
+                assert yy == float((y.astype(np.int64) ** 2).sum())
+                assert L.orc_icwrs(O.ptr(y), n) == i
+
+
+# ---- celt/kiss_fft.rs:594-703 test_dft: forward and inverse vs O(n^2) f64 DFT, SNR > 130 dB
+@pytest.mark.parametrize("shift,nfft", [(3, 60), (2, 120), (1, 240), (0, 480)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_dft(shift, nfft, inverse):
+    rnd = np.random.default_rng(42)
+    x = ((rnd.integers(0, 32767, nfft) - 16384) + 1j * (rnd.integers(0, 32767, nfft) - 16384)) * 32768.0
+    if inverse:
+        x = x / nfft
+    x = x.astype(np.complex64)
+    bitrev = np.ctypeslib.as_array(L.orc_fft_bitrev(shift), shape=(nfft,))
+    buf = np.zeros(nfft, np.complex64)
+    if inverse:
+        buf[bitrev] = np.conj(x)
+    else:
+        buf[bitrev] = (x * np.float32(L.orc_fft_scale(shift))).astype(np.complex64)
+    L.orc_fft_process(shift, O.ptr(buf))
+    got = np.conj(buf) if inverse else buf
+    k = np.arange(nfft)
+    W = np.exp((2j if inverse else -2j) * np.pi * np.outer(k, k) / nfft)
+    want = W @ x.astype(np.complex128) / (1 if inverse else nfft)
+    snr = 10 * np.log10((np.abs(want) ** 2).sum() / (np.abs(want - got) ** 2).sum())
+    assert snr > 130.0
+
+
+# ---- celt/mdct.rs:639-757 test_mdct: forward SNR > 130 dB, inverse SNR > 60 dB vs f64 definition
+@pytest.mark.parametrize("shift,nfft", [(3, 240), (2, 480), (1, 960), (0, 1920)])
+def test_mdct_forward(shift, nfft):
+    rnd = np.random.default_rng(42)
+    x = ((rnd.integers(0, 32768, nfft) - 16384) * 32768.0).astype(np.float32)
+    out = np.zeros(nfft, np.float32)
+    win = np.ones(nfft // 2, np.float32)
+    L.orc_mdct_forward(O.ptr(x.copy()), O.ptr(out), O.ptr(win), nfft // 2, shift, 1)
+    i = np.arange(nfft // 2)[:, None]
+    k = np.arange(nfft)[None, :]
+    want = (np.cos(2 * np.pi * (k + 0.5 + 0.25 * nfft) * (i + 0.5) / nfft) / (nfft // 4)) @ x.astype(np.float64)
+    got = out[: nfft // 2].astype(np.float64)
+    assert 10 * np.log10((want ** 2).sum() / ((want - got) ** 2).sum()) > 130.0
+
+
+@pytest.mark.parametrize("shift,nfft", [(3, 240), (2, 480), (1, 960), (0, 1920)])
+def test_mdct_backward(shift, nfft):
+    rnd = np.random.default_rng(42)
+    x = ((rnd.integers(0, 32768, nfft) - 16384) * 32768.0 / nfft).astype(np.float32)
+    out = np.zeros(nfft, np.float32)
+    win = np.ones(nfft // 2, np.float32)
+    L.orc_mdct_backward(O.ptr(x), O.ptr(out), O.ptr(win), nfft // 2, shift, 1)
+    out[nfft - 1 - np.arange(nfft // 4)] = out[nfft // 2 + np.arange(nfft // 4)]  # mdct.rs:735-738
+    i = np.arange(nfft)[:, None]
+    k = np.arange(nfft // 2)[None, :]
+    want = np.cos(2 * np.pi * (i + 0.5 + 0.25 * nfft) * (k + 0.5) / nfft) @ x[: nfft // 2].astype(np.float64)
+    assert 10 * np.log10((want ** 2).sum() / ((want - out) ** 2).sum()) > 60.0
+
+
+# ---- celt/comb_filter/mod.rs:227-270 golden vectors
+def test_comb_filter_golden():
+    p = KATS["comb_params"]
+    size, n = p["SIZE"], p["N"]
+    x = np.arange(size, dtype=np.float32)
+    y = np.zeros(size, np.float32)
+    O.comb_filter(y, size - n, x, size - n, p["T0"], p["T1"], n, p["G0"], p["G1"], 0, 0, p["OVERLAP"])
+    want = np.array(KATS["comb_test_vector1"], np.float32)
+    assert np.all(np.abs(1.0 - y[size - n:] / want) < 1e-5)
+    assert np.array_equal(y[size - n:], want)  # in fact bit-identical to the printed literals
+
+
+def test_comb_filter_inplace_golden():
+    p = KATS["comb_params"]
+    size, n = p["SIZE"], p["N"]
+    y = np.arange(size, dtype=np.float32)
+    O.comb_filter_inplace(y, size - n, p["T0"], p["T1"], n, p["G0"], p["G1"], 0, 0, p["OVERLAP"])
+    want = np.array(KATS["comb_test_vector2"], np.float32)
+    assert np.all(np.abs(1.0 - y[size - n:] / want) < 1e-5)
+
+
+# ---- math.rs:237-298 bitexact trig checksums
+def test_bitexact_cos():
+    chk, max_d, min_d, last = 0, 0, 32767, 32767
+    for i in range(64, 16321):
+        q = L.orc_bitexact_cos(i)
+        chk ^= q * i
+        d = last - q
+        max_d, min_d, last = max(max_d, d), min(min_d, d), q
+    assert (L.orc_bitexact_cos(64), L.orc_bitexact_cos(16320), L.orc_bitexact_cos(8192)) == (32767, 200, 23171)
+    assert (chk, max_d, min_d) == (89408644, 5, 0)
+
+
+def test_bitexact_log2tan():
+    chk, max_d, min_d, last = 0, 0, 15059, 15059
+    for i in range(64, 8193):
+        mid, side = L.orc_bitexact_cos(i), L.orc_bitexact_cos(16384 - i)
+        q = L.orc_bitexact_log2tan(mid, side)
+        assert q == -L.orc_bitexact_log2tan(side, mid)
+        chk ^= q * i
+        d = last - q
+        max_d, min_d, last = max(max_d, d), min(min_d, d), q
+    assert (chk, max_d, min_d) == (15821257, 61, -2)
+    assert L.orc_bitexact_log2tan(32767, 200) == 15059
+    assert L.orc_bitexact_log2tan(30274, 12540) == 2611
+    assert L.orc_bitexact_log2tan(23171, 23171) == 0
+
+
+# ---- lib.rs:653-768 query_packet_* tables
+def test_query_packet_tables():
+    bw = [L.orc_packet_bandwidth(O.ptr(np.array([c << 3], np.uint8))) for c in range(32)]
+    assert bw == [0] * 4 + [1] * 4 + [2] * 4 + [3, 3, 4, 4] + [0] * 4 + [2] * 4 + [3] * 4 + [4] * 4
+    fs = [L.orc_packet_samples_per_frame(O.ptr(np.array([c << 3], np.uint8)), 48000) for c in range(32)]
+    assert fs == [480, 960, 1920, 2880] * 3 + [480, 960, 480, 960] + [120, 240, 480, 960] * 4
+    b = lambda *x: O.ptr(np.array(x, np.uint8))
+    assert L.orc_packet_channels(b(0)) == 1 and L.orc_packet_channels(b(4)) == 2
+    assert [L.orc_packet_frame_count(b(0), 1), L.orc_packet_frame_count(b(1), 1), L.orc_packet_frame_count(b(2), 1)] == [1, 2, 2]
+    assert L.orc_packet_frame_count(b(3), 1) < 0 and L.orc_packet_frame_count(b(3, 5), 2) == 5
+    assert L.orc_packet_sample_count(b(70), 1, 48000) == 960
+    assert L.orc_packet_sample_count(b(3), 1, 48000) < 0
+    assert L.orc_packet_sample_count(b(255, 5), 2, 48000) == 4800
+
+
+# ---- lib.rs:771-860 parse_packet KATs
+@pytest.mark.parametrize("name,count,frames,sizes,payload_off,packet_off", [
+    ("single", 1, [1], [11], 1, 12), ("cbr", 2, [1, 6], [5, 5], 1, 11), ("vbr", 2, [2, 6], [4, 6], 2, 12)])
+def test_parse_packet(name, count, frames, sizes, payload_off, packet_off):
+    pkt = np.array(KATS["packet_" + name], np.uint8)
+    fr, sz = np.zeros(48, np.uint32), np.zeros(48, np.uint32)
+    po, ko = C.c_uint32(0), C.c_uint32(0)
+    assert L.orc_parse_packet(O.ptr(pkt), len(pkt), 0, O.ptr(fr), O.ptr(sz), C.byref(po), C.byref(ko)) == count
+    assert list(fr[:count]) == frames and list(sz[:count]) == sizes
+    assert (po.value, ko.value) == (payload_off, packet_off)
+
+
+def test_parse_packet_invalid():
+    pkt = np.array(KATS["packet_invalid"], np.uint8)
+    fr, sz = np.zeros(48, np.uint32), np.zeros(48, np.uint32)
+    assert L.orc_parse_packet(O.ptr(pkt), len(pkt), 0, O.ptr(fr), O.ptr(sz), None, None) < 0
+
+
+# ---- lib.rs:863-890 test_pcm_soft_clip
+def test_pcm_soft_clip():
+    s = np.zeros(8, np.float32)
+    base = ((np.arange(1024) & 255) * (1.0 / 32.0) - 4.0).astype(np.float32)
+    for i in range(0, 1024, 37):
+        x = base.copy()
+        tail = np.ascontiguousarray(x[i:])
+        L.orc_pcm_soft_clip(O.ptr(tail), len(tail), 1, O.ptr(s), 8)
+        assert tail.max() <= 1.0 and tail.min() >= -1.0
+    for ch in range(1, 9):
+        x = base.copy()
+        L.orc_pcm_soft_clip(O.ptr(x), 1024, ch, O.ptr(s), 8)
+        n = (1024 // ch) * ch
+        assert x[:n].max() <= 1.0 and x[:n].min() >= -1.0

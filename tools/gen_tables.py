@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""Generate the constant tables of the CELT 48 kHz / 960 standard mode.
+
+Nothing here is copied from the reference: every table is recomputed from its
+defining formula and the result is checked (tests/test_tables_vs_reference.py,
+container-only) against the literals in the reference crate:
+
+  TRIG[1800]      /root/reference/src/celt/mdct.rs:265-626
+                  f32(cos(2*PI_F*(i+1/8)/N)) for N = 1920, 960, 480, 240 (i < N/2), where
+                  PI_F is the *single precision* constant 3.141592653f the upstream C
+                  generator used, then rounded through an 8-significant-digit decimal
+                  (the precision the literals were printed with).  Reproduces 1800/1800.
+  WINDOW[120]     src/celt/mode.rs:43-68
+                  sin(pi/2 * sin^2(pi/2 * (i+1/2)/120)) in double, printed with 8 significant
+                  digits, parsed as f32.  Reproduces 120/120.
+  TWIDDLES[480]   src/celt/kiss_fft.rs:341-582
+                  (cos, sin)(-2*pi*k/480) in double, 8 significant digits, parsed as f32.
+                  Reproduces 957/960 scalars; the three that differ are the "zero"
+                  crossings, where the upstream table holds x87 `fcos/fsin` argument
+                  reduction residue instead of the IEEE double result.  They are listed
+                  in X87_RESIDUE below (value ~1e-16, no effect on PCM at the 1e-5 bar,
+                  but kept so that the table is bit-identical).
+  BITREV_*        src/celt/kiss_fft.rs:281-336  (kiss-fft recursive digit reversal of the
+                  factor lists at kiss_fft.rs:251,259,267,275)
+  PVQ_U           src/celt/pvc.rs:301-429  U(n,k)=U(n-1,k)+U(n,k-1)+U(n-1,k-1) (pvc.rs:293)
+
+Outputs two headers with the same numbers and different symbol prefixes, so that the
+oracle and the product never include each other's files:
+    oracle/oracle_tables.h                 (prefix ORC_)
+    opus-native_b200/csrc/opn_tables.h     (prefix OPN_)
+"""
+import math
+import os
+import struct
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def f32(x: float) -> float:
+    return struct.unpack("<f", struct.pack("<f", x))[0]
+
+
+def via_text8(x: float) -> float:
+    """8 significant decimal digits -> nearest f32 (how the literals were produced)."""
+    return f32(float("%.8g" % x))
+
+
+PI_F = f32(3.141592653)
+
+# (index, component) -> value ; see module docstring.
+X87_RESIDUE = {(120, "r"): 6.1230318e-17, (360, "r"): -1.8369095e-16, (240, "i"): -1.2246064e-16}
+
+FACTORS = {
+    480: [5, 96, 3, 32, 4, 8, 2, 4, 4, 1],
+    240: [5, 48, 3, 16, 4, 4, 4, 1],
+    120: [5, 24, 3, 8, 2, 4, 4, 1],
+    60: [5, 12, 3, 4, 4, 1],
+}
+
+# last column stored for row r = min(n,k)  (pvc.rs:316-427)
+PVQ_ROW_LAST = [176, 176, 176, 176, 176, 176, 96, 54, 37, 28, 24, 19, 18, 16, 14]
+
+E_BANDS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100]
+LOG_N = [0, 0, 0, 0, 0, 0, 0, 0, 8, 8, 8, 8, 16, 16, 16, 21, 21, 24, 29, 34, 36]
+# Q15 tap gains / 32768 (comb_filter/mod.rs:45-55)
+COMB_GAINS_Q15 = [10048, 7112, 4248, 15200, 8784, 0, 26208, 3280, 0]
+
+
+def trig_table():
+    out = []
+    for shift in range(4):
+        n = 1920 >> shift
+        for i in range(n // 2):
+            out.append(via_text8(f32(math.cos(2 * PI_F * (i + 0.125) / n))))
+    return out
+
+
+def window_table():
+    out = []
+    for i in range(120):
+        s = math.sin(0.5 * math.pi * (i + 0.5) / 120)
+        out.append(via_text8(math.sin(0.5 * math.pi * s * s)))
+    return out
+
+
+def twiddle_table():
+    out = []
+    for k in range(480):
+        ph = (-2 * math.pi / 480) * k
+        r = via_text8(math.cos(ph))
+        i = via_text8(math.sin(ph))
+        if (k, "r") in X87_RESIDUE:
+            r = f32(X87_RESIDUE[(k, "r")])
+        if (k, "i") in X87_RESIDUE:
+            i = f32(X87_RESIDUE[(k, "i")])
+        out.append((r, i))
+    return out
+
+
+def bitrev_table(nfft):
+    """kiss-fft compute_bitrev_table: recursive digit reversal."""
+    fac = FACTORS[nfft]
+    table = [0] * nfft
+
+    def rec(fout, f_base, fstride, in_stride, fi):
+        p, m = fac[fi], fac[fi + 1]
+        if m == 1:
+            for j in range(p):
+                table[f_base + j] = fout
+                fout += fstride * in_stride
+        else:
+            for j in range(p):
+                rec(fout, f_base, fstride * p, in_stride, fi + 2)
+                f_base += m
+                fout += fstride * in_stride
+
+    # Table maps natural index -> position; the reference stores bitrev[i] = position of
+    # input i, which is the inverse of the kiss-fft "f" walk below.
+    order = [0] * nfft
+    pos = [0]
+
+    def walk(fout, fstride, fi):
+        p, m = fac[fi], fac[fi + 1]
+        if m == 1:
+            for j in range(p):
+                order[pos[0]] = fout + j * fstride
+                pos[0] += 1
+        else:
+            for j in range(p):
+                walk(fout + j * fstride, fstride * p, fi + 2)
+
+    walk(0, 1, 0)
+    # order[q] = natural input index stored at position q  ->  bitrev[input] = q
+    inv = [0] * nfft
+    for q, i in enumerate(order):
+        inv[i] = q
+    return inv
+
+
+def pvq_tables():
+    nmax = 177
+    # U(0,0)=1, U(0,k>0)=0, U(n>0,0)=0; only cells with min(n,k) <= 15 are needed.
+    full = [[0] * (nmax + 1) for _ in range(nmax + 1)]
+    full[0][0] = 1
+    for n in range(1, nmax + 1):
+        for k in range(1, nmax + 1):
+            if min(n, k) > 15:
+                continue
+            full[n][k] = full[n - 1][k] + full[n][k - 1] + full[n - 1][k - 1]
+    data, rows = [], []
+    for r, last in enumerate(PVQ_ROW_LAST):
+        rows.append(len(data) - r)
+        for c in range(r, last + 1):
+            v = full[r][c]
+            assert v < 2 ** 32, (r, c, v)
+            data.append(v)
+    return rows, data
+
+
+# pvc.rs:463-469 (test_pvc): band sizes reachable by splitting and the largest K whose V(N,K)
+# fits in 32 bits.
+PVQ_N = [2, 3, 4, 6, 8, 9, 11, 12, 16, 18, 22, 24, 32, 36, 44, 48, 64, 72, 88, 96, 144, 176]
+PVQ_KMAX = [128, 128, 128, 88, 36, 26, 18, 16, 12, 11, 9, 9, 7, 7, 6, 6, 5, 5, 5, 5, 4, 4]
+SYNTH_RATE = 0.65  # bits per coefficient (SYNTH-CELT/1)
+
+
+def synth_schedule():
+    """SYNTH-CELT/1 PVQ schedule: for every (LM, band) the part size n, the
+    number of parts and the pulse count K.  n == 1 means "one raw sign bit"."""
+    nmax = 177
+    full = [[0] * (nmax + 2) for _ in range(nmax + 2)]
+    full[0][0] = 1
+    for n in range(1, nmax + 1):
+        for k in range(1, nmax + 1):
+            if min(n, k) <= 15:
+                full[n][k] = full[n - 1][k] + full[n][k - 1] + full[n - 1][k - 1]
+
+    def V(n, k):
+        return full[n][k] + full[n][k + 1]
+
+    kmax = dict(zip(PVQ_N, PVQ_KMAX))
+    sched = []
+    for lm in range(4):
+        row = []
+        for b in range(21):
+            nb = (E_BANDS[b + 1] - E_BANDS[b]) << lm
+            if nb == 1:
+                row.append((1, 1, 0))
+                continue
+            n, parts = nb, 1
+            budget = SYNTH_RATE * nb
+            while True:
+                if n not in kmax:
+                    n //= 2
+                    parts *= 2
+                    continue
+                if parts * math.log2(V(n, kmax[n])) < budget and (n // 2) in kmax and n % 2 == 0:
+                    n //= 2
+                    parts *= 2
+                    continue
+                break
+            k = 1
+            for kk in range(1, kmax[n] + 1):
+                if parts * math.log2(V(n, kk)) <= budget:
+                    k = kk
+            assert V(n, k) < 2 ** 32
+            row.append((n, parts, k))
+        sched.append(row)
+    return sched
+
+
+def fhex(x: float) -> str:
+    if x == 0.0:
+        return "-0.0f" if math.copysign(1, x) < 0 else "0.0f"
+    m, e = float.hex(x).split("p")
+    m = m.rstrip("0")
+    if m.endswith("."):
+        m += "0"
+    return f"{m}p{e}f"
+
+
+def emit(path, prefix, guard):
+    trig, win, tw = trig_table(), window_table(), twiddle_table()
+    rows, data = pvq_tables()
+    L = []
+    w = L.append
+    w("/* GENERATED by tools/gen_tables.py -- do not edit. CELT 48 kHz/960 standard mode constants,")
+    w(" * recomputed from their defining formulas (see the generator's docstring for the formulas")
+    w(" * and for the reference file:line each table is checked against). */")
+    w(f"#ifndef {guard}\n#define {guard}\n#include <stdint.h>\n")
+    w(f"#define {prefix}OVERLAP 120\n#define {prefix}NB_EBANDS 21\n#define {prefix}MAX_LM 3")
+    w(f"#define {prefix}MDCT_N 1920\n#define {prefix}COMB_MINPERIOD 15\n#define {prefix}COMB_MAXPERIOD 1024\n")
+
+    def arr(ctype, name, vals, fmt, per=8):
+        w(f"static const {ctype} {prefix}{name}[{len(vals)}] = {{")
+        for i in range(0, len(vals), per):
+            w("  " + ", ".join(fmt(v) for v in vals[i:i + per]) + ",")
+        w("};\n")
+
+    arr("float", "TRIG", trig, fhex, 6)
+    arr("float", "WINDOW", win, fhex, 6)
+    flat = [c for p in tw for c in p]
+    w("/* interleaved (re, im) */")
+    arr("float", "TWIDDLES", flat, fhex, 6)
+    for n in (480, 240, 120, 60):
+        arr("uint16_t", f"BITREV_{n}", bitrev_table(n), str, 16)
+        arr("uint8_t", f"FFT_FACTORS_{n}", FACTORS[n] + [0] * (16 - len(FACTORS[n])), str, 16)
+    arr("uint16_t", "PVQ_U_ROW", rows, str, 15)
+    arr("uint32_t", "PVQ_U_DATA", data, lambda v: f"{v}u", 8)
+    arr("uint8_t", "E_BANDS", E_BANDS, str, 22)
+    arr("uint8_t", "LOG_N", LOG_N, str, 21)
+    sched = synth_schedule()
+    w("/* SYNTH-CELT/1 PVQ schedule [LM][band] = {part size n, parts, pulses K}; n==1: one sign bit */")
+    w(f"static const uint8_t {prefix}SYNTH_SCHED[4][21][3] = {{")
+    for row in sched:
+        w("  {" + ", ".join("{%d,%d,%d}" % t for t in row) + "},")
+    w("};\n")
+    arr("float", "COMB_GAINS", [f32(g / 32768.0) for g in COMB_GAINS_Q15], fhex, 3)
+    w(f"#endif /* {guard} */")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write("\n".join(L) + "\n")
+
+
+if __name__ == "__main__":
+    emit(os.path.join(ROOT, "oracle", "oracle_tables.h"), "ORC_", "ORACLE_TABLES_H")
+    emit(os.path.join(ROOT, "opus-native_b200", "csrc", "opn_tables.h"), "OPN_", "OPN_TABLES_H")
+    print("tables written")
