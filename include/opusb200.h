@@ -1,0 +1,169 @@
+/* opusb200.h -- C ABI of the B200-native batched Opus decode engine (libopusb200.so).
+ *
+ * Drop-in boundary for the decode path of the Rust crate hasenbanck/opus-native.  The crate
+ * has no FFI of its own; each entry point below names the crate item it
+ * stands in for (paths relative to the crate root).  INTEGRATION.md shows the Rust
+ * `extern "C"` block and the safe wrapper a maintainer would add on the crate side.
+ *
+ * Rules: plain pointers and sizes only; no exceptions cross the ABI; the library keeps no
+ * caller pointer after a call returns (async device calls: after opn_batch_synchronize);
+ * one in-flight call per handle; handles are bound to one CUDA device.  There is no CPU
+ * fallback: every decode entry point fails with OPN_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef OPUSB200_H
+#define OPUSB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- errors: OpusError, src/error.rs:5-16 ------------------------------------------- */
+#define OPN_OK 0
+#define OPN_ERR_BAD_ARG (-1)              /* OpusError::BadArguments       */
+#define OPN_ERR_BUFFER_TOO_SMALL (-2)     /* OpusError::BufferToSmall      */
+#define OPN_ERR_INTERNAL (-3)             /* OpusError::InternalError      */
+#define OPN_ERR_INVALID_PACKET (-4)       /* OpusError::InvalidPacket      */
+#define OPN_ERR_FRAME_SIZE_TOO_SMALL (-5) /* OpusError::FrameSizeTooSmall  */
+#define OPN_ERR_UNIMPLEMENTED (-6)        /* reference: todo!()/unimplemented!() (SILK, hybrid, PLC bodies) */
+#define OPN_ERR_CUDA (-7)                 /* CUDA runtime failure or no usable device */
+const char *opn_strerror(int code);       /* Display for OpusError, src/error.rs:18-38 */
+const char *opn_last_cuda_error(void);    /* thread-local text of the last CUDA failure */
+int opn_device_count(void);
+
+/* ---- packet inspection: src/lib.rs:219-498 (host only) ------------------------------ */
+enum { OPN_BW_NARROW = 0, OPN_BW_MEDIUM = 1, OPN_BW_WIDE = 2, OPN_BW_SUPERWIDE = 3, OPN_BW_FULL = 4 };
+enum { OPN_MODE_SILK = 0, OPN_MODE_HYBRID = 1, OPN_MODE_CELT = 2 };
+int opn_packet_bandwidth(const uint8_t *packet);                             /* query_packet_bandwidth         lib.rs:219 */
+int opn_packet_channels(const uint8_t *packet);                              /* query_packet_channel_count     lib.rs:233 */
+int opn_packet_frame_count(const uint8_t *packet, size_t len);               /* query_packet_frame_count       lib.rs:250 */
+int opn_packet_samples_per_frame(const uint8_t *packet, int32_t fs_hz);      /* query_packet_samples_per_frame lib.rs:271 */
+int opn_packet_sample_count(const uint8_t *packet, size_t len, int32_t fs_hz); /* query_packet_sample_count    lib.rs:299 */
+int opn_packet_mode(const uint8_t *packet);                                  /* query_packet_codec_mode        lib.rs:317 */
+/* parse_packet, lib.rs:345-498.  frames may be NULL.  Returns the frame count or an error. */
+int opn_parse_packet(const uint8_t *packet, size_t len, int self_delimited, uint32_t frames[48],
+                     uint32_t sizes[48], uint32_t *payload_offset, uint32_t *packet_offset);
+
+/* ---- single-stream decoder: Decoder / DecoderConfiguration, src/decoder.rs:27-232 --- */
+typedef struct opn_decoder opn_decoder;
+/* Decoder::new (decoder.rs:61); fs_hz in {8000,12000,16000,24000,48000}, channels in {1,2}.
+ * Only 48000 Hz is implemented (the crate never computes its `downsample`, celt/decoder.rs:23). */
+int opn_decoder_create(int device, int32_t fs_hz, int32_t channels, int16_t gain_q8, opn_decoder **out);
+void opn_decoder_destroy(opn_decoder *dec);
+int opn_decoder_reset(opn_decoder *dec);                                     /* Decoder::reset decoder.rs:74 */
+/* Decoder::decode_float (decoder.rs:216-232).  packet == NULL means a lost packet.  Returns
+ * samples per channel (>= 0) or an error.  pcm holds frame_size*channels interleaved floats. */
+int opn_decode_float(opn_decoder *dec, const uint8_t *packet, size_t len, float *pcm,
+                     size_t frame_size, int decode_fec);
+/* Decoder::decode::<i16> (decoder.rs:148-193): soft clip then Sample::from_f32 (lib.rs:76-82).
+ * pcm_capacity is the slice length the Rust caller would pass (`samples.len()`). */
+int opn_decode_i16(opn_decoder *dec, const uint8_t *packet, size_t len, int16_t *pcm,
+                   size_t pcm_capacity, size_t frame_size, int decode_fec);
+int32_t opn_decoder_sampling_rate(const opn_decoder *dec);                   /* decoder.rs:80  */
+int32_t opn_decoder_channels(const opn_decoder *dec);                        /* decoder.rs:85  */
+int32_t opn_decoder_gain(const opn_decoder *dec);                            /* decoder.rs:90  */
+int32_t opn_decoder_bandwidth(const opn_decoder *dec);                       /* decoder.rs:95, -1 = None */
+int32_t opn_decoder_pitch(const opn_decoder *dec);                           /* decoder.rs:100, -1 = None */
+int32_t opn_decoder_last_packet_duration(const opn_decoder *dec);            /* decoder.rs:112, -1 = None */
+uint32_t opn_decoder_final_range(const opn_decoder *dec);                    /* decoder.rs:121 */
+
+/* ---- batch of independent streams (the entry point north_star adds) ------------------ */
+typedef struct opn_batch opn_batch;
+typedef struct {
+    int32_t fs_hz;        /* 48000 */
+    int32_t channels;     /* output channels, 1 or 2 */
+    int16_t gain_q8;      /* DecoderConfiguration::gain */
+    int16_t postfilter;   /* 1: run the comb post-filter epilogue (default), 0: IMDCT only */
+} opn_config;
+
+#define OPN_FLAG_DEVICE_PTRS 1u  /* arena/offsets/lens/pcm/results are device pointers; call is asynchronous */
+#define OPN_FLAG_NO_PCM_COPY 2u  /* leave PCM in the device ring only (read it with opn_batch_ring) */
+
+int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out);
+void opn_batch_destroy(opn_batch *b);
+int opn_batch_reset(opn_batch *b);
+/* One packet per stream (lens[i] == 0: lost).  Every stream i decodes packet
+ * arena[offsets[i] .. offsets[i]+lens[i]) into pcm[i*pcm_stride_floats ..] (interleaved).
+ * result_per_stream[i] = samples per channel or a negative error for that stream only: a bad
+ * packet never poisons its neighbours.  Semantics per stream = Decoder::decode_float. */
+int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *offsets,
+                           const uint32_t *lens, float *pcm, size_t pcm_stride_floats,
+                           size_t frame_size, int32_t *result_per_stream, uint32_t flags);
+int opn_batch_synchronize(opn_batch *b);
+/* Per-stream Decoder::final_range() of the last decoded frame (host buffer, n_streams words). */
+int opn_batch_final_ranges(opn_batch *b, uint32_t *out);
+/* Device-resident PCM ring (history + output): base pointer, samples per channel in the ring,
+ * and the per-stream write position after the last call (device pointer, n_streams words). */
+int opn_batch_ring(opn_batch *b, float **ring, uint32_t *ring_samples, uint32_t **ring_pos_dev);
+/* Counters for the measurement harness.  kernel_ms[k]/kernel_launches[k]: k = 0 symbol decode,
+ * 1 imdct+tdac+postfilter.  Timing must be enabled first (adds cudaEvents around launches). */
+int opn_batch_enable_timing(opn_batch *b, int on);
+int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[2], double kernel_ms[2], int reset);
+void *opn_batch_cuda_stream(opn_batch *b);
+
+/* ---- operator-level entry points (host pointers in/out; mirror the pub(crate) operators) */
+/* One record per range-coder call; replayed by one warp per packet.  RangeDecoder::*,
+ * src/range_coder/decoder.rs:50-355; decode_pulses, src/celt/pvc.rs:156-160. */
+enum { OPN_OP_UINT = 0, OPN_OP_BITS = 1, OPN_OP_BIT_LOGP = 2, OPN_OP_ICDF = 3, OPN_OP_LAPLACE = 4,
+       OPN_OP_BIT_VIA_DECODE = 5, OPN_OP_BIT_VIA_DECODE_BIN = 6, OPN_OP_PULSES = 7,
+       OPN_OP_SHRINK = 8, OPN_OP_TELL = 9 };
+typedef struct { uint32_t op, a, b; } opn_op;
+typedef struct { uint32_t value, tell_frac, rng; } opn_op_out;
+/* n_packets packets share one script.  out: [n_packets][n_ops]; y_out: [n_packets][y_stride]. */
+int opn_op_rangedec_script(int device, const uint8_t *arena, const uint32_t *offsets,
+                           const uint32_t *lens, uint32_t n_packets, const opn_op *ops,
+                           uint32_t n_ops, const uint8_t *icdf_pool, uint32_t icdf_pool_len,
+                           opn_op_out *out, int32_t *y_out, uint32_t y_stride);
+/* Mdct::backward, src/celt/mdct.rs:159-260, on n_rows independent rows with the standard
+ * window (mode::WINDOW) and overlap 120.  input row: (960>>shift)*stride floats; output row:
+ * out_stride floats whose first 60 hold the previous tail on entry; `blocks` (1 or `stride`)
+ * consecutive interleaved short blocks are transformed per row (blocks = stride = B). */
+int opn_op_imdct_tdac(int device, const float *input, size_t in_stride, float *output,
+                      size_t out_stride, uint32_t n_rows, int shift, int stride, int blocks);
+/* comb_filter_inplace / comb_filter, src/celt/comb_filter/mod.rs:59-193, one row per filter.
+ * params per row: {t0, t1, tapset0, tapset1}; gains per row: {g0, g1}. */
+int opn_op_comb_filter_inplace(int device, float *y, size_t row_stride, size_t y_offset, size_t n,
+                               uint32_t n_rows, const int32_t *params4, const float *gains2,
+                               size_t overlap);
+int opn_op_comb_filter(int device, float *y, const float *x, size_t row_stride, size_t offset,
+                       size_t n, uint32_t n_rows, const int32_t *params4, const float *gains2,
+                       size_t overlap);
+/* pcm_soft_clip, src/lib.rs:526-632: n_rows independent interleaved buffers. */
+int opn_op_pcm_soft_clip(int device, float *pcm, size_t row_stride, size_t row_len, int channels,
+                         uint32_t n_rows, float *softclip_mem /* [n_rows][channels] */);
+
+/* ---- SYNTH-CELT/1 frames: side information the symbol kernel reports ------ */
+typedef struct {
+    int32_t silence, postfilter, octave, period, gain_idx, tapset, transient, intra;
+    int32_t coarse[2][21];
+    int32_t fine[2][21];
+    uint32_t final_rng, tell_frac, n_pulses;
+} opn_synth_side;
+/* Symbol decode only (kernel 0): payloads (bytes after the TOC) -> side info, pulses, coefficients.
+ * y_out / coef_out: [n_packets][channels][120<<lm]; either may be NULL. */
+int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offsets,
+                         const uint32_t *lens, uint32_t n_packets, int lm, int channels,
+                         opn_synth_side *side_out, int32_t *y_out, float *coef_out);
+
+/* ---- synthetic stream generator (host; uses the library's own range ENCODER) --------- */
+/* Writes one packet of exactly pkt_bytes (TOC + SYNTH-CELT/1 payload) for (stream_id, frame).
+ * truth (optional) receives the values that were encoded.  Returns pkt_bytes or an error
+ * (OPN_ERR_BUFFER_TOO_SMALL when the frame does not fit). */
+int opn_synth_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels,
+                     uint32_t pkt_bytes, uint32_t transient_permille, uint8_t *out,
+                     opn_synth_side *truth);
+/* n_streams*n_frames packets, layout [frame][stream][pkt_bytes], generated on n_threads threads. */
+int opn_synth_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame,
+                   uint32_t n_frames, int lm, int channels, uint32_t pkt_bytes,
+                   uint32_t transient_permille, int n_threads, uint8_t *out);
+
+/* host range ENCODER, src/range_coder/encoder.rs (packet synthesis and round-trip tests) */
+int opn_enc_run_script(uint8_t *buf, uint32_t len, const opn_op *ops, const uint32_t *values,
+                       uint32_t n_ops, const uint8_t *icdf_pool, const int32_t *y_in,
+                       uint32_t *tell_frac_out, uint32_t *range_bytes, uint32_t *final_tell_frac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPUSB200_H */

@@ -1,0 +1,22 @@
+"""opus-native_b200 -- host-side Python mirror of the reference crate's decode interface
+(`Decoder`, `DecoderConfiguration`, `query_packet_*`, `parse_packet`; src/decoder.rs, src/lib.rs)
+on top of the C ABI of libopusb200.so (include/opusb200.h).
+
+Python is only plumbing here: it marshals numpy / torch buffers into the C ABI.  All decode work
+happens in the hand-written sm_100a kernels inside the shared library; if the library is missing
+or no B200-class device is usable every decode call raises -- there is no CPU fallback.
+"""
+from ._capi import (  # noqa: F401
+    OpusError, lib, library_path, build_library,
+    query_packet_bandwidth, query_packet_channel_count, query_packet_frame_count,
+    query_packet_samples_per_frame, query_packet_sample_count, query_packet_codec_mode, parse_packet,
+    DecoderConfiguration, Decoder, BatchDecoder,
+    op_rangedec_script, op_imdct_tdac, op_comb_filter_inplace, op_comb_filter, op_pcm_soft_clip,
+    op_synth_symbols, synth_packet, synth_fill, enc_run_script,
+    OP_DTYPE, OUT_DTYPE, SIDE_DTYPE,
+    OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN,
+    OP_PULSES, OP_SHRINK, OP_TELL, FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY,
+)
+from .sharding import shard_range  # noqa: F401
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,888 @@
+// host_runtime.cpp -- C-ABI entry points and the host runtime of libopusb200.
+//
+// Mirrors the reference's decode-path surface (src/decoder.rs): `opn_decoder` stands in for
+// `Decoder` (decode_native / decode_frame orchestration stays on the host, exactly as in the
+// crate: it is control flow over 1-3 header bytes), and `opn_batch` is the batch-of-streams
+// entry point: per-GPU context, per-stream state arenas in HBM (structure of arrays), pinned
+// staging and two kernels per step.  There is no CPU decode path in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "opn_internal.h"
+
+using namespace opn;
+
+namespace {
+
+thread_local std::string g_cuda_err;
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    g_cuda_err = buf;
+    return OPN_ERR_CUDA;
+}
+
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+int lm_of_frame(size_t nf)
+{
+    switch (nf) {
+    case 120: return 0;
+    case 240: return 1;
+    case 480: return 2;
+    case 960: return 3;
+    default: return -1;
+    }
+}
+
+int select_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n == 0 || device < 0 || device >= n) return cuda_fail(cudaErrorInvalidDevice, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) {
+        g_cuda_err = std::string("device '") + p.name + "' is not sm_100-class; libopusb200 ships sm_100a code only";
+        return OPN_ERR_CUDA;
+    }
+    CU(upload_tables(device));
+    return OPN_OK;
+}
+
+struct EventRing {
+    static constexpr int N = 512;
+    cudaEvent_t a[N], b[N];
+    int used = 0;
+    bool made = false;
+    double ms = 0.0;
+    uint64_t launches = 0;
+    int make()
+    {
+        if (made) return OPN_OK;
+        for (int i = 0; i < N; i++) {
+            CU(cudaEventCreate(&a[i]));
+            CU(cudaEventCreate(&b[i]));
+        }
+        made = true;
+        return OPN_OK;
+    }
+    int resolve()
+    {
+        for (int i = 0; i < used; i++) {
+            CU(cudaEventSynchronize(b[i]));
+            float t = 0;
+            CU(cudaEventElapsedTime(&t, a[i], b[i]));
+            ms += t;
+        }
+        used = 0;
+        return OPN_OK;
+    }
+    void destroy()
+    {
+        if (!made) return;
+        for (int i = 0; i < N; i++) {
+            cudaEventDestroy(a[i]);
+            cudaEventDestroy(b[i]);
+        }
+        made = false;
+    }
+};
+
+struct Item {
+    uint32_t stream, offset, len, dense_off;
+    int lm, wave;
+};
+
+}  // namespace
+
+struct opn_batch {
+    int device = 0;
+    uint32_t n = 0;
+    opn_config cfg{};
+    float gain = 1.0f;
+    cudaStream_t stream = nullptr;
+    // per-stream state (device, SoA)
+    float *d_carry = nullptr, *d_ring = nullptr, *d_coef = nullptr;
+    uint32_t *d_ring_pos = nullptr, *d_final = nullptr;
+    PfState *d_pf = nullptr;
+    opn_synth_side *d_side = nullptr;
+    int32_t *d_status = nullptr;
+    // host-path staging (device + pinned host)
+    uint8_t *d_arena = nullptr;
+    size_t arena_cap = 0;
+    uint32_t *d_items = nullptr, *h_items = nullptr;  // [4][cap]: offsets, lens, stream_idx, dense_off
+    size_t items_cap = 0;
+    float *d_dense = nullptr;
+    size_t dense_cap = 0;  // floats per stream
+    float *d_softclip = nullptr;
+    // host mirrors of DecoderInner fields (decoder.rs:236-258), per stream
+    std::vector<int32_t> last_nf, bandwidth, last_duration, have_mode;
+    // measurement
+    bool timing = false;
+    EventRing ev[2];
+    uint64_t launches[2] = {0, 0};
+};
+
+namespace {
+
+int batch_alloc_staging(opn_batch *b, size_t arena_bytes, size_t n_items, size_t dense_floats)
+{
+    if (arena_bytes > b->arena_cap) {
+        if (b->d_arena) cudaFree(b->d_arena);
+        b->arena_cap = arena_bytes + arena_bytes / 4 + 256;
+        CU(cudaMalloc(&b->d_arena, b->arena_cap));
+    }
+    if (n_items > b->items_cap) {
+        if (b->d_items) cudaFree(b->d_items);
+        if (b->h_items) cudaFreeHost(b->h_items);
+        b->items_cap = n_items + n_items / 4 + 64;
+        CU(cudaMalloc(&b->d_items, b->items_cap * 4 * sizeof(uint32_t)));
+        CU(cudaMallocHost(&b->h_items, b->items_cap * 4 * sizeof(uint32_t)));
+    }
+    if (dense_floats > b->dense_cap) {
+        if (b->d_dense) cudaFree(b->d_dense);
+        b->dense_cap = dense_floats;
+        CU(cudaMalloc(&b->d_dense, (size_t)b->n * b->dense_cap * sizeof(float)));
+    }
+    return OPN_OK;
+}
+
+int timed_launch(opn_batch *b, int kind, cudaError_t (*fn)(opn_batch *, const void *), const void *args)
+{
+    EventRing &r = b->ev[kind];
+    if (b->timing) {
+        if (r.used == EventRing::N) {
+            int rc = r.resolve();
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(r.a[r.used], b->stream));
+    }
+    CU(fn(b, args));
+    if (b->timing) {
+        CU(cudaEventRecord(r.b[r.used], b->stream));
+        r.used++;
+        r.launches++;
+    }
+    b->launches[kind]++;
+    return OPN_OK;
+}
+
+cudaError_t do_symbols(opn_batch *b, const void *a) { return launch_synth_symbols(*static_cast<const SymbolArgs *>(a), b->stream); }
+cudaError_t do_imdct(opn_batch *b, const void *a) { return launch_imdct_post(*static_cast<const ImdctArgs *>(a), b->stream); }
+
+// One bucket = items of equal frame size that may run concurrently.
+int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens,
+               const uint32_t *d_stream_idx, const uint32_t *d_dense_off, uint32_t n_items, int lm, int has_toc,
+               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result)
+{
+    SymbolArgs s{};
+    s.arena = d_arena;
+    s.offsets = d_offsets;
+    s.lens = d_lens;
+    s.stream_idx = d_stream_idx;
+    s.n_items = n_items;
+    s.lm = lm;
+    s.channels = b->cfg.channels;
+    s.has_toc = has_toc;
+    s.side = b->d_side;
+    s.status = b->d_status;
+    s.coef = b->d_coef;
+    s.y_out = nullptr;
+    s.pkt_cap = pkt_cap;
+    int rc = timed_launch(b, 0, do_symbols, &s);
+    if (rc) return rc;
+    ImdctArgs m{};
+    m.coef = b->d_coef;
+    m.side = b->d_side;
+    m.status = b->d_status;
+    m.stream_idx = d_stream_idx;
+    m.dense_off = d_dense_off;
+    m.n_items = n_items;
+    m.lm = lm;
+    m.channels = b->cfg.channels;
+    m.postfilter = b->cfg.postfilter;
+    m.carry = b->d_carry;
+    m.ring = b->d_ring;
+    m.ring_pos = b->d_ring_pos;
+    m.pf = b->d_pf;
+    m.dense = dense;
+    m.dense_stride = dense_stride;
+    m.gain = b->gain;
+    m.result = d_result;
+    m.final_range = b->d_final;
+    return timed_launch(b, 1, do_imdct, &m);
+}
+
+// PLC sizing of decode_native(None)/decode_frame(None), src/decoder.rs:427-441 and 467-513.
+void plc_frames(size_t frame_size, int32_t last_nf, std::vector<uint32_t> &out)
+{
+    size_t done = 0;
+    while (done < frame_size) {
+        size_t a = std::min(frame_size - done, (size_t)last_nf);
+        if (a > 960) a = 960;
+        else if (a < 960) {
+            if (a > 480) a = 480;
+            else if (a > 240 && a < 480) a = 240;
+        }
+        out.push_back((uint32_t)a);
+        done += a;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *opn_strerror(int code)
+{
+    switch (code) {
+    case OPN_OK: return "ok";
+    case OPN_ERR_BAD_ARG: return "bad arguments";
+    case OPN_ERR_BUFFER_TOO_SMALL: return "buffer is too small";
+    case OPN_ERR_INTERNAL: return "internal error";
+    case OPN_ERR_INVALID_PACKET: return "invalid packet";
+    case OPN_ERR_FRAME_SIZE_TOO_SMALL: return "the frame size is too small for the packet";
+    case OPN_ERR_UNIMPLEMENTED: return "not implemented (the reference crate stubs this path too)";
+    case OPN_ERR_CUDA: return "CUDA error";
+    default: return "unknown error";
+    }
+}
+
+const char *opn_last_cuda_error(void) { return g_cuda_err.c_str(); }
+
+int opn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------ batch
+int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out)
+{
+    if (!out || !cfg || n_streams == 0) return OPN_ERR_BAD_ARG;
+    if (cfg->channels < 1 || cfg->channels > 2) return OPN_ERR_BAD_ARG;
+    switch (cfg->fs_hz) {
+    case 48000: break;
+    case 8000: case 12000: case 16000: case 24000: return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:23 "TODO ... downsample"
+    default: return OPN_ERR_BAD_ARG;
+    }
+    int rc = select_device(device);
+    if (rc) return rc;
+    opn_batch *b = new (std::nothrow) opn_batch();
+    if (!b) return OPN_ERR_INTERNAL;
+    b->device = device;
+    b->n = n_streams;
+    b->cfg = *cfg;
+    b->gain = host_gain_from_q8(cfg->gain_q8);
+    const size_t n = n_streams, C = (size_t)cfg->channels;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_carry, n * C * 60 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_ring, n * C * RING_SAMPLES * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_coef, n * C * 960 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_ring_pos, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_side, n * sizeof(opn_synth_side));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_status, n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_softclip, n * 2 * sizeof(float));
+    if (e != cudaSuccess) {
+        opn_batch_destroy(b);
+        return cuda_fail(e, "opn_batch_create: allocation");
+    }
+    b->last_nf.assign(n, 120);  // DecoderInner::frame_size starts at fs/400 (decoder.rs:273)
+    b->bandwidth.assign(n, -1);
+    b->last_duration.assign(n, -1);
+    b->have_mode.assign(n, 0);
+    *out = b;
+    rc = opn_batch_reset(b);
+    if (rc) {
+        opn_batch_destroy(b);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+void opn_batch_destroy(opn_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    b->ev[0].destroy();
+    b->ev[1].destroy();
+    cudaFree(b->d_carry);
+    cudaFree(b->d_ring);
+    cudaFree(b->d_coef);
+    cudaFree(b->d_ring_pos);
+    cudaFree(b->d_final);
+    cudaFree(b->d_pf);
+    cudaFree(b->d_side);
+    cudaFree(b->d_status);
+    cudaFree(b->d_softclip);
+    cudaFree(b->d_arena);
+    cudaFree(b->d_items);
+    cudaFree(b->d_dense);
+    if (b->h_items) cudaFreeHost(b->h_items);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, for every stream
+{
+    if (!b) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n, C = (size_t)b->cfg.channels;
+    CU(cudaMemsetAsync(b->d_carry, 0, n * C * 60 * sizeof(float), b->stream));
+    CU(cudaMemsetAsync(b->d_ring, 0, n * C * RING_SAMPLES * sizeof(float), b->stream));
+    CU(cudaMemsetAsync(b->d_ring_pos, 0, n * sizeof(uint32_t), b->stream));
+    CU(cudaMemsetAsync(b->d_final, 0, n * sizeof(uint32_t), b->stream));
+    CU(cudaMemsetAsync(b->d_pf, 0, n * sizeof(PfState), b->stream));
+    CU(cudaMemsetAsync(b->d_side, 0, n * sizeof(opn_synth_side), b->stream));
+    CU(cudaMemsetAsync(b->d_status, 0, n * sizeof(int32_t), b->stream));
+    CU(cudaMemsetAsync(b->d_softclip, 0, n * 2 * sizeof(float), b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    std::fill(b->last_nf.begin(), b->last_nf.end(), 120);
+    std::fill(b->bandwidth.begin(), b->bandwidth.end(), -1);
+    std::fill(b->last_duration.begin(), b->last_duration.end(), -1);
+    std::fill(b->have_mode.begin(), b->have_mode.end(), 0);
+    return OPN_OK;
+}
+
+static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, float *pcm,
+                             size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags, int soft_clip)
+{
+    const uint32_t n = b->n;
+    const int C = b->cfg.channels;
+    std::vector<Item> items;
+    items.reserve(n);
+    std::vector<int32_t> res(n, 0);
+    std::vector<uint32_t> plc;
+    size_t arena_end = 0;
+    bool any_gap = false;  // some stream leaves part of its dense row unwritten
+    uint32_t max_len = 8;
+    int max_wave = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t len = lens[i];
+        if (len == 0) {  // lost packet: decode_native(None), decoder.rs:427-441
+            if (!b->have_mode[i]) {  // decoder.rs:478-487: nothing decoded yet -> zeros, state untouched
+                res[i] = (int32_t)frame_size;
+                any_gap = true;
+                b->last_duration[i] = (int32_t)frame_size;
+                continue;
+            }
+            plc.clear();
+            plc_frames(frame_size, b->last_nf[i], plc);
+            uint32_t at = 0;
+            int w = 0;
+            for (uint32_t a : plc) {
+                items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++});
+                at += a;
+            }
+            max_wave = std::max(max_wave, w);
+            res[i] = (int32_t)frame_size;
+            b->last_duration[i] = (int32_t)frame_size;
+            continue;
+        }
+        const uint8_t *pkt = arena + offsets[i];
+        // decode_native, decoder.rs:322-341
+        const int mode = opn_packet_mode(pkt);
+        const int pfs = opn_packet_samples_per_frame(pkt, 48000);
+        uint32_t fr[48], sz[48];
+        const int count = opn_parse_packet(pkt, len, 0, fr, sz, nullptr, nullptr);
+        if (count < 0) {
+            res[i] = count;
+            any_gap = true;
+            continue;
+        }
+        if ((size_t)count * (size_t)pfs > frame_size) {  // decoder.rs:388-390
+            res[i] = OPN_ERR_FRAME_SIZE_TOO_SMALL;
+            any_gap = true;
+            continue;
+        }
+        if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C) {
+            // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); mono<->stereo
+            // mapping lives in the stubbed CeltDecoder.
+            res[i] = OPN_ERR_UNIMPLEMENTED;
+            any_gap = true;
+            continue;
+        }
+        const int lm = lm_of_frame((size_t)pfs);
+        for (int w = 0; w < count; w++) {
+            items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), lm, w});
+            max_len = std::max(max_len, sz[w]);
+        }
+        max_wave = std::max(max_wave, count);
+        arena_end = std::max(arena_end, (size_t)offsets[i] + len);
+        if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
+        res[i] = count * pfs;
+        b->have_mode[i] = 1;
+        b->last_nf[i] = pfs;
+        b->bandwidth[i] = opn_packet_bandwidth(pkt);
+        b->last_duration[i] = count * pfs;
+    }
+    const size_t dense_stride = (frame_size * (size_t)C + 3) & ~(size_t)3;
+    int rc = batch_alloc_staging(b, arena_end, items.size(), dense_stride);
+    if (rc) return rc;
+    const bool want_pcm = pcm != nullptr && !(flags & OPN_FLAG_NO_PCM_COPY);
+    if (want_pcm && any_gap) CU(cudaMemsetAsync(b->d_dense, 0, (size_t)n * b->dense_cap * sizeof(float), b->stream));
+    if (!items.empty()) {
+        // order: wave-major, then frame size, so each (wave, lm) bucket is contiguous
+        std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
+            return x.wave != y.wave ? x.wave < y.wave : x.lm < y.lm;
+        });
+        const size_t cap = b->items_cap;
+        for (size_t k = 0; k < items.size(); k++) {
+            b->h_items[k] = items[k].offset;
+            b->h_items[cap + k] = items[k].len;
+            b->h_items[2 * cap + k] = items[k].stream;
+            b->h_items[3 * cap + k] = items[k].dense_off;
+        }
+        if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream));
+        for (int q = 0; q < 4; q++)
+            CU(cudaMemcpyAsync(b->d_items + q * cap, b->h_items + q * cap, items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               b->stream));
+        const uint32_t pkt_cap = (max_len + 15u) & ~15u;
+        size_t k0 = 0;
+        while (k0 < items.size()) {
+            size_t k1 = k0;
+            while (k1 < items.size() && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
+            rc = run_bucket(b, b->d_arena, b->d_items + k0, b->d_items + cap + k0, b->d_items + 2 * cap + k0,
+                            b->d_items + 3 * cap + k0, (uint32_t)(k1 - k0), items[k0].lm, 0, pkt_cap,
+                            want_pcm ? b->d_dense : nullptr, b->dense_cap, nullptr);
+            if (rc) return rc;
+            k0 = k1;
+        }
+    }
+    if (want_pcm) {
+        if (soft_clip) {
+            // decode_native(soft_clip=true), decoder.rs:413-419.  Reference quirk kept: the slice handed to
+            // pcm_soft_clip is samples[..sample_count] (per-channel count, not x channels).
+            // Only used by the single-stream decoder, where every row has the same sample_count.
+            CU(launch_op_soft_clip(b->d_dense, b->dense_cap, (size_t)std::max(res[0], 0), C, n, b->d_softclip, b->stream));
+        }
+        CU(cudaMemcpy2DAsync(pcm, pcm_stride * sizeof(float), b->d_dense, b->dense_cap * sizeof(float),
+                             frame_size * (size_t)C * sizeof(float), n, cudaMemcpyDeviceToHost, b->stream));
+    }
+    if (!soft_clip) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
+    CU(cudaStreamSynchronize(b->stream));
+    if (results) std::memcpy(results, res.data(), n * sizeof(int32_t));
+    return OPN_OK;
+}
+
+int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, float *pcm,
+                           size_t pcm_stride_floats, size_t frame_size, int32_t *result_per_stream, uint32_t flags)
+{
+    if (!b || !offsets || !lens) return OPN_ERR_BAD_ARG;
+    if (frame_size == 0 || frame_size % 120 != 0) return OPN_ERR_BAD_ARG;  // decoder.rs:316-320
+    const int C = b->cfg.channels;
+    CU(cudaSetDevice(b->device));
+    if (!(flags & OPN_FLAG_DEVICE_PTRS)) {
+        if (!arena) return OPN_ERR_BAD_ARG;
+        if (pcm && pcm_stride_floats < frame_size * (size_t)C) return OPN_ERR_BUFFER_TOO_SMALL;
+        return batch_decode_host(b, arena, offsets, lens, pcm, pcm_stride_floats, frame_size, result_per_stream, flags, 0);
+    }
+    // Device-resident step: one single-frame CELT packet of exactly frame_size per stream; the TOC
+    // is validated on the device and reported per stream.  Asynchronous on the batch stream.
+    const int lm = lm_of_frame(frame_size);
+    if (lm < 0 || !arena) return OPN_ERR_BAD_ARG;
+    float *dense = (flags & OPN_FLAG_NO_PCM_COPY) ? nullptr : pcm;
+    if (dense && (pcm_stride_floats < frame_size * (size_t)C || (pcm_stride_floats & 3) ||
+                  (reinterpret_cast<uintptr_t>(dense) & 15)))
+        return OPN_ERR_BAD_ARG;
+    return run_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, lm, 1, 1280u, dense, pcm_stride_floats, result_per_stream);
+}
+
+int opn_batch_synchronize(opn_batch *b)
+{
+    if (!b) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    return OPN_OK;
+}
+
+int opn_batch_final_ranges(opn_batch *b, uint32_t *out)
+{
+    if (!b || !out) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(out, b->d_final, b->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return OPN_OK;
+}
+
+int opn_batch_ring(opn_batch *b, float **ring, uint32_t *ring_samples, uint32_t **ring_pos_dev)
+{
+    if (!b) return OPN_ERR_BAD_ARG;
+    if (ring) *ring = b->d_ring;
+    if (ring_samples) *ring_samples = RING_SAMPLES;
+    if (ring_pos_dev) *ring_pos_dev = b->d_ring_pos;
+    return OPN_OK;
+}
+
+int opn_batch_enable_timing(opn_batch *b, int on)
+{
+    if (!b) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    if (on) {
+        int rc = b->ev[0].make();
+        if (!rc) rc = b->ev[1].make();
+        if (rc) return rc;
+    }
+    b->timing = on != 0;
+    return OPN_OK;
+}
+
+int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[2], double kernel_ms[2], int reset)
+{
+    if (!b) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    for (int k = 0; k < 2; k++) {
+        int rc = b->ev[k].resolve();
+        if (rc) return rc;
+        if (kernel_launches) kernel_launches[k] = b->launches[k];
+        if (kernel_ms) kernel_ms[k] = b->ev[k].ms;
+        if (reset) {
+            b->launches[k] = 0;
+            b->ev[k].ms = 0.0;
+            b->ev[k].launches = 0;
+        }
+    }
+    return OPN_OK;
+}
+
+void *opn_batch_cuda_stream(opn_batch *b) { return b ? (void *)b->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------ decoder
+}  // extern "C"
+
+struct opn_decoder {
+    opn_batch *batch = nullptr;  // a batch of one stream
+    int32_t fs = 48000, channels = 2;
+    int16_t gain_q8 = 0;
+    uint32_t final_range = 0;
+    float *h_pcm = nullptr;  // pinned staging
+    size_t h_cap = 0;
+};
+
+extern "C" {
+
+int opn_decoder_create(int device, int32_t fs_hz, int32_t channels, int16_t gain_q8, opn_decoder **out)
+{
+    if (!out) return OPN_ERR_BAD_ARG;
+    opn_config cfg{fs_hz, channels, gain_q8, 1};
+    opn_batch *b = nullptr;
+    int rc = opn_batch_create(device, 1, &cfg, &b);
+    if (rc) return rc;
+    opn_decoder *d = new (std::nothrow) opn_decoder();
+    if (!d) {
+        opn_batch_destroy(b);
+        return OPN_ERR_INTERNAL;
+    }
+    d->batch = b;
+    d->fs = fs_hz;
+    d->channels = channels;
+    d->gain_q8 = gain_q8;
+    *out = d;
+    return OPN_OK;
+}
+
+void opn_decoder_destroy(opn_decoder *d)
+{
+    if (!d) return;
+    if (d->h_pcm) cudaFreeHost(d->h_pcm);
+    opn_batch_destroy(d->batch);
+    delete d;
+}
+
+int opn_decoder_reset(opn_decoder *d)
+{
+    if (!d) return OPN_ERR_BAD_ARG;
+    d->final_range = 0;
+    return opn_batch_reset(d->batch);
+}
+
+static int decoder_decode(opn_decoder *d, const uint8_t *packet, size_t len, float *pcm, size_t frame_size, int decode_fec,
+                          int soft_clip)
+{
+    if (!d || !pcm) return OPN_ERR_BAD_ARG;
+    if (frame_size == 0 || frame_size % (size_t)(d->fs / 400) != 0) return OPN_ERR_BAD_ARG;  // decoder.rs:316-320
+    if (packet && len == 0) return OPN_ERR_BAD_ARG;                                           // decoder.rs:323-325
+    if (packet && len > 0xFFFFFFFFull) return OPN_ERR_BAD_ARG;
+    uint32_t off = 0, l = packet ? (uint32_t)len : 0u;
+    if (packet && decode_fec) {
+        // decoder.rs:343-350: FEC only exists in SILK frames; for a CELT-only packet (or decoder) the
+        // reference conceals the whole gap instead.  SILK/hybrid FEC needs the stubbed SilkDecoder.
+        if (opn_packet_mode(packet) != OPN_MODE_CELT && d->batch->have_mode[0] == 0) return OPN_ERR_UNIMPLEMENTED;
+        l = 0;
+    }
+    static const uint8_t dummy = 0;
+    int32_t res = 0;
+    int rc = batch_decode_host(d->batch, packet ? packet : &dummy, &off, &l, pcm, frame_size * (size_t)d->channels, frame_size,
+                               &res, 0, soft_clip);
+    if (rc) return rc;
+    if (res >= 0) {
+        uint32_t fr = 0;
+        rc = opn_batch_final_ranges(d->batch, &fr);
+        if (rc) return rc;
+        d->final_range = l ? fr : 0u;  // decoder.rs:799-803
+    }
+    return res;
+}
+
+int opn_decode_float(opn_decoder *d, const uint8_t *packet, size_t len, float *pcm, size_t frame_size, int decode_fec)
+{
+    return decoder_decode(d, packet, len, pcm, frame_size, decode_fec, 0);
+}
+
+int opn_decode_i16(opn_decoder *d, const uint8_t *packet, size_t len, int16_t *pcm, size_t pcm_capacity, size_t frame_size,
+                   int decode_fec)
+{
+    if (!d || !pcm) return OPN_ERR_BAD_ARG;
+    // Decoder::decode<S>, decoder.rs:148-193
+    if (!decode_fec && packet) {
+        if (len == 0) return OPN_ERR_BAD_ARG;
+        const int sc = opn_packet_sample_count(packet, len, d->fs);
+        if (sc < 0) return sc;
+        if (sc == 0) return OPN_ERR_INVALID_PACKET;
+        frame_size = std::min(frame_size, (size_t)sc);
+    }
+    const size_t need = frame_size * (size_t)d->channels;
+    if (need > d->h_cap) {
+        if (d->h_pcm) cudaFreeHost(d->h_pcm);
+        d->h_pcm = nullptr;
+        d->h_cap = 0;
+        CU(cudaMallocHost(&d->h_pcm, need * sizeof(float)));
+        d->h_cap = need;
+    }
+    const int n = decoder_decode(d, packet, len, d->h_pcm, frame_size, decode_fec, 1);
+    if (n <= 0) return n;
+    if ((size_t)n > pcm_capacity) return OPN_ERR_BUFFER_TOO_SMALL;  // decoder.rs:181 (per-channel count vs slice length)
+    if ((size_t)n * (size_t)d->channels > pcm_capacity) return OPN_ERR_BUFFER_TOO_SMALL;  // Rust would panic on the index
+    for (size_t i = 0; i < (size_t)n * (size_t)d->channels; i++) {
+        // Sample::from_f32 for i16, lib.rs:76-82 (format conversion of the already decoded PCM)
+        float f = d->h_pcm[i] * 32768.0f;
+        f = f < -32768.0f ? -32768.0f : (f > 32767.0f ? 32767.0f : f);
+        pcm[i] = (f != f) ? (int16_t)0 : (int16_t)f;
+    }
+    return n;
+}
+
+int32_t opn_decoder_sampling_rate(const opn_decoder *d) { return d ? d->fs : 0; }
+int32_t opn_decoder_channels(const opn_decoder *d) { return d ? d->channels : 0; }
+int32_t opn_decoder_gain(const opn_decoder *d) { return d ? d->gain_q8 : 0; }
+int32_t opn_decoder_bandwidth(const opn_decoder *d) { return d ? d->batch->bandwidth[0] : -1; }
+int32_t opn_decoder_last_packet_duration(const opn_decoder *d) { return d ? d->batch->last_duration[0] : -1; }
+uint32_t opn_decoder_final_range(const opn_decoder *d) { return d ? d->final_range : 0u; }
+
+int32_t opn_decoder_pitch(const opn_decoder *d)
+{
+    // Decoder::pitch (decoder.rs:100-109) forwards to CeltDecoder::pitch, a todo!() in the reference;
+    // libopus reports the post-filter period of the last frame, so do that.
+    if (!d || !d->batch->have_mode[0]) return -1;
+    PfState pf{};
+    if (cudaSetDevice(d->batch->device) != cudaSuccess) return -1;
+    if (cudaMemcpy(&pf, d->batch->d_pf, sizeof(pf), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return pf.period;
+}
+
+// ------------------------------------------------------------------------------------ operators
+}  // extern "C"
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+}  // namespace
+extern "C" {
+
+int opn_op_rangedec_script(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                           const opn_op *ops, uint32_t n_ops, const uint8_t *icdf_pool, uint32_t icdf_pool_len, opn_op_out *out,
+                           int32_t *y_out, uint32_t y_stride)
+{
+    if (!arena || !offsets || !lens || !ops || !out || n_packets == 0) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    size_t arena_end = 0;
+    uint32_t max_len = 8;
+    for (uint32_t i = 0; i < n_packets; i++) {
+        arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
+        max_len = std::max(max_len, lens[i]);
+    }
+    const uint32_t pkt_cap = std::min((max_len + 15u) & ~15u, 4096u);  // larger packets are read from global memory
+    DevBuf dA, dO, dL, dOps, dPool, dOut, dY;
+    CU(dA.alloc(arena_end));
+    CU(dO.alloc(n_packets * 4));
+    CU(dL.alloc(n_packets * 4));
+    CU(dOps.alloc((size_t)n_ops * sizeof(opn_op)));
+    CU(dPool.alloc(icdf_pool_len));
+    CU(dOut.alloc((size_t)n_packets * n_ops * sizeof(opn_op_out)));
+    CU(dY.alloc((size_t)n_packets * y_stride * 4));
+    CU(cudaMemcpy(dA.p, arena, arena_end, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dO.p, offsets, n_packets * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dL.p, lens, n_packets * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dOps.p, ops, (size_t)n_ops * sizeof(opn_op), cudaMemcpyHostToDevice));
+    if (icdf_pool && icdf_pool_len) CU(cudaMemcpy(dPool.p, icdf_pool, icdf_pool_len, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dY.p, 0, (size_t)n_packets * y_stride * 4 + (y_stride ? 0 : 16)));
+    CU(launch_rangedec_script(dA.as<uint8_t>(), dO.as<uint32_t>(), dL.as<uint32_t>(), n_packets, dOps.as<opn_op>(), n_ops,
+                              dPool.as<uint8_t>(), dOut.as<opn_op_out>(), y_out ? dY.as<int32_t>() : nullptr, y_stride, pkt_cap,
+                              nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, dOut.p, (size_t)n_packets * n_ops * sizeof(opn_op_out), cudaMemcpyDeviceToHost));
+    if (y_out && y_stride) CU(cudaMemcpy(y_out, dY.p, (size_t)n_packets * y_stride * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+int opn_op_imdct_tdac(int device, const float *input, size_t in_stride, float *output, size_t out_stride, uint32_t n_rows,
+                      int shift, int stride, int blocks)
+{
+    if (!input || !output || n_rows == 0 || shift < 0 || shift > 3 || blocks < 1 || stride != blocks) return OPN_ERR_BAD_ARG;
+    const size_t n2 = 960u >> shift;
+    if (n2 * (size_t)blocks > 960 || in_stride < n2 * (size_t)blocks || out_stride < n2 * (size_t)blocks + 60) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    DevBuf dI, dO;
+    CU(dI.alloc((size_t)n_rows * in_stride * 4));
+    CU(dO.alloc((size_t)n_rows * out_stride * 4));
+    CU(cudaMemcpy(dI.p, input, (size_t)n_rows * in_stride * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dO.p, output, (size_t)n_rows * out_stride * 4, cudaMemcpyHostToDevice));
+    CU(launch_op_imdct(dI.as<float>(), in_stride, dO.as<float>(), out_stride, n_rows, shift, blocks, nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(output, dO.p, (size_t)n_rows * out_stride * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+static int comb_args_ok(size_t offset, size_t n, uint32_t n_rows, const int32_t *p, const float *g, size_t row_stride,
+                        size_t overlap)
+{
+    if (!p || !g || n_rows == 0 || offset + n > row_stride || overlap > 120 || overlap > n) return 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const int32_t t0 = std::max(p[4 * r], 15), t1 = std::max(p[4 * r + 1], 15);
+        if (t0 > 1022 || t1 > 1022 || p[4 * r + 2] < 0 || p[4 * r + 2] > 2 || p[4 * r + 3] < 0 || p[4 * r + 3] > 2) return 0;
+        if ((size_t)std::max(t0, t1) + 2 > offset) return 0;  // history must exist (the Rust slice would panic)
+    }
+    return 1;
+}
+
+int opn_op_comb_filter_inplace(int device, float *y, size_t row_stride, size_t y_offset, size_t n, uint32_t n_rows,
+                               const int32_t *params4, const float *gains2, size_t overlap)
+{
+    if (!y || !comb_args_ok(y_offset, n, n_rows, params4, gains2, row_stride, overlap)) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    DevBuf dY, dP, dG;
+    CU(dY.alloc((size_t)n_rows * row_stride * 4));
+    CU(dP.alloc((size_t)n_rows * 16));
+    CU(dG.alloc((size_t)n_rows * 8));
+    CU(cudaMemcpy(dY.p, y, (size_t)n_rows * row_stride * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dP.p, params4, (size_t)n_rows * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dG.p, gains2, (size_t)n_rows * 8, cudaMemcpyHostToDevice));
+    CU(launch_op_comb_inplace(dY.as<float>(), row_stride, (int)y_offset, (int)n, n_rows, dP.as<int32_t>(), dG.as<float>(),
+                              (int)overlap, nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(y, dY.p, (size_t)n_rows * row_stride * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+int opn_op_comb_filter(int device, float *y, const float *x, size_t row_stride, size_t offset, size_t n, uint32_t n_rows,
+                       const int32_t *params4, const float *gains2, size_t overlap)
+{
+    if (!y || !x || !comb_args_ok(offset, n, n_rows, params4, gains2, row_stride, overlap)) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    DevBuf dY, dX, dP, dG;
+    CU(dY.alloc((size_t)n_rows * row_stride * 4));
+    CU(dX.alloc((size_t)n_rows * row_stride * 4));
+    CU(dP.alloc((size_t)n_rows * 16));
+    CU(dG.alloc((size_t)n_rows * 8));
+    CU(cudaMemcpy(dY.p, y, (size_t)n_rows * row_stride * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dX.p, x, (size_t)n_rows * row_stride * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dP.p, params4, (size_t)n_rows * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dG.p, gains2, (size_t)n_rows * 8, cudaMemcpyHostToDevice));
+    CU(launch_op_comb(dY.as<float>(), dX.as<float>(), row_stride, (int)offset, (int)n, n_rows, dP.as<int32_t>(), dG.as<float>(),
+                      (int)overlap, nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(y, dY.p, (size_t)n_rows * row_stride * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+int opn_op_pcm_soft_clip(int device, float *pcm, size_t row_stride, size_t row_len, int channels, uint32_t n_rows,
+                         float *softclip_mem)
+{
+    if (!pcm || !softclip_mem || n_rows == 0 || channels < 1 || row_len > row_stride) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    DevBuf dP, dM;
+    CU(dP.alloc((size_t)n_rows * row_stride * 4));
+    CU(dM.alloc((size_t)n_rows * channels * 4));
+    CU(cudaMemcpy(dP.p, pcm, (size_t)n_rows * row_stride * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dM.p, softclip_mem, (size_t)n_rows * channels * 4, cudaMemcpyHostToDevice));
+    CU(launch_op_soft_clip(dP.as<float>(), row_stride, row_len, channels, n_rows, dM.as<float>(), nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(pcm, dP.p, (size_t)n_rows * row_stride * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(softclip_mem, dM.p, (size_t)n_rows * channels * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                         int lm, int channels, opn_synth_side *side_out, int32_t *y_out, float *coef_out)
+{
+    if (!arena || !offsets || !lens || n_packets == 0 || lm < 0 || lm > 3 || channels < 1 || channels > 2) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    size_t arena_end = 0;
+    uint32_t max_len = 8;
+    for (uint32_t i = 0; i < n_packets; i++) {
+        arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
+        max_len = std::max(max_len, lens[i]);
+    }
+    const size_t row = (size_t)channels * (120u << lm);
+    DevBuf dA, dO, dL, dS, dSt, dY, dC;
+    CU(dA.alloc(arena_end));
+    CU(dO.alloc(n_packets * 4));
+    CU(dL.alloc(n_packets * 4));
+    CU(dS.alloc((size_t)n_packets * sizeof(opn_synth_side)));
+    CU(dSt.alloc(n_packets * 4));
+    CU(dY.alloc((size_t)n_packets * row * 4));
+    CU(dC.alloc((size_t)n_packets * row * 4));
+    CU(cudaMemcpy(dA.p, arena, arena_end, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dO.p, offsets, n_packets * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dL.p, lens, n_packets * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dS.p, 0, (size_t)n_packets * sizeof(opn_synth_side)));
+    SymbolArgs s{};
+    s.arena = dA.as<uint8_t>();
+    s.offsets = dO.as<uint32_t>();
+    s.lens = dL.as<uint32_t>();
+    s.n_items = n_packets;
+    s.lm = lm;
+    s.channels = channels;
+    s.has_toc = 0;
+    s.side = dS.as<opn_synth_side>();
+    s.status = dSt.as<int32_t>();
+    s.coef = dC.as<float>();
+    s.y_out = dY.as<int32_t>();
+    s.pkt_cap = (max_len + 15u) & ~15u;
+    CU(launch_synth_symbols(s, nullptr));
+    CU(cudaDeviceSynchronize());
+    if (side_out) CU(cudaMemcpy(side_out, dS.p, (size_t)n_packets * sizeof(opn_synth_side), cudaMemcpyDeviceToHost));
+    if (y_out) CU(cudaMemcpy(y_out, dY.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
+    if (coef_out) CU(cudaMemcpy(coef_out, dC.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// opn_internal.h -- declarations shared by the CUDA translation unit and the C++ host runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/opusb200.h"
+
+namespace opn {
+
+constexpr int SYM_WARPS_PER_CTA = 4;
+constexpr int IM_TPC = 128;         // kernel 1: threads per channel
+constexpr int HIST_CAP = 1024;      // comb history window in shared memory (T + 2 <= 1024)
+constexpr int RING_SAMPLES = 2880;  // per-channel PCM ring: 3 x 960 = 6 x 480 = 12 x 240 = 24 x 120
+constexpr int32_t ITEM_OK = 0, ITEM_LOST = 1;  // kernel-0 status; negative = OPN_ERR_* (state untouched)
+
+struct PfState {  // post-filter parameters of the previous frame
+    int32_t period, tapset;
+    float gain;
+    int32_t pad;
+};
+
+struct SymbolArgs {
+    const uint8_t *arena;
+    const uint32_t *offsets;     // [n_items] byte offset of the packet (or of the payload if !has_toc)
+    const uint32_t *lens;        // [n_items] bytes, 0 = lost
+    const uint32_t *stream_idx;  // [n_items] or nullptr (item k = stream k)
+    uint32_t n_items;
+    int lm, channels, has_toc;
+    opn_synth_side *side;        // [n_streams]
+    int32_t *status;             // [n_streams]
+    float *coef;                 // [n_streams][channels][120<<lm] or nullptr
+    int32_t *y_out;              // same shape or nullptr
+    uint32_t pkt_cap;            // bytes of shared memory per warp for the packet
+};
+
+struct ImdctArgs {
+    const float *coef;            // [n_streams][C][120<<lm]  (kernel 0 output)
+    const opn_synth_side *side;   // [n_streams]
+    const int32_t *status;        // [n_streams]  (kernel 0 output)
+    const uint32_t *stream_idx;   // [n_items] or nullptr
+    uint32_t n_items;
+    int lm, channels, postfilter;
+    float *carry;                 // [n_streams][C][60]
+    float *ring;                  // [n_streams][RING_SAMPLES][C]
+    uint32_t *ring_pos;           // [n_streams]
+    PfState *pf;                  // [n_streams]
+    float *dense;                 // [n_streams] rows of dense_stride floats, or nullptr
+    size_t dense_stride;
+    const uint32_t *dense_off;    // [n_items] float offset inside the row (frame w of a packet: w*nf*C) or nullptr
+    float gain;                   // DecoderConfiguration::gain as a linear factor (decoder.rs:790-797); 1 = none
+    int32_t *result;              // [n_streams] samples per channel or OPN_ERR_*; nullptr to skip
+    uint32_t *final_range;        // [n_streams]
+};
+
+// ---- launchers (opn_kernels.cu).  All return a cudaError_t and never synchronise.
+cudaError_t upload_tables(int device);  // idempotent per device
+cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                                   const opn_op *ops, uint32_t n_ops, const uint8_t *icdf_pool, opn_op_out *out,
+                                   int32_t *y_out, uint32_t y_stride, uint32_t pkt_cap, cudaStream_t st);
+cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st);
+cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st);
+cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
+                            int nblk, cudaStream_t st);
+cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, int n, uint32_t n_rows, const int32_t *params4,
+                                   const float *gains2, int overlap, cudaStream_t st);
+cudaError_t launch_op_comb(float *y, const float *x, size_t row_stride, int offset, int n, uint32_t n_rows,
+                           const int32_t *params4, const float *gains2, int overlap, cudaStream_t st);
+cudaError_t launch_op_soft_clip(float *pcm, size_t row_stride, size_t row_len, int channels, uint32_t n_rows, float *mem,
+                                cudaStream_t st);
+
+// ---- host-side pieces (host_*.cpp)
+float host_gain_from_q8(int16_t gain_q8);  // decoder.rs:790-791
+
+}  // namespace opn

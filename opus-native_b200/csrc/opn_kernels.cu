@@ -1,0 +1,121 @@
+// opn_kernels.cu -- the single CUDA translation unit of libopusb200 (sm_100a, -fmad=false).
+#include <mutex>
+
+#include "imdct.cuh"
+#include "opn_tables.h"
+#include "softclip.cuh"
+#include "symbols.cuh"
+
+namespace opn {
+
+
+static std::mutex g_tab_mutex;
+static bool g_tab_done[64];
+
+cudaError_t upload_tables(int device)
+{
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (g_tab_done[device]) return cudaSuccess;
+    static DevTables h;  // ~19 KB: keep it off the stack
+    for (int i = 0; i < 1800; i++) h.trig[i] = OPN_TRIG[i];
+    for (int i = 0; i < 120; i++) {
+        h.window[i] = OPN_WINDOW[i];
+        h.window_sq[i] = OPN_WINDOW[i] * OPN_WINDOW[i];  // host f32 product, single rounding
+    }
+    for (int i = 0; i < 480; i++) h.twiddles[i] = make_float2(OPN_TWIDDLES[2 * i], OPN_TWIDDLES[2 * i + 1]);
+    for (int i = 0; i < 480; i++) h.bitrev[0][i] = OPN_BITREV_480[i];
+    for (int i = 0; i < 240; i++) h.bitrev[1][i] = OPN_BITREV_240[i];
+    for (int i = 0; i < 120; i++) h.bitrev[2][i] = OPN_BITREV_120[i];
+    for (int i = 0; i < 60; i++) h.bitrev[3][i] = OPN_BITREV_60[i];
+    for (int i = 0; i < 1272; i++) h.pvq_u_data[i] = OPN_PVQ_U_DATA[i];
+    for (int i = 0; i < 15; i++) h.pvq_u_row[i] = OPN_PVQ_U_ROW[i];
+    for (int i = 0; i < 22; i++) h.e_bands[i] = OPN_E_BANDS[i];
+    for (int l = 0; l < 4; l++)
+        for (int b = 0; b < 21; b++)
+            for (int k = 0; k < 3; k++) h.synth_sched[l][b][k] = OPN_SYNTH_SCHED[l][b][k];
+    h.tapset_icdf[0] = 2; h.tapset_icdf[1] = 1; h.tapset_icdf[2] = 0; h.tapset_icdf[3] = 0;
+    for (int i = 0; i < 9; i++) h.comb_gains[i] = OPN_COMB_GAINS[i];
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
+    if (e != cudaSuccess) return e;
+    // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
+    e = cudaFuncSetAttribute(k_rangedec_script, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_synth_symbols, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    g_tab_done[device] = true;
+    return cudaSuccess;
+}
+
+static size_t symbols_smem(uint32_t pkt_cap)
+{
+    return PVQ_TABLE_WORDS * 4 + 32 + (size_t)SYM_WARPS_PER_CTA * Y_STAGE * 4 + (size_t)SYM_WARPS_PER_CTA * pkt_cap;
+}
+
+cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                                   const opn_op *ops, uint32_t n_ops, const uint8_t *icdf_pool, opn_op_out *out,
+                                   int32_t *y_out, uint32_t y_stride, uint32_t pkt_cap, cudaStream_t st)
+{
+    if (n_packets == 0) return cudaSuccess;
+    const uint32_t grid = (n_packets + SYM_WARPS_PER_CTA - 1) / SYM_WARPS_PER_CTA;
+    k_rangedec_script<<<grid, SYM_WARPS_PER_CTA * 32, symbols_smem(pkt_cap), st>>>(arena, offsets, lens, n_packets, ops, n_ops,
+                                                                                 icdf_pool, out, y_out, y_stride, pkt_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    const uint32_t grid = (a.n_items + SYM_WARPS_PER_CTA - 1) / SYM_WARPS_PER_CTA;
+    k_synth_symbols<<<grid, SYM_WARPS_PER_CTA * 32, symbols_smem(a.pkt_cap), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    const size_t smem = (size_t)a.channels * (SY_FLOATS * 4 + SF_CPLX * 8);
+    k_imdct_post<<<a.n_items, IM_TPC * a.channels, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
+                            int nblk, cudaStream_t st)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const size_t smem = (960 + 1024) * 4 + 480 * 8;
+    k_op_imdct<<<n_rows, IM_TPC, smem, st>>>(in, in_stride, out, out_stride, shift, nblk);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, int n, uint32_t n_rows, const int32_t *params4,
+                                   const float *gains2, int overlap, cudaStream_t st)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const int hist = y_offset < HIST_CAP + 2 ? y_offset : HIST_CAP + 2;
+    const size_t smem = (size_t)(hist + n) * 4;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    k_op_comb_inplace<<<n_rows, IM_TPC, smem, st>>>(y, row_stride, y_offset, n, params4, gains2, overlap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_op_comb(float *y, const float *x, size_t row_stride, int offset, int n, uint32_t n_rows,
+                           const int32_t *params4, const float *gains2, int overlap, cudaStream_t st)
+{
+    if (n_rows == 0) return cudaSuccess;
+    k_op_comb<<<n_rows, IM_TPC, 0, st>>>(y, x, row_stride, offset, n, params4, gains2, overlap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_op_soft_clip(float *pcm, size_t row_stride, size_t row_len, int channels, uint32_t n_rows, float *mem,
+                                cudaStream_t st)
+{
+    if (n_rows == 0 || channels <= 0) return cudaSuccess;
+    const uint32_t total = n_rows * (uint32_t)channels;
+    k_op_soft_clip<<<(total + 63) / 64, 64, 0, st>>>(pcm, row_stride, row_len, channels, n_rows, mem);
+    return cudaGetLastError();
+}
+
+}  // namespace opn

@@ -1,0 +1,352 @@
+// rangedec.cuh -- warp-per-stream entropy decoder for sm_100a.
+//
+// Device mirror of the reference's RangeDecoder (src/range_coder/decoder.rs:10-355, constants
+// src/range_coder/mod.rs:48-117) and of decode_pulses/cwrsi (src/celt/pvc.rs:156-298).
+//
+// Execution model: ONE WARP owns one packet.  The coder state (rng, val, ...) is warp-uniform:
+// all 32 lanes hold the same registers and take the same branches, so there is no divergence
+// and no shuffle traffic for the serial part.  The packet bytes live in shared memory (staged
+// once, coalesced), so the front/back byte reads are bank-broadcast loads.  Lanes only differ
+// where there is data parallelism: staging the packet, the PVQ zero-run scan, writing pulse
+// vectors and coefficients.
+#pragma once
+#include <stdint.h>
+
+namespace opn {
+
+// src/range_coder/mod.rs:48-68
+constexpr uint32_t RC_UINT_BITS = 8, RC_BITRES = 3, RC_WINDOW_SIZE = 32, RC_SYM_BITS = 8, RC_CODE_BITS = 32;
+constexpr uint32_t RC_SYM_MAX = (1u << RC_SYM_BITS) - 1u;
+constexpr uint32_t RC_CODE_TOP = 1u << (RC_CODE_BITS - 1u);
+constexpr uint32_t RC_CODE_BOT = RC_CODE_TOP >> RC_SYM_BITS;
+constexpr uint32_t RC_CODE_EXTRA = (RC_CODE_BITS - 2u) % RC_SYM_BITS + 1u;
+
+__device__ __forceinline__ uint32_t rc_ilog(uint32_t x) { return 32u - (uint32_t)__clz((int)x); }  // math.rs:5-7
+
+// src/range_coder/mod.rs:114-117
+__device__ __forceinline__ uint32_t laplace_freq1(uint32_t fs0, uint32_t decay)
+{
+    uint32_t ft = 32768u - 32u - fs0;
+    return (ft * (16384u - decay)) >> 15;
+}
+
+struct RangeDec {
+    const uint8_t *buf;  // shared memory
+    uint32_t storage, end_offs, end_window, end_bits, bits_total, offs, rng, val, ext, rem;
+
+    // decoder.rs:86-94
+    __device__ __forceinline__ uint32_t read_byte()
+    {
+        if (offs < storage) return buf[offs++];
+        return 0u;
+    }
+    // decoder.rs:97-104
+    __device__ __forceinline__ uint32_t read_byte_from_end()
+    {
+        if (end_offs < storage) {
+            end_offs += 1u;
+            return buf[storage - end_offs];
+        }
+        return 0u;
+    }
+    // decoder.rs:108-122
+    __device__ __forceinline__ void normalize()
+    {
+        while (rng <= RC_CODE_BOT) {
+            bits_total += RC_SYM_BITS;
+            rng <<= RC_SYM_BITS;
+            uint32_t symbol = rem;
+            rem = read_byte();
+            symbol = ((symbol << RC_SYM_BITS) | rem) >> (RC_SYM_BITS - RC_CODE_EXTRA);
+            val = ((val << RC_SYM_BITS) + (RC_SYM_MAX & ~symbol)) & (RC_CODE_TOP - 1u);
+        }
+    }
+    // decoder.rs:50-78
+    __device__ __forceinline__ void init(const uint8_t *b, uint32_t len)
+    {
+        buf = b;
+        storage = len;
+        end_offs = 0u;
+        end_window = 0u;
+        end_bits = 0u;
+        bits_total = RC_CODE_BITS + 1u - ((RC_CODE_BITS - RC_CODE_EXTRA) / RC_SYM_BITS) * RC_SYM_BITS;
+        offs = 0u;
+        rng = 1u << RC_CODE_EXTRA;
+        ext = 0u;
+        rem = read_byte();
+        val = rng - 1u - (rem >> (RC_SYM_BITS - RC_CODE_EXTRA));
+        normalize();
+    }
+    // decoder.rs:81-83
+    __device__ __forceinline__ void shrink_storage(uint32_t by) { storage -= by; }
+    // decoder.rs:143-147
+    __device__ __forceinline__ uint32_t decode(uint32_t ft)
+    {
+        ext = rng / ft;
+        uint32_t s = val / ext;
+        return ft - min(s + 1u, ft);
+    }
+    // decoder.rs:150-154
+    __device__ __forceinline__ uint32_t decode_bin(uint32_t bits)
+    {
+        ext = rng >> bits;
+        uint32_t s = val / ext;
+        return (1u << bits) - min(s + 1u, 1u << bits);
+    }
+    // decoder.rs:172-181
+    __device__ __forceinline__ void update(uint32_t fl, uint32_t fh, uint32_t ft)
+    {
+        uint32_t s = ext * (ft - fh);
+        val -= s;
+        rng = fl > 0u ? ext * (fh - fl) : rng - s;
+        normalize();
+    }
+    // decoder.rs:184-195
+    __device__ __forceinline__ uint32_t bit_logp(uint32_t logp)
+    {
+        uint32_t r = rng, d = val, s = r >> logp;
+        uint32_t ret = d < s ? 1u : 0u;
+        if (!ret) val = d - s;
+        rng = ret ? s : r - s;
+        normalize();
+        return ret;
+    }
+    // decoder.rs:210-232.  icdf may point to shared, global or constant memory.
+    __device__ __forceinline__ uint32_t icdf(const uint8_t *tab, uint32_t ftb)
+    {
+        uint32_t s = rng, d = val, r = s >> ftb, t, ret = 0u;
+        for (;;) {
+            t = s;
+            s = r * (uint32_t)tab[ret];
+            if (d >= s) break;
+            ret += 1u;
+        }
+        val = d - s;
+        rng = t - s;
+        normalize();
+        return ret;
+    }
+    // decoder.rs:279-303
+    __device__ __forceinline__ uint32_t bits(uint32_t nbits)
+    {
+        uint32_t window = end_window, available = end_bits;
+        if (available < nbits) {
+            do {
+                window |= read_byte_from_end() << available;
+                available += RC_SYM_BITS;
+            } while (available <= RC_WINDOW_SIZE - RC_SYM_BITS);
+        }
+        uint32_t ret = window & ((1u << nbits) - 1u);
+        window >>= nbits;
+        available -= nbits;
+        end_window = window;
+        end_bits = available;
+        bits_total += nbits;
+        return ret;
+    }
+    // decoder.rs:245-266
+    __device__ __forceinline__ uint32_t uint(uint32_t ft)
+    {
+        ft -= 1u;
+        uint32_t ftb = rc_ilog(ft);
+        if (ftb > RC_UINT_BITS) {
+            ftb -= RC_UINT_BITS;
+            uint32_t ft1 = (ft >> ftb) + 1u;
+            uint32_t s = decode(ft1);
+            update(s, s + 1u, ft1);
+            uint32_t t = (s << ftb) | bits(ftb);
+            return t <= ft ? t : ft;  // corrupt frame saturates (decoder.rs:255-259)
+        }
+        ft += 1u;
+        uint32_t s = decode(ft);
+        update(s, s + 1u, ft);
+        return s;
+    }
+    // decoder.rs:314-355
+    __device__ __forceinline__ int32_t laplace(uint32_t fs, uint32_t decay)
+    {
+        int32_t v = 0;
+        uint32_t fm = decode_bin(15u);
+        uint32_t fl = 0u;
+        if (fm >= fs) {
+            v += 1;
+            fl = fs;
+            fs = laplace_freq1(fs, decay) + 1u;
+            while (fs != 0u && fm >= fl + 2u * fs) {
+                fs *= 2u;
+                fl += fs;
+                fs = ((fs - 2u) * decay) >> 15;
+                fs += 1u;
+                v += 1;
+            }
+            if (fs <= 1u) {
+                uint32_t di = (fm - fl) >> 1;
+                v += (int32_t)di;
+                fl += 2u * di;
+            }
+            if (fm < fl + fs) v = -v;
+            else fl += fs;
+        }
+        update(fl, min(fl + fs, 32768u), 32768u);
+        return v;
+    }
+    // src/range_coder/mod.rs:84-86
+    __device__ __forceinline__ uint32_t tell() const { return bits_total - rc_ilog(rng); }
+    // src/range_coder/mod.rs:96-111
+    __device__ __forceinline__ uint32_t tell_frac() const
+    {
+        uint32_t nbits = bits_total << RC_BITRES;
+        uint32_t l = rc_ilog(rng);
+        uint32_t r = rng >> (l - 16u);
+        uint32_t b = (r >> 12) - 8u;
+        // correction = {35733, 38967, 42495, 46340, 50535, 55109, 60097, 65535}
+        uint32_t c = b == 0u ? 35733u : b == 1u ? 38967u : b == 2u ? 42495u : b == 3u ? 46340u
+                   : b == 4u ? 50535u : b == 5u ? 55109u : b == 6u ? 60097u : 65535u;
+        if (r > c) b += 1u;
+        l = (l << 3) + b;
+        return nbits - l;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// PVQ codeword expansion.  U(n,k) table in shared memory: rowoff[15] + data[1272]
+// (src/celt/pvc.rs:301-429).
+struct PvqTable {
+    const uint32_t *data;
+    const uint16_t *row;
+    __device__ __forceinline__ uint32_t u(uint32_t n, uint32_t k) const  // pvc.rs:295-298
+    {
+        uint32_t lo = min(n, k), hi = max(n, k);
+        return data[row[lo] + hi];
+    }
+    __device__ __forceinline__ uint32_t v(uint32_t n, uint32_t k) const { return u(n, k) + u(n, k + 1u); }  // pvc.rs:289-291
+};
+
+__device__ __forceinline__ uint32_t sat_add_u32(uint32_t a, uint32_t b)
+{
+    uint32_t s = a + b;
+    return s < a ? 0xFFFFFFFFu : s;
+}
+
+// cwrsi (pvc.rs:182-284) executed by a full warp.  y (shared memory, n ints) receives the pulse
+// vector; returns yy = sum y^2 (exact in f32: < 2^24).
+//
+// The "lots of dimensions" branch (k < n, pvc.rs:232-258) walks runs of empty dimensions one at
+// a time in the reference: while U(k,n) <= i < U(k+1,n) { i -= U(k,n); y = 0; n -= 1 }.  Here the
+// 32 lanes test 32 consecutive dimensions at once: lane t looks at dimension n-t, an exclusive
+// prefix sum of U(k,n-s), s<t (saturating, so it can never wrap below i) gives the value `i`
+// would have on reaching that dimension, and a ballot finds the first dimension that is not
+// empty.  The result is identical to the serial walk because every test uses exactly the serial
+// value of i.
+__device__ __forceinline__ float cwrsi_warp(const PvqTable &T, int32_t *y, uint32_t n, uint32_t k, uint32_t i,
+                                            uint32_t lane)
+{
+    uint32_t yp = 0u;
+    int32_t yy = 0;
+    while (n > 2u) {
+        uint32_t p, k0;
+        int32_t s, val;
+        if (k >= n) {  // lots of pulses (pvc.rs:196-231), warp-uniform serial
+            uint32_t row = T.row[n];
+            p = T.data[row + k + 1u];
+            s = i >= p ? -1 : 0;
+            i -= (uint32_t)((int32_t)p & s);
+            k0 = k;
+            uint32_t q = T.data[row + n];
+            if (q > i) {
+                k = n;
+                do {
+                    k -= 1u;
+                    p = T.data[T.row[k] + n];
+                } while (p > i);
+            } else {
+                p = T.data[row + k];
+                while (p > i) {
+                    k -= 1u;
+                    p = T.data[row + k];
+                }
+            }
+            i -= p;
+            val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+            if (lane == 0u) y[yp] = val;
+            yp += 1u;
+            yy += val * val;
+            n -= 1u;
+        } else {  // lots of dimensions (pvc.rs:232-258)
+            // ---- parallel zero-run scan over dimensions n, n-1, ..., n-31
+            uint32_t rk = T.row[k], rk1 = T.row[k + 1u];
+            uint32_t nt = n - lane;                       // dimension this lane inspects
+            // the run may only cover dimensions that stay in this branch: nt > 2 and nt > k
+            bool live = lane < n - max(2u, k);
+            uint32_t pt = live ? T.data[rk + nt] : 0u;
+            uint32_t qt = live ? T.data[rk1 + nt] : 0u;
+            uint32_t incl = pt;                           // inclusive saturating prefix sum
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl = sat_add_u32(incl, o);
+            }
+            uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 0u) excl = 0u;
+            bool zero = live && excl <= i && pt <= i - excl && (i - excl) < qt;
+            uint32_t nz = __ballot_sync(0xFFFFFFFFu, !zero);
+            uint32_t run = nz ? (uint32_t)(__ffs((int)nz) - 1) : 32u;  // number of leading empty dims
+            if (lane < run) y[yp + lane] = 0;
+            // i after the run = i - excl[run]  (excl of lane `run`, or incl of lane 31 if run == 32)
+            uint32_t sub = __shfl_sync(0xFFFFFFFFu, run < 32u ? excl : incl, run < 32u ? run : 31u);
+            i -= sub;
+            yp += run;
+            n -= run;
+            // If the run stopped because the next dimension leaves this branch (n <= 2 or
+            // k >= n) or because all 32 lanes were empty, re-dispatch from the loop head.
+            if (run < 32u && n > 2u && k < n) {
+                // ---- the dimension that holds pulses (pvc.rs:240-257), warp-uniform
+                uint32_t q = T.data[rk1 + n];
+                s = i >= q ? -1 : 0;
+                i -= (uint32_t)((int32_t)q & s);
+                k0 = k;
+                do {
+                    k -= 1u;
+                    p = T.data[T.row[k] + n];
+                } while (p > i);
+                i -= p;
+                val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+                if (lane == 0u) y[yp] = val;
+                yp += 1u;
+                yy += val * val;
+                n -= 1u;
+            }
+        }
+    }
+    {
+        // n == 2 (pvc.rs:262-275)
+        uint32_t p = 2u * k + 1u;
+        int32_t s = i >= p ? -1 : 0;
+        i -= (uint32_t)((int32_t)p & s);
+        uint32_t k0 = k;
+        k = (i + 1u) >> 1;
+        if (k != 0u) i -= 2u * k - 1u;
+        int32_t val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+        if (lane == 0u) y[yp] = val;
+        yp += 1u;
+        yy += val * val;
+        // n == 1 (pvc.rs:277-281)
+        s = -(int32_t)i;
+        val = ((int32_t)k + s) ^ s;
+        if (lane == 0u) y[yp] = val;
+        yy += val * val;
+    }
+    __syncwarp();
+    return (float)yy;
+}
+
+// decode_pulses (pvc.rs:156-160)
+__device__ __forceinline__ float decode_pulses_warp(RangeDec &d, const PvqTable &T, int32_t *y, uint32_t n, uint32_t k,
+                                                    uint32_t lane)
+{
+    uint32_t ft = T.v(n, k);
+    uint32_t i = d.uint(ft);
+    return cwrsi_warp(T, y, n, k, i, lane);
+}
+
+}  // namespace opn

@@ -88,7 +88,7 @@ int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t
     orc_synth_side side_local;
     if (!side) side = &side_local;
 
-    int lost = len == 0;
+    int lost = len <= 1; /* src/decoder.rs:467: payloads of 0 or 1 byte trigger PLC/DTX */
     if (lost) {
         memset(side, 0, sizeof(*side));
         memset(coef, 0, sizeof(float) * (size_t)nf * (size_t)channels);

@@ -1,0 +1,567 @@
+"""GPU parity tests: every CUDA entry point of libopusb200 (called through the C ABI) against the
+CPU oracle on the same seeded inputs.  Integer/byte/index results must be bit-exact; float PCM must
+be within max-abs 1e-5 and SNR > 100 dB (north_star), and is in fact expected to be bit-identical
+because the kernels keep the reference's operation order and are built with -fmad=false."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import opus_native_b200 as opn
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+PCM_TOL = 1e-5  # north_star: max-abs PCM error
+
+
+def snr_db(want, got):
+    want = want.astype(np.float64)
+    err = ((want - got.astype(np.float64)) ** 2).sum()
+    return 200.0 if err == 0 else 10 * np.log10((want ** 2).sum() / err)
+
+
+def assert_pcm(want, got, what=""):
+    assert np.all(np.isfinite(got)), what
+    assert np.abs(want.astype(np.float64) - got).max() <= PCM_TOL, what
+    assert snr_db(want, got) > 100.0, what
+
+
+# ------------------------------------------------------------------ range decoder (a1-a9)
+def test_rangedec_simple_uint_bits_kat():
+    """range_coder/mod.rs:191-263 replayed by one warp on the GPU: every symbol, the per-symbol
+    tell_frac and the final coder state match; the stream is the reference's 497192-byte KAT."""
+    ops, vals = [], []
+    for ft in range(2, 1024):
+        ops += [(opn.OP_UINT, ft, 0)] * ft
+        vals += list(range(ft))
+    for ftb in range(1, 16):
+        ops += [(opn.OP_BITS, ftb, 0)] * (1 << ftb)
+        vals += list(range(1 << ftb))
+    ops = np.array(ops, opn.OP_DTYPE)
+    vals = np.array(vals, np.uint32)
+    buf, tf, range_bytes, final_tf, err = opn.enc_run_script(600000, ops, vals)
+    assert err == 0 and range_bytes == KATS["simple_uint_bits"]["range_bytes"]
+    assert final_tf / 8.0 == KATS["simple_uint_bits"]["tell_frac_over_8"]
+    out, _ = opn.op_rangedec_script(buf, [0], [len(buf)], ops)
+    assert np.array_equal(out[0]["value"], vals)
+    assert np.array_equal(out[0]["tell_frac"], tf)
+    want, _ = O.dec_run_script(buf, ops)
+    assert np.array_equal(out[0], want)
+
+
+def test_rangedec_encoder_prefers_range_coder_data_kat():
+    """range_coder/mod.rs:271-298"""
+    ops = np.array([(opn.OP_BITS, 7, 0)] + [(opn.OP_UINT, ft, 0) for ft in (2, 3, 4, 5, 6, 7)], opn.OP_DTYPE)
+    buf, _, _, _, _ = opn.enc_run_script(2, ops, [0x55, 1, 1, 1, 1, 2, 6])
+    out, _ = opn.op_rangedec_script(buf, [0], [2], ops)
+    assert out[0]["value"].tolist() == [0x05, 1, 1, 1, 1, 2, 6]
+
+
+def _random_script(rnd, n_ops, with_pulses=True):
+    ops, vals, ys = [], [], []
+    for _ in range(n_ops):
+        kind = int(rnd.integers(0, 8 if with_pulses else 7))
+        if kind == 0:
+            ft = int(rnd.integers(2, 2 ** int(rnd.integers(2, 33)) - 1))
+            ops.append((opn.OP_UINT, ft, 0)); vals.append(int(rnd.integers(0, ft)))
+        elif kind == 1:
+            nb = int(rnd.integers(1, 26))
+            ops.append((opn.OP_BITS, nb, 0)); vals.append(int(rnd.integers(0, 1 << nb)))
+        elif kind == 2:
+            ops.append((opn.OP_BIT_LOGP, int(rnd.integers(1, 16)), 0)); vals.append(int(rnd.integers(0, 2)))
+        elif kind == 3:
+            ops.append((opn.OP_ICDF, 0, 5)); vals.append(int(rnd.integers(0, 6)))
+        elif kind == 4:
+            decay = int(rnd.integers(5000, 16000))
+            ops.append((opn.OP_LAPLACE, O.lib().orc_laplace_start_freq(decay), decay))
+            vals.append(int(rnd.integers(-12, 13)) & 0xFFFFFFFF)
+        elif kind == 5:
+            ops.append((opn.OP_BIT_VIA_DECODE, int(rnd.integers(1, 16)), 0)); vals.append(int(rnd.integers(0, 2)))
+        elif kind == 6:
+            ops.append((opn.OP_BIT_VIA_DECODE_BIN, int(rnd.integers(1, 16)), 0)); vals.append(int(rnd.integers(0, 2)))
+        else:
+            i = int(rnd.integers(0, 22))
+            n, kmax = KATS["pvc_pn"][i], KATS["pvc_pk_max"][i]
+            k = int(rnd.integers(1, kmax + 1))
+            y = np.zeros(n, np.int32)
+            O.lib().orc_cwrsi(O.ptr(y), n, k, int(rnd.integers(0, O.lib().orc_pvq_v(n, k))))
+            ops.append((opn.OP_PULSES, n, k)); vals.append(0); ys.extend(y.tolist())
+    return np.array(ops, opn.OP_DTYPE), vals, ys
+
+
+ICDF_POOL = np.array([30, 22, 15, 8, 3, 0], np.uint8)
+
+
+def test_rangedec_random_scripts_all_ops():
+    """Many packets, one script per launch: values, tell_frac, rng and pulse vectors, bit-exact.
+    Also covers test_random_data / test_compatibility / test_laplace (mod.rs:301-570) semantics:
+    decoder tell_frac equals the encoder's after every symbol."""
+    rnd = np.random.default_rng(11)
+    for trial in range(6):
+        ops, _, _ = _random_script(rnd, 150)
+        # same script shape, different symbol values per packet
+        bufs, tfs = [], []
+        n_pk = 40
+        for p in range(n_pk):
+            vals, ys = [], []
+            for op, a, b in ops:
+                if op == opn.OP_UINT: vals.append(int(rnd.integers(0, a)))
+                elif op == opn.OP_BITS: vals.append(int(rnd.integers(0, 1 << a)))
+                elif op == opn.OP_ICDF: vals.append(int(rnd.integers(0, 6)))
+                elif op == opn.OP_LAPLACE: vals.append(int(rnd.integers(-12, 13)) & 0xFFFFFFFF)
+                elif op == opn.OP_PULSES:
+                    y = np.zeros(a, np.int32)
+                    O.lib().orc_cwrsi(O.ptr(y), int(a), int(b), int(rnd.integers(0, O.lib().orc_pvq_v(int(a), int(b)))))
+                    vals.append(0); ys.extend(y.tolist())
+                else: vals.append(int(rnd.integers(0, 2)))
+            buf, tf, rb, ftf, err = opn.enc_run_script(1275, ops, vals, ICDF_POOL, ys or None)
+            assert err == 0
+            bufs.append(buf); tfs.append(tf)
+        arena = np.concatenate(bufs)
+        offsets = np.arange(n_pk, dtype=np.uint32) * 1275
+        lens = np.full(n_pk, 1275, np.uint32)
+        ystride = int(sum(a for op, a, b in ops if op == opn.OP_PULSES))
+        out, y = opn.op_rangedec_script(arena, offsets, lens, ops, ICDF_POOL, y_stride=ystride)
+        for p in range(n_pk):
+            want, wy = O.dec_run_script(bufs[p], ops, ICDF_POOL, y_cap=ystride)
+            assert np.array_equal(out[p], want), (trial, p)
+            assert np.array_equal(y[p, :len(wy)], wy)
+            assert np.array_equal(out[p]["tell_frac"], tfs[p])
+
+
+def test_rangedec_garbage_and_truncated_packets():
+    """Corrupt input: random bytes, short and empty buffers, storage shrink.  The decoder must do
+    exactly what the reference does (zero-extension, decode_uint saturation, decoder.rs:86-104,255-259)."""
+    rnd = np.random.default_rng(5)
+    base_ops, _, _ = _random_script(rnd, 120)
+    shrink_ops = np.concatenate([base_ops[:60], np.array([(opn.OP_SHRINK, 3, 0), (opn.OP_TELL, 0, 0)], opn.OP_DTYPE), base_ops[60:]])
+    # SHRINK by 3 needs len >= 3 (a usize underflow panic in the reference otherwise)
+    for ops, lens in ((base_ops, [0, 1, 2, 3, 5, 8, 13, 40, 100, 300, 1275, 17]), (shrink_ops, [3, 4, 5, 8, 13, 40, 100, 300, 1275, 17])):
+        lens = np.array(lens, np.uint32)
+        offsets = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+        arena = rnd.integers(0, 256, int(lens.sum()) + 4).astype(np.uint8)
+        ystride = int(sum(a for op, a, b in ops if op == opn.OP_PULSES))
+        out, y = opn.op_rangedec_script(arena, offsets, lens, ops, ICDF_POOL, y_stride=ystride)
+        for p in range(len(lens)):
+            want, wy = O.dec_run_script(arena[offsets[p]:offsets[p] + lens[p]], ops, ICDF_POOL, y_cap=ystride)
+            assert np.array_equal(out[p], want), p
+            assert np.array_equal(y[p, :len(wy)], wy), p
+
+
+# ------------------------------------------------------------------ PVQ (a10, a11)
+def test_cwrsi_all_band_sizes():
+    """celt/pvc.rs:453-503 test_pvc on the GPU: for every (N, K) of the ladder, evenly spaced codeword
+    indices -> pulse vector, sum|y| == K, yy exact, and identical to the oracle's cwrsi."""
+    def get_pulses(i):
+        return i if i < 8 else (8 + (i & 7)) << ((i >> 3) - 1)
+
+    L = O.lib()
+    for n, kmax in zip(KATS["pvc_pn"], KATS["pvc_pk_max"]):
+        for pseudo in range(1, 41):
+            k = get_pulses(pseudo)
+            if k > kmax:
+                break
+            nc = L.orc_pvq_v(n, k)
+            idx = np.unique(np.linspace(0, nc - 1, 48).astype(np.uint64)).astype(np.uint32)
+            # one packet per index, each holding a single decode_uint(V) == the codeword index
+            eop = np.array([(opn.OP_UINT, nc, 0)], opn.OP_DTYPE)
+            bufs = [opn.enc_run_script(16, eop, [int(i)])[0] for i in idx]
+            arena = np.concatenate(bufs)
+            offsets = np.arange(len(idx), dtype=np.uint32) * 16
+            out, y = opn.op_rangedec_script(arena, offsets, np.full(len(idx), 16, np.uint32),
+                                            np.array([(opn.OP_PULSES, n, k)], opn.OP_DTYPE), y_stride=n)
+            want = np.zeros(n, np.int32)
+            for j, i in enumerate(idx):
+                yy = L.orc_cwrsi(O.ptr(want), n, k, int(i))
+                assert np.array_equal(y[j], want), (n, k, int(i))
+                assert int(np.abs(y[j]).sum()) == k
+                assert out[j, 0]["value"] == np.float32(yy).view(np.uint32)
+                assert L.orc_icwrs(O.ptr(y[j].copy()), n) == i
+
+
+# ------------------------------------------------------------------ IMDCT + TDAC (a12-a14, a17)
+@pytest.mark.parametrize("shift", [0, 1, 2, 3])
+def test_imdct_tdac_long_blocks(shift):
+    rnd = np.random.default_rng(100 + shift)
+    n2 = 960 >> shift
+    rows = 37
+    coefs = (rnd.uniform(-1, 1, (rows, n2)) / 32).astype(np.float32)
+    coefs[:, (100 * 8) >> shift:] = 0  # above band 21
+    coefs[0] = 0
+    coefs[1] = (rnd.uniform(-1, 1, n2) * 32768.0).astype(np.float32)  # mdct.rs:711-714 scale
+    out = np.zeros((rows, n2 + 60), np.float32)
+    out[:, :60] = rnd.uniform(-1, 1, (rows, 60)).astype(np.float32)
+    want = out.copy()
+    for r in range(rows):
+        O.mdct_backward(coefs[r], want[r], shift)
+    got = opn.op_imdct_tdac(coefs, out.copy(), shift)
+    assert np.array_equal(got, want)  # bit-exact
+    assert_pcm(want[2:], got[2:])
+
+
+def test_imdct_matches_f64_definition():
+    """celt/mdct.rs:672-701 check_inv: SNR vs the O(n^2) f64 IMDCT (> 60 dB in the reference)."""
+    for shift, nfft in [(3, 240), (2, 480), (1, 960), (0, 1920)]:
+        rnd = np.random.default_rng(42)
+        x = ((rnd.integers(0, 32768, nfft // 2) - 16384) * 32768.0 / nfft).astype(np.float32)
+        out = np.zeros((1, nfft // 2 + 60), np.float32)
+        got = opn.op_imdct_tdac(x[None, :].copy(), out, shift)[0]
+        i = np.arange(nfft)[:, None]
+        k = np.arange(nfft // 2)[None, :]
+        full = np.cos(2 * np.pi * (i + 0.5 + 0.25 * nfft) * (k + 0.5) / nfft) @ x.astype(np.float64)
+        # out[60 + j] = y[N/4 + j] for the un-windowed part j in [60, N/2 - 60)  
+        j = np.arange(60, nfft // 2 - 60)
+        want = full[nfft // 4 + j]
+        assert 10 * np.log10((want ** 2).sum() / ((want - got[60 + j]) ** 2).sum()) > 100.0
+
+
+@pytest.mark.parametrize("blocks", [2, 4, 8])
+def test_imdct_tdac_short_blocks(blocks):
+    """Transient frames: B interleaved 120-bin blocks (stride = B), chained TDAC (mdct.rs:186,197-198)."""
+    rnd = np.random.default_rng(blocks)
+    rows = 19
+    coefs = (rnd.uniform(-1, 1, (rows, 120 * blocks)) / 32).astype(np.float32)
+    out = np.zeros((rows, 120 * blocks + 60), np.float32)
+    out[:, :60] = rnd.uniform(-1, 1, (rows, 60)).astype(np.float32)
+    want = out.copy()
+    for r in range(rows):
+        for b in range(blocks):
+            O.lib().orc_mdct_backward(O.ptr(coefs[r][b:]), O.ptr(want[r][120 * b:]), O.ptr(O.window()), 120, 3, blocks)
+    got = opn.op_imdct_tdac(coefs, out.copy(), 3, blocks=blocks)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ comb filter (a15, a16)
+def test_comb_filter_golden_vectors():
+    """celt/comb_filter/mod.rs:227-270: TEST_VECTOR1 (out of place) and TEST_VECTOR2 (in place)."""
+    p = KATS["comb_params"]
+    size, n = p["SIZE"], p["N"]
+    x = np.arange(size, dtype=np.float32)[None, :].copy()
+    params = [[p["T0"], p["T1"], 0, 0]]
+    gains = [[p["G0"], p["G1"]]]
+    y = opn.op_comb_filter(np.zeros_like(x), x, size - n, n, params, gains, p["OVERLAP"])
+    v1 = np.array(KATS["comb_test_vector1"], np.float32)
+    assert np.all(np.abs(1.0 - y[0, size - n:] / v1) < 1e-5)
+    assert np.array_equal(y[0, size - n:], v1)
+    y2 = opn.op_comb_filter_inplace(x.copy(), size - n, n, params, gains, p["OVERLAP"])
+    v2 = np.array(KATS["comb_test_vector2"], np.float32)
+    assert np.all(np.abs(1.0 - y2[0, size - n:] / v2) < 1e-5)
+
+
+def _comb_cases(rnd, rows):
+    params, gains = [], []
+    for r in range(rows):
+        t0, t1 = int(rnd.integers(0, 1023)), int(rnd.integers(0, 1023))
+        if r % 5 == 0: t1 = t0
+        if r % 7 == 0: t0, t1 = 15, 15
+        g0, g1 = float(rnd.integers(0, 9)) * 0.09375, float(rnd.integers(0, 9)) * 0.09375
+        if r % 11 == 0: g1 = g0
+        params.append([t0, t1, int(rnd.integers(0, 3)), int(rnd.integers(0, 3))])
+        gains.append([g0, g1])
+    params[0], gains[0] = [40, 40, 1, 1], [0.5, 0.5]      # unchanged filter -> overlap = 0
+    params[1], gains[1] = [100, 300, 0, 2], [0.0, 0.0]    # both gains zero -> untouched / copy
+    params[2], gains[2] = [100, 300, 0, 2], [0.75, 0.0]   # g1 = 0 -> only the cross-fade part
+    params[3], gains[3] = [0, 0, 0, 0], [0.0, 0.75]       # periods below COMBFILTER_MINPERIOD
+    params[4], gains[4] = [1022, 15, 2, 0], [0.75, 0.75]
+    return np.array(params, np.int32), np.array(gains, np.float32)
+
+
+@pytest.mark.parametrize("n,overlap", [(960, 120), (480, 120), (120, 120), (240, 64), (64, 8), (961, 120), (2, 0)])
+def test_comb_filter_inplace_random(n, overlap):
+    rnd = np.random.default_rng(n + overlap)
+    rows, off = 48, 1024
+    params, gains = _comb_cases(rnd, rows)
+    y = rnd.uniform(-0.5, 0.5, (rows, off + n)).astype(np.float32)
+    want = y.copy()
+    for r in range(rows):
+        O.comb_filter_inplace(want[r], off, int(params[r, 0]), int(params[r, 1]), n, float(gains[r, 0]), float(gains[r, 1]),
+                              int(params[r, 2]), int(params[r, 3]), overlap)
+    got = opn.op_comb_filter_inplace(y.copy(), off, n, params, gains, overlap)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,overlap", [(960, 120), (120, 120), (64, 8)])
+def test_comb_filter_out_of_place_random(n, overlap):
+    rnd = np.random.default_rng(n)
+    rows, off = 48, 1024
+    params, gains = _comb_cases(rnd, rows)
+    x = rnd.uniform(-0.5, 0.5, (rows, off + n)).astype(np.float32)
+    y0 = rnd.uniform(-0.5, 0.5, (rows, off + n)).astype(np.float32)
+    want = y0.copy()
+    for r in range(rows):
+        O.comb_filter(want[r], off, x[r], off, int(params[r, 0]), int(params[r, 1]), n, float(gains[r, 0]), float(gains[r, 1]),
+                      int(params[r, 2]), int(params[r, 3]), overlap)
+    got = opn.op_comb_filter(y0.copy(), x, off, n, params, gains, overlap)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ soft clip (a19)
+@pytest.mark.parametrize("channels", [1, 2, 3])
+def test_pcm_soft_clip(channels):
+    rnd = np.random.default_rng(channels)
+    rows, n = 33, 960
+    pcm = (rnd.normal(0, 0.9, (rows, n * channels))).astype(np.float32)
+    pcm[0] = ((np.arange(n * channels) & 255) * (1.0 / 32.0) - 4.0).astype(np.float32)  # lib.rs:868-870
+    mem = rnd.uniform(-0.2, 0.2, (rows, channels)).astype(np.float32)
+    mem[1] = 0
+    want, wmem = pcm.copy(), mem.copy()
+    for r in range(rows):
+        O.lib().orc_pcm_soft_clip(O.ptr(want[r]), n * channels, channels, O.ptr(wmem[r]), channels)
+    got_mem = mem.copy()
+    got = opn.op_pcm_soft_clip(pcm.copy(), n * channels, channels, got_mem)
+    assert np.array_equal(got, want) and np.array_equal(got_mem, wmem)
+    assert got.max() <= 1.0 and got.min() >= -1.0  # lib.rs:874-877
+
+
+# ------------------------------------------------------------------ SYNTH-CELT/1 symbol kernel
+@pytest.mark.parametrize("lm,channels,pkt_bytes", [(3, 2, 160), (3, 1, 100), (2, 2, 130), (1, 2, 100), (0, 2, 80), (0, 1, 48)])
+def test_synth_symbols(lm, channels, pkt_bytes):
+    n = 96
+    pk = opn.synth_fill(1000, n, 3, 1, lm, channels, pkt_bytes, transient_permille=200)[0]
+    payload = np.ascontiguousarray(pk[:, 1:])
+    side, y, coef = opn.op_synth_symbols(payload.reshape(-1), np.arange(n, dtype=np.uint32) * (pkt_bytes - 1),
+                                         np.full(n, pkt_bytes - 1, np.uint32), lm, channels)
+    for s in range(n):
+        w, wy, wc, _ = O.SynthStream(lm, channels).decode(payload[s])
+        for f in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra", "final_rng", "tell_frac", "n_pulses"):
+            assert side[s][f] == getattr(w, f), (s, f)
+        assert np.array_equal(side[s]["coarse"], np.ctypeslib.as_array(w.coarse))
+        assert np.array_equal(side[s]["fine"], np.ctypeslib.as_array(w.fine))
+        assert np.array_equal(y[s].reshape(-1), wy)
+        assert np.array_equal(coef[s].reshape(-1).view(np.uint32), wc.view(np.uint32))
+
+
+# ------------------------------------------------------------------ batch pipeline
+def _oracle_chain(packets, lm, channels, apply_comb=True):
+    """packets [frames, streams, bytes] -> pcm [frames, streams, nf*C], final_rng [frames, streams]"""
+    nfr, ns, _ = packets.shape
+    nf = 120 << lm
+    pcm = np.zeros((nfr, ns, nf * channels), np.float32)
+    rng = np.zeros((nfr, ns), np.uint32)
+    for s in range(ns):
+        st = O.SynthStream(lm, channels, apply_comb)
+        for f in range(nfr):
+            side, _, _, p = st.decode(packets[f, s, 1:])
+            pcm[f, s], rng[f, s] = p, side.final_rng
+    return pcm, rng
+
+
+@pytest.mark.parametrize("lm,channels,pkt_bytes,postfilter", [(3, 2, 160, True), (3, 2, 160, False), (3, 1, 100, True),
+                                                               (2, 2, 130, True), (1, 2, 100, True), (0, 2, 80, True)])
+def test_batch_decode_chain(lm, channels, pkt_bytes, postfilter):
+    ns, nfr, nf = 48, 12 if lm == 3 else 20, 120 << lm
+    packets = opn.synth_fill(7, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=150)
+    want, want_rng = _oracle_chain(packets, lm, channels, postfilter)
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), postfilter=postfilter)
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+    exact = True
+    for f in range(nfr):
+        pcm = np.zeros((ns, nf * channels), np.float32)
+        res = dec.decode_float(packets[f].reshape(-1), offsets, lens, pcm, nf)
+        assert np.all(res == nf)
+        assert_pcm(want[f], pcm, f"frame {f}")
+        exact &= np.array_equal(pcm, want[f])
+        assert np.array_equal(dec.final_ranges(), want_rng[f])
+    assert exact, "PCM within tolerance but not bit-identical to the oracle"
+
+
+def test_batch_lost_invalid_and_foreign_packets_do_not_poison_neighbours():
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 16, 6, 960
+    packets = opn.synth_fill(99, ns, 0, nfr, lm, channels, pkt_bytes)
+    dec = opn.BatchDecoder(ns)
+    oracle = [O.SynthStream(lm, channels) for _ in range(ns)]
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    for f in range(nfr):
+        arena = packets[f].copy()
+        lens = np.full(ns, pkt_bytes, np.uint32)
+        expect = np.full(ns, nf, np.int32)
+        want = np.zeros((ns, nf * channels), np.float32)
+        kinds = {}
+        if f in (2, 3):
+            lens[3] = 0; kinds[3] = "lost"            # packet loss -> concealment frame
+            arena[5, 0] = 0x48; kinds[5] = "silk"      # SILK-only TOC: unimplemented in the reference too
+            arena[7, 0] = 0xFF; arena[7, 1] = 0x00; kinds[7] = "invalid"   # code 3 with 0 frames
+            arena[9, 0] = 0xF8; kinds[9] = "mono"      # mono packet for a stereo decoder
+        if f == 0:
+            lens[11] = 0; kinds[11] = "lost-first"   # nothing decoded yet -> zeros, state untouched
+        for s in range(ns):
+            k = kinds.get(s)
+            if k is None:
+                want[s] = oracle[s].decode(arena[s, 1:])[3]
+            elif k == "lost":
+                want[s] = oracle[s].decode(b"")[3]
+            elif k == "silk" or k == "mono":
+                expect[s] = -6
+            elif k == "invalid":
+                expect[s] = -4
+        pcm = np.full((ns, nf * channels), 7.0, np.float32)
+        res = dec.decode_float(arena.reshape(-1), offsets, lens, pcm, nf)
+        assert np.array_equal(res, expect), f
+        for s in range(ns):
+            if expect[s] < 0:
+                assert np.all(pcm[s] == 0)
+            else:
+                assert np.array_equal(pcm[s], want[s]), (f, s, kinds.get(s))
+
+
+def test_batch_multi_frame_packets_and_larger_frame_size():
+    """Code-1 (two CBR frames) and code-3 packets built from SYNTH-CELT/1 frames: the host splits them
+    with parse_packet (lib.rs:345-498) and decodes the frames in order (decoder.rs:399-411)."""
+    lm, channels, fb, ns, nf = 2, 2, 129, 8, 480
+    frames = opn.synth_fill(3, ns, 0, 6, lm, channels, fb + 1)[:, :, 1:]  # payloads without TOC
+    toc = 0x80 | 0x60 | (lm << 3) | 0x4
+    dec = opn.BatchDecoder(ns)
+    oracle = [O.SynthStream(lm, channels) for _ in range(ns)]
+    # packet A: code 1, frames 0,1 ; packet B: code 3 CBR with 3 frames + 5 bytes padding ; packet C: code 0
+    pa = [np.concatenate([[toc | 1], frames[0, s], frames[1, s]]).astype(np.uint8) for s in range(ns)]
+    pb = [np.concatenate([[toc | 3, 0x40 | 3, 5], frames[2, s], frames[3, s], frames[4, s], np.zeros(5)]).astype(np.uint8) for s in range(ns)]
+    pc = [np.concatenate([[toc], frames[5, s]]).astype(np.uint8) for s in range(ns)]
+    fidx = 0
+    for pk, count in ((pa, 2), (pb, 3), (pc, 1)):
+        ln = len(pk[0])
+        arena = np.concatenate(pk)
+        offsets = np.arange(ns, dtype=np.uint32) * ln
+        lens = np.full(ns, ln, np.uint32)
+        pcm = np.zeros((ns, 1920 * channels), np.float32)
+        res = dec.decode_float(arena, offsets, lens, pcm, 1920)
+        assert np.all(res == count * nf)
+        for s in range(ns):
+            want = np.concatenate([oracle[s].decode(frames[fidx + w, s])[3] for w in range(count)])
+            assert np.array_equal(pcm[s, :count * nf * channels], want)
+            assert np.all(pcm[s, count * nf * channels:] == 0)
+        fidx += count
+    # frame_size smaller than the packet -> FrameSizeTooSmall for every stream (decoder.rs:388-390)
+    res = dec.decode_float(np.concatenate(pa), np.arange(ns, dtype=np.uint32) * len(pa[0]), np.full(ns, len(pa[0]), np.uint32),
+                           np.zeros((ns, 480 * channels), np.float32), 480)
+    assert np.all(res == -5)
+    with pytest.raises(opn.OpusError):  # frame_size not a multiple of 2.5 ms (decoder.rs:316-320)
+        dec.decode_float(np.concatenate(pc), np.arange(ns, dtype=np.uint32), np.ones(ns, np.uint32), None, 100)
+
+
+def test_batch_device_resident_path_matches_host_path():
+    torch = pytest.importorskip("torch")
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 64, 5, 960
+    packets = opn.synth_fill(500, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
+    packets[2, 10, 0] = 0x48  # one foreign packet: reported per stream, neighbours unaffected
+    want, _ = _oracle_chain(packets[:, [s for s in range(ns) if s != 10]], lm, channels)
+    dev = torch.device("cuda:0")
+    d_arena = torch.from_numpy(packets.reshape(-1).copy()).to(dev)
+    d_off = torch.arange(ns, dtype=torch.int32, device=dev) * pkt_bytes
+    d_len = torch.full((ns,), pkt_bytes, dtype=torch.int32, device=dev)
+    d_pcm = torch.zeros((ns, nf * channels), dtype=torch.float32, device=dev)
+    d_res = torch.zeros(ns, dtype=torch.int32, device=dev)
+    dec = opn.BatchDecoder(ns)
+    keep = [s for s in range(ns) if s != 10]
+    for f in range(nfr):
+        dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), d_pcm.data_ptr(),
+                              nf * channels, nf, d_res.data_ptr(), opn.FLAG_DEVICE_PTRS)
+        dec.synchronize()
+        res = d_res.cpu().numpy()
+        if f == 2:
+            assert res[10] == -6
+        assert np.all(res[keep] == nf)
+        assert np.array_equal(d_pcm.cpu().numpy()[keep], want[f])
+    # ring view: the last frame of stream 0 sits just before ring_pos
+    ring_ptr, ring_n, pos_ptr = dec.ring()
+    assert ring_n == 2880 and ring_ptr and pos_ptr
+
+
+# ------------------------------------------------------------------ Decoder API (decoder.rs:27-232)
+def test_decoder_api_single_stream():
+    lm, channels, pkt_bytes, nf = 3, 2, 160, 960
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0))
+    assert (dec.sampling_rate, dec.channels, dec.gain) == (48000, 2, 0)
+    assert dec.bandwidth is None and dec.last_packet_duration is None and dec.pitch is None
+    st = O.SynthStream(lm, channels)
+    pcm = np.zeros(nf * channels, np.float32)
+    # loss before any packet: zeros (decoder.rs:478-487)
+    assert dec.decode_float(None, pcm, nf) == nf and np.all(pcm == 0)
+    for f in range(4):
+        pkt, truth = opn.synth_packet(1, f, lm, channels, pkt_bytes)
+        assert dec.decode_float(pkt, pcm, nf) == nf
+        side, _, _, want = st.decode(pkt[1:])
+        assert np.array_equal(pcm, want)
+        assert dec.final_range == side.final_rng
+        assert dec.bandwidth == "Fullband" and dec.last_packet_duration == nf
+        assert dec.pitch == (truth["period"] if truth["postfilter"] else 0)
+    # lost packet -> concealment, final_range 0 (decoder.rs:799-803)
+    assert dec.decode_float(None, pcm, nf) == nf
+    assert np.array_equal(pcm, st.decode(b"")[3]) and dec.final_range == 0
+    # decode_fec on a CELT stream conceals instead (decoder.rs:343-350)
+    pkt, _ = opn.synth_packet(1, 9, lm, channels, pkt_bytes)
+    assert dec.decode_float(pkt, pcm, nf, decode_fec=True) == nf
+    assert np.array_equal(pcm, st.decode(b"")[3])
+    # argument errors (decoder.rs:316-325, 388-390)
+    for bad in (100, 0):
+        with pytest.raises(opn.OpusError) as e:
+            dec.decode_float(pkt, np.zeros(4000, np.float32), bad)
+        assert e.value.kind == "BadArguments"
+    with pytest.raises(opn.OpusError) as e:
+        dec.decode_float(b"", pcm, nf)
+    assert e.value.kind == "BadArguments"
+    with pytest.raises(opn.OpusError) as e:
+        dec.decode_float(pkt, np.zeros(480 * 2, np.float32), 480)
+    assert e.value.kind == "FrameSizeTooSmall"
+    with pytest.raises(opn.OpusError) as e:
+        dec.decode_float(bytes([0x48, 1, 2, 3]), pcm, nf)
+    assert e.value.kind == "Unimplemented"
+    dec.reset()
+    assert dec.bandwidth is None
+    pkt0, _ = opn.synth_packet(1, 0, lm, channels, pkt_bytes)
+    assert dec.decode_float(pkt0, pcm, nf) == nf
+    assert np.array_equal(pcm, O.SynthStream(lm, channels).decode(pkt0[1:])[3])
+
+
+def test_decoder_gain_and_i16_output():
+    lm, channels, pkt_bytes, nf = 3, 2, 160, 960
+    gain_q8 = 1536  # +6 dB
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, gain_q8))
+    st = O.SynthStream(lm, channels)
+    g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
+    pcm = np.zeros(nf * channels, np.float32)
+    mem = np.zeros(2, np.float32)
+    dec16 = opn.Decoder(opn.DecoderConfiguration(48000, 2, gain_q8))
+    st16 = O.SynthStream(lm, channels)
+    for f in range(3):
+        pkt, _ = opn.synth_packet(2, f, lm, channels, pkt_bytes)
+        assert dec.decode_float(pkt, pcm, nf) == nf
+        want = st.decode(pkt[1:])[3] * g
+        assert_pcm(want, pcm)
+        out16 = np.zeros(nf * channels, np.int16)
+        assert dec16.decode(pkt, out16, nf) == nf
+        w = st16.decode(pkt[1:])[3] * g
+        # decode<S>: soft clip over samples[..sample_count] (reference quirk, decoder.rs:415-419) then from_f32
+        O.lib().orc_pcm_soft_clip(O.ptr(w), nf, channels, O.ptr(mem), 2)
+        w16 = np.clip(w * np.float32(32768.0), -32768.0, 32767.0).astype(np.int16)
+        assert np.abs(out16.astype(np.int32) - w16.astype(np.int32)).max() <= 1
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config 2)
+def test_config2_full_size_properties():
+    """4096 CELT FB 20 ms stereo streams @64 kbps, 3 chained frames: checksum of final ranges and the
+    last frame's PCM for all streams against the multithreaded oracle; range state is a function of the
+    packet only, PCM depends on the whole chain (carry + comb history)."""
+    ns, nfr, lm, channels, pkt_bytes, nf = 4096, 3, 3, 2, 160, 960
+    packets = opn.synth_fill(0, ns, 0, nfr, lm, channels, pkt_bytes)
+    want_pcm = np.zeros((ns, nf * channels), np.float32)
+    x = C.c_uint32(0)
+    O.lib().orc_synth_bench(O.ptr(packets), ns, nfr, pkt_bytes, lm, channels, 1, os.cpu_count() or 1, O.ptr(want_pcm), C.byref(x))
+    dec = opn.BatchDecoder(ns)
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+    pcm = np.zeros((ns, nf * channels), np.float32)
+    acc = np.uint32(0)
+    for f in range(nfr):
+        res = dec.decode_float(packets[f].reshape(-1), offsets, lens, pcm, nf)
+        assert np.all(res == nf)
+        acc ^= np.bitwise_xor.reduce(dec.final_ranges())
+    assert int(acc) == x.value
+    assert_pcm(want_pcm, pcm)
+    assert np.array_equal(pcm, want_pcm)
+    rms = math.sqrt(float((pcm.astype(np.float64) ** 2).mean()))
+    assert 0.01 < rms < 1.0  # the 1e-5 bar is applied on +-1-scale PCM
