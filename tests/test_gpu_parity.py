@@ -43,7 +43,7 @@ def test_rangedec_simple_uint_bits_kat():
         vals += list(range(1 << ftb))
     ops = np.array(ops, opn.OP_DTYPE)
     vals = np.array(vals, np.uint32)
-    buf, tf, range_bytes, final_tf, err = opn.enc_run_script(600000, ops, vals)
+    buf, tf, range_bytes, final_tf, err = opn.enc_run_script(1 << 20, ops, vals)
     assert err == 0 and range_bytes == KATS["simple_uint_bits"]["range_bytes"]
     assert final_tf / 8.0 == KATS["simple_uint_bits"]["tell_frac_over_8"]
     out, _ = opn.op_rangedec_script(buf, [0], [len(buf)], ops)
@@ -205,7 +205,7 @@ def test_imdct_tdac_long_blocks(shift):
 
 def test_imdct_matches_f64_definition():
     """celt/mdct.rs:672-701 check_inv: SNR vs the O(n^2) f64 IMDCT (> 60 dB in the reference)."""
-    for shift, nfft in [(3, 240), (2, 480), (1, 960), (0, 1920)]:
+    for shift, nfft in [(2, 480), (1, 960), (0, 1920)]:  # N=240 has no un-windowed span with overlap 120
         rnd = np.random.default_rng(42)
         x = ((rnd.integers(0, 32768, nfft // 2) - 16384) * 32768.0 / nfft).astype(np.float32)
         out = np.zeros((1, nfft // 2 + 60), np.float32)
@@ -314,7 +314,9 @@ def test_pcm_soft_clip(channels):
     got_mem = mem.copy()
     got = opn.op_pcm_soft_clip(pcm.copy(), n * channels, channels, got_mem)
     assert np.array_equal(got, want) and np.array_equal(got_mem, wmem)
-    assert got.max() <= 1.0 and got.min() >= -1.0  # lib.rs:874-877
+    # lib.rs:874-877 asserts [-1, 1] for the reference's own sawtooth input (row 0).  For general input
+    # the reference's search-loop quirk (see oracle/packet.c) can overshoot; parity is what is checked.
+    assert got[0].max() <= 1.0 and got[0].min() >= -1.0
 
 
 # ------------------------------------------------------------------ SYNTH-CELT/1 symbol kernel
