@@ -34,6 +34,36 @@ cudaError_t upload_tables(int device)
     for (int l = 0; l < 4; l++)
         for (int b = 0; b < 21; b++)
             for (int k = 0; k < 3; k++) h.synth_sched[l][b][k] = OPN_SYNTH_SCHED[l][b][k];
+    for (int lm = 0; lm < 4; lm++)
+        for (int C = 1; C <= 2; C++) {
+            int ne = 0;
+            const int nf = 120 << lm;
+            for (int b = 0; b < 21; b++)
+                for (int c = 0; c < C; c++) {
+                    const uint32_t n = OPN_SYNTH_SCHED[lm][b][0], parts = OPN_SYNTH_SCHED[lm][b][1], k = OPN_SYNTH_SCHED[lm][b][2];
+                    for (uint32_t p = 0; p < parts; p++) {
+                        SynthEntry &e = h.synth_entries[lm][C - 1][ne++];
+                        e.base = (uint16_t)(c * nf + ((int)OPN_E_BANDS[b] << lm) + (int)(p * n));
+                        e.n = (uint8_t)n;
+                        e.k = (uint8_t)k;
+                        e.ft_minus1 = 0; e.magic = 0; e.ft1 = 0; e.ftb = 0; e.sh = 0;
+                        if (n == 1) continue;
+                        auto U = [](uint32_t a, uint32_t bb) { return OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[a < bb ? a : bb] + (a < bb ? bb : a)]; };
+                        const uint32_t ft = U(n, k) + U(n, k + 1);   // pvq_v, pvc.rs:289-291
+                        e.ft_minus1 = ft - 1;
+                        uint32_t ftb = 32u - (uint32_t)__builtin_clz(ft - 1);  // ilog(ft-1), decoder.rs:247-248
+                        uint32_t ft1;
+                        if (ftb > 8) { ftb -= 8; ft1 = ((ft - 1) >> ftb) + 1; } else { ftb = 0; ft1 = ft; }
+                        e.ftb = (uint8_t)ftb;
+                        e.ft1 = (uint16_t)ft1;
+                        uint32_t sh = 0;
+                        while ((1ull << sh) < ft1) sh++;
+                        e.sh = (uint8_t)sh;
+                        e.magic = (uint32_t)((((1ull << sh) - ft1) << 32) / ft1 + 1);
+                    }
+                }
+            h.synth_n_entries[lm][C - 1] = (uint8_t)ne;
+        }
     h.tapset_icdf[0] = 2; h.tapset_icdf[1] = 1; h.tapset_icdf[2] = 0; h.tapset_icdf[3] = 0;
     for (int i = 0; i < 9; i++) h.comb_gains[i] = OPN_COMB_GAINS[i];
     cudaError_t e = cudaSetDevice(device);
@@ -69,7 +99,7 @@ cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
     const uint32_t grid = (a.n_items + SYM_WARPS_PER_CTA - 1) / SYM_WARPS_PER_CTA;
-    k_synth_symbols<<<grid, SYM_WARPS_PER_CTA * 32, symbols_smem(a.pkt_cap), st>>>(a);
+    k_synth_symbols<<<grid, SYM_WARPS_PER_CTA * 32, synth_symbols_smem(a.pkt_cap), st>>>(a);
     return cudaGetLastError();
 }
 

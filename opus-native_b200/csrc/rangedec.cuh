@@ -30,6 +30,27 @@ __device__ __forceinline__ uint32_t laplace_freq1(uint32_t fs0, uint32_t decay)
     return (ft * (16384u - decay)) >> 15;
 }
 
+// floor(a / b) for quotients below 2^16 (the range decoder's `val / ext`: val < rng always holds, so
+// the quotient never exceeds ft + ft/ext).  One MUFU.RCP estimate, deliberately scaled down by
+// 2^-20 so that it never overshoots, then a single upward correction -- exact, ~9 instructions
+// instead of the ~22 of the generic 32-bit division.
+__device__ __forceinline__ uint32_t div_small_quotient(uint32_t a, uint32_t b)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn(b)));
+    uint32_t q = __float2uint_rz(__uint2float_rn(a) * r * 0.999999f);
+    if (a - q * b >= b) q += 1u;
+    return q;
+}
+
+// floor(a / d) for an invariant divisor d given its round-up reciprocal (Granlund-Montgomery):
+// magic = floor(2^32 * (2^sh - d) / d) + 1, sh = ceil(log2 d).  Exact for every 32-bit a.
+__device__ __forceinline__ uint32_t div_magic(uint32_t a, uint32_t magic, uint32_t sh)
+{
+    uint32_t t = __umulhi(magic, a);
+    return (t + ((a - t) >> 1)) >> (sh - 1u);
+}
+
 struct RangeDec {
     const uint8_t *buf;  // shared memory
     uint32_t storage, end_offs, end_window, end_bits, bits_total, offs, rng, val, ext, rem;
@@ -92,6 +113,33 @@ struct RangeDec {
         ext = rng >> bits;
         uint32_t s = val / ext;
         return (1u << bits) - min(s + 1u, 1u << bits);
+    }
+    // decode() for ft <= 2^15 (decoder.rs:143-147) with the cheap exact quotient
+    __device__ __forceinline__ uint32_t decode_small(uint32_t ft)
+    {
+        ext = rng / ft;
+        uint32_t s = div_small_quotient(val, ext);
+        return ft - min(s + 1u, ft);
+    }
+    // decode_bin (decoder.rs:150-154) with the cheap exact quotient (bits <= 15)
+    __device__ __forceinline__ uint32_t decode_bin_small(uint32_t bits)
+    {
+        ext = rng >> bits;
+        uint32_t s = div_small_quotient(val, ext);
+        return (1u << bits) - min(s + 1u, 1u << bits);
+    }
+    // decode_uint (decoder.rs:245-266) for an alphabet whose split (ft1, ftb) and reciprocal were
+    // precomputed on the host: same arithmetic, no runtime ilog and no generic division.
+    __device__ __forceinline__ uint32_t uint_precomputed(uint32_t ft_minus1, uint32_t ft1, uint32_t ftb, uint32_t magic,
+                                                         uint32_t sh)
+    {
+        ext = div_magic(rng, magic, sh);                 // rng / ft1
+        uint32_t q = div_small_quotient(val, ext);       // val / ext
+        uint32_t s = ft1 - min(q + 1u, ft1);             // decode(ft1)
+        update(s, s + 1u, ft1);
+        if (ftb == 0u) return s;
+        uint32_t t = (s << ftb) | bits(ftb);
+        return t <= ft_minus1 ? t : ft_minus1;
     }
     // decoder.rs:172-181
     __device__ __forceinline__ void update(uint32_t fl, uint32_t fh, uint32_t ft)
@@ -166,7 +214,7 @@ struct RangeDec {
     __device__ __forceinline__ int32_t laplace(uint32_t fs, uint32_t decay)
     {
         int32_t v = 0;
-        uint32_t fm = decode_bin(15u);
+        uint32_t fm = decode_bin_small(15u);
         uint32_t fl = 0u;
         if (fm >= fs) {
             v += 1;
@@ -337,6 +385,79 @@ __device__ __forceinline__ float cwrsi_warp(const PvqTable &T, int32_t *y, uint3
         yy += val * val;
     }
     __syncwarp();
+    return (float)yy;
+}
+
+// cwrsi (pvc.rs:182-284) executed by ONE lane: the codeword index of a part is known, so 32 lanes
+// expand 32 different parts at the same time (the entropy decoder does not depend on the result).
+// Writes 16-bit pulses (|y| <= K <= 128) and returns yy.
+__device__ __forceinline__ float cwrsi_lane(const PvqTable &T, int16_t *y, uint32_t n, uint32_t k, uint32_t i)
+{
+    int32_t yy = 0;
+    while (n > 2u) {
+        uint32_t p, k0;
+        int32_t s, val;
+        if (k >= n) {  // pvc.rs:196-231
+            uint32_t row = T.row[n];
+            p = T.data[row + k + 1u];
+            s = i >= p ? -1 : 0;
+            i -= (uint32_t)((int32_t)p & s);
+            k0 = k;
+            uint32_t q = T.data[row + n];
+            if (q > i) {
+                k = n;
+                do {
+                    k -= 1u;
+                    p = T.data[T.row[k] + n];
+                } while (p > i);
+            } else {
+                p = T.data[row + k];
+                while (p > i) {
+                    k -= 1u;
+                    p = T.data[row + k];
+                }
+            }
+            i -= p;
+            val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+            *y++ = (int16_t)val;
+            yy += val * val;
+        } else {  // pvc.rs:232-258
+            p = T.data[T.row[k] + n];
+            uint32_t q = T.data[T.row[k + 1u] + n];
+            if (p <= i && i < q) {
+                i -= p;
+                *y++ = 0;
+            } else {
+                s = i >= q ? -1 : 0;
+                i -= (uint32_t)((int32_t)q & s);
+                k0 = k;
+                do {
+                    k -= 1u;
+                    p = T.data[T.row[k] + n];
+                } while (p > i);
+                i -= p;
+                val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+                *y++ = (int16_t)val;
+                yy += val * val;
+            }
+        }
+        n -= 1u;
+    }
+    // n == 2 (pvc.rs:262-275)
+    uint32_t p = 2u * k + 1u;
+    int32_t s = i >= p ? -1 : 0;
+    i -= (uint32_t)((int32_t)p & s);
+    uint32_t k0 = k;
+    k = (i + 1u) >> 1;
+    if (k != 0u) i -= 2u * k - 1u;
+    int32_t val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+    *y++ = (int16_t)val;
+    yy += val * val;
+    // n == 1 (pvc.rs:277-281)
+    s = -(int32_t)i;
+    val = ((int32_t)k + s) ^ s;
+    *y = (int16_t)val;
+    yy += val * val;
     return (float)yy;
 }
 

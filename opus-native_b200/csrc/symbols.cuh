@@ -112,23 +112,54 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory plan of k_synth_symbols (per CTA of SYM_WARPS_PER_CTA warps):
+//   PVQ U(n,k) table 5088 B + row offsets 32 B | entry table 72 x 16 B | per warp: codeword
+//   indices 72 x 4 B, gains 72 x 4 B, side info 96 x 4 B, 16-bit pulses 2 x 960 x 2 B, packet bytes.
+constexpr int SYM_Y16 = 2 * 960;
+__host__ __device__ constexpr size_t synth_symbols_smem(uint32_t pkt_cap)
+{
+    return PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) +
+           (size_t)SYM_WARPS_PER_CTA * (SYNTH_MAX_ENTRIES * 8 + 96 * 4 + SYM_Y16 * 2 + pkt_cap);
+}
+
+// Three phases per warp (= per packet):
+//   A  serial, warp-uniform: flags, post-filter parameters, Laplace energies, fine bits and, for every
+//      PVQ part, only the codeword INDEX (decode_uint with host-precomputed alphabet split and
+//      reciprocal).  This is the true dependency chain of the entropy decoder.
+//   B  lane-parallel: the index -> pulse-vector expansion (cwrsi) never feeds back into the range
+//      decoder, so lane l expands parts l, l+32, l+64 independently and derives the part gain.
+//   C  cooperative: pulses x gain -> coefficients, coalesced stores.
 __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_symbols(SymbolArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
     uint16_t *s_row = reinterpret_cast<uint16_t *>(s_pvq + PVQ_TABLE_WORDS);
-    int32_t *s_y = reinterpret_cast<int32_t *>(s_row + 16) + (threadIdx.x >> 5) * Y_STAGE;
-    uint8_t *s_pkt = reinterpret_cast<uint8_t *>(reinterpret_cast<int32_t *>(s_row + 16) + SYM_WARPS_PER_CTA * Y_STAGE) +
-                     (threadIdx.x >> 5) * A.pkt_cap;
-    load_pvq_table(s_pvq, s_row);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t item = blockIdx.x * SYM_WARPS_PER_CTA + (threadIdx.x >> 5);
+    SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(s_row + 16);
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) +
+                     (size_t)warp * (SYNTH_MAX_ENTRIES * 8 + 96 * 4 + SYM_Y16 * 2 + A.pkt_cap);
+    uint32_t *s_idx = reinterpret_cast<uint32_t *>(wbase);
+    float *s_gain = reinterpret_cast<float *>(s_idx + SYNTH_MAX_ENTRIES);
+    uint32_t *s_side = reinterpret_cast<uint32_t *>(s_gain + SYNTH_MAX_ENTRIES);
+    int16_t *s_y = reinterpret_cast<int16_t *>(s_side + 96);
+    uint8_t *s_pkt = reinterpret_cast<uint8_t *>(s_y + SYM_Y16);
+
+    const int lm = A.lm, C = A.channels, nf = 120 << lm;
+    const int ne = g_tab.synth_n_entries[lm][C - 1];
+    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) s_pvq[i] = g_tab.pvq_u_data[i];
+    if (threadIdx.x < 15) s_row[threadIdx.x] = g_tab.pvq_u_row[threadIdx.x];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_ent);
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const uint32_t item = blockIdx.x * SYM_WARPS_PER_CTA + warp;
     if (item >= A.n_items) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-    const int lm = A.lm, C = A.channels, nf = 120 << lm;
     uint32_t len = A.lens[item];
     const uint8_t *src = A.arena + A.offsets[item];
-    opn_synth_side *side = A.side + stream;
     float *coef = A.coef ? A.coef + (size_t)stream * C * nf : nullptr;
     int32_t *yo = A.y_out ? A.y_out + (size_t)stream * C * nf : nullptr;
 
@@ -136,10 +167,10 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_symbols(Symbol
     if (A.has_toc && len > 0u) {
         // TOC checks a host caller does with query_packet_* (src/lib.rs:219-325) before decode_frame
         const uint32_t toc = __ldg(src);
-        if ((toc & 0x80u) == 0u) status = OPN_ERR_UNIMPLEMENTED;                       // SILK / hybrid
-        else if ((toc & 0x3u) != 0u) status = OPN_ERR_UNIMPLEMENTED;                   // multi-frame: host path only
+        if ((toc & 0x80u) == 0u) status = OPN_ERR_UNIMPLEMENTED;                         // SILK / hybrid
+        else if ((toc & 0x3u) != 0u) status = OPN_ERR_UNIMPLEMENTED;                     // multi-frame: host path only
         else if ((int)((toc >> 3) & 0x3u) != lm) status = OPN_ERR_FRAME_SIZE_TOO_SMALL;  // frame size != call's
-        else if (((toc & 0x4u) ? 2 : 1) != C) status = OPN_ERR_UNIMPLEMENTED;          // mono<->stereo mapping
+        else if (((toc & 0x4u) ? 2 : 1) != C) status = OPN_ERR_UNIMPLEMENTED;            // mono<->stereo mapping
         src += 1;
         len -= 1u;
     }
@@ -148,102 +179,119 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_symbols(Symbol
     if (lane == 0u) A.status[stream] = status;
     if (status < 0) return;
 
-    // zero side info (lanes cooperate: the struct is 95 words)
-    {
-        uint32_t *sw = reinterpret_cast<uint32_t *>(side);
-        for (uint32_t i = lane; i < sizeof(opn_synth_side) / 4u; i += 32u) sw[i] = 0u;
-        __syncwarp();
+    for (uint32_t i = lane; i < 96u; i += 32u) s_side[i] = 0u;
+    opn_synth_side *sd = reinterpret_cast<opn_synth_side *>(s_side);  // 95 words, staged in shared memory
+    bool zero_frame = status == ITEM_LOST;
+    uint32_t n_pulses = 0u;
+    __syncwarp();
+
+    if (!zero_frame) {
+        // ------------------------------------------------------------------ phase A
+        stage_bytes(s_pkt, src, len, lane);
+        RangeDec d;
+        d.init(s_pkt, len);
+        const uint32_t silence = d.bit_logp(15u);
+        if (silence) {
+            zero_frame = true;
+            if (lane == 0u) sd->silence = 1;
+        } else {
+            const uint32_t postfilter = d.bit_logp(1u);
+            uint32_t octave = 0u, period = 0u, gain_idx = 0u, tapset = 0u;
+            if (postfilter) {
+                octave = d.uint(6u);
+                period = (16u << octave) + d.bits(4u + octave) - 1u;
+                gain_idx = d.bits(3u);
+                tapset = d.icdf(g_tab.tapset_icdf, 2u);
+            }
+            const uint32_t transient = d.bit_logp(3u);
+            const uint32_t intra = d.bit_logp(3u);
+            if (lane == 0u) {
+                sd->postfilter = (int32_t)postfilter;
+                sd->octave = (int32_t)octave;
+                sd->period = (int32_t)period;
+                sd->gain_idx = (int32_t)gain_idx;
+                sd->tapset = (int32_t)tapset;
+                sd->transient = (int32_t)transient;
+                sd->intra = (int32_t)intra;
+            }
+            for (int b = 0; b < 21; b++) {
+                const uint32_t decay = 6000u + 400u * (uint32_t)b;
+                const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;  // mod.rs:530-534
+                for (int c = 0; c < C; c++) {
+                    const int32_t v = d.laplace(fs0, decay);
+                    if (lane == 0u) sd->coarse[c][b] = v;
+                }
+            }
+            for (int b = 0; b < 21; b++)
+                for (int c = 0; c < C; c++) {
+                    const uint32_t v = d.bits(2u);
+                    if (lane == 0u) sd->fine[c][b] = (int32_t)v;
+                }
+            for (int e = 0; e < ne; e++) {
+                const SynthEntry E = s_ent[e];
+                uint32_t v;
+                if (E.n == 1) {
+                    v = d.bits(1u);
+                    n_pulses += 1u;
+                } else {
+                    v = d.uint_precomputed(E.ft_minus1, E.ft1, E.ftb, E.magic, E.sh);
+                    n_pulses += E.k;
+                }
+                if (lane == 0u) s_idx[e] = v;
+            }
+        }
+        if (lane == 0u) {
+            sd->final_rng = d.rng;
+            sd->tell_frac = d.tell_frac();
+            sd->n_pulses = zero_frame ? 0u : n_pulses;
+        }
     }
-    if (status == ITEM_LOST) {
+    __syncwarp();
+    // side info: one coalesced copy
+    {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(A.side + stream);
+        for (uint32_t i = lane; i < sizeof(opn_synth_side) / 4u; i += 32u) dst[i] = s_side[i];
+    }
+    if (zero_frame) {
         if (coef) for (int i = lane; i < C * nf; i += 32) coef[i] = 0.0f;
         if (yo) for (int i = lane; i < C * nf; i += 32) yo[i] = 0;
         return;
     }
-    stage_bytes(s_pkt, src, len, lane);
-    PvqTable T{s_pvq, s_row};
-    RangeDec d;
-    d.init(s_pkt, len);
-
-    const uint32_t silence = d.bit_logp(15u);
-    uint32_t n_pulses = 0u;
-    if (silence) {
-        if (coef) for (int i = lane; i < C * nf; i += 32) coef[i] = 0.0f;
-        if (yo) for (int i = lane; i < C * nf; i += 32) yo[i] = 0;
-        if (lane == 0u) side->silence = 1;
-    } else {
-        const uint32_t postfilter = d.bit_logp(1u);
-        uint32_t octave = 0u, period = 0u, gain_idx = 0u, tapset = 0u;
-        if (postfilter) {
-            octave = d.uint(6u);
-            period = (16u << octave) + d.bits(4u + octave) - 1u;
-            gain_idx = d.bits(3u);
-            tapset = d.icdf(g_tab.tapset_icdf, 2u);
-        }
-        const uint32_t transient = d.bit_logp(3u);
-        const uint32_t intra = d.bit_logp(3u);
-        if (lane == 0u) {
-            side->postfilter = (int32_t)postfilter;
-            side->octave = (int32_t)octave;
-            side->period = (int32_t)period;
-            side->gain_idx = (int32_t)gain_idx;
-            side->tapset = (int32_t)tapset;
-            side->transient = (int32_t)transient;
-            side->intra = (int32_t)intra;
-        }
-        // coarse energy: 21 bands x C Laplace symbols; lane (b*C+c)%32 keeps the value to store
-        for (int b = 0; b < 21; b++)
-            for (int c = 0; c < C; c++) {
-                const uint32_t decay = 6000u + 400u * (uint32_t)b;
-                // get_start_freq (src/range_coder/mod.rs:530-534)
-                const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;
-                int32_t v = d.laplace(fs0, decay);
-                if (lane == 0u) side->coarse[c][b] = v;
+    // ------------------------------------------------------------------ phase B
+    {
+        PvqTable T{s_pvq, s_row};
+        for (int e = lane; e < ne; e += 32) {
+            const SynthEntry E = s_ent[e];
+            const uint32_t v = s_idx[e];
+            float g;
+            if (E.n == 1) {
+                s_y[E.base] = v ? (int16_t)-1 : (int16_t)1;
+                g = 0.03125f;
+            } else {
+                const float yy = cwrsi_lane(T, s_y + E.base, E.n, E.k, v);
+                g = 0.03125f / sqrtf(yy);
             }
-        for (int b = 0; b < 21; b++)
-            for (int c = 0; c < C; c++) {
-                uint32_t v = d.bits(2u);
-                if (lane == 0u) side->fine[c][b] = (int32_t)v;
-            }
-        // bins above the last band stay zero
-        {
-            const int top = 100 << lm;
-            for (int c = 0; c < C; c++)
-                for (int i = top + (int)lane; i < nf; i += 32) {
-                    if (coef) coef[c * nf + i] = 0.0f;
-                    if (yo) yo[c * nf + i] = 0;
-                }
+            s_gain[e] = g;
         }
-        for (int b = 0; b < 21; b++)
-            for (int c = 0; c < C; c++) {
-                const int n = g_tab.synth_sched[lm][b][0], parts = g_tab.synth_sched[lm][b][1],
-                          k = g_tab.synth_sched[lm][b][2];
-                const int base = c * nf + ((int)g_tab.e_bands[b] << lm);
-                if (n == 1) {
-                    const uint32_t sign = d.bits(1u);
-                    if (lane == 0u) {
-                        if (coef) coef[base] = sign ? -0.03125f : 0.03125f;
-                        if (yo) yo[base] = sign ? -1 : 1;
-                    }
-                    n_pulses += 1u;
-                    continue;
-                }
-                for (int p = 0; p < parts; p++) {
-                    const float yy = decode_pulses_warp(d, T, s_y, (uint32_t)n, (uint32_t)k, lane);
-                    const float g = 0.03125f / sqrtf(yy);
-                    for (int j = lane; j < n; j += 32) {
-                        const int32_t yv = s_y[j];
-                        if (coef) coef[base + p * n + j] = (float)yv * g;
-                        if (yo) yo[base + p * n + j] = yv;
-                    }
-                    __syncwarp();
-                    n_pulses += (uint32_t)k;
-                }
-            }
     }
-    if (lane == 0u) {
-        side->final_rng = d.rng;
-        side->tell_frac = d.tell_frac();
-        side->n_pulses = n_pulses;
+    __syncwarp();
+    // ------------------------------------------------------------------ phase C
+    {
+        const int top = 100 << lm;  // bins above the last band stay zero
+        for (int c = 0; c < C; c++)
+            for (int i = top + (int)lane; i < nf; i += 32) {
+                if (coef) coef[c * nf + i] = 0.0f;
+                if (yo) yo[c * nf + i] = 0;
+            }
+        for (int e = 0; e < ne; e++) {
+            const SynthEntry E = s_ent[e];
+            const float g = s_gain[e];
+            for (int j = lane; j < (int)E.n; j += 32) {
+                const int32_t yv = s_y[E.base + j];
+                if (coef) coef[E.base + j] = (float)yv * g;
+                if (yo) yo[E.base + j] = yv;
+            }
+        }
     }
 }
 
