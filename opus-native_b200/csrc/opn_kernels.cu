@@ -2,6 +2,7 @@
 #include <mutex>
 
 #include "imdct.cuh"
+#include "imdct_warp.cuh"
 #include "opn_tables.h"
 #include "softclip.cuh"
 #include "symbols.cuh"
@@ -11,6 +12,23 @@ namespace opn {
 
 static std::mutex g_tab_mutex;
 static bool g_tab_done[64];
+
+template <int LM, int C> static cudaError_t set_carveout()
+{
+    return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static cudaError_t set_warp_kernel_attributes()
+{
+    cudaError_t e = set_carveout<0, 1>();
+    if (e == cudaSuccess) e = set_carveout<0, 2>();
+    if (e == cudaSuccess) e = set_carveout<1, 1>();
+    if (e == cudaSuccess) e = set_carveout<1, 2>();
+    if (e == cudaSuccess) e = set_carveout<2, 1>();
+    if (e == cudaSuccess) e = set_carveout<2, 2>();
+    if (e == cudaSuccess) e = set_carveout<3, 1>();
+    if (e == cudaSuccess) e = set_carveout<3, 2>();
+    return e;
+}
 
 cudaError_t upload_tables(int device)
 {
@@ -24,6 +42,12 @@ cudaError_t upload_tables(int device)
         h.window_sq[i] = OPN_WINDOW[i] * OPN_WINDOW[i];  // host f32 product, single rounding
     }
     for (int i = 0; i < 480; i++) h.twiddles[i] = make_float2(OPN_TWIDDLES[2 * i], OPN_TWIDDLES[2 * i + 1]);
+    for (int s = 0, trigp = 0, nn = 1920; s < 4; s++) {
+        const int n4 = 480 >> s;
+        for (int i = 0; i < n4; i++) h.trig_pair[trig_pair_off(s) + i] = make_float2(OPN_TRIG[trigp + i], OPN_TRIG[trigp + n4 + i]);
+        nn >>= 1;
+        trigp += nn;
+    }
     for (int i = 0; i < 480; i++) h.bitrev[0][i] = OPN_BITREV_480[i];
     for (int i = 0; i < 240; i++) h.bitrev[1][i] = OPN_BITREV_240[i];
     for (int i = 0; i < 120; i++) h.bitrev[2][i] = OPN_BITREV_120[i];
@@ -70,6 +94,10 @@ cudaError_t upload_tables(int device)
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
     if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_tw, h.twiddles, sizeof(h.twiddles));
+    if (e != cudaSuccess) return e;
+    e = set_warp_kernel_attributes();
+    if (e != cudaSuccess) return e;
     // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
     e = cudaFuncSetAttribute(k_rangedec_script, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
@@ -77,6 +105,12 @@ cudaError_t upload_tables(int device)
     if (e != cudaSuccess) return e;
     g_tab_done[device] = true;
     return cudaSuccess;
+}
+
+template <int LM, int C> static cudaError_t launch_imdct_w(const ImdctArgs &a, cudaStream_t st)
+{
+    k_imdct_post_w<LM, C><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
+    return cudaGetLastError();
 }
 
 static size_t symbols_smem(uint32_t pkt_cap)
@@ -106,17 +140,41 @@ cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
 cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
-    const size_t smem = (size_t)a.channels * (SY_FLOATS * 4 + SF_CPLX * 8);
-    k_imdct_post<<<a.n_items, IM_TPC * a.channels, smem, st>>>(a);
-    return cudaGetLastError();
+    switch (a.lm * 2 + (a.channels - 1)) {
+    case 0: return launch_imdct_w<0, 1>(a, st);
+    case 1: return launch_imdct_w<0, 2>(a, st);
+    case 2: return launch_imdct_w<1, 1>(a, st);
+    case 3: return launch_imdct_w<1, 2>(a, st);
+    case 4: return launch_imdct_w<2, 1>(a, st);
+    case 5: return launch_imdct_w<2, 2>(a, st);
+    case 6: return launch_imdct_w<3, 1>(a, st);
+    case 7: return launch_imdct_w<3, 2>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
                             int nblk, cudaStream_t st)
 {
     if (n_rows == 0) return cudaSuccess;
-    const size_t smem = (960 + 1024) * 4 + 480 * 8;
-    k_op_imdct<<<n_rows, IM_TPC, smem, st>>>(in, in_stride, out, out_stride, shift, nblk);
+    const int lm = nblk == 1 ? 3 - shift : nblk == 2 ? 1 : nblk == 4 ? 2 : 3;
+    const size_t smem = w_smem_bytes(lm, 1);
+    if (nblk == 1) {
+        switch (shift) {
+        case 0: k_op_imdct_w<0, 1><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        case 1: k_op_imdct_w<1, 1><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        case 2: k_op_imdct_w<2, 1><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        default: k_op_imdct_w<3, 1><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        }
+    } else {
+        if (shift != 3) return cudaErrorInvalidValue;  // short blocks are always 120-bin MDCTs
+        switch (nblk) {
+        case 2: k_op_imdct_w<3, 2><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        case 4: k_op_imdct_w<3, 4><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        case 8: k_op_imdct_w<3, 8><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
+        default: return cudaErrorInvalidValue;
+        }
+    }
     return cudaGetLastError();
 }
 

@@ -177,3 +177,36 @@ def test_synth_fill_is_deterministic_and_threaded():
     assert np.array_equal(a, b)
     pkt, _ = opn.synth_packet(5 + 7, 2 + 1, 3, 2, 160)
     assert np.array_equal(a[1, 7], pkt)
+
+
+def test_digit_reversal_closed_form():
+    """imdct_warp.cuh resolves the kiss-fft digit reversal at compile time: the aligned group g (of
+    GS = 32 >> shift positions) holds exactly the inputs i = r + 15 q, r = g // 3 + 5 (g % 3), and the
+    in-group position p maps to q by w_qmap.  Check that closed form against the generated tables."""
+    src = open(os.path.join(ROOT, "opus-native_b200", "csrc", "opn_tables.h")).read()
+
+    def table(name):
+        body = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, src, re.S).group(1)
+        return [int(v) for v in body.replace("\n", " ").split(",") if v.strip()]
+
+    def qmap(shift, p):
+        if shift == 0:
+            return (p >> 3) + 4 * ((p >> 2) & 1) + 8 * (p & 3)
+        if shift == 1:
+            return (p >> 2) + 4 * (p & 3)
+        if shift == 2:
+            return (p >> 2) + 2 * (p & 3)
+        return p
+
+    for shift, nfft in [(0, 480), (1, 240), (2, 120), (3, 60)]:
+        bitrev = table("OPN_BITREV_%d" % nfft)
+        gs = 32 >> shift
+        seen = set()
+        for g in range(15):
+            j1, j2 = divmod(g, 3)
+            r = j1 + 5 * j2
+            for p in range(gs):
+                i = r + 15 * qmap(shift, p)
+                assert bitrev[i] == gs * g + p
+                seen.add(i)
+        assert len(seen) == nfft
