@@ -1,4 +1,4 @@
-// imdct_warp.cuh -- kernel 1, second generation: one WARP decodes one stream (both channels).
+// imdct_warp.cuh -- kernel 1, warp-per-stream generation: one WARP decodes one stream (both channels).
 //
 // Device mirror of Mdct::backward (src/celt/mdct.rs:159-260), KissFft::process and its
 // butterflies (src/celt/kiss_fft.rs:24-243), comb_filter_inplace
@@ -20,18 +20,17 @@
 //       pass B  lane u < GS (x block x channel): 15 elements, radix-3 then radix-5, post-rotation
 //               fused on the registers (FFT output k yields out[2k] and out[n2-1-2k] from the same
 //               two trig values).
-//   * A warp never waits for another warp: all hand-offs are __syncwarp(), CTAs are single warps,
-//     13 streams are resident per SM and slip past each other (memory phases of one stream overlap
-//     FP32 phases of the others).
-//   * Coefficient rows arrive by TMA (cp.async.bulk, one 3840-byte row per channel) into the
-//     region the output row later occupies; the comb history is staged from the interleaved PCM
-//     ring with float4 loads into the region the transpose used.
-//
-// Shared memory per channel (floats):  [ A: 1024 | O: nf + 60 ]
-//   A = transpose buffer (float2, 15*(GS+1) per block, padded so both passes are conflict-free),
-//       later y[-1024 .. -1] (post-filter history; ends exactly where O starts, so a tap at any
-//       signed index is one address)
-//   O = coefficient row (TMA destination), later out[0 .. nf+60): carry-in/TDAC, PCM, carry-out.
+//   * A warp never waits for another warp: all hand-offs are __syncwarp().  A CTA is W_WPC
+//     independent warps that only share read-only tables (trig pairs, twiddles, window) staged in
+//     shared memory once per CTA.
+//   * Coefficient rows arrive by TMA (cp.async.bulk, one 3840-byte row per channel) into the very
+//     row that later holds the output; the transpose buffer aliases that row too (every lane has its
+//     inputs in registers before the first transposed element is written), so a stream needs
+//     C x (nf + 60) floats of shared memory and ~20 streams are resident per SM.
+//   * The post-filter reads its history straight from the interleaved PCM ring in HBM/L2 (one
+//     float2 = both channels of a tap).  History-only spans of the frame have no recursion and are
+//     filtered in one parallel sweep, 4 samples per lane; only the truly recursive remainder is
+//     swept in chunks, from shared memory.
 #pragma once
 #include "imdct.cuh"
 
@@ -40,10 +39,10 @@ namespace opn {
 // Twiddles addressed with compile-time indices (src/celt/kiss_fft.rs:341-582): constant bank.
 __constant__ float2 c_tw[480];
 
-constexpr int WA_FLOATS = 1024;  // region A
-__host__ __device__ constexpr int w_ch_floats(int lm) { return WA_FLOATS + (120 << lm) + 60; }
-__host__ __device__ constexpr size_t w_smem_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16; }
+constexpr int W_MAX_WPC = 8;  // warps (= streams) per CTA, at most
+__host__ __device__ constexpr int w_ch_floats(int lm) { return (120 << lm) + 60; }
 __host__ __device__ constexpr int trig_pair_off(int shift) { return shift == 0 ? 0 : shift == 1 ? 480 : shift == 2 ? 720 : 840; }
+__host__ __device__ constexpr size_t w_smem_bytes(int lm, int channels) { return (size_t)channels * (w_ch_floats(lm) + HIST_CAP) * 4 + 16; }
 
 // ---- TMA / mbarrier (single-CTA cluster) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,7 +159,7 @@ template <int SHIFT> __host__ __device__ constexpr int w_qmap(int p)
 }
 
 // Stages that stay inside one group of GS positions (execution order, kiss_fft.rs:38-52).
-template <int SHIFT> __device__ __forceinline__ void w_group_stages(float2 (&d)[32 >> SHIFT])
+template <int SHIFT> __device__ __forceinline__ void w_group_stages(float2 *d)
 {
     constexpr int GS = 32 >> SHIFT;
 #pragma unroll
@@ -185,60 +184,65 @@ template <int SHIFT> __device__ __forceinline__ void w_group_stages(float2 (&d)[
 }
 
 // Mdct::backward for the C channels of one stream, NBLK interleaved blocks of nfft = 480 >> SHIFT
-// (NBLK == 1: one long block; SHIFT == 3 and NBLK == 2^LM: transient frame).  On entry O holds the
-// coefficient rows; on exit O holds out[0 .. nf+60) after the TDAC mirror (mdct.rs:241-259).
-// `carry` is this lane's float4 of the previous tail (lane = 15*ch + k -> out[4k .. 4k+4)).
-template <int SHIFT, int NBLK, int C> __device__ __forceinline__ void w_imdct(float *sm, int lane, float4 carry)
+// (NBLK == 1: one long block; SHIFT == 3 and NBLK == 2^LM: transient frame).  `o` is channel 0's
+// row of CHF = nf + 60 floats (channel 1 follows): on entry it holds the coefficients, on exit
+// out[0 .. nf+60) after the TDAC mirror (mdct.rs:241-259).  `carry` is this lane's float4 of the
+// previous tail (lane = 15*ch + k -> out[4k .. 4k+4)).
+template <int SHIFT, int NBLK, int C>
+__device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const float2 *tpair, const float2 *tw, const float *win)
 {
     constexpr int GS = 32 >> SHIFT, N2 = 960 >> SHIFT;
     constexpr int NF = N2 * NBLK, E = GS * NBLK;
-    constexpr int CHF = WA_FLOATS + NF + 60;
-    // Transpose buffer: position pos of a block lives at pos + pos / PADG (one float2 of padding per
-    // PADG positions keeps the stride-GS writes of pass A and the unit-stride reads of pass B on
-    // distinct banks).  Eight short blocks only fit region A with the coarser padding.
-    constexpr int PADG = (GS == 4 && NBLK == 8) ? 16 : GS;
-    constexpr int XBLK = 15 * GS + (15 * GS + PADG - 1) / PADG;  // float2 per block
-    static_assert(2 * XBLK * NBLK <= WA_FLOATS, "transpose buffer must fit region A");
-    const float2 *tpair = g_tab.trig_pair + trig_pair_off(SHIFT);
+    constexpr int CHF = NF + 60;
+    // Transpose buffer (aliases the row): element `a` (= position inside the transform, plus 60 per
+    // short block) lives at a + a / PADG -- one float2 of padding per PADG elements keeps the
+    // stride-GS writes of pass A and the unit-stride reads of pass B on distinct banks.  Short blocks
+    // only fit the row with the coarser padding.
+    constexpr int PADG = NBLK > 1 ? 16 : GS;
+    constexpr int NFFT = 15 * GS;
+    static_assert(2 * (NFFT * NBLK + (NFFT * NBLK + PADG - 1) / PADG) <= CHF, "transpose buffer must fit the row");
 
     // ---------------------------------------------------------------- pass A
-    if (lane < 15 * C) {
+    {
+        const bool on = lane < 15 * C;
         const int ch = (C == 2 && lane >= 15) ? 1 : 0;
-        const int g = lane - 15 * ch;
+        const int g = on ? lane - 15 * ch : 0;
         const int j1 = g / 3, j2 = g - 3 * j1, r = j1 + 5 * j2;
-        const float *x = sm + ch * CHF + WA_FLOATS;
-        float2 *xc = reinterpret_cast<float2 *>(sm + ch * CHF) + GS * g + (GS * g) / PADG;  // p < GS <= PADG adds no pad
+        const float *x = o + ch * CHF;
         const float2 *tp = tpair + r;
+        float2 d[NBLK * GS];
+        if (on) {
 #pragma unroll
-        for (int blk = 0; blk < NBLK; blk++) {
-            float2 d[GS];
+            for (int blk = 0; blk < NBLK; blk++)
 #pragma unroll
-            for (int p = 0; p < GS; p++) {  // pre-rotation, mdct.rs:184-200
-                const int q = w_qmap<SHIFT>(p);
-                const float x0 = x[blk + NBLK * (2 * r) + NBLK * 30 * q];
-                const float x1 = x[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * q];
-                const float2 t = __ldg(tp + 15 * q);  // (trig[i], trig[n4 + i])
-                const float re = (x1 * t.x) + (x0 * t.y);
-                const float im = (x0 * t.x) - (x1 * t.y);
-                d[p] = make_float2(im, re);
+                for (int p = 0; p < GS; p++) {  // pre-rotation, mdct.rs:184-200
+                    const int q = w_qmap<SHIFT>(p);
+                    const float x0 = x[blk + NBLK * (2 * r) + NBLK * 30 * q];
+                    const float x1 = x[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * q];
+                    const float2 t = __ldg(tp + 15 * q);  // (trig[i], trig[n4 + i])
+                    const float re = (x1 * t.x) + (x0 * t.y);
+                    const float im = (x0 * t.x) - (x1 * t.y);
+                    d[blk * GS + p] = make_float2(im, re);
+                }
+        }
+        __syncwarp();  // every coefficient is in a register: the row may be overwritten
+        if (on) {
+            float2 *xc = reinterpret_cast<float2 *>(o + ch * CHF);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; blk++) {
+                w_group_stages<SHIFT>(d + blk * GS);
+                const int a = NFFT * blk + GS * g;  // p < GS <= PADG never crosses a padding boundary
+#pragma unroll
+                for (int p = 0; p < GS; p++) xc[a + a / PADG + p] = d[blk * GS + p];
             }
-            w_group_stages<SHIFT>(d);
-#pragma unroll
-            for (int p = 0; p < GS; p++) xc[blk * XBLK + p] = d[p];
         }
     }
     __syncwarp();
-    // coefficient rows are consumed: out[0..60) <- previous tail
-    if (lane < 15 * C) {
-        const int ch = (C == 2 && lane >= 15) ? 1 : 0;
-        *reinterpret_cast<float4 *>(sm + ch * CHF + WA_FLOATS + 4 * (lane - 15 * ch)) = carry;
-    }
     // ---------------------------------------------------------------- pass B
     {
         constexpr int S3 = 5 << SHIFT;  // twiddle stride of the radix-3 stage
         const int col = lane % E, ch0 = lane / E;
         const int blk = col / GS, u = col % GS;
-        const float2 *tw = g_tab.twiddles;
         const float2 w31 = __ldg(tw + u * S3), w32 = __ldg(tw + 2 * u * S3);
         float2 w5[3][4];
 #pragma unroll
@@ -248,51 +252,98 @@ template <int SHIFT, int NBLK, int C> __device__ __forceinline__ void w_imdct(fl
         const float epi3y = c_tw[160].y;
         const float2 ya = c_tw[96], yb = c_tw[192];
         constexpr int ITER = (C * E + 31) / 32;
-#pragma unroll
+#pragma unroll 1
         for (int it = 0; it < ITER; it++) {
             const int ch = ch0 + it * (32 / E);
-            if (ch < C) {
-                const float2 *xc = reinterpret_cast<const float2 *>(sm + ch * CHF) + blk * XBLK + u;
-                float2 d[15];
+            const bool on = ch < C;
+            float2 d[15];
+            if (on) {
+                const float2 *xc = reinterpret_cast<const float2 *>(o + ch * CHF);
 #pragma unroll
-                for (int j = 0; j < 15; j++) d[j] = xc[GS * j + (GS * j) / PADG];  // u < GS adds no pad
+                for (int j = 0; j < 15; j++) {
+                    if constexpr (NBLK == 1) {
+                        d[j] = xc[u + GS * j + (GS * j) / PADG];  // u < GS = PADG adds no pad
+                    } else {
+                        const int a = NFFT * blk + GS * j + u;
+                        d[j] = xc[a + a / PADG];
+                    }
+                }
+            }
+            __syncwarp();  // transposed elements are in registers: the row may be overwritten
+            if (on) {
 #pragma unroll
                 for (int a = 0; a < 5; a++) r_bfly3(d[3 * a], d[3 * a + 1], d[3 * a + 2], w31, w32, epi3y);
 #pragma unroll
                 for (int jj = 0; jj < 3; jj++)
                     r_bfly5(d[jj], d[jj + 3], d[jj + 6], d[jj + 9], d[jj + 12], w5[jj][0], w5[jj][1], w5[jj][2], w5[jj][3], ya, yb);
                 // post-rotation and de-shuffle, mdct.rs:205-238: FFT output k = u + GS*j
-                float *o = sm + ch * CHF + WA_FLOATS + N2 * blk + 60;
+                float *ob = o + ch * CHF + N2 * blk + 60;
                 const float2 *tp = tpair + u;
 #pragma unroll
                 for (int j = 0; j < 15; j++) {
                     const float2 t = __ldg(tp + GS * j);
-                    o[2 * u + 2 * GS * j] = (d[j].y * t.x) + (d[j].x * t.y);
-                    o[N2 - 1 - 2 * u - 2 * GS * j] = (d[j].y * t.y) - (d[j].x * t.x);
+                    ob[2 * u + 2 * GS * j] = (d[j].y * t.x) + (d[j].x * t.y);
+                    ob[N2 - 1 - 2 * u - 2 * GS * j] = (d[j].y * t.y) - (d[j].x * t.x);
                 }
             }
         }
     }
+    // out[0..60) <- previous tail
+    if (lane < 15 * C) {
+        const int ch = (C == 2 && lane >= 15) ? 1 : 0;
+        *reinterpret_cast<float4 *>(o + ch * CHF + 4 * (lane - 15 * ch)) = carry;
+    }
     __syncwarp();
     // ---------------------------------------------------------------- TDAC mirror, mdct.rs:241-259
     for (int w = lane; w < C * NBLK * 60; w += 32) {
-        const int ch = w / (NBLK * 60), rem = w - ch * (NBLK * 60);
-        const int blk = rem / 60, i = rem - blk * 60;
-        float *o = sm + ch * CHF + WA_FLOATS + N2 * blk;
-        const float x0 = o[119 - i], x1 = o[i];
-        const float w0 = __ldg(&g_tab.window[i]), w1 = __ldg(&g_tab.window[119 - i]);
-        o[i] = (w1 * x1) - (w0 * x0);
-        o[119 - i] = (w0 * x1) + (w1 * x0);
+        int ch = 0, blk = 0, i = w;
+        if constexpr (NBLK == 1) {
+            if (C == 2 && w >= 60) { ch = 1; i = w - 60; }
+        } else {
+            ch = w / (NBLK * 60);
+            const int rem = w - ch * (NBLK * 60);
+            blk = rem / 60;
+            i = rem - blk * 60;
+        }
+        float *ob = o + ch * CHF + N2 * blk;
+        const float x0 = ob[119 - i], x1 = ob[i];
+        const float w0 = __ldg(win + i), w1 = __ldg(win + 119 - i);
+        ob[i] = (w1 * x1) - (w0 * x0);
+        ob[119 - i] = (w0 * x1) + (w1 * x0);
     }
     __syncwarp();
 }
 
-// comb_filter_inplace (comb_filter/mod.rs:130-193) for the C channels of one stream; channel ch's
-// samples are y + ch*chf, its history directly below.  Recursive filter: the warp sweeps the frame
-// in chunks of W = min(period) - 2 <= 32 samples, inside which every tap lies before the chunk.
+// ---- post-filter -------------------------------------------------------------------------------
+// One tap of the C channels at signed sample index idx relative to the frame start: idx >= 0 is this
+// frame (planar rows, already filtered where the recursion needs it), idx < 0 is history: the last
+// T+2 samples of the interleaved PCM ring, staged in shared memory by TMA while the FFT runs.
+template <int C> struct WTapSrc {
+    const float *y;   // channel 0 row; channel 1 at y + chf
+    int chf;
+    const float *h;   // staged history, interleaved like the ring: sample idx (< 0) of channel c at h[C*idx + c]
+    __device__ __forceinline__ float2 hist(int idx) const
+    {
+        if (C == 2) return *reinterpret_cast<const float2 *>(h + 2 * idx);
+        return make_float2(h[idx], 0.0f);
+    }
+    __device__ __forceinline__ float2 frame(int idx) const { return make_float2(y[idx], C == 2 ? y[chf + idx] : 0.0f); }
+    __device__ __forceinline__ float2 any(int idx) const { return idx < 0 ? hist(idx) : frame(idx); }
+};
+
+// comb_filter_const_inplace term order (fallback.rs:46-51): y + g0*x2 + g1*(x1+x3) + g2*(x0+x4)
+__device__ __forceinline__ float comb5(float y, float x0, float x1, float x2, float x3, float x4, float g0, float g1, float g2)
+{
+    return y + (g0 * x2) + (g1 * (x1 + x3)) + (g2 * (x0 + x4));
+}
+
+// comb_filter_inplace (comb_filter/mod.rs:130-193) for the C channels of one stream.  The filter is
+// recursive, y[i] depends on y[i-T-2 .. i-T+2]; wherever those taps are history the samples are
+// independent and are filtered in parallel, the rest is swept in chunks no longer than T-2.
+// A tap set whose gain is exactly zero contributes +-0 to every sum and is skipped.
 template <int C>
-__device__ __forceinline__ void w_comb(float *y, int chf, int t0, int t1, int n, float g0, float g1, int tap0, int tap1, int overlap,
-                                       int lane)
+__device__ __forceinline__ void w_comb(float *y, int chf, const float *hist_end, int t0, int t1, int n, float g0, float g1, int tap0,
+                                       int tap1, int overlap, int lane, const float *win_sq)
 {
     if (g0 == 0.0f && g1 == 0.0f) return;
     t0 = max(t0, 15);
@@ -302,42 +353,179 @@ __device__ __forceinline__ void w_comb(float *y, int chf, int t0, int t1, int n,
     const float g10 = g1 * g_tab.comb_gains[tap1 * 3], g11 = g1 * g_tab.comb_gains[tap1 * 3 + 1],
                 g12 = g1 * g_tab.comb_gains[tap1 * 3 + 2];
     if (fabsf(g0 - g1) < 1.1920929e-7f && t0 == t1 && tap0 == tap1) overlap = 0;
-    {  // cross-fade part (mod.rs:162-179)
-        const int W = min(min(t0, t1) - 2, 32);
-        for (int base = 0; base < overlap; base += W) {
-            const int i = base + lane;
-            if (lane < W && i < overlap) {
-                const float f = __ldg(&g_tab.window_sq[i]);
-                const float a0 = (1.0f - f) * g00, a1 = (1.0f - f) * g01, a2 = (1.0f - f) * g02;
-                const float b0 = f * g10, b1 = f * g11, b2 = f * g12;
+    const WTapSrc<C> src{y, chf, hist_end};
+    const bool has0 = g0 != 0.0f, has1 = g1 != 0.0f;
+
+    // ---- cross-fade part (mod.rs:162-179): samples [0, overlap)
+    if (overlap > 0) {
+        const int tmin = min(has0 ? t0 : 1 << 20, has1 ? t1 : 1 << 20);
+        // [0, pre): every tap of every live set is history -> independent samples, 4 per lane
+        const int pre = min(overlap, tmin - 2) & ~3;
+        {
+            const int i0 = 4 * lane;
+            if (i0 < pre) {
+                float2 a[8], b[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    a[k] = has0 ? src.hist(i0 - t0 - 2 + k) : make_float2(0.f, 0.f);
+                    b[k] = has1 ? src.hist(i0 - t1 - 2 + k) : make_float2(0.f, 0.f);
+                }
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    float *yc = y + c * chf;
-                    const float x0 = yc[i - t1 + 2], x1 = yc[i - t1 + 1], x2 = yc[i - t1], x3 = yc[i - t1 - 1], x4 = yc[i - t1 - 2];
-                    float acc = yc[i];
-                    acc = acc + (a0 * yc[i - t0]);
-                    acc = acc + (a1 * (yc[i - t0 + 1] + yc[i - t0 - 1]));
-                    acc = acc + (a2 * (yc[i - t0 + 2] + yc[i - t0 - 2]));
-                    acc = acc + (b0 * x2);
-                    acc = acc + (b1 * (x1 + x3));
-                    acc = acc + (b2 * (x0 + x4));
-                    yc[i] = acc;
+                    float4 v = *reinterpret_cast<float4 *>(y + c * chf + i0);
+                    float *vv = reinterpret_cast<float *>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float f = __ldg(win_sq + i0 + e);
+                        float acc = vv[e];
+                        if (has0) {
+                            const float x0 = c ? a[e + 4].y : a[e + 4].x, x1 = c ? a[e + 3].y : a[e + 3].x, x2 = c ? a[e + 2].y : a[e + 2].x,
+                                        x3 = c ? a[e + 1].y : a[e + 1].x, x4 = c ? a[e].y : a[e].x;
+                            acc = acc + (((1.0f - f) * g00) * x2);
+                            acc = acc + (((1.0f - f) * g01) * (x1 + x3));
+                            acc = acc + (((1.0f - f) * g02) * (x0 + x4));
+                        }
+                        if (has1) {
+                            const float x0 = c ? b[e + 4].y : b[e + 4].x, x1 = c ? b[e + 3].y : b[e + 3].x, x2 = c ? b[e + 2].y : b[e + 2].x,
+                                        x3 = c ? b[e + 1].y : b[e + 1].x, x4 = c ? b[e].y : b[e].x;
+                            acc = acc + ((f * g10) * x2);
+                            acc = acc + ((f * g11) * (x1 + x3));
+                            acc = acc + ((f * g12) * (x0 + x4));
+                        }
+                        vv[e] = acc;
+                    }
+                    *reinterpret_cast<float4 *>(y + c * chf + i0) = v;
+                }
+            }
+        }
+        __syncwarp();
+        // [pre, overlap): chunks of W <= tmin - 2 samples, one per lane; taps from wherever they live
+        const int W = min(tmin - 2, 32);
+        for (int base = pre; base < overlap; base += W) {
+            const int i = base + lane;
+            if (lane < W && i < overlap) {
+                const float f = __ldg(win_sq + i);
+                float2 a[5], b[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    a[k] = has0 ? src.any(i - t0 - 2 + k) : make_float2(0.f, 0.f);
+                    b[k] = has1 ? src.any(i - t1 - 2 + k) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float acc = y[c * chf + i];
+                    if (has0) {
+                        acc = acc + (((1.0f - f) * g00) * (c ? a[2].y : a[2].x));
+                        acc = acc + (((1.0f - f) * g01) * ((c ? a[3].y : a[3].x) + (c ? a[1].y : a[1].x)));
+                        acc = acc + (((1.0f - f) * g02) * ((c ? a[4].y : a[4].x) + (c ? a[0].y : a[0].x)));
+                    }
+                    if (has1) {
+                        acc = acc + ((f * g10) * (c ? b[2].y : b[2].x));
+                        acc = acc + ((f * g11) * ((c ? b[3].y : b[3].x) + (c ? b[1].y : b[1].x)));
+                        acc = acc + ((f * g12) * ((c ? b[4].y : b[4].x) + (c ? b[0].y : b[0].x)));
+                    }
+                    y[c * chf + i] = acc;
                 }
             }
             __syncwarp();
         }
     }
-    if (g1 == 0.0f) return;
-    {  // constant part (fallback.rs:32-53)
+    if (!has1) return;
+
+    // ---- constant part (fallback.rs:32-53): samples [overlap, n)
+    // (1) history-only span [overlap, hend): no recursion; 4 samples per lane, 128 per sweep
+    int at = overlap;  // overlap is 0 or 120: a multiple of 4
+    {
+        const int hend = overlap + ((max(min(n, t1 - 2) - overlap, 0)) & ~3);
+        for (int i0 = at + 4 * lane; i0 < hend; i0 += 128) {
+            float2 b[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) b[k] = src.hist(i0 - t1 - 2 + k);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                float4 v = *reinterpret_cast<float4 *>(y + c * chf + i0);
+                v.x = comb5(v.x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, c ? b[1].y : b[1].x, c ? b[0].y : b[0].x, g10, g11, g12);
+                v.y = comb5(v.y, c ? b[5].y : b[5].x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, c ? b[1].y : b[1].x, g10, g11, g12);
+                v.z = comb5(v.z, c ? b[6].y : b[6].x, c ? b[5].y : b[5].x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, g10, g11, g12);
+                v.w = comb5(v.w, c ? b[7].y : b[7].x, c ? b[6].y : b[6].x, c ? b[5].y : b[5].x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, g10, g11, g12);
+                *reinterpret_cast<float4 *>(y + c * chf + i0) = v;
+            }
+        }
+        at = max(at, hend);
+        __syncwarp();
+    }
+    // (2) the few samples whose taps straddle the frame start: [at, mid), mid = first multiple of 4
+    //     with every tap inside the frame.  mid - at <= 10 <= t1 - 2, so they are independent too.
+    {
+        const int mid = min(n, max(at, (t1 + 2 + 3) & ~3));
+        const int i = at + lane;
+        if (i < mid) {
+            float2 b[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) b[k] = src.any(i - t1 - 2 + k);
+#pragma unroll
+            for (int c = 0; c < C; c++)
+                y[c * chf + i] = comb5(y[c * chf + i], c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, c ? b[1].y : b[1].x,
+                                       c ? b[0].y : b[0].x, g10, g11, g12);
+        }
+        at = mid;
+        __syncwarp();
+    }
+    // (3) recursive remainder [at, n): every tap is in shared memory; chunk = 32*V <= t1 - 2 samples,
+    //     V = 4 or 2 consecutive samples per lane when the period allows (`at` is a multiple of 4)
+    if (t1 - 2 >= 128) {
+        const int vend = at + ((n - at) & ~3);
+        for (int base = at; base < vend; base += 128) {
+            const int i0 = base + 4 * lane;
+            if (i0 < vend) {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float *yc = y + c * chf;
+                    float t[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) t[k] = yc[i0 - t1 - 2 + k];
+                    float4 v = *reinterpret_cast<float4 *>(yc + i0);
+                    v.x = comb5(v.x, t[4], t[3], t[2], t[1], t[0], g10, g11, g12);
+                    v.y = comb5(v.y, t[5], t[4], t[3], t[2], t[1], g10, g11, g12);
+                    v.z = comb5(v.z, t[6], t[5], t[4], t[3], t[2], g10, g11, g12);
+                    v.w = comb5(v.w, t[7], t[6], t[5], t[4], t[3], g10, g11, g12);
+                    *reinterpret_cast<float4 *>(yc + i0) = v;
+                }
+            }
+            __syncwarp();
+        }
+        at = vend;
+    } else if (t1 - 2 >= 64) {
+        const int vend = at + ((n - at) & ~1);
+        for (int base = at; base < vend; base += 64) {
+            const int i0 = base + 2 * lane;
+            if (i0 < vend) {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float *yc = y + c * chf;
+                    float t[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) t[k] = yc[i0 - t1 - 2 + k];
+                    float2 v = *reinterpret_cast<float2 *>(yc + i0);
+                    v.x = comb5(v.x, t[4], t[3], t[2], t[1], t[0], g10, g11, g12);
+                    v.y = comb5(v.y, t[5], t[4], t[3], t[2], t[1], g10, g11, g12);
+                    *reinterpret_cast<float2 *>(yc + i0) = v;
+                }
+            }
+            __syncwarp();
+        }
+        at = vend;
+    }
+    {
         const int W = min(t1 - 2, 32);
-        for (int base = overlap; base < n; base += W) {
+        for (int base = at; base < n; base += W) {
             const int i = base + lane;
             if (lane < W && i < n) {
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     float *yc = y + c * chf;
                     const float x0 = yc[i - t1 + 2], x1 = yc[i - t1 + 1], x2 = yc[i - t1], x3 = yc[i - t1 - 1], x4 = yc[i - t1 - 2];
-                    yc[i] = yc[i] + (g10 * x2) + (g11 * (x1 + x3)) + (g12 * (x0 + x4));
+                    yc[i] = comb5(yc[i], x0, x1, x2, x3, x4, g10, g11, g12);
                 }
             }
             __syncwarp();
@@ -346,118 +534,115 @@ __device__ __forceinline__ void w_comb(float *y, int chf, int t0, int t1, int n,
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 1: grid = items (streams of this bucket), one warp per CTA.
-template <int LM, int C> __global__ void __launch_bounds__(32) k_imdct_post_w(ImdctArgs A)
+// kernel 1: one warp = one CTA = one stream (item).
+// Shared memory: C rows of nf+60 floats | interleaved post-filter history, up to 1024 samples x C |
+// two mbarriers (coefficient rows, history).  Both TMA transfers are issued before anything else;
+// the history lands while the FFT runs.
+template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imdct_post_w(ImdctArgs A)
 {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(16) float sm_all[];
     constexpr int NF = 120 << LM;
     constexpr int CHF = w_ch_floats(LM);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + C * CHF);
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sm = sm_all + warp * (w_smem_bytes(LM, C) / 4);
+    float *o = sm;
+    float *hs = sm + C * CHF;  // history staging, HIST_CAP samples x C
+    uint64_t *bar = reinterpret_cast<uint64_t *>(hs + C * HIST_CAP);
 
-    const uint32_t item = blockIdx.x;
+    // the warps of a CTA share nothing but the instruction stream (they start together, so they
+    // fetch the same straight-line code at about the same time)
+    const uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (item >= A.n_items) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    // everything the frame needs from per-stream state, requested in one go
+    const opn_synth_side *side = A.side + stream;
     const int32_t status = A.status[stream];
+    const PfState old = A.pf[stream];
+    const uint32_t pos = A.ring_pos[stream];
+    const int s_transient = side->transient, s_on = side->postfilter, s_period = side->period, s_gain = side->gain_idx,
+              s_tapset = side->tapset;
+    const uint32_t s_final = side->final_rng;
+    const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
+    float *carry_g = A.carry + (size_t)stream * C * 60;
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
     if (status < 0) {  // rejected packet: state untouched (decoder.rs:397)
         if (lane == 0 && A.result) A.result[stream] = status;
         return;
     }
-    // coefficient rows -> region O by TMA
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, C * NF * 4);
-#pragma unroll
-        for (int c = 0; c < C; c++)
-            bulk_g2s(sm + c * CHF + WA_FLOATS, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
-    }
-    const opn_synth_side *side = A.side + stream;
     const bool lost = status == ITEM_LOST;
-    const int transient = side->transient;
-
     // post-filter parameters: previous frame -> this frame
-    const PfState old = A.pf[stream];
     int t1 = old.period, tap1 = old.tapset;
     float g1 = old.gain;
     if (!lost) {
-        const int on = side->postfilter;
-        t1 = on ? side->period : 0;
-        g1 = on ? 0.09375f * (float)(side->gain_idx + 1) : 0.0f;
-        tap1 = on ? side->tapset : 0;
+        t1 = s_on ? s_period : 0;
+        g1 = s_on ? 0.09375f * (float)(s_gain + 1) : 0.0f;
+        tap1 = s_on ? s_tapset : 0;
     }
     const bool comb_on = A.postfilter && (old.gain != 0.0f || g1 != 0.0f);
-    const uint32_t pos = A.ring_pos[stream];
     float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
-    float *carry_g = A.carry + (size_t)stream * C * 60;
-    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
-
+    // history = the last `need` samples before pos (a multiple of 4, so every piece is 16-byte sized and aligned)
+    const int need = comb_on ? ((max(max(old.period, t1), 15) + 2 + 3) & ~3) : 0;
+    float *hist_end = hs + C * HIST_CAP;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_expect_tx(bar, C * NF * 4);
+#pragma unroll
+        for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
+        if (comb_on) {
+            mbar_expect_tx(bar + 1, need * C * 4);
+            const int first = (int)pos - need;  // may be negative: the span wraps around the ring end
+            if (first >= 0) {
+                bulk_g2s(hist_end - need * C, ring + (size_t)first * C, need * C * 4, bar + 1);
+            } else {
+                bulk_g2s(hist_end - need * C, ring + (size_t)(first + RING_SAMPLES) * C, -first * C * 4, bar + 1);
+                if (pos) bulk_g2s(hist_end - (int)pos * C, ring, pos * C * 4, bar + 1);
+            }
+        }
+    }
     __syncwarp();
     mbar_wait(bar, 0);
     if constexpr (LM > 0) {
-        if (transient) w_imdct<3, (1 << LM), C>(sm, lane, carry);
-        else w_imdct<3 - LM, 1, C>(sm, lane, carry);
+        if (s_transient) w_imdct<3, (1 << LM), C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
+        else w_imdct<3 - LM, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3 - LM), g_tab.twiddles, g_tab.window);
     } else {
-        w_imdct<3, 1, C>(sm, lane, carry);
+        w_imdct<3, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
     }
 
-    // tail of this frame -> carry; post-filter history <- PCM ring (region A is free again)
+    // tail of this frame -> carry
     if (lane < 15 * C) {
         const int ch = (C == 2 && lane >= 15) ? 1 : 0;
-        *reinterpret_cast<float4 *>(carry_g + 4 * lane) =
-            *reinterpret_cast<const float4 *>(sm + ch * CHF + WA_FLOATS + NF + 4 * (lane - 15 * ch));
+        *reinterpret_cast<float4 *>(carry_g + 4 * lane) = *reinterpret_cast<const float4 *>(o + ch * CHF + NF + 4 * (lane - 15 * ch));
     }
     if (comb_on) {
-        const int need = max(max(old.period, t1), 15) + 2;  // <= 1024
-        if (C == 2) {
-            // two samples x two channels per float4; pos is a multiple of 120, so pairs never straddle the wrap
-            for (int j = lane; 2 * j < need; j += 32) {
-                uint32_t p = pos + RING_SAMPLES - 2u - 2u * (uint32_t)j;
-                if (p >= RING_SAMPLES) p -= RING_SAMPLES;
-                const float4 v = *reinterpret_cast<const float4 *>(ring + (size_t)p * 2);
-                float *h0 = sm + WA_FLOATS - 2 - 2 * j, *h1 = h0 + CHF;
-                *reinterpret_cast<float2 *>(h0) = make_float2(v.x, v.z);
-                *reinterpret_cast<float2 *>(h1) = make_float2(v.y, v.w);
-            }
-        } else {
-            for (int j = lane; 4 * j < need; j += 32) {
-                uint32_t p = pos + RING_SAMPLES - 4u - 4u * (uint32_t)j;
-                if (p >= RING_SAMPLES) p -= RING_SAMPLES;
-                *reinterpret_cast<float4 *>(sm + WA_FLOATS - 4 - 4 * j) = *reinterpret_cast<const float4 *>(ring + p);
-            }
-        }
-        __syncwarp();
-        w_comb<C>(sm + WA_FLOATS, CHF, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane);
+        mbar_wait(bar + 1, 0);
+        w_comb<C>(o, CHF, hist_end, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane, g_tab.window_sq);
     }
     __syncwarp();
 
-    // epilogue: interleaved PCM -> ring (history + device-resident output) and optional dense rows
-    const float *s0 = sm + WA_FLOATS;
-    const float *s1 = s0 + CHF;
-    float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + (A.dense_off ? A.dense_off[item] : 0u) : nullptr;
+    // epilogue: interleaved PCM -> ring (history + device-resident output) and optional dense rows.
+    // The frame is contiguous in the ring except when it wraps (pos is a multiple of 120).
+    float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
     const float gain = A.gain;
-    if (C == 2) {
+    constexpr int VEC = C == 2 ? NF / 2 : NF / 4;         // float4 per frame
+    constexpr int SPV = C == 2 ? 2 : 4;                   // samples per float4
+    const int wrap_at = (int)(RING_SAMPLES - pos) / SPV;  // first float4 that lands at the ring start
+    float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)pos * C);
+    float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
 #pragma unroll 5
-        for (int i = lane; i < NF / 2; i += 32) {
-            const float2 a = *reinterpret_cast<const float2 *>(s0 + 2 * i), b = *reinterpret_cast<const float2 *>(s1 + 2 * i);
-            float4 v = make_float4(a.x, b.x, a.y, b.y);
-            uint32_t p = pos + 2u * (uint32_t)i;
-            if (p >= RING_SAMPLES) p -= RING_SAMPLES;
-            *reinterpret_cast<float4 *>(ring + (size_t)p * 2) = v;
-            if (dense) {
-                if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
-                *reinterpret_cast<float4 *>(dense + 4 * i) = v;
-            }
+    for (int i = lane; i < VEC; i += 32) {
+        float4 v;
+        if (C == 2) {
+            const float2 a = *reinterpret_cast<const float2 *>(o + 2 * i), b = *reinterpret_cast<const float2 *>(o + CHF + 2 * i);
+            v = make_float4(a.x, b.x, a.y, b.y);
+        } else {
+            v = *reinterpret_cast<const float4 *>(o + 4 * i);
         }
-    } else {
-        for (int i = lane; i < NF / 4; i += 32) {
-            float4 v = *reinterpret_cast<const float4 *>(s0 + 4 * i);
-            uint32_t p = pos + 4u * (uint32_t)i;
-            if (p >= RING_SAMPLES) p -= RING_SAMPLES;
-            *reinterpret_cast<float4 *>(ring + p) = v;
-            if (dense) {
-                if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
-                *reinterpret_cast<float4 *>(dense + 4 * i) = v;
-            }
+        (i < wrap_at ? r0 : r1)[i] = v;
+        if (dense) {
+            if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
+            reinterpret_cast<float4 *>(dense)[i] = v;
         }
     }
     if (lane == 0) {
@@ -471,7 +656,7 @@ template <int LM, int C> __global__ void __launch_bounds__(32) k_imdct_post_w(Im
         nw.pad = 0;
         A.pf[stream] = nw;
         if (A.result) A.result[stream] = NF;
-        if (A.final_range) A.final_range[stream] = lost ? 0u : side->final_rng;
+        if (A.final_range) A.final_range[stream] = lost ? 0u : s_final;
     }
 }
 
@@ -485,12 +670,35 @@ k_op_imdct_w(const float *__restrict__ input, size_t in_stride, float *__restric
     const int lane = threadIdx.x;
     const float *in = input + (size_t)blockIdx.x * in_stride;
     float *out = output + (size_t)blockIdx.x * out_stride;
-    for (int i = lane; i < NF; i += 32) sm[WA_FLOATS + i] = in[i];
+    for (int i = lane; i < NF; i += 32) sm[i] = in[i];
     float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < 15) carry = make_float4(out[4 * lane], out[4 * lane + 1], out[4 * lane + 2], out[4 * lane + 3]);
     __syncwarp();
-    w_imdct<SHIFT, NBLK, 1>(sm, lane, carry);
-    for (int i = lane; i < NF + 60; i += 32) out[i] = sm[WA_FLOATS + i];
+    w_imdct<SHIFT, NBLK, 1>(sm, lane, carry, g_tab.trig_pair + trig_pair_off(SHIFT), g_tab.twiddles, g_tab.window);
+    for (int i = lane; i < NF + 60; i += 32) out[i] = sm[i];
+}
+
+// Operator-level comb_filter_inplace on rows (tests; opn_op_comb_filter_inplace): one warp per row,
+// the row's own prefix [y_offset - hist, y_offset) plays the role of the PCM ring.
+__global__ void __launch_bounds__(32)
+k_op_comb_inplace_w(float *__restrict__ y, size_t row_stride, int y_offset, int n, const int32_t *__restrict__ params4,
+                    const float *__restrict__ gains2, int overlap)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x;
+    float *row = y + (size_t)blockIdx.x * row_stride;
+    const int t0 = params4[4 * blockIdx.x], t1 = params4[4 * blockIdx.x + 1];
+    const int tap0 = params4[4 * blockIdx.x + 2], tap1 = params4[4 * blockIdx.x + 3];
+    const float g0 = gains2[2 * blockIdx.x], g1 = gains2[2 * blockIdx.x + 1];
+    // shared memory: [HIST_CAP history | n samples]; the row's own prefix plays the role of the PCM ring
+    const int need = min(max(max(t0, t1), 15) + 2, y_offset);
+    float *ys = sm + HIST_CAP;
+    for (int i = lane; i < n; i += 32) ys[i] = row[y_offset + i];
+    for (int i = lane; i < need; i += 32) ys[-1 - i] = row[y_offset - 1 - i];
+    __syncwarp();
+    w_comb<1>(ys, 0, ys, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) row[y_offset + i] = ys[i];
 }
 
 }  // namespace opn

@@ -1,4 +1,5 @@
 // opn_kernels.cu -- the single CUDA translation unit of libopusb200 (sm_100a, -fmad=false).
+#include <cstdlib>
 #include <mutex>
 
 #include "imdct.cuh"
@@ -11,11 +12,18 @@ namespace opn {
 
 
 static std::mutex g_tab_mutex;
+static int g_sm_count = 148;
+constexpr int W_CARVEOUT_PCT = 100;
+constexpr int W_WPC = 1;  // warps per CTA of kernel 1
 static bool g_tab_done[64];
 
 template <int LM, int C> static cudaError_t set_carveout()
 {
-    return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // percent of the SM's unified 256 KB used as shared memory; the rest is L1 (tables, history taps)
+    static const int pct = getenv("OPN_CARVEOUT") ? atoi(getenv("OPN_CARVEOUT")) : W_CARVEOUT_PCT;
+    cudaError_t e = cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W_MAX_WPC * w_smem_bytes(LM, C)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 static cudaError_t set_warp_kernel_attributes()
 {
@@ -92,6 +100,8 @@ cudaError_t upload_tables(int device)
     for (int i = 0; i < 9; i++) h.comb_gains[i] = OPN_COMB_GAINS[i];
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_tw, h.twiddles, sizeof(h.twiddles));
@@ -109,7 +119,9 @@ cudaError_t upload_tables(int device)
 
 template <int LM, int C> static cudaError_t launch_imdct_w(const ImdctArgs &a, cudaStream_t st)
 {
-    k_imdct_post_w<LM, C><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
+    static const int wpc_env = getenv("OPN_IMDCT_WPC") ? atoi(getenv("OPN_IMDCT_WPC")) : W_WPC;
+    const uint32_t wpc = (uint32_t)(wpc_env < 1 ? 1 : wpc_env > W_MAX_WPC ? W_MAX_WPC : wpc_env);
+    k_imdct_post_w<LM, C><<<(a.n_items + wpc - 1) / wpc, 32 * wpc, wpc * w_smem_bytes(LM, C), st>>>(a);
     return cudaGetLastError();
 }
 
@@ -157,8 +169,7 @@ cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_
                             int nblk, cudaStream_t st)
 {
     if (n_rows == 0) return cudaSuccess;
-    const int lm = nblk == 1 ? 3 - shift : nblk == 2 ? 1 : nblk == 4 ? 2 : 3;
-    const size_t smem = w_smem_bytes(lm, 1);
+    const size_t smem = (size_t)((960 >> shift) * nblk + 60) * 4;
     if (nblk == 1) {
         switch (shift) {
         case 0: k_op_imdct_w<0, 1><<<n_rows, 32, smem, st>>>(in, in_stride, out, out_stride); break;
@@ -182,10 +193,9 @@ cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, in
                                    const float *gains2, int overlap, cudaStream_t st)
 {
     if (n_rows == 0) return cudaSuccess;
-    const int hist = y_offset < HIST_CAP + 2 ? y_offset : HIST_CAP + 2;
-    const size_t smem = (size_t)(hist + n) * 4;
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    k_op_comb_inplace<<<n_rows, IM_TPC, smem, st>>>(y, row_stride, y_offset, n, params4, gains2, overlap);
+    const size_t smem = (((size_t)n + HIST_CAP) * 4 + 15) & ~(size_t)15;
+    if (smem > 48 * 1024 || (overlap & 3)) return cudaErrorInvalidValue;
+    k_op_comb_inplace_w<<<n_rows, 32, smem, st>>>(y, row_stride, y_offset, n, params4, gains2, overlap);
     return cudaGetLastError();
 }
 

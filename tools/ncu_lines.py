@@ -52,13 +52,15 @@ def main():
         subprocess.run(["cuobjdump", "-xelf", "all", SO], cwd=td, capture_output=True)
         cub = [f for f in os.listdir(td) if f.startswith("opn_kernels")][0]
         sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
-    fn = re.search(r"(\w+)\(", kname).group(1) if "(" in kname else kname
-    fn = fn.split("::")[-1]
+    # "void k<3, 2>(Args)" -> base name "k" plus the mangled integer template arguments "ILi3ELi2EE"
+    m = re.search(r"([\w:]+)\s*(?:<([^>]*)>)?\s*\(", kname)
+    fn = (m.group(1) if m else kname).split("::")[-1]
+    targs = "I" + "".join("Li%sE" % re.sub(r"\(\w+\)", "", a).strip() for a in m.group(2).split(",")) + "E" if m and m.group(2) else ""
     line_of = {}
     cur, on = None, False
     for ln in sass.split("\n"):
         if ln.startswith(".text."):
-            on = fn in ln
+            on = fn in ln and targs in ln
             continue
         if not on:
             continue
