@@ -33,11 +33,18 @@
 //     swept in chunks, from shared memory.
 #pragma once
 #include "imdct.cuh"
+#include "opn_tables.h"
 
 namespace opn {
 
-// Twiddles addressed with compile-time indices (src/celt/kiss_fft.rs:341-582): constant bank.
-__constant__ float2 c_tw[480];
+// Twiddles addressed with compile-time indices (src/celt/kiss_fft.rs:341-582) fold into instruction
+// immediates: OPN_TWIDDLES is constexpr in C++ translation units.
+__device__ int g_dbg_skip;  // diagnostic only (OPN_IMDCT_SKIP): 1 = no FFT, 2 = no comb, 4 = no PCM stores, 8 = no carry/state
+
+template <int I> struct WTw {
+    static constexpr float re = OPN_TWIDDLES[2 * I], im = OPN_TWIDDLES[2 * I + 1];
+    __device__ __forceinline__ static float2 get() { return make_float2(re, im); }
+};
 
 constexpr int W_MAX_WPC = 8;  // warps (= streams) per CTA, at most
 __host__ __device__ constexpr int w_ch_floats(int lm) { return (120 << lm) + 60; }
@@ -147,6 +154,12 @@ __device__ __forceinline__ void r_bfly5(float2 &d0, float2 &d1, float2 &d2, floa
     d3 = c_sub(s11, s12);
 }
 
+// radix-4 butterfly U of the last in-group stage: elements U + M*{0,1,2,3}, twiddle stride S
+template <int U, int M, int S> __device__ __forceinline__ void w_bfly4_const(float2 *d)
+{
+    r_bfly4(d[U], d[U + M], d[U + 2 * M], d[U + 3 * M], WTw<S * U>::get(), WTw<2 * S * U>::get(), WTw<3 * S * U>::get());
+}
+
 // In-group position p (0 <= p < GS) -> q, where the group's inputs are i = r + 15 q
 // (digit reversal of kiss_fft.rs:281-336 for the factor lists :251,259,267,275; checked against the
 // generated tables in tests/test_host_logic.py::test_digit_reversal_closed_form).
@@ -174,12 +187,20 @@ template <int SHIFT> __device__ __forceinline__ void w_group_stages(float2 *d)
         }
     }
     if constexpr (SHIFT == 0) {  // radix 4, m = 8, twiddle stride 15
-#pragma unroll
-        for (int u = 0; u < 8; u++) r_bfly4(d[u], d[u + 8], d[u + 16], d[u + 24], c_tw[15 * u], c_tw[30 * u], c_tw[45 * u]);
+        w_bfly4_const<0, 8, 15>(d);
+        w_bfly4_const<1, 8, 15>(d);
+        w_bfly4_const<2, 8, 15>(d);
+        w_bfly4_const<3, 8, 15>(d);
+        w_bfly4_const<4, 8, 15>(d);
+        w_bfly4_const<5, 8, 15>(d);
+        w_bfly4_const<6, 8, 15>(d);
+        w_bfly4_const<7, 8, 15>(d);
     }
     if constexpr (SHIFT == 1) {  // radix 4, m = 4, twiddle stride 30
-#pragma unroll
-        for (int u = 0; u < 4; u++) r_bfly4(d[u], d[u + 4], d[u + 8], d[u + 12], c_tw[30 * u], c_tw[60 * u], c_tw[90 * u]);
+        w_bfly4_const<0, 4, 30>(d);
+        w_bfly4_const<1, 4, 30>(d);
+        w_bfly4_const<2, 4, 30>(d);
+        w_bfly4_const<3, 4, 30>(d);
     }
 }
 
@@ -249,8 +270,8 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
         for (int jj = 0; jj < 3; jj++)
 #pragma unroll
             for (int k = 0; k < 4; k++) w5[jj][k] = __ldg(tw + (((u + GS * jj) * (k + 1)) << SHIFT));
-        const float epi3y = c_tw[160].y;
-        const float2 ya = c_tw[96], yb = c_tw[192];
+        constexpr float epi3y = WTw<160>::im;
+        const float2 ya = WTw<96>::get(), yb = WTw<192>::get();
         constexpr int ITER = (C * E + 31) / 32;
 #pragma unroll 1
         for (int it = 0; it < ITER; it++) {
@@ -554,6 +575,14 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     const uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp;
     if (item >= A.n_items) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_expect_tx(bar, C * NF * 4);
+#pragma unroll
+        for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
+    }
     // everything the frame needs from per-stream state, requested in one go
     const opn_synth_side *side = A.side + stream;
     const int32_t status = A.status[stream];
@@ -566,8 +595,10 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     float *carry_g = A.carry + (size_t)stream * C * 60;
     float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
+    __syncwarp();
     if (status < 0) {  // rejected packet: state untouched (decoder.rs:397)
         if (lane == 0 && A.result) A.result[stream] = status;
+        mbar_wait(bar, 0);  // the rows are in flight: do not retire the CTA under them
         return;
     }
     const bool lost = status == ITEM_LOST;
@@ -584,39 +615,35 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     // history = the last `need` samples before pos (a multiple of 4, so every piece is 16-byte sized and aligned)
     const int need = comb_on ? ((max(max(old.period, t1), 15) + 2 + 3) & ~3) : 0;
     float *hist_end = hs + C * HIST_CAP;
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
-        mbar_expect_tx(bar, C * NF * 4);
-#pragma unroll
-        for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
-        if (comb_on) {
-            mbar_expect_tx(bar + 1, need * C * 4);
-            const int first = (int)pos - need;  // may be negative: the span wraps around the ring end
-            if (first >= 0) {
-                bulk_g2s(hist_end - need * C, ring + (size_t)first * C, need * C * 4, bar + 1);
-            } else {
-                bulk_g2s(hist_end - need * C, ring + (size_t)(first + RING_SAMPLES) * C, -first * C * 4, bar + 1);
-                if (pos) bulk_g2s(hist_end - (int)pos * C, ring, pos * C * 4, bar + 1);
-            }
+    if (lane == 0 && comb_on) {
+        mbar_expect_tx(bar + 1, need * C * 4);
+        const int first = (int)pos - need;  // may be negative: the span wraps around the ring end
+        if (first >= 0) {
+            bulk_g2s(hist_end - need * C, ring + (size_t)first * C, need * C * 4, bar + 1);
+        } else {
+            bulk_g2s(hist_end - need * C, ring + (size_t)(first + RING_SAMPLES) * C, -first * C * 4, bar + 1);
+            if (pos) bulk_g2s(hist_end - (int)pos * C, ring, pos * C * 4, bar + 1);
         }
     }
     __syncwarp();
     mbar_wait(bar, 0);
+    const int dbg = g_dbg_skip;
+    if (!(dbg & 1)) {
     if constexpr (LM > 0) {
         if (s_transient) w_imdct<3, (1 << LM), C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
         else w_imdct<3 - LM, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3 - LM), g_tab.twiddles, g_tab.window);
     } else {
         w_imdct<3, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
     }
+    }
 
     // tail of this frame -> carry
-    if (lane < 15 * C) {
+    if (lane < 15 * C && !(dbg & 8)) {
         const int ch = (C == 2 && lane >= 15) ? 1 : 0;
         *reinterpret_cast<float4 *>(carry_g + 4 * lane) = *reinterpret_cast<const float4 *>(o + ch * CHF + NF + 4 * (lane - 15 * ch));
     }
-    if (comb_on) {
-        mbar_wait(bar + 1, 0);
+    if (comb_on) mbar_wait(bar + 1, 0);
+    if (comb_on && !(dbg & 2)) {
         w_comb<C>(o, CHF, hist_end, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane, g_tab.window_sq);
     }
     __syncwarp();
@@ -630,8 +657,8 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     const int wrap_at = (int)(RING_SAMPLES - pos) / SPV;  // first float4 that lands at the ring start
     float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)pos * C);
     float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
-#pragma unroll 5
-    for (int i = lane; i < VEC; i += 32) {
+#pragma unroll
+    for (int i = lane; i < ((dbg & 4) ? 0 : VEC); i += 32) {
         float4 v;
         if (C == 2) {
             const float2 a = *reinterpret_cast<const float2 *>(o + 2 * i), b = *reinterpret_cast<const float2 *>(o + CHF + 2 * i);
@@ -645,7 +672,7 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
             reinterpret_cast<float4 *>(dense)[i] = v;
         }
     }
-    if (lane == 0) {
+    if (lane == 0 && !(dbg & 8)) {
         uint32_t np = pos + (uint32_t)NF;
         if (np >= RING_SAMPLES) np -= RING_SAMPLES;
         A.ring_pos[stream] = np;

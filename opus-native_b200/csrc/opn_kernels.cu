@@ -104,8 +104,11 @@ cudaError_t upload_tables(int device)
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(c_tw, h.twiddles, sizeof(h.twiddles));
-    if (e != cudaSuccess) return e;
+    {
+        const int dbg = getenv("OPN_IMDCT_SKIP") ? atoi(getenv("OPN_IMDCT_SKIP")) : 0;
+        e = cudaMemcpyToSymbol(g_dbg_skip, &dbg, sizeof(dbg));
+        if (e != cudaSuccess) return e;
+    }
     e = set_warp_kernel_attributes();
     if (e != cudaSuccess) return e;
     // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
@@ -113,6 +116,13 @@ cudaError_t upload_tables(int device)
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_synth_symbols, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
+    // same shared-memory/L1 split as kernel 1: alternating kernels with different carve-outs makes the
+    // SMs drain and reconfigure between every pair of launches
+    if (!getenv("OPN_NO_SYM_CARVEOUT")) {
+        e = cudaFuncSetAttribute(k_synth_symbols, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 getenv("OPN_CARVEOUT") ? atoi(getenv("OPN_CARVEOUT")) : W_CARVEOUT_PCT);
+        if (e != cudaSuccess) return e;
+    }
     g_tab_done[device] = true;
     return cudaSuccess;
 }

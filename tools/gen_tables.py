@@ -230,9 +230,12 @@ def emit(path, prefix, guard):
     w(f"#ifndef {guard}\n#define {guard}\n#include <stdint.h>\n")
     w(f"#define {prefix}OVERLAP 120\n#define {prefix}NB_EBANDS 21\n#define {prefix}MAX_LM 3")
     w(f"#define {prefix}MDCT_N 1920\n#define {prefix}COMB_MINPERIOD 15\n#define {prefix}COMB_MAXPERIOD 1024\n")
+    w("/* C++ translation units get constexpr tables: kernels that index them with compile-time")
+    w(" * constants receive the values as instruction immediates. */")
+    w(f"#ifdef __cplusplus\n#define {prefix}TABLE static constexpr\n#else\n#define {prefix}TABLE static const\n#endif\n")
 
     def arr(ctype, name, vals, fmt, per=8):
-        w(f"static const {ctype} {prefix}{name}[{len(vals)}] = {{")
+        w(f"{prefix}TABLE {ctype} {prefix}{name}[{len(vals)}] = {{")
         for i in range(0, len(vals), per):
             w("  " + ", ".join(fmt(v) for v in vals[i:i + per]) + ",")
         w("};\n")
