@@ -117,7 +117,7 @@ struct opn_batch {
     cudaStream_t stream = nullptr;
     // per-stream state (device, SoA)
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef = nullptr;
-    uint32_t *d_ring_pos = nullptr, *d_final = nullptr;
+    uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx = nullptr;
     PfState *d_pf = nullptr;
     opn_synth_side *d_side = nullptr;
     int32_t *d_status = nullptr;
@@ -202,9 +202,11 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.status = b->d_status;
     s.coef = b->d_coef;
     s.y_out = nullptr;
+    s.idx = b->d_idx;
     s.pkt_cap = pkt_cap;
     int rc = timed_launch(b, 0, do_symbols, &s);
     if (rc) return rc;
+    b->launches[0] += 1;  // kernel 0 is two launches: k_synth_rangedec + k_synth_expand
     ImdctArgs m{};
     m.coef = b->d_coef;
     m.side = b->d_side;
@@ -294,6 +296,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     if (e == cudaSuccess) e = cudaMalloc(&b->d_carry, n * C * 60 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring, n * C * RING_SAMPLES * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_coef, n * C * 960 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_idx, n * 72 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring_pos, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
@@ -327,6 +330,7 @@ void opn_batch_destroy(opn_batch *b)
     cudaFree(b->d_carry);
     cudaFree(b->d_ring);
     cudaFree(b->d_coef);
+    cudaFree(b->d_idx);
     cudaFree(b->d_ring_pos);
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
@@ -852,7 +856,7 @@ int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offse
         max_len = std::max(max_len, lens[i]);
     }
     const size_t row = (size_t)channels * (120u << lm);
-    DevBuf dA, dO, dL, dS, dSt, dY, dC;
+    DevBuf dA, dO, dL, dS, dSt, dY, dC, dI;
     CU(dA.alloc(arena_end));
     CU(dO.alloc(n_packets * 4));
     CU(dL.alloc(n_packets * 4));
@@ -860,6 +864,7 @@ int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offse
     CU(dSt.alloc(n_packets * 4));
     CU(dY.alloc((size_t)n_packets * row * 4));
     CU(dC.alloc((size_t)n_packets * row * 4));
+    CU(dI.alloc((size_t)n_packets * 72 * 4));
     CU(cudaMemcpy(dA.p, arena, arena_end, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dO.p, offsets, n_packets * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dL.p, lens, n_packets * 4, cudaMemcpyHostToDevice));
@@ -876,6 +881,7 @@ int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offse
     s.status = dSt.as<int32_t>();
     s.coef = dC.as<float>();
     s.y_out = dY.as<int32_t>();
+    s.idx = dI.as<uint32_t>();
     s.pkt_cap = (max_len + 15u) & ~15u;
     CU(launch_synth_symbols(s, nullptr));
     CU(cudaDeviceSynchronize());

@@ -31,6 +31,7 @@ struct SymbolArgs {
     int32_t *status;             // [n_streams]
     float *coef;                 // [n_streams][channels][120<<lm] or nullptr
     int32_t *y_out;              // same shape or nullptr
+    uint32_t *idx;               // [n_streams][72] scratch: PVQ codeword indices (range decode -> expansion)
     uint32_t pkt_cap;            // bytes of shared memory per warp for the packet
 };
 

@@ -95,6 +95,37 @@ cudaError_t upload_tables(int device)
                     }
                 }
             h.synth_n_entries[lm][C - 1] = (uint8_t)ne;
+            // bin -> part map for the coefficient write of k_synth_expand
+            uint8_t *eo = h.synth_entry_of[lm][C - 1];
+            for (int i = 0; i < 2 * 960; i++) eo[i] = 0xFF;
+            for (int e = 0; e < ne; e++) {
+                const SynthEntry &E = h.synth_entries[lm][C - 1][e];
+                for (int j = 0; j < (int)E.n; j++) eo[E.base + j] = (uint8_t)e;
+            }
+            // deal the parts to 32 lanes, longest first onto the least loaded lane (cwrsi walks n dimensions
+            // and k pulses, so n + k is its cost; sign-only parts cost 1)
+            uint8_t(*le)[SYNTH_LANE_SLOTS] = h.synth_lane_entries[lm][C - 1];
+            int load[32], used[32];
+            for (int l = 0; l < 32; l++) {
+                load[l] = used[l] = 0;
+                for (int q = 0; q < SYNTH_LANE_SLOTS; q++) le[l][q] = 0xFF;
+            }
+            bool taken[SYNTH_MAX_ENTRIES] = {false};
+            for (int round = 0; round < ne; round++) {
+                int best = -1, bcost = -1;
+                for (int e = 0; e < ne; e++) {
+                    const SynthEntry &E = h.synth_entries[lm][C - 1][e];
+                    const int cost = E.n == 1 ? 1 : (int)E.n + (int)E.k;
+                    if (!taken[e] && cost > bcost) { best = e; bcost = cost; }
+                }
+                int lane = -1;
+                for (int l = 0; l < 32; l++)
+                    if (used[l] < SYNTH_LANE_SLOTS && (lane < 0 || load[l] < load[lane])) lane = l;
+                if (lane < 0) return cudaErrorInvalidValue;  // cannot happen: 32 x SYNTH_LANE_SLOTS >= 72
+                taken[best] = true;
+                le[lane][used[lane]++] = (uint8_t)best;
+                load[lane] += bcost;
+            }
         }
     h.tapset_icdf[0] = 2; h.tapset_icdf[1] = 1; h.tapset_icdf[2] = 0; h.tapset_icdf[3] = 0;
     for (int i = 0; i < 9; i++) h.comb_gains[i] = OPN_COMB_GAINS[i];
@@ -114,15 +145,8 @@ cudaError_t upload_tables(int device)
     // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
     e = cudaFuncSetAttribute(k_rangedec_script, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_synth_symbols, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    e = cudaFuncSetAttribute(k_synth_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    // same shared-memory/L1 split as kernel 1: alternating kernels with different carve-outs makes the
-    // SMs drain and reconfigure between every pair of launches
-    if (!getenv("OPN_NO_SYM_CARVEOUT")) {
-        e = cudaFuncSetAttribute(k_synth_symbols, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 getenv("OPN_CARVEOUT") ? atoi(getenv("OPN_CARVEOUT")) : W_CARVEOUT_PCT);
-        if (e != cudaSuccess) return e;
-    }
     g_tab_done[device] = true;
     return cudaSuccess;
 }
@@ -154,8 +178,12 @@ cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets
 cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
+    if (!a.idx) return cudaErrorInvalidValue;
+    k_synth_rangedec<<<(a.n_items + 31u) / 32u, 32, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     const uint32_t grid = (a.n_items + SYM_WARPS_PER_CTA - 1) / SYM_WARPS_PER_CTA;
-    k_synth_symbols<<<grid, SYM_WARPS_PER_CTA * 32, synth_symbols_smem(a.pkt_cap), st>>>(a);
+    k_synth_expand<<<grid, SYM_WARPS_PER_CTA * 32, synth_expand_smem(), st>>>(a);
     return cudaGetLastError();
 }
 

@@ -112,58 +112,50 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory plan of k_synth_symbols (per CTA of SYM_WARPS_PER_CTA warps):
+// SYNTH-CELT/1 symbol decode, two kernels:
+//
+//   k_synth_rangedec  ONE LANE decodes one packet.  The entropy decoder is a strictly serial
+//      dependency chain per packet (two divisions and a byte refill per symbol); a warp that
+//      shares one chain between its 32 lanes issues ~60 warp-instructions per symbol for one
+//      packet, a warp whose lanes each own a chain issues about the same for 32 packets.  The chain
+//      only produces what depends on it: flags, post-filter parameters, energies and, for every PVQ
+//      part, the codeword INDEX (decode_uint with the host-precomputed alphabet split and
+//      reciprocal).  Packet bytes are read in place through L1 (each lane walks its own packet
+//      front-to-back and back-to-front, so every 128-byte line is fetched once).
+//   k_synth_expand    ONE WARP expands one packet's indices into pulse vectors (cwrsi never feeds
+//      back into the range decoder): the parts are dealt to the 32 lanes by a host-computed
+//      longest-first schedule so every lane walks about the same number of dimensions, then the warp
+//      writes pulses x gain as coalesced float4 coefficient rows.
+//
+// Shared memory of k_synth_expand (per CTA of SYM_WARPS_PER_CTA warps):
 //   PVQ U(n,k) table 5088 B + row offsets 32 B | entry table 72 x 16 B | per warp: codeword
-//   indices 72 x 4 B, gains 72 x 4 B, side info 96 x 4 B, 16-bit pulses 2 x 960 x 2 B, packet bytes.
+//   indices 72 x 4 B, gains 72 x 4 B, 16-bit pulses 2 x 960 x 2 B.
 constexpr int SYM_Y16 = 2 * 960;
-__host__ __device__ constexpr size_t synth_symbols_smem(uint32_t pkt_cap)
+constexpr size_t SYM_EXPAND_WARP_BYTES = SYNTH_MAX_ENTRIES * 8 + SYM_Y16 * 2;
+__host__ __device__ constexpr size_t synth_expand_smem()
 {
-    return PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) +
-           (size_t)SYM_WARPS_PER_CTA * (SYNTH_MAX_ENTRIES * 8 + 96 * 4 + SYM_Y16 * 2 + pkt_cap);
+    return PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)SYM_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
 }
 
-// Three phases per warp (= per packet):
-//   A  serial, warp-uniform: flags, post-filter parameters, Laplace energies, fine bits and, for every
-//      PVQ part, only the codeword INDEX (decode_uint with host-precomputed alphabet split and
-//      reciprocal).  This is the true dependency chain of the entropy decoder.
-//   B  lane-parallel: the index -> pulse-vector expansion (cwrsi) never feeds back into the range
-//      decoder, so lane l expands parts l, l+32, l+64 independently and derives the part gain.
-//   C  cooperative: pulses x gain -> coefficients, coalesced stores.
-__global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_symbols(SymbolArgs A)
+__global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
-    uint16_t *s_row = reinterpret_cast<uint16_t *>(s_pvq + PVQ_TABLE_WORDS);
-    SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(s_row + 16);
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) +
-                     (size_t)warp * (SYNTH_MAX_ENTRIES * 8 + 96 * 4 + SYM_Y16 * 2 + A.pkt_cap);
-    uint32_t *s_idx = reinterpret_cast<uint32_t *>(wbase);
-    float *s_gain = reinterpret_cast<float *>(s_idx + SYNTH_MAX_ENTRIES);
-    uint32_t *s_side = reinterpret_cast<uint32_t *>(s_gain + SYNTH_MAX_ENTRIES);
-    int16_t *s_y = reinterpret_cast<int16_t *>(s_side + 96);
-    uint8_t *s_pkt = reinterpret_cast<uint8_t *>(s_y + SYM_Y16);
-
-    const int lm = A.lm, C = A.channels, nf = 120 << lm;
+    __shared__ SynthEntry s_ent[SYNTH_MAX_ENTRIES];
+    const uint32_t lane = threadIdx.x;
+    const int lm = A.lm, C = A.channels;
     const int ne = g_tab.synth_n_entries[lm][C - 1];
-    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) s_pvq[i] = g_tab.pvq_u_data[i];
-    if (threadIdx.x < 15) s_row[threadIdx.x] = g_tab.pvq_u_row[threadIdx.x];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
         uint4 *dst = reinterpret_cast<uint4 *>(s_ent);
-        for (int i = threadIdx.x; i < ne; i += blockDim.x) dst[i] = src[i];
+        for (int i = lane; i < ne; i += 32) dst[i] = src[i];
     }
-    __syncthreads();
-
-    const uint32_t item = blockIdx.x * SYM_WARPS_PER_CTA + warp;
+    __syncwarp();
+    const uint32_t item = blockIdx.x * 32u + lane;
     if (item >= A.n_items) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
     uint32_t len = A.lens[item];
     const uint8_t *src = A.arena + A.offsets[item];
-    float *coef = A.coef ? A.coef + (size_t)stream * C * nf : nullptr;
-    int32_t *yo = A.y_out ? A.y_out + (size_t)stream * C * nf : nullptr;
 
-    int32_t status = ITEM_OK;
+    int32_t status = len == 0u ? ITEM_LOST : ITEM_OK;
     if (A.has_toc && len > 0u) {
         // TOC checks a host caller does with query_packet_* (src/lib.rs:219-325) before decode_frame
         const uint32_t toc = __ldg(src);
@@ -174,93 +166,123 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_symbols(Symbol
         src += 1;
         len -= 1u;
     }
-    if (status == ITEM_OK && len <= 1u) status = ITEM_LOST;  // src/decoder.rs:467
-    if (status == ITEM_OK && len > A.pkt_cap) status = OPN_ERR_INVALID_PACKET;
-    if (lane == 0u) A.status[stream] = status;
+    if (status == ITEM_OK && len <= 1u) status = ITEM_LOST;  // decoder.rs:467: len <= 1 means PLC/DTX
+    A.status[stream] = status;
     if (status < 0) return;
 
-    for (uint32_t i = lane; i < 96u; i += 32u) s_side[i] = 0u;
-    opn_synth_side *sd = reinterpret_cast<opn_synth_side *>(s_side);  // 95 words, staged in shared memory
-    bool zero_frame = status == ITEM_LOST;
-    uint32_t n_pulses = 0u;
-    __syncwarp();
-
-    if (!zero_frame) {
-        // ------------------------------------------------------------------ phase A
-        stage_bytes(s_pkt, src, len, lane);
-        RangeDec d;
-        d.init(s_pkt, len);
-        const uint32_t silence = d.bit_logp(15u);
-        if (silence) {
-            zero_frame = true;
-            if (lane == 0u) sd->silence = 1;
-        } else {
-            const uint32_t postfilter = d.bit_logp(1u);
-            uint32_t octave = 0u, period = 0u, gain_idx = 0u, tapset = 0u;
-            if (postfilter) {
-                octave = d.uint(6u);
-                period = (16u << octave) + d.bits(4u + octave) - 1u;
-                gain_idx = d.bits(3u);
-                tapset = d.icdf(g_tab.tapset_icdf, 2u);
-            }
-            const uint32_t transient = d.bit_logp(3u);
-            const uint32_t intra = d.bit_logp(3u);
-            if (lane == 0u) {
-                sd->postfilter = (int32_t)postfilter;
-                sd->octave = (int32_t)octave;
-                sd->period = (int32_t)period;
-                sd->gain_idx = (int32_t)gain_idx;
-                sd->tapset = (int32_t)tapset;
-                sd->transient = (int32_t)transient;
-                sd->intra = (int32_t)intra;
-            }
-            for (int b = 0; b < 21; b++) {
-                const uint32_t decay = 6000u + 400u * (uint32_t)b;
-                const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;  // mod.rs:530-534
-                for (int c = 0; c < C; c++) {
-                    const int32_t v = d.laplace(fs0, decay);
-                    if (lane == 0u) sd->coarse[c][b] = v;
-                }
-            }
-            for (int b = 0; b < 21; b++)
-                for (int c = 0; c < C; c++) {
-                    const uint32_t v = d.bits(2u);
-                    if (lane == 0u) sd->fine[c][b] = (int32_t)v;
-                }
-            for (int e = 0; e < ne; e++) {
-                const SynthEntry E = s_ent[e];
-                uint32_t v;
-                if (E.n == 1) {
-                    v = d.bits(1u);
-                    n_pulses += 1u;
-                } else {
-                    v = d.uint_precomputed(E.ft_minus1, E.ft1, E.ftb, E.magic, E.sh);
-                    n_pulses += E.k;
-                }
-                if (lane == 0u) s_idx[e] = v;
-            }
-        }
-        if (lane == 0u) {
-            sd->final_rng = d.rng;
-            sd->tell_frac = d.tell_frac();
-            sd->n_pulses = zero_frame ? 0u : n_pulses;
-        }
-    }
-    __syncwarp();
-    // side info: one coalesced copy
-    {
-        uint32_t *dst = reinterpret_cast<uint32_t *>(A.side + stream);
-        for (uint32_t i = lane; i < sizeof(opn_synth_side) / 4u; i += 32u) dst[i] = s_side[i];
-    }
-    if (zero_frame) {
-        if (coef) for (int i = lane; i < C * nf; i += 32) coef[i] = 0.0f;
-        if (yo) for (int i = lane; i < C * nf; i += 32) yo[i] = 0;
+    opn_synth_side *sd = A.side + stream;
+    uint32_t *sw = reinterpret_cast<uint32_t *>(sd);
+    constexpr uint32_t SIDE_WORDS = sizeof(opn_synth_side) / 4u;
+    if (status == ITEM_LOST) {
+        for (uint32_t i = 0; i < SIDE_WORDS; i++) sw[i] = 0u;
         return;
     }
-    // ------------------------------------------------------------------ phase B
+    RangeDec d;
+    d.init(src, len);
+    const uint32_t silence = d.bit_logp(15u);
+    if (silence) {
+        for (uint32_t i = 0; i < SIDE_WORDS; i++) sw[i] = 0u;
+        sd->silence = 1;
+        sd->final_rng = d.rng;
+        sd->tell_frac = d.tell_frac();
+        return;
+    }
+    const uint32_t postfilter = d.bit_logp(1u);
+    uint32_t octave = 0u, period = 0u, gain_idx = 0u, tapset = 0u;
+    if (postfilter) {
+        octave = d.uint(6u);
+        period = (16u << octave) + d.bits(4u + octave) - 1u;
+        gain_idx = d.bits(3u);
+        tapset = d.icdf(g_tab.tapset_icdf, 2u);
+    }
+    const uint32_t transient = d.bit_logp(3u);
+    const uint32_t intra = d.bit_logp(3u);
+    sd->silence = 0;
+    sd->postfilter = (int32_t)postfilter;
+    sd->octave = (int32_t)octave;
+    sd->period = (int32_t)period;
+    sd->gain_idx = (int32_t)gain_idx;
+    sd->tapset = (int32_t)tapset;
+    sd->transient = (int32_t)transient;
+    sd->intra = (int32_t)intra;
+    for (int b = 0; b < 21; b++) {
+        const uint32_t decay = 6000u + 400u * (uint32_t)b;
+        const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;  // mod.rs:530-534
+        for (int c = 0; c < C; c++) sd->coarse[c][b] = d.laplace(fs0, decay);
+        if (C == 1) sd->coarse[1][b] = 0;
+    }
+    for (int b = 0; b < 21; b++) {
+        for (int c = 0; c < C; c++) sd->fine[c][b] = (int32_t)d.bits(2u);
+        if (C == 1) sd->fine[1][b] = 0;
+    }
+    uint32_t *idx = A.idx + (size_t)stream * SYNTH_MAX_ENTRIES;
+    uint32_t n_pulses = 0u;
+    for (int e = 0; e < ne; e++) {
+        const SynthEntry E = s_ent[e];
+        uint32_t v;
+        if (E.n == 1) {
+            v = d.bits(1u);
+            n_pulses += 1u;
+        } else {
+            v = d.uint_precomputed(E.ft_minus1, E.ft1, E.ftb, E.magic, E.sh);
+            n_pulses += E.k;
+        }
+        idx[e] = v;
+    }
+    sd->final_rng = d.rng;
+    sd->tell_frac = d.tell_frac();
+    sd->n_pulses = n_pulses;
+}
+
+__global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolArgs A)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
+    uint16_t *s_row = reinterpret_cast<uint16_t *>(s_pvq + PVQ_TABLE_WORDS);
+    SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(s_row + 16);
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) + (size_t)warp * SYM_EXPAND_WARP_BYTES;
+    int16_t *s_y = reinterpret_cast<int16_t *>(wbase);  // 8-byte aligned: read back as 4 x int16
+    uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_y + SYM_Y16);
+    float *s_gain = reinterpret_cast<float *>(s_idx + SYNTH_MAX_ENTRIES);
+
+    const int lm = A.lm, C = A.channels, nf = 120 << lm;
+    const int ne = g_tab.synth_n_entries[lm][C - 1];
+    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) s_pvq[i] = g_tab.pvq_u_data[i];
+    if (threadIdx.x < 15) s_row[threadIdx.x] = g_tab.pvq_u_row[threadIdx.x];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_ent);
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) dst[i] = src[i];
+    }
+    const uint32_t item = blockIdx.x * SYM_WARPS_PER_CTA + warp;
+    const bool in_range = item < A.n_items;
+    const uint32_t stream = in_range ? (A.stream_idx ? A.stream_idx[item] : item) : 0u;
+    const int32_t status = in_range ? A.status[stream] : -1;
+    const bool zero_frame = status == ITEM_LOST || (status >= 0 && A.side[stream].silence != 0);
+    if (status >= 0 && !zero_frame)
+        for (int e = lane; e < ne; e += 32) s_idx[e] = A.idx[(size_t)stream * SYNTH_MAX_ENTRIES + e];
+    __syncthreads();
+    if (status < 0) return;
+
+    float4 *coef4 = A.coef ? reinterpret_cast<float4 *>(A.coef + (size_t)stream * C * nf) : nullptr;
+    int4 *yo4 = A.y_out ? reinterpret_cast<int4 *>(A.y_out + (size_t)stream * C * nf) : nullptr;
+    const int nvec = C * nf / 4;
+    if (zero_frame) {
+        for (int i = lane; i < nvec; i += 32) {
+            if (coef4) coef4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yo4) yo4[i] = make_int4(0, 0, 0, 0);
+        }
+        return;
+    }
+    // index -> pulse vector, parts dealt longest-first to the lanes (tables: opn_kernels.cu)
     {
         PvqTable T{s_pvq, s_row};
-        for (int e = lane; e < ne; e += 32) {
+        const uint8_t *mine = g_tab.synth_lane_entries[lm][C - 1][lane];
+#pragma unroll 1
+        for (int slot = 0; slot < SYNTH_LANE_SLOTS; slot++) {
+            const uint32_t e = mine[slot];
+            if (e == 0xFFu) break;
             const SynthEntry E = s_ent[e];
             const uint32_t v = s_idx[e];
             float g;
@@ -275,22 +297,26 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_symbols(Symbol
         }
     }
     __syncwarp();
-    // ------------------------------------------------------------------ phase C
+    // pulses x gain -> coefficient rows, 4 bins per lane and step (entry_of: bin -> part, 0xFF above the last band)
     {
-        const int top = 100 << lm;  // bins above the last band stay zero
-        for (int c = 0; c < C; c++)
-            for (int i = top + (int)lane; i < nf; i += 32) {
-                if (coef) coef[c * nf + i] = 0.0f;
-                if (yo) yo[c * nf + i] = 0;
-            }
-        for (int e = 0; e < ne; e++) {
-            const SynthEntry E = s_ent[e];
-            const float g = s_gain[e];
-            for (int j = lane; j < (int)E.n; j += 32) {
-                const int32_t yv = s_y[E.base + j];
-                if (coef) coef[E.base + j] = (float)yv * g;
-                if (yo) yo[E.base + j] = yv;
-            }
+        const uint32_t *ent4 = reinterpret_cast<const uint32_t *>(g_tab.synth_entry_of[lm][C - 1]);
+        const uint2 *y4 = reinterpret_cast<const uint2 *>(s_y);
+        for (int i = lane; i < nvec; i += 32) {
+            const uint32_t ids = __ldg(ent4 + i);
+            const uint2 yr = y4[i];
+            int4 yv;
+            float4 cv;
+            const uint32_t e0 = ids & 0xFFu, e1 = (ids >> 8) & 0xFFu, e2 = (ids >> 16) & 0xFFu, e3 = ids >> 24;
+            yv.x = e0 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.x & 0xFFFFu);
+            yv.y = e1 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.x >> 16);
+            yv.z = e2 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.y & 0xFFFFu);
+            yv.w = e3 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.y >> 16);
+            cv.x = e0 == 0xFFu ? 0.0f : (float)yv.x * s_gain[e0];
+            cv.y = e1 == 0xFFu ? 0.0f : (float)yv.y * s_gain[e1];
+            cv.z = e2 == 0xFFu ? 0.0f : (float)yv.z * s_gain[e2];
+            cv.w = e3 == 0xFFu ? 0.0f : (float)yv.w * s_gain[e3];
+            if (coef4) coef4[i] = cv;
+            if (yo4) yo4[i] = yv;
         }
     }
 }
