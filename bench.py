@@ -187,7 +187,7 @@ def main():
     d_off = (torch.arange(n, dtype=torch.int64, device=dev) * PKT_BYTES).to(torch.int32)
     d_len = torch.full((n,), PKT_BYTES, dtype=torch.int32, device=dev)
     d_res = torch.zeros(n, dtype=torch.int32, device=dev)
-    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY  # packets are resident: entropy stage may run a step ahead
 
     def step_resident(f):
         dec.decode_float_ptrs(d_arena.data_ptr() + f * step_bytes, d_off.data_ptr(), d_len.data_ptr(), None, 0, NF,

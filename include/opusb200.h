@@ -79,6 +79,10 @@ typedef struct {
 
 #define OPN_FLAG_DEVICE_PTRS 1u  /* arena/offsets/lens/pcm/results are device pointers; call is asynchronous */
 #define OPN_FLAG_NO_PCM_COPY 2u  /* leave PCM in the device ring only (read it with opn_batch_ring) */
+#define OPN_FLAG_INPUTS_READY 4u /* with DEVICE_PTRS: arena/offsets/lens are already complete in device memory and stay
+                                  * untouched until opn_batch_synchronize, so the entropy stage of this call may overlap the
+                                  * PVQ/IMDCT stage of the previous one (without the flag it is ordered after everything
+                                  * enqueued on opn_batch_cuda_stream) */
 
 int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out);
 void opn_batch_destroy(opn_batch *b);

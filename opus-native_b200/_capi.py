@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libopusb200.so")
 
 OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL = range(10)
-FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY = 1, 2
+FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY = 1, 2, 4
 OP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4")])
 OUT_DTYPE = np.dtype([("value", "<u4"), ("tell_frac", "<u4"), ("rng", "<u4")])
 SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra")]

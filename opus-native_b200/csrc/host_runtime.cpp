@@ -115,12 +115,21 @@ struct opn_batch {
     opn_config cfg{};
     float gain = 1.0f;
     cudaStream_t stream = nullptr;
+    // The entropy stage (k_synth_rangedec: one lane per packet, latency-bound, a few hundred warps)
+    // runs on its own stream and may run one step ahead of the PVQ/IMDCT stage: its outputs are
+    // double-buffered (set = step parity) and handed over with events.
+    cudaStream_t stream_rd = nullptr;
+    cudaEvent_t ev_rd[2] = {nullptr, nullptr};   // range decode of set p finished
+    cudaEvent_t ev_use[2] = {nullptr, nullptr};  // last consumer of set p finished
+    cudaEvent_t ev_in = nullptr;                 // inputs ordered on `stream` are complete
+    bool use_recorded[2] = {false, false};
+    int set = 0;
     // per-stream state (device, SoA)
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef = nullptr;
-    uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx = nullptr;
+    uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[2] = {nullptr, nullptr};
     PfState *d_pf = nullptr;
-    opn_synth_side *d_side = nullptr;
-    int32_t *d_status = nullptr;
+    opn_synth_side *d_side[2] = {nullptr, nullptr};
+    int32_t *d_status[2] = {nullptr, nullptr};
     // host-path staging (device + pinned host)
     uint8_t *d_arena = nullptr;
     size_t arena_cap = 0;
@@ -185,10 +194,14 @@ cudaError_t do_symbols(opn_batch *b, const void *a) { return launch_synth_symbol
 cudaError_t do_imdct(opn_batch *b, const void *a) { return launch_imdct_post(*static_cast<const ImdctArgs *>(a), b->stream); }
 
 // One bucket = items of equal frame size that may run concurrently.
+// inputs_on: 0 = the packets are already complete in device memory (the entropy stage may start at once),
+//            1 = they are ordered on b->stream, 2 = they are ordered on b->stream_rd (host path uploads there).
 int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens,
                const uint32_t *d_stream_idx, const uint32_t *d_dense_off, uint32_t n_items, int lm, int has_toc,
-               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result)
+               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on)
 {
+    const int p = b->set;
+    b->set ^= 1;
     SymbolArgs s{};
     s.arena = d_arena;
     s.offsets = d_offsets;
@@ -198,19 +211,38 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.lm = lm;
     s.channels = b->cfg.channels;
     s.has_toc = has_toc;
-    s.side = b->d_side;
-    s.status = b->d_status;
+    s.side = b->d_side[p];
+    s.status = b->d_status[p];
     s.coef = b->d_coef;
     s.y_out = nullptr;
-    s.idx = b->d_idx;
+    s.idx = b->d_idx[p];
     s.pkt_cap = pkt_cap;
-    int rc = timed_launch(b, 0, do_symbols, &s);
-    if (rc) return rc;
-    b->launches[0] += 1;  // kernel 0 is two launches: k_synth_rangedec + k_synth_expand
+    int rc;
+    if (b->timing) {
+        // measurement pass: everything in order on one stream, events around each stage
+        if (inputs_on == 2) {
+            CU(cudaEventRecord(b->ev_in, b->stream_rd));
+            CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
+        }
+        rc = timed_launch(b, 0, do_symbols, &s);
+        if (rc) return rc;
+        b->launches[0] += 1;  // stage 0 is two launches: k_synth_rangedec + k_synth_expand
+    } else {
+        if (inputs_on == 1) {
+            CU(cudaEventRecord(b->ev_in, b->stream));
+            CU(cudaStreamWaitEvent(b->stream_rd, b->ev_in, 0));
+        }
+        if (b->use_recorded[p]) CU(cudaStreamWaitEvent(b->stream_rd, b->ev_use[p], 0));  // set p is free again
+        CU(launch_synth_rangedec(s, b->stream_rd));
+        CU(cudaEventRecord(b->ev_rd[p], b->stream_rd));
+        CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
+        CU(launch_synth_expand(s, b->stream));
+        b->launches[0] += 2;
+    }
     ImdctArgs m{};
     m.coef = b->d_coef;
-    m.side = b->d_side;
-    m.status = b->d_status;
+    m.side = b->d_side[p];
+    m.status = b->d_status[p];
     m.stream_idx = d_stream_idx;
     m.dense_off = d_dense_off;
     m.n_items = n_items;
@@ -226,7 +258,11 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.gain = b->gain;
     m.result = d_result;
     m.final_range = b->d_final;
-    return timed_launch(b, 1, do_imdct, &m);
+    rc = timed_launch(b, 1, do_imdct, &m);
+    if (rc) return rc;
+    CU(cudaEventRecord(b->ev_use[p], b->stream));
+    b->use_recorded[p] = true;
+    return OPN_OK;
 }
 
 // PLC sizing of decode_native(None)/decode_frame(None), src/decoder.rs:427-441 and 467-513.
@@ -293,15 +329,21 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->gain = host_gain_from_q8(cfg->gain_q8);
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_rd, cudaStreamNonBlocking);
+    for (int q = 0; q < 2 && e == cudaSuccess; q++) {
+        e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_use[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_side[q], n * sizeof(opn_synth_side));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_carry, n * C * 60 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring, n * C * RING_SAMPLES * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_coef, n * C * 960 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_idx, n * 72 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring_pos, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_side, n * sizeof(opn_synth_side));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_status, n * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_softclip, n * 2 * sizeof(float));
     if (e != cudaSuccess) {
         opn_batch_destroy(b);
@@ -324,18 +366,25 @@ void opn_batch_destroy(opn_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
+    if (b->stream_rd) cudaStreamSynchronize(b->stream_rd);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    for (int q = 0; q < 2; q++) {
+        if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
+        if (b->ev_use[q]) cudaEventDestroy(b->ev_use[q]);
+        cudaFree(b->d_idx[q]);
+        cudaFree(b->d_side[q]);
+        cudaFree(b->d_status[q]);
+    }
+    if (b->ev_in) cudaEventDestroy(b->ev_in);
+    if (b->stream_rd) cudaStreamDestroy(b->stream_rd);
     b->ev[0].destroy();
     b->ev[1].destroy();
     cudaFree(b->d_carry);
     cudaFree(b->d_ring);
     cudaFree(b->d_coef);
-    cudaFree(b->d_idx);
     cudaFree(b->d_ring_pos);
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
-    cudaFree(b->d_side);
-    cudaFree(b->d_status);
     cudaFree(b->d_softclip);
     cudaFree(b->d_arena);
     cudaFree(b->d_items);
@@ -355,8 +404,13 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     CU(cudaMemsetAsync(b->d_ring_pos, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_final, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_pf, 0, n * sizeof(PfState), b->stream));
-    CU(cudaMemsetAsync(b->d_side, 0, n * sizeof(opn_synth_side), b->stream));
-    CU(cudaMemsetAsync(b->d_status, 0, n * sizeof(int32_t), b->stream));
+    CU(cudaStreamSynchronize(b->stream_rd));
+    for (int q = 0; q < 2; q++) {
+        CU(cudaMemsetAsync(b->d_side[q], 0, n * sizeof(opn_synth_side), b->stream));
+        CU(cudaMemsetAsync(b->d_status[q], 0, n * sizeof(int32_t), b->stream));
+        b->use_recorded[q] = false;
+    }
+    b->set = 0;
     CU(cudaMemsetAsync(b->d_softclip, 0, n * 2 * sizeof(float), b->stream));
     CU(cudaStreamSynchronize(b->stream));
     std::fill(b->last_nf.begin(), b->last_nf.end(), 120);
@@ -455,10 +509,11 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             b->h_items[2 * cap + k] = items[k].stream;
             b->h_items[3 * cap + k] = items[k].dense_off;
         }
-        if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream));
+        // uploads go on the entropy stage's stream: it is the first consumer
+        if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_rd));
         for (int q = 0; q < 4; q++)
             CU(cudaMemcpyAsync(b->d_items + q * cap, b->h_items + q * cap, items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                               b->stream));
+                               b->stream_rd));
         const uint32_t pkt_cap = (max_len + 15u) & ~15u;
         size_t k0 = 0;
         while (k0 < items.size()) {
@@ -466,7 +521,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             while (k1 < items.size() && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
             rc = run_bucket(b, b->d_arena, b->d_items + k0, b->d_items + cap + k0, b->d_items + 2 * cap + k0,
                             b->d_items + 3 * cap + k0, (uint32_t)(k1 - k0), items[k0].lm, 0, pkt_cap,
-                            want_pcm ? b->d_dense : nullptr, b->dense_cap, nullptr);
+                            want_pcm ? b->d_dense : nullptr, b->dense_cap, nullptr, 2);
             if (rc) return rc;
             k0 = k1;
         }
@@ -507,13 +562,15 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
     if (dense && (pcm_stride_floats < frame_size * (size_t)C || (pcm_stride_floats & 3) ||
                   (reinterpret_cast<uintptr_t>(dense) & 15)))
         return OPN_ERR_BAD_ARG;
-    return run_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, lm, 1, 1280u, dense, pcm_stride_floats, result_per_stream);
+    return run_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, lm, 1, 1280u, dense, pcm_stride_floats, result_per_stream,
+                      (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1);
 }
 
 int opn_batch_synchronize(opn_batch *b)
 {
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream_rd));
     CU(cudaStreamSynchronize(b->stream));
     return OPN_OK;
 }

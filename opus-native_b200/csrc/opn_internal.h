@@ -59,7 +59,9 @@ cudaError_t upload_tables(int device);  // idempotent per device
 cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
                                    const opn_op *ops, uint32_t n_ops, const uint8_t *icdf_pool, opn_op_out *out,
                                    int32_t *y_out, uint32_t y_stride, uint32_t pkt_cap, cudaStream_t st);
-cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st);
+cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st);   // both stages on one stream
+cudaError_t launch_synth_rangedec(const SymbolArgs &a, cudaStream_t st);  // stage 0a: one lane per packet
+cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st);    // stage 0b: one warp per packet
 cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st);
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
                             int nblk, cudaStream_t st);

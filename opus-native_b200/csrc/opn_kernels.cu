@@ -175,16 +175,28 @@ cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets
     return cudaGetLastError();
 }
 
-cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
+cudaError_t launch_synth_rangedec(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
     if (!a.idx) return cudaErrorInvalidValue;
     k_synth_rangedec<<<(a.n_items + 31u) / 32u, 32, 0, st>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    if (!a.idx) return cudaErrorInvalidValue;
     const uint32_t grid = (a.n_items + SYM_WARPS_PER_CTA - 1) / SYM_WARPS_PER_CTA;
     k_synth_expand<<<grid, SYM_WARPS_PER_CTA * 32, synth_expand_smem(), st>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
+{
+    cudaError_t e = launch_synth_rangedec(a, st);
+    if (e != cudaSuccess) return e;
+    return launch_synth_expand(a, st);
 }
 
 cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st)
