@@ -116,20 +116,21 @@ struct opn_batch {
     float gain = 1.0f;
     cudaStream_t stream = nullptr;
     // The entropy stage (k_synth_rangedec: one lane per packet, latency-bound, a few hundred warps)
-    // runs on its own stream and may run one step ahead of the PVQ/IMDCT stage: its outputs are
-    // double-buffered (set = step parity) and handed over with events.
-    cudaStream_t stream_rd = nullptr;
-    cudaEvent_t ev_rd[2] = {nullptr, nullptr};   // range decode of set p finished
-    cudaEvent_t ev_use[2] = {nullptr, nullptr};  // last consumer of set p finished
-    cudaEvent_t ev_in = nullptr;                 // inputs ordered on `stream` are complete
-    bool use_recorded[2] = {false, false};
+    // runs on its own streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
+    // live in NSETS buffer sets handed over with events.
+    static constexpr int NSETS = 4, NRD = 2;
+    cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: two entropy stages may overlap each other
+    cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
+    cudaEvent_t ev_use[NSETS] = {};       // last consumer of set p finished
+    cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` are complete
+    bool use_recorded[NSETS] = {};
     int set = 0;
     // per-stream state (device, SoA)
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef = nullptr;
-    uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[2] = {nullptr, nullptr};
+    uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[NSETS] = {};
     PfState *d_pf = nullptr;
-    opn_synth_side *d_side[2] = {nullptr, nullptr};
-    int32_t *d_status[2] = {nullptr, nullptr};
+    opn_synth_side *d_side[NSETS] = {};
+    int32_t *d_status[NSETS] = {};
     // host-path staging (device + pinned host)
     uint8_t *d_arena = nullptr;
     size_t arena_cap = 0;
@@ -201,7 +202,8 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
                uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on)
 {
     const int p = b->set;
-    b->set ^= 1;
+    b->set = (p + 1) % opn_batch::NSETS;
+    cudaStream_t srd = b->stream_rd[p % opn_batch::NRD];
     SymbolArgs s{};
     s.arena = d_arena;
     s.offsets = d_offsets;
@@ -221,7 +223,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     if (b->timing) {
         // measurement pass: everything in order on one stream, events around each stage
         if (inputs_on == 2) {
-            CU(cudaEventRecord(b->ev_in, b->stream_rd));
+            CU(cudaEventRecord(b->ev_in, b->stream_rd[0]));
             CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
         }
         rc = timed_launch(b, 0, do_symbols, &s);
@@ -230,11 +232,14 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     } else {
         if (inputs_on == 1) {
             CU(cudaEventRecord(b->ev_in, b->stream));
-            CU(cudaStreamWaitEvent(b->stream_rd, b->ev_in, 0));
+            CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
+        } else if (inputs_on == 2 && srd != b->stream_rd[0]) {  // the host path uploads on stream_rd[0]
+            CU(cudaEventRecord(b->ev_in, b->stream_rd[0]));
+            CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
         }
-        if (b->use_recorded[p]) CU(cudaStreamWaitEvent(b->stream_rd, b->ev_use[p], 0));  // set p is free again
-        CU(launch_synth_rangedec(s, b->stream_rd));
-        CU(cudaEventRecord(b->ev_rd[p], b->stream_rd));
+        if (b->use_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_use[p], 0));  // set p is free again
+        CU(launch_synth_rangedec(s, srd));
+        CU(cudaEventRecord(b->ev_rd[p], srd));
         CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
         CU(launch_synth_expand(s, b->stream));
         b->launches[0] += 2;
@@ -329,8 +334,8 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->gain = host_gain_from_q8(cfg->gain_q8);
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_rd, cudaStreamNonBlocking);
-    for (int q = 0; q < 2 && e == cudaSuccess; q++) {
+    for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++) e = cudaStreamCreateWithFlags(&b->stream_rd[q], cudaStreamNonBlocking);
+    for (int q = 0; q < opn_batch::NSETS && e == cudaSuccess; q++) {
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_use[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
@@ -366,9 +371,10 @@ void opn_batch_destroy(opn_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
-    if (b->stream_rd) cudaStreamSynchronize(b->stream_rd);
+    for (int q = 0; q < opn_batch::NRD; q++)
+        if (b->stream_rd[q]) cudaStreamSynchronize(b->stream_rd[q]);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < opn_batch::NSETS; q++) {
         if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
         if (b->ev_use[q]) cudaEventDestroy(b->ev_use[q]);
         cudaFree(b->d_idx[q]);
@@ -376,7 +382,8 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(b->d_status[q]);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
-    if (b->stream_rd) cudaStreamDestroy(b->stream_rd);
+    for (int q = 0; q < opn_batch::NRD; q++)
+        if (b->stream_rd[q]) cudaStreamDestroy(b->stream_rd[q]);
     b->ev[0].destroy();
     b->ev[1].destroy();
     cudaFree(b->d_carry);
@@ -404,8 +411,8 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     CU(cudaMemsetAsync(b->d_ring_pos, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_final, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_pf, 0, n * sizeof(PfState), b->stream));
-    CU(cudaStreamSynchronize(b->stream_rd));
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
+    for (int q = 0; q < opn_batch::NSETS; q++) {
         CU(cudaMemsetAsync(b->d_side[q], 0, n * sizeof(opn_synth_side), b->stream));
         CU(cudaMemsetAsync(b->d_status[q], 0, n * sizeof(int32_t), b->stream));
         b->use_recorded[q] = false;
@@ -510,10 +517,10 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             b->h_items[3 * cap + k] = items[k].dense_off;
         }
         // uploads go on the entropy stage's stream: it is the first consumer
-        if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_rd));
+        if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_rd[0]));
         for (int q = 0; q < 4; q++)
             CU(cudaMemcpyAsync(b->d_items + q * cap, b->h_items + q * cap, items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                               b->stream_rd));
+                               b->stream_rd[0]));
         const uint32_t pkt_cap = (max_len + 15u) & ~15u;
         size_t k0 = 0;
         while (k0 < items.size()) {
@@ -570,7 +577,7 @@ int opn_batch_synchronize(opn_batch *b)
 {
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
-    CU(cudaStreamSynchronize(b->stream_rd));
+    for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
     CU(cudaStreamSynchronize(b->stream));
     return OPN_OK;
 }

@@ -140,8 +140,13 @@ __host__ __device__ constexpr size_t synth_expand_smem()
 __global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
 {
     __shared__ SynthEntry s_ent[SYNTH_MAX_ENTRIES];
+    __shared__ uint32_t s_fs0[21];  // get_start_freq(decay) per band (src/range_coder/mod.rs:530-534)
     const uint32_t lane = threadIdx.x;
     const int lm = A.lm, C = A.channels;
+    if (lane < 21u) {
+        const uint32_t decay = 6000u + 400u * lane;
+        s_fs0[lane] = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;
+    }
     const int ne = g_tab.synth_n_entries[lm][C - 1];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
     sd->intra = (int32_t)intra;
     for (int b = 0; b < 21; b++) {
         const uint32_t decay = 6000u + 400u * (uint32_t)b;
-        const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;  // mod.rs:530-534
+        const uint32_t fs0 = s_fs0[b];
         for (int c = 0; c < C; c++) sd->coarse[c][b] = d.laplace(fs0, decay);
         if (C == 1) sd->coarse[1][b] = 0;
     }
