@@ -390,7 +390,7 @@ __device__ __forceinline__ float cwrsi_warp(const PvqTable &T, int32_t *y, uint3
 
 // cwrsi (pvc.rs:182-284) executed by ONE lane: the codeword index of a part is known, so 32 lanes
 // expand 32 different parts at the same time (the entropy decoder does not depend on the result).
-// Writes 16-bit pulses (|y| <= K <= 128) and returns yy.
+// Writes the NONZERO 16-bit pulses (|y| <= K <= 128) into y, which the caller has zeroed, and returns yy.
 __device__ __forceinline__ float cwrsi_lane(const PvqTable &T, int16_t *y, uint32_t n, uint32_t k, uint32_t i)
 {
     int32_t yy = 0;
@@ -422,24 +422,33 @@ __device__ __forceinline__ float cwrsi_lane(const PvqTable &T, int16_t *y, uint3
             *y++ = (int16_t)val;
             yy += val * val;
         } else {  // pvc.rs:232-258
-            p = T.data[T.row[k] + n];
-            uint32_t q = T.data[T.row[k + 1u] + n];
-            if (p <= i && i < q) {
+            // Runs of empty dimensions are the common case here (k < n): the two row offsets only
+            // change when k does, and an empty dimension is just "i -= U(k,n); next n" (y is pre-zeroed).
+            const uint32_t rk = T.row[k], rk1 = T.row[k + 1u];
+            uint32_t q;
+            bool empty;
+            for (;;) {
+                p = T.data[rk + n];
+                q = T.data[rk1 + n];
+                empty = p <= i && i < q;
+                if (!empty) break;
                 i -= p;
-                *y++ = 0;
-            } else {
-                s = i >= q ? -1 : 0;
-                i -= (uint32_t)((int32_t)q & s);
-                k0 = k;
-                do {
-                    k -= 1u;
-                    p = T.data[T.row[k] + n];
-                } while (p > i);
-                i -= p;
-                val = ((int32_t)k0 - (int32_t)k + s) ^ s;
-                *y++ = (int16_t)val;
-                yy += val * val;
+                y++;
+                n -= 1u;
+                if (n <= 2u || k >= n) break;
             }
+            if (empty) continue;  // reached the closed-form tail (n == 2) or the k >= n regime: dispatch again
+            s = i >= q ? -1 : 0;
+            i -= (uint32_t)((int32_t)q & s);
+            k0 = k;
+            do {
+                k -= 1u;
+                p = T.data[T.row[k] + n];
+            } while (p > i);
+            i -= p;
+            val = ((int32_t)k0 - (int32_t)k + s) ^ s;
+            *y++ = (int16_t)val;
+            yy += val * val;
         }
         n -= 1u;
     }

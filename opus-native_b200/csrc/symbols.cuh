@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
     uint16_t *s_row = reinterpret_cast<uint16_t *>(s_pvq + PVQ_TABLE_WORDS);
     SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(s_row + 16);
     uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) + (size_t)warp * SYM_EXPAND_WARP_BYTES;
-    int16_t *s_y = reinterpret_cast<int16_t *>(wbase);  // 8-byte aligned: read back as 4 x int16
+    int16_t *s_y = reinterpret_cast<int16_t *>(wbase);  // 16-byte aligned: zeroed as uint4, read back as 4 x int16
     uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_y + SYM_Y16);
     float *s_gain = reinterpret_cast<float *>(s_idx + SYNTH_MAX_ENTRIES);
 
@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
         }
         return;
     }
-    // index -> pulse vector, parts dealt longest-first to the lanes (tables: opn_kernels.cu)
+    // index -> pulse vector, parts dealt longest-first to the lanes (tables: opn_kernels.cu); cwrsi_lane
+    // only stores the nonzero pulses
+    for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
     {
         PvqTable T{s_pvq, s_row};
         const uint8_t *mine = g_tab.synth_lane_entries[lm][C - 1][lane];
@@ -312,10 +315,10 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
             int4 yv;
             float4 cv;
             const uint32_t e0 = ids & 0xFFu, e1 = (ids >> 8) & 0xFFu, e2 = (ids >> 16) & 0xFFu, e3 = ids >> 24;
-            yv.x = e0 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.x & 0xFFFFu);
-            yv.y = e1 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.x >> 16);
-            yv.z = e2 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.y & 0xFFFFu);
-            yv.w = e3 == 0xFFu ? 0 : (int32_t)(int16_t)(yr.y >> 16);
+            yv.x = (int32_t)(int16_t)(yr.x & 0xFFFFu);  // bins without a part were zeroed above
+            yv.y = (int32_t)(int16_t)(yr.x >> 16);
+            yv.z = (int32_t)(int16_t)(yr.y & 0xFFFFu);
+            yv.w = (int32_t)(int16_t)(yr.y >> 16);
             cv.x = e0 == 0xFFu ? 0.0f : (float)yv.x * s_gain[e0];
             cv.y = e1 == 0xFFu ? 0.0f : (float)yv.y * s_gain[e1];
             cv.z = e2 == 0xFFu ? 0.0f : (float)yv.z * s_gain[e2];
