@@ -122,7 +122,10 @@ struct opn_batch {
     cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: two entropy stages may overlap each other
     cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
     cudaEvent_t ev_use[NSETS] = {};       // last consumer of set p finished
-    cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` are complete
+    cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` / `stream_up` are complete
+    static constexpr int MAX_CHUNKS = 8;
+    cudaStream_t stream_up = nullptr, stream_dn = nullptr;  // host path: item/packet upload, PCM download
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};                  // PVQ/IMDCT stage of a chunk finished
     bool use_recorded[NSETS] = {};
     int set = 0;
     // per-stream state (device, SoA)
@@ -196,7 +199,7 @@ cudaError_t do_imdct(opn_batch *b, const void *a) { return launch_imdct_post(*st
 
 // One bucket = items of equal frame size that may run concurrently.
 // inputs_on: 0 = the packets are already complete in device memory (the entropy stage may start at once),
-//            1 = they are ordered on b->stream, 2 = they are ordered on b->stream_rd (host path uploads there).
+//            1 = they are ordered on b->stream, 2 = they are ordered on b->stream_up (host path).
 int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens,
                const uint32_t *d_stream_idx, const uint32_t *d_dense_off, uint32_t n_items, int lm, int has_toc,
                uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on)
@@ -223,7 +226,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     if (b->timing) {
         // measurement pass: everything in order on one stream, events around each stage
         if (inputs_on == 2) {
-            CU(cudaEventRecord(b->ev_in, b->stream_rd[0]));
+            CU(cudaEventRecord(b->ev_in, b->stream_up));
             CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
         }
         rc = timed_launch(b, 0, do_symbols, &s);
@@ -233,8 +236,8 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
         if (inputs_on == 1) {
             CU(cudaEventRecord(b->ev_in, b->stream));
             CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
-        } else if (inputs_on == 2 && srd != b->stream_rd[0]) {  // the host path uploads on stream_rd[0]
-            CU(cudaEventRecord(b->ev_in, b->stream_rd[0]));
+        } else if (inputs_on == 2) {
+            CU(cudaEventRecord(b->ev_in, b->stream_up));
             CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
         }
         if (b->use_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_use[p], 0));  // set p is free again
@@ -343,6 +346,9 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_up, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_dn, cudaStreamNonBlocking);
+    for (int q = 0; q < opn_batch::MAX_CHUNKS && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&b->ev_chunk[q], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_carry, n * C * 60 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring, n * C * RING_SAMPLES * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_coef, n * C * 960 * sizeof(float));
@@ -382,6 +388,16 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(b->d_status[q]);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
+    for (int q = 0; q < opn_batch::MAX_CHUNKS; q++)
+        if (b->ev_chunk[q]) cudaEventDestroy(b->ev_chunk[q]);
+    if (b->stream_dn) {
+        cudaStreamSynchronize(b->stream_dn);
+        cudaStreamDestroy(b->stream_dn);
+    }
+    if (b->stream_up) {
+        cudaStreamSynchronize(b->stream_up);
+        cudaStreamDestroy(b->stream_up);
+    }
     for (int q = 0; q < opn_batch::NRD; q++)
         if (b->stream_rd[q]) cudaStreamDestroy(b->stream_rd[q]);
     b->ev[0].destroy();
@@ -427,124 +443,153 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     return OPN_OK;
 }
 
+// Host-buffer path.  The streams are cut into chunks that flow through a five-stage pipeline:
+// host parse (decode_native's TOC/frame split) -> item upload -> entropy stage -> PVQ/IMDCT stage -> PCM
+// download, so that parsing, kernels and the PCIe copy of different chunks overlap.  The download is
+// the long pole (31.5 MB per 4096 stereo 20 ms frames); everything else hides behind it.
 static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, float *pcm,
                              size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags, int soft_clip)
 {
     const uint32_t n = b->n;
     const int C = b->cfg.channels;
+    // pre-pass: bytes to upload and an upper bound of the number of frames (items)
+    size_t arena_end = 0, items_ub = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (lens[i] == 0) {
+            items_ub += frame_size / 120;
+            continue;
+        }
+        arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
+        const int fc = opn_packet_frame_count(arena + offsets[i], lens[i]);
+        items_ub += fc > 0 ? (size_t)fc : 1;
+    }
+    const size_t dense_stride = (frame_size * (size_t)C + 3) & ~(size_t)3;
+    int rc = batch_alloc_staging(b, arena_end, items_ub, dense_stride);
+    if (rc) return rc;
+    const bool want_pcm = pcm != nullptr && !(flags & OPN_FLAG_NO_PCM_COPY);
+    if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_up));
+
+    const uint32_t n_chunks = std::min<uint32_t>(opn_batch::MAX_CHUNKS, std::max<uint32_t>(1u, n / 1024u));
+    const size_t cap = b->items_cap;
     std::vector<Item> items;
-    items.reserve(n);
+    items.reserve(items_ub / n_chunks + 64);
     std::vector<int32_t> res(n, 0);
     std::vector<uint32_t> plc;
-    size_t arena_end = 0;
-    bool any_gap = false;  // some stream leaves part of its dense row unwritten
-    uint32_t max_len = 8;
-    int max_wave = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t len = lens[i];
-        if (len == 0) {  // lost packet: decode_native(None), decoder.rs:427-441
-            if (!b->have_mode[i]) {  // decoder.rs:478-487: nothing decoded yet -> zeros, state untouched
+    size_t kbase = 0;  // items of earlier chunks
+    for (uint32_t ch = 0; ch < n_chunks; ch++) {
+        const uint32_t s0 = (uint32_t)((uint64_t)n * ch / n_chunks), s1 = (uint32_t)((uint64_t)n * (ch + 1) / n_chunks);
+        items.clear();
+        bool any_gap = false;  // some stream of the chunk leaves part of its dense row unwritten
+        uint32_t max_len = 8;
+        for (uint32_t i = s0; i < s1; i++) {
+            const uint32_t len = lens[i];
+            if (len == 0) {  // lost packet: decode_native(None), decoder.rs:427-441
+                if (!b->have_mode[i]) {  // decoder.rs:478-487: nothing decoded yet -> zeros, state untouched
+                    res[i] = (int32_t)frame_size;
+                    any_gap = true;
+                    b->last_duration[i] = (int32_t)frame_size;
+                    continue;
+                }
+                plc.clear();
+                plc_frames(frame_size, b->last_nf[i], plc);
+                uint32_t at = 0;
+                int w = 0;
+                for (uint32_t a : plc) {
+                    items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++});
+                    at += a;
+                }
                 res[i] = (int32_t)frame_size;
-                any_gap = true;
                 b->last_duration[i] = (int32_t)frame_size;
                 continue;
             }
-            plc.clear();
-            plc_frames(frame_size, b->last_nf[i], plc);
-            uint32_t at = 0;
-            int w = 0;
-            for (uint32_t a : plc) {
-                items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++});
-                at += a;
+            const uint8_t *pkt = arena + offsets[i];
+            // decode_native, decoder.rs:322-341
+            const int mode = opn_packet_mode(pkt);
+            const int pfs = opn_packet_samples_per_frame(pkt, 48000);
+            uint32_t fr[48], sz[48];
+            const int count = opn_parse_packet(pkt, len, 0, fr, sz, nullptr, nullptr);
+            if (count < 0) {
+                res[i] = count;
+                any_gap = true;
+                continue;
             }
-            max_wave = std::max(max_wave, w);
-            res[i] = (int32_t)frame_size;
-            b->last_duration[i] = (int32_t)frame_size;
-            continue;
+            if ((size_t)count * (size_t)pfs > frame_size) {  // decoder.rs:388-390
+                res[i] = OPN_ERR_FRAME_SIZE_TOO_SMALL;
+                any_gap = true;
+                continue;
+            }
+            if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C) {
+                // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); mono<->stereo
+                // mapping lives in the stubbed CeltDecoder.
+                res[i] = OPN_ERR_UNIMPLEMENTED;
+                any_gap = true;
+                continue;
+            }
+            const int lm = lm_of_frame((size_t)pfs);
+            for (int w = 0; w < count; w++) {
+                items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), lm, w});
+                max_len = std::max(max_len, sz[w]);
+            }
+            if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
+            res[i] = count * pfs;
+            b->have_mode[i] = 1;
+            b->last_nf[i] = pfs;
+            b->bandwidth[i] = opn_packet_bandwidth(pkt);
+            b->last_duration[i] = count * pfs;
         }
-        const uint8_t *pkt = arena + offsets[i];
-        // decode_native, decoder.rs:322-341
-        const int mode = opn_packet_mode(pkt);
-        const int pfs = opn_packet_samples_per_frame(pkt, 48000);
-        uint32_t fr[48], sz[48];
-        const int count = opn_parse_packet(pkt, len, 0, fr, sz, nullptr, nullptr);
-        if (count < 0) {
-            res[i] = count;
-            any_gap = true;
-            continue;
+        if (kbase + items.size() > cap) return OPN_ERR_INTERNAL;  // the pre-pass bound covers every frame
+        if (want_pcm && any_gap)
+            CU(cudaMemsetAsync(b->d_dense + (size_t)s0 * b->dense_cap, 0, (size_t)(s1 - s0) * b->dense_cap * sizeof(float), b->stream));
+        if (!items.empty()) {
+            // order: wave-major, then frame size, so each (wave, lm) bucket is contiguous
+            std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
+                return x.wave != y.wave ? x.wave < y.wave : x.lm < y.lm;
+            });
+            // one upload per chunk: [offsets | lens | stream ids | dense offsets], each cnt words, at 4*kbase
+            const size_t cnt = items.size();
+            uint32_t *hi = b->h_items + 4 * kbase, *di = b->d_items + 4 * kbase;
+            for (size_t k = 0; k < cnt; k++) {
+                hi[k] = items[k].offset;
+                hi[cnt + k] = items[k].len;
+                hi[2 * cnt + k] = items[k].stream;
+                hi[3 * cnt + k] = items[k].dense_off;
+            }
+            CU(cudaMemcpyAsync(di, hi, 4 * cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream_up));
+            const uint32_t pkt_cap = (max_len + 15u) & ~15u;
+            size_t k0 = 0;
+            while (k0 < cnt) {
+                size_t k1 = k0;
+                while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
+                rc = run_bucket(b, b->d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
+                                items[k0].lm, 0, pkt_cap, want_pcm ? b->d_dense : nullptr, b->dense_cap, nullptr, 2);
+                if (rc) return rc;
+                k0 = k1;
+            }
+            kbase += items.size();
         }
-        if ((size_t)count * (size_t)pfs > frame_size) {  // decoder.rs:388-390
-            res[i] = OPN_ERR_FRAME_SIZE_TOO_SMALL;
-            any_gap = true;
-            continue;
+        if (want_pcm) {
+            if (soft_clip) {
+                // decode_native(soft_clip=true), decoder.rs:413-419.  Reference quirk kept: the slice handed to
+                // pcm_soft_clip is samples[..sample_count] (per-channel count, not x channels).
+                // Only used by the single-stream decoder (one chunk, one row).
+                CU(launch_op_soft_clip(b->d_dense + (size_t)s0 * b->dense_cap, b->dense_cap, (size_t)std::max(res[s0], 0), C, s1 - s0,
+                                       b->d_softclip + (size_t)s0 * 2, b->stream));
+            }
+            // this chunk's PCM rows go home while the next chunk is decoded
+            CU(cudaEventRecord(b->ev_chunk[ch], b->stream));
+            CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
+            const size_t row_bytes = frame_size * (size_t)C * sizeof(float);
+            if (pcm_stride == b->dense_cap && pcm_stride * sizeof(float) == row_bytes)
+                CU(cudaMemcpyAsync(pcm + (size_t)s0 * pcm_stride, b->d_dense + (size_t)s0 * b->dense_cap, (size_t)(s1 - s0) * row_bytes,
+                                   cudaMemcpyDeviceToHost, b->stream_dn));
+            else
+                CU(cudaMemcpy2DAsync(pcm + (size_t)s0 * pcm_stride, pcm_stride * sizeof(float), b->d_dense + (size_t)s0 * b->dense_cap,
+                                     b->dense_cap * sizeof(float), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         }
-        if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C) {
-            // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); mono<->stereo
-            // mapping lives in the stubbed CeltDecoder.
-            res[i] = OPN_ERR_UNIMPLEMENTED;
-            any_gap = true;
-            continue;
-        }
-        const int lm = lm_of_frame((size_t)pfs);
-        for (int w = 0; w < count; w++) {
-            items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), lm, w});
-            max_len = std::max(max_len, sz[w]);
-        }
-        max_wave = std::max(max_wave, count);
-        arena_end = std::max(arena_end, (size_t)offsets[i] + len);
-        if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
-        res[i] = count * pfs;
-        b->have_mode[i] = 1;
-        b->last_nf[i] = pfs;
-        b->bandwidth[i] = opn_packet_bandwidth(pkt);
-        b->last_duration[i] = count * pfs;
-    }
-    const size_t dense_stride = (frame_size * (size_t)C + 3) & ~(size_t)3;
-    int rc = batch_alloc_staging(b, arena_end, items.size(), dense_stride);
-    if (rc) return rc;
-    const bool want_pcm = pcm != nullptr && !(flags & OPN_FLAG_NO_PCM_COPY);
-    if (want_pcm && any_gap) CU(cudaMemsetAsync(b->d_dense, 0, (size_t)n * b->dense_cap * sizeof(float), b->stream));
-    if (!items.empty()) {
-        // order: wave-major, then frame size, so each (wave, lm) bucket is contiguous
-        std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
-            return x.wave != y.wave ? x.wave < y.wave : x.lm < y.lm;
-        });
-        const size_t cap = b->items_cap;
-        for (size_t k = 0; k < items.size(); k++) {
-            b->h_items[k] = items[k].offset;
-            b->h_items[cap + k] = items[k].len;
-            b->h_items[2 * cap + k] = items[k].stream;
-            b->h_items[3 * cap + k] = items[k].dense_off;
-        }
-        // uploads go on the entropy stage's stream: it is the first consumer
-        if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_rd[0]));
-        for (int q = 0; q < 4; q++)
-            CU(cudaMemcpyAsync(b->d_items + q * cap, b->h_items + q * cap, items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                               b->stream_rd[0]));
-        const uint32_t pkt_cap = (max_len + 15u) & ~15u;
-        size_t k0 = 0;
-        while (k0 < items.size()) {
-            size_t k1 = k0;
-            while (k1 < items.size() && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
-            rc = run_bucket(b, b->d_arena, b->d_items + k0, b->d_items + cap + k0, b->d_items + 2 * cap + k0,
-                            b->d_items + 3 * cap + k0, (uint32_t)(k1 - k0), items[k0].lm, 0, pkt_cap,
-                            want_pcm ? b->d_dense : nullptr, b->dense_cap, nullptr, 2);
-            if (rc) return rc;
-            k0 = k1;
-        }
-    }
-    if (want_pcm) {
-        if (soft_clip) {
-            // decode_native(soft_clip=true), decoder.rs:413-419.  Reference quirk kept: the slice handed to
-            // pcm_soft_clip is samples[..sample_count] (per-channel count, not x channels).
-            // Only used by the single-stream decoder, where every row has the same sample_count.
-            CU(launch_op_soft_clip(b->d_dense, b->dense_cap, (size_t)std::max(res[0], 0), C, n, b->d_softclip, b->stream));
-        }
-        CU(cudaMemcpy2DAsync(pcm, pcm_stride * sizeof(float), b->d_dense, b->dense_cap * sizeof(float),
-                             frame_size * (size_t)C * sizeof(float), n, cudaMemcpyDeviceToHost, b->stream));
     }
     if (!soft_clip) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
     CU(cudaStreamSynchronize(b->stream));
+    CU(cudaStreamSynchronize(b->stream_dn));
     if (results) std::memcpy(results, res.data(), n * sizeof(int32_t));
     return OPN_OK;
 }
