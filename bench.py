@@ -241,7 +241,7 @@ def main():
         timed_resident(W, total)
     st = dec.stats(reset=True)
     dec.enable_timing(False)
-    k0_ms, k1_ms = st["ms"][0] / K, st["ms"][1] / K
+    k0_ms, k1_ms, k2_ms = st["ms"][0] / K, st["ms"][1] / K, st["ms"][2] / K
     assert int((d_res != NF).sum().item()) == 0
 
     # ---------------- end-to-end through the host-buffer API ----------------
@@ -307,7 +307,7 @@ def main():
                 "transient_permille": args.transient_permille,
                 "cache": f"inputs larger than L2: {total} distinct packet sets resident in HBM, each read once; "
                          "decoder state (PCM ring + carry + coefficients) is 130 MB per 4096 streams",
-                "per_kernel_ms": {"k_synth_rangedec+k_synth_expand": k0_ms, "k_imdct_post_w": k1_ms,
+                "per_kernel_ms": {"k_synth_rangedec+k_synth_expand": k0_ms, "k_imdct_post_w": k1_ms, "k_comb_post_w": k2_ms,
                                   "note": "second pass of the same steps, stages in order on one stream with cudaEvents around "
                                           "each; in the measured run the entropy stage of step n+1 overlaps the IMDCT of step n"},
                 "peak_source": peak_src, "e2e_checksum": checksum,

@@ -100,10 +100,11 @@ int opn_batch_final_ranges(opn_batch *b, uint32_t *out);
 /* Device-resident PCM ring (history + output): base pointer, samples per channel in the ring,
  * and the per-stream write position after the last call (device pointer, n_streams words). */
 int opn_batch_ring(opn_batch *b, float **ring, uint32_t *ring_samples, uint32_t **ring_pos_dev);
-/* Counters for the measurement harness.  kernel_ms[k]/kernel_launches[k]: k = 0 symbol decode,
- * 1 imdct+tdac+postfilter.  Timing must be enabled first (adds cudaEvents around launches). */
+/* Counters for the measurement harness.  kernel_ms[k]/kernel_launches[k]: k = 0 symbol decode (range
+ * decode + PVQ expansion, two launches), 1 IMDCT + TDAC + PCM store, 2 comb post-filter.  Timing must be
+ * enabled first (stages then run in order on one stream with cudaEvents around each). */
 int opn_batch_enable_timing(opn_batch *b, int on);
-int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[2], double kernel_ms[2], int reset);
+int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[3], int reset);
 void *opn_batch_cuda_stream(opn_batch *b);
 
 /* ---- operator-level entry points (host pointers in/out; mirror the pub(crate) operators) */

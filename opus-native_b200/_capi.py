@@ -279,10 +279,10 @@ class BatchDecoder:
         _chk(lib().opn_batch_enable_timing(self._h, int(on)))
 
     def stats(self, reset=False):
-        launches = (C.c_uint64 * 2)()
-        ms = (C.c_double * 2)()
+        launches = (C.c_uint64 * 3)()
+        ms = (C.c_double * 3)()
         _chk(lib().opn_batch_stats(self._h, launches, ms, int(reset)))
-        return {"launches": [launches[0], launches[1]], "ms": [ms[0], ms[1]]}
+        return {"launches": list(launches), "ms": list(ms)}
 
     @property
     def cuda_stream(self):

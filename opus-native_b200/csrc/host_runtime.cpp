@@ -132,6 +132,7 @@ struct opn_batch {
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef = nullptr;
     uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[NSETS] = {};
     PfState *d_pf = nullptr;
+    CombJob *d_job = nullptr;
     opn_synth_side *d_side[NSETS] = {};
     int32_t *d_status[NSETS] = {};
     // host-path staging (device + pinned host)
@@ -146,8 +147,8 @@ struct opn_batch {
     std::vector<int32_t> last_nf, bandwidth, last_duration, have_mode;
     // measurement
     bool timing = false;
-    EventRing ev[2];
-    uint64_t launches[2] = {0, 0};
+    EventRing ev[3];
+    uint64_t launches[3] = {0, 0, 0};
 };
 
 namespace {
@@ -196,6 +197,7 @@ int timed_launch(opn_batch *b, int kind, cudaError_t (*fn)(opn_batch *, const vo
 
 cudaError_t do_symbols(opn_batch *b, const void *a) { return launch_synth_symbols(*static_cast<const SymbolArgs *>(a), b->stream); }
 cudaError_t do_imdct(opn_batch *b, const void *a) { return launch_imdct_post(*static_cast<const ImdctArgs *>(a), b->stream); }
+cudaError_t do_comb(opn_batch *b, const void *a) { return launch_comb_post(*static_cast<const ImdctArgs *>(a), b->stream); }
 
 // One bucket = items of equal frame size that may run concurrently.
 // inputs_on: 0 = the packets are already complete in device memory (the entropy stage may start at once),
@@ -266,8 +268,13 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.gain = b->gain;
     m.result = d_result;
     m.final_range = b->d_final;
+    m.job = b->d_job;
     rc = timed_launch(b, 1, do_imdct, &m);
     if (rc) return rc;
+    if (m.postfilter) {
+        rc = timed_launch(b, 2, do_comb, &m);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(b->ev_use[p], b->stream));
     b->use_recorded[p] = true;
     return OPN_OK;
@@ -355,6 +362,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring_pos, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_job, n * sizeof(CombJob));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_softclip, n * 2 * sizeof(float));
     if (e != cudaSuccess) {
         opn_batch_destroy(b);
@@ -400,14 +408,14 @@ void opn_batch_destroy(opn_batch *b)
     }
     for (int q = 0; q < opn_batch::NRD; q++)
         if (b->stream_rd[q]) cudaStreamDestroy(b->stream_rd[q]);
-    b->ev[0].destroy();
-    b->ev[1].destroy();
+    for (int k = 0; k < 3; k++) b->ev[k].destroy();
     cudaFree(b->d_carry);
     cudaFree(b->d_ring);
     cudaFree(b->d_coef);
     cudaFree(b->d_ring_pos);
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
+    cudaFree(b->d_job);
     cudaFree(b->d_softclip);
     cudaFree(b->d_arena);
     cudaFree(b->d_items);
@@ -650,20 +658,21 @@ int opn_batch_enable_timing(opn_batch *b, int on)
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
     if (on) {
-        int rc = b->ev[0].make();
-        if (!rc) rc = b->ev[1].make();
-        if (rc) return rc;
+        for (int k = 0; k < 3; k++) {
+            int rc = b->ev[k].make();
+            if (rc) return rc;
+        }
     }
     b->timing = on != 0;
     return OPN_OK;
 }
 
-int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[2], double kernel_ms[2], int reset)
+int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[3], int reset)
 {
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
     CU(cudaStreamSynchronize(b->stream));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 3; k++) {
         int rc = b->ev[k].resolve();
         if (rc) return rc;
         if (kernel_launches) kernel_launches[k] = b->launches[k];

@@ -39,17 +39,20 @@ namespace opn {
 
 // Twiddles addressed with compile-time indices (src/celt/kiss_fft.rs:341-582) fold into instruction
 // immediates: OPN_TWIDDLES is constexpr in C++ translation units.
-__device__ int g_dbg_skip;  // diagnostic only (OPN_IMDCT_SKIP): 1 = no FFT, 2 = no comb, 4 = no PCM stores, 8 = no carry/state
-
 template <int I> struct WTw {
     static constexpr float re = OPN_TWIDDLES[2 * I], im = OPN_TWIDDLES[2 * I + 1];
     __device__ __forceinline__ static float2 get() { return make_float2(re, im); }
 };
 
-constexpr int W_MAX_WPC = 8;  // warps (= streams) per CTA, at most
+constexpr int W_MAX_WPC = 1;       // warps (= streams) per CTA
+#ifndef OPN_K1_MIN_CTAS
+#define OPN_K1_MIN_CTAS 20
+#endif
+constexpr int W_K1_MIN_CTAS = OPN_K1_MIN_CTAS;  // kernel 1 register budget: 65536 / (32 * this) per thread
 __host__ __device__ constexpr int w_ch_floats(int lm) { return (120 << lm) + 60; }
 __host__ __device__ constexpr int trig_pair_off(int shift) { return shift == 0 ? 0 : shift == 1 ? 480 : shift == 2 ? 720 : 840; }
-__host__ __device__ constexpr size_t w_smem_bytes(int lm, int channels) { return (size_t)channels * (w_ch_floats(lm) + HIST_CAP) * 4 + 16; }
+__host__ __device__ constexpr size_t w_smem_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16; }
+__host__ __device__ constexpr size_t w_comb_smem_bytes(int lm, int channels) { return (size_t)channels * (HIST_CAP + (120 << lm)) * 4 + 16; }
 
 // ---- TMA / mbarrier (single-CTA cluster) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -336,36 +339,81 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
 }
 
 // ---- post-filter -------------------------------------------------------------------------------
-// One tap of the C channels at signed sample index idx relative to the frame start: idx >= 0 is this
-// frame (planar rows, already filtered where the recursion needs it), idx < 0 is history: the last
-// T+2 samples of the interleaved PCM ring, staged in shared memory by TMA while the FFT runs.
-template <int C> struct WTapSrc {
-    const float *y;   // channel 0 row; channel 1 at y + chf
-    int chf;
-    const float *h;   // staged history, interleaved like the ring: sample idx (< 0) of channel c at h[C*idx + c]
-    __device__ __forceinline__ float2 hist(int idx) const
-    {
-        if (C == 2) return *reinterpret_cast<const float2 *>(h + 2 * idx);
-        return make_float2(h[idx], 0.0f);
-    }
-    __device__ __forceinline__ float2 frame(int idx) const { return make_float2(y[idx], C == 2 ? y[chf + idx] : 0.0f); }
-    __device__ __forceinline__ float2 any(int idx) const { return idx < 0 ? hist(idx) : frame(idx); }
-};
-
 // comb_filter_const_inplace term order (fallback.rs:46-51): y + g0*x2 + g1*(x1+x3) + g2*(x0+x4)
 __device__ __forceinline__ float comb5(float y, float x0, float x1, float x2, float x3, float x4, float g0, float g1, float g2)
 {
     return y + (g0 * x2) + (g1 * (x1 + x3)) + (g2 * (x0 + x4));
 }
 
-// comb_filter_inplace (comb_filter/mod.rs:130-193) for the C channels of one stream.  The filter is
-// recursive, y[i] depends on y[i-T-2 .. i-T+2]; wherever those taps are history the samples are
-// independent and are filtered in parallel, the rest is swept in chunks no longer than T-2.
-// A tap set whose gain is exactly zero contributes +-0 to every sum and is skipped.
+// One sample of the C interleaved channels (the PCM ring layout): C == 2 moves both channels of a tap
+// in one 64-bit access.
+template <int C> struct WSmp;
+template <> struct WSmp<1> {
+    float a;
+    __device__ __forceinline__ static WSmp ld(const float *p) { return WSmp{*p}; }
+    __device__ __forceinline__ void st(float *p) const { *p = a; }
+};
+template <> struct WSmp<2> {
+    float a, b;
+    __device__ __forceinline__ static WSmp ld(const float *p)
+    {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        return WSmp{v.x, v.y};
+    }
+    __device__ __forceinline__ void st(float *p) const { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+};
 template <int C>
-__device__ __forceinline__ void w_comb(float *y, int chf, const float *hist_end, int t0, int t1, int n, float g0, float g1, int tap0,
-                                       int tap1, int overlap, int lane, const float *win_sq)
+__device__ __forceinline__ WSmp<C> w_comb5(WSmp<C> y, WSmp<C> x0, WSmp<C> x1, WSmp<C> x2, WSmp<C> x3, WSmp<C> x4, float g0, float g1,
+                                           float g2)
 {
+    WSmp<C> r;
+    r.a = comb5(y.a, x0.a, x1.a, x2.a, x3.a, x4.a, g0, g1, g2);
+    if constexpr (C == 2) r.b = comb5(y.b, x0.b, x1.b, x2.b, x3.b, x4.b, g0, g1, g2);
+    return r;
+}
+// cross-fade accumulation order of comb_filter_inplace (mod.rs:166-177); a* = y[i-t0-2 .. i-t0+2],
+// b* = y[i-t1-2 .. i-t1+2]
+__device__ __forceinline__ float xfade1(float y, float a0, float a1, float a2, float a3, float a4, float b0, float b1, float b2, float b3,
+                                        float b4, bool has0, bool has1, float f, float g00, float g01, float g02, float g10, float g11,
+                                        float g12)
+{
+    float v = y;
+    if (has0) {
+        v = v + (((1.0f - f) * g00) * a2);
+        v = v + (((1.0f - f) * g01) * (a3 + a1));
+        v = v + (((1.0f - f) * g02) * (a4 + a0));
+    }
+    if (has1) {
+        v = v + ((f * g10) * b2);
+        v = v + ((f * g11) * (b3 + b1));
+        v = v + ((f * g12) * (b4 + b0));
+    }
+    return v;
+}
+template <int C>
+__device__ __forceinline__ WSmp<C> w_xfade(WSmp<C> y, const WSmp<C> *a, const WSmp<C> *b, bool has0, bool has1, float f, float g00,
+                                           float g01, float g02, float g10, float g11, float g12)
+{
+    WSmp<C> r;
+    r.a = xfade1(y.a, a[0].a, a[1].a, a[2].a, a[3].a, a[4].a, b[0].a, b[1].a, b[2].a, b[3].a, b[4].a, has0, has1, f, g00, g01, g02, g10,
+                 g11, g12);
+    if constexpr (C == 2)
+        r.b = xfade1(y.b, a[0].b, a[1].b, a[2].b, a[3].b, a[4].b, b[0].b, b[1].b, b[2].b, b[3].b, b[4].b, has0, has1, f, g00, g01, g02,
+                     g10, g11, g12);
+    return r;
+}
+
+// comb_filter_inplace (comb_filter/mod.rs:130-193) on one stream: y points at sample 0 of the frame,
+// sample i of channel c lives at y[C*i + c] and the history (the previous max(T)+2 samples) directly
+// below, exactly as in the PCM ring.  The filter is recursive, y[i] depends on y[i-T-2 .. i-T+2];
+// wherever those taps are history the samples are independent and are filtered in parallel, the rest
+// is swept in chunks no longer than T-2.  A tap set whose gain is exactly zero contributes +-0 to
+// every sum and is skipped.
+template <int C>
+__device__ __forceinline__ void w_comb(float *y, int t0, int t1, int n, float g0, float g1, int tap0, int tap1, int overlap, int lane,
+                                       const float *win_sq)
+{
+    using S = WSmp<C>;
     if (g0 == 0.0f && g1 == 0.0f) return;
     t0 = max(t0, 15);
     t1 = max(t1, 15);
@@ -374,79 +422,43 @@ __device__ __forceinline__ void w_comb(float *y, int chf, const float *hist_end,
     const float g10 = g1 * g_tab.comb_gains[tap1 * 3], g11 = g1 * g_tab.comb_gains[tap1 * 3 + 1],
                 g12 = g1 * g_tab.comb_gains[tap1 * 3 + 2];
     if (fabsf(g0 - g1) < 1.1920929e-7f && t0 == t1 && tap0 == tap1) overlap = 0;
-    const WTapSrc<C> src{y, chf, hist_end};
     const bool has0 = g0 != 0.0f, has1 = g1 != 0.0f;
 
+    // Independent samples are dealt to the lanes round-robin (sample = base + lane + 32 e): consecutive
+    // lanes touch consecutive float2, so every shared-memory access is conflict-free.
     // ---- cross-fade part (mod.rs:162-179): samples [0, overlap)
     if (overlap > 0) {
         const int tmin = min(has0 ? t0 : 1 << 20, has1 ? t1 : 1 << 20);
-        // [0, pre): every tap of every live set is history -> independent samples, 4 per lane
-        const int pre = min(overlap, tmin - 2) & ~3;
-        {
-            const int i0 = 4 * lane;
-            if (i0 < pre) {
-                float2 a[8], b[8];
+        // [0, pre): every tap of every live set is history -> no recursion
+        const int pre = min(overlap, tmin - 2);
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    a[k] = has0 ? src.hist(i0 - t0 - 2 + k) : make_float2(0.f, 0.f);
-                    b[k] = has1 ? src.hist(i0 - t1 - 2 + k) : make_float2(0.f, 0.f);
+        for (int e = 0; e < 4; e++) {
+            const int i = lane + 32 * e;
+            if (i < pre) {
+                const float f = __ldg(win_sq + i);
+                S a[5], b[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    a[k] = has0 ? S::ld(y + C * (i - t0 - 2 + k)) : S{};
+                    b[k] = has1 ? S::ld(y + C * (i - t1 - 2 + k)) : S{};
                 }
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    float4 v = *reinterpret_cast<float4 *>(y + c * chf + i0);
-                    float *vv = reinterpret_cast<float *>(&v);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const float f = __ldg(win_sq + i0 + e);
-                        float acc = vv[e];
-                        if (has0) {
-                            const float x0 = c ? a[e + 4].y : a[e + 4].x, x1 = c ? a[e + 3].y : a[e + 3].x, x2 = c ? a[e + 2].y : a[e + 2].x,
-                                        x3 = c ? a[e + 1].y : a[e + 1].x, x4 = c ? a[e].y : a[e].x;
-                            acc = acc + (((1.0f - f) * g00) * x2);
-                            acc = acc + (((1.0f - f) * g01) * (x1 + x3));
-                            acc = acc + (((1.0f - f) * g02) * (x0 + x4));
-                        }
-                        if (has1) {
-                            const float x0 = c ? b[e + 4].y : b[e + 4].x, x1 = c ? b[e + 3].y : b[e + 3].x, x2 = c ? b[e + 2].y : b[e + 2].x,
-                                        x3 = c ? b[e + 1].y : b[e + 1].x, x4 = c ? b[e].y : b[e].x;
-                            acc = acc + ((f * g10) * x2);
-                            acc = acc + ((f * g11) * (x1 + x3));
-                            acc = acc + ((f * g12) * (x0 + x4));
-                        }
-                        vv[e] = acc;
-                    }
-                    *reinterpret_cast<float4 *>(y + c * chf + i0) = v;
-                }
+                w_xfade<C>(S::ld(y + C * i), a, b, has0, has1, f, g00, g01, g02, g10, g11, g12).st(y + C * i);
             }
         }
         __syncwarp();
-        // [pre, overlap): chunks of W <= tmin - 2 samples, one per lane; taps from wherever they live
+        // [pre, overlap): chunks of W <= tmin - 2 samples, one per lane
         const int W = min(tmin - 2, 32);
         for (int base = pre; base < overlap; base += W) {
             const int i = base + lane;
             if (lane < W && i < overlap) {
                 const float f = __ldg(win_sq + i);
-                float2 a[5], b[5];
+                S a[5], b[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
-                    a[k] = has0 ? src.any(i - t0 - 2 + k) : make_float2(0.f, 0.f);
-                    b[k] = has1 ? src.any(i - t1 - 2 + k) : make_float2(0.f, 0.f);
+                    a[k] = has0 ? S::ld(y + C * (i - t0 - 2 + k)) : S{};
+                    b[k] = has1 ? S::ld(y + C * (i - t1 - 2 + k)) : S{};
                 }
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    float acc = y[c * chf + i];
-                    if (has0) {
-                        acc = acc + (((1.0f - f) * g00) * (c ? a[2].y : a[2].x));
-                        acc = acc + (((1.0f - f) * g01) * ((c ? a[3].y : a[3].x) + (c ? a[1].y : a[1].x)));
-                        acc = acc + (((1.0f - f) * g02) * ((c ? a[4].y : a[4].x) + (c ? a[0].y : a[0].x)));
-                    }
-                    if (has1) {
-                        acc = acc + ((f * g10) * (c ? b[2].y : b[2].x));
-                        acc = acc + ((f * g11) * ((c ? b[3].y : b[3].x) + (c ? b[1].y : b[1].x)));
-                        acc = acc + ((f * g12) * ((c ? b[4].y : b[4].x) + (c ? b[0].y : b[0].x)));
-                    }
-                    y[c * chf + i] = acc;
-                }
+                w_xfade<C>(S::ld(y + C * i), a, b, has0, has1, f, g00, g01, g02, g10, g11, g12).st(y + C * i);
             }
             __syncwarp();
         }
@@ -454,131 +466,74 @@ __device__ __forceinline__ void w_comb(float *y, int chf, const float *hist_end,
     if (!has1) return;
 
     // ---- constant part (fallback.rs:32-53): samples [overlap, n)
-    // (1) history-only span [overlap, hend): no recursion; 4 samples per lane, 128 per sweep
-    int at = overlap;  // overlap is 0 or 120: a multiple of 4
+    auto one = [&](int i) {
+        const float *p = y + C * (i - t1);
+        w_comb5<C>(S::ld(y + C * i), S::ld(p + 2 * C), S::ld(p + C), S::ld(p), S::ld(p - C), S::ld(p - 2 * C), g10, g11, g12).st(y + C * i);
+    };
+    // (1) history-only span [overlap, hend): no recursion, 128 samples per step
+    int at = overlap;
     {
-        const int hend = overlap + ((max(min(n, t1 - 2) - overlap, 0)) & ~3);
-        for (int i0 = at + 4 * lane; i0 < hend; i0 += 128) {
-            float2 b[8];
+        const int hend = max(at, min(n, t1 - 2));
+        for (int base = at; base < hend; base += 128) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) b[k] = src.hist(i0 - t1 - 2 + k);
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                float4 v = *reinterpret_cast<float4 *>(y + c * chf + i0);
-                v.x = comb5(v.x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, c ? b[1].y : b[1].x, c ? b[0].y : b[0].x, g10, g11, g12);
-                v.y = comb5(v.y, c ? b[5].y : b[5].x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, c ? b[1].y : b[1].x, g10, g11, g12);
-                v.z = comb5(v.z, c ? b[6].y : b[6].x, c ? b[5].y : b[5].x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, g10, g11, g12);
-                v.w = comb5(v.w, c ? b[7].y : b[7].x, c ? b[6].y : b[6].x, c ? b[5].y : b[5].x, c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, g10, g11, g12);
-                *reinterpret_cast<float4 *>(y + c * chf + i0) = v;
+            for (int e = 0; e < 4; e++) {
+                const int i = base + lane + 32 * e;
+                if (i < hend) one(i);
             }
         }
-        at = max(at, hend);
+        at = hend;
         __syncwarp();
     }
-    // (2) the few samples whose taps straddle the frame start: [at, mid), mid = first multiple of 4
-    //     with every tap inside the frame.  mid - at <= 10 <= t1 - 2, so they are independent too.
-    {
-        const int mid = min(n, max(at, (t1 + 2 + 3) & ~3));
-        const int i = at + lane;
-        if (i < mid) {
-            float2 b[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) b[k] = src.any(i - t1 - 2 + k);
-#pragma unroll
-            for (int c = 0; c < C; c++)
-                y[c * chf + i] = comb5(y[c * chf + i], c ? b[4].y : b[4].x, c ? b[3].y : b[3].x, c ? b[2].y : b[2].x, c ? b[1].y : b[1].x,
-                                       c ? b[0].y : b[0].x, g10, g11, g12);
-        }
-        at = mid;
-        __syncwarp();
-    }
-    // (3) recursive remainder [at, n): every tap is in shared memory; chunk = 32*V <= t1 - 2 samples,
-    //     V = 4 or 2 consecutive samples per lane when the period allows (`at` is a multiple of 4)
+    // (2) recursive remainder [at, n): chunks of min(t1 - 2, 128) samples; inside a chunk every tap lies
+    //     before the chunk
     if (t1 - 2 >= 128) {
-        const int vend = at + ((n - at) & ~3);
-        for (int base = at; base < vend; base += 128) {
-            const int i0 = base + 4 * lane;
-            if (i0 < vend) {
+        for (int base = at; base < n; base += 128) {
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    float *yc = y + c * chf;
-                    float t[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) t[k] = yc[i0 - t1 - 2 + k];
-                    float4 v = *reinterpret_cast<float4 *>(yc + i0);
-                    v.x = comb5(v.x, t[4], t[3], t[2], t[1], t[0], g10, g11, g12);
-                    v.y = comb5(v.y, t[5], t[4], t[3], t[2], t[1], g10, g11, g12);
-                    v.z = comb5(v.z, t[6], t[5], t[4], t[3], t[2], g10, g11, g12);
-                    v.w = comb5(v.w, t[7], t[6], t[5], t[4], t[3], g10, g11, g12);
-                    *reinterpret_cast<float4 *>(yc + i0) = v;
-                }
+            for (int e = 0; e < 4; e++) {
+                const int i = base + lane + 32 * e;
+                if (i < n) one(i);
             }
             __syncwarp();
         }
-        at = vend;
     } else if (t1 - 2 >= 64) {
-        const int vend = at + ((n - at) & ~1);
-        for (int base = at; base < vend; base += 64) {
-            const int i0 = base + 2 * lane;
-            if (i0 < vend) {
+        for (int base = at; base < n; base += 64) {
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    float *yc = y + c * chf;
-                    float t[6];
-#pragma unroll
-                    for (int k = 0; k < 6; k++) t[k] = yc[i0 - t1 - 2 + k];
-                    float2 v = *reinterpret_cast<float2 *>(yc + i0);
-                    v.x = comb5(v.x, t[4], t[3], t[2], t[1], t[0], g10, g11, g12);
-                    v.y = comb5(v.y, t[5], t[4], t[3], t[2], t[1], g10, g11, g12);
-                    *reinterpret_cast<float2 *>(yc + i0) = v;
-                }
+            for (int e = 0; e < 2; e++) {
+                const int i = base + lane + 32 * e;
+                if (i < n) one(i);
             }
             __syncwarp();
         }
-        at = vend;
-    }
-    {
+    } else {
         const int W = min(t1 - 2, 32);
         for (int base = at; base < n; base += W) {
             const int i = base + lane;
-            if (lane < W && i < n) {
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    float *yc = y + c * chf;
-                    const float x0 = yc[i - t1 + 2], x1 = yc[i - t1 + 1], x2 = yc[i - t1], x3 = yc[i - t1 - 1], x4 = yc[i - t1 - 2];
-                    yc[i] = comb5(yc[i], x0, x1, x2, x3, x4, g10, g11, g12);
-                }
-            }
+            if (lane < W && i < n) one(i);
             __syncwarp();
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 1: one warp = one CTA = one stream (item).
-// Shared memory: C rows of nf+60 floats | interleaved post-filter history, up to 1024 samples x C |
-// two mbarriers (coefficient rows, history).  Both TMA transfers are issued before anything else;
-// the history lands while the FFT runs.
-template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imdct_post_w(ImdctArgs A)
+// kernel 1 (IMDCT + TDAC overlap-add + PCM store): one warp = one stream (item).
+// Shared memory per warp: C rows of nf+60 floats and one mbarrier.  The post-filter runs in kernel 2
+// on the interleaved PCM this kernel leaves in the ring; kernel 1 only decides whether it is needed and
+// leaves the parameters (old -> new) in `job`.
+template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC, W_K1_MIN_CTAS) k_imdct_post_w(ImdctArgs A)
 {
     extern __shared__ __align__(16) float sm_all[];
     constexpr int NF = 120 << LM;
     constexpr int CHF = w_ch_floats(LM);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *sm = sm_all + warp * (w_smem_bytes(LM, C) / 4);
-    float *o = sm;
-    float *hs = sm + C * CHF;  // history staging, HIST_CAP samples x C
-    uint64_t *bar = reinterpret_cast<uint64_t *>(hs + C * HIST_CAP);
+    float *o = sm_all + warp * (w_smem_bytes(LM, C) / 4);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);
 
-    // the warps of a CTA share nothing but the instruction stream (they start together, so they
-    // fetch the same straight-line code at about the same time)
     const uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp;
     if (item >= A.n_items) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
     // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
         mbar_expect_tx(bar, C * NF * 4);
 #pragma unroll
         for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
@@ -597,7 +552,10 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
     __syncwarp();
     if (status < 0) {  // rejected packet: state untouched (decoder.rs:397)
-        if (lane == 0 && A.result) A.result[stream] = status;
+        if (lane == 0) {
+            if (A.result) A.result[stream] = status;
+            A.job[item].on = 0;
+        }
         mbar_wait(bar, 0);  // the rows are in flight: do not retire the CTA under them
         return;
     }
@@ -612,45 +570,23 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     }
     const bool comb_on = A.postfilter && (old.gain != 0.0f || g1 != 0.0f);
     float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
-    // history = the last `need` samples before pos (a multiple of 4, so every piece is 16-byte sized and aligned)
-    const int need = comb_on ? ((max(max(old.period, t1), 15) + 2 + 3) & ~3) : 0;
-    float *hist_end = hs + C * HIST_CAP;
-    if (lane == 0 && comb_on) {
-        mbar_expect_tx(bar + 1, need * C * 4);
-        const int first = (int)pos - need;  // may be negative: the span wraps around the ring end
-        if (first >= 0) {
-            bulk_g2s(hist_end - need * C, ring + (size_t)first * C, need * C * 4, bar + 1);
-        } else {
-            bulk_g2s(hist_end - need * C, ring + (size_t)(first + RING_SAMPLES) * C, -first * C * 4, bar + 1);
-            if (pos) bulk_g2s(hist_end - (int)pos * C, ring, pos * C * 4, bar + 1);
-        }
-    }
-    __syncwarp();
+
     mbar_wait(bar, 0);
-    const int dbg = g_dbg_skip;
-    if (!(dbg & 1)) {
     if constexpr (LM > 0) {
         if (s_transient) w_imdct<3, (1 << LM), C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
         else w_imdct<3 - LM, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3 - LM), g_tab.twiddles, g_tab.window);
     } else {
         w_imdct<3, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
     }
-    }
 
     // tail of this frame -> carry
-    if (lane < 15 * C && !(dbg & 8)) {
+    if (lane < 15 * C) {
         const int ch = (C == 2 && lane >= 15) ? 1 : 0;
         *reinterpret_cast<float4 *>(carry_g + 4 * lane) = *reinterpret_cast<const float4 *>(o + ch * CHF + NF + 4 * (lane - 15 * ch));
     }
-    if (comb_on) mbar_wait(bar + 1, 0);
-    if (comb_on && !(dbg & 2)) {
-        w_comb<C>(o, CHF, hist_end, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane, g_tab.window_sq);
-    }
-    __syncwarp();
-
-    // epilogue: interleaved PCM -> ring (history + device-resident output) and optional dense rows.
+    // interleaved PCM -> ring (history + device-resident output); dense rows only when no post-filter follows.
     // The frame is contiguous in the ring except when it wraps (pos is a multiple of 120).
-    float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
+    float *dense = (A.dense && !comb_on) ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
     const float gain = A.gain;
     constexpr int VEC = C == 2 ? NF / 2 : NF / 4;         // float4 per frame
     constexpr int SPV = C == 2 ? 2 : 4;                   // samples per float4
@@ -658,7 +594,7 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
     float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)pos * C);
     float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
 #pragma unroll
-    for (int i = lane; i < ((dbg & 4) ? 0 : VEC); i += 32) {
+    for (int i = lane; i < VEC; i += 32) {
         float4 v;
         if (C == 2) {
             const float2 a = *reinterpret_cast<const float2 *>(o + 2 * i), b = *reinterpret_cast<const float2 *>(o + CHF + 2 * i);
@@ -672,7 +608,7 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
             reinterpret_cast<float4 *>(dense)[i] = v;
         }
     }
-    if (lane == 0 && !(dbg & 8)) {
+    if (lane == 0) {
         uint32_t np = pos + (uint32_t)NF;
         if (np >= RING_SAMPLES) np -= RING_SAMPLES;
         A.ring_pos[stream] = np;
@@ -684,6 +620,77 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_imd
         A.pf[stream] = nw;
         if (A.result) A.result[stream] = NF;
         if (A.final_range) A.final_range[stream] = lost ? 0u : s_final;
+        CombJob j;
+        j.on = comb_on ? 1 : 0;
+        j.pos = pos;
+        j.t0 = old.period;
+        j.t1 = t1;
+        j.tap0 = old.tapset;
+        j.tap1 = tap1;
+        j.g0 = old.gain;
+        j.g1 = g1;
+        A.job[item] = j;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2 (pitch comb post-filter, comb_filter_inplace): one warp = one stream (item) whose job is on.
+// The history (the T+2 samples before the frame) and the frame are one contiguous span of the
+// interleaved ring: one TMA transfer (three when the span wraps) brings both into shared memory, the
+// filter runs in place on float2 = (left, right) samples, and the frame goes back to the ring and, for
+// host-buffer calls, to the dense output rows.
+template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_comb_post_w(ImdctArgs A)
+{
+    extern __shared__ __align__(16) float sm_all[];
+    constexpr int NF = 120 << LM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sm = sm_all + warp * (w_comb_smem_bytes(LM, C) / 4);
+    float *y = sm + C * HIST_CAP;  // sample 0 of the frame; history below
+    uint64_t *bar = reinterpret_cast<uint64_t *>(y + C * NF);
+
+    const uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (item >= A.n_items) return;
+    const CombJob j = A.job[item];
+    if (!j.on) return;
+    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
+    const int need = (max(max(j.t0, j.t1), 15) + 2 + 3) & ~3;  // multiple of 4: every piece 16-byte sized and aligned
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (need + NF) * C * 4);
+        // span [pos - need, pos + NF) of the ring, cut where it wraps
+        int first = (int)j.pos - need, count = need + NF;
+        float *dst = y - need * C;
+        if (first < 0) {
+            bulk_g2s(dst, ring + (size_t)(first + RING_SAMPLES) * C, -first * C * 4, bar);
+            dst += -first * C;
+            count += first;
+            first = 0;
+        }
+        const int fit = min(count, RING_SAMPLES - first);
+        bulk_g2s(dst, ring + (size_t)first * C, fit * C * 4, bar);
+        if (count > fit) bulk_g2s(dst + fit * C, ring, (count - fit) * C * 4, bar);
+    }
+    const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
+    __syncwarp();
+    mbar_wait(bar, 0);
+    w_comb<C>(y, j.t0, j.t1, NF, j.g0, j.g1, j.tap0, j.tap1, 120, lane, g_tab.window_sq);
+    __syncwarp();
+    float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
+    const float gain = A.gain;
+    constexpr int VEC = NF * C / 4;
+    constexpr int SPV = 4 / C;
+    const int wrap_at = (int)(RING_SAMPLES - j.pos) / SPV;
+    float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)j.pos * C);
+    float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
+#pragma unroll
+    for (int i = lane; i < VEC; i += 32) {
+        float4 v = reinterpret_cast<const float4 *>(y)[i];
+        (i < wrap_at ? r0 : r1)[i] = v;
+        if (dense) {
+            if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
+            reinterpret_cast<float4 *>(dense)[i] = v;
+        }
     }
 }
 
@@ -723,7 +730,7 @@ k_op_comb_inplace_w(float *__restrict__ y, size_t row_stride, int y_offset, int 
     for (int i = lane; i < n; i += 32) ys[i] = row[y_offset + i];
     for (int i = lane; i < need; i += 32) ys[-1 - i] = row[y_offset - 1 - i];
     __syncwarp();
-    w_comb<1>(ys, 0, ys, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq);
+    w_comb<1>(ys, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq);
     __syncwarp();
     for (int i = lane; i < n; i += 32) row[y_offset + i] = ys[i];
 }

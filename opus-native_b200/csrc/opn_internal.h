@@ -20,6 +20,13 @@ struct PfState {  // post-filter parameters of the previous frame
     int32_t pad;
 };
 
+struct CombJob {  // kernel 1 -> kernel 2: the post-filter to run on an item's frame
+    int32_t on;
+    uint32_t pos;  // ring position of the frame start
+    int32_t t0, t1, tap0, tap1;
+    float g0, g1;
+};
+
 struct SymbolArgs {
     const uint8_t *arena;
     const uint32_t *offsets;     // [n_items] byte offset of the packet (or of the payload if !has_toc)
@@ -52,6 +59,7 @@ struct ImdctArgs {
     float gain;                   // DecoderConfiguration::gain as a linear factor (decoder.rs:790-797); 1 = none
     int32_t *result;              // [n_streams] samples per channel or OPN_ERR_*; nullptr to skip
     uint32_t *final_range;        // [n_streams]
+    CombJob *job;                 // [n_items] scratch, kernel 1 -> kernel 2
 };
 
 // ---- launchers (opn_kernels.cu).  All return a cudaError_t and never synchronise.
@@ -62,7 +70,8 @@ cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets
 cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st);   // both stages on one stream
 cudaError_t launch_synth_rangedec(const SymbolArgs &a, cudaStream_t st);  // stage 0a: one lane per packet
 cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st);    // stage 0b: one warp per packet
-cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st);
+cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st);  // kernel 1: IMDCT + TDAC + PCM store
+cudaError_t launch_comb_post(const ImdctArgs &a, cudaStream_t st);   // kernel 2: comb post-filter on the ring
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
                             int nblk, cudaStream_t st);
 cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, int n, uint32_t n_rows, const int32_t *params4,

@@ -23,6 +23,10 @@ template <int LM, int C> static cudaError_t set_carveout()
     static const int pct = getenv("OPN_CARVEOUT") ? atoi(getenv("OPN_CARVEOUT")) : W_CARVEOUT_PCT;
     cudaError_t e = cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W_MAX_WPC * w_smem_bytes(LM, C)));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_comb_post_w<LM, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W_MAX_WPC * w_comb_smem_bytes(LM, C)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_comb_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 static cudaError_t set_warp_kernel_attributes()
@@ -135,11 +139,6 @@ cudaError_t upload_tables(int device)
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
     if (e != cudaSuccess) return e;
-    {
-        const int dbg = getenv("OPN_IMDCT_SKIP") ? atoi(getenv("OPN_IMDCT_SKIP")) : 0;
-        e = cudaMemcpyToSymbol(g_dbg_skip, &dbg, sizeof(dbg));
-        if (e != cudaSuccess) return e;
-    }
     e = set_warp_kernel_attributes();
     if (e != cudaSuccess) return e;
     // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
@@ -156,6 +155,12 @@ template <int LM, int C> static cudaError_t launch_imdct_w(const ImdctArgs &a, c
     static const int wpc_env = getenv("OPN_IMDCT_WPC") ? atoi(getenv("OPN_IMDCT_WPC")) : W_WPC;
     const uint32_t wpc = (uint32_t)(wpc_env < 1 ? 1 : wpc_env > W_MAX_WPC ? W_MAX_WPC : wpc_env);
     k_imdct_post_w<LM, C><<<(a.n_items + wpc - 1) / wpc, 32 * wpc, wpc * w_smem_bytes(LM, C), st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int LM, int C> static cudaError_t launch_comb_w(const ImdctArgs &a, cudaStream_t st)
+{
+    k_comb_post_w<LM, C><<<a.n_items, 32, w_comb_smem_bytes(LM, C), st>>>(a);
     return cudaGetLastError();
 }
 
@@ -215,6 +220,22 @@ cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st)
     }
 }
 
+cudaError_t launch_comb_post(const ImdctArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0 || !a.postfilter) return cudaSuccess;
+    switch (a.lm * 2 + (a.channels - 1)) {
+    case 0: return launch_comb_w<0, 1>(a, st);
+    case 1: return launch_comb_w<0, 2>(a, st);
+    case 2: return launch_comb_w<1, 1>(a, st);
+    case 3: return launch_comb_w<1, 2>(a, st);
+    case 4: return launch_comb_w<2, 1>(a, st);
+    case 5: return launch_comb_w<2, 2>(a, st);
+    case 6: return launch_comb_w<3, 1>(a, st);
+    case 7: return launch_comb_w<3, 2>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
                             int nblk, cudaStream_t st)
 {
@@ -244,7 +265,7 @@ cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, in
 {
     if (n_rows == 0) return cudaSuccess;
     const size_t smem = (((size_t)n + HIST_CAP) * 4 + 15) & ~(size_t)15;
-    if (smem > 48 * 1024 || (overlap & 3)) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
     k_op_comb_inplace_w<<<n_rows, 32, smem, st>>>(y, row_stride, y_offset, n, params4, gains2, overlap);
     return cudaGetLastError();
 }
