@@ -116,11 +116,13 @@ struct opn_batch {
     float gain = 1.0f;
     cudaStream_t stream = nullptr;
     // The entropy stage (k_synth_rangedec: one lane per packet, latency-bound, a few hundred warps)
-    // runs on its own streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
+    // runs on its own (high-priority) streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
     // live in NSETS buffer sets handed over with events.
-    static constexpr int NSETS = 4, NRD = 2;
+    static constexpr int NSETS = 6, NRD = 4;
     cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: two entropy stages may overlap each other
+    cudaStream_t stream_ex = nullptr;     // PVQ expansion: between the entropy streams and `stream`
     cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
+    cudaEvent_t ev_ex[NSETS] = {};        // PVQ expansion of set p finished (coefficients ready)
     cudaEvent_t ev_use[NSETS] = {};       // last consumer of set p finished
     cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` / `stream_up` are complete
     static constexpr int MAX_CHUNKS = 8;
@@ -129,7 +131,7 @@ struct opn_batch {
     bool use_recorded[NSETS] = {};
     int set = 0;
     // per-stream state (device, SoA)
-    float *d_carry = nullptr, *d_ring = nullptr, *d_coef = nullptr;
+    float *d_carry = nullptr, *d_ring = nullptr, *d_coef[NSETS] = {};
     uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[NSETS] = {};
     PfState *d_pf = nullptr;
     CombJob *d_job = nullptr;
@@ -220,7 +222,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.has_toc = has_toc;
     s.side = b->d_side[p];
     s.status = b->d_status[p];
-    s.coef = b->d_coef;
+    s.coef = b->d_coef[p];
     s.y_out = nullptr;
     s.idx = b->d_idx[p];
     s.pkt_cap = pkt_cap;
@@ -243,14 +245,18 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
             CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
         }
         if (b->use_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_use[p], 0));  // set p is free again
+        // three stages in flight at once: range decode of step n+2 (latency-bound, a few hundred warps), PVQ
+        // expansion of step n+1 (integer issue-bound) and IMDCT/post-filter of step n (FP32 / memory)
         CU(launch_synth_rangedec(s, srd));
         CU(cudaEventRecord(b->ev_rd[p], srd));
-        CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
-        CU(launch_synth_expand(s, b->stream));
+        CU(cudaStreamWaitEvent(b->stream_ex, b->ev_rd[p], 0));
+        CU(launch_synth_expand(s, b->stream_ex));
+        CU(cudaEventRecord(b->ev_ex[p], b->stream_ex));
+        CU(cudaStreamWaitEvent(b->stream, b->ev_ex[p], 0));
         b->launches[0] += 2;
     }
     ImdctArgs m{};
-    m.coef = b->d_coef;
+    m.coef = b->d_coef[p];
     m.side = b->d_side[p];
     m.status = b->d_status[p];
     m.stream_idx = d_stream_idx;
@@ -344,21 +350,29 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->gain = host_gain_from_q8(cfg->gain_q8);
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-    for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++) e = cudaStreamCreateWithFlags(&b->stream_rd[q], cudaStreamNonBlocking);
+    {
+        // the entropy stage is a handful of long-running warps: let its CTAs go first whenever an SM has room
+        int prio_lo = 0, prio_hi = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++)
+            e = cudaStreamCreateWithPriority(&b->stream_rd[q], cudaStreamNonBlocking, prio_hi);
+    }
     for (int q = 0; q < opn_batch::NSETS && e == cudaSuccess; q++) {
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_use[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_coef[q], n * (size_t)cfg->channels * 960 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_side[q], n * sizeof(opn_synth_side));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_dn, cudaStreamNonBlocking);
     for (int q = 0; q < opn_batch::MAX_CHUNKS && e == cudaSuccess; q++) e = cudaEventCreateWithFlags(&b->ev_chunk[q], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_carry, n * C * 60 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring, n * C * RING_SAMPLES * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_coef, n * C * 960 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring_pos, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
@@ -391,9 +405,15 @@ void opn_batch_destroy(opn_batch *b)
     for (int q = 0; q < opn_batch::NSETS; q++) {
         if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
         if (b->ev_use[q]) cudaEventDestroy(b->ev_use[q]);
+        if (b->ev_ex[q]) cudaEventDestroy(b->ev_ex[q]);
         cudaFree(b->d_idx[q]);
+        cudaFree(b->d_coef[q]);
         cudaFree(b->d_side[q]);
         cudaFree(b->d_status[q]);
+    }
+    if (b->stream_ex) {
+        cudaStreamSynchronize(b->stream_ex);
+        cudaStreamDestroy(b->stream_ex);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
     for (int q = 0; q < opn_batch::MAX_CHUNKS; q++)
@@ -411,7 +431,6 @@ void opn_batch_destroy(opn_batch *b)
     for (int k = 0; k < 3; k++) b->ev[k].destroy();
     cudaFree(b->d_carry);
     cudaFree(b->d_ring);
-    cudaFree(b->d_coef);
     cudaFree(b->d_ring_pos);
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
