@@ -9,7 +9,7 @@
 namespace opn {
 
 constexpr int SYM_WARPS_PER_CTA = 4;
-constexpr int IM_TPC = 128;         // kernel 1: threads per channel
+constexpr int IM_TPC = 128;         // threads per row of the out-of-place comb operator kernel
 constexpr int HIST_CAP = 1024;      // comb history window in shared memory (T + 2 <= 1024)
 constexpr int RING_SAMPLES = 2880;  // per-channel PCM ring: 3 x 960 = 6 x 480 = 12 x 240 = 24 x 120
 constexpr int32_t ITEM_OK = 0, ITEM_LOST = 1;  // kernel-0 status; negative = OPN_ERR_* (state untouched)

@@ -372,6 +372,35 @@ def test_batch_decode_chain(lm, channels, pkt_bytes, postfilter):
     assert exact, "PCM within tolerance but not bit-identical to the oracle"
 
 
+@pytest.mark.parametrize("channels", [2, 1])
+def test_batch_frame_size_changes_mid_stream(channels):
+    """A stream may change its frame size from packet to packet (decoder.rs:329-341 re-reads the TOC every
+    call).  The PCM ring then holds frames of mixed sizes: frames straddle the ring end, and the post-filter
+    history of a long frame spans several short ones (kernel 1's split store, kernel 2's three-piece load)."""
+    ns = 40
+    lms = [3, 0, 1, 3, 2, 0, 0, 3, 1, 2, 3, 3, 0, 2, 3, 1, 1, 3, 0, 3, 3, 2]
+    pkt_bytes = {0: 80, 1: 100, 2: 130, 3: 160}
+    if channels == 1:
+        pkt_bytes = {0: 48, 1: 60, 2: 80, 3: 100}
+    oracle = [O.SynthStream(3, channels) for _ in range(ns)]
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0))
+    exact = True
+    for f, lm in enumerate(lms):
+        nf, pb = 120 << lm, pkt_bytes[lm]
+        pk = opn.synth_fill(31, ns, f, 1, lm, channels, pb, transient_permille=200)[0]
+        pcm = np.zeros((ns, nf * channels), np.float32)
+        res = dec.decode_float(pk.reshape(-1), np.arange(ns, dtype=np.uint32) * pb, np.full(ns, pb, np.uint32), pcm, nf)
+        assert np.all(res == nf), (f, lm, res)
+        rng = dec.final_ranges()
+        for s in range(ns):
+            oracle[s].lm = lm
+            side, _, _, want = oracle[s].decode(pk[s, 1:])
+            assert rng[s] == side.final_rng
+            assert_pcm(want, pcm[s], f"frame {f} lm {lm} stream {s}")
+            exact &= np.array_equal(want, pcm[s])
+    assert exact, "PCM within tolerance but not bit-identical to the oracle"
+
+
 def test_batch_lost_invalid_and_foreign_packets_do_not_poison_neighbours():
     lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 16, 6, 960
     packets = opn.synth_fill(99, ns, 0, nfr, lm, channels, pkt_bytes)
