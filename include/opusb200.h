@@ -83,6 +83,7 @@ typedef struct {
                                   * untouched until opn_batch_synchronize, so the entropy stage of this call may overlap the
                                   * PVQ/IMDCT stage of the previous one (without the flag it is ordered after everything
                                   * enqueued on opn_batch_cuda_stream) */
+#define OPN_FLAG_SUBMIT_ONLY 8u  /* host-buffer call: enqueue and return a ticket for opn_batch_wait */
 
 int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out);
 void opn_batch_destroy(opn_batch *b);
@@ -95,6 +96,11 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
                            const uint32_t *lens, float *pcm, size_t pcm_stride_floats,
                            size_t frame_size, int32_t *result_per_stream, uint32_t flags);
 int opn_batch_synchronize(opn_batch *b);
+/* Host-buffer calls made with OPN_FLAG_SUBMIT_ONLY return a ticket (0 or 1) instead of waiting: at most two
+ * calls are in flight, so the PCM download of one overlaps the decode of the next.  The call's host buffers
+ * (arena, offsets, lens, pcm) belong to the library until opn_batch_wait(ticket) returns; result_per_stream is
+ * final on return of the submitting call. */
+int opn_batch_wait(opn_batch *b, int ticket);
 /* Per-stream Decoder::final_range() of the last decoded frame (host buffer, n_streams words). */
 int opn_batch_final_ranges(opn_batch *b, uint32_t *out);
 /* Device-resident PCM ring (history + output): base pointer, samples per channel in the ring,

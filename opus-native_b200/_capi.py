@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libopusb200.so")
 
 OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL = range(10)
-FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY = 1, 2, 4
+FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY = 1, 2, 4, 8
 OP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4")])
 OUT_DTYPE = np.dtype([("value", "<u4"), ("tell_frac", "<u4"), ("rng", "<u4")])
 SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra")]
@@ -89,6 +89,7 @@ def lib():
     sig("opn_batch_ring", C.c_int, vp, C.POINTER(vp), C.POINTER(u32), C.POINTER(vp))
     sig("opn_batch_enable_timing", C.c_int, vp, C.c_int)
     sig("opn_batch_stats", C.c_int, vp, vp, vp, C.c_int)
+    sig("opn_batch_wait", C.c_int, vp, C.c_int)
     sig("opn_batch_cuda_stream", vp, vp)
     sig("opn_op_rangedec_script", C.c_int, C.c_int, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp, u32)
     sig("opn_op_imdct_tdac", C.c_int, C.c_int, vp, sz, vp, sz, u32, C.c_int, C.c_int, C.c_int)
@@ -259,8 +260,12 @@ class BatchDecoder:
 
     def decode_float_ptrs(self, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_floats, frame_size, result_ptr, flags):
         """Raw pointers (host or device according to `flags`); used with pinned / device tensors."""
-        _chk(lib().opn_batch_decode_float(self._h, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_floats, frame_size,
-                                          result_ptr, flags))
+        return _chk(lib().opn_batch_decode_float(self._h, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_floats,
+                                                 frame_size, result_ptr, flags))
+
+    def wait(self, ticket):
+        """Completion of a host-buffer call submitted with FLAG_SUBMIT_ONLY (its return value is the ticket)."""
+        _chk(lib().opn_batch_wait(self._h, int(ticket)))
 
     def synchronize(self):
         _chk(lib().opn_batch_synchronize(self._h))

@@ -138,12 +138,18 @@ struct opn_batch {
     opn_synth_side *d_side[NSETS] = {};
     int32_t *d_status[NSETS] = {};
     // host-path staging (device + pinned host)
-    uint8_t *d_arena = nullptr;
-    size_t arena_cap = 0;
-    uint32_t *d_items = nullptr, *h_items = nullptr;  // [4][cap]: offsets, lens, stream_idx, dense_off
-    size_t items_cap = 0;
-    float *d_dense = nullptr;
-    size_t dense_cap = 0;  // floats per stream
+    // Two staging slots, so a host-buffer call can be submitted while the previous one is still downloading.
+    struct Staging {
+        uint8_t *d_arena = nullptr;
+        size_t arena_cap = 0;
+        uint32_t *d_items = nullptr, *h_items = nullptr;  // per chunk: [offsets | lens | stream ids | dense offsets]
+        size_t items_cap = 0;
+        float *d_dense = nullptr;
+        size_t dense_cap = 0;          // floats per stream
+        cudaEvent_t done = nullptr;    // everything that uses this slot has finished (incl. the PCM download)
+        bool pending = false;
+    } stg[2];
+    int stg_next = 0;
     float *d_softclip = nullptr;
     // host mirrors of DecoderInner fields (decoder.rs:236-258), per stream
     std::vector<int32_t> last_nf, bandwidth, last_duration, have_mode;
@@ -155,24 +161,25 @@ struct opn_batch {
 
 namespace {
 
-int batch_alloc_staging(opn_batch *b, size_t arena_bytes, size_t n_items, size_t dense_floats)
+int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes, size_t n_items, size_t dense_floats)
 {
-    if (arena_bytes > b->arena_cap) {
-        if (b->d_arena) cudaFree(b->d_arena);
-        b->arena_cap = arena_bytes + arena_bytes / 4 + 256;
-        CU(cudaMalloc(&b->d_arena, b->arena_cap));
+    if (!g.done) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    if (arena_bytes > g.arena_cap) {
+        if (g.d_arena) cudaFree(g.d_arena);
+        g.arena_cap = arena_bytes + arena_bytes / 4 + 256;
+        CU(cudaMalloc(&g.d_arena, g.arena_cap));
     }
-    if (n_items > b->items_cap) {
-        if (b->d_items) cudaFree(b->d_items);
-        if (b->h_items) cudaFreeHost(b->h_items);
-        b->items_cap = n_items + n_items / 4 + 64;
-        CU(cudaMalloc(&b->d_items, b->items_cap * 4 * sizeof(uint32_t)));
-        CU(cudaMallocHost(&b->h_items, b->items_cap * 4 * sizeof(uint32_t)));
+    if (n_items > g.items_cap) {
+        if (g.d_items) cudaFree(g.d_items);
+        if (g.h_items) cudaFreeHost(g.h_items);
+        g.items_cap = n_items + n_items / 4 + 64;
+        CU(cudaMalloc(&g.d_items, g.items_cap * 4 * sizeof(uint32_t)));
+        CU(cudaMallocHost(&g.h_items, g.items_cap * 4 * sizeof(uint32_t)));
     }
-    if (dense_floats > b->dense_cap) {
-        if (b->d_dense) cudaFree(b->d_dense);
-        b->dense_cap = dense_floats;
-        CU(cudaMalloc(&b->d_dense, (size_t)b->n * b->dense_cap * sizeof(float)));
+    if (dense_floats > g.dense_cap) {
+        if (g.d_dense) cudaFree(g.d_dense);
+        g.dense_cap = dense_floats;
+        CU(cudaMalloc(&g.d_dense, (size_t)b->n * g.dense_cap * sizeof(float)));
     }
     return OPN_OK;
 }
@@ -436,10 +443,13 @@ void opn_batch_destroy(opn_batch *b)
     cudaFree(b->d_pf);
     cudaFree(b->d_job);
     cudaFree(b->d_softclip);
-    cudaFree(b->d_arena);
-    cudaFree(b->d_items);
-    cudaFree(b->d_dense);
-    if (b->h_items) cudaFreeHost(b->h_items);
+    for (auto &g : b->stg) {
+        cudaFree(g.d_arena);
+        cudaFree(g.d_items);
+        cudaFree(g.d_dense);
+        if (g.h_items) cudaFreeHost(g.h_items);
+        if (g.done) cudaEventDestroy(g.done);
+    }
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -491,13 +501,20 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         items_ub += fc > 0 ? (size_t)fc : 1;
     }
     const size_t dense_stride = (frame_size * (size_t)C + 3) & ~(size_t)3;
-    int rc = batch_alloc_staging(b, arena_end, items_ub, dense_stride);
+    const int slot = b->stg_next;
+    b->stg_next ^= 1;
+    opn_batch::Staging &g = b->stg[slot];
+    if (g.pending) {  // the call that used this slot two submissions ago must be completely finished
+        CU(cudaEventSynchronize(g.done));
+        g.pending = false;
+    }
+    int rc = batch_alloc_staging(b, g, arena_end, items_ub, dense_stride);
     if (rc) return rc;
     const bool want_pcm = pcm != nullptr && !(flags & OPN_FLAG_NO_PCM_COPY);
-    if (arena_end) CU(cudaMemcpyAsync(b->d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_up));
+    if (arena_end) CU(cudaMemcpyAsync(g.d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_up));
 
     const uint32_t n_chunks = std::min<uint32_t>(opn_batch::MAX_CHUNKS, std::max<uint32_t>(1u, n / 1024u));
-    const size_t cap = b->items_cap;
+    const size_t cap = g.items_cap;
     std::vector<Item> items;
     items.reserve(items_ub / n_chunks + 64);
     std::vector<int32_t> res(n, 0);
@@ -566,7 +583,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         }
         if (kbase + items.size() > cap) return OPN_ERR_INTERNAL;  // the pre-pass bound covers every frame
         if (want_pcm && any_gap)
-            CU(cudaMemsetAsync(b->d_dense + (size_t)s0 * b->dense_cap, 0, (size_t)(s1 - s0) * b->dense_cap * sizeof(float), b->stream));
+            CU(cudaMemsetAsync(g.d_dense + (size_t)s0 * g.dense_cap, 0, (size_t)(s1 - s0) * g.dense_cap * sizeof(float), b->stream));
         if (!items.empty()) {
             // order: wave-major, then frame size, so each (wave, lm) bucket is contiguous
             std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
@@ -574,7 +591,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             });
             // one upload per chunk: [offsets | lens | stream ids | dense offsets], each cnt words, at 4*kbase
             const size_t cnt = items.size();
-            uint32_t *hi = b->h_items + 4 * kbase, *di = b->d_items + 4 * kbase;
+            uint32_t *hi = g.h_items + 4 * kbase, *di = g.d_items + 4 * kbase;
             for (size_t k = 0; k < cnt; k++) {
                 hi[k] = items[k].offset;
                 hi[cnt + k] = items[k].len;
@@ -587,8 +604,8 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             while (k0 < cnt) {
                 size_t k1 = k0;
                 while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
-                rc = run_bucket(b, b->d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
-                                items[k0].lm, 0, pkt_cap, want_pcm ? b->d_dense : nullptr, b->dense_cap, nullptr, 2);
+                rc = run_bucket(b, g.d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
+                                items[k0].lm, 0, pkt_cap, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2);
                 if (rc) return rc;
                 k0 = k1;
             }
@@ -599,26 +616,33 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 // decode_native(soft_clip=true), decoder.rs:413-419.  Reference quirk kept: the slice handed to
                 // pcm_soft_clip is samples[..sample_count] (per-channel count, not x channels).
                 // Only used by the single-stream decoder (one chunk, one row).
-                CU(launch_op_soft_clip(b->d_dense + (size_t)s0 * b->dense_cap, b->dense_cap, (size_t)std::max(res[s0], 0), C, s1 - s0,
+                CU(launch_op_soft_clip(g.d_dense + (size_t)s0 * g.dense_cap, g.dense_cap, (size_t)std::max(res[s0], 0), C, s1 - s0,
                                        b->d_softclip + (size_t)s0 * 2, b->stream));
             }
             // this chunk's PCM rows go home while the next chunk is decoded
             CU(cudaEventRecord(b->ev_chunk[ch], b->stream));
             CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
             const size_t row_bytes = frame_size * (size_t)C * sizeof(float);
-            if (pcm_stride == b->dense_cap && pcm_stride * sizeof(float) == row_bytes)
-                CU(cudaMemcpyAsync(pcm + (size_t)s0 * pcm_stride, b->d_dense + (size_t)s0 * b->dense_cap, (size_t)(s1 - s0) * row_bytes,
+            if (pcm_stride == g.dense_cap && pcm_stride * sizeof(float) == row_bytes)
+                CU(cudaMemcpyAsync(pcm + (size_t)s0 * pcm_stride, g.d_dense + (size_t)s0 * g.dense_cap, (size_t)(s1 - s0) * row_bytes,
                                    cudaMemcpyDeviceToHost, b->stream_dn));
             else
-                CU(cudaMemcpy2DAsync(pcm + (size_t)s0 * pcm_stride, pcm_stride * sizeof(float), b->d_dense + (size_t)s0 * b->dense_cap,
-                                     b->dense_cap * sizeof(float), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
+                CU(cudaMemcpy2DAsync(pcm + (size_t)s0 * pcm_stride, pcm_stride * sizeof(float), g.d_dense + (size_t)s0 * g.dense_cap,
+                                     g.dense_cap * sizeof(float), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         }
     }
     if (!soft_clip) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
-    CU(cudaStreamSynchronize(b->stream));
-    CU(cudaStreamSynchronize(b->stream_dn));
+    // completion of this call = the batch stream and the download stream have both drained
+    CU(cudaEventRecord(b->ev_in, b->stream));
+    CU(cudaStreamWaitEvent(b->stream_dn, b->ev_in, 0));
+    CU(cudaEventRecord(g.done, b->stream_dn));
+    g.pending = true;
     if (results) std::memcpy(results, res.data(), n * sizeof(int32_t));
-    return OPN_OK;
+    if (!(flags & OPN_FLAG_SUBMIT_ONLY)) {
+        CU(cudaEventSynchronize(g.done));
+        g.pending = false;
+    }
+    return slot;
 }
 
 int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, float *pcm,
@@ -631,7 +655,9 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
     if (!(flags & OPN_FLAG_DEVICE_PTRS)) {
         if (!arena) return OPN_ERR_BAD_ARG;
         if (pcm && pcm_stride_floats < frame_size * (size_t)C) return OPN_ERR_BUFFER_TOO_SMALL;
-        return batch_decode_host(b, arena, offsets, lens, pcm, pcm_stride_floats, frame_size, result_per_stream, flags, 0);
+        const int rc = batch_decode_host(b, arena, offsets, lens, pcm, pcm_stride_floats, frame_size, result_per_stream, flags, 0);
+        if (rc < 0) return rc;
+        return (flags & OPN_FLAG_SUBMIT_ONLY) ? rc : OPN_OK;  // submit-only: the ticket for opn_batch_wait
     }
     // Device-resident step: one single-frame CELT packet of exactly frame_size per stream; the TOC
     // is validated on the device and reported per stream.  Asynchronous on the batch stream.
@@ -650,7 +676,22 @@ int opn_batch_synchronize(opn_batch *b)
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
     for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
+    CU(cudaStreamSynchronize(b->stream_ex));
     CU(cudaStreamSynchronize(b->stream));
+    CU(cudaStreamSynchronize(b->stream_dn));
+    for (auto &g : b->stg) g.pending = false;
+    return OPN_OK;
+}
+
+int opn_batch_wait(opn_batch *b, int ticket)
+{
+    if (!b || ticket < 0 || ticket > 1) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    opn_batch::Staging &g = b->stg[ticket];
+    if (g.pending) {
+        CU(cudaEventSynchronize(g.done));
+        g.pending = false;
+    }
     return OPN_OK;
 }
 
@@ -774,7 +815,7 @@ static int decoder_decode(opn_decoder *d, const uint8_t *packet, size_t len, flo
     int32_t res = 0;
     int rc = batch_decode_host(d->batch, packet ? packet : &dummy, &off, &l, pcm, frame_size * (size_t)d->channels, frame_size,
                                &res, 0, soft_clip);
-    if (rc) return rc;
+    if (rc < 0) return rc;
     if (res >= 0) {
         uint32_t fr = 0;
         rc = opn_batch_final_ranges(d->batch, &fr);

@@ -401,6 +401,42 @@ def test_batch_frame_size_changes_mid_stream(channels):
     assert exact, "PCM within tolerance but not bit-identical to the oracle"
 
 
+def test_batch_submit_wait_two_calls_in_flight():
+    """OPN_FLAG_SUBMIT_ONLY / opn_batch_wait: the next call is submitted before the previous one's PCM has
+    been waited for; results equal the synchronous path (and the oracle) frame by frame."""
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 2304, 7, 960  # > 1024 streams: several chunks per call
+    packets = opn.synth_fill(1234, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+    sync = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0))
+    want = []
+    for f in range(nfr):
+        pcm = np.zeros((ns, nf * channels), np.float32)
+        sync.decode_float(packets[f].reshape(-1), offsets, lens, pcm, nf)
+        want.append(pcm)
+    oracle = [O.SynthStream(lm, channels) for _ in range(8)]
+    for f in range(nfr):
+        for s in range(8):
+            assert np.array_equal(oracle[s].decode(packets[f, s, 1:])[3], want[f][s])
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0))
+    bufs = [np.zeros((ns, nf * channels), np.float32) for _ in range(2)]
+    res = [np.zeros(ns, np.int32) for _ in range(2)]
+    arenas = [np.ascontiguousarray(packets[f].reshape(-1)) for f in range(nfr)]
+    ticket = None
+    for f in range(nfr):
+        q = f & 1
+        t = dec.decode_float_ptrs(arenas[f].ctypes.data, offsets.ctypes.data, lens.ctypes.data, bufs[q].ctypes.data, nf * channels, nf,
+                                  res[q].ctypes.data, opn.FLAG_SUBMIT_ONLY)
+        assert t in (0, 1)
+        if ticket is not None:
+            dec.wait(ticket)
+            assert np.array_equal(bufs[(f - 1) & 1], want[f - 1]), f - 1
+        ticket = t
+    dec.wait(ticket)
+    assert np.array_equal(bufs[(nfr - 1) & 1], want[nfr - 1])
+    assert np.all(res[0] == nf) and np.all(res[1] == nf)
+
+
 def test_batch_lost_invalid_and_foreign_packets_do_not_poison_neighbours():
     lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 16, 6, 960
     packets = opn.synth_fill(99, ns, 0, nfr, lm, channels, pkt_bytes)
