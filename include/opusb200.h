@@ -144,6 +144,11 @@ int opn_op_comb_filter(int device, float *y, const float *x, size_t row_stride, 
 int opn_op_pcm_soft_clip(int device, float *pcm, size_t row_stride, size_t row_len, int channels,
                          uint32_t n_rows, float *softclip_mem /* [n_rows][channels] */);
 
+/* bitexact_cos (src/math.rs:51-55) on x[0..n_cos) and bitexact_log2tan (math.rs:59-69) on (isin, icos)[0..n_log2tan):
+ * the Q15 integer trigonometry CELT's stereo/theta split uses.  Either half may be empty. */
+int opn_op_bitexact_trig(int device, const int16_t *x, int16_t *cos_out, uint32_t n_cos, const int32_t *isin,
+                         const int32_t *icos, int32_t *log2tan_out, uint32_t n_log2tan);
+
 /* ---- SYNTH-CELT/1 frames: side information the symbol kernel reports ------ */
 typedef struct {
     int32_t silence, postfilter, octave, period, gain_idx, tapset, transient, intra;

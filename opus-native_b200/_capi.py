@@ -90,6 +90,7 @@ def lib():
     sig("opn_batch_enable_timing", C.c_int, vp, C.c_int)
     sig("opn_batch_stats", C.c_int, vp, vp, vp, C.c_int)
     sig("opn_batch_wait", C.c_int, vp, C.c_int)
+    sig("opn_op_bitexact_trig", C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32)
     sig("opn_batch_cuda_stream", vp, vp)
     sig("opn_op_rangedec_script", C.c_int, C.c_int, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp, u32)
     sig("opn_op_imdct_tdac", C.c_int, C.c_int, vp, sz, vp, sz, u32, C.c_int, C.c_int, C.c_int)
@@ -336,6 +337,17 @@ def op_pcm_soft_clip(pcm, row_len, channels, mem, device=0):
     assert pcm.dtype == np.float32 and pcm.ndim == 2 and mem.dtype == np.float32 and mem.shape == (pcm.shape[0], channels)
     _chk(lib().opn_op_pcm_soft_clip(device, _p(pcm), pcm.shape[1], row_len, channels, pcm.shape[0], _p(mem)))
     return pcm
+
+
+def op_bitexact_trig(x=None, isin=None, icos=None, device=0):
+    """bitexact_cos(x) and/or bitexact_log2tan(isin, icos) on the device (src/math.rs:51-69)."""
+    x = np.zeros(0, np.int16) if x is None else np.ascontiguousarray(x, np.int16)
+    isin = np.zeros(0, np.int32) if isin is None else np.ascontiguousarray(isin, np.int32)
+    icos = np.zeros(0, np.int32) if icos is None else np.ascontiguousarray(icos, np.int32)
+    assert len(isin) == len(icos)
+    c, l = np.zeros(len(x), np.int16), np.zeros(len(isin), np.int32)
+    _chk(lib().opn_op_bitexact_trig(device, _p(x), _p(c), len(x), _p(isin), _p(icos), _p(l), len(isin)))
+    return c, l
 
 
 def op_synth_symbols(arena, offsets, lens, lm, channels, device=0):

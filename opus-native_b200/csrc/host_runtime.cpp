@@ -1021,6 +1021,31 @@ int opn_op_pcm_soft_clip(int device, float *pcm, size_t row_stride, size_t row_l
     return OPN_OK;
 }
 
+int opn_op_bitexact_trig(int device, const int16_t *x, int16_t *cos_out, uint32_t n_cos, const int32_t *isin, const int32_t *icos,
+                         int32_t *log2tan_out, uint32_t n_log2tan)
+{
+    if ((n_cos && (!x || !cos_out)) || (n_log2tan && (!isin || !icos || !log2tan_out))) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    DevBuf dX, dC, dS, dK, dL;
+    CU(dX.alloc((size_t)n_cos * 2));
+    CU(dC.alloc((size_t)n_cos * 2));
+    CU(dS.alloc((size_t)n_log2tan * 4));
+    CU(dK.alloc((size_t)n_log2tan * 4));
+    CU(dL.alloc((size_t)n_log2tan * 4));
+    if (n_cos) CU(cudaMemcpy(dX.p, x, (size_t)n_cos * 2, cudaMemcpyHostToDevice));
+    if (n_log2tan) {
+        CU(cudaMemcpy(dS.p, isin, (size_t)n_log2tan * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dK.p, icos, (size_t)n_log2tan * 4, cudaMemcpyHostToDevice));
+    }
+    CU(launch_op_bitexact_trig(dX.as<int16_t>(), dC.as<int16_t>(), n_cos, dS.as<int32_t>(), dK.as<int32_t>(), dL.as<int32_t>(),
+                               n_log2tan, nullptr));
+    CU(cudaDeviceSynchronize());
+    if (n_cos) CU(cudaMemcpy(cos_out, dC.p, (size_t)n_cos * 2, cudaMemcpyDeviceToHost));
+    if (n_log2tan) CU(cudaMemcpy(log2tan_out, dL.p, (size_t)n_log2tan * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
 int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
                          int lm, int channels, opn_synth_side *side_out, int32_t *y_out, float *coef_out)
 {

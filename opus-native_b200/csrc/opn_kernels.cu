@@ -4,6 +4,7 @@
 
 #include "imdct.cuh"
 #include "imdct_warp.cuh"
+#include "mathops.cuh"
 #include "opn_tables.h"
 #include "softclip.cuh"
 #include "symbols.cuh"
@@ -275,6 +276,15 @@ cudaError_t launch_op_comb(float *y, const float *x, size_t row_stride, int offs
 {
     if (n_rows == 0) return cudaSuccess;
     k_op_comb<<<n_rows, IM_TPC, 0, st>>>(y, x, row_stride, offset, n, params4, gains2, overlap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_op_bitexact_trig(const int16_t *x, int16_t *out_cos, uint32_t n_cos, const int32_t *isin, const int32_t *icos,
+                                    int32_t *out_l2t, uint32_t n_l2t, cudaStream_t st)
+{
+    const uint32_t n = n_cos > n_l2t ? n_cos : n_l2t;
+    if (n == 0) return cudaSuccess;
+    k_op_bitexact_trig<<<(n + 255) / 256, 256, 0, st>>>(x, out_cos, n_cos, isin, icos, out_l2t, n_l2t);
     return cudaGetLastError();
 }
 

@@ -337,6 +337,32 @@ def test_synth_symbols(lm, channels, pkt_bytes):
         assert np.array_equal(coef[s].reshape(-1).view(np.uint32), wc.view(np.uint32))
 
 
+def test_bitexact_trig_checksums():
+    """bitexact_cos / bitexact_log2tan on the device against the reference's own checksums
+    (src/math.rs:237-298) and, value by value, against the oracle."""
+    i = np.arange(64, 16321, dtype=np.int32)
+    c, _ = opn.op_bitexact_trig(x=i.astype(np.int16))
+    c = c.astype(np.int64)
+    assert (int(c[0]), int(c[-1]), int(c[8192 - 64])) == (32767, 200, 23171)
+    assert int(np.bitwise_xor.reduce(c * i)) == 89408644
+    d = np.diff(np.concatenate([[32767], c])) * -1
+    assert (int(d.max()), int(d.min())) == (5, 0)
+    L = O.lib()
+    assert np.array_equal(c, [L.orc_bitexact_cos(int(v)) for v in i])
+    j = np.arange(64, 8193, dtype=np.int32)
+    mid, _ = opn.op_bitexact_trig(x=j.astype(np.int16))
+    side, _ = opn.op_bitexact_trig(x=(16384 - j).astype(np.int16))
+    _, q = opn.op_bitexact_trig(isin=mid.astype(np.int32), icos=side.astype(np.int32))
+    _, qr = opn.op_bitexact_trig(isin=side.astype(np.int32), icos=mid.astype(np.int32))
+    assert np.array_equal(q, -qr)
+    q = q.astype(np.int64)
+    assert int(np.bitwise_xor.reduce(q * j)) == 15821257
+    d = np.diff(np.concatenate([[15059], q])) * -1
+    assert (int(d.max()), int(d.min())) == (61, -2)
+    _, k = opn.op_bitexact_trig(isin=[32767, 30274, 23171], icos=[200, 12540, 23171])
+    assert list(k) == [15059, 2611, 0]
+
+
 # ------------------------------------------------------------------ batch pipeline
 def _oracle_chain(packets, lm, channels, apply_comb=True):
     """packets [frames, streams, bytes] -> pcm [frames, streams, nf*C], final_rng [frames, streams]"""
