@@ -107,29 +107,34 @@ cudaError_t upload_tables(int device)
                 const SynthEntry &E = h.synth_entries[lm][C - 1][e];
                 for (int j = 0; j < (int)E.n; j++) eo[E.base + j] = (uint8_t)e;
             }
-            // deal the parts to 32 lanes, longest first onto the least loaded lane (cwrsi walks n dimensions
-            // and k pulses, so n + k is its cost; sign-only parts cost 1)
-            uint8_t(*le)[SYNTH_LANE_SLOTS] = h.synth_lane_entries[lm][C - 1];
-            int load[32], used[32];
-            for (int l = 0; l < 32; l++) {
-                load[l] = used[l] = 0;
-                for (int q = 0; q < SYNTH_LANE_SLOTS; q++) le[l][q] = 0xFF;
-            }
-            bool taken[SYNTH_MAX_ENTRIES] = {false};
-            for (int round = 0; round < ne; round++) {
-                int best = -1, bcost = -1;
-                for (int e = 0; e < ne; e++) {
-                    const SynthEntry &E = h.synth_entries[lm][C - 1][e];
-                    const int cost = E.n == 1 ? 1 : (int)E.n + (int)E.k;
-                    if (!taken[e] && cost > bcost) { best = e; bcost = cost; }
+            // k_synth_expand: parts sorted by size (descending), 32 per slot, so that the lanes of a slot walk
+            // similar numbers of dimensions in lockstep
+            {
+                int order[SYNTH_MAX_ENTRIES];
+                for (int e = 0; e < ne; e++) order[e] = e;
+                for (int a = 1; a < ne; a++) {  // insertion sort, stable
+                    const int v = order[a];
+                    int b2 = a - 1;
+                    while (b2 >= 0 && h.synth_entries[lm][C - 1][order[b2]].n < h.synth_entries[lm][C - 1][v].n) {
+                        order[b2 + 1] = order[b2];
+                        b2--;
+                    }
+                    order[b2 + 1] = v;
                 }
-                int lane = -1;
-                for (int l = 0; l < 32; l++)
-                    if (used[l] < SYNTH_LANE_SLOTS && (lane < 0 || load[l] < load[lane])) lane = l;
-                if (lane < 0) return cudaErrorInvalidValue;  // cannot happen: 32 x SYNTH_LANE_SLOTS >= 72
-                taken[best] = true;
-                le[lane][used[lane]++] = (uint8_t)best;
-                load[lane] += bcost;
+                const int nslots = (ne + 31) / 32;
+                if (nslots > SYNTH_SLOTS) return cudaErrorInvalidValue;
+                h.synth_n_slots[lm][C - 1] = (uint8_t)nslots;
+                for (int sl = 0; sl < SYNTH_SLOTS; sl++) {
+                    h.synth_slot_maxn[lm][C - 1][sl] = 0;
+                    for (int l = 0; l < 32; l++) {
+                        const int r = sl * 32 + l;
+                        h.synth_slot_entries[lm][C - 1][sl][l] = r < ne ? (uint8_t)order[r] : 0xFF;
+                        if (r < ne) {
+                            const uint8_t n = h.synth_entries[lm][C - 1][order[r]].n;
+                            if (n > h.synth_slot_maxn[lm][C - 1][sl]) h.synth_slot_maxn[lm][C - 1][sl] = n;
+                        }
+                    }
+                }
             }
         }
     h.tapset_icdf[0] = 2; h.tapset_icdf[1] = 1; h.tapset_icdf[2] = 0; h.tapset_icdf[3] = 0;

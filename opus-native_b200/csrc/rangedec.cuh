@@ -388,88 +388,6 @@ __device__ __forceinline__ float cwrsi_warp(const PvqTable &T, int32_t *y, uint3
     return (float)yy;
 }
 
-// cwrsi (pvc.rs:182-284) executed by ONE lane: the codeword index of a part is known, so 32 lanes
-// expand 32 different parts at the same time (the entropy decoder does not depend on the result).
-// Writes the NONZERO 16-bit pulses (|y| <= K <= 128) into y, which the caller has zeroed, and returns yy.
-__device__ __forceinline__ float cwrsi_lane(const PvqTable &T, int16_t *y, uint32_t n, uint32_t k, uint32_t i)
-{
-    int32_t yy = 0;
-    while (n > 2u) {
-        uint32_t p, k0;
-        int32_t s, val;
-        if (k >= n) {  // pvc.rs:196-231
-            uint32_t row = T.row[n];
-            p = T.data[row + k + 1u];
-            s = i >= p ? -1 : 0;
-            i -= (uint32_t)((int32_t)p & s);
-            k0 = k;
-            uint32_t q = T.data[row + n];
-            if (q > i) {
-                k = n;
-                do {
-                    k -= 1u;
-                    p = T.data[T.row[k] + n];
-                } while (p > i);
-            } else {
-                p = T.data[row + k];
-                while (p > i) {
-                    k -= 1u;
-                    p = T.data[row + k];
-                }
-            }
-            i -= p;
-            val = ((int32_t)k0 - (int32_t)k + s) ^ s;
-            *y++ = (int16_t)val;
-            yy += val * val;
-        } else {  // pvc.rs:232-258
-            // Runs of empty dimensions are the common case here (k < n): the two row offsets only
-            // change when k does, and an empty dimension is just "i -= U(k,n); next n" (y is pre-zeroed).
-            const uint32_t rk = T.row[k], rk1 = T.row[k + 1u];
-            uint32_t q;
-            bool empty;
-            for (;;) {
-                p = T.data[rk + n];
-                q = T.data[rk1 + n];
-                empty = p <= i && i < q;
-                if (!empty) break;
-                i -= p;
-                y++;
-                n -= 1u;
-                if (n <= 2u || k >= n) break;
-            }
-            if (empty) continue;  // reached the closed-form tail (n == 2) or the k >= n regime: dispatch again
-            s = i >= q ? -1 : 0;
-            i -= (uint32_t)((int32_t)q & s);
-            k0 = k;
-            do {
-                k -= 1u;
-                p = T.data[T.row[k] + n];
-            } while (p > i);
-            i -= p;
-            val = ((int32_t)k0 - (int32_t)k + s) ^ s;
-            *y++ = (int16_t)val;
-            yy += val * val;
-        }
-        n -= 1u;
-    }
-    // n == 2 (pvc.rs:262-275)
-    uint32_t p = 2u * k + 1u;
-    int32_t s = i >= p ? -1 : 0;
-    i -= (uint32_t)((int32_t)p & s);
-    uint32_t k0 = k;
-    k = (i + 1u) >> 1;
-    if (k != 0u) i -= 2u * k - 1u;
-    int32_t val = ((int32_t)k0 - (int32_t)k + s) ^ s;
-    *y++ = (int16_t)val;
-    yy += val * val;
-    // n == 1 (pvc.rs:277-281)
-    s = -(int32_t)i;
-    val = ((int32_t)k + s) ^ s;
-    *y = (int16_t)val;
-    yy += val * val;
-    return (float)yy;
-}
-
 // decode_pulses (pvc.rs:156-160)
 __device__ __forceinline__ float decode_pulses_warp(RangeDec &d, const PvqTable &T, int32_t *y, uint32_t n, uint32_t k,
                                                     uint32_t lane)

@@ -280,28 +280,103 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
         }
         return;
     }
-    // index -> pulse vector, parts dealt longest-first to the lanes (tables: opn_kernels.cu); cwrsi_lane
-    // only stores the nonzero pulses
+    // index -> pulse vector (cwrsi, pvc.rs:182-284; only nonzero pulses are stored).  The parts are sorted by
+    // size and dealt 32 at a time ("slots", tables: opn_kernels.cu); inside a slot the lanes run in lockstep on
+    // the dimension countdown c: a lane whose part has n dimensions joins when c reaches n, so every active
+    // lane is at dimension n == c and all lanes reach the closed-form tail (n == 2) together.  One loop
+    // iteration is one dimension for every lane -- empty or not -- instead of every lane's run of empty
+    // dimensions being waited for by the whole warp.
     for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
     {
-        PvqTable T{s_pvq, s_row};
-        const uint8_t *mine = g_tab.synth_lane_entries[lm][C - 1][lane];
+        const uint32_t *U = s_pvq;
+        const uint16_t *row = s_row;
+        const int nslots = g_tab.synth_n_slots[lm][C - 1];
 #pragma unroll 1
-        for (int slot = 0; slot < SYNTH_LANE_SLOTS; slot++) {
-            const uint32_t e = mine[slot];
-            if (e == 0xFFu) break;
-            const SynthEntry E = s_ent[e];
-            const uint32_t v = s_idx[e];
-            float g;
-            if (E.n == 1) {
-                s_y[E.base] = v ? (int16_t)-1 : (int16_t)1;
-                g = 0.03125f;
-            } else {
-                const float yy = cwrsi_lane(T, s_y + E.base, E.n, E.k, v);
-                g = 0.03125f / sqrtf(yy);
+        for (int slot = 0; slot < nslots; slot++) {
+            const uint32_t e = g_tab.synth_slot_entries[lm][C - 1][slot][lane];
+            const bool has = e != 0xFFu;
+            const SynthEntry E = s_ent[has ? e : 0u];
+            uint32_t n = has ? E.n : 0u, k = E.k, i = has ? s_idx[e] : 0u;
+            int16_t *y = s_y + E.base;
+            int32_t yy = 0;
+            if (has && n == 1u) {  // sign-only band
+                *y = i ? (int16_t)-1 : (int16_t)1;
+                yy = 1;
             }
-            s_gain[e] = g;
+            uint32_t rk = row[min(k, 14u)], rk1 = row[min(k + 1u, 14u)];  // row offsets of U(k,.) and U(k+1,.): only read when k < n
+            const int maxn = g_tab.synth_slot_maxn[lm][C - 1][slot];
+#pragma unroll 1
+            for (uint32_t c = (uint32_t)maxn; c > 2u; c--) {
+                if (n != c) continue;  // not started yet (n < c), no part (n == 0) or sign-only (n == 1)
+                if (k >= n) {  // lots of pulses, pvc.rs:196-231
+                    const uint32_t rn = row[n];
+                    uint32_t p = U[rn + k + 1u];
+                    const int32_t sg = i >= p ? -1 : 0;
+                    i -= (uint32_t)((int32_t)p & sg);
+                    const uint32_t k0 = k;
+                    const uint32_t q = U[rn + n];
+                    if (q > i) {
+                        k = n;
+                        do {
+                            k -= 1u;
+                            p = U[row[k] + n];
+                        } while (p > i);
+                    } else {
+                        p = U[rn + k];
+                        while (p > i) {
+                            k -= 1u;
+                            p = U[rn + k];
+                        }
+                    }
+                    i -= p;
+                    const int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
+                    *y = (int16_t)val;
+                    yy += val * val;
+                    rk = row[min(k, 14u)];
+                    rk1 = row[min(k + 1u, 14u)];
+                } else {  // lots of dimensions, pvc.rs:232-258
+                    uint32_t p = U[rk + n];
+                    const uint32_t q = U[rk1 + n];
+                    if (p <= i && i < q) {
+                        i -= p;
+                    } else {
+                        const int32_t sg = i >= q ? -1 : 0;
+                        i -= (uint32_t)((int32_t)q & sg);
+                        const uint32_t k0 = k;
+                        do {
+                            k -= 1u;
+                            p = U[row[k] + n];
+                        } while (p > i);
+                        i -= p;
+                        const int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
+                        *y = (int16_t)val;
+                        yy += val * val;
+                        rk = row[k];
+                        rk1 = row[k + 1u];
+                    }
+                }
+                y++;
+                n -= 1u;
+            }
+            if (n == 2u) {
+                // n == 2 (pvc.rs:262-275)
+                uint32_t p = 2u * k + 1u;
+                int32_t sg = i >= p ? -1 : 0;
+                i -= (uint32_t)((int32_t)p & sg);
+                const uint32_t k0 = k;
+                k = (i + 1u) >> 1;
+                if (k != 0u) i -= 2u * k - 1u;
+                int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
+                y[0] = (int16_t)val;
+                yy += val * val;
+                // n == 1 (pvc.rs:277-281)
+                sg = -(int32_t)i;
+                val = ((int32_t)k + sg) ^ sg;
+                y[1] = (int16_t)val;
+                yy += val * val;
+            }
+            if (has) s_gain[e] = 0.03125f / sqrtf((float)yy);
         }
     }
     __syncwarp();
