@@ -235,6 +235,7 @@ def main():
             e0.record()
             for f in range(k0, k1):
                 step_resident(f)
+            dec.join()  # the last post-filter kernel runs on an internal stream: make it an ancestor of e1
             e1.record()
         dec.synchronize()
         barrier()

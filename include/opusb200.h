@@ -112,6 +112,10 @@ int opn_batch_ring(opn_batch *b, float **ring, uint32_t *ring_samples, uint32_t 
 int opn_batch_enable_timing(opn_batch *b, int on);
 int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[3], int reset);
 void *opn_batch_cuda_stream(opn_batch *b);
+/* The library runs its stages on several internal streams.  opn_batch_join makes everything enqueued so far
+ * an ancestor of whatever is enqueued next on opn_batch_cuda_stream (e.g. the caller's end-of-region event or
+ * a consumer kernel reading the PCM ring); it does not block the host. */
+int opn_batch_join(opn_batch *b);
 
 /* ---- operator-level entry points (host pointers in/out; mirror the pub(crate) operators) */
 /* One record per range-coder call; replayed by one warp per packet.  RangeDecoder::*,

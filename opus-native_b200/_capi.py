@@ -90,6 +90,7 @@ def lib():
     sig("opn_batch_enable_timing", C.c_int, vp, C.c_int)
     sig("opn_batch_stats", C.c_int, vp, vp, vp, C.c_int)
     sig("opn_batch_wait", C.c_int, vp, C.c_int)
+    sig("opn_batch_join", C.c_int, vp)
     sig("opn_op_bitexact_trig", C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32)
     sig("opn_batch_cuda_stream", vp, vp)
     sig("opn_op_rangedec_script", C.c_int, C.c_int, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp, u32)
@@ -267,6 +268,10 @@ class BatchDecoder:
     def wait(self, ticket):
         """Completion of a host-buffer call submitted with FLAG_SUBMIT_ONLY (its return value is the ticket)."""
         _chk(lib().opn_batch_wait(self._h, int(ticket)))
+
+    def join(self):
+        """Order everything enqueued so far before whatever comes next on `cuda_stream` (no host wait)."""
+        _chk(lib().opn_batch_join(self._h))
 
     def synchronize(self):
         _chk(lib().opn_batch_synchronize(self._h))

@@ -121,6 +121,10 @@ struct opn_batch {
     static constexpr int NSETS = 6, NRD = 4;
     cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: two entropy stages may overlap each other
     cudaStream_t stream_ex = nullptr;     // PVQ expansion: between the entropy streams and `stream`
+    cudaStream_t stream_k2 = nullptr;     // kernel 2 (post-filter): one step behind kernel 1 on `stream`
+    cudaEvent_t ev_k1[NSETS] = {};        // kernel 1 of set p finished
+    cudaEvent_t ev_k2[NSETS] = {};        // kernel 2 of set p finished (recorded on `stream` when there is no kernel 2)
+    bool k2_recorded[NSETS] = {};
     cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
     cudaEvent_t ev_ex[NSETS] = {};        // PVQ expansion of set p finished (coefficients ready)
     cudaEvent_t ev_use[NSETS] = {};       // last consumer of set p finished
@@ -129,12 +133,12 @@ struct opn_batch {
     cudaStream_t stream_up = nullptr, stream_dn = nullptr;  // host path: item/packet upload, PCM download
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};                  // PVQ/IMDCT stage of a chunk finished
     bool use_recorded[NSETS] = {};
-    int set = 0;
+    int set = 0, last_set = -1;
     // per-stream state (device, SoA)
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef[NSETS] = {};
     uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[NSETS] = {};
     PfState *d_pf = nullptr;
-    CombJob *d_job = nullptr;
+    CombJob *d_job[NSETS] = {};
     opn_synth_side *d_side[NSETS] = {};
     int32_t *d_status[NSETS] = {};
     // host-path staging (device + pinned host)
@@ -281,15 +285,41 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.gain = b->gain;
     m.result = d_result;
     m.final_range = b->d_final;
-    m.job = b->d_job;
-    rc = timed_launch(b, 1, do_imdct, &m);
-    if (rc) return rc;
-    if (m.postfilter) {
-        rc = timed_launch(b, 2, do_comb, &m);
+    m.job = b->d_job[p];
+    if (b->timing) {
+        rc = timed_launch(b, 1, do_imdct, &m);
         if (rc) return rc;
+        if (m.postfilter) {
+            rc = timed_launch(b, 2, do_comb, &m);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(b->ev_k2[p], b->stream));
+        b->k2_recorded[p] = true;
+        CU(cudaEventRecord(b->ev_use[p], b->stream));
+        b->use_recorded[p] = true;
+        b->last_set = p;
+        return OPN_OK;
     }
-    CU(cudaEventRecord(b->ev_use[p], b->stream));
+    // Kernel 1 of this step may overlap kernel 2 of the previous step (it writes frame n+1 of the ring while
+    // the post-filter still reads frame n and up to 1024 samples before it), but not the one before that.
+    const int p2 = (p + opn_batch::NSETS - 2) % opn_batch::NSETS;
+    if (b->k2_recorded[p2]) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[p2], 0));
+    CU(launch_imdct_post(m, b->stream));
+    b->launches[1]++;
+    CU(cudaEventRecord(b->ev_k1[p], b->stream));
+    if (m.postfilter) {
+        CU(cudaStreamWaitEvent(b->stream_k2, b->ev_k1[p], 0));  // kernel 2 launches are ordered among themselves by stream_k2
+        CU(launch_comb_post(m, b->stream_k2));
+        b->launches[2]++;
+        CU(cudaEventRecord(b->ev_k2[p], b->stream_k2));
+        CU(cudaEventRecord(b->ev_use[p], b->stream_k2));
+    } else {
+        CU(cudaEventRecord(b->ev_k2[p], b->stream));
+        CU(cudaEventRecord(b->ev_use[p], b->stream));
+    }
+    b->k2_recorded[p] = true;
     b->use_recorded[p] = true;
+    b->last_set = p;
     return OPN_OK;
 }
 
@@ -368,12 +398,16 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_use[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k1[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k2[q], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_job[q], n * sizeof(CombJob));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_coef[q], n * (size_t)cfg->channels * 960 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_side[q], n * sizeof(opn_synth_side));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_k2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_dn, cudaStreamNonBlocking);
@@ -383,7 +417,6 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ring_pos, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_job, n * sizeof(CombJob));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_softclip, n * 2 * sizeof(float));
     if (e != cudaSuccess) {
         opn_batch_destroy(b);
@@ -413,6 +446,9 @@ void opn_batch_destroy(opn_batch *b)
         if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
         if (b->ev_use[q]) cudaEventDestroy(b->ev_use[q]);
         if (b->ev_ex[q]) cudaEventDestroy(b->ev_ex[q]);
+        if (b->ev_k1[q]) cudaEventDestroy(b->ev_k1[q]);
+        if (b->ev_k2[q]) cudaEventDestroy(b->ev_k2[q]);
+        cudaFree(b->d_job[q]);
         cudaFree(b->d_idx[q]);
         cudaFree(b->d_coef[q]);
         cudaFree(b->d_side[q]);
@@ -421,6 +457,10 @@ void opn_batch_destroy(opn_batch *b)
     if (b->stream_ex) {
         cudaStreamSynchronize(b->stream_ex);
         cudaStreamDestroy(b->stream_ex);
+    }
+    if (b->stream_k2) {
+        cudaStreamSynchronize(b->stream_k2);
+        cudaStreamDestroy(b->stream_k2);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
     for (int q = 0; q < opn_batch::MAX_CHUNKS; q++)
@@ -441,7 +481,6 @@ void opn_batch_destroy(opn_batch *b)
     cudaFree(b->d_ring_pos);
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
-    cudaFree(b->d_job);
     cudaFree(b->d_softclip);
     for (auto &g : b->stg) {
         cudaFree(g.d_arena);
@@ -465,12 +504,16 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     CU(cudaMemsetAsync(b->d_final, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_pf, 0, n * sizeof(PfState), b->stream));
     for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
+    CU(cudaStreamSynchronize(b->stream_ex));
+    CU(cudaStreamSynchronize(b->stream_k2));
     for (int q = 0; q < opn_batch::NSETS; q++) {
         CU(cudaMemsetAsync(b->d_side[q], 0, n * sizeof(opn_synth_side), b->stream));
         CU(cudaMemsetAsync(b->d_status[q], 0, n * sizeof(int32_t), b->stream));
         b->use_recorded[q] = false;
+        b->k2_recorded[q] = false;
     }
     b->set = 0;
+    b->last_set = -1;
     CU(cudaMemsetAsync(b->d_softclip, 0, n * 2 * sizeof(float), b->stream));
     CU(cudaStreamSynchronize(b->stream));
     std::fill(b->last_nf.begin(), b->last_nf.end(), 120);
@@ -612,6 +655,11 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             kbase += items.size();
         }
         if (want_pcm) {
+            // the chunk's last kernel 2 runs on its own stream: order the rest of this chunk after it
+            if (b->last_set >= 0 && b->k2_recorded[b->last_set]) {
+                if (soft_clip) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[b->last_set], 0));
+                else CU(cudaStreamWaitEvent(b->stream_dn, b->ev_k2[b->last_set], 0));
+            }
             if (soft_clip) {
                 // decode_native(soft_clip=true), decoder.rs:413-419.  Reference quirk kept: the slice handed to
                 // pcm_soft_clip is samples[..sample_count] (per-channel count, not x channels).
@@ -632,9 +680,10 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         }
     }
     if (!soft_clip) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
-    // completion of this call = the batch stream and the download stream have both drained
+    // completion of this call = the batch stream, the post-filter stream and the download stream have drained
     CU(cudaEventRecord(b->ev_in, b->stream));
     CU(cudaStreamWaitEvent(b->stream_dn, b->ev_in, 0));
+    if (b->last_set >= 0 && b->k2_recorded[b->last_set]) CU(cudaStreamWaitEvent(b->stream_dn, b->ev_k2[b->last_set], 0));
     CU(cudaEventRecord(g.done, b->stream_dn));
     g.pending = true;
     if (results) std::memcpy(results, res.data(), n * sizeof(int32_t));
@@ -678,8 +727,18 @@ int opn_batch_synchronize(opn_batch *b)
     for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
     CU(cudaStreamSynchronize(b->stream_ex));
     CU(cudaStreamSynchronize(b->stream));
+    CU(cudaStreamSynchronize(b->stream_k2));
     CU(cudaStreamSynchronize(b->stream_dn));
     for (auto &g : b->stg) g.pending = false;
+    return OPN_OK;
+}
+
+int opn_batch_join(opn_batch *b)
+{
+    if (!b) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    // everything enqueued so far ends either on `stream` or with a kernel 2 on stream_k2
+    if (b->last_set >= 0 && b->k2_recorded[b->last_set]) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[b->last_set], 0));
     return OPN_OK;
 }
 

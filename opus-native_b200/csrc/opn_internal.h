@@ -11,7 +11,9 @@ namespace opn {
 constexpr int SYM_WARPS_PER_CTA = 4;
 constexpr int IM_TPC = 128;         // threads per row of the out-of-place comb operator kernel
 constexpr int HIST_CAP = 1024;      // comb history window in shared memory (T + 2 <= 1024)
-constexpr int RING_SAMPLES = 2880;  // per-channel PCM ring: 3 x 960 = 6 x 480 = 12 x 240 = 24 x 120
+// per-channel PCM ring: 4 x 960 = 8 x 480 = 16 x 240 = 32 x 120.  Four long frames, so that kernel 1 may write
+// frame n+1 while kernel 2 still reads frame n and its history (960 + 960 + 1024 <= 3840).
+constexpr int RING_SAMPLES = 3840;
 constexpr int32_t ITEM_OK = 0, ITEM_LOST = 1;  // kernel-0 status; negative = OPN_ERR_* (state untouched)
 
 struct PfState {  // post-filter parameters of the previous frame

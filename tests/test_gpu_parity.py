@@ -561,7 +561,7 @@ def test_batch_device_resident_path_matches_host_path():
         assert np.array_equal(d_pcm.cpu().numpy()[keep], want[f])
     # ring view: the last frame of stream 0 sits just before ring_pos
     ring_ptr, ring_n, pos_ptr = dec.ring()
-    assert ring_n == 2880 and ring_ptr and pos_ptr
+    assert ring_n == 3840 and ring_ptr and pos_ptr
 
 
 # ------------------------------------------------------------------ Decoder API (decoder.rs:27-232)
