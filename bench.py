@@ -341,7 +341,8 @@ def main():
                 "streams_per_gpu": n, "frames_per_step_per_gpu": n, "packet_bytes": PKT_BYTES,
                 "transient_permille": args.transient_permille,
                 "cache": f"inputs larger than L2: {total} distinct packet sets resident in HBM, each read once; "
-                         "decoder state (PCM ring + carry + coefficients) is 130 MB per 4096 streams",
+                         "per 4096 streams the decoder touches 126 MB of PCM ring plus six rotating 31.5 MB coefficient sets, "
+                         "more than the 126 MB L2",
                 "per_kernel_ms": {"k_synth_rangedec+k_synth_expand": k0_ms, "k_imdct_post_w": k1_ms, "k_comb_post_w": k2_ms,
                                   "note": "second pass of the same steps, stages in order on one stream with cudaEvents around "
                                           "each; in the measured run the entropy stage of step n+1 overlaps the IMDCT of step n"},

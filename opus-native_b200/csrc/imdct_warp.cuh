@@ -44,7 +44,6 @@ template <int I> struct WTw {
     __device__ __forceinline__ static float2 get() { return make_float2(re, im); }
 };
 
-constexpr int W_MAX_WPC = 1;       // warps (= streams) per CTA
 #ifndef OPN_K1_MIN_CTAS
 #define OPN_K1_MIN_CTAS 20
 #endif
@@ -515,21 +514,19 @@ __device__ __forceinline__ void w_comb(float *y, int t0, int t1, int n, float g0
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 1 (IMDCT + TDAC overlap-add + PCM store): one warp = one stream (item).
+// kernel 1 (IMDCT + TDAC overlap-add + PCM store): one warp = one CTA = one stream (item).
 // Shared memory per warp: C rows of nf+60 floats and one mbarrier.  The post-filter runs in kernel 2
 // on the interleaved PCM this kernel leaves in the ring; kernel 1 only decides whether it is needed and
 // leaves the parameters (old -> new) in `job`.
-template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC, W_K1_MIN_CTAS) k_imdct_post_w(ImdctArgs A)
+template <int LM, int C> __global__ void __launch_bounds__(32, W_K1_MIN_CTAS) k_imdct_post_w(ImdctArgs A)
 {
-    extern __shared__ __align__(16) float sm_all[];
+    extern __shared__ __align__(16) float o[];
     constexpr int NF = 120 << LM;
     constexpr int CHF = w_ch_floats(LM);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *o = sm_all + warp * (w_smem_bytes(LM, C) / 4);
+    const int lane = threadIdx.x;
     uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);
 
-    const uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (item >= A.n_items) return;
+    const uint32_t item = blockIdx.x;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
     // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
     if (lane == 0) {
@@ -634,22 +631,20 @@ template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC, W_K1_
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel 2 (pitch comb post-filter, comb_filter_inplace): one warp = one stream (item) whose job is on.
+// kernel 2 (pitch comb post-filter, comb_filter_inplace): one warp = one CTA = one stream (item) whose job is on.
 // The history (the T+2 samples before the frame) and the frame are one contiguous span of the
 // interleaved ring: one TMA transfer (three when the span wraps) brings both into shared memory, the
 // filter runs in place on float2 = (left, right) samples, and the frame goes back to the ring and, for
 // host-buffer calls, to the dense output rows.
-template <int LM, int C> __global__ void __launch_bounds__(32 * W_MAX_WPC) k_comb_post_w(ImdctArgs A)
+template <int LM, int C> __global__ void __launch_bounds__(32) k_comb_post_w(ImdctArgs A)
 {
-    extern __shared__ __align__(16) float sm_all[];
+    extern __shared__ __align__(16) float sm[];
     constexpr int NF = 120 << LM;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *sm = sm_all + warp * (w_comb_smem_bytes(LM, C) / 4);
+    const int lane = threadIdx.x;
     float *y = sm + C * HIST_CAP;  // sample 0 of the frame; history below
     uint64_t *bar = reinterpret_cast<uint64_t *>(y + C * NF);
 
-    const uint32_t item = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (item >= A.n_items) return;
+    const uint32_t item = blockIdx.x;
     const CombJob j = A.job[item];
     if (!j.on) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;

@@ -1,5 +1,4 @@
 // opn_kernels.cu -- the single CUDA translation unit of libopusb200 (sm_100a, -fmad=false).
-#include <cstdlib>
 #include <mutex>
 
 #include "imdct.cuh"
@@ -15,20 +14,14 @@ namespace opn {
 static std::mutex g_tab_mutex;
 static int g_sm_count = 148;
 constexpr int W_CARVEOUT_PCT = 100;
-constexpr int W_WPC = 1;  // warps per CTA of kernel 1
 static bool g_tab_done[64];
 
 template <int LM, int C> static cudaError_t set_carveout()
 {
     // percent of the SM's unified 256 KB used as shared memory; the rest is L1 (tables, history taps)
-    static const int pct = getenv("OPN_CARVEOUT") ? atoi(getenv("OPN_CARVEOUT")) : W_CARVEOUT_PCT;
-    cudaError_t e = cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W_MAX_WPC * w_smem_bytes(LM, C)));
+    cudaError_t e = cudaFuncSetAttribute(k_comb_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_comb_post_w<LM, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W_MAX_WPC * w_comb_smem_bytes(LM, C)));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_comb_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
 }
 static cudaError_t set_warp_kernel_attributes()
 {
@@ -158,9 +151,7 @@ cudaError_t upload_tables(int device)
 
 template <int LM, int C> static cudaError_t launch_imdct_w(const ImdctArgs &a, cudaStream_t st)
 {
-    static const int wpc_env = getenv("OPN_IMDCT_WPC") ? atoi(getenv("OPN_IMDCT_WPC")) : W_WPC;
-    const uint32_t wpc = (uint32_t)(wpc_env < 1 ? 1 : wpc_env > W_MAX_WPC ? W_MAX_WPC : wpc_env);
-    k_imdct_post_w<LM, C><<<(a.n_items + wpc - 1) / wpc, 32 * wpc, wpc * w_smem_bytes(LM, C), st>>>(a);
+    k_imdct_post_w<LM, C><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
     return cudaGetLastError();
 }
 

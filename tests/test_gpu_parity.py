@@ -564,6 +564,37 @@ def test_batch_device_resident_path_matches_host_path():
     assert ring_n == 3840 and ring_ptr and pos_ptr
 
 
+@pytest.mark.parametrize("postfilter", [True, False])
+def test_batch_device_resident_steps_enqueued_back_to_back(postfilter):
+    """OPN_FLAG_INPUTS_READY: 14 steps are enqueued without a host wait in between, so range decode, PVQ
+    expansion, IMDCT and post-filter of up to six different steps are in flight at once (six buffer sets,
+    kernel 2 one step behind kernel 1 on the four-frame ring).  Every step's PCM row is written to its own
+    dense buffer and checked after one final synchronize, bit for bit, against the oracle."""
+    torch = pytest.importorskip("torch")
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 96, 14, 960
+    packets = opn.synth_fill(77, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=120)
+    want, want_rng = _oracle_chain(packets, lm, channels, postfilter)
+    dev = torch.device("cuda:0")
+    d_arena = torch.from_numpy(packets.reshape(-1).copy()).to(dev)
+    d_off = torch.arange(ns, dtype=torch.int32, device=dev) * pkt_bytes
+    d_len = torch.full((ns,), pkt_bytes, dtype=torch.int32, device=dev)
+    d_pcm = torch.zeros((nfr, ns, nf * channels), dtype=torch.float32, device=dev)
+    d_res = torch.zeros((nfr, ns), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), postfilter=postfilter)
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY
+    for f in range(nfr):
+        dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), d_pcm[f].data_ptr(),
+                              nf * channels, nf, d_res[f].data_ptr(), flags)
+    dec.join()
+    dec.synchronize()
+    assert np.all(d_res.cpu().numpy() == nf)
+    got = d_pcm.cpu().numpy()
+    for f in range(nfr):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(dec.final_ranges(), want_rng[nfr - 1])
+
+
 # ------------------------------------------------------------------ Decoder API (decoder.rs:27-232)
 def test_decoder_api_single_stream():
     lm, channels, pkt_bytes, nf = 3, 2, 160, 960
