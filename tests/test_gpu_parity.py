@@ -689,3 +689,14 @@ def test_config2_full_size_properties():
     assert np.array_equal(pcm, want_pcm)
     rms = math.sqrt(float((pcm.astype(np.float64) ** 2).mean()))
     assert 0.01 < rms < 1.0  # the 1e-5 bar is applied on +-1-scale PCM
+
+
+def test_cpp_mirror_example_single_equals_batch():
+    """examples/decode_batch.cpp through include/opusb200.hpp: BatchDecoder with two calls in flight and a
+    single-stream Decoder agree bit for bit on stream 0, from compiled host code (no Python in the path)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "examples")], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(root, "examples", "decode_batch"), "1500", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "single==batch:yes" in r.stdout

@@ -210,3 +210,15 @@ def test_digit_reversal_closed_form():
                 assert bitrev[i] == gs * g + p
                 seen.add(i)
         assert len(seen) == nfft
+
+
+def test_cpp_mirror_compiles_and_fails_loudly_without_gpu():
+    """include/opusb200.hpp (the C++ mirror of Decoder / DecoderConfiguration / OpusError) builds against the
+    library; without a CUDA device the example exits with the library's Cuda error, never with PCM."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
+    exe = os.path.join(ROOT, "examples", "decode_batch")
+    assert os.path.exists(exe)
+    if opn.lib().opn_device_count() > 0:
+        pytest.skip("a CUDA device is present (the GPU suite runs the example)")
+    r = subprocess.run([exe, "4", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "OpusError(-7)" in r.stderr and r.stdout == ""
