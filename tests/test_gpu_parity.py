@@ -596,6 +596,26 @@ def test_batch_device_resident_steps_enqueued_back_to_back(postfilter):
 
 
 # ------------------------------------------------------------------ Decoder API (decoder.rs:27-232)
+def test_baseline_config0_one_mono_stream_1000_chained_frames():
+    """BASELINE.json configs[0]: one synthetic 20 ms 48 kHz mono stream, 1000 chained frames, decoded through
+    Decoder::decode_float one packet at a time; the CPU oracle's output is the reference output.  Every
+    frame must be bit-identical (PCM and final_range): state (overlap carry, post-filter history across
+    many ring wraps, post-filter parameters) is carried for 20 s of audio."""
+    lm, channels, pkt_bytes, nf, nfr = 3, 1, 100, 960, 1000
+    packets = opn.synth_fill(4242, 1, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)[:, 0]
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 1, 0))
+    st = O.SynthStream(lm, channels)
+    pcm = np.zeros(nf, np.float32)
+    energy = 0.0
+    for f in range(nfr):
+        assert dec.decode_float(packets[f], pcm, nf) == nf
+        side, _, _, want = st.decode(packets[f, 1:])
+        assert np.array_equal(pcm, want), f
+        assert dec.final_range == side.final_rng, f
+        energy += float((pcm.astype(np.float64) ** 2).sum())
+    assert 0.01 < np.sqrt(energy / (nf * nfr)) < 1.0  # a real signal, not silence
+
+
 def test_decoder_api_single_stream():
     lm, channels, pkt_bytes, nf = 3, 2, 160, 960
     dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0))
