@@ -306,6 +306,33 @@ def main():
     assert np.all(res[0] == NF) and np.all(res[1] == NF)
     checksum = float(np.abs(p_np[(total - 1) & 1]).sum())
 
+    # ---------------- the same end-to-end loop through Decoder::decode::<i16> (extra figure, not the headline) ----
+    # soft clip + Sample::from_f32 run on the device, so half the bytes cross PCIe.
+    K16 = min(K, 100)
+    dec3 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local)
+    h_pcm16 = [torch.zeros((n, NF * CHANNELS), dtype=torch.int16).pin_memory() for _ in range(2)]
+    p16 = [t.numpy() for t in h_pcm16]
+
+    def run_e2e_i16(k0, k1):
+        ticket = None
+        for f in range(k0, k1):
+            q = f & 1
+            t = dec3.decode_i16_ptrs(a_np.ctypes.data + f * step_bytes, offs.ctypes.data, lens.ctypes.data, p16[q].ctypes.data,
+                                     NF * CHANNELS, NF, res[q].ctypes.data, opn.FLAG_SUBMIT_ONLY)
+            if ticket is not None:
+                dec3.wait(ticket)
+            ticket = t
+        dec3.wait(ticket)
+
+    run_e2e_i16(0, W)
+    barrier()
+    t0 = time.perf_counter()
+    run_e2e_i16(W, W + K16)
+    torch.cuda.synchronize()
+    t_e2e16 = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert np.all(res[0] == NF) and np.all(res[1] == NF) and int(np.abs(p16[(W + K16 - 1) & 1].astype(np.int32)).sum()) > 0
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -350,6 +377,10 @@ def main():
             },
             "e2e": {"value": e2e, "unit": "streams", "h2d_bytes_per_step": step_bytes + 4 * 4 * n,
                     "d2h_bytes_per_step": n * NF * CHANNELS * 4, "ms_per_step": 1e3 * t_e2e / K},
+            "e2e_i16": {"value": world * n * K16 / t_e2e16 * FRAME_S, "unit": "streams", "steps": K16,
+                        "d2h_bytes_per_step": n * NF * CHANNELS * 2, "ms_per_step": 1e3 * t_e2e16 / K16,
+                        "note": "extra: the same host-buffer loop through opn_batch_decode_i16 (Decoder::decode::<i16>: "
+                                "soft clip and sample conversion on the device); not the headline"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_imdct_post_w<3,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,

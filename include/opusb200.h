@@ -95,6 +95,13 @@ int opn_batch_reset(opn_batch *b);
 int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *offsets,
                            const uint32_t *lens, float *pcm, size_t pcm_stride_floats,
                            size_t frame_size, int32_t *result_per_stream, uint32_t flags);
+/* Decoder::decode::<i16> (decoder.rs:148-193) for every stream: pcm_soft_clip (per-stream memory, the reference's
+ * slice quirk kept, see opn_decode_i16) and Sample::from_f32 run on the device, so only 2 bytes per sample cross
+ * PCIe.  Host buffers only; pcm_stride_samples must be a multiple of 8 when it differs from frame_size*channels.
+ * OPN_FLAG_SUBMIT_ONLY / opn_batch_wait work as for opn_batch_decode_float. */
+int opn_batch_decode_i16(opn_batch *b, const uint8_t *arena, const uint32_t *offsets,
+                         const uint32_t *lens, int16_t *pcm, size_t pcm_stride_samples,
+                         size_t frame_size, int32_t *result_per_stream, uint32_t flags);
 int opn_batch_synchronize(opn_batch *b);
 /* Host-buffer calls made with OPN_FLAG_SUBMIT_ONLY return a ticket (0 or 1) instead of waiting: at most two
  * calls are in flight, so the PCM download of one overlaps the decode of the next.  The call's host buffers

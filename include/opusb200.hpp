@@ -127,6 +127,17 @@ public:
     {
         return check(opn_batch_decode_float(raw_, arena, offsets, lens, pcm, pcm_stride, frame_size, results, OPN_FLAG_SUBMIT_ONLY));
     }
+    // Decoder::decode::<i16> for every stream (soft clip + Sample::from_f32 on the device).
+    void decode(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm, size_t pcm_stride, size_t frame_size,
+                int32_t *results)
+    {
+        check(opn_batch_decode_i16(raw_, arena, offsets, lens, pcm, pcm_stride, frame_size, results, 0));
+    }
+    int submit(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm, size_t pcm_stride, size_t frame_size,
+               int32_t *results)
+    {
+        return check(opn_batch_decode_i16(raw_, arena, offsets, lens, pcm, pcm_stride, frame_size, results, OPN_FLAG_SUBMIT_ONLY));
+    }
     void wait(int ticket) { check(opn_batch_wait(raw_, ticket)); }
     void synchronize() { check(opn_batch_synchronize(raw_)); }
     std::vector<uint32_t> final_ranges()

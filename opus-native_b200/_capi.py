@@ -90,6 +90,7 @@ def lib():
     sig("opn_batch_enable_timing", C.c_int, vp, C.c_int)
     sig("opn_batch_stats", C.c_int, vp, vp, vp, C.c_int)
     sig("opn_batch_wait", C.c_int, vp, C.c_int)
+    sig("opn_batch_decode_i16", C.c_int, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, C.c_uint32)
     sig("opn_batch_join", C.c_int, vp)
     sig("opn_op_bitexact_trig", C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32)
     sig("opn_batch_cuda_stream", vp, vp)
@@ -264,6 +265,21 @@ class BatchDecoder:
         """Raw pointers (host or device according to `flags`); used with pinned / device tensors."""
         return _chk(lib().opn_batch_decode_float(self._h, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_floats,
                                                  frame_size, result_ptr, flags))
+
+    def decode_i16(self, arena, offsets, lens, pcm, frame_size, flags=0):
+        """`Decoder::decode::<i16>` for every stream: soft clip + Sample::from_f32 on the device; pcm is int16
+        [n_streams, >= frame_size*channels].  Returns (result_per_stream, ticket-or-0)."""
+        arena = np.ascontiguousarray(arena, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        lens = np.ascontiguousarray(lens, np.uint32)
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n_streams and pcm.flags.c_contiguous
+        res = np.zeros(self.n_streams, np.int32)
+        t = _chk(lib().opn_batch_decode_i16(self._h, _p(arena), _p(offsets), _p(lens), _p(pcm), pcm.shape[1], frame_size, _p(res), flags))
+        return res, t
+
+    def decode_i16_ptrs(self, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_samples, frame_size, result_ptr, flags):
+        return _chk(lib().opn_batch_decode_i16(self._h, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_samples, frame_size,
+                                               result_ptr, flags))
 
     def wait(self, ticket):
         """Completion of a host-buffer call submitted with FLAG_SUBMIT_ONLY (its return value is the ticket)."""

@@ -150,6 +150,9 @@ struct opn_batch {
         size_t items_cap = 0;
         float *d_dense = nullptr;
         size_t dense_cap = 0;          // floats per stream
+        int16_t *d_dense16 = nullptr;  // i16 rows (decode::<i16> calls), dense_cap samples per stream
+        size_t dense16_cap = 0;
+        int32_t *d_cliplen = nullptr, *h_cliplen = nullptr;  // [n] soft-clip slice length per stream
         cudaEvent_t done = nullptr;    // everything that uses this slot has finished (incl. the PCM download)
         bool pending = false;
     } stg[2];
@@ -165,7 +168,7 @@ struct opn_batch {
 
 namespace {
 
-int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes, size_t n_items, size_t dense_floats)
+int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes, size_t n_items, size_t dense_floats, bool want_i16)
 {
     if (!g.done) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     if (arena_bytes > g.arena_cap) {
@@ -184,6 +187,15 @@ int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes,
         if (g.d_dense) cudaFree(g.d_dense);
         g.dense_cap = dense_floats;
         CU(cudaMalloc(&g.d_dense, (size_t)b->n * g.dense_cap * sizeof(float)));
+    }
+    if (want_i16 && g.dense_cap > g.dense16_cap) {
+        if (g.d_dense16) cudaFree(g.d_dense16);
+        g.dense16_cap = g.dense_cap;
+        CU(cudaMalloc(&g.d_dense16, (size_t)b->n * g.dense16_cap * sizeof(int16_t)));
+    }
+    if (want_i16 && !g.d_cliplen) {
+        CU(cudaMalloc(&g.d_cliplen, (size_t)b->n * sizeof(int32_t)));
+        CU(cudaMallocHost(&g.h_cliplen, (size_t)b->n * sizeof(int32_t)));
     }
     return OPN_OK;
 }
@@ -486,6 +498,9 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(g.d_arena);
         cudaFree(g.d_items);
         cudaFree(g.d_dense);
+        cudaFree(g.d_dense16);
+        cudaFree(g.d_cliplen);
+        if (g.h_cliplen) cudaFreeHost(g.h_cliplen);
         if (g.h_items) cudaFreeHost(g.h_items);
         if (g.done) cudaEventDestroy(g.done);
     }
@@ -528,7 +543,8 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
 // download, so that parsing, kernels and the PCIe copy of different chunks overlap.  The download is
 // the long pole (31.5 MB per 4096 stereo 20 ms frames); everything else hides behind it.
 static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, float *pcm,
-                             size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags, int soft_clip)
+                             size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags, int soft_clip,
+                             int16_t *pcm16 = nullptr)
 {
     const uint32_t n = b->n;
     const int C = b->cfg.channels;
@@ -551,9 +567,9 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         CU(cudaEventSynchronize(g.done));
         g.pending = false;
     }
-    int rc = batch_alloc_staging(b, g, arena_end, items_ub, dense_stride);
+    int rc = batch_alloc_staging(b, g, arena_end, items_ub, dense_stride, pcm16 != nullptr);
     if (rc) return rc;
-    const bool want_pcm = pcm != nullptr && !(flags & OPN_FLAG_NO_PCM_COPY);
+    const bool want_pcm = (pcm != nullptr || pcm16 != nullptr) && !(flags & OPN_FLAG_NO_PCM_COPY);
     if (arena_end) CU(cudaMemcpyAsync(g.d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_up));
 
     const uint32_t n_chunks = std::min<uint32_t>(opn_batch::MAX_CHUNKS, std::max<uint32_t>(1u, n / 1024u));
@@ -654,7 +670,27 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             }
             kbase += items.size();
         }
-        if (want_pcm) {
+        if (want_pcm && pcm16) {
+            // decode::<i16>: soft clip + Sample::from_f32 on the device, then half the bytes go home.
+            // The epilogue kernel follows the chunk's kernels on the post-filter stream.
+            for (uint32_t i = s0; i < s1; i++) g.h_cliplen[i] = res[i];
+            CU(cudaMemcpyAsync(g.d_cliplen + s0, g.h_cliplen + s0, (size_t)(s1 - s0) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream_up));
+            CU(cudaEventRecord(b->ev_in, b->stream_up));
+            CU(cudaStreamWaitEvent(b->stream_k2, b->ev_in, 0));
+            CU(cudaEventRecord(b->ev_chunk[ch], b->stream));  // kernel 1 (and the gap memset) of this chunk
+            CU(cudaStreamWaitEvent(b->stream_k2, b->ev_chunk[ch], 0));
+            CU(launch_softclip_i16(g.d_dense, g.dense_cap, g.d_cliplen, C, (uint32_t)(frame_size * (size_t)C), s0, s1 - s0, b->d_softclip,
+                                   g.d_dense16, g.dense16_cap, b->stream_k2));
+            CU(cudaEventRecord(b->ev_chunk[ch], b->stream_k2));
+            CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
+            const size_t row_bytes = frame_size * (size_t)C * sizeof(int16_t);
+            if (pcm_stride == g.dense16_cap && pcm_stride * sizeof(int16_t) == row_bytes)
+                CU(cudaMemcpyAsync(pcm16 + (size_t)s0 * pcm_stride, g.d_dense16 + (size_t)s0 * g.dense16_cap, (size_t)(s1 - s0) * row_bytes,
+                                   cudaMemcpyDeviceToHost, b->stream_dn));
+            else
+                CU(cudaMemcpy2DAsync(pcm16 + (size_t)s0 * pcm_stride, pcm_stride * sizeof(int16_t), g.d_dense16 + (size_t)s0 * g.dense16_cap,
+                                     g.dense16_cap * sizeof(int16_t), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
+        } else if (want_pcm) {
             // the chunk's last kernel 2 runs on its own stream: order the rest of this chunk after it
             if (b->last_set >= 0 && b->k2_recorded[b->last_set]) {
                 if (soft_clip) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[b->last_set], 0));
@@ -679,7 +715,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                                      g.dense_cap * sizeof(float), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         }
     }
-    if (!soft_clip) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
+    if (!soft_clip && !pcm16) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
     // completion of this call = the batch stream, the post-filter stream and the download stream have drained
     CU(cudaEventRecord(b->ev_in, b->stream));
     CU(cudaStreamWaitEvent(b->stream_dn, b->ev_in, 0));
@@ -718,6 +754,19 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
         return OPN_ERR_BAD_ARG;
     return run_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, lm, 1, 1280u, dense, pcm_stride_floats, result_per_stream,
                       (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1);
+}
+
+int opn_batch_decode_i16(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm,
+                         size_t pcm_stride_samples, size_t frame_size, int32_t *result_per_stream, uint32_t flags)
+{
+    if (!b || !arena || !offsets || !lens || !pcm) return OPN_ERR_BAD_ARG;
+    if (frame_size == 0 || frame_size % 120 != 0) return OPN_ERR_BAD_ARG;  // decoder.rs:316-320
+    if (flags & (OPN_FLAG_DEVICE_PTRS | OPN_FLAG_NO_PCM_COPY)) return OPN_ERR_BAD_ARG;
+    if (pcm_stride_samples < frame_size * (size_t)b->cfg.channels) return OPN_ERR_BUFFER_TOO_SMALL;
+    CU(cudaSetDevice(b->device));
+    const int rc = batch_decode_host(b, arena, offsets, lens, nullptr, pcm_stride_samples, frame_size, result_per_stream, flags, 0, pcm);
+    if (rc < 0) return rc;
+    return (flags & OPN_FLAG_SUBMIT_ONLY) ? rc : OPN_OK;
 }
 
 int opn_batch_synchronize(opn_batch *b)

@@ -284,6 +284,16 @@ cudaError_t launch_op_bitexact_trig(const int16_t *x, int16_t *out_cos, uint32_t
     return cudaGetLastError();
 }
 
+cudaError_t launch_softclip_i16(const float *dense, size_t dense_stride, const int32_t *clip_len, int channels, uint32_t row_floats,
+                                uint32_t first_row, uint32_t n_rows, float *mem, int16_t *out, size_t out_stride, cudaStream_t st)
+{
+    if (n_rows == 0) return cudaSuccess;
+    if (row_floats % 8u || (dense_stride & 3) || (out_stride & 7)) return cudaErrorInvalidValue;
+    k_softclip_i16<<<n_rows, 32, (size_t)row_floats * sizeof(float), st>>>(dense, dense_stride, clip_len, channels, row_floats, first_row, mem,
+                                                                            out, out_stride);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_op_soft_clip(float *pcm, size_t row_stride, size_t row_len, int channels, uint32_t n_rows, float *mem,
                                 cudaStream_t st)
 {

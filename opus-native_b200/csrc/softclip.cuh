@@ -11,22 +11,10 @@ namespace opn {
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-__global__ void k_op_soft_clip(float *__restrict__ pcm_all, size_t row_stride, size_t row_len, int channels, uint32_t n_rows,
-                               float *__restrict__ mem_all)
+// One channel of pcm_soft_clip (lib.rs:540-630) on an interleaved buffer of `ch` channels; `a` is the
+// channel's declip memory (in/out).  pcm may point to global or shared memory.
+__device__ __forceinline__ void soft_clip_channel(float *pcm, int frame_size, int ch, int c, float &a)
 {
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_rows * (uint32_t)channels) return;
-    const uint32_t row = gid / (uint32_t)channels;
-    const int c = (int)(gid - row * (uint32_t)channels);
-    float *pcm = pcm_all + (size_t)row * row_stride;
-    const int ch = channels;
-    const int frame_size = (int)(row_len / (size_t)channels);
-    if (row_len == 0) return;
-    // saturate to +-2 (lib.rs:538); samples past frame_size*channels are clamped by channel 0's thread
-    for (int i = 0; i < frame_size; i++) pcm[c + i * ch] = clampf(pcm[c + i * ch], -2.0f, 2.0f);
-    if (c == 0)
-        for (size_t i = (size_t)frame_size * ch; i < row_len; i++) pcm[i] = clampf(pcm[i], -2.0f, 2.0f);
-    float a = mem_all[(size_t)row * channels + c];
     for (int i = 0; i < frame_size; i++) {
         const int off = c + i * ch;
         if (pcm[off] * a >= 0.0f) break;
@@ -75,7 +63,70 @@ __global__ void k_op_soft_clip(float *__restrict__ pcm_all, size_t row_stride, s
         curr = end;
         if (curr == frame_size) break;
     }
+}
+
+__global__ void k_op_soft_clip(float *__restrict__ pcm_all, size_t row_stride, size_t row_len, int channels, uint32_t n_rows,
+                               float *__restrict__ mem_all)
+{
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_rows * (uint32_t)channels) return;
+    const uint32_t row = gid / (uint32_t)channels;
+    const int c = (int)(gid - row * (uint32_t)channels);
+    float *pcm = pcm_all + (size_t)row * row_stride;
+    const int ch = channels;
+    const int frame_size = (int)(row_len / (size_t)channels);
+    if (row_len == 0) return;
+    // saturate to +-2 (lib.rs:538); samples past frame_size*channels are clamped by channel 0's thread
+    for (int i = 0; i < frame_size; i++) pcm[c + i * ch] = clampf(pcm[c + i * ch], -2.0f, 2.0f);
+    if (c == 0)
+        for (size_t i = (size_t)frame_size * ch; i < row_len; i++) pcm[i] = clampf(pcm[i], -2.0f, 2.0f);
+    float a = mem_all[(size_t)row * channels + c];
+    soft_clip_channel(pcm, frame_size, ch, c, a);
     mem_all[(size_t)row * channels + c] = a;
+}
+
+// Decoder::decode::<i16> epilogue for a batch (decoder.rs:177-189): one warp per stream stages the stream's
+// interleaved float row in shared memory, lanes 0..C-1 run pcm_soft_clip on their channel (a serial scan),
+// then the warp converts the row with Sample::from_f32 for i16 (lib.rs:76-82) and stores 8 samples per lane.
+// clip_len[row] is the slice length the reference hands to pcm_soft_clip (its sample_count: the per-channel
+// count, decoder.rs:415-419 omits the "x channels"); <= 0 skips the clip (error rows are all zeros).
+__global__ void __launch_bounds__(32)
+k_softclip_i16(const float *__restrict__ dense, size_t dense_stride, const int32_t *__restrict__ clip_len, int channels, uint32_t row_floats,
+               uint32_t first_row, float *__restrict__ mem_all, int16_t *__restrict__ out, size_t out_stride)
+{
+    extern __shared__ __align__(16) float s_row[];
+    const uint32_t row = first_row + blockIdx.x, lane = threadIdx.x;
+    const float4 *src = reinterpret_cast<const float4 *>(dense + (size_t)row * dense_stride);
+    for (uint32_t i = lane; i < row_floats / 4u; i += 32u) reinterpret_cast<float4 *>(s_row)[i] = src[i];
+    __syncwarp();
+    const int rl = clip_len[row];
+    if (rl > 0) {
+        const int frame_size = rl / channels;
+        for (int i = (int)lane; i < rl; i += 32) s_row[i] = clampf(s_row[i], -2.0f, 2.0f);  // lib.rs:538
+        __syncwarp();
+        if ((int)lane < channels && frame_size > 0) {
+            float a = mem_all[(size_t)row * 2 + lane];
+            soft_clip_channel(s_row, frame_size, channels, (int)lane, a);
+            mem_all[(size_t)row * 2 + lane] = a;
+        }
+        __syncwarp();
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)row * out_stride);
+    for (uint32_t i = lane; i < row_floats / 8u; i += 32u) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t h[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                float f = s_row[8u * i + 2u * k + e] * 32768.0f;  // Sample::from_f32, lib.rs:76-82
+                f = f < -32768.0f ? -32768.0f : (f > 32767.0f ? 32767.0f : f);
+                h[e] = (uint32_t)(uint16_t)((f != f) ? (int16_t)0 : (int16_t)f);
+            }
+            w[k] = h[0] | (h[1] << 16);
+        }
+        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 }  // namespace opn

@@ -685,6 +685,39 @@ def test_decoder_gain_and_i16_output():
         assert np.abs(out16.astype(np.int32) - w16.astype(np.int32)).max() <= 1
 
 
+def test_batch_decode_i16_matches_single_stream_decode_and_oracle():
+    """opn_batch_decode_i16 = Decoder::decode::<i16> for every stream: device-side pcm_soft_clip (per-stream
+    memory carried from frame to frame) + Sample::from_f32.  Checked against the single-stream decode::<i16>
+    (host conversion) sample for sample, and against the oracle's float PCM -> orc_pcm_soft_clip -> from_f32
+    within one LSB; a +12 dB decoder gain makes the clip non-trivial (peaks beyond full scale)."""
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 1100, 5, 960  # two chunks on the host path
+    gain_q8 = 3072  # +12 dB
+    g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
+    packets = opn.synth_fill(900, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
+    cfg = opn.DecoderConfiguration(48000, channels, gain_q8)
+    batch = opn.BatchDecoder(ns, cfg)
+    singles = {s: opn.Decoder(cfg) for s in (0, 7, 1099)}
+    oracle = {s: (O.SynthStream(lm, channels), np.zeros(2, np.float32)) for s in singles}
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+    clipped = 0
+    for f in range(nfr):
+        out = np.zeros((ns, nf * channels), np.int16)
+        res, _ = batch.decode_i16(packets[f].reshape(-1), offsets, lens, out, nf)
+        assert np.all(res == nf)
+        for s, dec in singles.items():
+            one = np.zeros(nf * channels, np.int16)
+            assert dec.decode(packets[f, s], one, nf) == nf
+            assert np.array_equal(one, out[s]), (f, s)
+            st, mem = oracle[s]
+            w = st.decode(packets[f, s, 1:])[3] * g
+            clipped += int((np.abs(w) > 1.0).sum())
+            O.lib().orc_pcm_soft_clip(O.ptr(w), nf, channels, O.ptr(mem), 2)
+            w16 = np.clip(w * np.float32(32768.0), -32768.0, 32767.0).astype(np.int16)
+            assert np.abs(out[s].astype(np.int32) - w16.astype(np.int32)).max() <= 1, (f, s)
+    assert clipped > 0, "the test signal never exceeded full scale"
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE config 2)
 def test_config2_full_size_properties():
     """4096 CELT FB 20 ms stereo streams @64 kbps, 3 chained frames: checksum of final ranges and the
