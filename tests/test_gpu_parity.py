@@ -595,6 +595,50 @@ def test_batch_device_resident_steps_enqueued_back_to_back(postfilter):
     assert np.array_equal(dec.final_ranges(), want_rng[nfr - 1])
 
 
+def test_batch_reset_in_the_middle_of_a_pipelined_run():
+    """Decoder::reset (decoder.rs:74, 286-303) on a batch with several steps in flight: after the reset the
+    streams decode exactly like a new batch (overlap carry, PCM ring, post-filter parameters, soft-clip memory,
+    buffer-set rotation all start over), and API misuse is rejected with BadArguments rather than run."""
+    torch = pytest.importorskip("torch")
+    lm, channels, pkt_bytes, ns, nf = 3, 2, 160, 80, 960
+    packets = opn.synth_fill(3100, ns, 0, 9, lm, channels, pkt_bytes, transient_permille=100)
+    dev = torch.device("cuda:0")
+    d_arena = torch.from_numpy(packets.reshape(-1).copy()).to(dev)
+    d_off = torch.arange(ns, dtype=torch.int32, device=dev) * pkt_bytes
+    d_len = torch.full((ns,), pkt_bytes, dtype=torch.int32, device=dev)
+    d_res = torch.zeros(ns, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY
+
+    def run(dec, frames):
+        out = torch.zeros((len(frames), ns, nf * channels), dtype=torch.float32, device=dev)
+        for k, f in enumerate(frames):
+            dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), out[k].data_ptr(),
+                                  nf * channels, nf, d_res.data_ptr(), flags)
+        dec.synchronize()
+        return out.cpu().numpy()
+
+    dec = opn.BatchDecoder(ns)
+    run(dec, [0, 1, 2, 3, 4])          # leaves state behind; five steps were in flight
+    dec.reset()
+    again = run(dec, [5, 6, 7, 8])
+    fresh = run(opn.BatchDecoder(ns), [5, 6, 7, 8])
+    assert np.array_equal(again, fresh)
+    want, _ = _oracle_chain(packets[5:9], lm, channels)
+    assert np.array_equal(again, want)
+    # misuse
+    with pytest.raises(opn.OpusError) as e:
+        dec.decode_float_ptrs(d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), None, 0, 100, d_res.data_ptr(), flags)
+    assert e.value.kind == "BadArguments"                      # frame size not a multiple of 2.5 ms
+    with pytest.raises(opn.OpusError) as e:
+        dec.wait(5)
+    assert e.value.kind == "BadArguments"
+    out16 = np.zeros((ns, nf * channels), np.int16)
+    with pytest.raises(opn.OpusError) as e:
+        dec.decode_i16_ptrs(0, 0, 0, out16.ctypes.data, nf * channels, nf, 0, 0)
+    assert e.value.kind == "BadArguments"
+
+
 # ------------------------------------------------------------------ Decoder API (decoder.rs:27-232)
 def test_baseline_config0_one_mono_stream_1000_chained_frames():
     """BASELINE.json configs[0]: one synthetic 20 ms 48 kHz mono stream, 1000 chained frames, decoded through
