@@ -127,12 +127,10 @@ struct opn_batch {
     bool k2_recorded[NSETS] = {};
     cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
     cudaEvent_t ev_ex[NSETS] = {};        // PVQ expansion of set p finished (coefficients ready)
-    cudaEvent_t ev_use[NSETS] = {};       // last consumer of set p finished
     cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` / `stream_up` are complete
     static constexpr int MAX_CHUNKS = 8;
     cudaStream_t stream_up = nullptr, stream_dn = nullptr;  // host path: item/packet upload, PCM download
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};                  // PVQ/IMDCT stage of a chunk finished
-    bool use_recorded[NSETS] = {};
     int set = 0, last_set = -1;
     // per-stream state (device, SoA)
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef[NSETS] = {};
@@ -267,7 +265,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
             CU(cudaEventRecord(b->ev_in, b->stream_up));
             CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
         }
-        if (b->use_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_use[p], 0));  // set p is free again
+        if (b->k2_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_k2[p], 0));  // set p is free again
         // three stages in flight at once: range decode of step n+2 (latency-bound, a few hundred warps), PVQ
         // expansion of step n+1 (integer issue-bound) and IMDCT/post-filter of step n (FP32 / memory)
         CU(launch_synth_rangedec(s, srd));
@@ -307,8 +305,6 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
         }
         CU(cudaEventRecord(b->ev_k2[p], b->stream));
         b->k2_recorded[p] = true;
-        CU(cudaEventRecord(b->ev_use[p], b->stream));
-        b->use_recorded[p] = true;
         b->last_set = p;
         return OPN_OK;
     }
@@ -324,13 +320,10 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
         CU(launch_comb_post(m, b->stream_k2));
         b->launches[2]++;
         CU(cudaEventRecord(b->ev_k2[p], b->stream_k2));
-        CU(cudaEventRecord(b->ev_use[p], b->stream_k2));
     } else {
         CU(cudaEventRecord(b->ev_k2[p], b->stream));
-        CU(cudaEventRecord(b->ev_use[p], b->stream));
     }
-    b->k2_recorded[p] = true;
-    b->use_recorded[p] = true;
+    b->k2_recorded[p] = true;  // also "set p is free again" for the entropy stage
     b->last_set = p;
     return OPN_OK;
 }
@@ -408,7 +401,6 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     }
     for (int q = 0; q < opn_batch::NSETS && e == cudaSuccess; q++) {
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_use[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k1[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k2[q], cudaEventDisableTiming);
@@ -456,7 +448,6 @@ void opn_batch_destroy(opn_batch *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int q = 0; q < opn_batch::NSETS; q++) {
         if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
-        if (b->ev_use[q]) cudaEventDestroy(b->ev_use[q]);
         if (b->ev_ex[q]) cudaEventDestroy(b->ev_ex[q]);
         if (b->ev_k1[q]) cudaEventDestroy(b->ev_k1[q]);
         if (b->ev_k2[q]) cudaEventDestroy(b->ev_k2[q]);
@@ -524,7 +515,6 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     for (int q = 0; q < opn_batch::NSETS; q++) {
         CU(cudaMemsetAsync(b->d_side[q], 0, n * sizeof(opn_synth_side), b->stream));
         CU(cudaMemsetAsync(b->d_status[q], 0, n * sizeof(int32_t), b->stream));
-        b->use_recorded[q] = false;
         b->k2_recorded[q] = false;
     }
     b->set = 0;
