@@ -224,9 +224,10 @@ def main():
     d_res = torch.zeros(n, dtype=torch.int32, device=dev)
     flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY  # packets are resident: entropy stage may run a step ahead
 
+    p_arena, p_off, p_len, p_res = d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr()
+
     def step_resident(f):
-        dec.decode_float_ptrs(d_arena.data_ptr() + f * step_bytes, d_off.data_ptr(), d_len.data_ptr(), None, 0, NF,
-                              d_res.data_ptr(), flags)
+        dec.decode_float_ptrs(p_arena + f * step_bytes, p_off, p_len, None, 0, NF, p_res, flags)
 
     def timed_resident(k0, k1):
         barrier()
