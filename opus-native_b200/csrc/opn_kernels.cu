@@ -100,15 +100,20 @@ cudaError_t upload_tables(int device)
                 const SynthEntry &E = h.synth_entries[lm][C - 1][e];
                 for (int j = 0; j < (int)E.n; j++) eo[E.base + j] = (uint8_t)e;
             }
-            // k_synth_expand: parts sorted by size (descending), 32 per slot, so that the lanes of a slot walk
-            // similar numbers of dimensions in lockstep
+            // k_synth_expand: parts sorted by the number of dimensions cwrsi has to walk (descending), 32 per slot,
+            // so that the lanes of a slot run similar countdowns in lockstep.  Sign-only bands (n == 1) and
+            // single-pulse parts (k == 1, closed form) walk nothing.
             {
+                auto walk = [&](int e) {
+                    const SynthEntry &E = h.synth_entries[lm][C - 1][e];
+                    return (E.n == 1 || E.k == 1) ? 0 : (int)E.n;
+                };
                 int order[SYNTH_MAX_ENTRIES];
                 for (int e = 0; e < ne; e++) order[e] = e;
                 for (int a = 1; a < ne; a++) {  // insertion sort, stable
                     const int v = order[a];
                     int b2 = a - 1;
-                    while (b2 >= 0 && h.synth_entries[lm][C - 1][order[b2]].n < h.synth_entries[lm][C - 1][v].n) {
+                    while (b2 >= 0 && walk(order[b2]) < walk(v)) {
                         order[b2 + 1] = order[b2];
                         b2--;
                     }
@@ -122,10 +127,7 @@ cudaError_t upload_tables(int device)
                     for (int l = 0; l < 32; l++) {
                         const int r = sl * 32 + l;
                         h.synth_slot_entries[lm][C - 1][sl][l] = r < ne ? (uint8_t)order[r] : 0xFF;
-                        if (r < ne) {
-                            const uint8_t n = h.synth_entries[lm][C - 1][order[r]].n;
-                            if (n > h.synth_slot_maxn[lm][C - 1][sl]) h.synth_slot_maxn[lm][C - 1][sl] = n;
-                        }
+                        if (r < ne && walk(order[r]) > h.synth_slot_maxn[lm][C - 1][sl]) h.synth_slot_maxn[lm][C - 1][sl] = (uint8_t)walk(order[r]);
                     }
                 }
             }

@@ -303,6 +303,13 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
             if (has && n == 1u) {  // sign-only band
                 *y = i ? (int16_t)-1 : (int16_t)1;
                 yy = 1;
+            } else if (has && k == 1u) {
+                // one pulse: cwrsi reduces to a closed form, y[i] = +1 for i < n, y[2n-1-i] = -1 otherwise
+                // (checked against the oracle for every band size in tests/test_oracle_kat.py::test_cwrsi_single_pulse_closed_form)
+                if (i < n) y[i] = (int16_t)1;
+                else y[2u * n - 1u - i] = (int16_t)-1;
+                yy = 1;
+                n = 0u;  // done: takes no part in the countdown below
             }
             uint32_t rk = row[min(k, 14u)], rk1 = row[min(k + 1u, 14u)];  // row offsets of U(k,.) and U(k+1,.): only read when k < n
             const int maxn = g_tab.synth_slot_maxn[lm][C - 1][slot];

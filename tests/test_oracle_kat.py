@@ -325,3 +325,19 @@ def test_pcm_soft_clip():
         L.orc_pcm_soft_clip(O.ptr(x), 1024, ch, O.ptr(s), 8)
         n = (1024 // ch) * ch
         assert x[:n].max() <= 1.0 and x[:n].min() >= -1.0
+
+
+def test_cwrsi_single_pulse_closed_form():
+    """k_synth_expand decodes single-pulse parts without walking the dimensions: for K = 1 cwrsi
+    (pvc.rs:182-284) gives y[i] = +1 for i < n and y[2n-1-i] = -1 otherwise.  Checked for every band size
+    the reference's test_pvc uses (pvc.rs:463-469) and every index."""
+    for n in [2, 3, 4, 6, 8, 9, 11, 12, 16, 18, 22, 24, 32, 36, 44, 48, 64, 72, 88, 96, 144, 176]:
+        for i in range(2 * n):
+            y = np.zeros(n, np.int32)
+            yy = L.orc_cwrsi(O.ptr(y), n, 1, i)
+            w = np.zeros(n, np.int32)
+            if i < n:
+                w[i] = 1
+            else:
+                w[2 * n - 1 - i] = -1
+            assert np.array_equal(y, w) and yy == 1.0, (n, i)
