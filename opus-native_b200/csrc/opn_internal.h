@@ -9,6 +9,10 @@
 namespace opn {
 
 constexpr int SYM_WARPS_PER_CTA = 4;
+#ifndef OPN_EXPAND_WARPS
+#define OPN_EXPAND_WARPS 6
+#endif
+constexpr int EXPAND_WARPS_PER_CTA = OPN_EXPAND_WARPS;  // k_synth_expand: 43 KB per CTA, 5 CTAs per SM, 4096 streams = one wave
 constexpr int IM_TPC = 128;         // threads per row of the out-of-place comb operator kernel
 constexpr int HIST_CAP = 1024;      // comb history window in shared memory (T + 2 <= 1024)
 // per-channel PCM ring: 4 x 960 = 8 x 480 = 16 x 240 = 32 x 120.  Four long frames, so that kernel 1 may write

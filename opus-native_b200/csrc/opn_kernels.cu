@@ -60,6 +60,18 @@ cudaError_t upload_tables(int device)
     for (int i = 0; i < 60; i++) h.bitrev[3][i] = OPN_BITREV_60[i];
     for (int i = 0; i < 1272; i++) h.pvq_u_data[i] = OPN_PVQ_U_DATA[i];
     for (int i = 0; i < 15; i++) h.pvq_u_row[i] = OPN_PVQ_U_ROW[i];
+    for (int k = 0; k < 15; k++) {  // row k holds columns k .. last(k); the rows are stored back to back
+        const int first = OPN_PVQ_U_ROW[k] + k, end = k < 14 ? OPN_PVQ_U_ROW[k + 1] + k + 1 : 1272;
+        const int next_end = k < 13 ? OPN_PVQ_U_ROW[k + 2] + k + 2 : 1272;  // end of row k+1
+        uint32_t acc = 0;
+        for (int i = first; i < end; i++) {
+            const int m = i - OPN_PVQ_U_ROW[k];
+            h.pvq_cw_data[i].x = acc;
+            acc += OPN_PVQ_U_DATA[i];
+            const int up = k < 14 ? OPN_PVQ_U_ROW[k + 1] + m : 1272;
+            h.pvq_cw_data[i].y = (m >= k + 1 && up < next_end) ? OPN_PVQ_U_DATA[up] - OPN_PVQ_U_DATA[i] : 0u;
+        }
+    }
     for (int i = 0; i < 22; i++) h.e_bands[i] = OPN_E_BANDS[i];
     for (int l = 0; l < 4; l++)
         for (int b = 0; b < 21; b++)
@@ -78,6 +90,12 @@ cudaError_t upload_tables(int device)
                         e.k = (uint8_t)k;
                         e.ft_minus1 = 0; e.magic = 0; e.ft1 = 0; e.ftb = 0; e.sh = 0;
                         if (n == 1) continue;
+                        if (n > 2 && k < n) {
+                            // k_synth_expand bisects on 32-bit sums: the whole row sum plus U(k+1,n) must not wrap
+                            uint64_t rowsum = 0;
+                            for (uint32_t j = k; j <= n; j++) rowsum += OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[k] + j];
+                            if (k >= 14 || rowsum + OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[k + 1] + n] >= (1ull << 32)) return cudaErrorInvalidValue;
+                        }
                         auto U = [](uint32_t a, uint32_t bb) { return OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[a < bb ? a : bb] + (a < bb ? bb : a)]; };
                         const uint32_t ft = U(n, k) + U(n, k + 1);   // pvq_v, pvc.rs:289-291
                         e.ft_minus1 = ft - 1;
@@ -95,7 +113,7 @@ cudaError_t upload_tables(int device)
             h.synth_n_entries[lm][C - 1] = (uint8_t)ne;
             // bin -> part map for the coefficient write of k_synth_expand
             uint8_t *eo = h.synth_entry_of[lm][C - 1];
-            for (int i = 0; i < 2 * 960; i++) eo[i] = 0xFF;
+            for (int i = 0; i < 2 * 960; i++) eo[i] = SYNTH_MAX_ENTRIES;
             for (int e = 0; e < ne; e++) {
                 const SynthEntry &E = h.synth_entries[lm][C - 1][e];
                 for (int j = 0; j < (int)E.n; j++) eo[E.base + j] = (uint8_t)e;
@@ -191,8 +209,8 @@ cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
     if (!a.idx) return cudaErrorInvalidValue;
-    const uint32_t grid = (a.n_items + SYM_WARPS_PER_CTA - 1) / SYM_WARPS_PER_CTA;
-    k_synth_expand<<<grid, SYM_WARPS_PER_CTA * 32, synth_expand_smem(), st>>>(a);
+    const uint32_t grid = (a.n_items + EXPAND_WARPS_PER_CTA - 1) / EXPAND_WARPS_PER_CTA;
+    k_synth_expand<<<grid, EXPAND_WARPS_PER_CTA * 32, synth_expand_smem(), st>>>(a);
     return cudaGetLastError();
 }
 

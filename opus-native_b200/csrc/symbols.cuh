@@ -127,14 +127,15 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 //      longest-first schedule so every lane walks about the same number of dimensions, then the warp
 //      writes pulses x gain as coalesced float4 coefficient rows.
 //
-// Shared memory of k_synth_expand (per CTA of SYM_WARPS_PER_CTA warps):
-//   PVQ U(n,k) table 5088 B + row offsets 32 B | entry table 72 x 16 B | per warp: codeword
-//   indices 72 x 4 B, gains 72 x 4 B, 16-bit pulses 2 x 960 x 2 B.
+// Shared memory of k_synth_expand (per CTA of EXPAND_WARPS_PER_CTA warps):
+//   PVQ U(n,k) table 5088 B + bisection table 10176 B + row offsets 32 B | entry table 72 x 16 B | per warp: codeword
+//   indices 72 x 4 B, gains 76 x 4 B (slot 72 = 0 for bins without a part), 16-bit pulses 2 x 960 x 2 B.
 constexpr int SYM_Y16 = 2 * 960;
-constexpr size_t SYM_EXPAND_WARP_BYTES = SYNTH_MAX_ENTRIES * 8 + SYM_Y16 * 2;
+constexpr int SYNTH_GAIN_SLOTS = SYNTH_MAX_ENTRIES + 4;
+constexpr size_t SYM_EXPAND_WARP_BYTES = SYNTH_MAX_ENTRIES * 4 + SYNTH_GAIN_SLOTS * 4 + SYM_Y16 * 2;
 __host__ __device__ constexpr size_t synth_expand_smem()
 {
-    return PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)SYM_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
+    return 3 * PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)EXPAND_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
 }
 
 __global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
@@ -239,12 +240,13 @@ __global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
     sd->n_pulses = n_pulses;
 }
 
-__global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolArgs A)
+__global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(SymbolArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
-    uint16_t *s_row = reinterpret_cast<uint16_t *>(s_pvq + PVQ_TABLE_WORDS);
+    uint2 *s_cw = reinterpret_cast<uint2 *>(s_pvq + PVQ_TABLE_WORDS);
+    uint16_t *s_row = reinterpret_cast<uint16_t *>(s_cw + PVQ_TABLE_WORDS);
     SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(s_row + 16);
     uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) + (size_t)warp * SYM_EXPAND_WARP_BYTES;
     int16_t *s_y = reinterpret_cast<int16_t *>(wbase);  // 16-byte aligned: zeroed as uint4, read back as 4 x int16
@@ -253,14 +255,17 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
 
     const int lm = A.lm, C = A.channels, nf = 120 << lm;
     const int ne = g_tab.synth_n_entries[lm][C - 1];
-    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) s_pvq[i] = g_tab.pvq_u_data[i];
+    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) {
+        s_pvq[i] = g_tab.pvq_u_data[i];
+        s_cw[i] = g_tab.pvq_cw_data[i];
+    }
     if (threadIdx.x < 15) s_row[threadIdx.x] = g_tab.pvq_u_row[threadIdx.x];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
         uint4 *dst = reinterpret_cast<uint4 *>(s_ent);
         for (int i = threadIdx.x; i < ne; i += blockDim.x) dst[i] = src[i];
     }
-    const uint32_t item = blockIdx.x * SYM_WARPS_PER_CTA + warp;
+    const uint32_t item = blockIdx.x * EXPAND_WARPS_PER_CTA + warp;
     const bool in_range = item < A.n_items;
     const uint32_t stream = in_range ? (A.stream_idx ? A.stream_idx[item] : item) : 0u;
     const int32_t status = in_range ? A.status[stream] : -1;
@@ -290,6 +295,7 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
     __syncwarp();
     {
         const uint32_t *U = s_pvq;
+        const uint2 *CW = s_cw;
         const uint16_t *row = s_row;
         const int nslots = g_tab.synth_n_slots[lm][C - 1];
 #pragma unroll 1
@@ -311,12 +317,20 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
                 yy = 1;
                 n = 0u;  // done: takes no part in the countdown below
             }
+            // A lane walks its part in EVENTS, not dimensions.  While k < n (pvc.rs:232-258) a dimension is
+            // empty iff U(k,n) <= i < U(k+1,n), and stepping over it subtracts U(k,n); after t empty dimensions
+            // i has lost A(t) = C(k,n) - C(k,n-t) (C = running row sum of U), so "dimension n-t is empty given
+            // all before it were" reads A(t) + U(k,n-t) <= i < A(t) + U(k+1,n-t), or as one unsigned comparison
+            // i - C(k,n) + C(k,n-t-1) < U(k+1,n-t) - U(k,n-t) (no sum wraps for the parts of the schedule: checked
+            // when the tables are built).  That predicate is monotone in t
+            // (once a dimension is occupied the sequential loop stops there), so the length of the run of empty
+            // dimensions is found by bisection over t in [0, T], T = n - max(k,2) being where the regime ends
+            // (k >= n, or the closed-form tail n == 2).  One event = one run + the occupied dimension after it:
+            // a part with k pulses takes at most k+1 events instead of n-2 lockstep steps.
             uint32_t rk = row[min(k, 14u)], rk1 = row[min(k + 1u, 14u)];  // row offsets of U(k,.) and U(k+1,.): only read when k < n
-            const int maxn = g_tab.synth_slot_maxn[lm][C - 1][slot];
 #pragma unroll 1
-            for (uint32_t c = (uint32_t)maxn; c > 2u; c--) {
-                if (n != c) continue;  // not started yet (n < c), no part (n == 0) or sign-only (n == 1)
-                if (k >= n) {  // lots of pulses, pvc.rs:196-231
+            while (n > 2u) {
+                if (k >= n) {  // lots of pulses, pvc.rs:196-231: one dimension per event
                     const uint32_t rn = row[n];
                     uint32_t p = U[rn + k + 1u];
                     const int32_t sg = i >= p ? -1 : 0;
@@ -342,15 +356,30 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
                     yy += val * val;
                     rk = row[min(k, 14u)];
                     rk1 = row[min(k + 1u, 14u)];
+                    y++;
+                    n -= 1u;
                 } else {  // lots of dimensions, pvc.rs:232-258
-                    uint32_t p = U[rk + n];
-                    const uint32_t q = U[rk1 + n];
-                    if (p <= i && i < q) {
-                        i -= p;
-                    } else {
+                    const uint32_t T = n - max(k, 2u);
+                    const uint2 *pw = CW + rk + n;              // pw[-t] = (C(k,n-t-1), V(n-t-1,k))
+                    const uint32_t ic = i - (pw[0].x + U[rk + n]);  // i - C(k,n)
+                    uint32_t lo = 0u, hi = T;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        const uint2 cw = pw[-(int32_t)mid];
+                        // i - A(mid) - U(k,n-mid) as one unsigned number: below V(n-mid-1,k) iff dimension n-mid is empty
+                        const bool empty = ic + cw.x < cw.y;
+                        lo = empty ? mid + 1u : lo;
+                        hi = empty ? hi : mid;
+                    }
+                    if (lo) i = ic + pw[1 - (int32_t)lo].x;  // i - A(lo)
+                    y += lo;
+                    n -= lo;
+                    if (lo < T) {  // dimension n holds pulses
+                        const uint32_t q = U[rk1 + n];
                         const int32_t sg = i >= q ? -1 : 0;
                         i -= (uint32_t)((int32_t)q & sg);
                         const uint32_t k0 = k;
+                        uint32_t p;
                         do {
                             k -= 1u;
                             p = U[row[k] + n];
@@ -361,10 +390,10 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
                         yy += val * val;
                         rk = row[k];
                         rk1 = row[k + 1u];
+                        y++;
+                        n -= 1u;
                     }
                 }
-                y++;
-                n -= 1u;
             }
             if (n == 2u) {
                 // n == 2 (pvc.rs:262-275)
@@ -385,12 +414,14 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
             }
             if (has) s_gain[e] = 0.03125f / sqrtf((float)yy);
         }
+        if (lane == 0) s_gain[SYNTH_MAX_ENTRIES] = 0.0f;
     }
     __syncwarp();
-    // pulses x gain -> coefficient rows, 4 bins per lane and step (entry_of: bin -> part, 0xFF above the last band)
+    // pulses x gain -> coefficient rows, 4 bins per lane and step (entry_of: bin -> part)
     {
         const uint32_t *ent4 = reinterpret_cast<const uint32_t *>(g_tab.synth_entry_of[lm][C - 1]);
         const uint2 *y4 = reinterpret_cast<const uint2 *>(s_y);
+#pragma unroll 3
         for (int i = lane; i < nvec; i += 32) {
             const uint32_t ids = __ldg(ent4 + i);
             const uint2 yr = y4[i];
@@ -401,10 +432,10 @@ __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32) k_synth_expand(SymbolA
             yv.y = (int32_t)(int16_t)(yr.x >> 16);
             yv.z = (int32_t)(int16_t)(yr.y & 0xFFFFu);
             yv.w = (int32_t)(int16_t)(yr.y >> 16);
-            cv.x = e0 == 0xFFu ? 0.0f : (float)yv.x * s_gain[e0];
-            cv.y = e1 == 0xFFu ? 0.0f : (float)yv.y * s_gain[e1];
-            cv.z = e2 == 0xFFu ? 0.0f : (float)yv.z * s_gain[e2];
-            cv.w = e3 == 0xFFu ? 0.0f : (float)yv.w * s_gain[e3];
+            cv.x = (float)yv.x * s_gain[e0];  // bins without a part: pulse 0 x gain slot 72 (= 0)
+            cv.y = (float)yv.y * s_gain[e1];
+            cv.z = (float)yv.z * s_gain[e2];
+            cv.w = (float)yv.w * s_gain[e3];
             if (coef4) coef4[i] = cv;
             if (yo4) yo4[i] = yv;
         }
