@@ -10,9 +10,9 @@ namespace opn {
 
 constexpr int SYM_WARPS_PER_CTA = 4;
 #ifndef OPN_EXPAND_WARPS
-#define OPN_EXPAND_WARPS 6
+#define OPN_EXPAND_WARPS 8
 #endif
-constexpr int EXPAND_WARPS_PER_CTA = OPN_EXPAND_WARPS;  // k_synth_expand: 43 KB per CTA, 5 CTAs per SM, 4096 streams = one wave
+constexpr int EXPAND_WARPS_PER_CTA = OPN_EXPAND_WARPS;  // k_synth_expand: 52 KB per CTA, 4 CTAs per SM, 4096 streams = 512 CTAs = one wave (5/6/8 measured: 1.38/1.49/1.52 M)
 constexpr int IM_TPC = 128;         // threads per row of the out-of-place comb operator kernel
 constexpr int HIST_CAP = 1024;      // comb history window in shared memory (T + 2 <= 1024)
 // per-channel PCM ring: 4 x 960 = 8 x 480 = 16 x 240 = 32 x 120.  Four long frames, so that kernel 1 may write
