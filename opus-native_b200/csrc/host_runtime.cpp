@@ -117,9 +117,17 @@ struct opn_batch {
     cudaStream_t stream = nullptr;
     // The entropy stage (k_synth_rangedec: one lane per packet, latency-bound, a few hundred warps)
     // runs on its own (high-priority) streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
-    // live in NSETS buffer sets handed over with events.
-    static constexpr int NSETS = 6, NRD = 4;
-    cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: two entropy stages may overlap each other
+    // live in NSETS buffer sets handed over with events.  Under load one range decode takes several step times (its
+    // warps share the schedulers with everything else), so the number in flight bounds the step: 6 sets / 4
+    // streams 52.8 us per 4096-stream step, 8 / 8 45.5 us, 12 / 6, 12 / 12 and 16 / 16 no better (46-47 us).
+#ifndef OPN_NSETS
+#define OPN_NSETS 8
+#endif
+#ifndef OPN_NRD
+#define OPN_NRD 8
+#endif
+    static constexpr int NSETS = OPN_NSETS, NRD = OPN_NRD;
+    cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: entropy stages of NRD steps overlap each other
     cudaStream_t stream_ex = nullptr;     // PVQ expansion: between the entropy streams and `stream`
     cudaStream_t stream_k2 = nullptr;     // kernel 2 (post-filter): one step behind kernel 1 on `stream`
     cudaEvent_t ev_k1[NSETS] = {};        // kernel 1 of set p finished

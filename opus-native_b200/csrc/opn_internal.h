@@ -9,6 +9,12 @@
 namespace opn {
 
 constexpr int SYM_WARPS_PER_CTA = 4;
+#ifndef OPN_RD_WARPS
+#define OPN_RD_WARPS 1
+#endif
+// k_synth_rangedec: one packet per thread.  1, 2, 4 and 8 warps per CTA measure the same (46.7-48 us per step):
+// the SMs' 32 CTA slots are not what the long-running entropy launches take from the other kernels.
+constexpr int RANGEDEC_WARPS_PER_CTA = OPN_RD_WARPS;
 #ifndef OPN_EXPAND_WARPS
 #define OPN_EXPAND_WARPS 8
 #endif

@@ -201,7 +201,8 @@ cudaError_t launch_synth_rangedec(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
     if (!a.idx) return cudaErrorInvalidValue;
-    k_synth_rangedec<<<(a.n_items + 31u) / 32u, 32, 0, st>>>(a);
+    constexpr uint32_t per_cta = RANGEDEC_WARPS_PER_CTA * 32u;
+    k_synth_rangedec<<<(a.n_items + per_cta - 1u) / per_cta, per_cta, 0, st>>>(a);
     return cudaGetLastError();
 }
 

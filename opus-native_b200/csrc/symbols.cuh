@@ -138,11 +138,11 @@ __host__ __device__ constexpr size_t synth_expand_smem()
     return 3 * PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)EXPAND_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
 }
 
-__global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
+__global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(SymbolArgs A)
 {
     __shared__ SynthEntry s_ent[SYNTH_MAX_ENTRIES];
     __shared__ uint32_t s_fs0[21];  // get_start_freq(decay) per band (src/range_coder/mod.rs:530-534)
-    const uint32_t lane = threadIdx.x;
+    const uint32_t lane = threadIdx.x;  // index inside the CTA: one packet per thread
     const int lm = A.lm, C = A.channels;
     if (lane < 21u) {
         const uint32_t decay = 6000u + 400u * lane;
@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(32) k_synth_rangedec(SymbolArgs A)
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
         uint4 *dst = reinterpret_cast<uint4 *>(s_ent);
-        for (int i = lane; i < ne; i += 32) dst[i] = src[i];
+        for (int i = lane; i < ne; i += RANGEDEC_WARPS_PER_CTA * 32) dst[i] = src[i];
     }
-    __syncwarp();
-    const uint32_t item = blockIdx.x * 32u + lane;
+    __syncthreads();
+    const uint32_t item = blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u) + lane;
     if (item >= A.n_items) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
     uint32_t len = A.lens[item];

@@ -6,7 +6,10 @@ import torch
 
 import opus_native_b200 as opn
 
-n, pkt, nf, steps = 4096, 160, 960, 300
+import sys
+
+n, pkt, nf = 4096, 160, 960
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40  # keep below the launch-queue depth or the host blocks on the GPU
 packets = opn.synth_fill(0, n, 0, steps + 10, 3, 2, pkt, 0, n_threads=8)
 dev = torch.device("cuda:0")
 d_arena = torch.from_numpy(packets.reshape(-1)).to(dev)
