@@ -341,3 +341,126 @@ def test_cwrsi_single_pulse_closed_form():
             else:
                 w[2 * n - 1 - i] = -1
             assert np.array_equal(y, w) and yy == 1.0, (n, i)
+
+
+def _pvq_tables():
+    """U(n,k) table and row offsets as the library holds them (opn_tables.h, generated by tools/gen_tables.py)."""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "opus-native_b200", "csrc", "opn_tables.h")).read()
+
+    def tab(name):
+        m = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, src, re.S)
+        return [int(x.strip().rstrip("u")) for x in m.group(1).replace("\n", " ").split(",") if x.strip()]
+
+    return tab("OPN_PVQ_U_DATA"), tab("OPN_PVQ_U_ROW")
+
+
+def test_cwrsi_event_walk_matches_oracle():
+    """k_synth_expand (symbols.cuh) walks a part in events: while k < n the run of empty dimensions is found by
+    bisection on running row sums of U, with the single unsigned test i - C(k,n) + C(k,n-t-1) < V(n-t-1,k).
+    This is the same algorithm in Python on the same tables, checked against the oracle's sequential cwrsi
+    (pvc.rs:182-284) for the part shapes of SYNTH-CELT/1, shapes that enter the k >= n regime, and the largest
+    (n,k) the reference's own test uses with k < n."""
+    U, ROW = _pvq_tables()
+    M = 0xFFFFFFFF
+    CW = [(0, 0)] * len(U)  # (running row sum up to the previous column, U(k+1,m) - U(k,m)), as upload_tables builds it
+    for k in range(15):
+        first = ROW[k] + k
+        end = ROW[k + 1] + k + 1 if k < 14 else len(U)
+        next_end = ROW[k + 2] + k + 2 if k < 13 else len(U)
+        acc = 0
+        for i in range(first, end):
+            m = i - ROW[k]
+            up = ROW[k + 1] + m if k < 14 else len(U)
+            w = (U[up] - U[i]) & M if (m >= k + 1 and up < next_end) else 0
+            CW[i] = (acc, w)
+            acc = (acc + U[i]) & M
+
+    def walk(n, k, i):
+        y = [0] * n
+        pos = 0
+        events = 0
+        while n > 2:
+            events += 1
+            if k >= n:
+                rn = ROW[n]
+                p = U[rn + k + 1]
+                sg = -1 if i >= p else 0
+                i -= p if sg else 0
+                k0 = k
+                if U[rn + n] > i:
+                    k = n
+                    while True:
+                        k -= 1
+                        p = U[ROW[k] + n]
+                        if p <= i:
+                            break
+                else:
+                    p = U[rn + k]
+                    while p > i:
+                        k -= 1
+                        p = U[rn + k]
+                i -= p
+                y[pos] = (k0 - k + sg) ^ sg
+                pos += 1
+                n -= 1
+                continue
+            rk, rk1 = ROW[min(k, 14)], ROW[min(k + 1, 14)]
+            T = n - max(k, 2)
+            ic = (i - (CW[rk + n][0] + U[rk + n])) & M
+            lo, hi = 0, T
+            while lo < hi:
+                mid = (lo + hi) >> 1
+                c, w = CW[rk + n - mid]
+                if ((ic + c) & M) < w:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            if lo:
+                i = (ic + CW[rk + n + 1 - lo][0]) & M
+            pos += lo
+            n -= lo
+            if lo < T:
+                q = U[rk1 + n]
+                sg = -1 if i >= q else 0
+                i -= q if sg else 0
+                k0 = k
+                while True:
+                    k -= 1
+                    p = U[ROW[k] + n]
+                    if p <= i:
+                        break
+                i -= p
+                y[pos] = (k0 - k + sg) ^ sg
+                pos += 1
+                n -= 1
+        if n == 2:
+            p = 2 * k + 1
+            sg = -1 if i >= p else 0
+            i -= p if sg else 0
+            k0 = k
+            k = (i + 1) >> 1
+            if k:
+                i -= 2 * k - 1
+            y[pos] = (k0 - k + sg) ^ sg
+            sg = -i
+            y[pos + 1] = (k + sg) ^ sg
+        return y, events
+
+    def V(n, k):
+        u = lambda a, b: U[ROW[min(a, b)] + max(a, b)]
+        return u(n, k) + u(n, k + 1)
+
+    rnd = np.random.default_rng(5)
+    shapes = [(8, 1), (16, 2), (24, 3), (32, 4), (36, 4), (44, 5), (8, 3), (6, 4), (4, 6), (3, 10), (12, 9),
+              (11, 12), (22, 9), (176, 4), (96, 5), (48, 6), (9, 20), (2, 5)]
+    for n, k in shapes:
+        v = V(n, k)
+        idxs = {0, 1, v - 1, v - 2, v // 2} | {int(x) for x in rnd.integers(0, v, 300)}
+        for i in idxs:
+            y = np.zeros(n, np.int32)
+            L.orc_cwrsi(O.ptr(y), n, k, int(i))
+            w, events = walk(n, k, int(i))
+            assert list(y) == w, (n, k, i)
+            if k < n:
+                assert events <= k + 1, (n, k, i, events)  # one event per pulse-bearing dimension plus the last run
