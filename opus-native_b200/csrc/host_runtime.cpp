@@ -116,7 +116,7 @@ struct opn_batch {
     float gain = 1.0f;
     cudaStream_t stream = nullptr;
     // The entropy stage (k_synth_rangedec: one lane per packet, latency-bound, a few hundred warps)
-    // runs on its own (high-priority) streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
+    // runs on its own streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
     // live in NSETS buffer sets handed over with events.  Under load one range decode takes several step times (its
     // warps share the schedulers with everything else), so the number in flight bounds the step: 6 sets / 4
     // streams 52.8 us per 4096-stream step, 8 / 8 45.5 us, 12 / 6, 12 / 12 and 16 / 16 no better (46-47 us).
@@ -400,13 +400,10 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->gain = host_gain_from_q8(cfg->gain_q8);
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-    {
-        // the entropy stage is a handful of long-running warps: let its CTAs go first whenever an SM has room
-        int prio_lo = 0, prio_hi = 0;
-        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++)
-            e = cudaStreamCreateWithPriority(&b->stream_rd[q], cudaStreamNonBlocking, prio_hi);
-    }
+    // All pipeline streams have the same priority.  Measured (tools/experiments/priorities.sh, us per 4096-stream
+    // step, three processes each): all equal 45-46.5 and steady; entropy streams raised 45-53 with slow stretches;
+    // expansion raised 53-55; kernels 1/2 raised (drain first) 62-69.
+    for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++) e = cudaStreamCreateWithFlags(&b->stream_rd[q], cudaStreamNonBlocking);
     for (int q = 0; q < opn_batch::NSETS && e == cudaSuccess; q++) {
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
