@@ -285,12 +285,19 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
         }
         return;
     }
+    // bin -> part map of the coefficient write at the end: fetched now (15 words per lane at most), so the loads
+    // are long complete when the pulses are (the map sits in global memory; read in the loop, each L1 round trip
+    // was exposed: 28 % of the kernel's stall samples)
+    constexpr int MAX_VEC_PER_LANE = 2 * 960 / 4 / 32;
+    uint32_t ids[MAX_VEC_PER_LANE];
+    {
+        const uint32_t *ent4 = reinterpret_cast<const uint32_t *>(g_tab.synth_entry_of[lm][C - 1]);
+#pragma unroll
+        for (int j = 0; j < MAX_VEC_PER_LANE; j++) ids[j] = (int)lane + 32 * j < nvec ? __ldg(ent4 + lane + 32 * j) : 0u;
+    }
     // index -> pulse vector (cwrsi, pvc.rs:182-284; only nonzero pulses are stored).  The parts are sorted by
-    // size and dealt 32 at a time ("slots", tables: opn_kernels.cu); inside a slot the lanes run in lockstep on
-    // the dimension countdown c: a lane whose part has n dimensions joins when c reaches n, so every active
-    // lane is at dimension n == c and all lanes reach the closed-form tail (n == 2) together.  One loop
-    // iteration is one dimension for every lane -- empty or not -- instead of every lane's run of empty
-    // dimensions being waited for by the whole warp.
+    // size and dealt 32 at a time ("slots", tables: opn_kernels.cu), one part per lane; every lane walks its part
+    // in events (see below), the warp leaves a slot when its slowest lane is done.
     for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
     {
@@ -419,15 +426,16 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     __syncwarp();
     // pulses x gain -> coefficient rows, 4 bins per lane and step (entry_of: bin -> part)
     {
-        const uint32_t *ent4 = reinterpret_cast<const uint32_t *>(g_tab.synth_entry_of[lm][C - 1]);
         const uint2 *y4 = reinterpret_cast<const uint2 *>(s_y);
-#pragma unroll 3
-        for (int i = lane; i < nvec; i += 32) {
-            const uint32_t ids = __ldg(ent4 + i);
+#pragma unroll
+        for (int j = 0; j < MAX_VEC_PER_LANE; j++) {
+            const int i = (int)lane + 32 * j;
+            if (i >= nvec) break;
+            const uint32_t idw = ids[j];
             const uint2 yr = y4[i];
             int4 yv;
             float4 cv;
-            const uint32_t e0 = ids & 0xFFu, e1 = (ids >> 8) & 0xFFu, e2 = (ids >> 16) & 0xFFu, e3 = ids >> 24;
+            const uint32_t e0 = idw & 0xFFu, e1 = (idw >> 8) & 0xFFu, e2 = (idw >> 16) & 0xFFu, e3 = idw >> 24;
             yv.x = (int32_t)(int16_t)(yr.x & 0xFFFFu);  // bins without a part were zeroed above
             yv.y = (int32_t)(int16_t)(yr.x >> 16);
             yv.z = (int32_t)(int16_t)(yr.y & 0xFFFFu);
