@@ -128,14 +128,14 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 //      writes pulses x gain as coalesced float4 coefficient rows.
 //
 // Shared memory of k_synth_expand (per CTA of EXPAND_WARPS_PER_CTA warps):
-//   PVQ U(n,k) table 5088 B + bisection table 10176 B + row offsets 32 B | entry table 72 x 16 B | per warp: codeword
+//   PVQ U(n,k) table 5088 B + bisection table 10176 B (both by TMA) + row offsets 32 B + mbarrier 16 B | entry table 72 x 16 B | per warp: codeword
 //   indices 72 x 4 B, gains 76 x 4 B (slot 72 = 0 for bins without a part), 16-bit pulses 2 x 960 x 2 B.
 constexpr int SYM_Y16 = 2 * 960;
 constexpr int SYNTH_GAIN_SLOTS = SYNTH_MAX_ENTRIES + 4;
 constexpr size_t SYM_EXPAND_WARP_BYTES = SYNTH_MAX_ENTRIES * 4 + SYNTH_GAIN_SLOTS * 4 + SYM_Y16 * 2;
 __host__ __device__ constexpr size_t synth_expand_smem()
 {
-    return 3 * PVQ_TABLE_WORDS * 4 + 32 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)EXPAND_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
+    return 3 * PVQ_TABLE_WORDS * 4 + 32 + 16 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)EXPAND_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
 }
 
 __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(SymbolArgs A)
@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
     uint2 *s_cw = reinterpret_cast<uint2 *>(s_pvq + PVQ_TABLE_WORDS);
     uint16_t *s_row = reinterpret_cast<uint16_t *>(s_cw + PVQ_TABLE_WORDS);
-    SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(s_row + 16);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_row + 16);
+    SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(bar + 2);
     uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) + (size_t)warp * SYM_EXPAND_WARP_BYTES;
     int16_t *s_y = reinterpret_cast<int16_t *>(wbase);  // 16-byte aligned: zeroed as uint4, read back as 4 x int16
     uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_y + SYM_Y16);
@@ -255,9 +256,12 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
 
     const int lm = A.lm, C = A.channels, nf = 120 << lm;
     const int ne = g_tab.synth_n_entries[lm][C - 1];
-    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) {
-        s_pvq[i] = g_tab.pvq_u_data[i];
-        s_cw[i] = g_tab.pvq_cw_data[i];
+    // the two PVQ tables (15 KB) arrive by TMA while the warps fetch their indices and clear their pulse rows
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, 3 * PVQ_TABLE_WORDS * 4);
+        bulk_g2s(s_pvq, g_tab.pvq_u_data, PVQ_TABLE_WORDS * 4, bar);
+        bulk_g2s(s_cw, g_tab.pvq_cw_data, 2 * PVQ_TABLE_WORDS * 4, bar);
     }
     if (threadIdx.x < 15) s_row[threadIdx.x] = g_tab.pvq_u_row[threadIdx.x];
     {
@@ -272,8 +276,12 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     const bool zero_frame = status == ITEM_LOST || (status >= 0 && A.side[stream].silence != 0);
     if (status >= 0 && !zero_frame)
         for (int e = lane; e < ne; e += 32) s_idx[e] = A.idx[(size_t)stream * SYNTH_MAX_ENTRIES + e];
-    __syncthreads();
-    if (status < 0) return;
+    for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();  // entry table, row offsets and the mbarrier are set up
+    if (status < 0) {
+        mbar_wait(bar, 0);  // do not let the CTA retire under the table transfer
+        return;
+    }
 
     float4 *coef4 = A.coef ? reinterpret_cast<float4 *>(A.coef + (size_t)stream * C * nf) : nullptr;
     int4 *yo4 = A.y_out ? reinterpret_cast<int4 *>(A.y_out + (size_t)stream * C * nf) : nullptr;
@@ -283,6 +291,7 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
             if (coef4) coef4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (yo4) yo4[i] = make_int4(0, 0, 0, 0);
         }
+        mbar_wait(bar, 0);
         return;
     }
     // bin -> part map of the coefficient write at the end: fetched now (15 words per lane at most), so the loads
@@ -298,8 +307,7 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     // index -> pulse vector (cwrsi, pvc.rs:182-284; only nonzero pulses are stored).  The parts are sorted by
     // size and dealt 32 at a time ("slots", tables: opn_kernels.cu), one part per lane; every lane walks its part
     // in events (see below), the warp leaves a slot when its slowest lane is done.
-    for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncwarp();
+    mbar_wait(bar, 0);
     {
         const uint32_t *U = s_pvq;
         const uint2 *CW = s_cw;
