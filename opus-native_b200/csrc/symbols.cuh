@@ -124,12 +124,13 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 //      front-to-back and back-to-front, so every 128-byte line is fetched once).
 //   k_synth_expand    ONE WARP expands one packet's indices into pulse vectors (cwrsi never feeds
 //      back into the range decoder): the parts are dealt to the 32 lanes by a host-computed
-//      longest-first schedule so every lane walks about the same number of dimensions, then the warp
-//      writes pulses x gain as coalesced float4 coefficient rows.
+//      longest-first schedule, one part per lane and slot; a lane walks its part in events (one run of
+//      empty dimensions, found by bisection, plus the occupied dimension after it), then the warp writes
+//      pulses x gain as coalesced float4 coefficient rows.
 //
 // Shared memory of k_synth_expand (per CTA of EXPAND_WARPS_PER_CTA warps):
-//   PVQ U(n,k) table 5088 B + bisection table 10176 B (both by TMA) + row offsets 32 B + mbarrier 16 B | entry table 72 x 16 B | per warp: codeword
-//   indices 72 x 4 B, gains 76 x 4 B (slot 72 = 0 for bins without a part), 16-bit pulses 2 x 960 x 2 B.
+//   PVQ U(n,k) table 5088 B + bisection table 10176 B (both by TMA) + row offsets 32 B + mbarrier 16 B |
+//   entry table 72 x 16 B | per warp: codeword indices 72 x 4 B, gains 76 x 4 B (slot 72 = 0 for bins without a part), 16-bit pulses 2 x 960 x 2 B.
 constexpr int SYM_Y16 = 2 * 960;
 constexpr int SYNTH_GAIN_SLOTS = SYNTH_MAX_ENTRIES + 4;
 constexpr size_t SYM_EXPAND_WARP_BYTES = SYNTH_MAX_ENTRIES * 4 + SYNTH_GAIN_SLOTS * 4 + SYM_Y16 * 2;
