@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     {
         const uint32_t *ent4 = reinterpret_cast<const uint32_t *>(g_tab.synth_entry_of[lm][C - 1]);
 #pragma unroll
-        for (int j = 0; j < MAX_VEC_PER_LANE; j++) ids[j] = (int)lane + 32 * j < nvec ? __ldg(ent4 + lane + 32 * j) : 0u;
+        for (int j = 0; j < MAX_VEC_PER_LANE; j++) ids[j] = __ldg(ent4 + lane + 32 * j);  // always inside the 1920-byte map; unconditional so nothing waits on it here
     }
     // index -> pulse vector (cwrsi, pvc.rs:182-284; only nonzero pulses are stored).  The parts are sorted by
     // size and dealt 32 at a time ("slots", tables: opn_kernels.cu), one part per lane; every lane walks its part
