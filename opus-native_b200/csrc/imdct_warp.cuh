@@ -408,18 +408,31 @@ __device__ __forceinline__ WSmp<C> w_xfade(WSmp<C> y, const WSmp<C> *a, const WS
 // wherever those taps are history the samples are independent and are filtered in parallel, the rest
 // is swept in chunks no longer than T-2.  A tap set whose gain is exactly zero contributes +-0 to
 // every sum and is skipped.
+// tap gains of the old and the new filter (comb_filter/mod.rs:45-55, 146-151); a separate step so that kernel 2 can
+// have the table reads in flight while its samples are still arriving
+struct CombGains {
+    float g00, g01, g02, g10, g11, g12;
+};
+__device__ __forceinline__ CombGains w_comb_gains(float g0, float g1, int tap0, int tap1)
+{
+    CombGains k;
+    k.g00 = g0 * g_tab.comb_gains[tap0 * 3];
+    k.g01 = g0 * g_tab.comb_gains[tap0 * 3 + 1];
+    k.g02 = g0 * g_tab.comb_gains[tap0 * 3 + 2];
+    k.g10 = g1 * g_tab.comb_gains[tap1 * 3];
+    k.g11 = g1 * g_tab.comb_gains[tap1 * 3 + 1];
+    k.g12 = g1 * g_tab.comb_gains[tap1 * 3 + 2];
+    return k;
+}
 template <int C>
 __device__ __forceinline__ void w_comb(float *y, int t0, int t1, int n, float g0, float g1, int tap0, int tap1, int overlap, int lane,
-                                       const float *win_sq)
+                                       const float *win_sq, const CombGains &kg)
 {
     using S = WSmp<C>;
     if (g0 == 0.0f && g1 == 0.0f) return;
     t0 = max(t0, 15);
     t1 = max(t1, 15);
-    const float g00 = g0 * g_tab.comb_gains[tap0 * 3], g01 = g0 * g_tab.comb_gains[tap0 * 3 + 1],
-                g02 = g0 * g_tab.comb_gains[tap0 * 3 + 2];
-    const float g10 = g1 * g_tab.comb_gains[tap1 * 3], g11 = g1 * g_tab.comb_gains[tap1 * 3 + 1],
-                g12 = g1 * g_tab.comb_gains[tap1 * 3 + 2];
+    const float g00 = kg.g00, g01 = kg.g01, g02 = kg.g02, g10 = kg.g10, g11 = kg.g11, g12 = kg.g12;
     if (fabsf(g0 - g1) < 1.1920929e-7f && t0 == t1 && tap0 == tap1) overlap = 0;
     const bool has0 = g0 != 0.0f, has1 = g1 != 0.0f;
 
@@ -667,9 +680,10 @@ template <int LM, int C> __global__ void __launch_bounds__(32) k_comb_post_w(Imd
         if (count > fit) bulk_g2s(dst + fit * C, ring, (count - fit) * C * 4, bar);
     }
     const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
+    const CombGains kg = w_comb_gains(j.g0, j.g1, j.tap0, j.tap1);
     __syncwarp();
     mbar_wait(bar, 0);
-    w_comb<C>(y, j.t0, j.t1, NF, j.g0, j.g1, j.tap0, j.tap1, 120, lane, g_tab.window_sq);
+    w_comb<C>(y, j.t0, j.t1, NF, j.g0, j.g1, j.tap0, j.tap1, 120, lane, g_tab.window_sq, kg);
     __syncwarp();
     float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
     const float gain = A.gain;
@@ -725,7 +739,7 @@ k_op_comb_inplace_w(float *__restrict__ y, size_t row_stride, int y_offset, int 
     for (int i = lane; i < n; i += 32) ys[i] = row[y_offset + i];
     for (int i = lane; i < need; i += 32) ys[-1 - i] = row[y_offset - 1 - i];
     __syncwarp();
-    w_comb<1>(ys, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq);
+    w_comb<1>(ys, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq, w_comb_gains(g0, g1, tap0, tap1));
     __syncwarp();
     for (int i = lane; i < n; i += 32) row[y_offset + i] = ys[i];
 }

@@ -273,10 +273,13 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     const uint32_t item = blockIdx.x * EXPAND_WARPS_PER_CTA + warp;
     const bool in_range = item < A.n_items;
     const uint32_t stream = in_range ? (A.stream_idx ? A.stream_idx[item] : item) : 0u;
+    // status, silence flag and codeword indices are requested together (one memory round trip, not three): the
+    // index rows exist for every stream, whatever the status turns out to be
     const int32_t status = in_range ? A.status[stream] : -1;
-    const bool zero_frame = status == ITEM_LOST || (status >= 0 && A.side[stream].silence != 0);
-    if (status >= 0 && !zero_frame)
+    const int32_t silence = in_range ? A.side[stream].silence : 0;
+    if (in_range)
         for (int e = lane; e < ne; e += 32) s_idx[e] = A.idx[(size_t)stream * SYNTH_MAX_ENTRIES + e];
+    const bool zero_frame = status == ITEM_LOST || (status >= 0 && silence != 0);
     for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();  // entry table, row offsets and the mbarrier are set up
     if (status < 0) {
