@@ -60,6 +60,20 @@ int opn_decode_float(opn_decoder *dec, const uint8_t *packet, size_t len, float 
  * pcm_capacity is the slice length the Rust caller would pass (`samples.len()`). */
 int opn_decode_i16(opn_decoder *dec, const uint8_t *packet, size_t len, int16_t *pcm,
                    size_t pcm_capacity, size_t frame_size, int decode_fec);
+/* Decoder::decode::<S> (decoder.rs:148-193) for every S the crate implements `Sample` for (lib.rs:63-107):
+ * pcm_soft_clip, then S::from_f32 on the device.  sample_format picks S; pcm points at pcm_capacity elements of
+ * that type.  The crate's conversions are kept as written: i16/i32 clamp to the type's range (the i32 bound
+ * 2147483647.0 rounds to 2^31 in f32 and the cast saturates), u16/u32 clamp to [0, 32768] / [0, 2^31] (upper
+ * bound = midpoint + full scale, lib.rs:93-107), NaN converts to 0 like a Rust `as` cast. */
+#define OPN_SAMPLE_F32 0 /* Sample for f32, lib.rs:63-68  */
+#define OPN_SAMPLE_I16 1 /* Sample for i16, lib.rs:77-83  */
+#define OPN_SAMPLE_I32 2 /* Sample for i32, lib.rs:85-91  */
+#define OPN_SAMPLE_U16 3 /* Sample for u16, lib.rs:93-99  */
+#define OPN_SAMPLE_U32 4 /* Sample for u32, lib.rs:101-107 */
+#define OPN_SAMPLE_F64 5 /* Sample for f64, lib.rs:70-75  */
+int opn_decode_pcm(opn_decoder *dec, const uint8_t *packet, size_t len, void *pcm, size_t pcm_capacity,
+                   int sample_format, size_t frame_size, int decode_fec);
+size_t opn_sample_size(int sample_format); /* bytes per sample, 0 for an unknown format */
 int32_t opn_decoder_sampling_rate(const opn_decoder *dec);                   /* decoder.rs:80  */
 int32_t opn_decoder_channels(const opn_decoder *dec);                        /* decoder.rs:85  */
 int32_t opn_decoder_gain(const opn_decoder *dec);                            /* decoder.rs:90  */
@@ -101,6 +115,10 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
  * OPN_FLAG_SUBMIT_ONLY / opn_batch_wait work as for opn_batch_decode_float. */
 int opn_batch_decode_i16(opn_batch *b, const uint8_t *arena, const uint32_t *offsets,
                          const uint32_t *lens, int16_t *pcm, size_t pcm_stride_samples,
+                         size_t frame_size, int32_t *result_per_stream, uint32_t flags);
+/* The same for any sample type (OPN_SAMPLE_*): Decoder::decode::<S> for every stream. */
+int opn_batch_decode_pcm(opn_batch *b, const uint8_t *arena, const uint32_t *offsets,
+                         const uint32_t *lens, void *pcm, size_t pcm_stride_samples, int sample_format,
                          size_t frame_size, int32_t *result_per_stream, uint32_t flags);
 int opn_batch_synchronize(opn_batch *b);
 /* Host-buffer calls made with OPN_FLAG_SUBMIT_ONLY return a ticket (0 or 1) instead of waiting: at most two

@@ -4,7 +4,7 @@
 //
 //   DecoderConfiguration            src/decoder.rs:27-44   (default: 48 kHz, stereo, gain 0)
 //   OpusError                       src/error.rs:5-16
-//   Decoder::{new, reset, decode_float, decode (i16), getters}   src/decoder.rs:54-232
+//   Decoder::{new, reset, decode_float, decode::<S>, getters}   src/decoder.rs:54-232
 //   BatchDecoder                    the batch-of-streams entry point this engine adds
 //
 // Rust's Result<T, OpusError> becomes a C++ exception of type opus_native::OpusError; Option<&[u8]>
@@ -24,6 +24,15 @@ namespace opus_native {
 enum class SamplingRate : int32_t { Hz8000 = 8000, Hz12000 = 12000, Hz16000 = 16000, Hz24000 = 24000, Hz48000 = 48000 };  // lib.rs:124-135
 enum class Channels : int32_t { Mono = 1, Stereo = 2 };                                                                   // lib.rs:111-118
 enum class Bandwidth : int32_t { Narrowband = 0, Mediumband = 1, Wideband = 2, Superwideband = 3, Fullband = 4 };           // lib.rs:168-185
+
+// The `Sample` trait (lib.rs:58-107): the output types decode::<S> is implemented for.
+template <typename S> struct Sample;
+template <> struct Sample<float> { static constexpr int format = OPN_SAMPLE_F32; };
+template <> struct Sample<double> { static constexpr int format = OPN_SAMPLE_F64; };
+template <> struct Sample<int16_t> { static constexpr int format = OPN_SAMPLE_I16; };
+template <> struct Sample<int32_t> { static constexpr int format = OPN_SAMPLE_I32; };
+template <> struct Sample<uint16_t> { static constexpr int format = OPN_SAMPLE_U16; };
+template <> struct Sample<uint32_t> { static constexpr int format = OPN_SAMPLE_U32; };
 
 struct DecoderConfiguration {  // decoder.rs:27-44
     SamplingRate sampling_rate = SamplingRate::Hz48000;
@@ -80,10 +89,11 @@ public:
         if (samples_len < frame_size * (size_t)cfg_.channels) throw OpusError(OPN_ERR_BUFFER_TOO_SMALL);
         return (size_t)check(opn_decode_float(raw_, packet, len, samples, frame_size, decode_fec ? 1 : 0));
     }
-    // decode::<i16> (:148-193): soft clip, then Sample::from_f32.
-    size_t decode(const uint8_t *packet, size_t len, int16_t *samples, size_t samples_len, size_t frame_size, bool decode_fec)
+    // decode::<S> (:148-193): soft clip, then Sample::from_f32; S = int16_t, int32_t, uint16_t, uint32_t, float, double.
+    template <typename S>
+    size_t decode(const uint8_t *packet, size_t len, S *samples, size_t samples_len, size_t frame_size, bool decode_fec)
     {
-        return (size_t)check(opn_decode_i16(raw_, packet, len, samples, samples_len, frame_size, decode_fec ? 1 : 0));
+        return (size_t)check(opn_decode_pcm(raw_, packet, len, samples, samples_len, Sample<S>::format, frame_size, decode_fec ? 1 : 0));
     }
     SamplingRate sampling_rate() const { return cfg_.sampling_rate; }                        // :80
     Channels channels() const { return cfg_.channels; }                                      // :85
@@ -127,16 +137,19 @@ public:
     {
         return check(opn_batch_decode_float(raw_, arena, offsets, lens, pcm, pcm_stride, frame_size, results, OPN_FLAG_SUBMIT_ONLY));
     }
-    // Decoder::decode::<i16> for every stream (soft clip + Sample::from_f32 on the device).
-    void decode(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm, size_t pcm_stride, size_t frame_size,
+    // Decoder::decode::<S> for every stream (soft clip + Sample::from_f32 on the device).
+    template <typename S>
+    void decode(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, S *pcm, size_t pcm_stride, size_t frame_size,
                 int32_t *results)
     {
-        check(opn_batch_decode_i16(raw_, arena, offsets, lens, pcm, pcm_stride, frame_size, results, 0));
+        check(opn_batch_decode_pcm(raw_, arena, offsets, lens, pcm, pcm_stride, Sample<S>::format, frame_size, results, 0));
     }
-    int submit(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm, size_t pcm_stride, size_t frame_size,
+    template <typename S>
+    int submit(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, S *pcm, size_t pcm_stride, size_t frame_size,
                int32_t *results)
     {
-        return check(opn_batch_decode_i16(raw_, arena, offsets, lens, pcm, pcm_stride, frame_size, results, OPN_FLAG_SUBMIT_ONLY));
+        return check(opn_batch_decode_pcm(raw_, arena, offsets, lens, pcm, pcm_stride, Sample<S>::format, frame_size, results,
+                                          OPN_FLAG_SUBMIT_ONLY));
     }
     void wait(int ticket) { check(opn_batch_wait(raw_, ticket)); }
     void synchronize() { check(opn_batch_synchronize(raw_)); }

@@ -11,6 +11,10 @@ _SO = os.path.join(_HERE, "libopusb200.so")
 
 OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL = range(10)
 FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY = 1, 2, 4, 8
+# OPN_SAMPLE_*: the types the crate implements `Sample` for (lib.rs:63-107)
+SAMPLE_F32, SAMPLE_I16, SAMPLE_I32, SAMPLE_U16, SAMPLE_U32, SAMPLE_F64 = 0, 1, 2, 3, 4, 5
+SAMPLE_FORMAT_OF = {np.dtype(np.float32): SAMPLE_F32, np.dtype(np.int16): SAMPLE_I16, np.dtype(np.int32): SAMPLE_I32,
+                    np.dtype(np.uint16): SAMPLE_U16, np.dtype(np.uint32): SAMPLE_U32, np.dtype(np.float64): SAMPLE_F64}
 OP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4")])
 OUT_DTYPE = np.dtype([("value", "<u4"), ("tell_frac", "<u4"), ("rng", "<u4")])
 SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra")]
@@ -77,6 +81,8 @@ def lib():
     sig("opn_decoder_reset", C.c_int, vp)
     sig("opn_decode_float", C.c_int, vp, u8p, sz, vp, sz, C.c_int)
     sig("opn_decode_i16", C.c_int, vp, u8p, sz, vp, sz, sz, C.c_int)
+    sig("opn_decode_pcm", C.c_int, vp, u8p, sz, vp, sz, C.c_int, sz, C.c_int)
+    sig("opn_sample_size", sz, C.c_int)
     for g in ("sampling_rate", "channels", "gain", "bandwidth", "pitch", "last_packet_duration"):
         sig("opn_decoder_" + g, i32, vp)
     sig("opn_decoder_final_range", u32, vp)
@@ -91,6 +97,7 @@ def lib():
     sig("opn_batch_stats", C.c_int, vp, vp, vp, C.c_int)
     sig("opn_batch_wait", C.c_int, vp, C.c_int)
     sig("opn_batch_decode_i16", C.c_int, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, C.c_uint32)
+    sig("opn_batch_decode_pcm", C.c_int, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_size_t, vp, C.c_uint32)
     sig("opn_batch_join", C.c_int, vp)
     sig("opn_op_bitexact_trig", C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32)
     sig("opn_batch_cuda_stream", vp, vp)
@@ -199,12 +206,14 @@ class Decoder:
         return _chk(lib().opn_decode_float(self._h, _p(b), len(b), _p(samples), frame_size, int(decode_fec)))
 
     def decode(self, packet, samples: np.ndarray, frame_size: int, decode_fec: bool = False) -> int:
-        """Generic `decode<S>` for S = i16 (soft clip + Sample::from_f32)."""
-        assert samples.dtype == np.int16 and samples.flags.c_contiguous
+        """Generic `decode<S>` (soft clip + Sample::from_f32); S is the dtype of `samples`: int16, int32, uint16,
+        uint32, float32 or float64."""
+        assert samples.flags.c_contiguous
+        fmt = SAMPLE_FORMAT_OF[samples.dtype]
         if packet is None:
-            return _chk(lib().opn_decode_i16(self._h, None, 0, _p(samples), samples.size, frame_size, int(decode_fec)))
+            return _chk(lib().opn_decode_pcm(self._h, None, 0, _p(samples), samples.size, fmt, frame_size, int(decode_fec)))
         b = _bytes(packet)
-        return _chk(lib().opn_decode_i16(self._h, _p(b), len(b), _p(samples), samples.size, frame_size, int(decode_fec)))
+        return _chk(lib().opn_decode_pcm(self._h, _p(b), len(b), _p(samples), samples.size, fmt, frame_size, int(decode_fec)))
 
     sampling_rate = property(lambda s: lib().opn_decoder_sampling_rate(s._h))
     channels = property(lambda s: lib().opn_decoder_channels(s._h))
@@ -275,6 +284,18 @@ class BatchDecoder:
         assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n_streams and pcm.flags.c_contiguous
         res = np.zeros(self.n_streams, np.int32)
         t = _chk(lib().opn_batch_decode_i16(self._h, _p(arena), _p(offsets), _p(lens), _p(pcm), pcm.shape[1], frame_size, _p(res), flags))
+        return res, t
+
+    def decode_pcm(self, arena, offsets, lens, pcm, frame_size, flags=0):
+        """`Decoder::decode::<S>` for every stream, S = pcm.dtype (int16, int32, uint16, uint32, float32, float64);
+        pcm is [n_streams, >= frame_size*channels].  Returns (result_per_stream, ticket-or-0)."""
+        arena = np.ascontiguousarray(arena, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint32)
+        lens = np.ascontiguousarray(lens, np.uint32)
+        assert pcm.ndim == 2 and pcm.shape[0] == self.n_streams and pcm.flags.c_contiguous
+        res = np.zeros(self.n_streams, np.int32)
+        t = _chk(lib().opn_batch_decode_pcm(self._h, _p(arena), _p(offsets), _p(lens), _p(pcm), pcm.shape[1], SAMPLE_FORMAT_OF[pcm.dtype],
+                                            frame_size, _p(res), flags))
         return res, t
 
     def decode_i16_ptrs(self, arena_ptr, offsets_ptr, lens_ptr, pcm_ptr, pcm_stride_samples, frame_size, result_ptr, flags):

@@ -156,8 +156,8 @@ struct opn_batch {
         size_t items_cap = 0;
         float *d_dense = nullptr;
         size_t dense_cap = 0;          // floats per stream
-        int16_t *d_dense16 = nullptr;  // i16 rows (decode::<i16> calls), dense_cap samples per stream
-        size_t dense16_cap = 0;
+        void *d_conv = nullptr;        // converted rows (decode::<S> calls), conv_cap samples of conv_esize bytes per stream
+        size_t conv_cap = 0, conv_esize = 0;
         int32_t *d_cliplen = nullptr, *h_cliplen = nullptr;  // [n] soft-clip slice length per stream
         cudaEvent_t done = nullptr;    // everything that uses this slot has finished (incl. the PCM download)
         bool pending = false;
@@ -174,7 +174,7 @@ struct opn_batch {
 
 namespace {
 
-int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes, size_t n_items, size_t dense_floats, bool want_i16)
+int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes, size_t n_items, size_t dense_floats, size_t conv_esize)
 {
     if (!g.done) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     if (arena_bytes > g.arena_cap) {
@@ -194,12 +194,14 @@ int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes,
         g.dense_cap = dense_floats;
         CU(cudaMalloc(&g.d_dense, (size_t)b->n * g.dense_cap * sizeof(float)));
     }
-    if (want_i16 && g.dense_cap > g.dense16_cap) {
-        if (g.d_dense16) cudaFree(g.d_dense16);
-        g.dense16_cap = g.dense_cap;
-        CU(cudaMalloc(&g.d_dense16, (size_t)b->n * g.dense16_cap * sizeof(int16_t)));
+    if (conv_esize && (g.dense_cap > g.conv_cap || conv_esize > g.conv_esize)) {
+        if (g.d_conv) cudaFree(g.d_conv);
+        g.d_conv = nullptr;
+        g.conv_cap = g.dense_cap;
+        g.conv_esize = std::max(conv_esize, g.conv_esize);
+        CU(cudaMalloc(&g.d_conv, (size_t)b->n * g.conv_cap * g.conv_esize));
     }
-    if (want_i16 && !g.d_cliplen) {
+    if (conv_esize && !g.d_cliplen) {
         CU(cudaMalloc(&g.d_cliplen, (size_t)b->n * sizeof(int32_t)));
         CU(cudaMallocHost(&g.h_cliplen, (size_t)b->n * sizeof(int32_t)));
     }
@@ -494,7 +496,7 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(g.d_arena);
         cudaFree(g.d_items);
         cudaFree(g.d_dense);
-        cudaFree(g.d_dense16);
+        cudaFree(g.d_conv);
         cudaFree(g.d_cliplen);
         if (g.h_cliplen) cudaFreeHost(g.h_cliplen);
         if (g.h_items) cudaFreeHost(g.h_items);
@@ -538,8 +540,8 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
 // download, so that parsing, kernels and the PCIe copy of different chunks overlap.  The download is
 // the long pole (31.5 MB per 4096 stereo 20 ms frames); everything else hides behind it.
 static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, float *pcm,
-                             size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags, int soft_clip,
-                             int16_t *pcm16 = nullptr)
+                             size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags,
+                             void *pcm_conv = nullptr, int sample_format = OPN_SAMPLE_F32)
 {
     const uint32_t n = b->n;
     const int C = b->cfg.channels;
@@ -562,9 +564,11 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         CU(cudaEventSynchronize(g.done));
         g.pending = false;
     }
-    int rc = batch_alloc_staging(b, g, arena_end, items_ub, dense_stride, pcm16 != nullptr);
+    const size_t esize = pcm_conv ? opn_sample_size(sample_format) : 0;
+    if (pcm_conv && esize == 0) return OPN_ERR_BAD_ARG;
+    int rc = batch_alloc_staging(b, g, arena_end, items_ub, dense_stride, esize);
     if (rc) return rc;
-    const bool want_pcm = (pcm != nullptr || pcm16 != nullptr) && !(flags & OPN_FLAG_NO_PCM_COPY);
+    const bool want_pcm = (pcm != nullptr || pcm_conv != nullptr) && !(flags & OPN_FLAG_NO_PCM_COPY);
     if (arena_end) CU(cudaMemcpyAsync(g.d_arena, arena, arena_end, cudaMemcpyHostToDevice, b->stream_up));
 
     const uint32_t n_chunks = std::min<uint32_t>(opn_batch::MAX_CHUNKS, std::max<uint32_t>(1u, n / 1024u));
@@ -665,8 +669,8 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             }
             kbase += items.size();
         }
-        if (want_pcm && pcm16) {
-            // decode::<i16>: soft clip + Sample::from_f32 on the device, then half the bytes go home.
+        if (want_pcm && pcm_conv) {
+            // decode::<S>: soft clip + Sample::from_f32 on the device; for the 16-bit types half the bytes go home.
             // The epilogue kernel follows the chunk's kernels on the post-filter stream.
             for (uint32_t i = s0; i < s1; i++) g.h_cliplen[i] = res[i];
             CU(cudaMemcpyAsync(g.d_cliplen + s0, g.h_cliplen + s0, (size_t)(s1 - s0) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream_up));
@@ -674,30 +678,20 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             CU(cudaStreamWaitEvent(b->stream_k2, b->ev_in, 0));
             CU(cudaEventRecord(b->ev_chunk[ch], b->stream));  // kernel 1 (and the gap memset) of this chunk
             CU(cudaStreamWaitEvent(b->stream_k2, b->ev_chunk[ch], 0));
-            CU(launch_softclip_i16(g.d_dense, g.dense_cap, g.d_cliplen, C, (uint32_t)(frame_size * (size_t)C), s0, s1 - s0, b->d_softclip,
-                                   g.d_dense16, g.dense16_cap, b->stream_k2));
+            CU(launch_softclip_convert(sample_format, g.d_dense, g.dense_cap, g.d_cliplen, C, (uint32_t)(frame_size * (size_t)C), s0, s1 - s0,
+                                       b->d_softclip, g.d_conv, g.conv_cap, b->stream_k2));
             CU(cudaEventRecord(b->ev_chunk[ch], b->stream_k2));
             CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
-            const size_t row_bytes = frame_size * (size_t)C * sizeof(int16_t);
-            if (pcm_stride == g.dense16_cap && pcm_stride * sizeof(int16_t) == row_bytes)
-                CU(cudaMemcpyAsync(pcm16 + (size_t)s0 * pcm_stride, g.d_dense16 + (size_t)s0 * g.dense16_cap, (size_t)(s1 - s0) * row_bytes,
-                                   cudaMemcpyDeviceToHost, b->stream_dn));
+            const size_t row_bytes = frame_size * (size_t)C * esize;
+            uint8_t *dst = static_cast<uint8_t *>(pcm_conv) + (size_t)s0 * pcm_stride * esize;
+            const uint8_t *srcp = static_cast<const uint8_t *>(g.d_conv) + (size_t)s0 * g.conv_cap * esize;
+            if (pcm_stride == g.conv_cap && pcm_stride * esize == row_bytes)
+                CU(cudaMemcpyAsync(dst, srcp, (size_t)(s1 - s0) * row_bytes, cudaMemcpyDeviceToHost, b->stream_dn));
             else
-                CU(cudaMemcpy2DAsync(pcm16 + (size_t)s0 * pcm_stride, pcm_stride * sizeof(int16_t), g.d_dense16 + (size_t)s0 * g.dense16_cap,
-                                     g.dense16_cap * sizeof(int16_t), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
+                CU(cudaMemcpy2DAsync(dst, pcm_stride * esize, srcp, g.conv_cap * esize, row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         } else if (want_pcm) {
             // the chunk's last kernel 2 runs on its own stream: order the rest of this chunk after it
-            if (b->last_set >= 0 && b->k2_recorded[b->last_set]) {
-                if (soft_clip) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[b->last_set], 0));
-                else CU(cudaStreamWaitEvent(b->stream_dn, b->ev_k2[b->last_set], 0));
-            }
-            if (soft_clip) {
-                // decode_native(soft_clip=true), decoder.rs:413-419.  Reference quirk kept: the slice handed to
-                // pcm_soft_clip is samples[..sample_count] (per-channel count, not x channels).
-                // Only used by the single-stream decoder (one chunk, one row).
-                CU(launch_op_soft_clip(g.d_dense + (size_t)s0 * g.dense_cap, g.dense_cap, (size_t)std::max(res[s0], 0), C, s1 - s0,
-                                       b->d_softclip + (size_t)s0 * 2, b->stream));
-            }
+            if (b->last_set >= 0 && b->k2_recorded[b->last_set]) CU(cudaStreamWaitEvent(b->stream_dn, b->ev_k2[b->last_set], 0));
             // this chunk's PCM rows go home while the next chunk is decoded
             CU(cudaEventRecord(b->ev_chunk[ch], b->stream));
             CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
@@ -710,7 +704,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                                      g.dense_cap * sizeof(float), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         }
     }
-    if (!soft_clip && !pcm16) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
+    if (!pcm_conv) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
     // completion of this call = the batch stream, the post-filter stream and the download stream have drained
     CU(cudaEventRecord(b->ev_in, b->stream));
     CU(cudaStreamWaitEvent(b->stream_dn, b->ev_in, 0));
@@ -735,7 +729,7 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
     if (!(flags & OPN_FLAG_DEVICE_PTRS)) {
         if (!arena) return OPN_ERR_BAD_ARG;
         if (pcm && pcm_stride_floats < frame_size * (size_t)C) return OPN_ERR_BUFFER_TOO_SMALL;
-        const int rc = batch_decode_host(b, arena, offsets, lens, pcm, pcm_stride_floats, frame_size, result_per_stream, flags, 0);
+        const int rc = batch_decode_host(b, arena, offsets, lens, pcm, pcm_stride_floats, frame_size, result_per_stream, flags);
         if (rc < 0) return rc;
         return (flags & OPN_FLAG_SUBMIT_ONLY) ? rc : OPN_OK;  // submit-only: the ticket for opn_batch_wait
     }
@@ -751,17 +745,38 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
                       (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1);
 }
 
-int opn_batch_decode_i16(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm,
-                         size_t pcm_stride_samples, size_t frame_size, int32_t *result_per_stream, uint32_t flags)
+size_t opn_sample_size(int sample_format)
+{
+    switch (sample_format) {
+    case OPN_SAMPLE_F32: return sizeof(float);
+    case OPN_SAMPLE_I16: return sizeof(int16_t);
+    case OPN_SAMPLE_I32: return sizeof(int32_t);
+    case OPN_SAMPLE_U16: return sizeof(uint16_t);
+    case OPN_SAMPLE_U32: return sizeof(uint32_t);
+    case OPN_SAMPLE_F64: return sizeof(double);
+    default: return 0;
+    }
+}
+
+int opn_batch_decode_pcm(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, void *pcm,
+                         size_t pcm_stride_samples, int sample_format, size_t frame_size, int32_t *result_per_stream, uint32_t flags)
 {
     if (!b || !arena || !offsets || !lens || !pcm) return OPN_ERR_BAD_ARG;
+    if (opn_sample_size(sample_format) == 0) return OPN_ERR_BAD_ARG;
     if (frame_size == 0 || frame_size % 120 != 0) return OPN_ERR_BAD_ARG;  // decoder.rs:316-320
     if (flags & (OPN_FLAG_DEVICE_PTRS | OPN_FLAG_NO_PCM_COPY)) return OPN_ERR_BAD_ARG;
     if (pcm_stride_samples < frame_size * (size_t)b->cfg.channels) return OPN_ERR_BUFFER_TOO_SMALL;
     CU(cudaSetDevice(b->device));
-    const int rc = batch_decode_host(b, arena, offsets, lens, nullptr, pcm_stride_samples, frame_size, result_per_stream, flags, 0, pcm);
+    const int rc = batch_decode_host(b, arena, offsets, lens, nullptr, pcm_stride_samples, frame_size, result_per_stream, flags, pcm,
+                                     sample_format);
     if (rc < 0) return rc;
     return (flags & OPN_FLAG_SUBMIT_ONLY) ? rc : OPN_OK;
+}
+
+int opn_batch_decode_i16(opn_batch *b, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, int16_t *pcm,
+                         size_t pcm_stride_samples, size_t frame_size, int32_t *result_per_stream, uint32_t flags)
+{
+    return opn_batch_decode_pcm(b, arena, offsets, lens, pcm, pcm_stride_samples, OPN_SAMPLE_I16, frame_size, result_per_stream, flags);
 }
 
 int opn_batch_synchronize(opn_batch *b)
@@ -859,8 +874,8 @@ struct opn_decoder {
     int32_t fs = 48000, channels = 2;
     int16_t gain_q8 = 0;
     uint32_t final_range = 0;
-    float *h_pcm = nullptr;  // pinned staging
-    size_t h_cap = 0;
+    void *h_pcm = nullptr;  // pinned staging of decode::<S> (converted samples)
+    size_t h_cap = 0;       // bytes
 };
 
 extern "C" {
@@ -901,9 +916,9 @@ int opn_decoder_reset(opn_decoder *d)
 }
 
 static int decoder_decode(opn_decoder *d, const uint8_t *packet, size_t len, float *pcm, size_t frame_size, int decode_fec,
-                          int soft_clip)
+                          void *pcm_conv = nullptr, int sample_format = OPN_SAMPLE_F32)
 {
-    if (!d || !pcm) return OPN_ERR_BAD_ARG;
+    if (!d || (!pcm && !pcm_conv)) return OPN_ERR_BAD_ARG;
     if (frame_size == 0 || frame_size % (size_t)(d->fs / 400) != 0) return OPN_ERR_BAD_ARG;  // decoder.rs:316-320
     if (packet && len == 0) return OPN_ERR_BAD_ARG;                                           // decoder.rs:323-325
     if (packet && len > 0xFFFFFFFFull) return OPN_ERR_BAD_ARG;
@@ -917,7 +932,7 @@ static int decoder_decode(opn_decoder *d, const uint8_t *packet, size_t len, flo
     static const uint8_t dummy = 0;
     int32_t res = 0;
     int rc = batch_decode_host(d->batch, packet ? packet : &dummy, &off, &l, pcm, frame_size * (size_t)d->channels, frame_size,
-                               &res, 0, soft_clip);
+                               &res, 0, pcm_conv, sample_format);
     if (rc < 0) return rc;
     if (res >= 0) {
         uint32_t fr = 0;
@@ -930,13 +945,15 @@ static int decoder_decode(opn_decoder *d, const uint8_t *packet, size_t len, flo
 
 int opn_decode_float(opn_decoder *d, const uint8_t *packet, size_t len, float *pcm, size_t frame_size, int decode_fec)
 {
-    return decoder_decode(d, packet, len, pcm, frame_size, decode_fec, 0);
+    return decoder_decode(d, packet, len, pcm, frame_size, decode_fec);
 }
 
-int opn_decode_i16(opn_decoder *d, const uint8_t *packet, size_t len, int16_t *pcm, size_t pcm_capacity, size_t frame_size,
-                   int decode_fec)
+int opn_decode_pcm(opn_decoder *d, const uint8_t *packet, size_t len, void *pcm, size_t pcm_capacity, int sample_format,
+                   size_t frame_size, int decode_fec)
 {
     if (!d || !pcm) return OPN_ERR_BAD_ARG;
+    const size_t esize = opn_sample_size(sample_format);
+    if (esize == 0) return OPN_ERR_BAD_ARG;
     // Decoder::decode<S>, decoder.rs:148-193
     if (!decode_fec && packet) {
         if (len == 0) return OPN_ERR_BAD_ARG;
@@ -945,25 +962,28 @@ int opn_decode_i16(opn_decoder *d, const uint8_t *packet, size_t len, int16_t *p
         if (sc == 0) return OPN_ERR_INVALID_PACKET;
         frame_size = std::min(frame_size, (size_t)sc);
     }
-    const size_t need = frame_size * (size_t)d->channels;
+    const size_t need = frame_size * (size_t)d->channels * esize;
     if (need > d->h_cap) {
         if (d->h_pcm) cudaFreeHost(d->h_pcm);
         d->h_pcm = nullptr;
         d->h_cap = 0;
-        CU(cudaMallocHost(&d->h_pcm, need * sizeof(float)));
+        CU(cudaMallocHost(&d->h_pcm, need));
         d->h_cap = need;
     }
-    const int n = decoder_decode(d, packet, len, d->h_pcm, frame_size, decode_fec, 1);
+    // soft clip and S::from_f32 run on the device (k_softclip_convert); the converted samples land in the decoder's
+    // own buffer first, as in the crate (self.buffer), and reach the caller's slice only if it is long enough
+    const int n = decoder_decode(d, packet, len, nullptr, frame_size, decode_fec, d->h_pcm, sample_format);
     if (n <= 0) return n;
     if ((size_t)n > pcm_capacity) return OPN_ERR_BUFFER_TOO_SMALL;  // decoder.rs:181 (per-channel count vs slice length)
     if ((size_t)n * (size_t)d->channels > pcm_capacity) return OPN_ERR_BUFFER_TOO_SMALL;  // Rust would panic on the index
-    for (size_t i = 0; i < (size_t)n * (size_t)d->channels; i++) {
-        // Sample::from_f32 for i16, lib.rs:76-82 (format conversion of the already decoded PCM)
-        float f = d->h_pcm[i] * 32768.0f;
-        f = f < -32768.0f ? -32768.0f : (f > 32767.0f ? 32767.0f : f);
-        pcm[i] = (f != f) ? (int16_t)0 : (int16_t)f;
-    }
+    std::memcpy(pcm, d->h_pcm, (size_t)n * (size_t)d->channels * esize);
     return n;
+}
+
+int opn_decode_i16(opn_decoder *d, const uint8_t *packet, size_t len, int16_t *pcm, size_t pcm_capacity, size_t frame_size,
+                   int decode_fec)
+{
+    return opn_decode_pcm(d, packet, len, pcm, pcm_capacity, OPN_SAMPLE_I16, frame_size, decode_fec);
 }
 
 int32_t opn_decoder_sampling_rate(const opn_decoder *d) { return d ? d->fs : 0; }

@@ -92,8 +92,9 @@ cudaError_t launch_op_comb(float *y, const float *x, size_t row_stride, int offs
                            const int32_t *params4, const float *gains2, int overlap, cudaStream_t st);
 cudaError_t launch_op_bitexact_trig(const int16_t *x, int16_t *out_cos, uint32_t n_cos, const int32_t *isin, const int32_t *icos,
                                     int32_t *out_l2t, uint32_t n_l2t, cudaStream_t st);
-cudaError_t launch_softclip_i16(const float *dense, size_t dense_stride, const int32_t *clip_len, int channels, uint32_t row_floats,
-                                uint32_t first_row, uint32_t n_rows, float *mem, int16_t *out, size_t out_stride, cudaStream_t st);
+cudaError_t launch_softclip_convert(int sample_format, const float *dense, size_t dense_stride, const int32_t *clip_len, int channels,
+                                    uint32_t row_floats, uint32_t first_row, uint32_t n_rows, float *mem, void *out, size_t out_stride,
+                                    cudaStream_t st);
 cudaError_t launch_op_soft_clip(float *pcm, size_t row_stride, size_t row_len, int channels, uint32_t n_rows, float *mem,
                                 cudaStream_t st);
 

@@ -305,14 +305,31 @@ cudaError_t launch_op_bitexact_trig(const int16_t *x, int16_t *out_cos, uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_softclip_i16(const float *dense, size_t dense_stride, const int32_t *clip_len, int channels, uint32_t row_floats,
-                                uint32_t first_row, uint32_t n_rows, float *mem, int16_t *out, size_t out_stride, cudaStream_t st)
+template <typename T>
+static cudaError_t launch_softclip_convert_t(const float *dense, size_t dense_stride, const int32_t *clip_len, int channels,
+                                             uint32_t row_floats, uint32_t first_row, uint32_t n_rows, float *mem, void *out,
+                                             size_t out_stride, cudaStream_t st)
+{
+    k_softclip_convert<T><<<n_rows, 32, (size_t)row_floats * sizeof(float), st>>>(dense, dense_stride, clip_len, channels, row_floats,
+                                                                                   first_row, mem, static_cast<T *>(out), out_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_softclip_convert(int sample_format, const float *dense, size_t dense_stride, const int32_t *clip_len, int channels,
+                                    uint32_t row_floats, uint32_t first_row, uint32_t n_rows, float *mem, void *out, size_t out_stride,
+                                    cudaStream_t st)
 {
     if (n_rows == 0) return cudaSuccess;
     if (row_floats % 8u || (dense_stride & 3) || (out_stride & 7)) return cudaErrorInvalidValue;
-    k_softclip_i16<<<n_rows, 32, (size_t)row_floats * sizeof(float), st>>>(dense, dense_stride, clip_len, channels, row_floats, first_row, mem,
-                                                                            out, out_stride);
-    return cudaGetLastError();
+    switch (sample_format) {
+    case OPN_SAMPLE_F32: return launch_softclip_convert_t<float>(dense, dense_stride, clip_len, channels, row_floats, first_row, n_rows, mem, out, out_stride, st);
+    case OPN_SAMPLE_I16: return launch_softclip_convert_t<int16_t>(dense, dense_stride, clip_len, channels, row_floats, first_row, n_rows, mem, out, out_stride, st);
+    case OPN_SAMPLE_I32: return launch_softclip_convert_t<int32_t>(dense, dense_stride, clip_len, channels, row_floats, first_row, n_rows, mem, out, out_stride, st);
+    case OPN_SAMPLE_U16: return launch_softclip_convert_t<uint16_t>(dense, dense_stride, clip_len, channels, row_floats, first_row, n_rows, mem, out, out_stride, st);
+    case OPN_SAMPLE_U32: return launch_softclip_convert_t<uint32_t>(dense, dense_stride, clip_len, channels, row_floats, first_row, n_rows, mem, out, out_stride, st);
+    case OPN_SAMPLE_F64: return launch_softclip_convert_t<double>(dense, dense_stride, clip_len, channels, row_floats, first_row, n_rows, mem, out, out_stride, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_op_soft_clip(float *pcm, size_t row_stride, size_t row_len, int channels, uint32_t n_rows, float *mem,

@@ -85,14 +85,41 @@ __global__ void k_op_soft_clip(float *__restrict__ pcm_all, size_t row_stride, s
     mem_all[(size_t)row * channels + c] = a;
 }
 
-// Decoder::decode::<i16> epilogue for a batch (decoder.rs:177-189): one warp per stream stages the stream's
+// Sample::from_f32 (lib.rs:63-107) as the crate writes it: scale (and offset), clamp, then a Rust `as` cast, i.e.
+// truncation toward zero that saturates and maps NaN to 0 -- exactly what cvt.rzi does.  f32::clamp keeps NaN.
+template <typename T> __device__ __forceinline__ T sample_from_f32(float f);
+template <> __device__ __forceinline__ float sample_from_f32<float>(float f) { return f; }
+template <> __device__ __forceinline__ double sample_from_f32<double>(float f) { return (double)f; }
+template <> __device__ __forceinline__ int16_t sample_from_f32<int16_t>(float f)
+{
+    f = clampf(f * 32768.0f, -32768.0f, 32767.0f);
+    return (int16_t)__float2int_rz(f);
+}
+template <> __device__ __forceinline__ int32_t sample_from_f32<int32_t>(float f)
+{
+    f = clampf(f * 2147483648.0f, -2147483648.0f, 2147483648.0f);  // the crate's 2_147_483_647.0 is 2^31 as an f32
+    return __float2int_rz(f);                                        // saturates at i32::MAX
+}
+template <> __device__ __forceinline__ uint16_t sample_from_f32<uint16_t>(float f)
+{
+    f = clampf(f * 32768.0f + 32768.0f, 0.0f, 32768.0f);
+    return (uint16_t)__float2uint_rz(f);
+}
+template <> __device__ __forceinline__ uint32_t sample_from_f32<uint32_t>(float f)
+{
+    f = clampf(f * 2147483648.0f + 2147483648.0f, 0.0f, 2147483648.0f);
+    return __float2uint_rz(f);
+}
+
+// Decoder::decode::<S> epilogue for a batch (decoder.rs:177-189): one warp per stream stages the stream's
 // interleaved float row in shared memory, lanes 0..C-1 run pcm_soft_clip on their channel (a serial scan),
-// then the warp converts the row with Sample::from_f32 for i16 (lib.rs:76-82) and stores 8 samples per lane.
+// then the warp converts the row with Sample::from_f32 and stores 8 samples per lane and step.
 // clip_len[row] is the slice length the reference hands to pcm_soft_clip (its sample_count: the per-channel
 // count, decoder.rs:415-419 omits the "x channels"); <= 0 skips the clip (error rows are all zeros).
+template <typename T>
 __global__ void __launch_bounds__(32)
-k_softclip_i16(const float *__restrict__ dense, size_t dense_stride, const int32_t *__restrict__ clip_len, int channels, uint32_t row_floats,
-               uint32_t first_row, float *__restrict__ mem_all, int16_t *__restrict__ out, size_t out_stride)
+k_softclip_convert(const float *__restrict__ dense, size_t dense_stride, const int32_t *__restrict__ clip_len, int channels,
+                   uint32_t row_floats, uint32_t first_row, float *__restrict__ mem_all, T *__restrict__ out, size_t out_stride)
 {
     extern __shared__ __align__(16) float s_row[];
     const uint32_t row = first_row + blockIdx.x, lane = threadIdx.x;
@@ -111,21 +138,17 @@ k_softclip_i16(const float *__restrict__ dense, size_t dense_stride, const int32
         }
         __syncwarp();
     }
+    constexpr uint32_t NV = sizeof(T) * 8u / 16u;  // 16-byte stores per 8 samples
     uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)row * out_stride);
     for (uint32_t i = lane; i < row_floats / 8u; i += 32u) {
-        uint32_t w[4];
+        union {
+            T v[8];
+            uint4 q[NV];
+        } pk;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t h[2];
+        for (int e = 0; e < 8; e++) pk.v[e] = sample_from_f32<T>(s_row[8u * i + e]);
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                float f = s_row[8u * i + 2u * k + e] * 32768.0f;  // Sample::from_f32, lib.rs:76-82
-                f = f < -32768.0f ? -32768.0f : (f > 32767.0f ? 32767.0f : f);
-                h[e] = (uint32_t)(uint16_t)((f != f) ? (int16_t)0 : (int16_t)f);
-            }
-            w[k] = h[0] | (h[1] << 16);
-        }
-        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (uint32_t q = 0; q < NV; q++) dst[i * NV + q] = pk.q[q];
     }
 }
 

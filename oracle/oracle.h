@@ -131,6 +131,7 @@ void orc_pcm_soft_clip(float *pcm, size_t total_len, size_t channels, float *sof
                        size_t mem_len);
 void orc_smooth_fade(const float *in1, const float *in2, float *out, int overlap, int channels,
                      int fs);
+int orc_sample_from_f32(int format, const float *in, void *out, size_t n); /* lib.rs:63-107 */
 
 /* ---- SYNTH-CELT/1 frame decode: the oracle side of the fused pipeline ---- */
 typedef struct {

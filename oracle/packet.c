@@ -236,6 +236,55 @@ void orc_pcm_soft_clip(float *pcm, size_t total_len, size_t channels, float *mem
     }
 }
 
+/* Sample::from_f32 (lib.rs:63-107), restated with Rust's cast semantics spelled out: `x as iN/uN` truncates toward
+ * zero, saturates at the type's bounds and maps NaN to 0; f32::clamp returns NaN for NaN.  The literals are the
+ * crate's, evaluated as f32: 2_147_483_647.0 is 2^31, so the i32 clamp lets 2^31 through and the cast saturates
+ * it to i32::MAX; the unsigned upper bounds are midpoint + full scale (32768, 2^31), as written in the crate.
+ * format: 0 f32, 1 i16, 2 i32, 3 u16, 4 u32, 5 f64 (include/opusb200.h OPN_SAMPLE_*). */
+static int64_t rust_f32_as_int(float x, int64_t lo, int64_t hi)
+{
+    if (x != x) return 0;
+    if (x <= (float)lo) return lo;
+    if (x >= (float)hi) return hi;
+    return (int64_t)x; /* in range: C truncates toward zero like Rust */
+}
+int orc_sample_from_f32(int format, const float *in, void *out, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        float f = in[i];
+        switch (format) {
+        case 0: ((float *)out)[i] = f; break;                                               /* lib.rs:63-68 */
+        case 5: ((double *)out)[i] = (double)f; break;                                      /* lib.rs:70-75 */
+        case 1: {                                                                           /* lib.rs:77-83 */
+            float x = f * 32768.0f;
+            x = x != x ? x : clampf(x, -32768.0f, 32767.0f);
+            ((int16_t *)out)[i] = (int16_t)rust_f32_as_int(x, -32768, 32767);
+            break;
+        }
+        case 2: {                                                                           /* lib.rs:85-91 */
+            float x = f * 2147483648.0f;
+            x = x != x ? x : clampf(x, -2147483648.0f, 2147483648.0f /* 2_147_483_647.0 as f32 */);
+            ((int32_t *)out)[i] = (int32_t)rust_f32_as_int(x, -2147483648LL, 2147483647LL);
+            break;
+        }
+        case 3: {                                                                           /* lib.rs:93-99 */
+            float x = f * 32768.0f + 32768.0f;
+            x = x != x ? x : clampf(x, 0.0f, 32768.0f);
+            ((uint16_t *)out)[i] = (uint16_t)rust_f32_as_int(x, 0, 65535);
+            break;
+        }
+        case 4: {                                                                           /* lib.rs:101-107 */
+            float x = f * 2147483648.0f + 2147483648.0f;
+            x = x != x ? x : clampf(x, 0.0f, 2147483648.0f);
+            ((uint32_t *)out)[i] = (uint32_t)rust_f32_as_int(x, 0, 4294967295LL);
+            break;
+        }
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
 /* decoder.rs:833-865: out = w^2*in2 + (1-w^2)*in1 */
 void orc_smooth_fade(const float *in1, const float *in2, float *out, int overlap, int channels, int fs)
 {

@@ -119,6 +119,7 @@ def lib():
     sig("orc_parse_packet", C.c_int, vp, sz, C.c_int, vp, vp, C.POINTER(u32), C.POINTER(u32))
     sig("orc_pcm_soft_clip", None, vp, sz, sz, vp, sz)
     sig("orc_smooth_fade", None, vp, vp, vp, C.c_int, C.c_int, C.c_int)
+    sig("orc_sample_from_f32", C.c_int, C.c_int, vp, vp, sz)
     sig("orc_synth_state_init", None, C.POINTER(SynthState))
     sig("orc_synth_decode_frame", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int,
         C.POINTER(SynthSide), vp, vp, vp)

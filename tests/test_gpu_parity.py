@@ -810,6 +810,68 @@ def test_batch_decode_i16_matches_single_stream_decode_and_oracle():
     assert clipped > 0, "the test signal never exceeded full scale"
 
 
+@pytest.mark.parametrize("dtype,fmt,full_scale", [(np.int16, 1, 32768.0), (np.int32, 2, 2147483648.0), (np.uint16, 3, 32768.0),
+                                                   (np.uint32, 4, 2147483648.0), (np.float64, 5, 1.0)])
+def test_decode_generic_sample_types_match_oracle(dtype, fmt, full_scale):
+    """Decoder::decode::<S> for every S the crate implements `Sample` for (lib.rs:63-107), batch and single-stream.
+    Three checks per frame: (1) the single-stream decode::<S> equals the batch row; (2) S::from_f32 on the device
+    is exact: the S output equals orc_sample_from_f32 of the device's own decode::<f32> output (same packets, a
+    second decoder), for every stream and sample; (3) the whole chain against the oracle's float PCM ->
+    orc_pcm_soft_clip -> orc_sample_from_f32 within 4e-5 of full scale or one step of S (the +12 dB gain factor is computed by the
+    host library and by numpy here, which may differ in the last bit).  The gain drives peaks past full scale so
+    that the clip, the clamps and the saturating casts all fire."""
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 96, 4, 960
+    gain_q8 = 3072
+    g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
+    packets = opn.synth_fill(4000, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
+    cfg = opn.DecoderConfiguration(48000, channels, gain_q8)
+    batch, batch_f = opn.BatchDecoder(ns, cfg), opn.BatchDecoder(ns, cfg)
+    picks = (0, 31, 95)
+    singles = {s: opn.Decoder(cfg) for s in picks}
+    oracle = {s: (O.SynthStream(lm, channels), np.zeros(2, np.float32)) for s in picks}
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+    beyond = 0
+    for f in range(nfr):
+        out = np.zeros((ns, nf * channels), dtype)
+        res, _ = batch.decode_pcm(packets[f].reshape(-1), offsets, lens, out, nf)
+        assert np.all(res == nf)
+        out_f = np.zeros((ns, nf * channels), np.float32)
+        res, _ = batch_f.decode_pcm(packets[f].reshape(-1), offsets, lens, out_f, nf)
+        assert np.all(res == nf)
+        exact = np.zeros((ns, nf * channels), dtype)
+        assert O.lib().orc_sample_from_f32(fmt, O.ptr(out_f), O.ptr(exact), exact.size) == 0
+        assert np.array_equal(out, exact), (f, np.argwhere(out != exact)[:3].tolist())
+        for s in picks:
+            one = np.zeros(nf * channels, dtype)
+            assert singles[s].decode(packets[f, s], one, nf) == nf
+            assert np.array_equal(one, out[s]), (f, s)
+            st, mem = oracle[s]
+            w = st.decode(packets[f, s, 1:])[3] * g
+            beyond += int((np.abs(w) > 1.0).sum())
+            O.lib().orc_pcm_soft_clip(O.ptr(w), nf, channels, O.ptr(mem), 2)  # the crate's slice quirk: nf, not nf*channels
+            want = np.zeros(nf * channels, dtype)
+            assert O.lib().orc_sample_from_f32(fmt, O.ptr(w), O.ptr(want), want.size) == 0
+            # north_star's 1e-5 PCM bar, times the 4x gain applied after it; at least one step of an integer type
+            tol = 4e-5 * full_scale if dtype == np.float64 else max(1.0, 4e-5 * full_scale)
+            assert np.abs(out[s].astype(np.float64) - want.astype(np.float64)).max() <= tol, (f, s)
+    assert beyond > 0, "the test signal never exceeded full scale"
+
+
+def test_decode_pcm_rejects_unknown_format_and_short_buffers():
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0))
+    pkt, _ = opn.synth_packet(5, 0, 3, 2, 160)
+    b = np.frombuffer(bytes(pkt), np.uint8)
+    out = np.zeros(1920, np.int32)
+    rc = opn.lib().opn_decode_pcm(dec._h, b.ctypes.data_as(C.c_void_p), b.size, out.ctypes.data_as(C.c_void_p), out.size, 17, 960, 0)
+    assert rc == -1  # BadArguments
+    short = np.zeros(1000, np.int32)  # >= 960 (the crate's per-channel check passes) but < 960*2: Rust would panic on the index
+    with pytest.raises(opn.OpusError) as e:
+        dec.decode(pkt, short, 960)
+    assert e.value.code == -2
+    assert opn.lib().opn_sample_size(5) == 8 and opn.lib().opn_sample_size(3) == 2 and opn.lib().opn_sample_size(-1) == 0
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE config 2)
 def test_config2_full_size_properties():
     """4096 CELT FB 20 ms stereo streams @64 kbps, 3 chained frames: checksum of final ranges and the

@@ -464,3 +464,27 @@ def test_cwrsi_event_walk_matches_oracle():
             assert list(y) == w, (n, k, i)
             if k < n:
                 assert events <= k + 1, (n, k, i, events)  # one event per pulse-bearing dimension plus the last run
+
+
+def test_sample_from_f32_follows_the_crates_conversions():
+    """`Sample::from_f32` (lib.rs:63-107) has no test in the reference; the oracle restates it with Rust's cast
+    rules (truncate toward zero, saturate, NaN -> 0) and the crate's own clamp bounds, including the two that look
+    odd: the i32 upper bound 2_147_483_647.0 is 2^31 as an f32 (the cast then saturates to i32::MAX) and the
+    unsigned types clamp to midpoint + full scale, so full-scale positive input lands on the midpoint."""
+    x = np.array([0.0, 1.0, -1.0, 0.5, -0.5, 2.0, -2.0, np.nan, 1.0 / 32768.0, 0.99999, -0.99999, 3.0e-10], np.float32)
+
+    def conv(fmt, dtype):
+        out = np.zeros(x.size, dtype)
+        assert L.orc_sample_from_f32(fmt, O.ptr(x), O.ptr(out), x.size) == 0
+        return out
+
+    assert conv(1, np.int16).tolist() == [0, 32767, -32768, 16384, -16384, 32767, -32768, 0, 1, 32767, -32767, 0]
+    assert conv(2, np.int32).tolist() == [0, 2147483647, -2147483648, 1073741824, -1073741824, 2147483647, -2147483648, 0,
+                                           65536, 2147462144, -2147462144, 0]
+    assert conv(3, np.uint16).tolist() == [32768, 32768, 0, 32768, 16384, 32768, 0, 0, 32768, 32768, 0, 32768]
+    assert conv(4, np.uint32).tolist() == [2147483648, 2147483648, 0, 2147483648, 1073741824, 2147483648, 0, 0, 2147483648,
+                                            2147483648, 21504, 2147483648]
+    assert np.array_equal(conv(0, np.float32)[[0, 1, 2, 3]], x[[0, 1, 2, 3]])
+    f64 = conv(5, np.float64)
+    assert np.array_equal(f64[~np.isnan(f64)], x[~np.isnan(x)].astype(np.float64)) and np.isnan(f64[7])
+    assert L.orc_sample_from_f32(9, O.ptr(x), O.ptr(np.zeros(x.size, np.float64)), x.size) == -1
