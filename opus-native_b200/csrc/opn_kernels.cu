@@ -119,7 +119,7 @@ cudaError_t upload_tables(int device)
                 for (int j = 0; j < (int)E.n; j++) eo[E.base + j] = (uint8_t)e;
             }
             // k_synth_expand: parts sorted by the number of dimensions cwrsi has to walk (descending), 32 per slot,
-            // so that the lanes of a slot run similar countdowns in lockstep.  Sign-only bands (n == 1) and
+            // so that the lanes of a slot have walks of similar length.  Sign-only bands (n == 1) and
             // single-pulse parts (k == 1, closed form) walk nothing.
             {
                 auto walk = [&](int e) {

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
                 if (i < n) y[i] = (int16_t)1;
                 else y[2u * n - 1u - i] = (int16_t)-1;
                 yy = 1;
-                n = 0u;  // done: takes no part in the countdown below
+                n = 0u;  // done: takes no part in the walk below
             }
             // A lane walks its part in EVENTS, not dimensions.  While k < n (pvc.rs:232-258) a dimension is
             // empty iff U(k,n) <= i < U(k+1,n), and stepping over it subtracts U(k,n); after t empty dimensions

@@ -615,7 +615,7 @@ def test_batch_device_resident_path_matches_host_path():
 @pytest.mark.parametrize("postfilter", [True, False])
 def test_batch_device_resident_steps_enqueued_back_to_back(postfilter):
     """OPN_FLAG_INPUTS_READY: 14 steps are enqueued without a host wait in between, so range decode, PVQ
-    expansion, IMDCT and post-filter of up to six different steps are in flight at once (six buffer sets,
+    expansion, IMDCT and post-filter of up to eight different steps are in flight at once (eight buffer sets,
     kernel 2 one step behind kernel 1 on the four-frame ring).  Every step's PCM row is written to its own
     dense buffer and checked after one final synchronize, bit for bit, against the oracle."""
     torch = pytest.importorskip("torch")
