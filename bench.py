@@ -2,16 +2,18 @@
 """bench.py -- throughput of the batched Opus decode hot path on B200.
 
 Workload (BASELINE.json configs[1]): 4096 CELT-only fullband 20 ms stereo streams @64 kbps
-(160-byte packets, TOC 0xFC) per GPU; one "step" decodes one packet of every stream:
-kernel 0 (warp-per-stream range decode + PVQ expansion) then kernel 1 (IMDCT + TDAC overlap-add
-+ comb post-filter + interleaved PCM store).  Streams are independent, so N GPUs each own their
-own 4096 streams (weak scaling, no collective on the data path).
+(160-byte packets, TOC 0xFC) per GPU; one "step" decodes one packet of every stream in two launches:
+k_synth_rangedec (one lane per packet: every range-coded symbol) and k_frame_w (one warp per stream:
+PVQ expansion -> IMDCT + TDAC overlap-add -> comb post-filter -> interleaved PCM store, nothing in
+between leaves the SM).  Streams are independent, so N GPUs each own their own 4096 streams (weak
+scaling, no collective on the data path).
 
   value  : concurrent realtime streams = stereo frames decoded per second x 0.020 s, whole job,
            packets already resident in HBM, PCM left in the device ring (CUDA events, max over ranks)
   e2e    : the same metric through the host-buffer entry point (BatchDecoder.decode_float):
            pinned host packets -> H2D -> decode -> D2H float PCM inside the timed region
-  roofline: kernel 1, algorithmic bytes 4*(2*960+120) per channel-frame / average launch time
+  roofline: the frame kernel, algorithmic bytes 4*(2*960+120) per channel-frame plus the
+           4*(T+2) bytes of comb history of every channel-frame the post-filter ran on / average launch time
   cpu_baseline / --impl reference: the CPU oracle (a C port of the reference crate's code for this
            path; the crate itself is Rust and cannot be built in this image) on the host cores.
 
@@ -102,6 +104,27 @@ class ClockSampler:
                 "how": "NVML polled every ~2 ms inside the timed regions (resident, per-kernel and end-to-end passes)"}
 
 
+def workload_config(n, transient_permille):
+    """The `config` object of both arms (identical by construction)."""
+    return {"workload": f"{n} CELT-only fullband 20 ms stereo streams @64 kbps per GPU (BASELINE configs[1]; SYNTH-CELT/1, "
+                        "160 B packets): range decode + PVQ + IMDCT/TDAC + comb post-filter",
+            "streams_per_gpu": n, "frames_per_step_per_gpu": n, "packet_bytes": PKT_BYTES, "frame_ms": 20, "channels": CHANNELS,
+            "transient_permille": transient_permille}
+
+
+def pin_rank_to_cpus(local, world):
+    """All GPUs of these boxes hang off one CPU set; give every rank its own slice of it, so that the ranks' feeder
+    threads (packet synthesis, the copy-issuing thread, the checksum) do not migrate onto each other."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // max(1, world))
+        mine = cpus[local * per:(local + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -110,8 +133,8 @@ def cpu_threads():
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the same path, all host threads, same config/metric."""
-    import opus_native_b200 as opn  # packet synthesis only (host code); no GPU call on this arm
+    """--impl reference: the CPU implementation of the same path, all host threads, same config/metric.
+    Nothing of the product is loaded here: the packets come from the oracle's own range encoder."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     rank = int(os.environ.get("RANK", "0"))
@@ -120,7 +143,7 @@ def run_reference(args):
     n = args.streams
     cores = cpu_threads()
     total = args.steps + args.warmup
-    packets = opn.synth_fill(0, n, 0, total, LM, CHANNELS, PKT_BYTES, n_threads=cores)
+    packets = O.synth_fill(0, n, 0, total, LM, CHANNELS, PKT_BYTES, args.transient_permille, n_threads=cores)
     L = O.lib()
     x = ctypes.c_uint32(0)
     # Frames are chained per stream (overlap carry, comb history), exactly like the GPU steps: the
@@ -134,8 +157,7 @@ def run_reference(args):
         "impl": "reference", "metric": "concurrent_realtime_48k_streams_decoded", "value": value, "unit": "streams",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
-        "config": {"workload": f"{n} CELT-only fullband 20 ms stereo streams @64 kbps (SYNTH-CELT/1, 160 B packets), "
-                               "range decode + PVQ + IMDCT/TDAC + comb post-filter, CPU", "streams_per_step": n},
+        "config": workload_config(n, args.transient_permille),
         "cpu_baseline": {"value": value, "unit": "streams", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} chained steps x {n} stereo 20 ms frames (the full workload step), "
                                    "C oracle port of the reference crate (Rust toolchain absent), one thread per core"},
@@ -167,8 +189,8 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (BASELINE config 2: 4096)")
     ap.add_argument("--transient-permille", type=int, default=0)
@@ -188,6 +210,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libopusb200 has no CPU fallback")
+    cpus = pin_rank_to_cpus(local, world)  # before any allocation: pinned buffers and threads stay on this rank's cores
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -211,18 +234,18 @@ def main():
     K, W = args.steps, args.warmup
     total = K + W
     lo, hi = opn.shard_range(n * world, rank, world)  # this rank's global stream ids
-    cores = cpu_threads()
-    packets = opn.synth_fill(lo, n, 0, total, LM, CHANNELS, PKT_BYTES, args.transient_permille, n_threads=max(1, cores // max(1, world)))
+    cores = cpu_threads()  # this rank's share after pinning
+    packets = opn.synth_fill(lo, n, 0, total, LM, CHANNELS, PKT_BYTES, args.transient_permille, n_threads=cores)
     step_bytes = n * PKT_BYTES
 
     # ---------------- resident-input measurement (value) ----------------
-    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local)
+    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
     stream = torch.cuda.ExternalStream(dec.cuda_stream, device=dev)
     d_arena = torch.from_numpy(packets.reshape(-1)).to(dev)
     d_off = (torch.arange(n, dtype=torch.int64, device=dev) * PKT_BYTES).to(torch.int32)
     d_len = torch.full((n,), PKT_BYTES, dtype=torch.int32, device=dev)
     d_res = torch.zeros(n, dtype=torch.int32, device=dev)
-    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY  # packets are resident: the entropy stage may run up to 8 steps ahead
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY  # packets are resident: the range decode may run up to 8 steps ahead
 
     p_arena, p_off, p_len, p_res = d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr()
 
@@ -236,7 +259,6 @@ def main():
             e0.record()
             for f in range(k0, k1):
                 step_resident(f)
-            dec.join()  # the last post-filter kernel runs on an internal stream: make it an ancestor of e1
             e1.record()
         dec.synchronize()
         barrier()
@@ -264,13 +286,14 @@ def main():
     st = dec.stats(reset=True)
     dec.enable_timing(False)
     k0_ms, k1_ms, k2_ms = st["ms"][0] / K, st["ms"][1] / K, st["ms"][2] / K
+    hist_samples = dec.history_samples(reset=True) / K  # per launch: sum over channel-frames of max(T0,T1)+2
     assert int((d_res != NF).sum().item()) == 0
 
     # ---------------- end-to-end through the host-buffer API ----------------
     # The call a user makes: pinned host packets in, pinned host PCM out, every step.  Two calls are kept
     # in flight (OPN_FLAG_SUBMIT_ONLY + opn_batch_wait), so the 31.5 MB PCM download of step n overlaps the
     # upload and decode of step n+1; each step's PCM is read on the host (checksum) after its wait.
-    dec2 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local)
+    dec2 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
     h_arena = torch.from_numpy(packets.reshape(-1)).pin_memory()
     h_pcm = [torch.zeros((n, NF * CHANNELS), dtype=torch.float32).pin_memory() for _ in range(2)]
     a_np, p_np = h_arena.numpy(), [t.numpy() for t in h_pcm]
@@ -295,6 +318,22 @@ def main():
         probe += float(p_np[(k1 - 1) & 1][0, 0]) + float(p_np[(k1 - 1) & 1][-1, -1])
         return probe
 
+    # plain pinned D2H copies of one step's PCM (31.5 MB), all ranks at once: the ceiling the e2e figure is read against
+    probe_src = torch.empty(n * NF * CHANNELS, dtype=torch.float32, device=dev)
+    probe_dst = h_pcm[0].view(-1)
+    for _ in range(3):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(20):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    t_probe = max_over_ranks(pe0.elapsed_time(pe1) * 1e-3 / 20)
+    pcie_gbs = probe_src.numel() * 4 / t_probe / 1e9  # per GPU, slowest rank
+    del probe_src
+
     run_e2e(0, W)
     barrier()
     with sampler.region():
@@ -310,7 +349,7 @@ def main():
     # ---------------- the same end-to-end loop through Decoder::decode::<i16> (extra figure, not the headline) ----
     # soft clip + Sample::from_f32 run on the device, so half the bytes cross PCIe.
     K16 = min(K, 100)
-    dec3 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local)
+    dec3 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
     h_pcm16 = [torch.zeros((n, NF * CHANNELS), dtype=torch.int16).pin_memory() for _ in range(2)]
     p16 = [t.numpy() for t in h_pcm16]
 
@@ -349,43 +388,50 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         ch_frames = n * CHANNELS
-        achieved = ch_frames * ALGO_BYTES_PER_CHANNEL_FRAME / (k1_ms * 1e-3) / 1e9
+        algo_bytes = ch_frames * ALGO_BYTES_PER_CHANNEL_FRAME + 4 * hist_samples
+        achieved = algo_bytes / (k1_ms * 1e-3) / 1e9
         value = world * n * K / t_value * FRAME_S
         e2e = world * n * K / t_e2e * FRAME_S
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_imdct_post_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_frame_w_dram_bytes_per_launch")
+                traffic_src = "static: " + tj.get("source", "ncu --set full capture kept in profiles/traffic.json")
             except Exception:
                 traffic = None
+        d2h = n * NF * CHANNELS * 4
         line = {
             "metric": "concurrent_realtime_48k_streams_decoded", "value": value, "unit": "streams",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_value / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
-            "config": {
-                "workload": f"{n} CELT-only fullband 20 ms stereo streams @64 kbps per GPU (BASELINE configs[1]; SYNTH-CELT/1, "
-                            "160 B packets): range decode + PVQ + IMDCT/TDAC + comb post-filter",
-                "streams_per_gpu": n, "frames_per_step_per_gpu": n, "packet_bytes": PKT_BYTES,
-                "transient_permille": args.transient_permille,
-                "cache": f"inputs larger than L2: {total} distinct packet sets resident in HBM, each read once; "
-                         "per 4096 streams the decoder touches 126 MB of PCM ring plus eight rotating 31.5 MB coefficient sets, "
-                         "more than the 126 MB L2",
-                "per_kernel_ms": {"k_synth_rangedec+k_synth_expand": k0_ms, "k_imdct_post_w": k1_ms, "k_comb_post_w": k2_ms,
+            "config": workload_config(n, args.transient_permille),
+            "detail": {
+                "cache": f"inputs larger than L2: {total} distinct packet sets resident in HBM, each read once; per 4096 streams "
+                         "the decoder's PCM ring is 94 MB and every step writes 31.5 MB of new PCM into it",
+                "per_kernel_ms": {"k_synth_rangedec": k0_ms, "k_frame_w": k1_ms, "k_synth_expand (unfused variant only)": k2_ms,
                                   "note": "second pass of the same steps, stages in order on one stream with cudaEvents around "
-                                          "each; in the measured run the entropy stages of up to 8 later steps overlap the IMDCT of step n"},
-                "peak_source": peak_src, "e2e_checksum": checksum,
+                                          "each; in the measured run the range decode of up to 8 later steps overlaps the frame kernel of step n"},
+                "peak_source": peak_src, "e2e_checksum": checksum, "rank_cpus": cpus,
             },
             "e2e": {"value": e2e, "unit": "streams", "h2d_bytes_per_step": step_bytes + 4 * 4 * n,
-                    "d2h_bytes_per_step": n * NF * CHANNELS * 4, "ms_per_step": 1e3 * t_e2e / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / K,
+                    "pcie_peak_gbs": pcie_gbs, "pcie_frac": (d2h / (t_e2e / K) / 1e9) / pcie_gbs,
+                    "pcie_note": f"pcie_peak_gbs = plain pinned D2H copies of {d2h} bytes, {world} rank(s) at once, per GPU (slowest rank); "
+                                 "pcie_frac = this rank's PCM download rate inside the e2e loop / that ceiling"},
             "e2e_i16": {"value": world * n * K16 / t_e2e16 * FRAME_S, "unit": "streams", "steps": K16,
                         "d2h_bytes_per_step": n * NF * CHANNELS * 2, "ms_per_step": 1e3 * t_e2e16 / K16,
                         "note": "extra: the same host-buffer loop through opn_batch_decode_i16 (Decoder::decode::<i16>: "
                                 "soft clip and sample conversion on the device); not the headline"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_imdct_post_w<3,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": ch_frames * ALGO_BYTES_PER_CHANNEL_FRAME},
+            "roofline": {"bound": "hbm", "kernel": "k_frame_w<3,2,true> (PVQ expansion + IMDCT/TDAC + comb post-filter + PCM store)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "bytes_note": f"{ch_frames} channel-frames x 4*(2*960+120) B (coefficients + carry in, PCM + carry out, SURVEY 8d) "
+                                       f"+ 4 B x {hist_samples:.0f} comb history samples (sum of max(T0,T1)+2 over the channel-frames the "
+                                       "post-filter ran on, counted by the kernel)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

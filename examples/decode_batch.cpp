@@ -26,8 +26,8 @@ int main(int argc, char **argv)
     std::vector<uint32_t> offsets(ns), lens(ns, pkt);
     for (uint32_t s = 0; s < ns; s++) offsets[s] = s * pkt;
     try {
-        BatchDecoder batch(ns);
-        Decoder single;
+        BatchDecoder batch(ns, DecoderConfiguration(), 0, true, OPN_BITSTREAM_SYNTH_CELT_1);  // the synthetic frame layout is an explicit opt-in
+        Decoder single(DecoderConfiguration(), 0, OPN_BITSTREAM_SYNTH_CELT_1);
         std::vector<float> pcm[2] = {std::vector<float>((size_t)ns * nf * channels), std::vector<float>((size_t)ns * nf * channels)};
         std::vector<int32_t> res[2] = {std::vector<int32_t>(ns), std::vector<int32_t>(ns)};
         std::vector<float> one(nf * channels);

@@ -49,7 +49,8 @@ int opn_parse_packet(const uint8_t *packet, size_t len, int self_delimited, uint
 typedef struct opn_decoder opn_decoder;
 /* Decoder::new (decoder.rs:61); fs_hz in {8000,12000,16000,24000,48000}, channels in {1,2}.
  * Only 48000 Hz is implemented (the crate never computes its `downsample`, celt/decoder.rs:23). */
-int opn_decoder_create(int device, int32_t fs_hz, int32_t channels, int16_t gain_q8, opn_decoder **out);
+int opn_decoder_create(int device, int32_t fs_hz, int32_t channels, int16_t gain_q8, int32_t bitstream /* OPN_BITSTREAM_* */,
+                       opn_decoder **out);
 void opn_decoder_destroy(opn_decoder *dec);
 int opn_decoder_reset(opn_decoder *dec);                                     /* Decoder::reset decoder.rs:74 */
 /* Decoder::decode_float (decoder.rs:216-232).  packet == NULL means a lost packet.  Returns
@@ -89,7 +90,15 @@ typedef struct {
     int32_t channels;     /* output channels, 1 or 2 */
     int16_t gain_q8;      /* DecoderConfiguration::gain */
     int16_t postfilter;   /* 1: run the comb post-filter epilogue (default), 0: IMDCT only */
+    int32_t bitstream;    /* OPN_BITSTREAM_*: how CELT frame payloads are laid out */
 } opn_config;
+/* CeltDecoder::decode is todo!() in the crate (src/celt/decoder.rs:47-56): nothing defines how the symbols of a real
+ * RFC 6716 CELT frame become MDCT coefficients, so with OPN_BITSTREAM_OPUS (the default a drop-in caller gets) every
+ * CELT frame is reported as OPN_ERR_UNIMPLEMENTED -- exactly where the crate panics.  OPN_BITSTREAM_SYNTH_CELT_1 is an
+ * explicit opt-in to the synthetic frame layout of DESIGN.md section 3 (flags, post-filter parameters, Laplace energies,
+ * PVQ parts on a fixed schedule): built only from operations the crate implements, NOT interoperable with Opus. */
+#define OPN_BITSTREAM_OPUS 0
+#define OPN_BITSTREAM_SYNTH_CELT_1 1
 
 #define OPN_FLAG_DEVICE_PTRS 1u  /* arena/offsets/lens/pcm/results are device pointers; call is asynchronous */
 #define OPN_FLAG_NO_PCM_COPY 2u  /* leave PCM in the device ring only (read it with opn_batch_ring) */
@@ -131,15 +140,20 @@ int opn_batch_final_ranges(opn_batch *b, uint32_t *out);
 /* Device-resident PCM ring (history + output): base pointer, samples per channel in the ring,
  * and the per-stream write position after the last call (device pointer, n_streams words). */
 int opn_batch_ring(opn_batch *b, float **ring, uint32_t *ring_samples, uint32_t **ring_pos_dev);
-/* Counters for the measurement harness.  kernel_ms[k]/kernel_launches[k]: k = 0 symbol decode (range
- * decode + PVQ expansion, two launches), 1 IMDCT + TDAC + PCM store, 2 comb post-filter.  Timing must be
- * enabled first (stages then run in order on one stream with cudaEvents around each). */
+/* Counters for the measurement harness.  kernel_ms[k]/kernel_launches[k]: k = 0 range decode (k_synth_rangedec),
+ * 1 frame kernel (k_frame_w: PVQ expansion + IMDCT + TDAC + comb post-filter + PCM store), 2 stand-alone PVQ expansion
+ * (only in the unfused variant, OPN_UNFUSED_EXPAND=1).  Timing must be enabled first (stages then run in order on one
+ * stream with cudaEvents around each). */
 int opn_batch_enable_timing(opn_batch *b, int on);
 int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[3], int reset);
+/* Sum over the channel-frames the post-filter ran on, in timed passes, of max(T0,T1)+2: the history samples it had to
+ * read (4 bytes each) -- the comb term of the frame kernel's algorithmic bytes. */
+int opn_batch_history_samples(opn_batch *b, uint64_t *out, int reset);
 void *opn_batch_cuda_stream(opn_batch *b);
-/* The library runs its stages on several internal streams.  opn_batch_join makes everything enqueued so far
- * an ancestor of whatever is enqueued next on opn_batch_cuda_stream (e.g. the caller's end-of-region event or
- * a consumer kernel reading the PCM ring); it does not block the host. */
+/* The library runs the range decode on internal streams, but every step ends with its frame kernel on
+ * opn_batch_cuda_stream: whatever the caller enqueues there next (an end-of-region event, a consumer kernel reading
+ * the PCM ring) is ordered after everything submitted so far.  opn_batch_join is kept for callers written against
+ * earlier versions and does nothing. */
 int opn_batch_join(opn_batch *b);
 
 /* ---- operator-level entry points (host pointers in/out; mirror the pub(crate) operators) */
@@ -147,7 +161,8 @@ int opn_batch_join(opn_batch *b);
  * src/range_coder/decoder.rs:50-355; decode_pulses, src/celt/pvc.rs:156-160. */
 enum { OPN_OP_UINT = 0, OPN_OP_BITS = 1, OPN_OP_BIT_LOGP = 2, OPN_OP_ICDF = 3, OPN_OP_LAPLACE = 4,
        OPN_OP_BIT_VIA_DECODE = 5, OPN_OP_BIT_VIA_DECODE_BIN = 6, OPN_OP_PULSES = 7,
-       OPN_OP_SHRINK = 8, OPN_OP_TELL = 9 };
+       OPN_OP_SHRINK = 8, OPN_OP_TELL = 9,
+       OPN_OP_PULSES_EVENTS = 10 /* decode_pulses through the product path's cwrsi (event walk, csrc/symbols.cuh) */ };
 typedef struct { uint32_t op, a, b; } opn_op;
 typedef struct { uint32_t value, tell_frac, rng; } opn_op_out;
 /* n_packets packets share one script.  out: [n_packets][n_ops]; y_out: [n_packets][y_stride]. */

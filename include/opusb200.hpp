@@ -73,9 +73,12 @@ inline int check(int rc)
 // Decoder, src/decoder.rs:54-232.  One call at a time per object (Rust: &mut self).
 class Decoder {
 public:
-    explicit Decoder(const DecoderConfiguration &cfg = DecoderConfiguration(), int device = 0) : cfg_(cfg)  // Decoder::new, :61
+    // Decoder::new, :61.  `bitstream`: OPN_BITSTREAM_OPUS (CELT frames are Unimplemented, as in the crate) or the explicit
+    // opt-in OPN_BITSTREAM_SYNTH_CELT_1 (synthetic frame layout, not Opus-interoperable; see opusb200.h).
+    explicit Decoder(const DecoderConfiguration &cfg = DecoderConfiguration(), int device = 0, int32_t bitstream = OPN_BITSTREAM_OPUS)
+        : cfg_(cfg)
     {
-        check(opn_decoder_create(device, (int32_t)cfg.sampling_rate, (int32_t)cfg.channels, cfg.gain, &raw_));
+        check(opn_decoder_create(device, (int32_t)cfg.sampling_rate, (int32_t)cfg.channels, cfg.gain, bitstream, &raw_));
     }
     ~Decoder() { opn_decoder_destroy(raw_); }
     Decoder(const Decoder &) = delete;  // Clone (decoder.rs:53) would be a device-to-device copy of the stream slot
@@ -111,10 +114,11 @@ private:
 // n independent streams on one GPU; per stream the semantics of Decoder::decode_float.
 class BatchDecoder {
 public:
-    BatchDecoder(uint32_t n_streams, const DecoderConfiguration &cfg = DecoderConfiguration(), int device = 0, bool postfilter = true)
+    BatchDecoder(uint32_t n_streams, const DecoderConfiguration &cfg = DecoderConfiguration(), int device = 0, bool postfilter = true,
+                 int32_t bitstream = OPN_BITSTREAM_OPUS)
         : n_(n_streams), channels_((int)cfg.channels)
     {
-        opn_config c{(int32_t)cfg.sampling_rate, (int32_t)cfg.channels, cfg.gain, (int16_t)(postfilter ? 1 : 0)};
+        opn_config c{(int32_t)cfg.sampling_rate, (int32_t)cfg.channels, cfg.gain, (int16_t)(postfilter ? 1 : 0), bitstream};
         check(opn_batch_create(device, n_streams, &c, &raw_));
     }
     ~BatchDecoder() { opn_batch_destroy(raw_); }

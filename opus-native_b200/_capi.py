@@ -9,8 +9,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libopusb200.so")
 
-OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL = range(10)
+OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL, OP_PULSES_EVENTS = range(11)
 FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY = 1, 2, 4, 8
+# OPN_BITSTREAM_*: CELT frames are Unimplemented (as in the crate, whose CeltDecoder::decode is todo!()) unless the caller
+# opts in to the synthetic SYNTH-CELT/1 frame layout (not Opus-interoperable)
+BITSTREAM_OPUS, BITSTREAM_SYNTH_CELT_1 = 0, 1
 # OPN_SAMPLE_*: the types the crate implements `Sample` for (lib.rs:63-107)
 SAMPLE_F32, SAMPLE_I16, SAMPLE_I32, SAMPLE_U16, SAMPLE_U32, SAMPLE_F64 = 0, 1, 2, 3, 4, 5
 SAMPLE_FORMAT_OF = {np.dtype(np.float32): SAMPLE_F32, np.dtype(np.int16): SAMPLE_I16, np.dtype(np.int32): SAMPLE_I32,
@@ -76,7 +79,7 @@ def lib():
     sig("opn_packet_sample_count", C.c_int, u8p, sz, i32)
     sig("opn_packet_mode", C.c_int, u8p)
     sig("opn_parse_packet", C.c_int, u8p, sz, C.c_int, vp, vp, C.POINTER(u32), C.POINTER(u32))
-    sig("opn_decoder_create", C.c_int, C.c_int, i32, i32, C.c_int16, C.POINTER(vp))
+    sig("opn_decoder_create", C.c_int, C.c_int, i32, i32, C.c_int16, i32, C.POINTER(vp))
     sig("opn_decoder_destroy", None, vp)
     sig("opn_decoder_reset", C.c_int, vp)
     sig("opn_decode_float", C.c_int, vp, u8p, sz, vp, sz, C.c_int)
@@ -99,6 +102,7 @@ def lib():
     sig("opn_batch_decode_i16", C.c_int, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t, vp, C.c_uint32)
     sig("opn_batch_decode_pcm", C.c_int, vp, vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_size_t, vp, C.c_uint32)
     sig("opn_batch_join", C.c_int, vp)
+    sig("opn_batch_history_samples", C.c_int, vp, C.POINTER(C.c_uint64), C.c_int)
     sig("opn_op_bitexact_trig", C.c_int, C.c_int, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32)
     sig("opn_batch_cuda_stream", vp, vp)
     sig("opn_op_rangedec_script", C.c_int, C.c_int, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp, u32)
@@ -180,10 +184,10 @@ class DecoderConfiguration:
 class Decoder:
     """`Decoder` of the reference crate: one stream, packets in order, `None` = lost packet."""
 
-    def __init__(self, configuration: DecoderConfiguration = None, device: int = 0):
+    def __init__(self, configuration: DecoderConfiguration = None, device: int = 0, bitstream: int = BITSTREAM_OPUS):
         cfg = configuration or DecoderConfiguration()
         h = C.c_void_p()
-        _chk(lib().opn_decoder_create(device, cfg.sampling_rate, cfg.channels, cfg.gain, C.byref(h)))
+        _chk(lib().opn_decoder_create(device, cfg.sampling_rate, cfg.channels, cfg.gain, bitstream, C.byref(h)))
         self._h, self._cfg = h, cfg
 
     def __del__(self):
@@ -237,15 +241,16 @@ class Decoder:
 
 
 class _Config(C.Structure):
-    _fields_ = [("fs_hz", C.c_int32), ("channels", C.c_int32), ("gain_q8", C.c_int16), ("postfilter", C.c_int16)]
+    _fields_ = [("fs_hz", C.c_int32), ("channels", C.c_int32), ("gain_q8", C.c_int16), ("postfilter", C.c_int16), ("bitstream", C.c_int32)]
 
 
 class BatchDecoder:
     """Batch-of-streams entry point: n independent `Decoder`s advanced by one call per step."""
 
-    def __init__(self, n_streams: int, configuration: DecoderConfiguration = None, device: int = 0, postfilter: bool = True):
+    def __init__(self, n_streams: int, configuration: DecoderConfiguration = None, device: int = 0, postfilter: bool = True,
+                 bitstream: int = BITSTREAM_OPUS):
         cfg = configuration or DecoderConfiguration()
-        c = _Config(cfg.sampling_rate, cfg.channels, cfg.gain, int(postfilter))
+        c = _Config(cfg.sampling_rate, cfg.channels, cfg.gain, int(postfilter), bitstream)
         h = C.c_void_p()
         _chk(lib().opn_batch_create(device, n_streams, C.byref(c), C.byref(h)))
         self._h, self.n_streams, self.channels, self.device = h, n_streams, cfg.channels, device
@@ -331,6 +336,12 @@ class BatchDecoder:
         ms = (C.c_double * 3)()
         _chk(lib().opn_batch_stats(self._h, launches, ms, int(reset)))
         return {"launches": list(launches), "ms": list(ms)}
+
+    def history_samples(self, reset=False):
+        """Comb history samples (summed over channel-frames) the frame kernel read in timed passes."""
+        v = C.c_uint64(0)
+        _chk(lib().opn_batch_history_samples(self._h, C.byref(v), int(reset)))
+        return v.value
 
     @property
     def cuda_stream(self):

@@ -1,0 +1,375 @@
+// frame_warp.cuh -- the frame kernel: one WARP turns one stream's decoded symbols into PCM.
+//
+//   codeword indices --w_expand--> coefficient rows (shared memory) --w_imdct--> out[0 .. nf+60) (same rows)
+//   --w_comb_ring--> post-filtered frame (same rows) --> interleaved float4 PCM in the ring (+ dense rows)
+//
+// Nothing between the range decoder's 288 bytes of indices and the PCM leaves the SM: the coefficient rows are
+// produced in the very shared-memory rows Mdct::backward transforms in place, and the pitch comb post-filter
+// (comb_filter_inplace, src/celt/comb_filter/mod.rs:130-193, scalar kernel fallback.rs:32-53) runs on those rows
+// before the only PCM store.  The post-filter's history -- the previous max(T0,T1)+2 output samples -- is the PCM ring
+// itself: taps that fall before the frame are read from the ring through L1/L2 (one float2 = both channels of a
+// sample), taps inside the frame from the rows.  Shared memory per stream: C rows of nf+60 floats and one mbarrier
+// (8 KB for a stereo 20 ms frame), as for the IMDCT alone.
+//
+// A variant of the same kernel (EXPAND = false) takes its coefficient rows from global memory by TMA instead
+// (unfused pipeline, kept for measurements).
+#pragma once
+#include "imdct_warp.cuh"
+#include "symbols.cuh"
+
+namespace opn {
+
+// ---- post-filter -------------------------------------------------------------------------------
+// comb_filter_const_inplace term order (fallback.rs:46-51): y + g0*x2 + g1*(x1+x3) + g2*(x0+x4)
+__device__ __forceinline__ float comb5(float y, float x0, float x1, float x2, float x3, float x4, float g0, float g1, float g2)
+{
+    return y + (g0 * x2) + (g1 * (x1 + x3)) + (g2 * (x0 + x4));
+}
+
+// One sample of the C channels of a stream.
+template <int C> struct WSmp;
+template <> struct WSmp<1> {
+    float a;
+    __device__ __forceinline__ static WSmp ld(const float *p) { return WSmp{*p}; }  // interleaved layout (the PCM ring)
+};
+template <> struct WSmp<2> {
+    float a, b;
+    __device__ __forceinline__ static WSmp ld(const float *p)
+    {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        return WSmp{v.x, v.y};
+    }
+};
+template <int C>
+__device__ __forceinline__ WSmp<C> w_comb5(WSmp<C> y, WSmp<C> x0, WSmp<C> x1, WSmp<C> x2, WSmp<C> x3, WSmp<C> x4, float g0, float g1,
+                                           float g2)
+{
+    WSmp<C> r;
+    r.a = comb5(y.a, x0.a, x1.a, x2.a, x3.a, x4.a, g0, g1, g2);
+    if constexpr (C == 2) r.b = comb5(y.b, x0.b, x1.b, x2.b, x3.b, x4.b, g0, g1, g2);
+    return r;
+}
+// cross-fade accumulation order of comb_filter_inplace (mod.rs:166-177); a* = y[i-t0-2 .. i-t0+2],
+// b* = y[i-t1-2 .. i-t1+2]
+__device__ __forceinline__ float xfade1(float y, float a0, float a1, float a2, float a3, float a4, float b0, float b1, float b2, float b3,
+                                        float b4, bool has0, bool has1, float f, float g00, float g01, float g02, float g10, float g11,
+                                        float g12)
+{
+    float v = y;
+    if (has0) {
+        v = v + (((1.0f - f) * g00) * a2);
+        v = v + (((1.0f - f) * g01) * (a3 + a1));
+        v = v + (((1.0f - f) * g02) * (a4 + a0));
+    }
+    if (has1) {
+        v = v + ((f * g10) * b2);
+        v = v + ((f * g11) * (b3 + b1));
+        v = v + ((f * g12) * (b4 + b0));
+    }
+    return v;
+}
+template <int C>
+__device__ __forceinline__ WSmp<C> w_xfade(WSmp<C> y, const WSmp<C> *a, const WSmp<C> *b, bool has0, bool has1, float f, float g00,
+                                           float g01, float g02, float g10, float g11, float g12)
+{
+    WSmp<C> r;
+    r.a = xfade1(y.a, a[0].a, a[1].a, a[2].a, a[3].a, a[4].a, b[0].a, b[1].a, b[2].a, b[3].a, b[4].a, has0, has1, f, g00, g01, g02, g10,
+                 g11, g12);
+    if constexpr (C == 2)
+        r.b = xfade1(y.b, a[0].b, a[1].b, a[2].b, a[3].b, a[4].b, b[0].b, b[1].b, b[2].b, b[3].b, b[4].b, has0, has1, f, g00, g01, g02,
+                     g10, g11, g12);
+    return r;
+}
+
+// tap gains of the old and the new filter (comb_filter/mod.rs:45-55, 146-151)
+struct CombGains {
+    float g00, g01, g02, g10, g11, g12;
+};
+__device__ __forceinline__ CombGains w_comb_gains(float g0, float g1, int tap0, int tap1)
+{
+    CombGains k;
+    k.g00 = g0 * g_tab.comb_gains[tap0 * 3];
+    k.g01 = g0 * g_tab.comb_gains[tap0 * 3 + 1];
+    k.g02 = g0 * g_tab.comb_gains[tap0 * 3 + 2];
+    k.g10 = g1 * g_tab.comb_gains[tap1 * 3];
+    k.g11 = g1 * g_tab.comb_gains[tap1 * 3 + 1];
+    k.g12 = g1 * g_tab.comb_gains[tap1 * 3 + 2];
+    return k;
+}
+
+// Where the samples of one stream live while its frame is filtered: sample i >= 0 of channel c is rows[c*CHF + i]
+// (shared memory, planar), sample i < 0 (history) is ring[((pos + i) mod RING_SAMPLES)*C + c] (global memory, interleaved).
+template <int C, int CHF> struct FrameView {
+    using S = WSmp<C>;
+    float *rows;
+    const float *ring;
+    int pos;  // ring position of sample 0
+    __device__ __forceinline__ S ld_row(int i) const
+    {
+        S r;
+        r.a = rows[i];
+        if constexpr (C == 2) r.b = rows[CHF + i];
+        return r;
+    }
+    __device__ __forceinline__ void st_row(int i, S v) const
+    {
+        rows[i] = v.a;
+        if constexpr (C == 2) rows[CHF + i] = v.b;
+    }
+    __device__ __forceinline__ S ld_hist(int i) const
+    {
+        int j = pos + i;
+        if (j < 0) j += RING_SAMPLES;
+        return S::ld(ring + (size_t)j * C);
+    }
+    __device__ __forceinline__ S ld(int i) const { return i >= 0 ? ld_row(i) : ld_hist(i); }
+};
+
+// comb_filter_inplace (comb_filter/mod.rs:130-193) on the frame in V.  The filter is recursive, y[i] depends on the
+// already filtered y[i-T-2 .. i-T+2]; samples whose taps all lie before the span being processed are independent and are
+// filtered in parallel, one per lane, consecutive lanes on consecutive samples (conflict-free in shared memory,
+// coalesced in the ring); the frame is swept in spans no longer than T-2.  A tap set whose gain is exactly zero
+// contributes +-0 to every sum and is skipped.
+template <int C, int CHF>
+__device__ __forceinline__ void w_comb_ring(const FrameView<C, CHF> &V, int t0, int t1, int n, float g0, float g1, int tap0, int tap1,
+                                            int overlap, int lane, const float *win_sq, const CombGains &kg)
+{
+    using S = WSmp<C>;
+    if (g0 == 0.0f && g1 == 0.0f) return;
+    t0 = max(t0, 15);
+    t1 = max(t1, 15);
+    const float g00 = kg.g00, g01 = kg.g01, g02 = kg.g02, g10 = kg.g10, g11 = kg.g11, g12 = kg.g12;
+    if (fabsf(g0 - g1) < 1.1920929e-7f && t0 == t1 && tap0 == tap1) overlap = 0;
+    const bool has0 = g0 != 0.0f, has1 = g1 != 0.0f;
+
+    // ---- cross-fade part (mod.rs:162-179): samples [0, overlap), spans of min(T)-2 (at most 32) samples
+    if (overlap > 0) {
+        const int tmin = min(has0 ? t0 : 1 << 20, has1 ? t1 : 1 << 20);
+        const int W = min(tmin - 2, 32);
+        for (int base = 0; base < overlap; base += W) {
+            const int i = base + lane;
+            if (lane < W && i < overlap) {
+                const float f = __ldg(win_sq + i);
+                S a[5], b[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    a[k] = has0 ? V.ld(i - t0 - 2 + k) : S{};
+                    b[k] = has1 ? V.ld(i - t1 - 2 + k) : S{};
+                }
+                V.st_row(i, w_xfade<C>(V.ld_row(i), a, b, has0, has1, f, g00, g01, g02, g10, g11, g12));
+            }
+            __syncwarp();
+        }
+    }
+    if (!has1) return;
+
+    // ---- constant part (fallback.rs:32-53): samples [overlap, n)
+    // (1) [overlap, hend): every tap is history -> no recursion, 128 samples per step straight from the ring
+    int at = overlap;
+    {
+        const int hend = max(at, min(n, t1 - 2));
+        for (int base = at; base < hend; base += 128) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int i = base + lane + 32 * e;
+                if (i < hend) {
+                    const int p = i - t1;
+                    V.st_row(i, w_comb5<C>(V.ld_row(i), V.ld_hist(p + 2), V.ld_hist(p + 1), V.ld_hist(p), V.ld_hist(p - 1), V.ld_hist(p - 2),
+                                           g10, g11, g12));
+                }
+            }
+        }
+        at = hend;
+        __syncwarp();
+    }
+    // (2) recursive remainder [at, n): spans of min(T1-2, 128) samples; inside a span every tap lies before the span.
+    //     Only the first span can still reach below the frame start.
+    const int W2 = min(t1 - 2, 128);
+    const int rounds = (W2 + 31) >> 5;
+    for (int base = at; base < n; base += W2) {
+        const bool mixed = base - t1 - 2 < 0;
+        for (int e = 0; e < rounds; e++) {
+            const int l = lane + 32 * e, i = base + l;
+            if (l < W2 && i < n) {
+                const int p = i - t1;
+                if (mixed)
+                    V.st_row(i, w_comb5<C>(V.ld_row(i), V.ld(p + 2), V.ld(p + 1), V.ld(p), V.ld(p - 1), V.ld(p - 2), g10, g11, g12));
+                else
+                    V.st_row(i, w_comb5<C>(V.ld_row(i), V.ld_row(p + 2), V.ld_row(p + 1), V.ld_row(p), V.ld_row(p - 1), V.ld_row(p - 2), g10,
+                                           g11, g12));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// The frame kernel: one warp = one CTA = one stream (item).
+template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32, W_K1_MIN_CTAS) k_frame_w(FrameArgs A)
+{
+    extern __shared__ __align__(16) float o[];
+    constexpr int NF = 120 << LM;
+    constexpr int CHF = w_ch_floats(LM);
+    const int lane = threadIdx.x;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);
+
+    const uint32_t item = blockIdx.x;
+    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    if constexpr (!EXPAND) {
+        // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, C * NF * 4);
+#pragma unroll
+            for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
+        }
+    }
+    // What the transform needs is loaded now; the post-filter state (previous parameters, ring position) is only
+    // prefetched into L1 and read after the transform, so that it does not occupy registers across it.
+    const int32_t status = A.status[stream];
+    const uint32_t hdr_x = A.hdr[stream].x;
+    prefetch_l1(A.pf + stream);
+    prefetch_l1(A.ring_pos + stream);
+    float *carry_g = A.carry + (size_t)stream * C * 60;
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
+    if constexpr (EXPAND) {
+        // the coefficient rows start out zero: w_expand only writes the pulses
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            for (int i = lane; i < NF / 4; i += 32) reinterpret_cast<float4 *>(o + c * CHF)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if (status < 0) {  // rejected packet: state untouched (decoder.rs:397)
+        if (lane == 0 && A.result) A.result[stream] = status;
+        if constexpr (!EXPAND) mbar_wait(bar, 0);  // the rows are in flight: do not retire the CTA under them
+        return;
+    }
+    const bool lost = status == ITEM_LOST;
+    if constexpr (EXPAND) {
+        if (!lost && !(hdr_x & 1u)) {  // not silence
+            const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, g_tab.synth_entries[LM][C - 1]};
+            w_expand<C>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(bar, 0);
+    }
+    if constexpr (LM > 0) {
+        if ((hdr_x >> 2) & 1u) w_imdct<3, (1 << LM), C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
+        else w_imdct<3 - LM, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3 - LM), g_tab.twiddles, g_tab.window);
+    } else {
+        w_imdct<3, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
+    }
+
+    // post-filter parameters: previous frame -> this frame
+    const uint4 hdr = A.hdr[stream];
+    const PfState old = A.pf[stream];
+    const uint32_t pos = A.ring_pos[stream];
+    const int s_on = (hdr.x >> 1) & 1u, s_tapset = (hdr.x >> 4) & 15u, s_gain = (hdr.x >> 8) & 15u, s_period = hdr.x >> 16;
+    int t1 = old.period, tap1 = old.tapset;
+    float g1 = old.gain;
+    if (!lost) {
+        t1 = s_on ? s_period : 0;
+        g1 = s_on ? 0.09375f * (float)(s_gain + 1) : 0.0f;
+        tap1 = s_on ? s_tapset : 0;
+    }
+    const bool comb_on = A.postfilter && (old.gain != 0.0f || g1 != 0.0f);
+    float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
+
+    // tail of this frame -> carry
+    if (lane < 15 * C) {
+        const int ch = (C == 2 && lane >= 15) ? 1 : 0;
+        *reinterpret_cast<float4 *>(carry_g + 4 * lane) = *reinterpret_cast<const float4 *>(o + ch * CHF + NF + 4 * (lane - 15 * ch));
+    }
+    // pitch comb post-filter, previous parameters -> this frame's over the first 120 samples
+    if (comb_on) {
+        const FrameView<C, CHF> V{o, ring, (int)pos};
+        w_comb_ring<C, CHF>(V, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane, g_tab.window_sq,
+                            w_comb_gains(old.gain, g1, old.tapset, tap1));
+        __syncwarp();
+        if (A.hist_samples && lane == 0) atomicAdd(A.hist_samples, (unsigned long long)(C * (max(max(old.period, t1), 15) + 2)));
+    }
+    // interleaved PCM -> ring (history of the next frames + device-resident output) and dense rows (host-path output).
+    // The frame is contiguous in the ring except when it wraps (pos is a multiple of 120).
+    const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
+    float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
+    const float gain = A.gain;
+    constexpr int VEC = C == 2 ? NF / 2 : NF / 4;         // float4 per frame
+    constexpr int SPV = C == 2 ? 2 : 4;                   // samples per float4
+    const int wrap_at = (int)(RING_SAMPLES - pos) / SPV;  // first float4 that lands at the ring start
+    float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)pos * C);
+    float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
+#pragma unroll
+    for (int i = lane; i < VEC; i += 32) {
+        float4 v;
+        if (C == 2) {
+            const float2 a = *reinterpret_cast<const float2 *>(o + 2 * i), b = *reinterpret_cast<const float2 *>(o + CHF + 2 * i);
+            v = make_float4(a.x, b.x, a.y, b.y);
+        } else {
+            v = *reinterpret_cast<const float4 *>(o + 4 * i);
+        }
+        (i < wrap_at ? r0 : r1)[i] = v;
+        if (dense) {
+            if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
+            reinterpret_cast<float4 *>(dense)[i] = v;
+        }
+    }
+    if (lane == 0) {
+        uint32_t np = pos + (uint32_t)NF;
+        if (np >= RING_SAMPLES) np -= RING_SAMPLES;
+        A.ring_pos[stream] = np;
+        PfState nw;
+        nw.period = t1;
+        nw.tapset = tap1;
+        nw.gain = g1;
+        nw.pad = 0;
+        A.pf[stream] = nw;
+        if (A.result) A.result[stream] = NF;
+        if (A.final_range) A.final_range[stream] = lost ? 0u : hdr.y;
+        if (A.softclip_reset && !lost) *reinterpret_cast<float2 *>(A.softclip_reset + 2 * (size_t)stream) = make_float2(0.f, 0.f);
+    }
+}
+
+// Operator-level Mdct::backward on independent rows (tests; opn_op_imdct_tdac): one warp per row.
+template <int SHIFT, int NBLK>
+__global__ void __launch_bounds__(32)
+k_op_imdct_w(const float *__restrict__ input, size_t in_stride, float *__restrict__ output, size_t out_stride)
+{
+    extern __shared__ __align__(16) float sm[];
+    constexpr int N2 = 960 >> SHIFT, NF = N2 * NBLK;
+    const int lane = threadIdx.x;
+    const float *in = input + (size_t)blockIdx.x * in_stride;
+    float *out = output + (size_t)blockIdx.x * out_stride;
+    for (int i = lane; i < NF; i += 32) sm[i] = in[i];
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 15) carry = make_float4(out[4 * lane], out[4 * lane + 1], out[4 * lane + 2], out[4 * lane + 3]);
+    __syncwarp();
+    w_imdct<SHIFT, NBLK, 1>(sm, lane, carry, g_tab.trig_pair + trig_pair_off(SHIFT), g_tab.twiddles, g_tab.window);
+    for (int i = lane; i < NF + 60; i += 32) out[i] = sm[i];
+}
+
+// Operator-level comb_filter_inplace on rows (tests; opn_op_comb_filter_inplace): one warp per row runs the frame
+// kernel's w_comb_ring; the n samples from y_offset on are the frame (shared memory), the row's own prefix in global
+// memory plays the role of the PCM ring (history).
+__global__ void __launch_bounds__(32)
+k_op_comb_inplace_w(float *__restrict__ y, size_t row_stride, int y_offset, int n, const int32_t *__restrict__ params4,
+                    const float *__restrict__ gains2, int overlap)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x;
+    float *row = y + (size_t)blockIdx.x * row_stride;
+    const int t0 = params4[4 * blockIdx.x], t1 = params4[4 * blockIdx.x + 1];
+    const int tap0 = params4[4 * blockIdx.x + 2], tap1 = params4[4 * blockIdx.x + 3];
+    const float g0 = gains2[2 * blockIdx.x], g1 = gains2[2 * blockIdx.x + 1];
+    for (int i = lane; i < n; i += 32) sm[i] = row[y_offset + i];
+    __syncwarp();
+    const FrameView<1, 0> V{sm, row, y_offset};  // max(t0, t1) + 2 <= y_offset (checked by the caller): the view never wraps
+    w_comb_ring<1, 0>(V, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq, w_comb_gains(g0, g1, tap0, tap1));
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) row[y_offset + i] = sm[i];
+}
+
+}  // namespace opn

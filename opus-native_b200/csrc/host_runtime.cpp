@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -115,11 +116,11 @@ struct opn_batch {
     opn_config cfg{};
     float gain = 1.0f;
     cudaStream_t stream = nullptr;
-    // The entropy stage (k_synth_rangedec: one lane per packet, latency-bound, a few hundred warps)
-    // runs on its own streams and may run up to NSETS-1 steps ahead of the PVQ/IMDCT stage: its outputs
-    // live in NSETS buffer sets handed over with events.  Under load one range decode takes several step times (its
-    // warps share the schedulers with everything else), so the number in flight bounds the step: 6 sets / 4
-    // streams 52.8 us per 4096-stream step, 8 / 8 45.5 us, 12 / 6, 12 / 12 and 16 / 16 no better (46-47 us).
+    // One step = two launches: the range decode (k_synth_rangedec: one lane per packet, a latency-bound serial chain on a
+    // few hundred warps) and the frame kernel (k_frame_w: PVQ expansion + IMDCT + post-filter + PCM store, one warp per
+    // stream).  The range decode runs on its own streams and may run up to NSETS-1 steps ahead of the frame kernel: its
+    // outputs (frame header, status, codeword indices: 308 bytes per stream) live in NSETS buffer sets handed over with
+    // events.
 #ifndef OPN_NSETS
 #define OPN_NSETS 8
 #endif
@@ -128,24 +129,22 @@ struct opn_batch {
 #endif
     static constexpr int NSETS = OPN_NSETS, NRD = OPN_NRD;
     cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: entropy stages of NRD steps overlap each other
-    cudaStream_t stream_ex = nullptr;     // PVQ expansion: between the entropy streams and `stream`
-    cudaStream_t stream_k2 = nullptr;     // kernel 2 (post-filter): one step behind kernel 1 on `stream`
-    cudaEvent_t ev_k1[NSETS] = {};        // kernel 1 of set p finished
-    cudaEvent_t ev_k2[NSETS] = {};        // kernel 2 of set p finished (recorded on `stream` when there is no kernel 2)
-    bool k2_recorded[NSETS] = {};
+    cudaStream_t stream_ex = nullptr;     // unfused variant only: stand-alone PVQ expansion between the entropy streams and `stream`
+    cudaEvent_t ev_k1[NSETS] = {};        // frame kernel of set p finished: the set is free again
+    bool k1_recorded[NSETS] = {};
     cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
-    cudaEvent_t ev_ex[NSETS] = {};        // PVQ expansion of set p finished (coefficients ready)
+    cudaEvent_t ev_ex[NSETS] = {};        // unfused variant: coefficients of set p ready
     cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` / `stream_up` are complete
     static constexpr int MAX_CHUNKS = 8;
     cudaStream_t stream_up = nullptr, stream_dn = nullptr;  // host path: item/packet upload, PCM download
-    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};                  // PVQ/IMDCT stage of a chunk finished
-    int set = 0, last_set = -1;
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};                  // frame kernels (and epilogue) of a chunk finished
+    int set = 0;
+    bool unfused = false;  // OPN_UNFUSED_EXPAND=1 in the environment at creation: expansion as its own kernel, coefficient rows through HBM
     // per-stream state (device, SoA)
     float *d_carry = nullptr, *d_ring = nullptr, *d_coef[NSETS] = {};
     uint32_t *d_ring_pos = nullptr, *d_final = nullptr, *d_idx[NSETS] = {};
     PfState *d_pf = nullptr;
-    CombJob *d_job[NSETS] = {};
-    opn_synth_side *d_side[NSETS] = {};
+    uint4 *d_hdr[NSETS] = {};
     int32_t *d_status[NSETS] = {};
     // host-path staging (device + pinned host)
     // Two staging slots, so a host-buffer call can be submitted while the previous one is still downloading.
@@ -164,6 +163,7 @@ struct opn_batch {
     } stg[2];
     int stg_next = 0;
     float *d_softclip = nullptr;
+    unsigned long long *d_hist_samples = nullptr;  // measurement: history samples the post-filter needed (timed passes only)
     // host mirrors of DecoderInner fields (decoder.rs:236-258), per stream
     std::vector<int32_t> last_nf, bandwidth, last_duration, have_mode;
     // measurement
@@ -228,16 +228,27 @@ int timed_launch(opn_batch *b, int kind, cudaError_t (*fn)(opn_batch *, const vo
     return OPN_OK;
 }
 
-cudaError_t do_symbols(opn_batch *b, const void *a) { return launch_synth_symbols(*static_cast<const SymbolArgs *>(a), b->stream); }
-cudaError_t do_imdct(opn_batch *b, const void *a) { return launch_imdct_post(*static_cast<const ImdctArgs *>(a), b->stream); }
-cudaError_t do_comb(opn_batch *b, const void *a) { return launch_comb_post(*static_cast<const ImdctArgs *>(a), b->stream); }
+cudaError_t do_rangedec(opn_batch *b, const void *a) { return launch_synth_rangedec(*static_cast<const SymbolArgs *>(a), b->stream); }
+cudaError_t do_expand(opn_batch *b, const void *a) { return launch_synth_expand(*static_cast<const SymbolArgs *>(a), b->stream); }
+cudaError_t do_frame(opn_batch *b, const void *a) { return launch_frame(*static_cast<const FrameArgs *>(a), b->stream); }
+
+int sync_pipeline(opn_batch *b)
+{
+    for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
+    CU(cudaStreamSynchronize(b->stream_ex));
+    CU(cudaStreamSynchronize(b->stream_up));
+    CU(cudaStreamSynchronize(b->stream));
+    CU(cudaStreamSynchronize(b->stream_dn));
+    return OPN_OK;
+}
 
 // One bucket = items of equal frame size that may run concurrently.
 // inputs_on: 0 = the packets are already complete in device memory (the entropy stage may start at once),
 //            1 = they are ordered on b->stream, 2 = they are ordered on b->stream_up (host path).
+// softclip_reset: a float call clears the soft-clip memory of every stream that decodes a packet (decoder.rs:420-423).
 int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens,
                const uint32_t *d_stream_idx, const uint32_t *d_dense_off, uint32_t n_items, int lm, int has_toc,
-               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on)
+               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
 {
     const int p = b->set;
     b->set = (p + 1) % opn_batch::NSETS;
@@ -251,9 +262,10 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.lm = lm;
     s.channels = b->cfg.channels;
     s.has_toc = has_toc;
-    s.side = b->d_side[p];
+    s.side = nullptr;
+    s.hdr = b->d_hdr[p];
     s.status = b->d_status[p];
-    s.coef = b->d_coef[p];
+    s.coef = b->unfused ? b->d_coef[p] : nullptr;
     s.y_out = nullptr;
     s.idx = b->d_idx[p];
     s.pkt_cap = pkt_cap;
@@ -264,9 +276,12 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
             CU(cudaEventRecord(b->ev_in, b->stream_up));
             CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
         }
-        rc = timed_launch(b, 0, do_symbols, &s);
+        rc = timed_launch(b, 0, do_rangedec, &s);
         if (rc) return rc;
-        b->launches[0] += 1;  // stage 0 is two launches: k_synth_rangedec + k_synth_expand
+        if (b->unfused) {
+            rc = timed_launch(b, 2, do_expand, &s);
+            if (rc) return rc;
+        }
     } else {
         if (inputs_on == 1) {
             CU(cudaEventRecord(b->ev_in, b->stream));
@@ -275,20 +290,24 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
             CU(cudaEventRecord(b->ev_in, b->stream_up));
             CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
         }
-        if (b->k2_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_k2[p], 0));  // set p is free again
-        // three stages in flight at once: range decode of step n+2 (latency-bound, a few hundred warps), PVQ
-        // expansion of step n+1 (integer issue-bound) and IMDCT/post-filter of step n (FP32 / memory)
+        if (b->k1_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_k1[p], 0));  // set p is free again
         CU(launch_synth_rangedec(s, srd));
         CU(cudaEventRecord(b->ev_rd[p], srd));
-        CU(cudaStreamWaitEvent(b->stream_ex, b->ev_rd[p], 0));
-        CU(launch_synth_expand(s, b->stream_ex));
-        CU(cudaEventRecord(b->ev_ex[p], b->stream_ex));
-        CU(cudaStreamWaitEvent(b->stream, b->ev_ex[p], 0));
-        b->launches[0] += 2;
+        b->launches[0]++;
+        if (b->unfused) {
+            CU(cudaStreamWaitEvent(b->stream_ex, b->ev_rd[p], 0));
+            CU(launch_synth_expand(s, b->stream_ex));
+            CU(cudaEventRecord(b->ev_ex[p], b->stream_ex));
+            CU(cudaStreamWaitEvent(b->stream, b->ev_ex[p], 0));
+            b->launches[2]++;
+        } else {
+            CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
+        }
     }
-    ImdctArgs m{};
-    m.coef = b->d_coef[p];
-    m.side = b->d_side[p];
+    FrameArgs m{};
+    m.coef = b->unfused ? b->d_coef[p] : nullptr;
+    m.idx = b->d_idx[p];
+    m.hdr = b->d_hdr[p];
     m.status = b->d_status[p];
     m.stream_idx = d_stream_idx;
     m.dense_off = d_dense_off;
@@ -305,36 +324,17 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.gain = b->gain;
     m.result = d_result;
     m.final_range = b->d_final;
-    m.job = b->d_job[p];
+    m.softclip_reset = softclip_reset ? b->d_softclip : nullptr;
+    m.hist_samples = b->timing ? b->d_hist_samples : nullptr;
     if (b->timing) {
-        rc = timed_launch(b, 1, do_imdct, &m);
+        rc = timed_launch(b, 1, do_frame, &m);
         if (rc) return rc;
-        if (m.postfilter) {
-            rc = timed_launch(b, 2, do_comb, &m);
-            if (rc) return rc;
-        }
-        CU(cudaEventRecord(b->ev_k2[p], b->stream));
-        b->k2_recorded[p] = true;
-        b->last_set = p;
-        return OPN_OK;
-    }
-    // Kernel 1 of this step may overlap kernel 2 of the previous step (it writes frame n+1 of the ring while
-    // the post-filter still reads frame n and up to 1024 samples before it), but not the one before that.
-    const int p2 = (p + opn_batch::NSETS - 2) % opn_batch::NSETS;
-    if (b->k2_recorded[p2]) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[p2], 0));
-    CU(launch_imdct_post(m, b->stream));
-    b->launches[1]++;
-    CU(cudaEventRecord(b->ev_k1[p], b->stream));
-    if (m.postfilter) {
-        CU(cudaStreamWaitEvent(b->stream_k2, b->ev_k1[p], 0));  // kernel 2 launches are ordered among themselves by stream_k2
-        CU(launch_comb_post(m, b->stream_k2));
-        b->launches[2]++;
-        CU(cudaEventRecord(b->ev_k2[p], b->stream_k2));
     } else {
-        CU(cudaEventRecord(b->ev_k2[p], b->stream));
+        CU(launch_frame(m, b->stream));
+        b->launches[1]++;
     }
-    b->k2_recorded[p] = true;  // also "set p is free again" for the entropy stage
-    b->last_set = p;
+    CU(cudaEventRecord(b->ev_k1[p], b->stream));
+    b->k1_recorded[p] = true;
     return OPN_OK;
 }
 
@@ -387,6 +387,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
 {
     if (!out || !cfg || n_streams == 0) return OPN_ERR_BAD_ARG;
     if (cfg->channels < 1 || cfg->channels > 2) return OPN_ERR_BAD_ARG;
+    if (cfg->bitstream != OPN_BITSTREAM_OPUS && cfg->bitstream != OPN_BITSTREAM_SYNTH_CELT_1) return OPN_ERR_BAD_ARG;
     switch (cfg->fs_hz) {
     case 48000: break;
     case 8000: case 12000: case 16000: case 24000: return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:23 "TODO ... downsample"
@@ -400,25 +401,23 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->n = n_streams;
     b->cfg = *cfg;
     b->gain = host_gain_from_q8(cfg->gain_q8);
+    const char *uf = std::getenv("OPN_UNFUSED_EXPAND");
+    b->unfused = uf && uf[0] == '1';
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-    // All pipeline streams have the same priority.  Measured (tools/experiments/priorities.sh, us per 4096-stream
-    // step, three processes each): all equal 45-46.5 and steady; entropy streams raised 45-53 with slow stretches;
-    // expansion raised 53-55; kernels 1/2 raised (drain first) 62-69.
+    // All pipeline streams have the same priority (measured in round 1, tools/experiments/priorities.sh: raising the
+    // entropy streams gave slow stretches, raising the frame stream serialised the pipeline).
     for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++) e = cudaStreamCreateWithFlags(&b->stream_rd[q], cudaStreamNonBlocking);
     for (int q = 0; q < opn_batch::NSETS && e == cudaSuccess; q++) {
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k1[q], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k2[q], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaMalloc(&b->d_job[q], n * sizeof(CombJob));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
-        if (e == cudaSuccess) e = cudaMalloc(&b->d_coef[q], n * (size_t)cfg->channels * 960 * sizeof(float));
-        if (e == cudaSuccess) e = cudaMalloc(&b->d_side[q], n * sizeof(opn_synth_side));
+        if (e == cudaSuccess && b->unfused) e = cudaMalloc(&b->d_coef[q], n * C * 960 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_hdr[q], n * sizeof(uint4));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_k2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_dn, cudaStreamNonBlocking);
@@ -429,6 +428,8 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_softclip, n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_hist_samples, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(b->d_hist_samples, 0, sizeof(unsigned long long));
     if (e != cudaSuccess) {
         opn_batch_destroy(b);
         return cuda_fail(e, "opn_batch_create: allocation");
@@ -452,37 +453,22 @@ void opn_batch_destroy(opn_batch *b)
     cudaSetDevice(b->device);
     for (int q = 0; q < opn_batch::NRD; q++)
         if (b->stream_rd[q]) cudaStreamSynchronize(b->stream_rd[q]);
-    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (cudaStream_t st : {b->stream_ex, b->stream_up, b->stream, b->stream_dn})
+        if (st) cudaStreamSynchronize(st);
     for (int q = 0; q < opn_batch::NSETS; q++) {
         if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
         if (b->ev_ex[q]) cudaEventDestroy(b->ev_ex[q]);
         if (b->ev_k1[q]) cudaEventDestroy(b->ev_k1[q]);
-        if (b->ev_k2[q]) cudaEventDestroy(b->ev_k2[q]);
-        cudaFree(b->d_job[q]);
         cudaFree(b->d_idx[q]);
         cudaFree(b->d_coef[q]);
-        cudaFree(b->d_side[q]);
+        cudaFree(b->d_hdr[q]);
         cudaFree(b->d_status[q]);
-    }
-    if (b->stream_ex) {
-        cudaStreamSynchronize(b->stream_ex);
-        cudaStreamDestroy(b->stream_ex);
-    }
-    if (b->stream_k2) {
-        cudaStreamSynchronize(b->stream_k2);
-        cudaStreamDestroy(b->stream_k2);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
     for (int q = 0; q < opn_batch::MAX_CHUNKS; q++)
         if (b->ev_chunk[q]) cudaEventDestroy(b->ev_chunk[q]);
-    if (b->stream_dn) {
-        cudaStreamSynchronize(b->stream_dn);
-        cudaStreamDestroy(b->stream_dn);
-    }
-    if (b->stream_up) {
-        cudaStreamSynchronize(b->stream_up);
-        cudaStreamDestroy(b->stream_up);
-    }
+    for (cudaStream_t st : {b->stream_ex, b->stream_up, b->stream_dn})
+        if (st) cudaStreamDestroy(st);
     for (int q = 0; q < opn_batch::NRD; q++)
         if (b->stream_rd[q]) cudaStreamDestroy(b->stream_rd[q]);
     for (int k = 0; k < 3; k++) b->ev[k].destroy();
@@ -492,6 +478,7 @@ void opn_batch_destroy(opn_batch *b)
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
     cudaFree(b->d_softclip);
+    cudaFree(b->d_hist_samples);
     for (auto &g : b->stg) {
         cudaFree(g.d_arena);
         cudaFree(g.d_items);
@@ -510,22 +497,23 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
 {
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
+    // Steps may still be in flight on any of the pipeline's streams (a frame kernel writing the ring, a range decode
+    // writing a buffer set, a download reading staging): nothing is cleared before all of them have drained.
+    int rc = sync_pipeline(b);
+    if (rc) return rc;
+    for (auto &g : b->stg) g.pending = false;
     const size_t n = b->n, C = (size_t)b->cfg.channels;
     CU(cudaMemsetAsync(b->d_carry, 0, n * C * 60 * sizeof(float), b->stream));
     CU(cudaMemsetAsync(b->d_ring, 0, n * C * RING_SAMPLES * sizeof(float), b->stream));
     CU(cudaMemsetAsync(b->d_ring_pos, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_final, 0, n * sizeof(uint32_t), b->stream));
     CU(cudaMemsetAsync(b->d_pf, 0, n * sizeof(PfState), b->stream));
-    for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
-    CU(cudaStreamSynchronize(b->stream_ex));
-    CU(cudaStreamSynchronize(b->stream_k2));
     for (int q = 0; q < opn_batch::NSETS; q++) {
-        CU(cudaMemsetAsync(b->d_side[q], 0, n * sizeof(opn_synth_side), b->stream));
+        CU(cudaMemsetAsync(b->d_hdr[q], 0, n * sizeof(uint4), b->stream));
         CU(cudaMemsetAsync(b->d_status[q], 0, n * sizeof(int32_t), b->stream));
-        b->k2_recorded[q] = false;
+        b->k1_recorded[q] = false;
     }
     b->set = 0;
-    b->last_set = -1;
     CU(cudaMemsetAsync(b->d_softclip, 0, n * 2 * sizeof(float), b->stream));
     CU(cudaStreamSynchronize(b->stream));
     std::fill(b->last_nf.begin(), b->last_nf.end(), 120);
@@ -620,9 +608,10 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 any_gap = true;
                 continue;
             }
-            if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C) {
+            if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C || b->cfg.bitstream != OPN_BITSTREAM_SYNTH_CELT_1) {
                 // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); mono<->stereo
-                // mapping lives in the stubbed CeltDecoder.
+                // mapping lives in the stubbed CeltDecoder; CeltDecoder::decode itself is todo!() (celt/decoder.rs:47-56):
+                // CELT frames decode only when the batch was created for the SYNTH-CELT/1 layout.
                 res[i] = OPN_ERR_UNIMPLEMENTED;
                 any_gap = true;
                 continue;
@@ -663,7 +652,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 size_t k1 = k0;
                 while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
                 rc = run_bucket(b, g.d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
-                                items[k0].lm, 0, pkt_cap, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2);
+                                items[k0].lm, 0, pkt_cap, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2, pcm_conv == nullptr);
                 if (rc) return rc;
                 k0 = k1;
             }
@@ -671,16 +660,15 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         }
         if (want_pcm && pcm_conv) {
             // decode::<S>: soft clip + Sample::from_f32 on the device; for the 16-bit types half the bytes go home.
-            // The epilogue kernel follows the chunk's kernels on the post-filter stream.
-            for (uint32_t i = s0; i < s1; i++) g.h_cliplen[i] = res[i];
+            // The epilogue kernel follows the chunk's frame kernels on the batch stream.  Concealed frames are not
+            // clipped and leave the soft-clip memory alone (decode_native's None branch, decoder.rs:427-441).
+            for (uint32_t i = s0; i < s1; i++) g.h_cliplen[i] = (lens[i] != 0 && res[i] > 0) ? res[i] : 0;
             CU(cudaMemcpyAsync(g.d_cliplen + s0, g.h_cliplen + s0, (size_t)(s1 - s0) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream_up));
             CU(cudaEventRecord(b->ev_in, b->stream_up));
-            CU(cudaStreamWaitEvent(b->stream_k2, b->ev_in, 0));
-            CU(cudaEventRecord(b->ev_chunk[ch], b->stream));  // kernel 1 (and the gap memset) of this chunk
-            CU(cudaStreamWaitEvent(b->stream_k2, b->ev_chunk[ch], 0));
+            CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
             CU(launch_softclip_convert(sample_format, g.d_dense, g.dense_cap, g.d_cliplen, C, (uint32_t)(frame_size * (size_t)C), s0, s1 - s0,
-                                       b->d_softclip, g.d_conv, g.conv_cap, b->stream_k2));
-            CU(cudaEventRecord(b->ev_chunk[ch], b->stream_k2));
+                                       b->d_softclip, g.d_conv, g.conv_cap, b->stream));
+            CU(cudaEventRecord(b->ev_chunk[ch], b->stream));
             CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
             const size_t row_bytes = frame_size * (size_t)C * esize;
             uint8_t *dst = static_cast<uint8_t *>(pcm_conv) + (size_t)s0 * pcm_stride * esize;
@@ -690,8 +678,6 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             else
                 CU(cudaMemcpy2DAsync(dst, pcm_stride * esize, srcp, g.conv_cap * esize, row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         } else if (want_pcm) {
-            // the chunk's last kernel 2 runs on its own stream: order the rest of this chunk after it
-            if (b->last_set >= 0 && b->k2_recorded[b->last_set]) CU(cudaStreamWaitEvent(b->stream_dn, b->ev_k2[b->last_set], 0));
             // this chunk's PCM rows go home while the next chunk is decoded
             CU(cudaEventRecord(b->ev_chunk[ch], b->stream));
             CU(cudaStreamWaitEvent(b->stream_dn, b->ev_chunk[ch], 0));
@@ -704,11 +690,9 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                                      g.dense_cap * sizeof(float), row_bytes, s1 - s0, cudaMemcpyDeviceToHost, b->stream_dn));
         }
     }
-    if (!pcm_conv) CU(cudaMemsetAsync(b->d_softclip, 0, (size_t)n * 2 * sizeof(float), b->stream));  // decoder.rs:420-423
-    // completion of this call = the batch stream, the post-filter stream and the download stream have drained
+    // completion of this call = the batch stream and the download stream have drained
     CU(cudaEventRecord(b->ev_in, b->stream));
     CU(cudaStreamWaitEvent(b->stream_dn, b->ev_in, 0));
-    if (b->last_set >= 0 && b->k2_recorded[b->last_set]) CU(cudaStreamWaitEvent(b->stream_dn, b->ev_k2[b->last_set], 0));
     CU(cudaEventRecord(g.done, b->stream_dn));
     g.pending = true;
     if (results) std::memcpy(results, res.data(), n * sizeof(int32_t));
@@ -737,12 +721,13 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
     // is validated on the device and reported per stream.  Asynchronous on the batch stream.
     const int lm = lm_of_frame(frame_size);
     if (lm < 0 || !arena) return OPN_ERR_BAD_ARG;
+    if (b->cfg.bitstream != OPN_BITSTREAM_SYNTH_CELT_1) return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:47-56 is todo!()
     float *dense = (flags & OPN_FLAG_NO_PCM_COPY) ? nullptr : pcm;
     if (dense && (pcm_stride_floats < frame_size * (size_t)C || (pcm_stride_floats & 3) ||
                   (reinterpret_cast<uintptr_t>(dense) & 15)))
         return OPN_ERR_BAD_ARG;
     return run_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, lm, 1, 1280u, dense, pcm_stride_floats, result_per_stream,
-                      (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1);
+                      (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1, true);
 }
 
 size_t opn_sample_size(int sample_format)
@@ -766,6 +751,7 @@ int opn_batch_decode_pcm(opn_batch *b, const uint8_t *arena, const uint32_t *off
     if (frame_size == 0 || frame_size % 120 != 0) return OPN_ERR_BAD_ARG;  // decoder.rs:316-320
     if (flags & (OPN_FLAG_DEVICE_PTRS | OPN_FLAG_NO_PCM_COPY)) return OPN_ERR_BAD_ARG;
     if (pcm_stride_samples < frame_size * (size_t)b->cfg.channels) return OPN_ERR_BUFFER_TOO_SMALL;
+    if (frame_size * (size_t)b->cfg.channels * sizeof(float) > 200 * 1024) return OPN_ERR_BAD_ARG;  // the clip epilogue stages a row on chip
     CU(cudaSetDevice(b->device));
     const int rc = batch_decode_host(b, arena, offsets, lens, nullptr, pcm_stride_samples, frame_size, result_per_stream, flags, pcm,
                                      sample_format);
@@ -783,11 +769,8 @@ int opn_batch_synchronize(opn_batch *b)
 {
     if (!b) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
-    for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
-    CU(cudaStreamSynchronize(b->stream_ex));
-    CU(cudaStreamSynchronize(b->stream));
-    CU(cudaStreamSynchronize(b->stream_k2));
-    CU(cudaStreamSynchronize(b->stream_dn));
+    int rc = sync_pipeline(b);
+    if (rc) return rc;
     for (auto &g : b->stg) g.pending = false;
     return OPN_OK;
 }
@@ -795,9 +778,7 @@ int opn_batch_synchronize(opn_batch *b)
 int opn_batch_join(opn_batch *b)
 {
     if (!b) return OPN_ERR_BAD_ARG;
-    CU(cudaSetDevice(b->device));
-    // everything enqueued so far ends either on `stream` or with a kernel 2 on stream_k2
-    if (b->last_set >= 0 && b->k2_recorded[b->last_set]) CU(cudaStreamWaitEvent(b->stream, b->ev_k2[b->last_set], 0));
+    // every step ends with its frame kernel on the batch stream: whatever is enqueued there next is ordered after it
     return OPN_OK;
 }
 
@@ -841,6 +822,11 @@ int opn_batch_enable_timing(opn_batch *b, int on)
             if (rc) return rc;
         }
     }
+    if (b->timing != (on != 0)) {
+        // the two modes order their kernels differently (events across streams / one stream): drain before switching
+        int rc = sync_pipeline(b);
+        if (rc) return rc;
+    }
     b->timing = on != 0;
     return OPN_OK;
 }
@@ -864,6 +850,18 @@ int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[
     return OPN_OK;
 }
 
+int opn_batch_history_samples(opn_batch *b, uint64_t *out, int reset)
+{
+    if (!b || !out) return OPN_ERR_BAD_ARG;
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, b->d_hist_samples, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(b->d_hist_samples, 0, sizeof(v)));
+    *out = v;
+    return OPN_OK;
+}
+
 void *opn_batch_cuda_stream(opn_batch *b) { return b ? (void *)b->stream : nullptr; }
 
 // ------------------------------------------------------------------------------------ decoder
@@ -880,10 +878,10 @@ struct opn_decoder {
 
 extern "C" {
 
-int opn_decoder_create(int device, int32_t fs_hz, int32_t channels, int16_t gain_q8, opn_decoder **out)
+int opn_decoder_create(int device, int32_t fs_hz, int32_t channels, int16_t gain_q8, int32_t bitstream, opn_decoder **out)
 {
     if (!out) return OPN_ERR_BAD_ARG;
-    opn_config cfg{fs_hz, channels, gain_q8, 1};
+    opn_config cfg{fs_hz, channels, gain_q8, 1, bitstream};
     opn_batch *b = nullptr;
     int rc = opn_batch_create(device, 1, &cfg, &b);
     if (rc) return rc;
@@ -1182,12 +1180,13 @@ int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offse
         max_len = std::max(max_len, lens[i]);
     }
     const size_t row = (size_t)channels * (120u << lm);
-    DevBuf dA, dO, dL, dS, dSt, dY, dC, dI;
+    DevBuf dA, dO, dL, dS, dSt, dY, dC, dI, dH;
     CU(dA.alloc(arena_end));
     CU(dO.alloc(n_packets * 4));
     CU(dL.alloc(n_packets * 4));
     CU(dS.alloc((size_t)n_packets * sizeof(opn_synth_side)));
     CU(dSt.alloc(n_packets * 4));
+    CU(dH.alloc((size_t)n_packets * sizeof(uint4)));
     CU(dY.alloc((size_t)n_packets * row * 4));
     CU(dC.alloc((size_t)n_packets * row * 4));
     CU(dI.alloc((size_t)n_packets * 72 * 4));
@@ -1204,6 +1203,7 @@ int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offse
     s.channels = channels;
     s.has_toc = 0;
     s.side = dS.as<opn_synth_side>();
+    s.hdr = dH.as<uint4>();
     s.status = dSt.as<int32_t>();
     s.coef = dC.as<float>();
     s.y_out = dY.as<int32_t>();

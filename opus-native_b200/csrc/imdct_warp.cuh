@@ -1,8 +1,7 @@
-// imdct_warp.cuh -- kernel 1, warp-per-stream generation: one WARP decodes one stream (both channels).
+// imdct_warp.cuh -- Mdct::backward by one WARP for the channels of one stream (device function w_imdct).
 //
 // Device mirror of Mdct::backward (src/celt/mdct.rs:159-260), KissFft::process and its
-// butterflies (src/celt/kiss_fft.rs:24-243), comb_filter_inplace
-// (src/celt/comb_filter/mod.rs:130-193, scalar kernel fallback.rs:32-53).
+// butterflies (src/celt/kiss_fft.rs:24-243).
 //
 // Arithmetic contract (unchanged from imdct.cuh): every sum and product is evaluated in the
 // reference's order with single roundings; the TU is compiled with -fmad=false.  What changes is
@@ -27,10 +26,7 @@
 //     row that later holds the output; the transpose buffer aliases that row too (every lane has its
 //     inputs in registers before the first transposed element is written), so a stream needs
 //     C x (nf + 60) floats of shared memory and ~20 streams are resident per SM.
-//   * The post-filter reads its history straight from the interleaved PCM ring in HBM/L2 (one
-//     float2 = both channels of a tap).  History-only spans of the frame have no recursion and are
-//     filtered in one parallel sweep, 4 samples per lane; only the truly recursive remainder is
-//     swept in chunks, from shared memory.
+//   * The kernels that call w_imdct (frame kernel, operator kernel) are in frame_warp.cuh.
 #pragma once
 #include "imdct.cuh"
 #include "opn_tables.h"
@@ -51,7 +47,6 @@ constexpr int W_K1_MIN_CTAS = OPN_K1_MIN_CTAS;  // kernel 1 register budget: 655
 __host__ __device__ constexpr int w_ch_floats(int lm) { return (120 << lm) + 60; }
 __host__ __device__ constexpr int trig_pair_off(int shift) { return shift == 0 ? 0 : shift == 1 ? 480 : shift == 2 ? 720 : 840; }
 __host__ __device__ constexpr size_t w_smem_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16; }
-__host__ __device__ constexpr size_t w_comb_smem_bytes(int lm, int channels) { return (size_t)channels * (HIST_CAP + (120 << lm)) * 4 + 16; }
 
 // ---- TMA / mbarrier (single-CTA cluster) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -335,413 +330,6 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
         ob[119 - i] = (w0 * x1) + (w1 * x0);
     }
     __syncwarp();
-}
-
-// ---- post-filter -------------------------------------------------------------------------------
-// comb_filter_const_inplace term order (fallback.rs:46-51): y + g0*x2 + g1*(x1+x3) + g2*(x0+x4)
-__device__ __forceinline__ float comb5(float y, float x0, float x1, float x2, float x3, float x4, float g0, float g1, float g2)
-{
-    return y + (g0 * x2) + (g1 * (x1 + x3)) + (g2 * (x0 + x4));
-}
-
-// One sample of the C interleaved channels (the PCM ring layout): C == 2 moves both channels of a tap
-// in one 64-bit access.
-template <int C> struct WSmp;
-template <> struct WSmp<1> {
-    float a;
-    __device__ __forceinline__ static WSmp ld(const float *p) { return WSmp{*p}; }
-    __device__ __forceinline__ void st(float *p) const { *p = a; }
-};
-template <> struct WSmp<2> {
-    float a, b;
-    __device__ __forceinline__ static WSmp ld(const float *p)
-    {
-        const float2 v = *reinterpret_cast<const float2 *>(p);
-        return WSmp{v.x, v.y};
-    }
-    __device__ __forceinline__ void st(float *p) const { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
-};
-template <int C>
-__device__ __forceinline__ WSmp<C> w_comb5(WSmp<C> y, WSmp<C> x0, WSmp<C> x1, WSmp<C> x2, WSmp<C> x3, WSmp<C> x4, float g0, float g1,
-                                           float g2)
-{
-    WSmp<C> r;
-    r.a = comb5(y.a, x0.a, x1.a, x2.a, x3.a, x4.a, g0, g1, g2);
-    if constexpr (C == 2) r.b = comb5(y.b, x0.b, x1.b, x2.b, x3.b, x4.b, g0, g1, g2);
-    return r;
-}
-// cross-fade accumulation order of comb_filter_inplace (mod.rs:166-177); a* = y[i-t0-2 .. i-t0+2],
-// b* = y[i-t1-2 .. i-t1+2]
-__device__ __forceinline__ float xfade1(float y, float a0, float a1, float a2, float a3, float a4, float b0, float b1, float b2, float b3,
-                                        float b4, bool has0, bool has1, float f, float g00, float g01, float g02, float g10, float g11,
-                                        float g12)
-{
-    float v = y;
-    if (has0) {
-        v = v + (((1.0f - f) * g00) * a2);
-        v = v + (((1.0f - f) * g01) * (a3 + a1));
-        v = v + (((1.0f - f) * g02) * (a4 + a0));
-    }
-    if (has1) {
-        v = v + ((f * g10) * b2);
-        v = v + ((f * g11) * (b3 + b1));
-        v = v + ((f * g12) * (b4 + b0));
-    }
-    return v;
-}
-template <int C>
-__device__ __forceinline__ WSmp<C> w_xfade(WSmp<C> y, const WSmp<C> *a, const WSmp<C> *b, bool has0, bool has1, float f, float g00,
-                                           float g01, float g02, float g10, float g11, float g12)
-{
-    WSmp<C> r;
-    r.a = xfade1(y.a, a[0].a, a[1].a, a[2].a, a[3].a, a[4].a, b[0].a, b[1].a, b[2].a, b[3].a, b[4].a, has0, has1, f, g00, g01, g02, g10,
-                 g11, g12);
-    if constexpr (C == 2)
-        r.b = xfade1(y.b, a[0].b, a[1].b, a[2].b, a[3].b, a[4].b, b[0].b, b[1].b, b[2].b, b[3].b, b[4].b, has0, has1, f, g00, g01, g02,
-                     g10, g11, g12);
-    return r;
-}
-
-// comb_filter_inplace (comb_filter/mod.rs:130-193) on one stream: y points at sample 0 of the frame,
-// sample i of channel c lives at y[C*i + c] and the history (the previous max(T)+2 samples) directly
-// below, exactly as in the PCM ring.  The filter is recursive, y[i] depends on y[i-T-2 .. i-T+2];
-// wherever those taps are history the samples are independent and are filtered in parallel, the rest
-// is swept in chunks no longer than T-2.  A tap set whose gain is exactly zero contributes +-0 to
-// every sum and is skipped.
-// tap gains of the old and the new filter (comb_filter/mod.rs:45-55, 146-151); a separate step so that kernel 2 can
-// have the table reads in flight while its samples are still arriving
-struct CombGains {
-    float g00, g01, g02, g10, g11, g12;
-};
-__device__ __forceinline__ CombGains w_comb_gains(float g0, float g1, int tap0, int tap1)
-{
-    CombGains k;
-    k.g00 = g0 * g_tab.comb_gains[tap0 * 3];
-    k.g01 = g0 * g_tab.comb_gains[tap0 * 3 + 1];
-    k.g02 = g0 * g_tab.comb_gains[tap0 * 3 + 2];
-    k.g10 = g1 * g_tab.comb_gains[tap1 * 3];
-    k.g11 = g1 * g_tab.comb_gains[tap1 * 3 + 1];
-    k.g12 = g1 * g_tab.comb_gains[tap1 * 3 + 2];
-    return k;
-}
-template <int C>
-__device__ __forceinline__ void w_comb(float *y, int t0, int t1, int n, float g0, float g1, int tap0, int tap1, int overlap, int lane,
-                                       const float *win_sq, const CombGains &kg)
-{
-    using S = WSmp<C>;
-    if (g0 == 0.0f && g1 == 0.0f) return;
-    t0 = max(t0, 15);
-    t1 = max(t1, 15);
-    const float g00 = kg.g00, g01 = kg.g01, g02 = kg.g02, g10 = kg.g10, g11 = kg.g11, g12 = kg.g12;
-    if (fabsf(g0 - g1) < 1.1920929e-7f && t0 == t1 && tap0 == tap1) overlap = 0;
-    const bool has0 = g0 != 0.0f, has1 = g1 != 0.0f;
-
-    // Independent samples are dealt to the lanes round-robin (sample = base + lane + 32 e): consecutive
-    // lanes touch consecutive float2, so every shared-memory access is conflict-free.
-    // ---- cross-fade part (mod.rs:162-179): samples [0, overlap)
-    if (overlap > 0) {
-        const int tmin = min(has0 ? t0 : 1 << 20, has1 ? t1 : 1 << 20);
-        // [0, pre): every tap of every live set is history -> no recursion
-        const int pre = min(overlap, tmin - 2);
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int i = lane + 32 * e;
-            if (i < pre) {
-                const float f = __ldg(win_sq + i);
-                S a[5], b[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    a[k] = has0 ? S::ld(y + C * (i - t0 - 2 + k)) : S{};
-                    b[k] = has1 ? S::ld(y + C * (i - t1 - 2 + k)) : S{};
-                }
-                w_xfade<C>(S::ld(y + C * i), a, b, has0, has1, f, g00, g01, g02, g10, g11, g12).st(y + C * i);
-            }
-        }
-        __syncwarp();
-        // [pre, overlap): chunks of W <= tmin - 2 samples, one per lane
-        const int W = min(tmin - 2, 32);
-        for (int base = pre; base < overlap; base += W) {
-            const int i = base + lane;
-            if (lane < W && i < overlap) {
-                const float f = __ldg(win_sq + i);
-                S a[5], b[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    a[k] = has0 ? S::ld(y + C * (i - t0 - 2 + k)) : S{};
-                    b[k] = has1 ? S::ld(y + C * (i - t1 - 2 + k)) : S{};
-                }
-                w_xfade<C>(S::ld(y + C * i), a, b, has0, has1, f, g00, g01, g02, g10, g11, g12).st(y + C * i);
-            }
-            __syncwarp();
-        }
-    }
-    if (!has1) return;
-
-    // ---- constant part (fallback.rs:32-53): samples [overlap, n)
-    auto one = [&](int i) {
-        const float *p = y + C * (i - t1);
-        w_comb5<C>(S::ld(y + C * i), S::ld(p + 2 * C), S::ld(p + C), S::ld(p), S::ld(p - C), S::ld(p - 2 * C), g10, g11, g12).st(y + C * i);
-    };
-    // (1) history-only span [overlap, hend): no recursion, 128 samples per step
-    int at = overlap;
-    {
-        const int hend = max(at, min(n, t1 - 2));
-        for (int base = at; base < hend; base += 128) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int i = base + lane + 32 * e;
-                if (i < hend) one(i);
-            }
-        }
-        at = hend;
-        __syncwarp();
-    }
-    // (2) recursive remainder [at, n): chunks of min(t1 - 2, 128) samples; inside a chunk every tap lies
-    //     before the chunk
-    if (t1 - 2 >= 128) {
-        for (int base = at; base < n; base += 128) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int i = base + lane + 32 * e;
-                if (i < n) one(i);
-            }
-            __syncwarp();
-        }
-    } else if (t1 - 2 >= 64) {
-        for (int base = at; base < n; base += 64) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int i = base + lane + 32 * e;
-                if (i < n) one(i);
-            }
-            __syncwarp();
-        }
-    } else {
-        const int W = min(t1 - 2, 32);
-        for (int base = at; base < n; base += W) {
-            const int i = base + lane;
-            if (lane < W && i < n) one(i);
-            __syncwarp();
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernel 1 (IMDCT + TDAC overlap-add + PCM store): one warp = one CTA = one stream (item).
-// Shared memory per warp: C rows of nf+60 floats and one mbarrier.  The post-filter runs in kernel 2
-// on the interleaved PCM this kernel leaves in the ring; kernel 1 only decides whether it is needed and
-// leaves the parameters (old -> new) in `job`.
-template <int LM, int C> __global__ void __launch_bounds__(32, W_K1_MIN_CTAS) k_imdct_post_w(ImdctArgs A)
-{
-    extern __shared__ __align__(16) float o[];
-    constexpr int NF = 120 << LM;
-    constexpr int CHF = w_ch_floats(LM);
-    const int lane = threadIdx.x;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);
-
-    const uint32_t item = blockIdx.x;
-    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-    // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, C * NF * 4);
-#pragma unroll
-        for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
-    }
-    // everything the frame needs from per-stream state, requested in one go
-    const opn_synth_side *side = A.side + stream;
-    const int32_t status = A.status[stream];
-    const PfState old = A.pf[stream];
-    const uint32_t pos = A.ring_pos[stream];
-    const int s_transient = side->transient, s_on = side->postfilter, s_period = side->period, s_gain = side->gain_idx,
-              s_tapset = side->tapset;
-    const uint32_t s_final = side->final_rng;
-    const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
-    float *carry_g = A.carry + (size_t)stream * C * 60;
-    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
-    __syncwarp();
-    if (status < 0) {  // rejected packet: state untouched (decoder.rs:397)
-        if (lane == 0) {
-            if (A.result) A.result[stream] = status;
-            A.job[item].on = 0;
-        }
-        mbar_wait(bar, 0);  // the rows are in flight: do not retire the CTA under them
-        return;
-    }
-    const bool lost = status == ITEM_LOST;
-    // post-filter parameters: previous frame -> this frame
-    int t1 = old.period, tap1 = old.tapset;
-    float g1 = old.gain;
-    if (!lost) {
-        t1 = s_on ? s_period : 0;
-        g1 = s_on ? 0.09375f * (float)(s_gain + 1) : 0.0f;
-        tap1 = s_on ? s_tapset : 0;
-    }
-    const bool comb_on = A.postfilter && (old.gain != 0.0f || g1 != 0.0f);
-    float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
-
-    mbar_wait(bar, 0);
-    if constexpr (LM > 0) {
-        if (s_transient) w_imdct<3, (1 << LM), C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
-        else w_imdct<3 - LM, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3 - LM), g_tab.twiddles, g_tab.window);
-    } else {
-        w_imdct<3, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
-    }
-
-    // tail of this frame -> carry
-    if (lane < 15 * C) {
-        const int ch = (C == 2 && lane >= 15) ? 1 : 0;
-        *reinterpret_cast<float4 *>(carry_g + 4 * lane) = *reinterpret_cast<const float4 *>(o + ch * CHF + NF + 4 * (lane - 15 * ch));
-    }
-    // interleaved PCM -> ring (history + device-resident output); dense rows only when no post-filter follows.
-    // The frame is contiguous in the ring except when it wraps (pos is a multiple of 120).
-    float *dense = (A.dense && !comb_on) ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
-    const float gain = A.gain;
-    constexpr int VEC = C == 2 ? NF / 2 : NF / 4;         // float4 per frame
-    constexpr int SPV = C == 2 ? 2 : 4;                   // samples per float4
-    const int wrap_at = (int)(RING_SAMPLES - pos) / SPV;  // first float4 that lands at the ring start
-    float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)pos * C);
-    float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
-#pragma unroll
-    for (int i = lane; i < VEC; i += 32) {
-        float4 v;
-        if (C == 2) {
-            const float2 a = *reinterpret_cast<const float2 *>(o + 2 * i), b = *reinterpret_cast<const float2 *>(o + CHF + 2 * i);
-            v = make_float4(a.x, b.x, a.y, b.y);
-        } else {
-            v = *reinterpret_cast<const float4 *>(o + 4 * i);
-        }
-        (i < wrap_at ? r0 : r1)[i] = v;
-        if (dense) {
-            if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
-            reinterpret_cast<float4 *>(dense)[i] = v;
-        }
-    }
-    if (lane == 0) {
-        uint32_t np = pos + (uint32_t)NF;
-        if (np >= RING_SAMPLES) np -= RING_SAMPLES;
-        A.ring_pos[stream] = np;
-        PfState nw;
-        nw.period = t1;
-        nw.tapset = tap1;
-        nw.gain = g1;
-        nw.pad = 0;
-        A.pf[stream] = nw;
-        if (A.result) A.result[stream] = NF;
-        if (A.final_range) A.final_range[stream] = lost ? 0u : s_final;
-        CombJob j;
-        j.on = comb_on ? 1 : 0;
-        j.pos = pos;
-        j.t0 = old.period;
-        j.t1 = t1;
-        j.tap0 = old.tapset;
-        j.tap1 = tap1;
-        j.g0 = old.gain;
-        j.g1 = g1;
-        A.job[item] = j;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernel 2 (pitch comb post-filter, comb_filter_inplace): one warp = one CTA = one stream (item) whose job is on.
-// The history (the T+2 samples before the frame) and the frame are one contiguous span of the
-// interleaved ring: one TMA transfer (three when the span wraps) brings both into shared memory, the
-// filter runs in place on float2 = (left, right) samples, and the frame goes back to the ring and, for
-// host-buffer calls, to the dense output rows.
-template <int LM, int C> __global__ void __launch_bounds__(32) k_comb_post_w(ImdctArgs A)
-{
-    extern __shared__ __align__(16) float sm[];
-    constexpr int NF = 120 << LM;
-    const int lane = threadIdx.x;
-    float *y = sm + C * HIST_CAP;  // sample 0 of the frame; history below
-    uint64_t *bar = reinterpret_cast<uint64_t *>(y + C * NF);
-
-    const uint32_t item = blockIdx.x;
-    const CombJob j = A.job[item];
-    if (!j.on) return;
-    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-    float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
-    const int need = (max(max(j.t0, j.t1), 15) + 2 + 3) & ~3;  // multiple of 4: every piece 16-byte sized and aligned
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (need + NF) * C * 4);
-        // span [pos - need, pos + NF) of the ring, cut where it wraps
-        int first = (int)j.pos - need, count = need + NF;
-        float *dst = y - need * C;
-        if (first < 0) {
-            bulk_g2s(dst, ring + (size_t)(first + RING_SAMPLES) * C, -first * C * 4, bar);
-            dst += -first * C;
-            count += first;
-            first = 0;
-        }
-        const int fit = min(count, RING_SAMPLES - first);
-        bulk_g2s(dst, ring + (size_t)first * C, fit * C * 4, bar);
-        if (count > fit) bulk_g2s(dst + fit * C, ring, (count - fit) * C * 4, bar);
-    }
-    const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
-    const CombGains kg = w_comb_gains(j.g0, j.g1, j.tap0, j.tap1);
-    __syncwarp();
-    mbar_wait(bar, 0);
-    w_comb<C>(y, j.t0, j.t1, NF, j.g0, j.g1, j.tap0, j.tap1, 120, lane, g_tab.window_sq, kg);
-    __syncwarp();
-    float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
-    const float gain = A.gain;
-    constexpr int VEC = NF * C / 4;
-    constexpr int SPV = 4 / C;
-    const int wrap_at = (int)(RING_SAMPLES - j.pos) / SPV;
-    float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)j.pos * C);
-    float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
-#pragma unroll
-    for (int i = lane; i < VEC; i += 32) {
-        float4 v = reinterpret_cast<const float4 *>(y)[i];
-        (i < wrap_at ? r0 : r1)[i] = v;
-        if (dense) {
-            if (gain != 1.0f) { v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain; }
-            reinterpret_cast<float4 *>(dense)[i] = v;
-        }
-    }
-}
-
-// Operator-level Mdct::backward on independent rows (tests; opn_op_imdct_tdac): one warp per row.
-template <int SHIFT, int NBLK>
-__global__ void __launch_bounds__(32)
-k_op_imdct_w(const float *__restrict__ input, size_t in_stride, float *__restrict__ output, size_t out_stride)
-{
-    extern __shared__ __align__(16) float sm[];
-    constexpr int N2 = 960 >> SHIFT, NF = N2 * NBLK;
-    const int lane = threadIdx.x;
-    const float *in = input + (size_t)blockIdx.x * in_stride;
-    float *out = output + (size_t)blockIdx.x * out_stride;
-    for (int i = lane; i < NF; i += 32) sm[i] = in[i];
-    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < 15) carry = make_float4(out[4 * lane], out[4 * lane + 1], out[4 * lane + 2], out[4 * lane + 3]);
-    __syncwarp();
-    w_imdct<SHIFT, NBLK, 1>(sm, lane, carry, g_tab.trig_pair + trig_pair_off(SHIFT), g_tab.twiddles, g_tab.window);
-    for (int i = lane; i < NF + 60; i += 32) out[i] = sm[i];
-}
-
-// Operator-level comb_filter_inplace on rows (tests; opn_op_comb_filter_inplace): one warp per row,
-// the row's own prefix [y_offset - hist, y_offset) plays the role of the PCM ring.
-__global__ void __launch_bounds__(32)
-k_op_comb_inplace_w(float *__restrict__ y, size_t row_stride, int y_offset, int n, const int32_t *__restrict__ params4,
-                    const float *__restrict__ gains2, int overlap)
-{
-    extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x;
-    float *row = y + (size_t)blockIdx.x * row_stride;
-    const int t0 = params4[4 * blockIdx.x], t1 = params4[4 * blockIdx.x + 1];
-    const int tap0 = params4[4 * blockIdx.x + 2], tap1 = params4[4 * blockIdx.x + 3];
-    const float g0 = gains2[2 * blockIdx.x], g1 = gains2[2 * blockIdx.x + 1];
-    // shared memory: [HIST_CAP history | n samples]; the row's own prefix plays the role of the PCM ring
-    const int need = min(max(max(t0, t1), 15) + 2, y_offset);
-    float *ys = sm + HIST_CAP;
-    for (int i = lane; i < n; i += 32) ys[i] = row[y_offset + i];
-    for (int i = lane; i < need; i += 32) ys[-1 - i] = row[y_offset - 1 - i];
-    __syncwarp();
-    w_comb<1>(ys, t0, t1, n, g0, g1, tap0, tap1, overlap, lane, g_tab.window_sq, w_comb_gains(g0, g1, tap0, tap1));
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) row[y_offset + i] = ys[i];
 }
 
 }  // namespace opn

@@ -16,14 +16,13 @@ constexpr int SYM_WARPS_PER_CTA = 4;
 // the SMs' 32 CTA slots are not what the long-running entropy launches take from the other kernels.
 constexpr int RANGEDEC_WARPS_PER_CTA = OPN_RD_WARPS;
 #ifndef OPN_EXPAND_WARPS
-#define OPN_EXPAND_WARPS 8
+#define OPN_EXPAND_WARPS 4
 #endif
-constexpr int EXPAND_WARPS_PER_CTA = OPN_EXPAND_WARPS;  // k_synth_expand: 52 KB per CTA, 4 CTAs per SM, 4096 streams = 512 CTAs = one wave (5/6/8 measured: 1.38/1.49/1.52 M)
+constexpr int EXPAND_WARPS_PER_CTA = OPN_EXPAND_WARPS;  // stand-alone k_synth_expand: 47 KB per CTA (tables 16.5 KB + 7.5 KB of rows per warp)
 constexpr int IM_TPC = 128;         // threads per row of the out-of-place comb operator kernel
-constexpr int HIST_CAP = 1024;      // comb history window in shared memory (T + 2 <= 1024)
-// per-channel PCM ring: 4 x 960 = 8 x 480 = 16 x 240 = 32 x 120.  Four long frames, so that kernel 1 may write
-// frame n+1 while kernel 2 still reads frame n and its history (960 + 960 + 1024 <= 3840).
-constexpr int RING_SAMPLES = 3840;
+// per-channel PCM ring (output + comb history): 3 x 960 = 6 x 480 = 12 x 240 = 24 x 120 samples.  A frame never overlaps
+// the history it is filtered against: 960 + 1024 + 2 <= 2880.
+constexpr int RING_SAMPLES = 2880;
 constexpr int32_t ITEM_OK = 0, ITEM_LOST = 1;  // kernel-0 status; negative = OPN_ERR_* (state untouched)
 
 struct PfState {  // post-filter parameters of the previous frame
@@ -32,12 +31,14 @@ struct PfState {  // post-filter parameters of the previous frame
     int32_t pad;
 };
 
-struct CombJob {  // kernel 1 -> kernel 2: the post-filter to run on an item's frame
-    int32_t on;
-    uint32_t pos;  // ring position of the frame start
-    int32_t t0, t1, tap0, tap1;
-    float g0, g1;
-};
+// Frame header, range decode -> frame kernel: one uint4 per stream.
+//   .x = silence | postfilter << 1 | transient << 2 | intra << 3 | tapset << 4 | gain_idx << 8 | octave << 12 | period << 16
+//   .y = final range (Decoder::final_range), .z = tell_frac, .w = number of pulses
+__host__ __device__ inline uint32_t hdr_pack(uint32_t silence, uint32_t postfilter, uint32_t transient, uint32_t intra, uint32_t tapset,
+                                             uint32_t gain_idx, uint32_t octave, uint32_t period)
+{
+    return silence | postfilter << 1 | transient << 2 | intra << 3 | tapset << 4 | gain_idx << 8 | octave << 12 | period << 16;
+}
 
 struct SymbolArgs {
     const uint8_t *arena;
@@ -46,7 +47,8 @@ struct SymbolArgs {
     const uint32_t *stream_idx;  // [n_items] or nullptr (item k = stream k)
     uint32_t n_items;
     int lm, channels, has_toc;
-    opn_synth_side *side;        // [n_streams]
+    opn_synth_side *side;        // [n_streams] or nullptr: full side record (tests)
+    uint4 *hdr;                  // [n_streams] frame header for the frame kernel
     int32_t *status;             // [n_streams]
     float *coef;                 // [n_streams][channels][120<<lm] or nullptr
     int32_t *y_out;              // same shape or nullptr
@@ -54,10 +56,11 @@ struct SymbolArgs {
     uint32_t pkt_cap;            // bytes of shared memory per warp for the packet
 };
 
-struct ImdctArgs {
-    const float *coef;            // [n_streams][C][120<<lm]  (kernel 0 output)
-    const opn_synth_side *side;   // [n_streams]
-    const int32_t *status;        // [n_streams]  (kernel 0 output)
+struct FrameArgs {
+    const float *coef;            // [n_streams][C][120<<lm] coefficient rows (unfused variant only)
+    const uint32_t *idx;          // [n_streams][72] PVQ codeword indices (range decode output)
+    const uint4 *hdr;             // [n_streams] frame headers (range decode output)
+    const int32_t *status;        // [n_streams]  (range decode output)
     const uint32_t *stream_idx;   // [n_items] or nullptr
     uint32_t n_items;
     int lm, channels, postfilter;
@@ -71,7 +74,8 @@ struct ImdctArgs {
     float gain;                   // DecoderConfiguration::gain as a linear factor (decoder.rs:790-797); 1 = none
     int32_t *result;              // [n_streams] samples per channel or OPN_ERR_*; nullptr to skip
     uint32_t *final_range;        // [n_streams]
-    CombJob *job;                 // [n_items] scratch, kernel 1 -> kernel 2
+    float *softclip_reset;        // [n_streams][2] or nullptr: cleared for every stream that decodes a packet (decoder.rs:420-423)
+    unsigned long long *hist_samples;  // measurement (or nullptr): += max(T0,T1)+2 per channel-frame the post-filter runs on
 };
 
 // ---- launchers (opn_kernels.cu).  All return a cudaError_t and never synchronise.
@@ -82,8 +86,8 @@ cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets
 cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st);   // both stages on one stream
 cudaError_t launch_synth_rangedec(const SymbolArgs &a, cudaStream_t st);  // stage 0a: one lane per packet
 cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st);    // stage 0b: one warp per packet
-cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st);  // kernel 1: IMDCT + TDAC + PCM store
-cudaError_t launch_comb_post(const ImdctArgs &a, cudaStream_t st);   // kernel 2: comb post-filter on the ring
+// the frame kernel: (PVQ expansion when a.coef == nullptr) + IMDCT + TDAC + comb post-filter + PCM store
+cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st);
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
                             int nblk, cudaStream_t st);
 cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, int n, uint32_t n_rows, const int32_t *params4,

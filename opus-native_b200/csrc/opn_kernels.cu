@@ -1,8 +1,10 @@
 // opn_kernels.cu -- the single CUDA translation unit of libopusb200 (sm_100a, -fmad=false).
+#include <algorithm>
 #include <mutex>
 
 #include "imdct.cuh"
 #include "imdct_warp.cuh"
+#include "frame_warp.cuh"
 #include "mathops.cuh"
 #include "opn_tables.h"
 #include "softclip.cuh"
@@ -19,9 +21,9 @@ static bool g_tab_done[64];
 template <int LM, int C> static cudaError_t set_carveout()
 {
     // percent of the SM's unified 256 KB used as shared memory; the rest is L1 (tables, history taps)
-    cudaError_t e = cudaFuncSetAttribute(k_comb_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    cudaError_t e = cudaFuncSetAttribute(k_frame_w<LM, C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_imdct_post_w<LM, C>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    return cudaFuncSetAttribute(k_frame_w<LM, C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
 }
 static cudaError_t set_warp_kernel_attributes()
 {
@@ -72,6 +74,18 @@ cudaError_t upload_tables(int device)
             h.pvq_cw_data[i].y = (m >= k + 1 && up < next_end) ? OPN_PVQ_U_DATA[up] - OPN_PVQ_U_DATA[i] : 0u;
         }
     }
+    for (int k = 0; k < 16; k++) {
+        h.pvq_ev_nmax[k] = 0;
+        if (k > 13) continue;  // the k < n regime reads U(k+1,.): rows 1..14
+        auto last_col = [](int r) { return (r < 14 ? OPN_PVQ_U_ROW[r + 1] + r : 1271) - OPN_PVQ_U_ROW[r]; };  // rows are stored back to back
+        const int last = std::min(last_col(k), last_col(k + 1));
+        uint64_t rowsum = 0;  // sum_{j=k..n} U(k,j)
+        for (int n = k; n <= last && n < 256; n++) {
+            rowsum += OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[k] + n];
+            if (n > k && rowsum + OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[k + 1] + n] < (1ull << 32)) h.pvq_ev_nmax[k] = (uint8_t)n;
+            else if (n > k) break;
+        }
+    }
     for (int i = 0; i < 22; i++) h.e_bands[i] = OPN_E_BANDS[i];
     for (int l = 0; l < 4; l++)
         for (int b = 0; b < 21; b++)
@@ -89,12 +103,14 @@ cudaError_t upload_tables(int device)
                         e.n = (uint8_t)n;
                         e.k = (uint8_t)k;
                         e.ft_minus1 = 0; e.magic = 0; e.ft1 = 0; e.ftb = 0; e.sh = 0;
+                        if (n > 64 || k > 6) return cudaErrorInvalidValue;  // w_expand keeps a part's pulses as six 10-bit records
                         if (n == 1) continue;
                         if (n > 2 && k < n) {
                             // k_synth_expand bisects on 32-bit sums: the whole row sum plus U(k+1,n) must not wrap
                             uint64_t rowsum = 0;
                             for (uint32_t j = k; j <= n; j++) rowsum += OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[k] + j];
                             if (k >= 14 || rowsum + OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[k + 1] + n] >= (1ull << 32)) return cudaErrorInvalidValue;
+                            if (n > h.pvq_ev_nmax[k]) return cudaErrorInvalidValue;  // the schedule's parts all take the event path
                         }
                         auto U = [](uint32_t a, uint32_t bb) { return OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[a < bb ? a : bb] + (a < bb ? bb : a)]; };
                         const uint32_t ft = U(n, k) + U(n, k + 1);   // pvq_v, pvc.rs:289-291
@@ -163,27 +179,22 @@ cudaError_t upload_tables(int device)
     // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
     e = cudaFuncSetAttribute(k_rangedec_script, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_synth_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    e = cudaFuncSetAttribute(k_synth_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)synth_expand_smem());
     if (e != cudaSuccess) return e;
     g_tab_done[device] = true;
     return cudaSuccess;
 }
 
-template <int LM, int C> static cudaError_t launch_imdct_w(const ImdctArgs &a, cudaStream_t st)
+template <int LM, int C> static cudaError_t launch_frame_w(const FrameArgs &a, cudaStream_t st)
 {
-    k_imdct_post_w<LM, C><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
-    return cudaGetLastError();
-}
-
-template <int LM, int C> static cudaError_t launch_comb_w(const ImdctArgs &a, cudaStream_t st)
-{
-    k_comb_post_w<LM, C><<<a.n_items, 32, w_comb_smem_bytes(LM, C), st>>>(a);
+    if (a.coef) k_frame_w<LM, C, false><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
+    else k_frame_w<LM, C, true><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
     return cudaGetLastError();
 }
 
 static size_t symbols_smem(uint32_t pkt_cap)
 {
-    return PVQ_TABLE_WORDS * 4 + 32 + (size_t)SYM_WARPS_PER_CTA * Y_STAGE * 4 + (size_t)SYM_WARPS_PER_CTA * pkt_cap;
+    return 3 * PVQ_TABLE_WORDS * 4 + 32 + 16 + (size_t)SYM_WARPS_PER_CTA * Y_STAGE * 4 + (size_t)SYM_WARPS_PER_CTA * pkt_cap;
 }
 
 cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
@@ -222,34 +233,19 @@ cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
     return launch_synth_expand(a, st);
 }
 
-cudaError_t launch_imdct_post(const ImdctArgs &a, cudaStream_t st)
+cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
+    if (!a.coef && !a.idx) return cudaErrorInvalidValue;
     switch (a.lm * 2 + (a.channels - 1)) {
-    case 0: return launch_imdct_w<0, 1>(a, st);
-    case 1: return launch_imdct_w<0, 2>(a, st);
-    case 2: return launch_imdct_w<1, 1>(a, st);
-    case 3: return launch_imdct_w<1, 2>(a, st);
-    case 4: return launch_imdct_w<2, 1>(a, st);
-    case 5: return launch_imdct_w<2, 2>(a, st);
-    case 6: return launch_imdct_w<3, 1>(a, st);
-    case 7: return launch_imdct_w<3, 2>(a, st);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-cudaError_t launch_comb_post(const ImdctArgs &a, cudaStream_t st)
-{
-    if (a.n_items == 0 || !a.postfilter) return cudaSuccess;
-    switch (a.lm * 2 + (a.channels - 1)) {
-    case 0: return launch_comb_w<0, 1>(a, st);
-    case 1: return launch_comb_w<0, 2>(a, st);
-    case 2: return launch_comb_w<1, 1>(a, st);
-    case 3: return launch_comb_w<1, 2>(a, st);
-    case 4: return launch_comb_w<2, 1>(a, st);
-    case 5: return launch_comb_w<2, 2>(a, st);
-    case 6: return launch_comb_w<3, 1>(a, st);
-    case 7: return launch_comb_w<3, 2>(a, st);
+    case 0: return launch_frame_w<0, 1>(a, st);
+    case 1: return launch_frame_w<0, 2>(a, st);
+    case 2: return launch_frame_w<1, 1>(a, st);
+    case 3: return launch_frame_w<1, 2>(a, st);
+    case 4: return launch_frame_w<2, 1>(a, st);
+    case 5: return launch_frame_w<2, 2>(a, st);
+    case 6: return launch_frame_w<3, 1>(a, st);
+    case 7: return launch_frame_w<3, 2>(a, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -282,7 +278,7 @@ cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, in
                                    const float *gains2, int overlap, cudaStream_t st)
 {
     if (n_rows == 0) return cudaSuccess;
-    const size_t smem = (((size_t)n + HIST_CAP) * 4 + 15) & ~(size_t)15;
+    const size_t smem = ((size_t)n * 4 + 15) & ~(size_t)15;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     k_op_comb_inplace_w<<<n_rows, 32, smem, st>>>(y, row_stride, y_offset, n, params4, gains2, overlap);
     return cudaGetLastError();
@@ -310,7 +306,15 @@ static cudaError_t launch_softclip_convert_t(const float *dense, size_t dense_st
                                              uint32_t row_floats, uint32_t first_row, uint32_t n_rows, float *mem, void *out,
                                              size_t out_stride, cudaStream_t st)
 {
-    k_softclip_convert<T><<<n_rows, 32, (size_t)row_floats * sizeof(float), st>>>(dense, dense_stride, clip_len, channels, row_floats,
+    // the row is staged in shared memory: frame sizes beyond 120 ms (a larger buffer than any packet can fill) need more
+    // than the 48 KB default
+    const size_t smem = (size_t)row_floats * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_softclip_convert<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    k_softclip_convert<T><<<n_rows, 32, smem, st>>>(dense, dense_stride, clip_len, channels, row_floats,
                                                                                    first_row, mem, static_cast<T *>(out), out_stride);
     return cudaGetLastError();
 }

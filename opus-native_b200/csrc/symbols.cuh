@@ -37,6 +37,126 @@ __device__ __forceinline__ void load_pvq_table(uint32_t *s_data, uint16_t *s_row
 }
 
 // ---------------------------------------------------------------------------------------------
+// cwrsi (pvc.rs:182-284) walked by ONE LANE in EVENTS, not dimensions; `y` (zero-initialised by the caller, only nonzero
+// pulses are stored) receives the pulse vector, the return value is yy = sum y^2.  n <= 2 on entry skips the walk
+// (n == 0: nothing to do, the lane idles through its slot).
+//
+// While k < n (pvc.rs:232-258) a dimension is empty iff U(k,n) <= i < U(k+1,n), and stepping over it subtracts U(k,n);
+// after t empty dimensions i has lost A(t) = C(k,n) - C(k,n-t) (C = running row sum of U), so "dimension n-t is empty
+// given all before it were" reads A(t) + U(k,n-t) <= i < A(t) + U(k+1,n-t), or as one unsigned comparison
+// i - C(k,n) + C(k,n-t-1) < U(k+1,n-t) - U(k,n-t).  That predicate is monotone in t (once a dimension is occupied the
+// sequential loop stops there), so the length of the run of empty dimensions is found by bisection over t in [0, T],
+// T = n - max(k,2) being where the regime ends (k >= n, or the closed-form tail n == 2).  One event = one run + the
+// occupied dimension after it: a part with k pulses takes at most k+1 events instead of n-2 steps.
+// The single comparison is only valid while the 32-bit sums cannot wrap: C(k,n) + U(k+1,n) < 2^32.  `ev_nmax[k]` is the
+// largest n for which that holds (built next to the tables in upload_tables); above it the walk takes the reference's
+// one-dimension step until n has come down.  The k >= n regime keeps the reference's per-dimension code.
+// Every nonzero pulse is handed to `put(position, value)`; zero dimensions are never visited.
+template <class Sink>
+__device__ __forceinline__ int32_t cwrsi_events(const uint32_t *U, const uint2 *CW, const uint16_t *row, const uint8_t *ev_nmax,
+                                                uint32_t n, uint32_t k, uint32_t i, Sink &&put)
+{
+    int32_t yy = 0;
+    uint32_t y = 0u;  // position inside the part
+    uint32_t rk = row[min(k, 14u)], rk1 = row[min(k + 1u, 14u)];  // row offsets of U(k,.) and U(k+1,.): only read when k < n
+#pragma unroll 1
+    while (n > 2u) {
+        if (k >= n) {  // lots of pulses, pvc.rs:196-231: one dimension per event
+            const uint32_t rn = row[n];
+            uint32_t p = U[rn + k + 1u];
+            const int32_t sg = i >= p ? -1 : 0;
+            i -= (uint32_t)((int32_t)p & sg);
+            const uint32_t k0 = k;
+            const uint32_t q = U[rn + n];
+            if (q > i) {
+                k = n;
+                do {
+                    k -= 1u;
+                    p = U[row[k] + n];
+                } while (p > i);
+            } else {
+                p = U[rn + k];
+                while (p > i) {
+                    k -= 1u;
+                    p = U[rn + k];
+                }
+            }
+            i -= p;
+            const int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
+            if (val) put(y, val);
+            yy += val * val;
+            rk = row[min(k, 14u)];
+            rk1 = row[min(k + 1u, 14u)];
+            y++;
+            n -= 1u;
+        } else {  // lots of dimensions, pvc.rs:232-258
+            uint32_t T, lo = 0u;
+            if (n <= (uint32_t)ev_nmax[k]) {
+                T = n - max(k, 2u);
+                const uint2 *pw = CW + rk + n;                  // pw[-t] = (C(k,n-t-1), V(n-t-1,k))
+                const uint32_t ic = i - (pw[0].x + U[rk + n]);  // i - C(k,n)
+                uint32_t hi = T;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    const uint2 cw = pw[-(int32_t)mid];
+                    // i - A(mid) - U(k,n-mid) as one unsigned number: below V(n-mid-1,k) iff dimension n-mid is empty
+                    const bool empty = ic + cw.x < cw.y;
+                    lo = empty ? mid + 1u : lo;
+                    hi = empty ? hi : mid;
+                }
+                if (lo) i = ic + pw[1 - (int32_t)lo].x;  // i - A(lo)
+            } else {  // the sums could wrap for this (n, k): the reference's test of one dimension
+                T = 1u;
+                const uint32_t p = U[rk + n];
+                if (p <= i && i < U[rk1 + n]) {
+                    i -= p;
+                    lo = 1u;
+                }
+            }
+            y += lo;
+            n -= lo;
+            if (lo < T) {  // dimension n holds pulses
+                const uint32_t q = U[rk1 + n];
+                const int32_t sg = i >= q ? -1 : 0;
+                i -= (uint32_t)((int32_t)q & sg);
+                const uint32_t k0 = k;
+                uint32_t p;
+                do {
+                    k -= 1u;
+                    p = U[row[k] + n];
+                } while (p > i);
+                i -= p;
+                const int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
+                put(y, val);  // never zero here: k dropped by at least one
+                yy += val * val;
+                rk = row[k];
+                rk1 = row[k + 1u];
+                y++;
+                n -= 1u;
+            }
+        }
+    }
+    if (n == 2u) {
+        // n == 2 (pvc.rs:262-275)
+        uint32_t p = 2u * k + 1u;
+        int32_t sg = i >= p ? -1 : 0;
+        i -= (uint32_t)((int32_t)p & sg);
+        const uint32_t k0 = k;
+        k = (i + 1u) >> 1;
+        if (k != 0u) i -= 2u * k - 1u;
+        int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
+        if (val) put(y, val);
+        yy += val * val;
+        // n == 1 (pvc.rs:277-281)
+        sg = -(int32_t)i;
+        val = ((int32_t)k + sg) ^ sg;
+        if (val) put(y + 1u, val);
+        yy += val * val;
+    }
+    return yy;
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SYM_WARPS_PER_CTA * 32)
 k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ offsets,
                   const uint32_t *__restrict__ lens, uint32_t n_packets, const opn_op *__restrict__ ops,
@@ -45,10 +165,14 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
-    uint16_t *s_row = reinterpret_cast<uint16_t *>(s_pvq + PVQ_TABLE_WORDS);
-    int32_t *s_y = reinterpret_cast<int32_t *>(s_row + 16) + (threadIdx.x >> 5) * Y_STAGE;
-    uint8_t *s_pkt = reinterpret_cast<uint8_t *>(reinterpret_cast<int32_t *>(s_row + 16) + SYM_WARPS_PER_CTA * Y_STAGE) +
+    uint2 *s_cw = reinterpret_cast<uint2 *>(s_pvq + PVQ_TABLE_WORDS);
+    uint16_t *s_row = reinterpret_cast<uint16_t *>(s_cw + PVQ_TABLE_WORDS);
+    uint8_t *s_nmax = reinterpret_cast<uint8_t *>(s_row + 16);
+    int32_t *s_y = reinterpret_cast<int32_t *>(s_nmax + 16) + (threadIdx.x >> 5) * Y_STAGE;
+    uint8_t *s_pkt = reinterpret_cast<uint8_t *>(reinterpret_cast<int32_t *>(s_nmax + 16) + SYM_WARPS_PER_CTA * Y_STAGE) +
                      (threadIdx.x >> 5) * pkt_cap;
+    for (int i = threadIdx.x; i < PVQ_TABLE_WORDS; i += blockDim.x) s_cw[i] = g_tab.pvq_cw_data[i];
+    if (threadIdx.x < 16) s_nmax[threadIdx.x] = g_tab.pvq_ev_nmax[threadIdx.x];
     load_pvq_table(s_pvq, s_row);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t pkt = blockIdx.x * SYM_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -97,6 +221,22 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
             __syncwarp();
             break;
         }
+        case OPN_OP_PULSES_EVENTS: {
+            // decode_pulses (pvc.rs:156-160) with the product path's cwrsi: the event walk of k_synth_expand, run by lane 0
+            const uint32_t ci = d.uint(T.v(a, b));
+            for (uint32_t j = lane; j < a; j += 32u) s_y[j] = 0;
+            __syncwarp();
+            int32_t yy = 0;
+            if (lane == 0u) yy = cwrsi_events(s_pvq, s_cw, s_row, s_nmax, a, b, ci, [&](uint32_t at, int32_t val) { s_y[at] = val; });
+            yy = __shfl_sync(0xFFFFFFFFu, yy, 0);
+            __syncwarp();
+            v = __float_as_uint((float)yy);
+            if (y_out)
+                for (uint32_t j = lane; j < a; j += 32u) y_out[(size_t)pkt * y_stride + ny + j] = s_y[j];
+            ny += a;
+            __syncwarp();
+            break;
+        }
         case OPN_OP_SHRINK: d.shrink_storage(a); break;
         case OPN_OP_TELL: v = d.tell(); break;
         default: break;
@@ -131,12 +271,10 @@ k_rangedec_script(const uint8_t *__restrict__ arena, const uint32_t *__restrict_
 // Shared memory of k_synth_expand (per CTA of EXPAND_WARPS_PER_CTA warps):
 //   PVQ U(n,k) table 5088 B + bisection table 10176 B (both by TMA) + row offsets 32 B + mbarrier 16 B |
 //   entry table 72 x 16 B | per warp: codeword indices 72 x 4 B, gains 76 x 4 B (slot 72 = 0 for bins without a part), 16-bit pulses 2 x 960 x 2 B.
-constexpr int SYM_Y16 = 2 * 960;
-constexpr int SYNTH_GAIN_SLOTS = SYNTH_MAX_ENTRIES + 4;
-constexpr size_t SYM_EXPAND_WARP_BYTES = SYNTH_MAX_ENTRIES * 4 + SYNTH_GAIN_SLOTS * 4 + SYM_Y16 * 2;
+constexpr size_t SYM_EXPAND_WARP_BYTES = 2 * 960 * 4;  // coefficient rows of one packet
 __host__ __device__ constexpr size_t synth_expand_smem()
 {
-    return 3 * PVQ_TABLE_WORDS * 4 + 32 + 16 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)EXPAND_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
+    return 3 * PVQ_TABLE_WORDS * 4 + 32 + 16 + 16 + SYNTH_MAX_ENTRIES * sizeof(SynthEntry) + (size_t)EXPAND_WARPS_PER_CTA * SYM_EXPAND_WARP_BYTES;
 }
 
 __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(SymbolArgs A)
@@ -177,21 +315,28 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
     A.status[stream] = status;
     if (status < 0) return;
 
-    opn_synth_side *sd = A.side + stream;
+    // What the frame kernel needs travels in one 16-byte header; the full side record (energies included) is only
+    // written when the caller asked for it (operator entry / tests).
+    opn_synth_side *sd = A.side ? A.side + stream : nullptr;
     uint32_t *sw = reinterpret_cast<uint32_t *>(sd);
     constexpr uint32_t SIDE_WORDS = sizeof(opn_synth_side) / 4u;
     if (status == ITEM_LOST) {
-        for (uint32_t i = 0; i < SIDE_WORDS; i++) sw[i] = 0u;
+        if (sd)
+            for (uint32_t i = 0; i < SIDE_WORDS; i++) sw[i] = 0u;
+        A.hdr[stream] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     RangeDec d;
     d.init(src, len);
     const uint32_t silence = d.bit_logp(15u);
     if (silence) {
-        for (uint32_t i = 0; i < SIDE_WORDS; i++) sw[i] = 0u;
-        sd->silence = 1;
-        sd->final_rng = d.rng;
-        sd->tell_frac = d.tell_frac();
+        if (sd) {
+            for (uint32_t i = 0; i < SIDE_WORDS; i++) sw[i] = 0u;
+            sd->silence = 1;
+            sd->final_rng = d.rng;
+            sd->tell_frac = d.tell_frac();
+        }
+        A.hdr[stream] = make_uint4(1u, d.rng, d.tell_frac(), 0u);
         return;
     }
     const uint32_t postfilter = d.bit_logp(1u);
@@ -204,23 +349,31 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
     }
     const uint32_t transient = d.bit_logp(3u);
     const uint32_t intra = d.bit_logp(3u);
-    sd->silence = 0;
-    sd->postfilter = (int32_t)postfilter;
-    sd->octave = (int32_t)octave;
-    sd->period = (int32_t)period;
-    sd->gain_idx = (int32_t)gain_idx;
-    sd->tapset = (int32_t)tapset;
-    sd->transient = (int32_t)transient;
-    sd->intra = (int32_t)intra;
+    if (sd) {
+        sd->silence = 0;
+        sd->postfilter = (int32_t)postfilter;
+        sd->octave = (int32_t)octave;
+        sd->period = (int32_t)period;
+        sd->gain_idx = (int32_t)gain_idx;
+        sd->tapset = (int32_t)tapset;
+        sd->transient = (int32_t)transient;
+        sd->intra = (int32_t)intra;
+    }
     for (int b = 0; b < 21; b++) {
         const uint32_t decay = 6000u + 400u * (uint32_t)b;
         const uint32_t fs0 = s_fs0[b];
-        for (int c = 0; c < C; c++) sd->coarse[c][b] = d.laplace(fs0, decay);
-        if (C == 1) sd->coarse[1][b] = 0;
+        for (int c = 0; c < C; c++) {
+            const int32_t v = d.laplace(fs0, decay);
+            if (sd) sd->coarse[c][b] = v;
+        }
+        if (sd && C == 1) sd->coarse[1][b] = 0;
     }
     for (int b = 0; b < 21; b++) {
-        for (int c = 0; c < C; c++) sd->fine[c][b] = (int32_t)d.bits(2u);
-        if (C == 1) sd->fine[1][b] = 0;
+        for (int c = 0; c < C; c++) {
+            const uint32_t v = d.bits(2u);
+            if (sd) sd->fine[c][b] = (int32_t)v;
+        }
+        if (sd && C == 1) sd->fine[1][b] = 0;
     }
     uint32_t *idx = A.idx + (size_t)stream * SYNTH_MAX_ENTRIES;
     uint32_t n_pulses = 0u;
@@ -236,11 +389,89 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
         }
         idx[e] = v;
     }
-    sd->final_rng = d.rng;
-    sd->tell_frac = d.tell_frac();
-    sd->n_pulses = n_pulses;
+    const uint32_t tf = d.tell_frac();
+    if (sd) {
+        sd->final_rng = d.rng;
+        sd->tell_frac = tf;
+        sd->n_pulses = n_pulses;
+    }
+    A.hdr[stream] = make_uint4(hdr_pack(0u, postfilter, transient, intra, tapset, gain_idx, octave, period), d.rng, tf, n_pulses);
 }
 
+// PVQ expansion of one packet by one warp: codeword indices -> coefficient rows (SYNTH-CELT/1: unit-norm parts scaled by
+// 2^-5).  `rows` holds C channels of `chs` floats each and must be ZERO on entry: only the nonzero pulses are
+// written.  The parts are dealt to the lanes by the host-built slot tables (sorted by size, 32 per slot); a lane walks its
+// part with cwrsi_events and keeps the (position, value) pairs of the at most 6 nonzero pulses in one 64-bit register
+// (10 bits each: the schedule has n <= 64 and k <= 6, checked in upload_tables) until the part's norm is known.
+// Tables may live in shared or global memory.
+struct ExpandTables {
+    const uint32_t *U;
+    const uint2 *CW;
+    const uint16_t *row;
+    const uint8_t *nmax;
+    const SynthEntry *ent;  // [n_entries]
+};
+template <int C>
+__device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t lane, const uint32_t *__restrict__ idx, float *rows, int chs,
+                                         int32_t *__restrict__ y_out)
+{
+    const int nf = 120 << lm;
+    const int nslots = g_tab.synth_n_slots[lm][C - 1];
+    // everything a lane needs for its (at most SYNTH_SLOTS) parts is requested before the first walk starts
+    uint32_t ee[SYNTH_SLOTS], ii[SYNTH_SLOTS];
+#pragma unroll
+    for (int slot = 0; slot < SYNTH_SLOTS; slot++) {
+        ee[slot] = slot < nslots ? g_tab.synth_slot_entries[lm][C - 1][slot][lane] : 0xFFu;
+        ii[slot] = ee[slot] != 0xFFu ? __ldg(idx + ee[slot]) : 0u;
+    }
+#pragma unroll 1
+    for (int slot = 0; slot < nslots; slot++) {
+        uint32_t e = ee[0], i = ii[0];
+#pragma unroll
+        for (int q = 1; q < SYNTH_SLOTS; q++)
+            if (slot == q) { e = ee[q]; i = ii[q]; }
+        const bool has = e != 0xFFu;
+        const SynthEntry E = T.ent[has ? e : 0u];
+        uint32_t n = has ? E.n : 0u;
+        const uint32_t k = E.k;
+        uint64_t rec = 0ull;  // nonzero pulses, 10 bits each: position << 4 | (value & 15)
+        uint32_t cnt = 0u;
+        auto put = [&](uint32_t at, int32_t val) {
+            rec |= (uint64_t)((at << 4) | ((uint32_t)val & 15u)) << (10u * cnt);
+            cnt += 1u;
+        };
+        int32_t yy = 0;
+        if (has && n == 1u) {  // sign-only band
+            put(0u, i ? -1 : 1);
+            yy = 1;
+        } else if (has && k == 1u) {
+            // one pulse: cwrsi reduces to a closed form, y[i] = +1 for i < n, y[2n-1-i] = -1 otherwise
+            // (checked against the oracle for every band size in tests/test_oracle_kat.py::test_cwrsi_single_pulse_closed_form)
+            if (i < n) put(i, 1);
+            else put(2u * n - 1u - i, -1);
+            yy = 1;
+            n = 0u;  // done: takes no part in the walk below
+        }
+        yy += cwrsi_events(T.U, T.CW, T.row, T.nmax, n, k, i, put);
+        if (has) {
+            const float gain = 0.03125f / sqrtf((float)yy);
+            const uint32_t ch = E.base >= (uint32_t)nf ? 1u : 0u;
+            float *dst = rows + E.base + ch * (uint32_t)(chs - nf);
+#pragma unroll
+            for (uint32_t j = 0; j < 6u; j++) {
+                if (j < cnt) {
+                    const uint32_t r = (uint32_t)(rec >> (10u * j)) & 1023u;
+                    const int32_t val = ((int32_t)(r << 28)) >> 28;
+                    dst[r >> 4] = (float)val * gain;
+                    if (y_out) y_out[E.base + (r >> 4)] = val;
+                }
+            }
+        }
+    }
+}
+
+// Stand-alone expansion kernel (operator entry opn_op_synth_symbols and the unfused pipeline variant): the same w_expand
+// the frame kernel runs, with the PVQ tables staged in shared memory by TMA; the coefficient rows leave as float4.
 __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(SymbolArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -248,16 +479,14 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     uint32_t *s_pvq = reinterpret_cast<uint32_t *>(smem);
     uint2 *s_cw = reinterpret_cast<uint2 *>(s_pvq + PVQ_TABLE_WORDS);
     uint16_t *s_row = reinterpret_cast<uint16_t *>(s_cw + PVQ_TABLE_WORDS);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(s_row + 16);
+    uint8_t *s_nmax = reinterpret_cast<uint8_t *>(s_row + 16);  // 16 bytes: ev_nmax[k] of cwrsi_events
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_nmax + 16);
     SynthEntry *s_ent = reinterpret_cast<SynthEntry *>(bar + 2);
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) + (size_t)warp * SYM_EXPAND_WARP_BYTES;
-    int16_t *s_y = reinterpret_cast<int16_t *>(wbase);  // 16-byte aligned: zeroed as uint4, read back as 4 x int16
-    uint32_t *s_idx = reinterpret_cast<uint32_t *>(s_y + SYM_Y16);
-    float *s_gain = reinterpret_cast<float *>(s_idx + SYNTH_MAX_ENTRIES);
+    float *s_rows = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(s_ent + SYNTH_MAX_ENTRIES) + (size_t)warp * SYM_EXPAND_WARP_BYTES);
 
     const int lm = A.lm, C = A.channels, nf = 120 << lm;
     const int ne = g_tab.synth_n_entries[lm][C - 1];
-    // the two PVQ tables (15 KB) arrive by TMA while the warps fetch their indices and clear their pulse rows
+    // the two PVQ tables (15 KB) arrive by TMA while the warps clear their rows
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, 3 * PVQ_TABLE_WORDS * 4);
@@ -265,6 +494,7 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
         bulk_g2s(s_cw, g_tab.pvq_cw_data, 2 * PVQ_TABLE_WORDS * 4, bar);
     }
     if (threadIdx.x < 15) s_row[threadIdx.x] = g_tab.pvq_u_row[threadIdx.x];
+    if (threadIdx.x < 16) s_nmax[threadIdx.x] = g_tab.pvq_ev_nmax[threadIdx.x];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_tab.synth_entries[lm][C - 1]);
         uint4 *dst = reinterpret_cast<uint4 *>(s_ent);
@@ -273,193 +503,27 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     const uint32_t item = blockIdx.x * EXPAND_WARPS_PER_CTA + warp;
     const bool in_range = item < A.n_items;
     const uint32_t stream = in_range ? (A.stream_idx ? A.stream_idx[item] : item) : 0u;
-    // status, silence flag and codeword indices are requested together (one memory round trip, not three): the
-    // index rows exist for every stream, whatever the status turns out to be
     const int32_t status = in_range ? A.status[stream] : -1;
-    const int32_t silence = in_range ? A.side[stream].silence : 0;
-    if (in_range)
-        for (int e = lane; e < ne; e += 32) s_idx[e] = A.idx[(size_t)stream * SYNTH_MAX_ENTRIES + e];
+    const int32_t silence = in_range ? (int32_t)(A.hdr[stream].x & 1u) : 0;
     const bool zero_frame = status == ITEM_LOST || (status >= 0 && silence != 0);
-    for (int i = lane; i < C * nf / 8; i += 32) reinterpret_cast<uint4 *>(s_y)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();  // entry table, row offsets and the mbarrier are set up
-    if (status < 0) {
-        mbar_wait(bar, 0);  // do not let the CTA retire under the table transfer
-        return;
-    }
-
-    float4 *coef4 = A.coef ? reinterpret_cast<float4 *>(A.coef + (size_t)stream * C * nf) : nullptr;
-    int4 *yo4 = A.y_out ? reinterpret_cast<int4 *>(A.y_out + (size_t)stream * C * nf) : nullptr;
     const int nvec = C * nf / 4;
-    if (zero_frame) {
-        for (int i = lane; i < nvec; i += 32) {
-            if (coef4) coef4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yo4) yo4[i] = make_int4(0, 0, 0, 0);
-        }
-        mbar_wait(bar, 0);
-        return;
-    }
-    // bin -> part map of the coefficient write at the end: fetched now (15 words per lane at most), so the loads
-    // are long complete when the pulses are (the map sits in global memory; read in the loop, each L1 round trip
-    // was exposed: 28 % of the kernel's stall samples)
-    constexpr int MAX_VEC_PER_LANE = 2 * 960 / 4 / 32;
-    uint32_t ids[MAX_VEC_PER_LANE];
-    {
-        const uint32_t *ent4 = reinterpret_cast<const uint32_t *>(g_tab.synth_entry_of[lm][C - 1]);
-#pragma unroll
-        for (int j = 0; j < MAX_VEC_PER_LANE; j++) ids[j] = __ldg(ent4 + lane + 32 * j);  // always inside the 1920-byte map; unconditional so nothing waits on it here
-    }
-    // index -> pulse vector (cwrsi, pvc.rs:182-284; only nonzero pulses are stored).  The parts are sorted by
-    // size and dealt 32 at a time ("slots", tables: opn_kernels.cu), one part per lane; every lane walks its part
-    // in events (see below), the warp leaves a slot when its slowest lane is done.
+    for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4 *>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();  // entry table, row offsets and the mbarrier are set up
     mbar_wait(bar, 0);
-    {
-        const uint32_t *U = s_pvq;
-        const uint2 *CW = s_cw;
-        const uint16_t *row = s_row;
-        const int nslots = g_tab.synth_n_slots[lm][C - 1];
-#pragma unroll 1
-        for (int slot = 0; slot < nslots; slot++) {
-            const uint32_t e = g_tab.synth_slot_entries[lm][C - 1][slot][lane];
-            const bool has = e != 0xFFu;
-            const SynthEntry E = s_ent[has ? e : 0u];
-            uint32_t n = has ? E.n : 0u, k = E.k, i = has ? s_idx[e] : 0u;
-            int16_t *y = s_y + E.base;
-            int32_t yy = 0;
-            if (has && n == 1u) {  // sign-only band
-                *y = i ? (int16_t)-1 : (int16_t)1;
-                yy = 1;
-            } else if (has && k == 1u) {
-                // one pulse: cwrsi reduces to a closed form, y[i] = +1 for i < n, y[2n-1-i] = -1 otherwise
-                // (checked against the oracle for every band size in tests/test_oracle_kat.py::test_cwrsi_single_pulse_closed_form)
-                if (i < n) y[i] = (int16_t)1;
-                else y[2u * n - 1u - i] = (int16_t)-1;
-                yy = 1;
-                n = 0u;  // done: takes no part in the walk below
-            }
-            // A lane walks its part in EVENTS, not dimensions.  While k < n (pvc.rs:232-258) a dimension is
-            // empty iff U(k,n) <= i < U(k+1,n), and stepping over it subtracts U(k,n); after t empty dimensions
-            // i has lost A(t) = C(k,n) - C(k,n-t) (C = running row sum of U), so "dimension n-t is empty given
-            // all before it were" reads A(t) + U(k,n-t) <= i < A(t) + U(k+1,n-t), or as one unsigned comparison
-            // i - C(k,n) + C(k,n-t-1) < U(k+1,n-t) - U(k,n-t) (no sum wraps for the parts of the schedule: checked
-            // when the tables are built).  That predicate is monotone in t
-            // (once a dimension is occupied the sequential loop stops there), so the length of the run of empty
-            // dimensions is found by bisection over t in [0, T], T = n - max(k,2) being where the regime ends
-            // (k >= n, or the closed-form tail n == 2).  One event = one run + the occupied dimension after it:
-            // a part with k pulses takes at most k+1 events instead of n-2 lockstep steps.
-            uint32_t rk = row[min(k, 14u)], rk1 = row[min(k + 1u, 14u)];  // row offsets of U(k,.) and U(k+1,.): only read when k < n
-#pragma unroll 1
-            while (n > 2u) {
-                if (k >= n) {  // lots of pulses, pvc.rs:196-231: one dimension per event
-                    const uint32_t rn = row[n];
-                    uint32_t p = U[rn + k + 1u];
-                    const int32_t sg = i >= p ? -1 : 0;
-                    i -= (uint32_t)((int32_t)p & sg);
-                    const uint32_t k0 = k;
-                    const uint32_t q = U[rn + n];
-                    if (q > i) {
-                        k = n;
-                        do {
-                            k -= 1u;
-                            p = U[row[k] + n];
-                        } while (p > i);
-                    } else {
-                        p = U[rn + k];
-                        while (p > i) {
-                            k -= 1u;
-                            p = U[rn + k];
-                        }
-                    }
-                    i -= p;
-                    const int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
-                    *y = (int16_t)val;
-                    yy += val * val;
-                    rk = row[min(k, 14u)];
-                    rk1 = row[min(k + 1u, 14u)];
-                    y++;
-                    n -= 1u;
-                } else {  // lots of dimensions, pvc.rs:232-258
-                    const uint32_t T = n - max(k, 2u);
-                    const uint2 *pw = CW + rk + n;              // pw[-t] = (C(k,n-t-1), V(n-t-1,k))
-                    const uint32_t ic = i - (pw[0].x + U[rk + n]);  // i - C(k,n)
-                    uint32_t lo = 0u, hi = T;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        const uint2 cw = pw[-(int32_t)mid];
-                        // i - A(mid) - U(k,n-mid) as one unsigned number: below V(n-mid-1,k) iff dimension n-mid is empty
-                        const bool empty = ic + cw.x < cw.y;
-                        lo = empty ? mid + 1u : lo;
-                        hi = empty ? hi : mid;
-                    }
-                    if (lo) i = ic + pw[1 - (int32_t)lo].x;  // i - A(lo)
-                    y += lo;
-                    n -= lo;
-                    if (lo < T) {  // dimension n holds pulses
-                        const uint32_t q = U[rk1 + n];
-                        const int32_t sg = i >= q ? -1 : 0;
-                        i -= (uint32_t)((int32_t)q & sg);
-                        const uint32_t k0 = k;
-                        uint32_t p;
-                        do {
-                            k -= 1u;
-                            p = U[row[k] + n];
-                        } while (p > i);
-                        i -= p;
-                        const int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
-                        *y = (int16_t)val;
-                        yy += val * val;
-                        rk = row[k];
-                        rk1 = row[k + 1u];
-                        y++;
-                        n -= 1u;
-                    }
-                }
-            }
-            if (n == 2u) {
-                // n == 2 (pvc.rs:262-275)
-                uint32_t p = 2u * k + 1u;
-                int32_t sg = i >= p ? -1 : 0;
-                i -= (uint32_t)((int32_t)p & sg);
-                const uint32_t k0 = k;
-                k = (i + 1u) >> 1;
-                if (k != 0u) i -= 2u * k - 1u;
-                int32_t val = ((int32_t)k0 - (int32_t)k + sg) ^ sg;
-                y[0] = (int16_t)val;
-                yy += val * val;
-                // n == 1 (pvc.rs:277-281)
-                sg = -(int32_t)i;
-                val = ((int32_t)k + sg) ^ sg;
-                y[1] = (int16_t)val;
-                yy += val * val;
-            }
-            if (has) s_gain[e] = 0.03125f / sqrtf((float)yy);
-        }
-        if (lane == 0) s_gain[SYNTH_MAX_ENTRIES] = 0.0f;
+    if (status < 0) return;
+    float4 *coef4 = A.coef ? reinterpret_cast<float4 *>(A.coef + (size_t)stream * C * nf) : nullptr;
+    int32_t *yo = A.y_out ? A.y_out + (size_t)stream * C * nf : nullptr;
+    if (yo)
+        for (int i = lane; i < nvec; i += 32) reinterpret_cast<int4 *>(yo)[i] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    if (!zero_frame) {
+        const ExpandTables T{s_pvq, s_cw, s_row, s_nmax, s_ent};
+        if (C == 2) w_expand<2>(T, lm, lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, s_rows, nf, yo);
+        else w_expand<1>(T, lm, lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, s_rows, nf, yo);
     }
     __syncwarp();
-    // pulses x gain -> coefficient rows, 4 bins per lane and step (entry_of: bin -> part)
-    {
-        const uint2 *y4 = reinterpret_cast<const uint2 *>(s_y);
-#pragma unroll
-        for (int j = 0; j < MAX_VEC_PER_LANE; j++) {
-            const int i = (int)lane + 32 * j;
-            if (i >= nvec) break;
-            const uint32_t idw = ids[j];
-            const uint2 yr = y4[i];
-            int4 yv;
-            float4 cv;
-            const uint32_t e0 = idw & 0xFFu, e1 = (idw >> 8) & 0xFFu, e2 = (idw >> 16) & 0xFFu, e3 = idw >> 24;
-            yv.x = (int32_t)(int16_t)(yr.x & 0xFFFFu);  // bins without a part were zeroed above
-            yv.y = (int32_t)(int16_t)(yr.x >> 16);
-            yv.z = (int32_t)(int16_t)(yr.y & 0xFFFFu);
-            yv.w = (int32_t)(int16_t)(yr.y >> 16);
-            cv.x = (float)yv.x * s_gain[e0];  // bins without a part: pulse 0 x gain slot 72 (= 0)
-            cv.y = (float)yv.y * s_gain[e1];
-            cv.z = (float)yv.z * s_gain[e2];
-            cv.w = (float)yv.w * s_gain[e3];
-            if (coef4) coef4[i] = cv;
-            if (yo4) yo4[i] = yv;
-        }
-    }
+    if (coef4)
+        for (int i = lane; i < nvec; i += 32) coef4[i] = reinterpret_cast<const float4 *>(s_rows)[i];
 }
 
 }  // namespace opn

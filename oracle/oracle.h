@@ -141,9 +141,14 @@ typedef struct {
     uint32_t final_rng, tell_frac, n_pulses;
 } orc_synth_side;
 
+#define ORC_SYNTH_HIST 1024 /* T + 2 <= 1024 */
+#define ORC_SYNTH_BUF (ORC_SYNTH_HIST + 8 * 960 + 60)
 typedef struct {
-    float carry[2][60];        /* un-windowed IMDCT tail of the previous frame      */
-    float hist[2][1024];       /* last 1024 post-filtered output samples (T+2 <= 1024) */
+    /* Rolling output buffer per channel: [.. history | frame | 60-sample un-windowed IMDCT tail].  Frames are
+     * appended at `pos` (the previous frame's tail is already there, the comb history directly below it); when
+     * the buffer is full the last 1024 samples + tail move to the front (once per 8 long frames). */
+    float buf[2][ORC_SYNTH_BUF];
+    uint32_t pos;
     int32_t pf_period, pf_tapset;  /* post-filter parameters of the previous frame  */
     float pf_gain;
 } orc_synth_state;
@@ -154,6 +159,11 @@ void orc_synth_state_init(orc_synth_state *s);
 int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm,
                            int channels, int apply_comb, orc_synth_side *side, int32_t *y_out,
                            float *coef_out, float *pcm_out);
+/* SYNTH-CELT/1 packet generator on the oracle's own range encoder (same seeded draws as opn_synth_packet). */
+int orc_synth_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes,
+                     uint32_t transient_permille, uint8_t *out);
+int orc_synth_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,
+                   uint32_t pkt_bytes, uint32_t transient_permille, int n_threads, uint8_t *out);
 /* Multithreaded CPU baseline: streams statically partitioned over n_threads; each thread walks
  * its streams frame by frame.  packets: [n_frames][n_streams][pkt_bytes].  Returns seconds. */
 double orc_synth_bench(const uint8_t *packets, uint32_t n_streams, uint32_t n_frames,

@@ -18,10 +18,14 @@
 #include <string.h>
 #include <time.h>
 
-#define HIST 1024
+#define HIST ORC_SYNTH_HIST
 static const uint8_t TAPSET_ICDF[3] = {2, 1, 0};
 
-void orc_synth_state_init(orc_synth_state *s) { memset(s, 0, sizeof(*s)); }
+void orc_synth_state_init(orc_synth_state *s)
+{
+    memset(s, 0, sizeof(*s));
+    s->pos = HIST;
+}
 
 static void decode_symbols(orc_dec *d, int lm, int channels, orc_synth_side *side, int32_t *y_out,
                            float *coef)
@@ -109,10 +113,13 @@ int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t
 
     int blocks = side->transient ? (1 << lm) : 1;
     int shift = side->transient ? 3 : 3 - lm;
-    float work[HIST + 960 + 60];
+    if (st->pos + (uint32_t)nf + 60 > ORC_SYNTH_BUF) { /* buffer full: history + tail to the front */
+        for (int c = 0; c < channels; c++)
+            memmove(st->buf[c], st->buf[c] + st->pos - HIST, sizeof(float) * (HIST + 60));
+        st->pos = HIST;
+    }
     for (int c = 0; c < channels; c++) {
-        memcpy(work, st->hist[c], sizeof(float) * HIST);
-        memcpy(work + HIST, st->carry[c], sizeof(float) * 60);
+        float *work = st->buf[c] + st->pos - HIST; /* work[HIST .. HIST+60) already holds the previous tail */
         memset(work + HIST + 60, 0, sizeof(float) * (size_t)nf);
         for (int b = 0; b < blocks; b++)
             orc_mdct_backward(coef + c * nf + b, work + HIST + 120 * b * (blocks > 1), ORC_WINDOW,
@@ -121,13 +128,130 @@ int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t
             orc_comb_filter_inplace(work, HIST, (size_t)st->pf_period, (size_t)t1, (size_t)nf,
                                     st->pf_gain, g1, (size_t)st->pf_tapset, (size_t)tap1, ORC_OVERLAP);
         for (int i = 0; i < nf; i++) pcm_out[i * channels + c] = work[HIST + i];
-        memcpy(st->carry[c], work + HIST + nf, sizeof(float) * 60);
-        memcpy(st->hist[c], work + nf, sizeof(float) * HIST);
     }
+    st->pos += (uint32_t)nf;
     st->pf_period = t1;
     st->pf_gain = g1;
     st->pf_tapset = tap1;
     return nf;
+}
+
+/* ------------------------------------------------------------------ packet generator
+ * SYNTH-CELT/1 packets for the reference arm of bench.py (so that it never loads the product library) and for
+ * cross-checking the product's generator: the same splitmix64 stream and draw order as opn_synth_packet
+ * (seed 42 + 1000003*stream, per frame), written with the oracle's own range encoder. */
+typedef struct { uint64_t s; } splitmix64;
+static uint64_t sm_next(splitmix64 *r)
+{
+    uint64_t z = (r->s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static uint32_t sm_below(splitmix64 *r, uint32_t n) { return (uint32_t)(((sm_next(r) >> 32) * (uint64_t)n) >> 32); }
+
+static int synth_packet_attempt(uint64_t stream_id, uint64_t frame_idx, uint32_t attempt, int lm, int channels,
+                                uint32_t pkt_bytes, uint32_t transient_permille, uint8_t *out)
+{
+    /* TOC: CELT-only fullband, frame size by LM, stereo flag, code 0 (src/lib.rs:271-289, 317-325) */
+    out[0] = (uint8_t)(0x80 | 0x60 | (lm << 3) | (channels == 2 ? 0x4 : 0));
+    splitmix64 rng = {42ull + 1000003ull * stream_id + 0xD1B54A32D192ED03ull * frame_idx + 0x2545F4914F6CDD1Dull * attempt};
+    orc_enc e;
+    orc_enc_init(&e, out + 1, pkt_bytes - 1);
+    orc_enc_bit_logp(&e, 0, 15);
+    uint32_t postfilter = (uint32_t)(sm_next(&rng) & 1);
+    orc_enc_bit_logp(&e, postfilter, 1);
+    if (postfilter) {
+        uint32_t octave = sm_below(&rng, 6);
+        uint32_t fine_period = sm_below(&rng, 1u << (4 + octave));
+        uint32_t gain_idx = sm_below(&rng, 8);
+        uint32_t tapset = sm_below(&rng, 3);
+        orc_enc_uint(&e, octave, 6);
+        orc_enc_bits(&e, fine_period, 4 + octave);
+        orc_enc_bits(&e, gain_idx, 3);
+        orc_enc_icdf(&e, tapset, TAPSET_ICDF, 2);
+    }
+    orc_enc_bit_logp(&e, sm_below(&rng, 1000) < transient_permille ? 1u : 0u, 3);
+    orc_enc_bit_logp(&e, sm_below(&rng, 8) == 0 ? 1u : 0u, 3);
+    for (int b = 0; b < 21; b++)
+        for (int c = 0; c < channels; c++) {
+            uint32_t decay = 6000u + 400u * (uint32_t)b;
+            int32_t v = (int32_t)sm_below(&rng, 16) - 7;
+            orc_enc_laplace(&e, &v, orc_laplace_start_freq(decay), decay);
+        }
+    for (int b = 0; b < 21; b++)
+        for (int c = 0; c < channels; c++) orc_enc_bits(&e, sm_below(&rng, 4), 2);
+    for (int b = 0; b < 21; b++)
+        for (int c = 0; c < channels; c++) {
+            uint32_t n = ORC_SYNTH_SCHED[lm][b][0], parts = ORC_SYNTH_SCHED[lm][b][1], k = ORC_SYNTH_SCHED[lm][b][2];
+            if (n == 1) {
+                orc_enc_bits(&e, (uint32_t)(sm_next(&rng) & 1), 1);
+                continue;
+            }
+            for (uint32_t p = 0; p < parts; p++) {
+                uint32_t v = orc_pvq_v(n, k);
+                orc_enc_uint(&e, sm_below(&rng, v), v); /* a uniform codeword index == encode_pulses(cwrsi(index)) */
+            }
+        }
+    if (e.error) return e.error;
+    if (orc_enc_tell(&e) > 8u * (pkt_bytes - 1u)) return ORC_ERR_BUFFER_TOO_SMALL;
+    orc_enc_done(&e);
+    return e.error ? e.error : (int)pkt_bytes;
+}
+
+int orc_synth_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes,
+                     uint32_t transient_permille, uint8_t *out)
+{
+    if (!out || lm < 0 || lm > 3 || channels < 1 || channels > 2 || pkt_bytes < 3 || pkt_bytes > 1276) return ORC_ERR_BAD_ARG;
+    int rc = ORC_ERR_BUFFER_TOO_SMALL; /* a draw that overruns the byte budget is redrawn from the next sub-seed */
+    for (uint32_t attempt = 0; attempt < 8 && rc == ORC_ERR_BUFFER_TOO_SMALL; attempt++)
+        rc = synth_packet_attempt(stream_id, frame_idx, attempt, lm, channels, pkt_bytes, transient_permille, out);
+    return rc;
+}
+
+typedef struct {
+    uint64_t first_stream, first_frame, w0, w1;
+    uint32_t n_streams, pkt_bytes, transient_permille;
+    int lm, channels, rc;
+    uint8_t *out;
+} fill_job;
+
+static void *fill_thread(void *arg)
+{
+    fill_job *j = (fill_job *)arg;
+    for (uint64_t w = j->w0; w < j->w1; w++) {
+        int r = orc_synth_packet(j->first_stream + w % j->n_streams, j->first_frame + w / j->n_streams, j->lm, j->channels,
+                                 j->pkt_bytes, j->transient_permille, j->out + w * j->pkt_bytes);
+        if (r < 0) j->rc = r;
+    }
+    return NULL;
+}
+
+/* layout [frame][stream][pkt_bytes], like opn_synth_fill */
+int orc_synth_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,
+                   uint32_t pkt_bytes, uint32_t transient_permille, int n_threads, uint8_t *out)
+{
+    if (!out || n_streams == 0 || n_frames == 0) return ORC_ERR_BAD_ARG;
+    if (n_threads < 1) n_threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    fill_job *jobs = (fill_job *)calloc((size_t)n_threads, sizeof(fill_job));
+    const uint64_t total = (uint64_t)n_streams * n_frames;
+    for (int t = 0; t < n_threads; t++) {
+        fill_job *j = &jobs[t];
+        j->first_stream = first_stream; j->first_frame = first_frame;
+        j->w0 = total * (uint64_t)t / (uint64_t)n_threads; j->w1 = total * (uint64_t)(t + 1) / (uint64_t)n_threads;
+        j->n_streams = n_streams; j->pkt_bytes = pkt_bytes; j->transient_permille = transient_permille;
+        j->lm = lm; j->channels = channels; j->out = out;
+        pthread_create(&th[t], NULL, fill_thread, j);
+    }
+    int rc = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        if (jobs[t].rc < 0) rc = jobs[t].rc;
+    }
+    free(th);
+    free(jobs);
+    return rc;
 }
 
 /* ------------------------------------------------------------------ CPU baseline */

@@ -38,7 +38,7 @@ class SynthSide(C.Structure):
 
 
 class SynthState(C.Structure):
-    _fields_ = [("carry", (C.c_float * 60) * 2), ("hist", (C.c_float * 1024) * 2),
+    _fields_ = [("buf", (C.c_float * (1024 + 8 * 960 + 60)) * 2), ("pos", C.c_uint32),
                 ("pf_period", C.c_int32), ("pf_tapset", C.c_int32), ("pf_gain", C.c_float)]
 
 
@@ -123,6 +123,8 @@ def lib():
     sig("orc_synth_state_init", None, C.POINTER(SynthState))
     sig("orc_synth_decode_frame", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int,
         C.POINTER(SynthSide), vp, vp, vp)
+    sig("orc_synth_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp)
+    sig("orc_synth_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("orc_synth_bench", C.c_double, vp, u32, u32, u32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32))
     _lib = L
     return L
@@ -178,6 +180,14 @@ def comb_filter(y, y_offset, x, x_offset, t0, t1, n, g0, g1, tap0, tap1, overlap
     x = np.ascontiguousarray(x, dtype=np.float32)
     lib().orc_comb_filter(ptr(y), y_offset, ptr(x), x_offset, t0, t1, n, g0, g1, tap0, tap1, overlap)
     return y
+
+
+def synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt_bytes, transient_permille=0, n_threads=1):
+    """-> uint8 [n_frames, n_streams, pkt_bytes], generated with the oracle's range encoder"""
+    out = np.zeros((n_frames, n_streams, pkt_bytes), np.uint8)
+    rc = lib().orc_synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt_bytes, transient_permille, n_threads, ptr(out))
+    assert rc == 0, rc
+    return out
 
 
 class SynthStream:

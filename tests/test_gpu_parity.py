@@ -16,6 +16,7 @@ import oracle_lib as O
 pytestmark = pytest.mark.gpu
 KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
 PCM_TOL = 1e-5  # north_star: max-abs PCM error
+SYNTH = dict(bitstream=opn.BITSTREAM_SYNTH_CELT_1)  # CELT frames only decode after this explicit opt-in (opusb200.h)
 
 
 def snr_db(want, got):
@@ -183,6 +184,36 @@ def test_cwrsi_all_band_sizes():
                 assert L.orc_icwrs(O.ptr(y[j].copy()), n) == i
 
 
+def test_cwrsi_event_walk_all_band_sizes():
+    """The product path's cwrsi (cwrsi_events in csrc/symbols.cuh: the function k_synth_expand calls, reached here through
+    OPN_OP_PULSES_EVENTS) on the whole (N, K) ladder of celt/pvc.rs:462-503, including the shapes whose 32-bit running
+    sums would wrap ((24,9), (18,11), (16,12): the walk falls back to the reference's one-dimension step there)."""
+    def get_pulses(i):
+        return i if i < 8 else (8 + (i & 7)) << ((i >> 3) - 1)
+
+    L = O.lib()
+    rnd = np.random.default_rng(11)
+    for n, kmax in zip(KATS["pvc_pn"], KATS["pvc_pk_max"]):
+        for pseudo in range(1, 41):
+            k = get_pulses(pseudo)
+            if k > kmax:
+                break
+            nc = L.orc_pvq_v(n, k)
+            idx = np.unique(np.concatenate([np.linspace(0, nc - 1, 40).astype(np.uint64), rnd.integers(0, nc, 24).astype(np.uint64)])).astype(np.uint32)
+            eop = np.array([(opn.OP_UINT, nc, 0)], opn.OP_DTYPE)
+            arena = np.concatenate([opn.enc_run_script(16, eop, [int(i)])[0] for i in idx])
+            offsets = np.arange(len(idx), dtype=np.uint32) * 16
+            lens = np.full(len(idx), 16, np.uint32)
+            out, y = opn.op_rangedec_script(arena, offsets, lens, np.array([(opn.OP_PULSES_EVENTS, n, k)], opn.OP_DTYPE), y_stride=n)
+            ref, yref = opn.op_rangedec_script(arena, offsets, lens, np.array([(opn.OP_PULSES, n, k)], opn.OP_DTYPE), y_stride=n)
+            assert np.array_equal(y, yref) and np.array_equal(out, ref), (n, k)  # both device implementations agree
+            want = np.zeros(n, np.int32)
+            for j, i in enumerate(idx):
+                yy = L.orc_cwrsi(O.ptr(want), n, k, int(i))
+                assert np.array_equal(y[j], want), (n, k, int(i))
+                assert out[j, 0]["value"] == np.float32(yy).view(np.uint32)
+
+
 # ------------------------------------------------------------------ IMDCT + TDAC (a12-a14, a17)
 @pytest.mark.parametrize("shift", [0, 1, 2, 3])
 def test_imdct_tdac_long_blocks(shift):
@@ -337,6 +368,33 @@ def test_synth_symbols(lm, channels, pkt_bytes):
         assert np.array_equal(coef[s].reshape(-1).view(np.uint32), wc.view(np.uint32))
 
 
+@pytest.mark.parametrize("lm,channels", [(3, 2), (3, 1), (2, 2), (0, 2), (0, 1)])
+def test_synth_symbols_garbage_and_truncated_payloads(lm, channels):
+    """Corrupt input through the PRODUCT kernels (k_synth_rangedec's uint_precomputed / div_small_quotient / div_magic
+    and k_synth_expand), not the generic script decoder: random bytes and truncated real payloads of 2..160 bytes must
+    give exactly what the reference's arithmetic gives (zero extension past the buffer, decode_uint saturating at ft-1,
+    decoder.rs:86-104, 255-259) -- every symbol, the final range, tell_frac, pulses and coefficients."""
+    rnd = np.random.default_rng(100 * lm + channels)
+    lens = np.concatenate([np.arange(2, 161, 3), rnd.integers(2, 161, 80)]).astype(np.uint32)
+    n = len(lens)
+    offsets = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    arena = rnd.integers(0, 256, int(lens.sum()) + 8).astype(np.uint8)
+    # every third packet: a real payload cut short instead of noise (valid prefix, then zero extension)
+    real = opn.synth_fill(7, n, 0, 1, lm, channels, 161, transient_permille=300)[0][:, 1:]
+    for s in range(0, n, 3):
+        arena[offsets[s]:offsets[s] + lens[s]] = real[s, :lens[s]]
+    arena[offsets[1]] &= 0x7F  # make sure noise packets do not all start with the silence flag pattern
+    side, y, coef = opn.op_synth_symbols(arena, offsets, lens, lm, channels)
+    for s in range(n):
+        w, wy, wc, _ = O.SynthStream(lm, channels).decode(arena[offsets[s]:offsets[s] + lens[s]])
+        for f in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra", "final_rng", "tell_frac", "n_pulses"):
+            assert side[s][f] == getattr(w, f), (s, int(lens[s]), f)
+        assert np.array_equal(side[s]["coarse"], np.ctypeslib.as_array(w.coarse)), s
+        assert np.array_equal(side[s]["fine"], np.ctypeslib.as_array(w.fine)), s
+        assert np.array_equal(y[s].reshape(-1), wy), (s, int(lens[s]))
+        assert np.array_equal(coef[s].reshape(-1).view(np.uint32), wc.view(np.uint32)), s
+
+
 def test_bitexact_trig_checksums():
     """bitexact_cos / bitexact_log2tan on the device against the reference's own checksums
     (src/math.rs:237-298) and, value by value, against the oracle."""
@@ -384,7 +442,7 @@ def test_batch_decode_chain(lm, channels, pkt_bytes, postfilter):
     ns, nfr, nf = 48, 12 if lm == 3 else 20, 120 << lm
     packets = opn.synth_fill(7, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=150)
     want, want_rng = _oracle_chain(packets, lm, channels, postfilter)
-    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), postfilter=postfilter)
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), postfilter=postfilter, **SYNTH)
     offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
     lens = np.full(ns, pkt_bytes, np.uint32)
     exact = True
@@ -409,7 +467,7 @@ def test_batch_frame_size_changes_mid_stream(channels):
     if channels == 1:
         pkt_bytes = {0: 48, 1: 60, 2: 80, 3: 100}
     oracle = [O.SynthStream(3, channels) for _ in range(ns)]
-    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0))
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **SYNTH)
     exact = True
     for f, lm in enumerate(lms):
         nf, pb = 120 << lm, pkt_bytes[lm]
@@ -434,7 +492,7 @@ def test_batch_submit_wait_two_calls_in_flight():
     packets = opn.synth_fill(1234, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
     offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
     lens = np.full(ns, pkt_bytes, np.uint32)
-    sync = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0))
+    sync = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **SYNTH)
     want = []
     for f in range(nfr):
         pcm = np.zeros((ns, nf * channels), np.float32)
@@ -444,7 +502,7 @@ def test_batch_submit_wait_two_calls_in_flight():
     for f in range(nfr):
         for s in range(8):
             assert np.array_equal(oracle[s].decode(packets[f, s, 1:])[3], want[f][s])
-    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0))
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **SYNTH)
     bufs = [np.zeros((ns, nf * channels), np.float32) for _ in range(2)]
     res = [np.zeros(ns, np.int32) for _ in range(2)]
     arenas = [np.ascontiguousarray(packets[f].reshape(-1)) for f in range(nfr)]
@@ -466,7 +524,7 @@ def test_batch_submit_wait_two_calls_in_flight():
 def test_batch_lost_invalid_and_foreign_packets_do_not_poison_neighbours():
     lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 16, 6, 960
     packets = opn.synth_fill(99, ns, 0, nfr, lm, channels, pkt_bytes)
-    dec = opn.BatchDecoder(ns)
+    dec = opn.BatchDecoder(ns, **SYNTH)
     oracle = [O.SynthStream(lm, channels) for _ in range(ns)]
     offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
     for f in range(nfr):
@@ -508,7 +566,7 @@ def test_batch_multi_frame_packets_and_larger_frame_size():
     lm, channels, fb, ns, nf = 2, 2, 129, 8, 480
     frames = opn.synth_fill(3, ns, 0, 6, lm, channels, fb + 1)[:, :, 1:]  # payloads without TOC
     toc = 0x80 | 0x60 | (lm << 3) | 0x4
-    dec = opn.BatchDecoder(ns)
+    dec = opn.BatchDecoder(ns, **SYNTH)
     oracle = [O.SynthStream(lm, channels) for _ in range(ns)]
     # packet A: code 1, frames 0,1 ; packet B: code 3 CBR with 3 frames + 5 bytes padding ; packet C: code 0
     pa = [np.concatenate([[toc | 1], frames[0, s], frames[1, s]]).astype(np.uint8) for s in range(ns)]
@@ -547,7 +605,7 @@ def test_batch_mixed_frame_sizes_across_streams_in_one_call():
     pkt_bytes = {0: 80, 1: 100, 2: 130, 3: 160}
     oracle = [O.SynthStream(int(lm_of[s]), channels) for s in range(ns)]
     by_lm = {lm: np.nonzero(lm_of == lm)[0] for lm in range(4)}
-    dec = opn.BatchDecoder(ns)
+    dec = opn.BatchDecoder(ns, **SYNTH)
     stride = 160
     exact = True
     for f in range(ncalls):
@@ -596,7 +654,7 @@ def test_batch_device_resident_path_matches_host_path():
     d_len = torch.full((ns,), pkt_bytes, dtype=torch.int32, device=dev)
     d_pcm = torch.zeros((ns, nf * channels), dtype=torch.float32, device=dev)
     d_res = torch.zeros(ns, dtype=torch.int32, device=dev)
-    dec = opn.BatchDecoder(ns)
+    dec = opn.BatchDecoder(ns, **SYNTH)
     keep = [s for s in range(ns) if s != 10]
     for f in range(nfr):
         dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), d_pcm.data_ptr(),
@@ -629,7 +687,7 @@ def test_batch_device_resident_steps_enqueued_back_to_back(postfilter):
     d_pcm = torch.zeros((nfr, ns, nf * channels), dtype=torch.float32, device=dev)
     d_res = torch.zeros((nfr, ns), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
-    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), postfilter=postfilter)
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), postfilter=postfilter, **SYNTH)
     flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY
     for f in range(nfr):
         dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), d_pcm[f].data_ptr(),
@@ -666,11 +724,11 @@ def test_batch_reset_in_the_middle_of_a_pipelined_run():
         dec.synchronize()
         return out.cpu().numpy()
 
-    dec = opn.BatchDecoder(ns)
+    dec = opn.BatchDecoder(ns, **SYNTH)
     run(dec, [0, 1, 2, 3, 4])          # leaves state behind; five steps were in flight
     dec.reset()
     again = run(dec, [5, 6, 7, 8])
-    fresh = run(opn.BatchDecoder(ns), [5, 6, 7, 8])
+    fresh = run(opn.BatchDecoder(ns, **SYNTH), [5, 6, 7, 8])
     assert np.array_equal(again, fresh)
     want, _ = _oracle_chain(packets[5:9], lm, channels)
     assert np.array_equal(again, want)
@@ -687,6 +745,72 @@ def test_batch_reset_in_the_middle_of_a_pipelined_run():
     assert e.value.kind == "BadArguments"
 
 
+def test_batch_reset_without_synchronize_while_steps_are_in_flight():
+    """opn_batch_reset straight after enqueueing device-resident steps, with NO synchronize in between: the frame
+    kernels of those steps are still running (they write the PCM ring, the carry and the post-filter state), so the
+    reset has to drain every pipeline stream before it clears anything.  Afterwards the batch must decode exactly like
+    a new one; a frame kernel that outlived the memsets would leave a stale frame in the ring = comb history of the
+    frames that follow."""
+    torch = pytest.importorskip("torch")
+    lm, channels, pkt_bytes, ns, nf = 3, 2, 160, 2048, 960  # large enough for the enqueued steps to outlast the host
+    packets = opn.synth_fill(5100, ns, 0, 8, lm, channels, pkt_bytes, transient_permille=100)
+    dev = torch.device("cuda:0")
+    d_arena = torch.from_numpy(packets.reshape(-1).copy()).to(dev)
+    d_off = torch.arange(ns, dtype=torch.int32, device=dev) * pkt_bytes
+    d_len = torch.full((ns,), pkt_bytes, dtype=torch.int32, device=dev)
+    d_res = torch.zeros(ns, dtype=torch.int32, device=dev)
+    out = torch.zeros((4, ns, nf * channels), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY
+
+    def step(dec, f, dst):
+        dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), dst, nf * channels if dst else 0,
+                              nf, d_res.data_ptr(), flags | (0 if dst else opn.FLAG_NO_PCM_COPY))
+
+    dec = opn.BatchDecoder(ns, **SYNTH)
+    for rep in range(3):
+        for f in range(4):
+            step(dec, f, None)
+        dec.reset()  # no synchronize: four steps are in flight
+        for k, f in enumerate(range(4, 8)):
+            step(dec, f, out[k].data_ptr())
+        dec.synchronize()
+        got = out.cpu().numpy()
+        if rep == 0:
+            picks = [0, 1, 777, ns - 1]
+            want, _ = _oracle_chain(packets[4:8][:, picks], lm, channels)
+        assert np.array_equal(got[:, picks], want), rep
+        if rep == 0:
+            first = got.copy()
+        assert np.array_equal(got, first), rep
+
+
+def test_celt_frames_need_the_explicit_bitstream_opt_in():
+    """CeltDecoder::decode is todo!() in the crate (celt/decoder.rs:47-56).  A decoder created the way a drop-in caller
+    creates it (OPN_BITSTREAM_OPUS) must not turn CELT packets into sound: it reports Unimplemented, per stream on the
+    batch path, and leaves the streams' state alone; only OPN_BITSTREAM_SYNTH_CELT_1 decodes the synthetic layout."""
+    lm, channels, pkt_bytes, ns, nf = 3, 2, 160, 8, 960
+    packets = opn.synth_fill(1, ns, 0, 1, lm, channels, pkt_bytes)[0]
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+    lens[3] = 0  # a lost packet before anything was decoded: zeros (decoder.rs:478-487), not an error
+    pcm = np.full((ns, nf * channels), 7.0, np.float32)
+    res = opn.BatchDecoder(ns).decode_float(packets.reshape(-1), offsets, lens, pcm, nf)
+    assert [int(r) for r in res] == [-6, -6, -6, nf, -6, -6, -6, -6]
+    assert not pcm[3].any()
+    with pytest.raises(opn.OpusError) as e:
+        opn.Decoder().decode_float(packets[0], np.zeros(nf * channels, np.float32), nf)
+    assert e.value.kind == "Unimplemented"
+    torch = pytest.importorskip("torch")
+    d = torch.zeros(16, dtype=torch.int32, device="cuda:0")
+    with pytest.raises(opn.OpusError) as e:
+        opn.BatchDecoder(4).decode_float_ptrs(d.data_ptr(), d.data_ptr(), d.data_ptr(), None, 0, nf, d.data_ptr(),
+                                              opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY)
+    assert e.value.kind == "Unimplemented"
+    res = opn.BatchDecoder(ns, **SYNTH).decode_float(packets.reshape(-1), offsets, lens, pcm, nf)
+    assert [int(r) for r in res] == [nf] * ns
+
+
 # ------------------------------------------------------------------ Decoder API (decoder.rs:27-232)
 def test_baseline_config0_one_mono_stream_1000_chained_frames():
     """BASELINE.json configs[0]: one synthetic 20 ms 48 kHz mono stream, 1000 chained frames, decoded through
@@ -695,7 +819,7 @@ def test_baseline_config0_one_mono_stream_1000_chained_frames():
     many ring wraps, post-filter parameters) is carried for 20 s of audio."""
     lm, channels, pkt_bytes, nf, nfr = 3, 1, 100, 960, 1000
     packets = opn.synth_fill(4242, 1, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)[:, 0]
-    dec = opn.Decoder(opn.DecoderConfiguration(48000, 1, 0))
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 1, 0), **SYNTH)
     st = O.SynthStream(lm, channels)
     pcm = np.zeros(nf, np.float32)
     energy = 0.0
@@ -710,7 +834,7 @@ def test_baseline_config0_one_mono_stream_1000_chained_frames():
 
 def test_decoder_api_single_stream():
     lm, channels, pkt_bytes, nf = 3, 2, 160, 960
-    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0))
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0), **SYNTH)
     assert (dec.sampling_rate, dec.channels, dec.gain) == (48000, 2, 0)
     assert dec.bandwidth is None and dec.last_packet_duration is None and dec.pitch is None
     st = O.SynthStream(lm, channels)
@@ -756,12 +880,12 @@ def test_decoder_api_single_stream():
 def test_decoder_gain_and_i16_output():
     lm, channels, pkt_bytes, nf = 3, 2, 160, 960
     gain_q8 = 1536  # +6 dB
-    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, gain_q8))
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, gain_q8), **SYNTH)
     st = O.SynthStream(lm, channels)
     g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
     pcm = np.zeros(nf * channels, np.float32)
     mem = np.zeros(2, np.float32)
-    dec16 = opn.Decoder(opn.DecoderConfiguration(48000, 2, gain_q8))
+    dec16 = opn.Decoder(opn.DecoderConfiguration(48000, 2, gain_q8), **SYNTH)
     st16 = O.SynthStream(lm, channels)
     for f in range(3):
         pkt, _ = opn.synth_packet(2, f, lm, channels, pkt_bytes)
@@ -787,8 +911,8 @@ def test_batch_decode_i16_matches_single_stream_decode_and_oracle():
     g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
     packets = opn.synth_fill(900, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
     cfg = opn.DecoderConfiguration(48000, channels, gain_q8)
-    batch = opn.BatchDecoder(ns, cfg)
-    singles = {s: opn.Decoder(cfg) for s in (0, 7, 1099)}
+    batch = opn.BatchDecoder(ns, cfg, **SYNTH)
+    singles = {s: opn.Decoder(cfg, **SYNTH) for s in (0, 7, 1099)}
     oracle = {s: (O.SynthStream(lm, channels), np.zeros(2, np.float32)) for s in singles}
     offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
     lens = np.full(ns, pkt_bytes, np.uint32)
@@ -810,6 +934,44 @@ def test_batch_decode_i16_matches_single_stream_decode_and_oracle():
     assert clipped > 0, "the test signal never exceeded full scale"
 
 
+def test_decode_i16_lost_packet_after_a_clipping_frame_is_not_clipped():
+    """decode_native's None branch (decoder.rs:427-441) neither calls pcm_soft_clip nor touches softclip_mem: a
+    concealed frame that follows a clipping frame goes through Sample::from_f32 unclipped, and the clip memory the
+    next real packet sees is the one the last real packet left.  Batch and single-stream decode::<i16>, against the
+    oracle chain float PCM -> (clip only on real packets) -> from_f32."""
+    lm, channels, pkt_bytes, ns, nf = 3, 2, 160, 40, 960
+    gain_q8 = 3072  # +12 dB: peaks beyond full scale
+    g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
+    packets = opn.synth_fill(7700, ns, 0, 6, lm, channels, pkt_bytes)
+    cfg = opn.DecoderConfiguration(48000, channels, gain_q8)
+    batch = opn.BatchDecoder(ns, cfg, **SYNTH)
+    single = opn.Decoder(cfg, **SYNTH)
+    lost_at = {1: {3, 4}, 2: {3}, 4: {3, 9}}  # frame -> streams that lose their packet
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    oracle = {s: (O.SynthStream(lm, channels), np.zeros(2, np.float32)) for s in (3, 4, 9, 20)}
+    clipped = 0
+    for f in range(6):
+        lens = np.full(ns, pkt_bytes, np.uint32)
+        for s in lost_at.get(f, ()):
+            lens[s] = 0
+        out = np.zeros((ns, nf * channels), np.int16)
+        res, _ = batch.decode_i16(packets[f].reshape(-1), offsets, lens, out, nf)
+        assert np.all(res == nf)
+        one = np.zeros(nf * channels, np.int16)
+        assert single.decode(packets[f, 3] if lens[3] else None, one, nf) == nf
+        assert np.array_equal(one, out[3]), f
+        for s, (st, mem) in oracle.items():
+            lost = lens[s] == 0
+            w = st.decode(b"" if lost else packets[f, s, 1:])[3] * g
+            if not lost:
+                clipped += int((np.abs(w) > 1.0).sum())
+                O.lib().orc_pcm_soft_clip(O.ptr(w), nf, channels, O.ptr(mem), 2)
+            w16 = np.zeros(nf * channels, np.int16)
+            assert O.lib().orc_sample_from_f32(1, O.ptr(w), O.ptr(w16), w.size) == 0
+            assert np.abs(out[s].astype(np.int32) - w16.astype(np.int32)).max() <= 1, (f, s)
+    assert clipped > 0
+
+
 @pytest.mark.parametrize("dtype,fmt,full_scale", [(np.int16, 1, 32768.0), (np.int32, 2, 2147483648.0), (np.uint16, 3, 32768.0),
                                                    (np.uint32, 4, 2147483648.0), (np.float64, 5, 1.0)])
 def test_decode_generic_sample_types_match_oracle(dtype, fmt, full_scale):
@@ -825,9 +987,9 @@ def test_decode_generic_sample_types_match_oracle(dtype, fmt, full_scale):
     g = np.float32(np.exp(np.float32(np.float32(6.48814081e-4) * np.float32(gain_q8)) * np.float32(0.6931471805599453)))
     packets = opn.synth_fill(4000, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
     cfg = opn.DecoderConfiguration(48000, channels, gain_q8)
-    batch, batch_f = opn.BatchDecoder(ns, cfg), opn.BatchDecoder(ns, cfg)
+    batch, batch_f = opn.BatchDecoder(ns, cfg, **SYNTH), opn.BatchDecoder(ns, cfg, **SYNTH)
     picks = (0, 31, 95)
-    singles = {s: opn.Decoder(cfg) for s in picks}
+    singles = {s: opn.Decoder(cfg, **SYNTH) for s in picks}
     oracle = {s: (O.SynthStream(lm, channels), np.zeros(2, np.float32)) for s in picks}
     offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
     lens = np.full(ns, pkt_bytes, np.uint32)
@@ -859,7 +1021,7 @@ def test_decode_generic_sample_types_match_oracle(dtype, fmt, full_scale):
 
 
 def test_decode_pcm_rejects_unknown_format_and_short_buffers():
-    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0))
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0), **SYNTH)
     pkt, _ = opn.synth_packet(5, 0, 3, 2, 160)
     b = np.frombuffer(bytes(pkt), np.uint8)
     out = np.zeros(1920, np.int32)
@@ -882,7 +1044,7 @@ def test_config2_full_size_properties():
     want_pcm = np.zeros((ns, nf * channels), np.float32)
     x = C.c_uint32(0)
     O.lib().orc_synth_bench(O.ptr(packets), ns, nfr, pkt_bytes, lm, channels, 1, os.cpu_count() or 1, O.ptr(want_pcm), C.byref(x))
-    dec = opn.BatchDecoder(ns)
+    dec = opn.BatchDecoder(ns, **SYNTH)
     offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
     lens = np.full(ns, pkt_bytes, np.uint32)
     pcm = np.zeros((ns, nf * channels), np.float32)

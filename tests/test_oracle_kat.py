@@ -375,6 +375,19 @@ def test_cwrsi_event_walk_matches_oracle():
             w = (U[up] - U[i]) & M if (m >= k + 1 and up < next_end) else 0
             CW[i] = (acc, w)
             acc = (acc + U[i]) & M
+    # ev_nmax[k]: largest n whose sums C(k,n) + U(k+1,n) stay below 2^32 (upload_tables, opn_kernels.cu)
+    last_col = lambda r: (ROW[r + 1] + r if r < 14 else len(U) - 1) - ROW[r]
+    NMAX = [0] * 16
+    for k in range(14):
+        rowsum = 0
+        for n in range(k, min(last_col(k), last_col(k + 1)) + 1):
+            rowsum += U[ROW[k] + n]
+            if n > k:
+                if rowsum + U[ROW[k + 1] + n] < (1 << 32):
+                    NMAX[k] = n
+                else:
+                    break
+    assert NMAX[4] == 176 and NMAX[9] == 23 and NMAX[11] == 17 and NMAX[12] == 15, NMAX  # (24,9), (18,11), (16,12) of the ladder take the guard
 
     def walk(n, k, i):
         y = [0] * n
@@ -406,18 +419,25 @@ def test_cwrsi_event_walk_matches_oracle():
                 n -= 1
                 continue
             rk, rk1 = ROW[min(k, 14)], ROW[min(k + 1, 14)]
-            T = n - max(k, 2)
-            ic = (i - (CW[rk + n][0] + U[rk + n])) & M
-            lo, hi = 0, T
-            while lo < hi:
-                mid = (lo + hi) >> 1
-                c, w = CW[rk + n - mid]
-                if ((ic + c) & M) < w:
-                    lo = mid + 1
-                else:
-                    hi = mid
-            if lo:
-                i = (ic + CW[rk + n + 1 - lo][0]) & M
+            if n <= NMAX[k]:
+                T = n - max(k, 2)
+                ic = (i - (CW[rk + n][0] + U[rk + n])) & M
+                lo, hi = 0, T
+                while lo < hi:
+                    mid = (lo + hi) >> 1
+                    c, w = CW[rk + n - mid]
+                    if ((ic + c) & M) < w:
+                        lo = mid + 1
+                    else:
+                        hi = mid
+                if lo:
+                    i = (ic + CW[rk + n + 1 - lo][0]) & M
+            else:  # the sums could wrap: one dimension, as the reference tests it
+                T, lo = 1, 0
+                p = U[rk + n]
+                if p <= i < U[rk1 + n]:
+                    i -= p
+                    lo = 1
             pos += lo
             n -= lo
             if lo < T:
@@ -462,8 +482,20 @@ def test_cwrsi_event_walk_matches_oracle():
             L.orc_cwrsi(O.ptr(y), n, k, int(i))
             w, events = walk(n, k, int(i))
             assert list(y) == w, (n, k, i)
-            if k < n:
+            if k < n and n <= NMAX[k]:
                 assert events <= k + 1, (n, k, i, events)  # one event per pulse-bearing dimension plus the last run
+    # the whole ladder of the reference's test_pvc (pvc.rs:462-503), a few indices per shape
+    get_pulses = lambda i: i if i < 8 else (8 + (i & 7)) << ((i >> 3) - 1)
+    for n, kmax in zip(KATS["pvc_pn"], KATS["pvc_pk_max"]):
+        for pseudo in range(1, 41):
+            k = get_pulses(pseudo)
+            if k > kmax:
+                break
+            v = V(n, k)
+            for i in {0, v - 1, v // 3} | {int(x) for x in rnd.integers(0, v, 5)}:
+                y = np.zeros(n, np.int32)
+                L.orc_cwrsi(O.ptr(y), n, k, int(i))
+                assert list(y) == walk(n, k, int(i))[0], (n, k, i)
 
 
 def test_sample_from_f32_follows_the_crates_conversions():

@@ -16,7 +16,7 @@ d_arena = torch.from_numpy(packets.reshape(-1)).to(dev)
 d_off = (torch.arange(n, dtype=torch.int64, device=dev) * pkt).to(torch.int32)
 d_len = torch.full((n,), pkt, dtype=torch.int32, device=dev)
 d_res = torch.zeros(n, dtype=torch.int32, device=dev)
-dec = opn.BatchDecoder(n)
+dec = opn.BatchDecoder(n, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
 flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY
 for f in range(10):
     dec.decode_float_ptrs(d_arena.data_ptr() + f * n * pkt, d_off.data_ptr(), d_len.data_ptr(), None, 0, nf, d_res.data_ptr(), flags)

@@ -13,7 +13,7 @@ for channels, n, pkt in ((2, 4096, 160), (1, 8192, 100)):
     d_off = (torch.arange(n, dtype=torch.int64, device=dev) * pkt).to(torch.int32)
     d_len = torch.full((n,), pkt, dtype=torch.int32, device=dev)
     d_res = torch.zeros(n, dtype=torch.int32, device=dev)
-    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, channels, 0))
+    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, channels, 0), bitstream=opn.BITSTREAM_SYNTH_CELT_1)
     flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY
     dec.enable_timing(True)
     for f in range(5):

@@ -17,7 +17,7 @@ d_arena = torch.from_numpy(packets.reshape(-1)).to(dev)
 d_off = (torch.arange(n, dtype=torch.int64, device=dev) * pkt).to(torch.int32)
 d_len = torch.full((n,), pkt, dtype=torch.int32, device=dev)
 d_res = torch.zeros(n, dtype=torch.int32, device=dev)
-dec = opn.BatchDecoder(n)
+dec = opn.BatchDecoder(n, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
 stream = torch.cuda.ExternalStream(dec.cuda_stream, device=dev)
 flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY
 pa, po, pl, pr = d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr()
