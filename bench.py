@@ -259,6 +259,7 @@ def main():
             e0.record()
             for f in range(k0, k1):
                 step_resident(f)
+            dec.join()  # half of the streams' frame kernels run on an internal stream: make them ancestors of e1
             e1.record()
         dec.synchronize()
         barrier()
@@ -373,6 +374,25 @@ def main():
     barrier()
     assert np.all(res[0] == NF) and np.all(res[1] == NF) and int(np.abs(p16[(W + K16 - 1) & 1].astype(np.int32)).sum()) > 0
 
+    # ---------------- the same loop with ordinary pageable caller memory (extra figure) ----------------
+    # What a Rust Vec<f32> / &mut [f32] is: the CUDA runtime stages such copies through its own bounce buffer,
+    # synchronously, so calls cannot overlap.  opn_host_alloc / opn_host_register give a caller the pinned kind.
+    KP = min(K, 30)
+    dec4 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
+    pg_arena = packets.reshape(-1)
+    pg_pcm = np.zeros((n, NF * CHANNELS), np.float32)
+    for f in range(W):
+        dec4.decode_float_ptrs(pg_arena.ctypes.data + f * step_bytes, offs.ctypes.data, lens.ctypes.data, pg_pcm.ctypes.data, NF * CHANNELS,
+                               NF, res[0].ctypes.data, 0)
+    barrier()
+    t0 = time.perf_counter()
+    for f in range(W, W + KP):
+        dec4.decode_float_ptrs(pg_arena.ctypes.data + f * step_bytes, offs.ctypes.data, lens.ctypes.data, pg_pcm.ctypes.data, NF * CHANNELS,
+                               NF, res[0].ctypes.data, 0)
+    t_pg = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert np.all(res[0] == NF) and float(np.abs(pg_pcm).sum()) > 0
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -424,6 +444,9 @@ def main():
                         "d2h_bytes_per_step": n * NF * CHANNELS * 2, "ms_per_step": 1e3 * t_e2e16 / K16,
                         "note": "extra: the same host-buffer loop through opn_batch_decode_i16 (Decoder::decode::<i16>: "
                                 "soft clip and sample conversion on the device); not the headline"},
+            "e2e_pageable": {"value": world * n * KP / t_pg * FRAME_S, "unit": "streams", "steps": KP, "ms_per_step": 1e3 * t_pg / KP,
+                             "note": "extra: pageable caller buffers (plain numpy arrays = what a Rust slice is), one synchronous call per step; "
+                                     "the headline e2e uses pinned buffers (opn_host_alloc / opn_host_register) and two calls in flight"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_frame_w<3,2,true> (PVQ expansion + IMDCT/TDAC + comb post-filter + PCM store)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -83,6 +83,17 @@ int32_t opn_decoder_pitch(const opn_decoder *dec);                           /* 
 int32_t opn_decoder_last_packet_duration(const opn_decoder *dec);            /* decoder.rs:112, -1 = None */
 uint32_t opn_decoder_final_range(const opn_decoder *dec);                    /* decoder.rs:121 */
 
+/* ---- host memory for the host-buffer entry points ------------------------------------- */
+/* The decode calls below accept any host memory.  Page-locked buffers are copied by asynchronous DMA at PCIe speed
+ * (and are what OPN_FLAG_SUBMIT_ONLY needs to overlap two calls); ordinary pageable memory -- a Rust Vec or slice --
+ * is staged by the CUDA runtime through a bounce buffer, synchronously: correct, but slower (bench.py e2e_pageable).
+ * A caller that owns its buffers gets the fast kind by allocating them here, or by registering (pinning in place)
+ * memory it already has; registered memory must be unregistered before it is freed. */
+void *opn_host_alloc(size_t bytes);          /* page-locked, NULL on failure */
+void opn_host_free(void *p);
+int opn_host_register(void *p, size_t bytes);
+int opn_host_unregister(void *p);
+
 /* ---- batch of independent streams (the entry point north_star adds) ------------------ */
 typedef struct opn_batch opn_batch;
 typedef struct {
@@ -150,10 +161,10 @@ int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[
  * read (4 bytes each) -- the comb term of the frame kernel's algorithmic bytes. */
 int opn_batch_history_samples(opn_batch *b, uint64_t *out, int reset);
 void *opn_batch_cuda_stream(opn_batch *b);
-/* The library runs the range decode on internal streams, but every step ends with its frame kernel on
- * opn_batch_cuda_stream: whatever the caller enqueues there next (an end-of-region event, a consumer kernel reading
- * the PCM ring) is ordered after everything submitted so far.  opn_batch_join is kept for callers written against
- * earlier versions and does nothing. */
+/* The library runs its stages on several internal streams (range decode; the frame kernel of a large batch in two
+ * halves).  opn_batch_join makes everything enqueued so far an ancestor of whatever is enqueued next on
+ * opn_batch_cuda_stream (e.g. the caller's end-of-region event or a consumer kernel reading the PCM ring); it does
+ * not block the host. */
 int opn_batch_join(opn_batch *b);
 
 /* ---- operator-level entry points (host pointers in/out; mirror the pub(crate) operators) */

@@ -10,7 +10,7 @@ from ._capi import (  # noqa: F401
     OpusError, lib, library_path, build_library,
     query_packet_bandwidth, query_packet_channel_count, query_packet_frame_count,
     query_packet_samples_per_frame, query_packet_sample_count, query_packet_codec_mode, parse_packet,
-    DecoderConfiguration, Decoder, BatchDecoder,
+    DecoderConfiguration, Decoder, BatchDecoder, HostBuffer, host_register, host_unregister,
     op_rangedec_script, op_imdct_tdac, op_comb_filter_inplace, op_comb_filter, op_pcm_soft_clip, op_bitexact_trig,
     op_synth_symbols, synth_packet, synth_fill, enc_run_script,
     OP_DTYPE, OUT_DTYPE, SIDE_DTYPE,

@@ -89,6 +89,10 @@ def lib():
     for g in ("sampling_rate", "channels", "gain", "bandwidth", "pitch", "last_packet_duration"):
         sig("opn_decoder_" + g, i32, vp)
     sig("opn_decoder_final_range", u32, vp)
+    sig("opn_host_alloc", vp, sz)
+    sig("opn_host_free", None, vp)
+    sig("opn_host_register", C.c_int, vp, sz)
+    sig("opn_host_unregister", C.c_int, vp)
     sig("opn_batch_create", C.c_int, C.c_int, u32, vp, C.POINTER(vp))
     sig("opn_batch_destroy", None, vp)
     sig("opn_batch_reset", C.c_int, vp)
@@ -346,6 +350,33 @@ class BatchDecoder:
     @property
     def cuda_stream(self):
         return lib().opn_batch_cuda_stream(self._h)
+
+
+# ---------------------------------------------------------------- host memory
+class HostBuffer:
+    """Page-locked host memory from opn_host_alloc, viewed as a numpy array (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        self._p = lib().opn_host_alloc(n)
+        if not self._p:
+            raise MemoryError("opn_host_alloc failed")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n).from_address(self._p)).view(self.dtype).reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib().opn_host_free(self._p)
+            self._p = None
+
+
+def host_register(a: np.ndarray):
+    _chk(lib().opn_host_register(_p(a), a.nbytes))
+
+
+def host_unregister(a: np.ndarray):
+    _chk(lib().opn_host_unregister(_p(a)))
 
 
 # ---------------------------------------------------------------- operator level

@@ -130,7 +130,7 @@ template <int C, int CHF> struct FrameView {
 // filtered in parallel, one per lane, consecutive lanes on consecutive samples (conflict-free in shared memory,
 // coalesced in the ring); the frame is swept in spans no longer than T-2.  A tap set whose gain is exactly zero
 // contributes +-0 to every sum and is skipped.
-template <int C, int CHF>
+template <int C, int CHF, bool TS = false>
 __device__ __forceinline__ void w_comb_ring(const FrameView<C, CHF> &V, int t0, int t1, int n, float g0, float g1, int tap0, int tap1,
                                             int overlap, int lane, const float *win_sq, const CombGains &kg)
 {
@@ -149,7 +149,7 @@ __device__ __forceinline__ void w_comb_ring(const FrameView<C, CHF> &V, int t0, 
         for (int base = 0; base < overlap; base += W) {
             const int i = base + lane;
             if (lane < W && i < overlap) {
-                const float f = __ldg(win_sq + i);
+                const float f = tab_ld<TS>(win_sq + i);
                 S a[5], b[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
@@ -173,9 +173,16 @@ __device__ __forceinline__ void w_comb_ring(const FrameView<C, CHF> &V, int t0, 
             for (int e = 0; e < 4; e++) {
                 const int i = base + lane + 32 * e;
                 if (i < hend) {
-                    const int p = i - t1;
-                    V.st_row(i, w_comb5<C>(V.ld_row(i), V.ld_hist(p + 2), V.ld_hist(p + 1), V.ld_hist(p), V.ld_hist(p - 1), V.ld_hist(p - 2),
-                                           g10, g11, g12));
+                    int j = V.pos + i - t1 - 2;  // ring index of the lowest tap, y[i-T-2]
+                    if (j < 0) j += RING_SAMPLES;
+                    if (j + 4 < RING_SAMPLES) {  // the five taps are contiguous in the ring (all but <= 4 samples per frame)
+                        const float *hp = V.ring + (size_t)j * C;
+                        V.st_row(i, w_comb5<C>(V.ld_row(i), S::ld(hp + 4 * C), S::ld(hp + 3 * C), S::ld(hp + 2 * C), S::ld(hp + C), S::ld(hp), g10, g11, g12));
+                    } else {
+                        const int p = i - t1;
+                        V.st_row(i, w_comb5<C>(V.ld_row(i), V.ld_hist(p + 2), V.ld_hist(p + 1), V.ld_hist(p), V.ld_hist(p - 1), V.ld_hist(p - 2),
+                                               g10, g11, g12));
+                    }
                 }
             }
         }
@@ -204,53 +211,101 @@ __device__ __forceinline__ void w_comb_ring(const FrameView<C, CHF> &V, int t0, 
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------------------
-// The frame kernel: one warp = one CTA = one stream (item).
-template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32, W_K1_MIN_CTAS) k_frame_w(FrameArgs A)
+// The frame kernel: one warp = one stream (item), FRAME_WARPS warps per CTA.  The warps of a CTA are independent (all
+// hand-offs inside a stream are __syncwarp); what they share is one copy of the read-only tables (trig pairs, twiddles,
+// window, the schedule's slice of the PVQ tables, part entries: FBlobHdr), staged in shared memory by ONE TMA bulk copy
+// per CTA that is in flight while the warps load their streams' state and clear their rows.
+// Shared memory: [mbarrier 16 B | table blob | FRAME_WARPS x (C rows of nf+60 floats + 16 B)].
+#ifndef OPN_FRAME_WARPS
+#define OPN_FRAME_WARPS 5
+#endif
+#ifndef OPN_FRAME_CTAS
+#define OPN_FRAME_CTAS 4
+#endif
+constexpr int FRAME_WARPS = OPN_FRAME_WARPS, FRAME_CTAS = OPN_FRAME_CTAS;
+__host__ __device__ constexpr size_t frame_warp_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16; }
+__host__ __device__ constexpr size_t frame_smem_bytes(int lm, int channels, size_t blob_bytes)
 {
-    extern __shared__ __align__(16) float o[];
+    return 16 + blob_bytes + (size_t)FRAME_WARPS * frame_warp_bytes(lm, channels);
+}
+
+template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NF = 120 << LM;
     constexpr int CHF = w_ch_floats(LM);
-    const int lane = threadIdx.x;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t *tbar = reinterpret_cast<uint64_t *>(smem);
+    const uint8_t *blob = smem + 16;
+    const FBlobHdr H = g_tab.fblob_hdr[LM][C - 1];
+    float *o = reinterpret_cast<float *>(smem + 16 + H.total + (size_t)warp * frame_warp_bytes(LM, C));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);  // this warp's barrier (coefficient rows by TMA, unfused variant)
 
-    const uint32_t item = blockIdx.x;
-    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    if (threadIdx.x == 0) {
+        mbar_init(tbar, 1);
+        mbar_expect_tx(tbar, H.total);
+        bulk_g2s(smem + 16, g_fblob[LM][C - 1], H.total, tbar);
+    }
+    const uint32_t item = A.item0 + blockIdx.x * FRAME_WARPS + warp;
+    const bool in_range = item < A.item_end;
+    const uint32_t stream = in_range ? (A.stream_idx ? A.stream_idx[item] : item) : 0u;
     if constexpr (!EXPAND) {
         // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
-        if (lane == 0) {
+        if (lane == 0 && in_range) {
             mbar_init(bar, 1);
             mbar_expect_tx(bar, C * NF * 4);
 #pragma unroll
             for (int c = 0; c < C; c++) bulk_g2s(o + c * CHF, A.coef + ((size_t)stream * C + c) * NF, NF * 4, bar);
         }
     }
-    // What the transform needs is loaded now; the post-filter state (previous parameters, ring position) is only
-    // prefetched into L1 and read after the transform, so that it does not occupy registers across it.
-    const int32_t status = A.status[stream];
-    const uint32_t hdr_x = A.hdr[stream].x;
-    prefetch_l1(A.pf + stream);
-    prefetch_l1(A.ring_pos + stream);
+    // What the transform needs is loaded now; the rest of the post-filter state is read after the transform, so that it
+    // does not occupy registers across it (its cache lines are already here by then).
+    const int32_t status = in_range ? A.status[stream] : -1;
+    const uint32_t hdr_x = in_range ? A.hdr[stream].x : 0u;
     float *carry_g = A.carry + (size_t)stream * C * 60;
     float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
+    if (in_range && lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
+    float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
+    if (in_range && status >= 0 && A.postfilter) {
+        // The post-filter will read the last max(T_old, T_new)+2 samples before this frame from the ring: ask for those
+        // lines now (HBM -> L2), a whole transform ahead of their use.
+        const int t_old = A.pf[stream].period, t_new = (hdr_x >> 1) & 1u ? (int)(hdr_x >> 16) : 0;
+        const int pos0 = (int)A.ring_pos[stream];
+        const int need = max(max(t_old, t_new), 15) + 2;
+        for (int l = lane * (128 / (4 * C)); l < need + 128 / (4 * C); l += 32 * (128 / (4 * C))) {  // one 128-byte line per lane and round
+            int j = pos0 - need + l;
+            if (j >= pos0) j = pos0 - 1;
+            if (j < 0) j += RING_SAMPLES;
+            prefetch_l2(ring + (size_t)j * C);
+        }
+    }
     if constexpr (EXPAND) {
         // the coefficient rows start out zero: w_expand only writes the pulses
 #pragma unroll
         for (int c = 0; c < C; c++)
             for (int i = lane; i < NF / 4; i += 32) reinterpret_cast<float4 *>(o + c * CHF)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncwarp();
-    if (status < 0) {  // rejected packet: state untouched (decoder.rs:397)
-        if (lane == 0 && A.result) A.result[stream] = status;
-        if constexpr (!EXPAND) mbar_wait(bar, 0);  // the rows are in flight: do not retire the CTA under them
+    __syncthreads();  // the table barrier is initialised
+    mbar_wait(tbar, 0);
+    if (status < 0) {  // out of range, or a rejected packet: state untouched (decoder.rs:397)
+        if (in_range && lane == 0 && A.result) A.result[stream] = status;
+        if constexpr (!EXPAND) {
+            if (in_range) mbar_wait(bar, 0);  // the rows are in flight: do not retire the CTA under them
+        }
         return;
     }
+    const float2 *t_long = reinterpret_cast<const float2 *>(blob + H.tp_long), *t_short = reinterpret_cast<const float2 *>(blob + H.tp_short);
+    const float2 *t_tw = reinterpret_cast<const float2 *>(blob + H.tw);
+    const float *t_win = reinterpret_cast<const float *>(blob + H.win), *t_winsq = reinterpret_cast<const float *>(blob + H.win_sq);
     const bool lost = status == ITEM_LOST;
     if constexpr (EXPAND) {
         if (!lost && !(hdr_x & 1u)) {  // not silence
-            const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, g_tab.synth_entries[LM][C - 1]};
+            const ExpandTables T{reinterpret_cast<const uint32_t *>(blob + H.pvq_u), reinterpret_cast<const uint2 *>(blob + H.pvq_cw),
+                                 reinterpret_cast<const uint16_t *>(blob + H.pvq_row), blob + H.pvq_nmax,
+                                 reinterpret_cast<const SynthEntry *>(blob + H.ent), blob + H.slots, (int)H.n_slots};
             w_expand<C>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr);
         }
         __syncwarp();
@@ -258,10 +313,10 @@ template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32, W_K1
         mbar_wait(bar, 0);
     }
     if constexpr (LM > 0) {
-        if ((hdr_x >> 2) & 1u) w_imdct<3, (1 << LM), C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
-        else w_imdct<3 - LM, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3 - LM), g_tab.twiddles, g_tab.window);
+        if ((hdr_x >> 2) & 1u) w_imdct<3, (1 << LM), C, true>(o, lane, carry, t_short, t_tw, t_win);
+        else w_imdct<3 - LM, 1, C, true>(o, lane, carry, t_long, t_tw, t_win);
     } else {
-        w_imdct<3, 1, C>(o, lane, carry, g_tab.trig_pair + trig_pair_off(3), g_tab.twiddles, g_tab.window);
+        w_imdct<3, 1, C, true>(o, lane, carry, t_long, t_tw, t_win);
     }
 
     // post-filter parameters: previous frame -> this frame
@@ -277,7 +332,6 @@ template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32, W_K1
         tap1 = s_on ? s_tapset : 0;
     }
     const bool comb_on = A.postfilter && (old.gain != 0.0f || g1 != 0.0f);
-    float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
 
     // tail of this frame -> carry
     if (lane < 15 * C) {
@@ -287,8 +341,8 @@ template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32, W_K1
     // pitch comb post-filter, previous parameters -> this frame's over the first 120 samples
     if (comb_on) {
         const FrameView<C, CHF> V{o, ring, (int)pos};
-        w_comb_ring<C, CHF>(V, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane, g_tab.window_sq,
-                            w_comb_gains(old.gain, g1, old.tapset, tap1));
+        w_comb_ring<C, CHF, true>(V, old.period, t1, NF, old.gain, g1, old.tapset, tap1, 120, lane, t_winsq,
+                                  w_comb_gains(old.gain, g1, old.tapset, tap1));
         __syncwarp();
         if (A.hist_samples && lane == 0) atomicAdd(A.hist_samples, (unsigned long long)(C * (max(max(old.period, t1), 15) + 2)));
     }

@@ -130,8 +130,23 @@ struct opn_batch {
     static constexpr int NSETS = OPN_NSETS, NRD = OPN_NRD;
     cudaStream_t stream_rd[NRD] = {};     // set p decodes on stream_rd[p % NRD]: entropy stages of NRD steps overlap each other
     cudaStream_t stream_ex = nullptr;     // unfused variant only: stand-alone PVQ expansion between the entropy streams and `stream`
-    cudaEvent_t ev_k1[NSETS] = {};        // frame kernel of set p finished: the set is free again
+    // A large bucket's frame kernel is cut into NGROUPS launches over contiguous stream ranges, group g on stream_fr[g]
+    // (stream_fr[0] is `stream`).  A stream's frames stay in order (its group's stream), but the tail of one group's launch
+    // overlaps the body of the other's, and step n+1 of a group may start while step n of the other is still running:
+    // the SMs never drain between steps.
+#ifndef OPN_FRAME_GROUPS
+#define OPN_FRAME_GROUPS 2
+#endif
+    static constexpr int NGROUPS = OPN_FRAME_GROUPS;
+    static constexpr uint32_t GROUP_MIN_ITEMS = 2048;  // smaller buckets run as one launch on `stream`
+    cudaStream_t stream_fr[NGROUPS] = {};
+    cudaEvent_t ev_fr[NSETS][NGROUPS] = {};  // frame kernel of set p, group g finished
+    cudaEvent_t ev_sw = nullptr;             // mode switch: everything enqueued on `stream` so far
+    bool fr_pending[NGROUPS] = {};           // group g >= 1 has work that `stream` has not been ordered after yet
+    int fr_last_set[NGROUPS] = {};
+    cudaEvent_t ev_k1[NSETS] = {};        // frame kernel(s) of set p finished on `stream` (group 0 / ungrouped): the set is free again
     bool k1_recorded[NSETS] = {};
+    bool k1_grouped[NSETS] = {};          // set p was last used by a grouped launch: ev_fr[p][1..] are part of "set p is free"
     cudaEvent_t ev_rd[NSETS] = {};        // range decode of set p finished
     cudaEvent_t ev_ex[NSETS] = {};        // unfused variant: coefficients of set p ready
     cudaEvent_t ev_in = nullptr;          // inputs ordered on `stream` / `stream_up` are complete
@@ -232,10 +247,25 @@ cudaError_t do_rangedec(opn_batch *b, const void *a) { return launch_synth_range
 cudaError_t do_expand(opn_batch *b, const void *a) { return launch_synth_expand(*static_cast<const SymbolArgs *>(a), b->stream); }
 cudaError_t do_frame(opn_batch *b, const void *a) { return launch_frame(*static_cast<const FrameArgs *>(a), b->stream); }
 
+// Orders `stream` after everything the other frame groups have been given so far.
+int join_groups(opn_batch *b)
+{
+    for (int g = 1; g < opn_batch::NGROUPS; g++)
+        if (b->fr_pending[g]) {
+            CU(cudaStreamWaitEvent(b->stream, b->ev_fr[b->fr_last_set[g]][g], 0));
+            b->fr_pending[g] = false;
+        }
+    return OPN_OK;
+}
+
 int sync_pipeline(opn_batch *b)
 {
     for (int q = 0; q < opn_batch::NRD; q++) CU(cudaStreamSynchronize(b->stream_rd[q]));
     CU(cudaStreamSynchronize(b->stream_ex));
+    for (int g = 1; g < opn_batch::NGROUPS; g++) {
+        CU(cudaStreamSynchronize(b->stream_fr[g]));
+        b->fr_pending[g] = false;
+    }
     CU(cudaStreamSynchronize(b->stream_up));
     CU(cudaStreamSynchronize(b->stream));
     CU(cudaStreamSynchronize(b->stream_dn));
@@ -290,7 +320,11 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
             CU(cudaEventRecord(b->ev_in, b->stream_up));
             CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
         }
-        if (b->k1_recorded[p]) CU(cudaStreamWaitEvent(srd, b->ev_k1[p], 0));  // set p is free again
+        if (b->k1_recorded[p]) {  // set p is free again
+            CU(cudaStreamWaitEvent(srd, b->ev_k1[p], 0));
+            if (b->k1_grouped[p])
+                for (int g = 1; g < opn_batch::NGROUPS; g++) CU(cudaStreamWaitEvent(srd, b->ev_fr[p][g], 0));
+        }
         CU(launch_synth_rangedec(s, srd));
         CU(cudaEventRecord(b->ev_rd[p], srd));
         b->launches[0]++;
@@ -312,6 +346,8 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.stream_idx = d_stream_idx;
     m.dense_off = d_dense_off;
     m.n_items = n_items;
+    m.item0 = 0;
+    m.item_end = n_items;
     m.lm = lm;
     m.channels = b->cfg.channels;
     m.postfilter = b->cfg.postfilter;
@@ -326,15 +362,41 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.final_range = b->d_final;
     m.softclip_reset = softclip_reset ? b->d_softclip : nullptr;
     m.hist_samples = b->timing ? b->d_hist_samples : nullptr;
+    const bool grouped = !b->timing && !b->unfused && opn_batch::NGROUPS > 1 && n_items >= opn_batch::GROUP_MIN_ITEMS && !d_stream_idx;
     if (b->timing) {
+        rc = join_groups(b);
+        if (rc) return rc;
         rc = timed_launch(b, 1, do_frame, &m);
         if (rc) return rc;
-    } else {
+    } else if (!grouped) {
+        rc = join_groups(b);  // streams of the other groups' ranges may be in this bucket
+        if (rc) return rc;
         CU(launch_frame(m, b->stream));
         b->launches[1]++;
+    } else {
+        // group 0 on `stream`, the others on their own streams: each after its own previous frames (stream order), after
+        // this step's range decode and after whatever `stream` held when the groups were last joined
+        CU(cudaEventRecord(b->ev_sw, b->stream));
+        for (int g = 0; g < opn_batch::NGROUPS; g++) {
+            cudaStream_t st = g == 0 ? b->stream : b->stream_fr[g];
+            if (g > 0) {
+                if (!b->fr_pending[g]) CU(cudaStreamWaitEvent(st, b->ev_sw, 0));
+                CU(cudaStreamWaitEvent(st, b->ev_rd[p], 0));
+            }
+            m.item0 = (uint32_t)((uint64_t)n_items * g / opn_batch::NGROUPS);
+            m.item_end = (uint32_t)((uint64_t)n_items * (g + 1) / opn_batch::NGROUPS);
+            CU(launch_frame(m, st));
+            b->launches[1]++;
+            if (g > 0) {
+                CU(cudaEventRecord(b->ev_fr[p][g], st));
+                b->fr_pending[g] = true;
+                b->fr_last_set[g] = p;
+            }
+        }
     }
     CU(cudaEventRecord(b->ev_k1[p], b->stream));
     b->k1_recorded[p] = true;
+    b->k1_grouped[p] = grouped;
     return OPN_OK;
 }
 
@@ -382,6 +444,40 @@ int opn_device_count(void)
     return n;
 }
 
+// ------------------------------------------------------------------------------------ host memory
+// The host-buffer entry points copy straight between the caller's buffers and the device.  With page-locked buffers
+// those copies are asynchronous DMA at PCIe speed; with ordinary (pageable) memory -- what a Rust Vec or slice is --
+// the CUDA runtime stages them through its own pinned bounce buffer, synchronously.  Both work; these helpers give a
+// caller the fast kind.
+void *opn_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (bytes == 0 || cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void opn_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int opn_host_register(void *p, size_t bytes)
+{
+    if (!p || bytes == 0) return OPN_ERR_BAD_ARG;
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return OPN_OK;
+}
+
+int opn_host_unregister(void *p)
+{
+    if (!p) return OPN_ERR_BAD_ARG;
+    CU(cudaHostUnregister(p));
+    return OPN_OK;
+}
+
 // ------------------------------------------------------------------------------------ batch
 int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out)
 {
@@ -412,12 +508,15 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_k1[q], cudaEventDisableTiming);
+        for (int g = 1; g < opn_batch::NGROUPS && e == cudaSuccess; g++) e = cudaEventCreateWithFlags(&b->ev_fr[q][g], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
         if (e == cudaSuccess && b->unfused) e = cudaMalloc(&b->d_coef[q], n * C * 960 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_hdr[q], n * sizeof(uint4));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
+    for (int g = 1; g < opn_batch::NGROUPS && e == cudaSuccess; g++) e = cudaStreamCreateWithFlags(&b->stream_fr[g], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_sw, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_dn, cudaStreamNonBlocking);
@@ -455,7 +554,15 @@ void opn_batch_destroy(opn_batch *b)
         if (b->stream_rd[q]) cudaStreamSynchronize(b->stream_rd[q]);
     for (cudaStream_t st : {b->stream_ex, b->stream_up, b->stream, b->stream_dn})
         if (st) cudaStreamSynchronize(st);
+    for (int g = 1; g < opn_batch::NGROUPS; g++)
+        if (b->stream_fr[g]) {
+            cudaStreamSynchronize(b->stream_fr[g]);
+            cudaStreamDestroy(b->stream_fr[g]);
+        }
+    if (b->ev_sw) cudaEventDestroy(b->ev_sw);
     for (int q = 0; q < opn_batch::NSETS; q++) {
+        for (int g = 1; g < opn_batch::NGROUPS; g++)
+            if (b->ev_fr[q][g]) cudaEventDestroy(b->ev_fr[q][g]);
         if (b->ev_rd[q]) cudaEventDestroy(b->ev_rd[q]);
         if (b->ev_ex[q]) cudaEventDestroy(b->ev_ex[q]);
         if (b->ev_k1[q]) cudaEventDestroy(b->ev_k1[q]);
@@ -778,8 +885,9 @@ int opn_batch_synchronize(opn_batch *b)
 int opn_batch_join(opn_batch *b)
 {
     if (!b) return OPN_ERR_BAD_ARG;
-    // every step ends with its frame kernel on the batch stream: whatever is enqueued there next is ordered after it
-    return OPN_OK;
+    CU(cudaSetDevice(b->device));
+    // every step ends with frame kernels: group 0 on the batch stream, the other groups on their own streams
+    return join_groups(b);
 }
 
 int opn_batch_wait(opn_batch *b, int ticket)
@@ -798,6 +906,8 @@ int opn_batch_final_ranges(opn_batch *b, uint32_t *out)
 {
     if (!b || !out) return OPN_ERR_BAD_ARG;
     CU(cudaSetDevice(b->device));
+    int rc = join_groups(b);
+    if (rc) return rc;
     CU(cudaMemcpyAsync(out, b->d_final, b->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return OPN_OK;

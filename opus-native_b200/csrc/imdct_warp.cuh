@@ -40,13 +40,8 @@ template <int I> struct WTw {
     __device__ __forceinline__ static float2 get() { return make_float2(re, im); }
 };
 
-#ifndef OPN_K1_MIN_CTAS
-#define OPN_K1_MIN_CTAS 20
-#endif
-constexpr int W_K1_MIN_CTAS = OPN_K1_MIN_CTAS;  // kernel 1 register budget: 65536 / (32 * this) per thread
 __host__ __device__ constexpr int w_ch_floats(int lm) { return (120 << lm) + 60; }
 __host__ __device__ constexpr int trig_pair_off(int shift) { return shift == 0 ? 0 : shift == 1 ? 480 : shift == 2 ? 720 : 840; }
-__host__ __device__ constexpr size_t w_smem_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16; }
 
 // ---- TMA / mbarrier (single-CTA cluster) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -206,7 +201,13 @@ template <int SHIFT> __device__ __forceinline__ void w_group_stages(float2 *d)
 // row of CHF = nf + 60 floats (channel 1 follows): on entry it holds the coefficients, on exit
 // out[0 .. nf+60) after the TDAC mirror (mdct.rs:241-259).  `carry` is this lane's float4 of the
 // previous tail (lane = 15*ch + k -> out[4k .. 4k+4)).
-template <int SHIFT, int NBLK, int C>
+// TS: the tables (trig pairs, twiddles, window) are in shared memory (frame kernel) rather than global memory.
+template <bool TS, class T> __device__ __forceinline__ T tab_ld(const T *p)
+{
+    if constexpr (TS) return *p;
+    else return __ldg(p);
+}
+template <int SHIFT, int NBLK, int C, bool TS = false>
 __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const float2 *tpair, const float2 *tw, const float *win)
 {
     constexpr int GS = 32 >> SHIFT, N2 = 960 >> SHIFT;
@@ -237,7 +238,7 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
                     const int q = w_qmap<SHIFT>(p);
                     const float x0 = x[blk + NBLK * (2 * r) + NBLK * 30 * q];
                     const float x1 = x[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * q];
-                    const float2 t = __ldg(tp + 15 * q);  // (trig[i], trig[n4 + i])
+                    const float2 t = tab_ld<TS>(tp + 15 * q);  // (trig[i], trig[n4 + i])
                     const float re = (x1 * t.x) + (x0 * t.y);
                     const float im = (x0 * t.x) - (x1 * t.y);
                     d[blk * GS + p] = make_float2(im, re);
@@ -261,12 +262,12 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
         constexpr int S3 = 5 << SHIFT;  // twiddle stride of the radix-3 stage
         const int col = lane % E, ch0 = lane / E;
         const int blk = col / GS, u = col % GS;
-        const float2 w31 = __ldg(tw + u * S3), w32 = __ldg(tw + 2 * u * S3);
+        const float2 w31 = tab_ld<TS>(tw + u * S3), w32 = tab_ld<TS>(tw + 2 * u * S3);
         float2 w5[3][4];
 #pragma unroll
         for (int jj = 0; jj < 3; jj++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) w5[jj][k] = __ldg(tw + (((u + GS * jj) * (k + 1)) << SHIFT));
+            for (int k = 0; k < 4; k++) w5[jj][k] = tab_ld<TS>(tw + (((u + GS * jj) * (k + 1)) << SHIFT));
         constexpr float epi3y = WTw<160>::im;
         const float2 ya = WTw<96>::get(), yb = WTw<192>::get();
         constexpr int ITER = (C * E + 31) / 32;
@@ -299,7 +300,7 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
                 const float2 *tp = tpair + u;
 #pragma unroll
                 for (int j = 0; j < 15; j++) {
-                    const float2 t = __ldg(tp + GS * j);
+                    const float2 t = tab_ld<TS>(tp + GS * j);
                     ob[2 * u + 2 * GS * j] = (d[j].y * t.x) + (d[j].x * t.y);
                     ob[N2 - 1 - 2 * u - 2 * GS * j] = (d[j].y * t.y) - (d[j].x * t.x);
                 }
@@ -325,7 +326,7 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
         }
         float *ob = o + ch * CHF + N2 * blk;
         const float x0 = ob[119 - i], x1 = ob[i];
-        const float w0 = __ldg(win + i), w1 = __ldg(win + 119 - i);
+        const float w0 = tab_ld<TS>(win + i), w1 = tab_ld<TS>(win + 119 - i);
         ob[i] = (w1 * x1) - (w0 * x0);
         ob[119 - i] = (w0 * x1) + (w1 * x0);
     }

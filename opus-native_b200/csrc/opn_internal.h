@@ -62,7 +62,8 @@ struct FrameArgs {
     const uint4 *hdr;             // [n_streams] frame headers (range decode output)
     const int32_t *status;        // [n_streams]  (range decode output)
     const uint32_t *stream_idx;   // [n_items] or nullptr
-    uint32_t n_items;
+    uint32_t n_items;             // items of the bucket
+    uint32_t item0, item_end;     // this launch covers items [item0, item_end) of them (a bucket may be cut into groups)
     int lm, channels, postfilter;
     float *carry;                 // [n_streams][C][60]
     float *ring;                  // [n_streams][RING_SAMPLES][C]

@@ -1,6 +1,8 @@
 // opn_kernels.cu -- the single CUDA translation unit of libopusb200 (sm_100a, -fmad=false).
 #include <algorithm>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "imdct.cuh"
 #include "imdct_warp.cuh"
@@ -17,13 +19,17 @@ static std::mutex g_tab_mutex;
 static int g_sm_count = 148;
 constexpr int W_CARVEOUT_PCT = 100;
 static bool g_tab_done[64];
+static uint16_t g_fblob_bytes[4][2];  // FBlobHdr::total per (LM, channels): the launchers size shared memory with it
 
 template <int LM, int C> static cudaError_t set_carveout()
 {
-    // percent of the SM's unified 256 KB used as shared memory; the rest is L1 (tables, history taps)
+    // percent of the SM's unified 256 KB used as shared memory; the rest is L1 (history taps, per-stream state)
+    const int smem = (int)frame_smem_bytes(LM, C, g_fblob_bytes[LM][C - 1]);
     cudaError_t e = cudaFuncSetAttribute(k_frame_w<LM, C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_frame_w<LM, C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
 }
 static cudaError_t set_warp_kernel_attributes()
 {
@@ -168,11 +174,70 @@ cudaError_t upload_tables(int device)
         }
     h.tapset_icdf[0] = 2; h.tapset_icdf[1] = 1; h.tapset_icdf[2] = 0; h.tapset_icdf[3] = 0;
     for (int i = 0; i < 9; i++) h.comb_gains[i] = OPN_COMB_GAINS[i];
+    // ---- the frame kernel's table blobs (FBlobHdr), one per (LM, channels)
+    static uint8_t blobs[4][2][FBLOB_MAX_BYTES];
+    for (int lm = 0; lm < 4; lm++)
+        for (int C = 1; C <= 2; C++) {
+            uint8_t *bl = blobs[lm][C - 1];
+            std::memset(bl, 0, FBLOB_MAX_BYTES);
+            FBlobHdr &H = h.fblob_hdr[lm][C - 1];
+            size_t at = 0;
+            auto put = [&](const void *src, size_t bytes) {
+                const size_t off = at;
+                if (off + bytes > FBLOB_MAX_BYTES) return (size_t)0xFFFF;
+                if (src) std::memcpy(bl + off, src, bytes);
+                at = (off + bytes + 15) & ~(size_t)15;
+                return off;
+            };
+            const int shift = 3 - lm;
+            H.tp_long = (uint16_t)put(h.trig_pair + trig_pair_off(shift), (size_t)(480 >> shift) * sizeof(float2));
+            H.tp_short = (uint16_t)put(h.trig_pair + trig_pair_off(3), 60 * sizeof(float2));
+            H.tw = (uint16_t)put(h.twiddles, 480 * sizeof(float2));
+            H.win = (uint16_t)put(h.window, 120 * sizeof(float));
+            H.win_sq = (uint16_t)put(h.window_sq, 120 * sizeof(float));
+            // rectangular slice of the PVQ tables that covers the schedule's parts: rows 0 .. kmax+1, columns 0 .. nmax
+            const int ne = h.synth_n_entries[lm][C - 1];
+            int kmax = 1, nmax = 2;
+            for (int e2 = 0; e2 < ne; e2++) {
+                kmax = std::max(kmax, (int)h.synth_entries[lm][C - 1][e2].k);
+                nmax = std::max(nmax, (int)h.synth_entries[lm][C - 1][e2].n);
+            }
+            nmax = std::max(nmax, kmax + 1);
+            const int rows = kmax + 2, cols = nmax + 1;
+            if (rows > 15) return cudaErrorInvalidValue;
+            std::vector<uint32_t> cu((size_t)rows * cols, 0u);
+            std::vector<uint2> ccw((size_t)rows * cols, make_uint2(0u, 0u));
+            auto last_col = [](int r) { return (r < 14 ? OPN_PVQ_U_ROW[r + 1] + r : 1271) - OPN_PVQ_U_ROW[r]; };
+            for (int k = 0; k < rows; k++)
+                for (int n = 0; n < cols; n++) {
+                    const int lo = std::min(k, n), hi = std::max(k, n);
+                    if (hi > last_col(lo)) return cudaErrorInvalidValue;
+                    cu[(size_t)k * cols + n] = OPN_PVQ_U_DATA[OPN_PVQ_U_ROW[lo] + hi];
+                    if (n >= k) ccw[(size_t)k * cols + n] = h.pvq_cw_data[OPN_PVQ_U_ROW[k] + n];
+                }
+            H.pvq_u = (uint16_t)put(cu.data(), cu.size() * sizeof(uint32_t));
+            H.pvq_cw = (uint16_t)put(ccw.data(), ccw.size() * sizeof(uint2));
+            uint16_t row16[16];
+            for (int k = 0; k < 16; k++) row16[k] = (uint16_t)(std::min(k, rows - 1) * cols);
+            H.pvq_row = (uint16_t)put(row16, sizeof(row16));
+            H.pvq_nmax = (uint16_t)put(h.pvq_ev_nmax, 16);
+            H.ent = (uint16_t)put(h.synth_entries[lm][C - 1], (size_t)ne * sizeof(SynthEntry));
+            H.slots = (uint16_t)put(h.synth_slot_entries[lm][C - 1], SYNTH_SLOTS * 32);
+            if (at > FBLOB_MAX_BYTES || at > 0xFFF0) return cudaErrorInvalidValue;
+            H.total = (uint16_t)at;
+            H.n_slots = h.synth_n_slots[lm][C - 1];
+            H.n_entries = (uint16_t)ne;
+            H.cols = (uint16_t)cols;
+            H.pad = 0;
+            g_fblob_bytes[lm][C - 1] = H.total;
+        }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_tab, &h, sizeof(h));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(g_fblob, blobs, sizeof(blobs));
     if (e != cudaSuccess) return e;
     e = set_warp_kernel_attributes();
     if (e != cudaSuccess) return e;
@@ -187,8 +252,10 @@ cudaError_t upload_tables(int device)
 
 template <int LM, int C> static cudaError_t launch_frame_w(const FrameArgs &a, cudaStream_t st)
 {
-    if (a.coef) k_frame_w<LM, C, false><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
-    else k_frame_w<LM, C, true><<<a.n_items, 32, w_smem_bytes(LM, C), st>>>(a);
+    const size_t smem = frame_smem_bytes(LM, C, g_fblob_bytes[LM][C - 1]);
+    const uint32_t grid = (a.item_end - a.item0 + FRAME_WARPS - 1) / FRAME_WARPS;
+    if (a.coef) k_frame_w<LM, C, false><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    else k_frame_w<LM, C, true><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -235,7 +302,7 @@ cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
 
 cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st)
 {
-    if (a.n_items == 0) return cudaSuccess;
+    if (a.item_end <= a.item0) return cudaSuccess;
     if (!a.coef && !a.idx) return cudaErrorInvalidValue;
     switch (a.lm * 2 + (a.channels - 1)) {
     case 0: return launch_frame_w<0, 1>(a, st);

@@ -37,7 +37,11 @@ __device__ __forceinline__ uint32_t laplace_freq1(uint32_t fs0, uint32_t decay)
 __device__ __forceinline__ uint32_t div_small_quotient(uint32_t a, uint32_t b)
 {
     float r;
+#ifdef OPN_HOST_SHIM  // host build for tests/host_shim: any estimate within the correction step's reach gives the same quotient
+    r = 1.0f / __uint2float_rn(b);
+#else
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rn(b)));
+#endif
     uint32_t q = __float2uint_rz(__uint2float_rn(a) * r * 0.999999f);
     if (a - q * b >= b) q += 1u;
     return q;
@@ -257,6 +261,243 @@ struct RangeDec {
 };
 
 // ---------------------------------------------------------------------------------------------
+// LaneDec: the same decoder for the lane-per-packet kernel (k_synth_rangedec), where the serial dependency chain of one
+// packet IS the kernel's run time.  Same arithmetic, value for value, as RangeDec / the reference; what changes is how
+// the bytes get there and that nothing on the chain branches:
+//   * normalize (decoder.rs:108-122) runs its 0..3 iterations at once: the number of byte shifts follows from rng alone,
+//     the k input bytes come out of a register (a 64-bit LSB-first shift register refilled one aligned 32-bit word at a
+//     time, the word fetched long before it is needed), and the k chained updates
+//     val = ((val << 8) + (255 & ~sym)) & (2^31 - 1) collapse into one shift-and-mask because the symbols of consecutive
+//     iterations are consecutive 8-bit windows, one bit apart, of the string [rem | b1 .. bk];
+//   * decode_bits (decoder.rs:279-303) reads from a 64-bit window refilled 32 bits at a time from the end of the packet;
+//   * bytes past `storage` read as zero on both ends, as read_byte / read_byte_from_end define it;
+//   * decode_laplace (decoder.rs:314-355) finds the magnitude by counting the thresholds it reaches in a table of the
+//     loop's (fl, fs) states (laplace_table below) instead of walking the loop.
+// The device words that hold packet bytes are read with aligned 32-bit loads: up to 3 bytes before the packet start and
+// after its end are touched (and masked off), never a word that holds no packet byte.
+constexpr int LAP_N = 16;  // tabulated magnitudes; larger ones continue the reference's loop
+
+// (fl, fs) of decode_laplace after the magnitude loop stopped at magnitude v, v = 0..LAP_N (decoder.rs:319-337):
+// fl[0] = 0, fs[0] = fs0; fl[1] = fs0, fs[1] = freq1 + 1; fl[v+1] = fl[v] + 2 fs[v], fs[v+1] = (((2 fs[v] - 2) decay) >> 15) + 1.
+// The loop runs while fm >= fl[v] + 2 fs[v] = fl[v+1], so the magnitude is the number of fl[1..] that fm reaches.
+__device__ __forceinline__ void laplace_table(uint32_t fs0, uint32_t decay, uint32_t *fl_tab, uint32_t *fs_tab)
+{
+    uint32_t fl = fs0, fs = laplace_freq1(fs0, decay) + 1u;
+    fl_tab[0] = 0u;
+    fs_tab[0] = fs0;
+    for (int v = 1; v <= LAP_N; v++) {
+        fl_tab[v] = fl;
+        fs_tab[v] = fs;
+        fs *= 2u;
+        fl += fs;
+        fs = (((fs - 2u) * decay) >> 15) + 1u;
+    }
+}
+
+struct LaneDec {
+    const uint8_t *src;
+    uint32_t storage;
+    uint64_t fbuf;        // front reader: the next fn bytes of the packet, first byte in bits 0..7
+    uint32_t fn;
+    const uint32_t *fw;   // next aligned word to fetch for the front reader
+    int32_t foff;         // packet offset of that word's first byte
+    uint64_t bbuf;        // back reader: the next bn raw bits, first bit in bit 0
+    uint32_t bn;
+    int32_t bhi;          // packet bytes [0, bhi) have not been handed to the back reader yet
+    uint32_t bits_total, rng, val, ext, rem;
+
+    __device__ __forceinline__ void front_fetch()
+    {
+        uint32_t w = 0u;
+        if (foff < (int32_t)storage) {  // the word holds at least one packet byte
+            w = __ldg(fw);
+            const int32_t keep = (int32_t)storage - foff;
+            if (keep < 4) w &= (1u << (8 * keep)) - 1u;
+        }
+        fbuf |= (uint64_t)w << (8u * fn);
+        fn += 4u;
+        fw += 1;
+        foff += 4;
+    }
+    __device__ __forceinline__ void back_fetch()
+    {
+        uint32_t r = 0u;
+        if (bhi >= 4) {
+            const uint8_t *q = src + (bhi - 4);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+            const uint32_t shb = ((uint32_t)reinterpret_cast<uintptr_t>(q) & 3u) * 8u;
+            const uint32_t lo = __ldg(base);
+            const uint32_t hi = shb ? __ldg(base + 1) : 0u;
+            r = __byte_perm(__funnelshift_r(lo, hi, shb), 0u, 0x0123);  // q[3] is read first (decoder.rs:97-104)
+        } else if (bhi > 0) {  // the first 1..3 bytes of the packet, then zeros
+            for (int j = 0; j < bhi; j++) r |= (uint32_t)src[bhi - 1 - j] << (8 * j);
+        }
+        bbuf |= (uint64_t)r << bn;
+        bn += 32u;
+        bhi -= 4;
+    }
+    // decoder.rs:108-122, all iterations at once
+    __device__ __forceinline__ void normalize()
+    {
+        const uint32_t k = (rng <= (1u << 23) ? 1u : 0u) + (rng <= (1u << 15) ? 1u : 0u) + (rng <= (1u << 7) ? 1u : 0u);
+        const uint32_t t = __byte_perm((uint32_t)fbuf, 0u, 0x4012);    // b1 << 16 | b2 << 8 | b3
+        const uint32_t w = ((rem << 24) | t) >> (8u * (3u - k));       // [rem | b1 .. bk]
+        const uint32_t sh = 8u * k;
+        val = ((val << sh) + (~(w >> 1) & ((1u << sh) - 1u))) & (RC_CODE_TOP - 1u);
+        rng <<= sh;
+        bits_total += sh;
+        rem = w & 255u;
+        fbuf >>= sh;
+        fn -= k;
+        if (fn <= 4u) front_fetch();
+    }
+    // decoder.rs:50-78
+    __device__ __forceinline__ void init(const uint8_t *b, uint32_t len)
+    {
+        src = b;
+        storage = len;
+        const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(b) & 3u;
+        fw = reinterpret_cast<const uint32_t *>(b - a);
+        foff = -(int32_t)a;
+        fbuf = 0ull;
+        fn = 0u;
+        {  // first word: the a bytes before the packet are dropped, bytes past its end are zero
+            uint32_t w = len ? __ldg(fw) : 0u;
+            if (a + len < 4u) w &= (1u << (8u * (a + len))) - 1u;
+            fbuf = (uint64_t)(w >> (8u * a));
+            fn = 4u - a;
+            fw += 1;
+            foff += 4;
+        }
+        front_fetch();
+        bbuf = 0ull;
+        bn = 0u;
+        bhi = (int32_t)len;
+        back_fetch();
+        back_fetch();
+        bits_total = RC_CODE_BITS + 1u - ((RC_CODE_BITS - RC_CODE_EXTRA) / RC_SYM_BITS) * RC_SYM_BITS;
+        rng = 1u << RC_CODE_EXTRA;
+        ext = 0u;
+        rem = (uint32_t)fbuf & 255u;  // read_byte
+        fbuf >>= 8;
+        fn -= 1u;
+        val = rng - 1u - (rem >> (RC_SYM_BITS - RC_CODE_EXTRA));
+        normalize();
+    }
+    // decoder.rs:172-181
+    __device__ __forceinline__ void update(uint32_t fl, uint32_t fh, uint32_t ft)
+    {
+        const uint32_t s = ext * (ft - fh);
+        val -= s;
+        rng = fl > 0u ? ext * (fh - fl) : rng - s;
+        normalize();
+    }
+    // decode_bin (decoder.rs:150-154), bits <= 15
+    __device__ __forceinline__ uint32_t decode_bin_small(uint32_t bits)
+    {
+        ext = rng >> bits;
+        const uint32_t s = div_small_quotient(val, ext);
+        return (1u << bits) - min(s + 1u, 1u << bits);
+    }
+    // decode_uint (decoder.rs:245-266) for ft <= 2^8: decode + update, no raw bits
+    __device__ __forceinline__ uint32_t uint_small(uint32_t ft)
+    {
+        ext = rng / ft;
+        const uint32_t q = div_small_quotient(val, ext);
+        const uint32_t s = ft - min(q + 1u, ft);
+        update(s, s + 1u, ft);
+        return s;
+    }
+    // decode_uint with the alphabet split and reciprocal precomputed on the host (see RangeDec::uint_precomputed)
+    __device__ __forceinline__ uint32_t uint_precomputed(uint32_t ft_minus1, uint32_t ft1, uint32_t ftb, uint32_t magic, uint32_t sh)
+    {
+        ext = div_magic(rng, magic, sh);
+        const uint32_t q = div_small_quotient(val, ext);
+        const uint32_t s = ft1 - min(q + 1u, ft1);
+        update(s, s + 1u, ft1);
+        if (ftb == 0u) return s;
+        const uint32_t t = (s << ftb) | bits(ftb);
+        return t <= ft_minus1 ? t : ft_minus1;  // corrupt frame saturates (decoder.rs:255-259)
+    }
+    // decoder.rs:184-195
+    __device__ __forceinline__ uint32_t bit_logp(uint32_t logp)
+    {
+        const uint32_t r = rng, d = val, s = r >> logp;
+        const uint32_t ret = d < s ? 1u : 0u;
+        val = ret ? d : d - s;
+        rng = ret ? s : r - s;
+        normalize();
+        return ret;
+    }
+    // decoder.rs:210-232
+    __device__ __forceinline__ uint32_t icdf(const uint8_t *tab, uint32_t ftb)
+    {
+        uint32_t s = rng, d = val, r = s >> ftb, t, ret = 0u;
+        for (;;) {
+            t = s;
+            s = r * (uint32_t)tab[ret];
+            if (d >= s) break;
+            ret += 1u;
+        }
+        val = d - s;
+        rng = t - s;
+        normalize();
+        return ret;
+    }
+    // decoder.rs:279-303, nbits <= 25
+    __device__ __forceinline__ uint32_t bits(uint32_t nbits)
+    {
+        const uint32_t ret = (uint32_t)bbuf & ((1u << nbits) - 1u);
+        bbuf >>= nbits;
+        bn -= nbits;
+        bits_total += nbits;
+        if (bn <= 32u) back_fetch();
+        return ret;
+    }
+    // decoder.rs:314-355 on the tables of laplace_table (same fs0, decay)
+    __device__ __forceinline__ int32_t laplace(const uint32_t *fl_tab, const uint32_t *fs_tab, uint32_t decay)
+    {
+        const uint32_t fm = decode_bin_small(15u);
+        uint32_t v = 0u;
+#pragma unroll
+        for (int j = 1; j <= 8; j++) v += fm >= fl_tab[j] ? 1u : 0u;
+        if (v == 8u) {
+#pragma unroll
+            for (int j = 9; j <= LAP_N; j++) v += fm >= fl_tab[j] ? 1u : 0u;
+        }
+        uint32_t fl = fl_tab[v], fs = fs_tab[v];
+        if (v == (uint32_t)LAP_N) {  // beyond the table: the reference's loop, continued
+            while (fm >= fl + 2u * fs) {
+                fs *= 2u;
+                fl += fs;
+                fs = (((fs - 2u) * decay) >> 15) + 1u;
+                v += 1u;
+            }
+        }
+        int32_t ret = (int32_t)v;
+        if (v) {
+            if (fm < fl + fs) ret = -ret;
+            else fl += fs;
+        }
+        update(fl, min(fl + fs, 32768u), 32768u);
+        return ret;
+    }
+    // src/range_coder/mod.rs:96-111
+    __device__ __forceinline__ uint32_t tell_frac() const
+    {
+        const uint32_t nbits = bits_total << RC_BITRES;
+        uint32_t l = rc_ilog(rng);
+        const uint32_t r = rng >> (l - 16u);
+        uint32_t b = (r >> 12) - 8u;
+        const uint32_t c = b == 0u ? 35733u : b == 1u ? 38967u : b == 2u ? 42495u : b == 3u ? 46340u
+                         : b == 4u ? 50535u : b == 5u ? 55109u : b == 6u ? 60097u : 65535u;
+        if (r > c) b += 1u;
+        l = (l << 3) + b;
+        return nbits - l;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // PVQ codeword expansion.  U(n,k) table in shared memory: rowoff[15] + data[1272]
 // (src/celt/pvc.rs:301-429).
 struct PvqTable {
@@ -270,6 +511,7 @@ struct PvqTable {
     __device__ __forceinline__ uint32_t v(uint32_t n, uint32_t k) const { return u(n, k) + u(n, k + 1u); }  // pvc.rs:289-291
 };
 
+#ifndef OPN_HOST_SHIM  // the warp-cooperative cwrsi below needs a warp
 __device__ __forceinline__ uint32_t sat_add_u32(uint32_t a, uint32_t b)
 {
     uint32_t s = a + b;
@@ -396,5 +638,6 @@ __device__ __forceinline__ float decode_pulses_warp(RangeDec &d, const PvqTable 
     uint32_t i = d.uint(ft);
     return cwrsi_warp(T, y, n, k, i, lane);
 }
+#endif  // OPN_HOST_SHIM
 
 }  // namespace opn

@@ -280,12 +280,13 @@ __host__ __device__ constexpr size_t synth_expand_smem()
 __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(SymbolArgs A)
 {
     __shared__ SynthEntry s_ent[SYNTH_MAX_ENTRIES];
-    __shared__ uint32_t s_fs0[21];  // get_start_freq(decay) per band (src/range_coder/mod.rs:530-534)
+    __shared__ uint32_t s_lfl[21][LAP_N + 1], s_lfs[21][LAP_N + 1];  // decode_laplace states per band (laplace_table)
     const uint32_t lane = threadIdx.x;  // index inside the CTA: one packet per thread
     const int lm = A.lm, C = A.channels;
     if (lane < 21u) {
         const uint32_t decay = 6000u + 400u * lane;
-        s_fs0[lane] = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;
+        const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;  // get_start_freq, src/range_coder/mod.rs:530-534
+        laplace_table(fs0, decay, s_lfl[lane], s_lfs[lane]);
     }
     const int ne = g_tab.synth_n_entries[lm][C - 1];
     {
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
         A.hdr[stream] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    RangeDec d;
+    LaneDec d;
     d.init(src, len);
     const uint32_t silence = d.bit_logp(15u);
     if (silence) {
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
     const uint32_t postfilter = d.bit_logp(1u);
     uint32_t octave = 0u, period = 0u, gain_idx = 0u, tapset = 0u;
     if (postfilter) {
-        octave = d.uint(6u);
+        octave = d.uint_small(6u);
         period = (16u << octave) + d.bits(4u + octave) - 1u;
         gain_idx = d.bits(3u);
         tapset = d.icdf(g_tab.tapset_icdf, 2u);
@@ -361,9 +362,8 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
     }
     for (int b = 0; b < 21; b++) {
         const uint32_t decay = 6000u + 400u * (uint32_t)b;
-        const uint32_t fs0 = s_fs0[b];
         for (int c = 0; c < C; c++) {
-            const int32_t v = d.laplace(fs0, decay);
+            const int32_t v = d.laplace(s_lfl[b], s_lfs[b], decay);
             if (sd) sd->coarse[c][b] = v;
         }
         if (sd && C == 1) sd->coarse[1][b] = 0;
@@ -410,18 +410,20 @@ struct ExpandTables {
     const uint16_t *row;
     const uint8_t *nmax;
     const SynthEntry *ent;  // [n_entries]
+    const uint8_t *slots;   // [n_slots][32]: lane -> entry, 0xFF = none
+    int n_slots;
 };
 template <int C>
 __device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t lane, const uint32_t *__restrict__ idx, float *rows, int chs,
                                          int32_t *__restrict__ y_out)
 {
     const int nf = 120 << lm;
-    const int nslots = g_tab.synth_n_slots[lm][C - 1];
+    const int nslots = T.n_slots;
     // everything a lane needs for its (at most SYNTH_SLOTS) parts is requested before the first walk starts
     uint32_t ee[SYNTH_SLOTS], ii[SYNTH_SLOTS];
 #pragma unroll
     for (int slot = 0; slot < SYNTH_SLOTS; slot++) {
-        ee[slot] = slot < nslots ? g_tab.synth_slot_entries[lm][C - 1][slot][lane] : 0xFFu;
+        ee[slot] = slot < nslots ? T.slots[slot * 32 + lane] : 0xFFu;
         ii[slot] = ee[slot] != 0xFFu ? __ldg(idx + ee[slot]) : 0u;
     }
 #pragma unroll 1
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
         for (int i = lane; i < nvec; i += 32) reinterpret_cast<int4 *>(yo)[i] = make_int4(0, 0, 0, 0);
     __syncwarp();
     if (!zero_frame) {
-        const ExpandTables T{s_pvq, s_cw, s_row, s_nmax, s_ent};
+        const ExpandTables T{s_pvq, s_cw, s_row, s_nmax, s_ent, &g_tab.synth_slot_entries[lm][C - 1][0][0], g_tab.synth_n_slots[lm][C - 1]};
         if (C == 2) w_expand<2>(T, lm, lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, s_rows, nf, yo);
         else w_expand<1>(T, lm, lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, s_rows, nf, yo);
     }

@@ -1,0 +1,71 @@
+// Host build of the DEVICE source csrc/rangedec.cuh (LaneDec: the branch-free range decoder of k_synth_rangedec), so that
+// the CPU test suite can replay range-coder scripts through the very code the kernel runs and compare every symbol,
+// tell_frac and rng with the oracle.  Test infrastructure: the CUDA intrinsics the header uses are given host bodies.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#define __device__
+#define __forceinline__ inline
+#define OPN_HOST_SHIM 1
+using std::max;
+using std::min;
+static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline float __uint2float_rn(uint32_t a) { return (float)a; }
+static inline uint32_t __float2uint_rz(float f) { return f <= 0.f ? 0u : (uint32_t)f; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
+{
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 255u) << (8 * i);
+    return r;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
+#include "../../opus-native_b200/csrc/rangedec.cuh"
+
+using namespace opn;
+struct Op { uint32_t op, a, b; };
+struct Out { uint32_t value, tell_frac, rng; };
+enum { OP_UINT = 0, OP_BITS = 1, OP_BIT_LOGP = 2, OP_ICDF = 3, OP_LAPLACE = 4 };
+
+// `buf` must be readable from the aligned word below buf to the aligned word above buf+len (the kernel's contract).
+extern "C" int lanedec_run_script(const uint8_t *buf, uint32_t len, const Op *ops, uint32_t n_ops, const uint8_t *icdf_pool, Out *out)
+{
+    LaneDec d;
+    d.init(buf, len);
+    for (uint32_t i = 0; i < n_ops; i++) {
+        const uint32_t a = ops[i].a, b = ops[i].b;
+        uint32_t v = 0;
+        switch (ops[i].op) {
+        case OP_UINT: {
+            if (a <= 256u) { v = d.uint_small(a); break; }
+            // the alphabet split and reciprocal of upload_tables (opn_kernels.cu)
+            const uint32_t ftm1 = a - 1u;
+            uint32_t ftb = 32u - (uint32_t)__builtin_clz(ftm1);
+            uint32_t ft1;
+            if (ftb > 8) { ftb -= 8; ft1 = (ftm1 >> ftb) + 1; } else { ftb = 0; ft1 = a; }
+            uint32_t sh = 0;
+            while ((1ull << sh) < ft1) sh++;
+            const uint32_t magic = (uint32_t)((((1ull << sh) - ft1) << 32) / ft1 + 1);
+            v = d.uint_precomputed(ftm1, ft1, ftb, magic, sh);
+            break;
+        }
+        case OP_BITS: v = d.bits(a); break;
+        case OP_BIT_LOGP: v = d.bit_logp(a); break;
+        case OP_ICDF: v = d.icdf(icdf_pool + a, b); break;
+        case OP_LAPLACE: {
+            uint32_t fl[LAP_N + 1], fs[LAP_N + 1];
+            laplace_table(a, b, fl, fs);
+            v = (uint32_t)d.laplace(fl, fs, b);
+            break;
+        }
+        default: return -1;
+        }
+        out[i].value = v;
+        out[i].tell_frac = d.tell_frac();
+        out[i].rng = d.rng;
+    }
+    return 0;
+}

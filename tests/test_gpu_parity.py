@@ -667,7 +667,7 @@ def test_batch_device_resident_path_matches_host_path():
         assert np.array_equal(d_pcm.cpu().numpy()[keep], want[f])
     # ring view: the last frame of stream 0 sits just before ring_pos
     ring_ptr, ring_n, pos_ptr = dec.ring()
-    assert ring_n == 3840 and ring_ptr and pos_ptr
+    assert ring_n == 2880 and ring_ptr and pos_ptr  # 3 x 960: a frame plus the 1024 + 2 samples of history before it
 
 
 @pytest.mark.parametrize("postfilter", [True, False])
@@ -783,6 +783,52 @@ def test_batch_reset_without_synchronize_while_steps_are_in_flight():
         if rep == 0:
             first = got.copy()
         assert np.array_equal(got, first), rep
+
+
+def test_pageable_pinned_and_registered_caller_buffers_give_the_same_pcm():
+    """The host-buffer entry point takes any host memory: pageable numpy arrays (what a Rust slice is: staged,
+    synchronous copies), buffers from opn_host_alloc and memory pinned in place with opn_host_register (asynchronous DMA,
+    two calls in flight).  Same packets, same PCM, bit for bit; the oracle checks one of them."""
+    lm, channels, pkt_bytes, ns, nfr, nf = 3, 2, 160, 1500, 4, 960
+    packets = opn.synth_fill(8800, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    lens = np.full(ns, pkt_bytes, np.uint32)
+
+    def run(make_pcm, arena_of, submit_only):
+        dec = opn.BatchDecoder(ns, **SYNTH)
+        out, keep, ticket = [], [], None
+        for f in range(nfr):
+            pcm = make_pcm()
+            keep.append(pcm)
+            arr = pcm.array if isinstance(pcm, opn.HostBuffer) else pcm
+            res = np.zeros(ns, np.int32)
+            t = dec.decode_float_ptrs(arena_of(f).ctypes.data, offsets.ctypes.data, lens.ctypes.data, arr.ctypes.data, nf * channels, nf,
+                                      res.ctypes.data, opn.FLAG_SUBMIT_ONLY if submit_only else 0)
+            if submit_only:
+                if ticket is not None:
+                    dec.wait(ticket)
+                ticket = t
+            assert np.all(res == nf)
+            out.append(arr)
+        if submit_only:
+            dec.wait(ticket)
+        return np.stack([o.copy() for o in out])
+
+    pageable = run(lambda: np.zeros((ns, nf * channels), np.float32), lambda f: packets[f].reshape(-1), False)
+    pinned_arena = opn.HostBuffer(packets.shape, np.uint8)
+    pinned_arena.array[...] = packets
+    pinned = run(lambda: opn.HostBuffer((ns, nf * channels), np.float32), lambda f: pinned_arena.array[f].reshape(-1), True)
+    regs = [np.zeros((ns, nf * channels), np.float32) for _ in range(nfr)]
+    for r in regs:
+        opn.host_register(r)
+    it = iter(regs)
+    registered = run(lambda: next(it), lambda f: packets[f].reshape(-1), True)
+    for r in regs:
+        opn.host_unregister(r)
+    assert np.array_equal(pageable, pinned) and np.array_equal(pageable, registered)
+    picks = [0, 1023, 1024, ns - 1]
+    want, _ = _oracle_chain(packets[:, picks], lm, channels)
+    assert np.array_equal(pageable[:, picks], want)
 
 
 def test_celt_frames_need_the_explicit_bitstream_opt_in():

@@ -55,7 +55,11 @@ def main():
     # "void k<3, 2>(Args)" -> base name "k" plus the mangled integer template arguments "ILi3ELi2EE"
     m = re.search(r"([\w:]+)\s*(?:<([^>]*)>)?\s*\(", kname)
     fn = (m.group(1) if m else kname).split("::")[-1]
-    targs = "I" + "".join("Li%sE" % re.sub(r"\(\w+\)", "", a).strip() for a in m.group(2).split(",")) + "E" if m and m.group(2) else ""
+    def mangle(a):  # "(int)3" -> Li3E, "(bool)1" -> Lb1E
+        t = re.match(r"\s*\((\w+)\)\s*(\w+)", a)
+        code = {"int": "i", "bool": "b", "unsigned": "j"}.get(t.group(1), "i") if t else "i"
+        return "L%s%sE" % (code, t.group(2) if t else a.strip())
+    targs = "I" + "".join(mangle(a) for a in m.group(2).split(",")) + "E" if m and m.group(2) else ""
     line_of = {}
     cur, on = None, False
     for ln in sass.split("\n"):
