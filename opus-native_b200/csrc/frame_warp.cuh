@@ -20,17 +20,14 @@
 namespace opn {
 
 // ---- post-filter -------------------------------------------------------------------------------
-// comb_filter_const_inplace term order (fallback.rs:46-51): y + g0*x2 + g1*(x1+x3) + g2*(x0+x4)
-__device__ __forceinline__ float comb5(float y, float x0, float x1, float x2, float x3, float x4, float g0, float g1, float g2)
-{
-    return y + (g0 * x2) + (g1 * (x1 + x3)) + (g2 * (x0 + x4));
-}
-
-// One sample of the C channels of a stream.
+// One sample of the C channels of a stream.  For stereo the two channels of a sample travel as a float2 and every sum
+// of the filter is ONE packed add (p_add, imdct.cuh) for both; the products stay scalar (see p_add).
 template <int C> struct WSmp;
 template <> struct WSmp<1> {
     float a;
     __device__ __forceinline__ static WSmp ld(const float *p) { return WSmp{*p}; }  // interleaved layout (the PCM ring)
+    __device__ __forceinline__ WSmp operator+(WSmp o) const { return WSmp{a + o.a}; }
+    __device__ __forceinline__ WSmp scaled(float g) const { return WSmp{g * a}; }
 };
 template <> struct WSmp<2> {
     float a, b;
@@ -39,46 +36,38 @@ template <> struct WSmp<2> {
         const float2 v = *reinterpret_cast<const float2 *>(p);
         return WSmp{v.x, v.y};
     }
+    __device__ __forceinline__ WSmp operator+(WSmp o) const
+    {
+        const float2 r = p_add(make_float2(a, b), make_float2(o.a, o.b));
+        return WSmp{r.x, r.y};
+    }
+    __device__ __forceinline__ WSmp scaled(float g) const { return WSmp{g * a, g * b}; }
 };
+// comb_filter_const_inplace term order (fallback.rs:46-51): y + g0*x2 + g1*(x1+x3) + g2*(x0+x4)
 template <int C>
 __device__ __forceinline__ WSmp<C> w_comb5(WSmp<C> y, WSmp<C> x0, WSmp<C> x1, WSmp<C> x2, WSmp<C> x3, WSmp<C> x4, float g0, float g1,
                                            float g2)
 {
-    WSmp<C> r;
-    r.a = comb5(y.a, x0.a, x1.a, x2.a, x3.a, x4.a, g0, g1, g2);
-    if constexpr (C == 2) r.b = comb5(y.b, x0.b, x1.b, x2.b, x3.b, x4.b, g0, g1, g2);
-    return r;
+    return y + x2.scaled(g0) + (x1 + x3).scaled(g1) + (x0 + x4).scaled(g2);
 }
 // cross-fade accumulation order of comb_filter_inplace (mod.rs:166-177); a* = y[i-t0-2 .. i-t0+2],
 // b* = y[i-t1-2 .. i-t1+2]
-__device__ __forceinline__ float xfade1(float y, float a0, float a1, float a2, float a3, float a4, float b0, float b1, float b2, float b3,
-                                        float b4, bool has0, bool has1, float f, float g00, float g01, float g02, float g10, float g11,
-                                        float g12)
-{
-    float v = y;
-    if (has0) {
-        v = v + (((1.0f - f) * g00) * a2);
-        v = v + (((1.0f - f) * g01) * (a3 + a1));
-        v = v + (((1.0f - f) * g02) * (a4 + a0));
-    }
-    if (has1) {
-        v = v + ((f * g10) * b2);
-        v = v + ((f * g11) * (b3 + b1));
-        v = v + ((f * g12) * (b4 + b0));
-    }
-    return v;
-}
 template <int C>
 __device__ __forceinline__ WSmp<C> w_xfade(WSmp<C> y, const WSmp<C> *a, const WSmp<C> *b, bool has0, bool has1, float f, float g00,
                                            float g01, float g02, float g10, float g11, float g12)
 {
-    WSmp<C> r;
-    r.a = xfade1(y.a, a[0].a, a[1].a, a[2].a, a[3].a, a[4].a, b[0].a, b[1].a, b[2].a, b[3].a, b[4].a, has0, has1, f, g00, g01, g02, g10,
-                 g11, g12);
-    if constexpr (C == 2)
-        r.b = xfade1(y.b, a[0].b, a[1].b, a[2].b, a[3].b, a[4].b, b[0].b, b[1].b, b[2].b, b[3].b, b[4].b, has0, has1, f, g00, g01, g02,
-                     g10, g11, g12);
-    return r;
+    WSmp<C> v = y;
+    if (has0) {
+        v = v + a[2].scaled((1.0f - f) * g00);
+        v = v + (a[3] + a[1]).scaled((1.0f - f) * g01);
+        v = v + (a[4] + a[0]).scaled((1.0f - f) * g02);
+    }
+    if (has1) {
+        v = v + b[2].scaled(f * g10);
+        v = v + (b[3] + b[1]).scaled(f * g11);
+        v = v + (b[4] + b[0]).scaled(f * g12);
+    }
+    return v;
 }
 
 // tap gains of the old and the new filter (comb_filter/mod.rs:45-55, 146-151)

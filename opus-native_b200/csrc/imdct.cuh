@@ -11,10 +11,27 @@
 
 namespace opn {
 
-__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// src/math.rs:115-124
-__device__ __forceinline__ float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// Packed FP32 adds (sm_100 FADD2, PTX add.rn.f32x2): one instruction, both halves rounded to nearest once -- the same two
+// values two scalar FADDs give.  The SASS operand may swap its halves and negate either one for free, which ptxas
+// recovers from the way the operand is put together here (p_add(a, make_float2(s.y, -s.x)) is ONE FADD2).
+// Only sums are packed.  ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even under --fmad=false
+// (checked on 12.9), which would change roundings; a scalar FMUL is never contracted, so every product that feeds a sum
+// stays scalar.  tests/test_host_logic.py::test_no_fma_in_the_float_kernels looks at the SASS.
+__device__ __forceinline__ float2 p_add(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return p_add(a, b); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return p_add(a, make_float2(-b.x, -b.y)); }  // x - y == x + (-y), exactly
+// (a.x + s.y, a.y - s.x) and (a.x - s.y, a.y + s.x): a -/+ i s, the rotated sums of the butterflies
+__device__ __forceinline__ float2 c_add_mrot(float2 a, float2 s) { return p_add(a, make_float2(s.y, -s.x)); }
+__device__ __forceinline__ float2 c_sub_mrot(float2 a, float2 s) { return p_add(a, make_float2(-s.y, s.x)); }
+// src/math.rs:115-124: (a.x b.x - a.y b.y, a.x b.y + a.y b.x); four scalar products, one packed sum
+__device__ __forceinline__ float2 c_mul(float2 a, float2 b) { return p_add(make_float2(a.x * b.x, a.x * b.y), make_float2(-(a.y * b.y), a.y * b.x)); }
 __device__ __forceinline__ float2 c_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
 #define OPN_FRAC_1_SQRT_2 0.70710678118654752440f

@@ -82,8 +82,8 @@ __device__ __forceinline__ void r_bfly4(float2 &d0, float2 &d1, float2 &d2, floa
     const float2 s3 = c_add(s0, s2), s4 = c_sub(s0, s2);
     d2 = c_sub(a0, s3);
     d0 = c_add(a0, s3);
-    d1 = make_float2(s5.x + s4.y, s5.y - s4.x);
-    d3 = make_float2(s5.x - s4.y, s5.y + s4.x);
+    d1 = c_add_mrot(s5, s4);
+    d3 = c_sub_mrot(s5, s4);
 }
 // kiss_fft.rs:129-147 (m == 1)
 __device__ __forceinline__ void r_bfly4_m1(float2 &d0, float2 &d1, float2 &d2, float2 &d3)
@@ -94,19 +94,29 @@ __device__ __forceinline__ void r_bfly4_m1(float2 &d0, float2 &d1, float2 &d2, f
     d2 = c_sub(a0, s1);
     d0 = c_add(a0, s1);
     s1 = c_sub(d1, d3);
-    d1 = make_float2(s0.x + s1.y, s0.y - s1.x);
-    d3 = make_float2(s0.x - s1.y, s0.y + s1.x);
+    d1 = c_add_mrot(s0, s1);
+    d3 = c_sub_mrot(s0, s1);
 }
 // kiss_fft.rs:55-87, pair J of a group of 8: (lo, hi) = (d[J], d[4+J])
 template <int J> __device__ __forceinline__ void r_bfly2(float2 &lo, float2 &hi)
 {
     const float2 x = hi;
+    const float2 a = lo;
+    if (J == 2) {  // t = (x.y, -x.x)
+        hi = c_sub_mrot(a, x);
+        lo = c_add_mrot(a, x);
+        return;
+    }
     float2 t;
     if (J == 0) t = x;
-    else if (J == 1) t = make_float2((x.x + x.y) * OPN_FRAC_1_SQRT_2, (x.y - x.x) * OPN_FRAC_1_SQRT_2);
-    else if (J == 2) t = make_float2(x.y, -x.x);
-    else t = make_float2((x.y - x.x) * OPN_FRAC_1_SQRT_2, (-(x.y + x.x)) * OPN_FRAC_1_SQRT_2);
-    const float2 a = lo;
+    else if (J == 1) {
+        const float2 u = c_add_mrot(x, x);  // (x.x + x.y, x.y - x.x)
+        t = make_float2(u.x * OPN_FRAC_1_SQRT_2, u.y * OPN_FRAC_1_SQRT_2);
+    } else {
+        // (x.y - x.x, -(x.y + x.x)); negating both operands of a sum negates it exactly, signed zeros included
+        const float2 u = p_add(make_float2(x.y, -x.y), make_float2(-x.x, -x.x));
+        t = make_float2(u.x * OPN_FRAC_1_SQRT_2, u.y * OPN_FRAC_1_SQRT_2);
+    }
     hi = c_sub(a, t);
     lo = c_add(a, t);
 }
@@ -119,8 +129,8 @@ __device__ __forceinline__ void r_bfly3(float2 &d0, float2 &d1, float2 &d2, floa
     const float2 dm = c_sub(d0, c_scale(s3, 0.5f));
     s0 = c_scale(s0, epi3y);
     d0 = c_add(d0, s3);
-    d2 = make_float2(dm.x + s0.y, dm.y - s0.x);
-    d1 = make_float2(dm.x - s0.y, dm.y + s0.x);
+    d2 = c_add_mrot(dm, s0);
+    d1 = c_sub_mrot(dm, s0);
 }
 // kiss_fft.rs:190-243
 __device__ __forceinline__ void r_bfly5(float2 &d0, float2 &d1, float2 &d2, float2 &d3, float2 &d4, float2 w1, float2 w2,
@@ -131,17 +141,14 @@ __device__ __forceinline__ void r_bfly5(float2 &d0, float2 &d1, float2 &d2, floa
     const float2 s7 = c_add(s1, s4), s10 = c_sub(s1, s4);
     const float2 s8 = c_add(s2, s3), s9 = c_sub(s2, s3);
     d0 = c_add(s0, c_add(s7, s8));
-    float2 s5, s6, s11, s12;
-    s5.x = s0.x + (s7.x * ya.x + s8.x * yb.x);
-    s5.y = s0.y + (s7.y * ya.x + s8.y * yb.x);
-    s6.x = s10.y * ya.y + s9.y * yb.y;
-    s6.y = -(s10.x * ya.y + s9.x * yb.y);
-    d1 = c_sub(s5, s6);
-    d4 = c_add(s5, s6);
-    s11.x = s0.x + (s7.x * yb.x + s8.x * ya.x);
-    s11.y = s0.y + (s7.y * yb.x + s8.y * ya.x);
-    s12.x = s9.y * ya.y - s10.y * yb.y;
-    s12.y = s10.x * yb.y - s9.x * ya.y;
+    // s5 = s0 + (s7 ya.x + s8 yb.x);  s6 = (s10.y ya.y + s9.y yb.y, -(s10.x ya.y + s9.x yb.y))
+    const float2 s5 = p_add(s0, p_add(make_float2(s7.x * ya.x, s7.y * ya.x), make_float2(s8.x * yb.x, s8.y * yb.x)));
+    const float2 q6 = p_add(make_float2(s10.y * ya.y, s10.x * ya.y), make_float2(s9.y * yb.y, s9.x * yb.y));  // (s6.x, -s6.y)
+    d1 = p_add(s5, make_float2(-q6.x, q6.y));   // s5 - s6
+    d4 = p_add(s5, make_float2(q6.x, -q6.y));   // s5 + s6
+    // s11 = s0 + (s7 yb.x + s8 ya.x);  s12 = (s9.y ya.y - s10.y yb.y, s10.x yb.y - s9.x ya.y)
+    const float2 s11 = p_add(s0, p_add(make_float2(s7.x * yb.x, s7.y * yb.x), make_float2(s8.x * ya.x, s8.y * ya.x)));
+    const float2 s12 = p_add(make_float2(s9.y * ya.y, s10.x * yb.y), make_float2(-(s10.y * yb.y), -(s9.x * ya.y)));
     d2 = c_add(s11, s12);
     d3 = c_sub(s11, s12);
 }
@@ -239,9 +246,8 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
                     const float x0 = x[blk + NBLK * (2 * r) + NBLK * 30 * q];
                     const float x1 = x[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * q];
                     const float2 t = tab_ld<TS>(tp + 15 * q);  // (trig[i], trig[n4 + i])
-                    const float re = (x1 * t.x) + (x0 * t.y);
-                    const float im = (x0 * t.x) - (x1 * t.y);
-                    d[blk * GS + p] = make_float2(im, re);
+                    // re = (x1 t.x) + (x0 t.y), im = (x0 t.x) - (x1 t.y); the element is (im, re)
+                    d[blk * GS + p] = p_add(make_float2(x0 * t.x, x1 * t.x), make_float2(-(x1 * t.y), x0 * t.y));
                 }
         }
         __syncwarp();  // every coefficient is in a register: the row may be overwritten
@@ -301,8 +307,10 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
 #pragma unroll
                 for (int j = 0; j < 15; j++) {
                     const float2 t = tab_ld<TS>(tp + GS * j);
-                    ob[2 * u + 2 * GS * j] = (d[j].y * t.x) + (d[j].x * t.y);
-                    ob[N2 - 1 - 2 * u - 2 * GS * j] = (d[j].y * t.y) - (d[j].x * t.x);
+                    // out[2k] = (d.y t.x) + (d.x t.y), out[n2-1-2k] = (d.y t.y) - (d.x t.x)
+                    const float2 r = p_add(make_float2(d[j].y * t.x, d[j].y * t.y), make_float2(d[j].x * t.y, -(d[j].x * t.x)));
+                    ob[2 * u + 2 * GS * j] = r.x;
+                    ob[N2 - 1 - 2 * u - 2 * GS * j] = r.y;
                 }
             }
         }
@@ -327,8 +335,9 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
         float *ob = o + ch * CHF + N2 * blk;
         const float x0 = ob[119 - i], x1 = ob[i];
         const float w0 = tab_ld<TS>(win + i), w1 = tab_ld<TS>(win + 119 - i);
-        ob[i] = (w1 * x1) - (w0 * x0);
-        ob[119 - i] = (w0 * x1) + (w1 * x0);
+        const float2 r = p_add(make_float2(w1 * x1, w0 * x1), make_float2(-(w0 * x0), w1 * x0));
+        ob[i] = r.x;        // (w1 x1) - (w0 x0)
+        ob[119 - i] = r.y;  // (w0 x1) + (w1 x0)
     }
     __syncwarp();
 }

@@ -275,7 +275,8 @@ struct RangeDec {
 //     loop's (fl, fs) states (laplace_table below) instead of walking the loop.
 // The device words that hold packet bytes are read with aligned 32-bit loads: up to 3 bytes before the packet start and
 // after its end are touched (and masked off), never a word that holds no packet byte.
-constexpr int LAP_N = 16;  // tabulated magnitudes; larger ones continue the reference's loop
+constexpr int LAP_N = 16;      // tabulated magnitudes; larger ones continue the reference's loop
+constexpr int LAP_FIRST = 9;   // thresholds every call compares against before it looks at the rest (magnitudes up to 8 stop here)
 
 // (fl, fs) of decode_laplace after the magnitude loop stopped at magnitude v, v = 0..LAP_N (decoder.rs:319-337):
 // fl[0] = 0, fs[0] = fs0; fl[1] = fs0, fs[1] = freq1 + 1; fl[v+1] = fl[v] + 2 fs[v], fs[v+1] = (((2 fs[v] - 2) decay) >> 15) + 1.
@@ -301,25 +302,40 @@ struct LaneDec {
     uint32_t fn;
     const uint32_t *fw;   // next aligned word to fetch for the front reader
     int32_t foff;         // packet offset of that word's first byte
+    uint32_t fpend;       // the word before it, already loaded (consumed by the next refill: its load latency is off the chain)
     uint64_t bbuf;        // back reader: the next bn raw bits, first bit in bit 0
     uint32_t bn;
     int32_t bhi;          // packet bytes [0, bhi) have not been handed to the back reader yet
+    uint32_t bpend;       // the next 32 raw bits, already loaded and put in order
     uint32_t bits_total, rng, val, ext, rem;
 
-    __device__ __forceinline__ void front_fetch()
+    // One aligned word of the packet, bytes past `storage` zeroed (packet offset of its first byte: off >= 0).
+    __device__ __forceinline__ uint32_t front_load(const uint32_t *p, int32_t off) const
     {
         uint32_t w = 0u;
-        if (foff < (int32_t)storage) {  // the word holds at least one packet byte
-            w = __ldg(fw);
-            const int32_t keep = (int32_t)storage - foff;
+        if (off < (int32_t)storage) {  // the word holds at least one packet byte
+            w = __ldg(p);
+            const int32_t keep = (int32_t)storage - off;
             if (keep < 4) w &= (1u << (8 * keep)) - 1u;
         }
-        fbuf |= (uint64_t)w << (8u * fn);
+        return w;
+    }
+    __device__ __forceinline__ void front_fetch()
+    {
+        fbuf |= (uint64_t)fpend << (8u * fn);  // loaded one refill ago
         fn += 4u;
+        fpend = front_load(fw, foff);
         fw += 1;
         foff += 4;
     }
     __device__ __forceinline__ void back_fetch()
+    {
+        bbuf |= (uint64_t)bpend << bn;  // loaded one refill ago
+        bn += 32u;
+        bpend = back_load();
+    }
+    // the next four bytes from the end, first one in bits 0..7; zeros once the packet start is passed
+    __device__ __forceinline__ uint32_t back_load()
     {
         uint32_t r = 0u;
         if (bhi >= 4) {
@@ -332,9 +348,8 @@ struct LaneDec {
         } else if (bhi > 0) {  // the first 1..3 bytes of the packet, then zeros
             for (int j = 0; j < bhi; j++) r |= (uint32_t)src[bhi - 1 - j] << (8 * j);
         }
-        bbuf |= (uint64_t)r << bn;
-        bn += 32u;
         bhi -= 4;
+        return r;
     }
     // decoder.rs:108-122, all iterations at once
     __device__ __forceinline__ void normalize()
@@ -369,10 +384,14 @@ struct LaneDec {
             fw += 1;
             foff += 4;
         }
+        fpend = front_load(fw, foff);
+        fw += 1;
+        foff += 4;
         front_fetch();
         bbuf = 0ull;
         bn = 0u;
         bhi = (int32_t)len;
+        bpend = back_load();
         back_fetch();
         back_fetch();
         bits_total = RC_CODE_BITS + 1u - ((RC_CODE_BITS - RC_CODE_EXTRA) / RC_SYM_BITS) * RC_SYM_BITS;
@@ -460,10 +479,10 @@ struct LaneDec {
         const uint32_t fm = decode_bin_small(15u);
         uint32_t v = 0u;
 #pragma unroll
-        for (int j = 1; j <= 8; j++) v += fm >= fl_tab[j] ? 1u : 0u;
-        if (v == 8u) {
+        for (int j = 1; j <= LAP_FIRST; j++) v += fm >= fl_tab[j] ? 1u : 0u;
+        if (v == (uint32_t)LAP_FIRST) {
 #pragma unroll
-            for (int j = 9; j <= LAP_N; j++) v += fm >= fl_tab[j] ? 1u : 0u;
+            for (int j = LAP_FIRST + 1; j <= LAP_N; j++) v += fm >= fl_tab[j] ? 1u : 0u;
         }
         uint32_t fl = fl_tab[v], fs = fs_tab[v];
         if (v == (uint32_t)LAP_N) {  // beyond the table: the reference's loop, continued

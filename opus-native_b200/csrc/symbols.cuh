@@ -368,13 +368,16 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
         }
         if (sd && C == 1) sd->coarse[1][b] = 0;
     }
-    for (int b = 0; b < 21; b++) {
-        for (int c = 0; c < C; c++) {
-            const uint32_t v = d.bits(2u);
-            if (sd) sd->fine[c][b] = (int32_t)v;
-        }
-        if (sd && C == 1) sd->fine[1][b] = 0;
+    // fine energy: 21*C two-bit fields, band-major.  decode_bits is a plain LSB-first bit window (decoder.rs:279-303), so
+    // twelve consecutive 2-bit reads are one 24-bit read cut into fields.
+    for (int f0 = 0; f0 < 21 * C; f0 += 12) {
+        const int nfld = min(12, 21 * C - f0);
+        uint32_t w = d.bits(2u * (uint32_t)nfld);
+        if (sd)
+            for (int f = f0; f < f0 + nfld; f++, w >>= 2) sd->fine[f % C][f / C] = (int32_t)(w & 3u);
     }
+    if (sd && C == 1)
+        for (int b = 0; b < 21; b++) sd->fine[1][b] = 0;
     uint32_t *idx = A.idx + (size_t)stream * SYNTH_MAX_ENTRIES;
     uint32_t n_pulses = 0u;
     for (int e = 0; e < ne; e++) {

@@ -29,6 +29,36 @@ def test_library_exports_every_declared_symbol():
         assert getattr(L, name) is not None
 
 
+def test_no_fma_in_the_float_kernels():
+    """The float kernels must round exactly like the reference (no contraction of a*b+c): the TU is built with -fmad=false
+    and only SUMS are packed (FADD2); ptxas would contract a packed multiply feeding a packed add into FFMA2 regardless
+    of --fmad=false, so there must be none.  The only FMAs allowed are the division / square-root expansions of the PVQ
+    gain (2^-5 / sqrt(yy)) in the kernels that expand pulses, and of the soft clip."""
+    import collections
+    sass = subprocess.run(["cuobjdump", "-sass", opn.library_path()], capture_output=True, text=True, check=True).stdout
+    counts, cur = collections.defaultdict(collections.Counter), None
+    for ln in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+([A-Z0-9]+)", ln)
+        if m and cur:
+            counts[cur][m.group(1)] += 1
+    frame = [k for k in counts if "k_frame_w" in k]
+    assert len(frame) == 16
+    for k, c in counts.items():
+        assert c["FFMA2"] == 0 and c["FMUL2"] == 0, (k, dict(c))
+        if "k_frame_w" in k:
+            assert c["FADD2"] > 100, k                      # the packed sums are there
+            if k.endswith("Lb0EEEvNS_9FrameArgsE"):         # coefficient rows from memory: no expansion, no sqrt
+                assert c["FFMA"] == 0, (k, c["FFMA"])
+            else:
+                assert c["FFMA"] <= 24, (k, c["FFMA"])
+        if "k_op_imdct_w" in k or "k_op_comb" in k:
+            assert c["FFMA"] == 0, (k, c["FFMA"])
+
+
 def test_no_gpu_means_loud_failure():
     if opn.lib().opn_device_count() > 0:
         pytest.skip("a CUDA device is present")

@@ -16,7 +16,7 @@ import tempfile
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "opus-native_b200", "libopusb200.so")
+SO = os.environ.get("OPN_SO", os.path.join(ROOT, "opus-native_b200", "libopusb200.so"))  # the library the report was taken with
 
 
 def main():
