@@ -104,9 +104,9 @@ class ClockSampler:
                 "how": "NVML polled every ~2 ms inside the timed regions (resident, per-kernel and end-to-end passes)"}
 
 
-def workload_config(n, transient_permille):
+def workload_config(n, transient_permille, bitstream=1):
     """The `config` object of both arms (identical by construction)."""
-    return {"workload": f"{n} CELT-only fullband 20 ms stereo streams @64 kbps per GPU (BASELINE configs[1]; SYNTH-CELT/1, "
+    return {"workload": f"{n} CELT-only fullband 20 ms stereo streams @64 kbps per GPU (BASELINE configs[1]; SYNTH-CELT/{bitstream}, "
                         "160 B packets): range decode + PVQ + IMDCT/TDAC + comb post-filter",
             "streams_per_gpu": n, "frames_per_step_per_gpu": n, "packet_bytes": PKT_BYTES, "frame_ms": 20, "channels": CHANNELS,
             "transient_permille": transient_permille}
@@ -157,7 +157,7 @@ def run_reference(args):
         "impl": "reference", "metric": "concurrent_realtime_48k_streams_decoded", "value": value, "unit": "streams",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
-        "config": workload_config(n, args.transient_permille),
+        "config": workload_config(n, args.transient_permille, args.bitstream),
         "cpu_baseline": {"value": value, "unit": "streams", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} chained steps x {n} stereo 20 ms frames (the full workload step), "
                                    "C oracle port of the reference crate (Rust toolchain absent), one thread per core"},
@@ -195,10 +195,14 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (BASELINE config 2: 4096)")
     ap.add_argument("--transient-permille", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bitstream", type=int, default=1, choices=[1, 2],
+                    help="1: SYNTH-CELT/1 (the headline workload), 2: SYNTH-CELT/2 (allocation-driven frames; kept next to it under profiles/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     quiet_stdout()
     if args.impl == "reference":
+        if args.bitstream != 1:
+            raise SystemExit("--impl reference times the SYNTH-CELT/1 workload (the headline); there is no CPU loop for --bitstream 2")
         run_reference(args)
         return
 
@@ -235,11 +239,12 @@ def main():
     total = K + W
     lo, hi = opn.shard_range(n * world, rank, world)  # this rank's global stream ids
     cores = cpu_threads()  # this rank's share after pinning
-    packets = opn.synth_fill(lo, n, 0, total, LM, CHANNELS, PKT_BYTES, args.transient_permille, n_threads=cores)
+    fill = opn.synth_fill if args.bitstream == 1 else opn.celt2_fill
+    packets = fill(lo, n, 0, total, LM, CHANNELS, PKT_BYTES, args.transient_permille, n_threads=cores)
     step_bytes = n * PKT_BYTES
 
     # ---------------- resident-input measurement (value) ----------------
-    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
+    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=args.bitstream)
     stream = torch.cuda.ExternalStream(dec.cuda_stream, device=dev)
     d_arena = torch.from_numpy(packets.reshape(-1)).to(dev)
     d_off = (torch.arange(n, dtype=torch.int64, device=dev) * PKT_BYTES).to(torch.int32)
@@ -294,7 +299,7 @@ def main():
     # The call a user makes: pinned host packets in, pinned host PCM out, every step.  Two calls are kept
     # in flight (OPN_FLAG_SUBMIT_ONLY + opn_batch_wait), so the 31.5 MB PCM download of step n overlaps the
     # upload and decode of step n+1; each step's PCM is read on the host (checksum) after its wait.
-    dec2 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
+    dec2 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=args.bitstream)
     h_arena = torch.from_numpy(packets.reshape(-1)).pin_memory()
     h_pcm = [torch.zeros((n, NF * CHANNELS), dtype=torch.float32).pin_memory() for _ in range(2)]
     a_np, p_np = h_arena.numpy(), [t.numpy() for t in h_pcm]
@@ -350,7 +355,7 @@ def main():
     # ---------------- the same end-to-end loop through Decoder::decode::<i16> (extra figure, not the headline) ----
     # soft clip + Sample::from_f32 run on the device, so half the bytes cross PCIe.
     K16 = min(K, 100)
-    dec3 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
+    dec3 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=args.bitstream)
     h_pcm16 = [torch.zeros((n, NF * CHANNELS), dtype=torch.int16).pin_memory() for _ in range(2)]
     p16 = [t.numpy() for t in h_pcm16]
 
@@ -378,7 +383,7 @@ def main():
     # What a Rust Vec<f32> / &mut [f32] is: the CUDA runtime stages such copies through its own bounce buffer,
     # synchronously, so calls cannot overlap.  opn_host_alloc / opn_host_register give a caller the pinned kind.
     KP = min(K, 30)
-    dec4 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=opn.BITSTREAM_SYNTH_CELT_1)
+    dec4 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=args.bitstream)
     pg_arena = packets.reshape(-1)
     pg_pcm = np.zeros((n, NF * CHANNELS), np.float32)
     for f in range(W):
@@ -395,7 +400,7 @@ def main():
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.bitstream == 1:  # the CPU loop restates SYNTH-CELT/1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
         fr = min(total, 48)
@@ -426,7 +431,7 @@ def main():
             "metric": "concurrent_realtime_48k_streams_decoded", "value": value, "unit": "streams",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_value / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f32", "data": "synthetic",
-            "config": workload_config(n, args.transient_permille),
+            "config": workload_config(n, args.transient_permille, args.bitstream),
             "detail": {
                 "cache": f"inputs larger than L2: {total} distinct packet sets resident in HBM, each read once; per 4096 streams "
                          "the decoder's PCM ring is 94 MB and every step writes 31.5 MB of new PCM into it",

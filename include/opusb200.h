@@ -110,6 +110,12 @@ typedef struct {
  * PVQ parts on a fixed schedule): built only from operations the crate implements, NOT interoperable with Opus. */
 #define OPN_BITSTREAM_OPUS 0
 #define OPN_BITSTREAM_SYNTH_CELT_1 1
+/* OPN_BITSTREAM_SYNTH_CELT_2: the allocation-driven layout of DESIGN.md section 3b -- band boosts, allocation trim,
+ * compute_allocation from the mode's tables (src/celt/mode.rs:13-28, 70-111) driven by the running tell_frac, fine-energy
+ * bits, and per band a theta split (bitexact_cos / bitexact_log2tan, src/math.rs:51-75) down to PVQ leaves whose (n, K) are
+ * computed per frame on the device.  A slice of a real CELT frame (no tf, spreading, folding, joint stereo, energies):
+ * closer to RFC 6716 section 4.3 than SYNTH-CELT/1, still NOT Opus-interoperable, and parity-unpinned like it. */
+#define OPN_BITSTREAM_SYNTH_CELT_2 2
 
 #define OPN_FLAG_DEVICE_PTRS 1u  /* arena/offsets/lens/pcm/results are device pointers; call is asynchronous */
 #define OPN_FLAG_NO_PCM_COPY 2u  /* leave PCM in the device ring only (read it with opn_batch_ring) */
@@ -161,8 +167,8 @@ int opn_batch_stats(opn_batch *b, uint64_t kernel_launches[3], double kernel_ms[
  * read (4 bytes each) -- the comb term of the frame kernel's algorithmic bytes. */
 int opn_batch_history_samples(opn_batch *b, uint64_t *out, int reset);
 void *opn_batch_cuda_stream(opn_batch *b);
-/* The library runs its stages on several internal streams (range decode; the frame kernel of a large batch in two
- * halves).  opn_batch_join makes everything enqueued so far an ancestor of whatever is enqueued next on
+/* The library runs its stages on several internal streams (range decode; the frame kernel of a large batch in three
+ * groups of streams).  opn_batch_join makes everything enqueued so far an ancestor of whatever is enqueued next on
  * opn_batch_cuda_stream (e.g. the caller's end-of-region event or a consumer kernel reading the PCM ring); it does
  * not block the host. */
 int opn_batch_join(opn_batch *b);
@@ -216,6 +222,25 @@ typedef struct {
 int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offsets,
                          const uint32_t *lens, uint32_t n_packets, int lm, int channels,
                          opn_synth_side *side_out, int32_t *y_out, float *coef_out);
+
+/* ---- SYNTH-CELT/2 frames: everything the frame decode derives besides the coefficients ---------------------------- */
+typedef struct {
+    int32_t silence, postfilter, octave, period, gain_idx, tapset, transient, intra;
+    int32_t spread, alloc_trim, coded_bands, intensity, dual_stereo, anti_collapse, balance;
+    int32_t offsets[21], pulses[21], ebits[21], fine_priority[21]; /* band boosts; compute_allocation's outputs */
+    int32_t coarse[2][21], fine[2][21], fine_final[2][21];
+    uint32_t n_parts, n_pulses, n_splits, theta_sum;
+    uint32_t final_rng, tell_frac;
+} opn_celt2_side;
+/* Symbol decode + expansion only: payloads (bytes after the TOC) -> side record, pulses, coefficients.
+ * y_out / coef_out: [n_packets][channels][120<<lm]; any output may be NULL. */
+int opn_op_celt2_symbols(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                         int lm, int channels, opn_celt2_side *side_out, int32_t *y_out, float *coef_out);
+/* Generator (host): one packet of exactly pkt_bytes (TOC + SYNTH-CELT/2 payload) / a [frame][stream][pkt_bytes] block. */
+int opn_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes,
+                     uint32_t transient_permille, uint8_t *out, opn_celt2_side *truth);
+int opn_celt2_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,
+                   uint32_t pkt_bytes, uint32_t transient_permille, int n_threads, uint8_t *out);
 
 /* ---- synthetic stream generator (host; uses the library's own range ENCODER) --------- */
 /* Writes one packet of exactly pkt_bytes (TOC + SYNTH-CELT/1 payload) for (stream_id, frame).

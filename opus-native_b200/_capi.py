@@ -13,7 +13,7 @@ OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VI
 FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY = 1, 2, 4, 8
 # OPN_BITSTREAM_*: CELT frames are Unimplemented (as in the crate, whose CeltDecoder::decode is todo!()) unless the caller
 # opts in to the synthetic SYNTH-CELT/1 frame layout (not Opus-interoperable)
-BITSTREAM_OPUS, BITSTREAM_SYNTH_CELT_1 = 0, 1
+BITSTREAM_OPUS, BITSTREAM_SYNTH_CELT_1, BITSTREAM_SYNTH_CELT_2 = 0, 1, 2
 # OPN_SAMPLE_*: the types the crate implements `Sample` for (lib.rs:63-107)
 SAMPLE_F32, SAMPLE_I16, SAMPLE_I32, SAMPLE_U16, SAMPLE_U32, SAMPLE_F64 = 0, 1, 2, 3, 4, 5
 SAMPLE_FORMAT_OF = {np.dtype(np.float32): SAMPLE_F32, np.dtype(np.int16): SAMPLE_I16, np.dtype(np.int32): SAMPLE_I32,
@@ -22,6 +22,12 @@ OP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4")])
 OUT_DTYPE = np.dtype([("value", "<u4"), ("tell_frac", "<u4"), ("rng", "<u4")])
 SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra")]
                       + [("coarse", "<i4", (2, 21)), ("fine", "<i4", (2, 21)), ("final_rng", "<u4"), ("tell_frac", "<u4"), ("n_pulses", "<u4")])
+
+CELT2_SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra",
+                                                  "spread", "alloc_trim", "coded_bands", "intensity", "dual_stereo", "anti_collapse", "balance")]
+                            + [(n, "<i4", (21,)) for n in ("offsets", "pulses", "ebits", "fine_priority")]
+                            + [(n, "<i4", (2, 21)) for n in ("coarse", "fine", "fine_final")]
+                            + [(n, "<u4") for n in ("n_parts", "n_pulses", "n_splits", "theta_sum", "final_rng", "tell_frac")])
 
 _ERR_NAMES = {-1: "BadArguments", -2: "BufferToSmall", -3: "InternalError", -4: "InvalidPacket",
               -5: "FrameSizeTooSmall", -6: "Unimplemented", -7: "Cuda"}
@@ -115,6 +121,9 @@ def lib():
     sig("opn_op_comb_filter", C.c_int, C.c_int, vp, vp, sz, sz, sz, u32, vp, vp, sz)
     sig("opn_op_pcm_soft_clip", C.c_int, C.c_int, vp, sz, sz, C.c_int, u32, vp)
     sig("opn_op_synth_symbols", C.c_int, C.c_int, vp, vp, vp, u32, C.c_int, C.c_int, vp, vp, vp)
+    sig("opn_op_celt2_symbols", C.c_int, C.c_int, vp, vp, vp, u32, C.c_int, C.c_int, vp, vp, vp)
+    sig("opn_celt2_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp, vp)
+    sig("opn_celt2_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("opn_synth_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp, vp)
     sig("opn_synth_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("opn_enc_run_script", C.c_int, vp, u32, vp, vp, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32))
@@ -463,6 +472,34 @@ def synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt
     nt = n_threads or min(os.cpu_count() or 1, 32)
     _chk(lib().opn_synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt_bytes, transient_permille, nt, _p(out)))
     return out
+
+
+def celt2_packet(stream_id, frame_idx, lm, channels, pkt_bytes, transient_permille=0):
+    """One SYNTH-CELT/2 packet (TOC + payload) and the side record the generator's own frame logic produced."""
+    out = np.zeros(pkt_bytes, np.uint8)
+    truth = np.zeros(1, CELT2_SIDE_DTYPE)
+    _chk(lib().opn_celt2_packet(stream_id, frame_idx, lm, channels, pkt_bytes, transient_permille, _p(out), _p(truth)))
+    return out, truth[0]
+
+
+def celt2_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt_bytes, transient_permille=0, n_threads=None):
+    """-> uint8 [n_frames, n_streams, pkt_bytes]"""
+    out = np.zeros((n_frames, n_streams, pkt_bytes), np.uint8)
+    nt = n_threads or min(os.cpu_count() or 1, 32)
+    _chk(lib().opn_celt2_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt_bytes, transient_permille, nt, _p(out)))
+    return out
+
+
+def op_celt2_symbols(arena, offsets, lens, lm, channels, device=0):
+    arena = np.ascontiguousarray(arena, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint32)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    n, nf = len(offsets), 120 << lm
+    side = np.zeros(n, CELT2_SIDE_DTYPE)
+    y = np.zeros((n, channels, nf), np.int32)
+    coef = np.zeros((n, channels, nf), np.float32)
+    _chk(lib().opn_op_celt2_symbols(device, _p(arena), _p(offsets), _p(lens), n, lm, channels, _p(side), _p(y), _p(coef)))
+    return side, y, coef
 
 
 def enc_run_script(nbytes, ops, values, icdf_pool=None, y_in=None):

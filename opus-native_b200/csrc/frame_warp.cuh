@@ -221,8 +221,12 @@ __host__ __device__ constexpr size_t frame_smem_bytes(int lm, int channels, size
     return 16 + blob_bytes + (size_t)FRAME_WARPS * frame_warp_bytes(lm, channels);
 }
 
-template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
+// MODE: where the coefficient rows come from.  FRAME_ROWS: global memory, by TMA (unfused variant); FRAME_SYNTH1: expanded from
+// the codeword indices of the static SYNTH-CELT/1 schedule; FRAME_SYNTH2: expanded from the per-frame part list of SYNTH-CELT/2.
+enum { FRAME_ROWS = 0, FRAME_SYNTH1 = 1, FRAME_SYNTH2 = 2 };
+template <int LM, int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
 {
+    constexpr bool EXPAND = MODE != FRAME_ROWS;
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NF = 120 << LM;
     constexpr int CHF = w_ch_floats(LM);
@@ -290,12 +294,19 @@ template <int LM, int C, bool EXPAND> __global__ void __launch_bounds__(32 * FRA
     const float2 *t_tw = reinterpret_cast<const float2 *>(blob + H.tw);
     const float *t_win = reinterpret_cast<const float *>(blob + H.win), *t_winsq = reinterpret_cast<const float *>(blob + H.win_sq);
     const bool lost = status == ITEM_LOST;
-    if constexpr (EXPAND) {
+    if constexpr (MODE == FRAME_SYNTH1) {
         if (!lost && !(hdr_x & 1u)) {  // not silence
             const ExpandTables T{reinterpret_cast<const uint32_t *>(blob + H.pvq_u), reinterpret_cast<const uint2 *>(blob + H.pvq_cw),
                                  reinterpret_cast<const uint16_t *>(blob + H.pvq_row), blob + H.pvq_nmax,
                                  reinterpret_cast<const SynthEntry *>(blob + H.ent), blob + H.slots, (int)H.n_slots};
             w_expand<C>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr);
+        }
+        __syncwarp();
+    } else if constexpr (MODE == FRAME_SYNTH2) {
+        if (!lost && !(hdr_x & 1u)) {
+            // part shapes are only known per frame: the walk uses the full PVQ tables in global memory (L1/L2 resident)
+            const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
+            w_expand2<C>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, o, CHF, nullptr);
         }
         __syncwarp();
     } else {

@@ -11,6 +11,7 @@
 
 #include "opn_internal.h"
 #include "opn_tables.h"
+#include "celt2.cuh"
 
 namespace opn {
 
@@ -29,6 +30,7 @@ public:
     RangeEncoder(uint8_t *buf, uint32_t len) : buf_(buf), storage_(len) {}
 
     int error() const { return err_; }
+    uint32_t rng() const { return rng_; }
     uint32_t range_bytes() const { return offs_; }
     uint32_t tell() const { return bits_total_ - ilog(rng_); }  // mod.rs:84-86
     uint32_t tell_frac() const                                   // mod.rs:96-111
@@ -352,6 +354,124 @@ int opn_synth_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channel
     for (uint32_t attempt = 0; attempt < 8 && rc == OPN_ERR_BUFFER_TOO_SMALL; attempt++)
         rc = synth_packet_attempt(stream_id, frame_idx, attempt, lm, channels, pkt_bytes, transient_permille, out, t);
     return rc;
+}
+
+// ---- SYNTH-CELT/2 generator: celt2_frame (celt2.cuh) run by an ENCODING coder that draws every symbol value from
+// splitmix64 and writes it with the host range encoder.  The frame logic is the very code the decode kernel runs; only the
+// coder differs.  The oracle's generator (oracle/celt2.c, an independent restatement) must produce the same bytes.
+namespace {
+struct GenCoder {
+    RangeEncoder &e;
+    SplitMix64 rng;
+    uint32_t tp;
+    uint32_t tell() const { return e.tell(); }
+    uint32_t tell_frac() const { return e.tell_frac(); }
+    uint32_t transient_permille() const { return tp; }
+    uint32_t bit_logp(uint32_t logp, uint32_t p1_permille)
+    {
+        const uint32_t v = rng.below(1000) < p1_permille ? 1u : 0u;
+        e.bit_logp(v, logp);
+        return v;
+    }
+    uint32_t icdf(const uint8_t *tab, uint32_t ftb, uint32_t n_sym)
+    {
+        const uint32_t v = rng.below(n_sym);
+        e.icdf(v, tab, ftb);
+        return v;
+    }
+    uint32_t uint_(uint32_t ft)
+    {
+        const uint32_t v = rng.below(ft);
+        e.uint(v, ft);
+        return v;
+    }
+    uint32_t pulses_index(uint32_t ft) { return uint_(ft); }  // a uniform codeword index == encode_pulses(cwrsi(index))
+    uint32_t bits(uint32_t n)
+    {
+        const uint32_t v = rng.below(1u << n);
+        e.bits(v, n);
+        return v;
+    }
+    int32_t laplace(int band)
+    {
+        const uint32_t decay = 6000u + 400u * (uint32_t)band;
+        const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;
+        return e.laplace((int32_t)rng.below(16) - 7, fs0, decay);
+    }
+    uint32_t theta_tri(uint32_t qn)
+    {
+        const uint32_t h = qn >> 1, ft = (h + 1) * (h + 1);
+        const uint32_t itheta = rng.below(qn + 1);
+        uint32_t fl, fs;
+        if (itheta <= h) {
+            fs = itheta + 1;
+            fl = (itheta * (itheta + 1)) >> 1;
+        } else {
+            fs = qn + 1 - itheta;
+            fl = ft - (((qn + 1 - itheta) * (qn + 2 - itheta)) >> 1);
+        }
+        e.encode(fl, fl + fs, ft);
+        return itheta;
+    }
+};
+struct CountSink {
+    uint32_t n = 0, np = 0;
+    void put_part(int, int, int k, uint32_t, float) { n++; np += (uint32_t)k; }
+    uint32_t nsign = 0;
+    void put_sign(int, uint32_t) { nsign++; }  // one-bin bands are not PVQ leaves, but the decoder's list holds them too
+    uint32_t pulses() const { return np; }
+};
+const Celt2Tabs kHostCelt2Tabs{OPN_E_BANDS, OPN_LOG_N, OPN_ALLOC_VECTORS, OPN_CACHE_BITS, OPN_CACHE_CAPS, OPN_LOG2_FRAC_TABLE, OPN_CACHE_INDEX,
+                               OPN_PVQ_U_DATA, OPN_PVQ_U_ROW};
+}  // namespace
+
+int opn_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes, uint32_t transient_permille,
+                     uint8_t *out, opn_celt2_side *truth)
+{
+    if (!out || lm < 0 || lm > 3 || channels < 1 || channels > 2 || pkt_bytes < 8 || pkt_bytes > 1276) return OPN_ERR_BAD_ARG;
+    static_assert(sizeof(opn_celt2_side) == sizeof(Celt2Side), "opusb200.h and celt2.cuh describe the same record");
+    Celt2Side local;
+    Celt2Side *sd = truth ? reinterpret_cast<Celt2Side *>(truth) : &local;
+    std::memset(sd, 0, sizeof(*sd));
+    out[0] = (uint8_t)(0x80 | 0x60 | (lm << 3) | (channels == 2 ? 0x4 : 0) | 0x0);
+    RangeEncoder enc(out + 1, pkt_bytes - 1);
+    GenCoder gc{enc, SplitMix64{4242ull + 1000003ull * stream_id + 0xD1B54A32D192ED03ull * frame_idx}, transient_permille};
+    CountSink sink;
+    uint32_t flags = 0, n_pulses = 0;
+    celt2_frame(gc, kHostCelt2Tabs, pkt_bytes - 1, lm, channels, sd, sink, flags, n_pulses);
+    sd->n_parts = sink.n;
+    sd->n_pulses = n_pulses;
+    sd->tell_frac = enc.tell_frac();
+    sd->final_rng = enc.rng();
+    if (sink.n + sink.nsign > (uint32_t)CELT2_MAX_PARTS) return OPN_ERR_INTERNAL;  // more leaves than the decoder's list holds
+    if (enc.error()) return enc.error();
+    if (enc.tell() > 8u * (pkt_bytes - 1u)) return OPN_ERR_BUFFER_TOO_SMALL;
+    enc.done();
+    if (enc.error()) return enc.error();
+    return (int)pkt_bytes;
+}
+
+int opn_celt2_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,
+                   uint32_t pkt_bytes, uint32_t transient_permille, int n_threads, uint8_t *out)
+{
+    if (!out || n_streams == 0 || n_frames == 0) return OPN_ERR_BAD_ARG;
+    if (n_threads < 1) n_threads = 1;
+    std::vector<int> rc((size_t)n_threads, 0);
+    std::vector<std::thread> pool;
+    const uint64_t total = (uint64_t)n_streams * n_frames;
+    for (int th = 0; th < n_threads; th++)
+        pool.emplace_back([&, th]() {
+            for (uint64_t w = total * th / n_threads; w < total * (th + 1) / n_threads; w++) {
+                const uint64_t f = w / n_streams, s = w % n_streams;
+                int r = opn_celt2_packet(first_stream + s, first_frame + f, lm, channels, pkt_bytes, transient_permille, out + w * pkt_bytes,
+                                         nullptr);
+                if (r < 0) rc[th] = r;
+            }
+        });
+    for (auto &t : pool) t.join();
+    for (int r : rc)
+        if (r < 0) return r;
+    return OPN_OK;
 }
 
 int opn_synth_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,

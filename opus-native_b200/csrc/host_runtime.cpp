@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "opn_internal.h"
+#include "celt2.cuh"
 
 using namespace opn;
 
@@ -133,9 +134,10 @@ struct opn_batch {
     // A large bucket's frame kernel is cut into NGROUPS launches over contiguous stream ranges, group g on stream_fr[g]
     // (stream_fr[0] is `stream`).  A stream's frames stay in order (its group's stream), but the tail of one group's launch
     // overlaps the body of the other's, and step n+1 of a group may start while step n of the other is still running:
-    // the SMs never drain between steps.
+    // the SMs never drain between steps.  Measured at 4096 stereo 20 ms streams (tools/experiments/variants.sh, us per
+    // step): 1 group 71-72, 2 groups 46.3, 3 groups 44.1-44.8, 4 groups 49.
 #ifndef OPN_FRAME_GROUPS
-#define OPN_FRAME_GROUPS 2
+#define OPN_FRAME_GROUPS 3
 #endif
     static constexpr int NGROUPS = OPN_FRAME_GROUPS;
     static constexpr uint32_t GROUP_MIN_ITEMS = 2048;  // smaller buckets run as one launch on `stream`
@@ -161,6 +163,7 @@ struct opn_batch {
     PfState *d_pf = nullptr;
     uint4 *d_hdr[NSETS] = {};
     int32_t *d_status[NSETS] = {};
+    Celt2Part *d_parts[NSETS] = {};  // SYNTH-CELT/2 batches only: PVQ leaves per stream
     // host-path staging (device + pinned host)
     // Two staging slots, so a host-buffer call can be submitted while the previous one is still downloading.
     struct Staging {
@@ -243,7 +246,11 @@ int timed_launch(opn_batch *b, int kind, cudaError_t (*fn)(opn_batch *, const vo
     return OPN_OK;
 }
 
-cudaError_t do_rangedec(opn_batch *b, const void *a) { return launch_synth_rangedec(*static_cast<const SymbolArgs *>(a), b->stream); }
+cudaError_t do_rangedec(opn_batch *b, const void *a)
+{
+    const SymbolArgs &s = *static_cast<const SymbolArgs *>(a);
+    return b->cfg.bitstream == OPN_BITSTREAM_SYNTH_CELT_2 ? launch_celt2_rangedec(s, b->stream) : launch_synth_rangedec(s, b->stream);
+}
 cudaError_t do_expand(opn_batch *b, const void *a) { return launch_synth_expand(*static_cast<const SymbolArgs *>(a), b->stream); }
 cudaError_t do_frame(opn_batch *b, const void *a) { return launch_frame(*static_cast<const FrameArgs *>(a), b->stream); }
 
@@ -299,6 +306,9 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.y_out = nullptr;
     s.idx = b->d_idx[p];
     s.pkt_cap = pkt_cap;
+    s.parts = b->d_parts[p];
+    s.side2 = nullptr;
+    const bool celt2 = b->cfg.bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
     int rc;
     if (b->timing) {
         // measurement pass: everything in order on one stream, events around each stage
@@ -325,7 +335,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
             if (b->k1_grouped[p])
                 for (int g = 1; g < opn_batch::NGROUPS; g++) CU(cudaStreamWaitEvent(srd, b->ev_fr[p][g], 0));
         }
-        CU(launch_synth_rangedec(s, srd));
+        CU(celt2 ? launch_celt2_rangedec(s, srd) : launch_synth_rangedec(s, srd));
         CU(cudaEventRecord(b->ev_rd[p], srd));
         b->launches[0]++;
         if (b->unfused) {
@@ -340,7 +350,8 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     }
     FrameArgs m{};
     m.coef = b->unfused ? b->d_coef[p] : nullptr;
-    m.idx = b->d_idx[p];
+    m.idx = celt2 ? nullptr : b->d_idx[p];
+    m.parts = celt2 ? b->d_parts[p] : nullptr;
     m.hdr = b->d_hdr[p];
     m.status = b->d_status[p];
     m.stream_idx = d_stream_idx;
@@ -483,7 +494,8 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
 {
     if (!out || !cfg || n_streams == 0) return OPN_ERR_BAD_ARG;
     if (cfg->channels < 1 || cfg->channels > 2) return OPN_ERR_BAD_ARG;
-    if (cfg->bitstream != OPN_BITSTREAM_OPUS && cfg->bitstream != OPN_BITSTREAM_SYNTH_CELT_1) return OPN_ERR_BAD_ARG;
+    if (cfg->bitstream != OPN_BITSTREAM_OPUS && cfg->bitstream != OPN_BITSTREAM_SYNTH_CELT_1 && cfg->bitstream != OPN_BITSTREAM_SYNTH_CELT_2)
+        return OPN_ERR_BAD_ARG;
     switch (cfg->fs_hz) {
     case 48000: break;
     case 8000: case 12000: case 16000: case 24000: return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:23 "TODO ... downsample"
@@ -498,7 +510,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->cfg = *cfg;
     b->gain = host_gain_from_q8(cfg->gain_q8);
     const char *uf = std::getenv("OPN_UNFUSED_EXPAND");
-    b->unfused = uf && uf[0] == '1';
+    b->unfused = uf && uf[0] == '1' && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_1;
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     // All pipeline streams have the same priority (measured in round 1, tools/experiments/priorities.sh: raising the
@@ -512,6 +524,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
         if (e == cudaSuccess && b->unfused) e = cudaMalloc(&b->d_coef[q], n * C * 960 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_hdr[q], n * sizeof(uint4));
+        if (e == cudaSuccess && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_parts[q], n * CELT2_MAX_PARTS * sizeof(Celt2Part));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
@@ -569,6 +582,7 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(b->d_idx[q]);
         cudaFree(b->d_coef[q]);
         cudaFree(b->d_hdr[q]);
+        cudaFree(b->d_parts[q]);
         cudaFree(b->d_status[q]);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
@@ -715,7 +729,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 any_gap = true;
                 continue;
             }
-            if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C || b->cfg.bitstream != OPN_BITSTREAM_SYNTH_CELT_1) {
+            if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C || b->cfg.bitstream == OPN_BITSTREAM_OPUS) {
                 // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); mono<->stereo
                 // mapping lives in the stubbed CeltDecoder; CeltDecoder::decode itself is todo!() (celt/decoder.rs:47-56):
                 // CELT frames decode only when the batch was created for the SYNTH-CELT/1 layout.
@@ -828,7 +842,7 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
     // is validated on the device and reported per stream.  Asynchronous on the batch stream.
     const int lm = lm_of_frame(frame_size);
     if (lm < 0 || !arena) return OPN_ERR_BAD_ARG;
-    if (b->cfg.bitstream != OPN_BITSTREAM_SYNTH_CELT_1) return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:47-56 is todo!()
+    if (b->cfg.bitstream == OPN_BITSTREAM_OPUS) return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:47-56 is todo!()
     float *dense = (flags & OPN_FLAG_NO_PCM_COPY) ? nullptr : pcm;
     if (dense && (pcm_stride_floats < frame_size * (size_t)C || (pcm_stride_floats & 3) ||
                   (reinterpret_cast<uintptr_t>(dense) & 15)))
@@ -1322,6 +1336,53 @@ int opn_op_synth_symbols(int device, const uint8_t *arena, const uint32_t *offse
     CU(launch_synth_symbols(s, nullptr));
     CU(cudaDeviceSynchronize());
     if (side_out) CU(cudaMemcpy(side_out, dS.p, (size_t)n_packets * sizeof(opn_synth_side), cudaMemcpyDeviceToHost));
+    if (y_out) CU(cudaMemcpy(y_out, dY.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
+    if (coef_out) CU(cudaMemcpy(coef_out, dC.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+int opn_op_celt2_symbols(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                         int lm, int channels, opn_celt2_side *side_out, int32_t *y_out, float *coef_out)
+{
+    if (!arena || !offsets || !lens || n_packets == 0 || lm < 0 || lm > 3 || channels < 1 || channels > 2) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    size_t arena_end = 0;
+    for (uint32_t i = 0; i < n_packets; i++) arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
+    const size_t row = (size_t)channels * (120u << lm);
+    DevBuf dA, dO, dL, dS, dSt, dY, dC, dH, dP;
+    CU(dA.alloc(arena_end + 8));
+    CU(dO.alloc(n_packets * 4));
+    CU(dL.alloc(n_packets * 4));
+    CU(dS.alloc((size_t)n_packets * sizeof(Celt2Side)));
+    CU(dSt.alloc(n_packets * 4));
+    CU(dH.alloc((size_t)n_packets * sizeof(uint4)));
+    CU(dP.alloc((size_t)n_packets * CELT2_MAX_PARTS * sizeof(Celt2Part)));
+    CU(dY.alloc((size_t)n_packets * row * 4));
+    CU(dC.alloc((size_t)n_packets * row * 4));
+    CU(cudaMemcpy(dA.p, arena, arena_end, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dO.p, offsets, n_packets * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dL.p, lens, n_packets * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dY.p, 0, (size_t)n_packets * row * 4));
+    CU(cudaMemset(dC.p, 0, (size_t)n_packets * row * 4));
+    SymbolArgs s{};
+    s.arena = dA.as<uint8_t>();
+    s.offsets = dO.as<uint32_t>();
+    s.lens = dL.as<uint32_t>();
+    s.n_items = n_packets;
+    s.lm = lm;
+    s.channels = channels;
+    s.has_toc = 0;
+    s.hdr = dH.as<uint4>();
+    s.status = dSt.as<int32_t>();
+    s.coef = dC.as<float>();
+    s.y_out = dY.as<int32_t>();
+    s.parts = dP.as<Celt2Part>();
+    s.side2 = dS.as<Celt2Side>();
+    CU(launch_celt2_rangedec(s, nullptr));
+    CU(launch_celt2_expand(s, nullptr));
+    CU(cudaDeviceSynchronize());
+    if (side_out) CU(cudaMemcpy(side_out, dS.p, (size_t)n_packets * sizeof(Celt2Side), cudaMemcpyDeviceToHost));
     if (y_out) CU(cudaMemcpy(y_out, dY.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
     if (coef_out) CU(cudaMemcpy(coef_out, dC.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
     return OPN_OK;

@@ -8,6 +8,9 @@
 
 namespace opn {
 
+struct Celt2Part;
+struct Celt2Side;
+
 constexpr int SYM_WARPS_PER_CTA = 4;
 #ifndef OPN_RD_WARPS
 #define OPN_RD_WARPS 1
@@ -54,11 +57,14 @@ struct SymbolArgs {
     int32_t *y_out;              // same shape or nullptr
     uint32_t *idx;               // [n_streams][72] scratch: PVQ codeword indices (range decode -> expansion)
     uint32_t pkt_cap;            // bytes of shared memory per warp for the packet
+    struct Celt2Part *parts;     // SYNTH-CELT/2: [n_streams][CELT2_MAX_PARTS] PVQ leaves (range decode -> expansion)
+    struct Celt2Side *side2;     // SYNTH-CELT/2: [n_streams] or nullptr: full side record (tests)
 };
 
 struct FrameArgs {
     const float *coef;            // [n_streams][C][120<<lm] coefficient rows (unfused variant only)
-    const uint32_t *idx;          // [n_streams][72] PVQ codeword indices (range decode output)
+    const uint32_t *idx;          // [n_streams][72] PVQ codeword indices (range decode output, SYNTH-CELT/1)
+    const struct Celt2Part *parts;  // [n_streams][CELT2_MAX_PARTS] PVQ leaves (range decode output, SYNTH-CELT/2) or nullptr
     const uint4 *hdr;             // [n_streams] frame headers (range decode output)
     const int32_t *status;        // [n_streams]  (range decode output)
     const uint32_t *stream_idx;   // [n_items] or nullptr
@@ -87,6 +93,8 @@ cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets
 cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st);   // both stages on one stream
 cudaError_t launch_synth_rangedec(const SymbolArgs &a, cudaStream_t st);  // stage 0a: one lane per packet
 cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st);    // stage 0b: one warp per packet
+cudaError_t launch_celt2_rangedec(const SymbolArgs &a, cudaStream_t st);  // SYNTH-CELT/2: one lane per packet -> header + part list
+cudaError_t launch_celt2_expand(const SymbolArgs &a, cudaStream_t st);    // SYNTH-CELT/2 operator: part lists -> coefficient rows
 // the frame kernel: (PVQ expansion when a.coef == nullptr) + IMDCT + TDAC + comb post-filter + PCM store
 cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st);
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,

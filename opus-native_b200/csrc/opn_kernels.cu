@@ -25,10 +25,12 @@ template <int LM, int C> static cudaError_t set_carveout()
 {
     // percent of the SM's unified 256 KB used as shared memory; the rest is L1 (history taps, per-stream state)
     const int smem = (int)frame_smem_bytes(LM, C, g_fblob_bytes[LM][C - 1]);
-    cudaError_t e = cudaFuncSetAttribute(k_frame_w<LM, C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH1>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH2>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
 }
 static cudaError_t set_warp_kernel_attributes()
@@ -172,6 +174,12 @@ cudaError_t upload_tables(int device)
                 }
             }
         }
+    for (int i = 0; i < 21; i++) h.log_n[i] = OPN_LOG_N[i];
+    for (int i = 0; i < 231; i++) h.alloc_vectors[i] = OPN_ALLOC_VECTORS[i];
+    for (int i = 0; i < 105; i++) h.cache_index[i] = OPN_CACHE_INDEX[i];
+    for (int i = 0; i < 392; i++) h.cache_bits[i] = OPN_CACHE_BITS[i];
+    for (int i = 0; i < 168; i++) h.cache_caps[i] = OPN_CACHE_CAPS[i];
+    for (int i = 0; i < 24; i++) h.log2_frac[i] = OPN_LOG2_FRAC_TABLE[i];
     h.tapset_icdf[0] = 2; h.tapset_icdf[1] = 1; h.tapset_icdf[2] = 0; h.tapset_icdf[3] = 0;
     for (int i = 0; i < 9; i++) h.comb_gains[i] = OPN_COMB_GAINS[i];
     // ---- the frame kernel's table blobs (FBlobHdr), one per (LM, channels)
@@ -254,8 +262,9 @@ template <int LM, int C> static cudaError_t launch_frame_w(const FrameArgs &a, c
 {
     const size_t smem = frame_smem_bytes(LM, C, g_fblob_bytes[LM][C - 1]);
     const uint32_t grid = (a.item_end - a.item0 + FRAME_WARPS - 1) / FRAME_WARPS;
-    if (a.coef) k_frame_w<LM, C, false><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
-    else k_frame_w<LM, C, true><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    if (a.coef) k_frame_w<LM, C, FRAME_ROWS><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    else if (a.parts) k_frame_w<LM, C, FRAME_SYNTH2><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    else k_frame_w<LM, C, FRAME_SYNTH1><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -293,6 +302,22 @@ cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+cudaError_t launch_celt2_rangedec(const SymbolArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    if (!a.parts || !a.hdr) return cudaErrorInvalidValue;
+    constexpr uint32_t per_cta = RANGEDEC_WARPS_PER_CTA * 32u;
+    k_celt2_rangedec<<<(a.n_items + per_cta - 1u) / per_cta, per_cta, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_celt2_expand(const SymbolArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    k_celt2_expand<<<(a.n_items + 3u) / 4u, 128, 4 * 2 * 960 * sizeof(float), st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
 {
     cudaError_t e = launch_synth_rangedec(a, st);
@@ -303,7 +328,7 @@ cudaError_t launch_synth_symbols(const SymbolArgs &a, cudaStream_t st)
 cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st)
 {
     if (a.item_end <= a.item0) return cudaSuccess;
-    if (!a.coef && !a.idx) return cudaErrorInvalidValue;
+    if (!a.coef && !a.idx && !a.parts) return cudaErrorInvalidValue;
     switch (a.lm * 2 + (a.channels - 1)) {
     case 0: return launch_frame_w<0, 1>(a, st);
     case 1: return launch_frame_w<0, 2>(a, st);

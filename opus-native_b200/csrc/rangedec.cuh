@@ -427,6 +427,33 @@ struct LaneDec {
         update(s, s + 1u, ft);
         return s;
     }
+    // decode (decoder.rs:143-147), any ft
+    __device__ __forceinline__ uint32_t decode(uint32_t ft)
+    {
+        ext = rng / ft;
+        const uint32_t s = val / ext;
+        return ft - min(s + 1u, ft);
+    }
+    // decode_uint (decoder.rs:245-266), any ft >= 2
+    __device__ __forceinline__ uint32_t uint_any(uint32_t ft)
+    {
+        ft -= 1u;
+        uint32_t ftb = rc_ilog(ft);
+        if (ftb > RC_UINT_BITS) {
+            ftb -= RC_UINT_BITS;
+            const uint32_t ft1 = (ft >> ftb) + 1u;
+            const uint32_t s = decode(ft1);
+            update(s, s + 1u, ft1);
+            const uint32_t t = (s << ftb) | bits(ftb);
+            return t <= ft ? t : ft;  // corrupt frame saturates (decoder.rs:255-259)
+        }
+        ft += 1u;
+        const uint32_t s = decode(ft);
+        update(s, s + 1u, ft);
+        return s;
+    }
+    // src/range_coder/mod.rs:84-86
+    __device__ __forceinline__ uint32_t tell() const { return bits_total - rc_ilog(rng); }
     // decode_uint with the alphabet split and reciprocal precomputed on the host (see RangeDec::uint_precomputed)
     __device__ __forceinline__ uint32_t uint_precomputed(uint32_t ft_minus1, uint32_t ft1, uint32_t ftb, uint32_t magic, uint32_t sh)
     {

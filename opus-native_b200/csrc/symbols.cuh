@@ -9,6 +9,7 @@
 #include "opn_device.cuh"
 #include "opn_internal.h"
 #include "rangedec.cuh"
+#include "celt2.cuh"
 
 namespace opn {
 
@@ -529,6 +530,183 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     __syncwarp();
     if (coef4)
         for (int i = lane; i < nvec; i += 32) coef4[i] = reinterpret_cast<const float4 *>(s_rows)[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// SYNTH-CELT/2 (celt2.cuh): allocation-driven frames.  ONE LANE decodes one packet: the whole frame logic is a serial
+// function of the range decoder's state (every budget decision reads tell_frac).  It leaves the frame header and the list
+// of PVQ leaves (position, size, pulses, codeword index, gain) for the frame kernel, whose warps expand them.
+struct LaneCoder {  // the Coder of celt2_frame on top of LaneDec
+    LaneDec d;
+    const uint32_t (*lfl)[LAP_N + 1];
+    const uint32_t (*lfs)[LAP_N + 1];
+    __device__ __forceinline__ uint32_t tell() const { return d.tell(); }
+    __device__ __forceinline__ uint32_t tell_frac() const { return d.tell_frac(); }
+    __device__ __forceinline__ uint32_t transient_permille() const { return 0u; }
+    __device__ __forceinline__ uint32_t bit_logp(uint32_t logp, uint32_t) { return d.bit_logp(logp); }
+    __device__ __forceinline__ uint32_t icdf(const uint8_t *tab, uint32_t ftb, uint32_t) { return d.icdf(tab, ftb); }
+    __device__ __forceinline__ uint32_t uint_(uint32_t ft) { return d.uint_any(ft); }
+    __device__ __forceinline__ uint32_t pulses_index(uint32_t ft) { return d.uint_any(ft); }
+    __device__ __forceinline__ uint32_t bits(uint32_t n) { return d.bits(n); }
+    __device__ __forceinline__ int32_t laplace(int band) { return d.laplace(lfl[band], lfs[band], 6000u + 400u * (uint32_t)band); }
+    // the split angle, triangular pdf over 0..qn (RFC 6716 4.3.4.2; decode + update, decoder.rs:143-181)
+    __device__ __forceinline__ uint32_t theta_tri(uint32_t qn)
+    {
+        const uint32_t h = qn >> 1, ft = (h + 1u) * (h + 1u);
+        const uint32_t fm = d.decode(ft);
+        uint32_t itheta, fl, fs;
+        if (fm < ((h * (h + 1u)) >> 1)) {
+            itheta = (c2_isqrt32(8u * fm + 1u) - 1u) >> 1;
+            fs = itheta + 1u;
+            fl = (itheta * (itheta + 1u)) >> 1;
+        } else {
+            itheta = (2u * (qn + 1u) - c2_isqrt32(8u * (ft - fm - 1u) + 1u)) >> 1;
+            fs = qn + 1u - itheta;
+            fl = ft - (((qn + 1u - itheta) * (qn + 2u - itheta)) >> 1);
+        }
+        d.update(fl, fl + fs, ft);
+        return itheta;
+    }
+};
+struct LanePartSink {
+    Celt2Part *parts;
+    uint32_t n, np, nsign;
+    __device__ __forceinline__ void put_part(int base, int nn, int k, uint32_t index, float gain)
+    {
+        if (n < (uint32_t)CELT2_MAX_PARTS) parts[n] = Celt2Part{(uint16_t)base, (uint8_t)nn, (uint8_t)k, index, gain};
+        n += 1u;
+        np += (uint32_t)k;
+    }
+    __device__ __forceinline__ void put_sign(int base, uint32_t sign)  // a one-bin band: its pulse is counted by celt2_frame itself
+    {
+        put_part(base, 1, 1, sign, 0.03125f);
+        np -= 1u;
+        nsign += 1u;
+    }
+    __device__ __forceinline__ uint32_t pulses() const { return np; }
+};
+
+__device__ __forceinline__ Celt2Tabs device_celt2_tabs()
+{
+    return Celt2Tabs{g_tab.e_bands, g_tab.log_n, g_tab.alloc_vectors, g_tab.cache_bits, g_tab.cache_caps, g_tab.log2_frac, g_tab.cache_index,
+                     g_tab.pvq_u_data, g_tab.pvq_u_row};
+}
+
+__global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_celt2_rangedec(SymbolArgs A)
+{
+    __shared__ uint32_t s_lfl[21][LAP_N + 1], s_lfs[21][LAP_N + 1];
+    const uint32_t lane = threadIdx.x;
+    const int lm = A.lm, C = A.channels;
+    if (lane < 21u) {
+        const uint32_t decay = 6000u + 400u * lane;
+        const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;
+        laplace_table(fs0, decay, s_lfl[lane], s_lfs[lane]);
+    }
+    __syncthreads();
+    const uint32_t item = blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u) + lane;
+    if (item >= A.n_items) return;
+    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    uint32_t len = A.lens[item];
+    const uint8_t *src = A.arena + A.offsets[item];
+    int32_t status = len == 0u ? ITEM_LOST : ITEM_OK;
+    if (A.has_toc && len > 0u) {
+        const uint32_t toc = __ldg(src);
+        if ((toc & 0x80u) == 0u) status = OPN_ERR_UNIMPLEMENTED;
+        else if ((toc & 0x3u) != 0u) status = OPN_ERR_UNIMPLEMENTED;
+        else if ((int)((toc >> 3) & 0x3u) != lm) status = OPN_ERR_FRAME_SIZE_TOO_SMALL;
+        else if (((toc & 0x4u) ? 2 : 1) != C) status = OPN_ERR_UNIMPLEMENTED;
+        src += 1;
+        len -= 1u;
+    }
+    if (status == ITEM_OK && len <= 1u) status = ITEM_LOST;
+    Celt2Side *sd = A.side2 ? A.side2 + stream : nullptr;
+    if (sd) {
+        uint32_t *sw = reinterpret_cast<uint32_t *>(sd);
+        for (uint32_t i = 0; i < sizeof(Celt2Side) / 4u; i++) sw[i] = 0u;
+    }
+    if (status != ITEM_OK) {
+        A.status[stream] = status;
+        if (status == ITEM_LOST) A.hdr[stream] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    LaneCoder ec;
+    ec.lfl = s_lfl;
+    ec.lfs = s_lfs;
+    ec.d.init(src, len);
+    LanePartSink sink{A.parts + (size_t)stream * CELT2_MAX_PARTS, 0u, 0u, 0u};
+    uint32_t flags = 0u, n_pulses = 0u;
+    celt2_frame(ec, device_celt2_tabs(), len, lm, C, sd, sink, flags, n_pulses);
+    const uint32_t tf = ec.d.tell_frac();
+    if (sd) {
+        sd->n_parts = sink.n - sink.nsign;  // PVQ leaves (the list also holds the one-bin bands)
+        sd->n_pulses = n_pulses;
+        sd->final_rng = ec.d.rng;
+        sd->tell_frac = tf;
+    }
+    if (sink.n > (uint32_t)CELT2_MAX_PARTS) status = OPN_ERR_INTERNAL;  // more leaves than the list holds: reject the packet, state untouched
+    A.status[stream] = status;
+    A.hdr[stream] = make_uint4(flags, ec.d.rng, tf, sink.n);
+}
+
+// Expansion of a SYNTH-CELT/2 part list by one warp: the leaves are dealt to the lanes round-robin; a lane walks its leaf
+// with cwrsi_events (any (n, K): the walk itself falls back where its 32-bit sums could wrap), writes the pulses as
+// floats and scales the leaf by gain / sqrt(yy) once the norm is known.  `rows` must be zero on entry.
+template <int C>
+__device__ __forceinline__ void w_expand2(const ExpandTables &T, int lm, uint32_t lane, const Celt2Part *__restrict__ parts, uint32_t n_parts,
+                                          float *rows, int chs, int32_t *__restrict__ y_out)
+{
+    const int nf = 120 << lm;
+    for (uint32_t p = lane; p < n_parts; p += 32u) {
+        const Celt2Part P = parts[p];
+        const uint32_t ch = P.base >= (uint32_t)nf ? 1u : 0u;
+        float *dst = rows + P.base + ch * (uint32_t)(chs - nf);
+        int32_t *yo = y_out ? y_out + P.base : nullptr;
+        if (P.n == 1u) {  // sign-only band
+            dst[0] = P.index ? -P.gain : P.gain;
+            if (yo) yo[0] = P.index ? -1 : 1;
+            continue;
+        }
+        const int32_t yy = cwrsi_events(T.U, T.CW, T.row, T.nmax, (uint32_t)P.n, (uint32_t)P.k, P.index, [&](uint32_t at, int32_t val) {
+            dst[at] = (float)val;
+            if (yo) yo[at] = val;
+        });
+        const float g = P.gain / sqrtf((float)yy);
+        for (uint32_t j = 0; j < P.n; j++) {
+            const float v = dst[j];
+            if (v != 0.0f) dst[j] = v * g;
+        }
+    }
+}
+
+// Stand-alone expansion of part lists (operator entry opn_op_celt2_symbols): coefficient rows and pulses to global memory.
+__global__ void __launch_bounds__(128) k_celt2_expand(SymbolArgs A)
+{
+    extern __shared__ __align__(16) float s_rows_all[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const int lm = A.lm, C = A.channels, nf = 120 << lm;
+    float *rows = s_rows_all + (size_t)warp * 2 * 960;
+    const uint32_t item = blockIdx.x * 4u + warp;
+    if (item >= A.n_items) return;
+    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    const int32_t status = A.status[stream];
+    if (status < 0) return;
+    const uint4 hdr = A.hdr[stream];
+    const int nvec = C * nf / 4;
+    for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4 *>(rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t *yo = A.y_out ? A.y_out + (size_t)stream * C * nf : nullptr;
+    if (yo)
+        for (int i = lane; i < nvec; i += 32) reinterpret_cast<int4 *>(yo)[i] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    if (status == ITEM_OK && !(hdr.x & 1u)) {
+        const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
+        if (C == 2) w_expand2<2>(T, lm, lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, hdr.w, rows, nf, yo);
+        else w_expand2<1>(T, lm, lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, hdr.w, rows, nf, yo);
+    }
+    __syncwarp();
+    if (A.coef) {
+        float4 *coef4 = reinterpret_cast<float4 *>(A.coef + (size_t)stream * C * nf);
+        for (int i = lane; i < nvec; i += 32) coef4[i] = reinterpret_cast<const float4 *>(rows)[i];
+    }
 }
 
 }  // namespace opn

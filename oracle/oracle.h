@@ -154,11 +154,38 @@ typedef struct {
 } orc_synth_state;
 
 void orc_synth_state_init(orc_synth_state *s);
+/* coefficients (channel-major) -> interleaved PCM; the back half of every SYNTH-CELT frame decode */
+int orc_synth_finish_frame(orc_synth_state *st, const float *coef, int lm, int channels, int apply_comb, int lost, int postfilter,
+                           int period, int gain_idx, int tapset, int transient, float *pcm_out);
 /* payload = frame bytes after the TOC.  y_out: >= channels*100<<LM ints; coef_out: same, floats
  * (channel-major, frequency order); pcm_out: interleaved frame_size*channels floats. */
 int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm,
                            int channels, int apply_comb, orc_synth_side *side, int32_t *y_out,
                            float *coef_out, float *pcm_out);
+/* ---- SYNTH-CELT/2 (oracle/celt2.c): allocation-driven CELT frame decode, PARITY UNPINNED (no reference code exists) ---- */
+#define ORC_CELT2_MAX_PARTS 192
+typedef struct {
+    int32_t silence, postfilter, octave, period, gain_idx, tapset, transient, intra;
+    int32_t spread, alloc_trim, coded_bands, intensity, dual_stereo, anti_collapse, balance;
+    int32_t offsets[21], pulses[21], ebits[21], fine_priority[21];
+    int32_t coarse[2][21], fine[2][21], fine_final[2][21];
+    uint32_t n_parts, n_pulses, n_splits, theta_sum;
+    uint32_t final_rng, tell_frac;
+} orc_celt2_side;
+typedef struct { /* one PVQ leaf: coefficients [base, base+n) of the channel-major frame = cwrsi(n, k, index) * gain / sqrt(yy) */
+    uint16_t base;
+    uint8_t n, k;
+    uint32_t index;
+    float gain;
+} orc_celt2_part;
+/* payload = frame bytes after the TOC.  y_out / coef_out: [channels][120<<lm] (channel-major); parts may be NULL. */
+int orc_celt2_decode_symbols(const uint8_t *payload, uint32_t len, int lm, int channels, orc_celt2_side *side, orc_celt2_part *parts,
+                             int32_t *y_out, float *coef_out);
+int orc_celt2_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm, int channels, int apply_comb,
+                           orc_celt2_side *side, float *pcm_out);
+int orc_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes, uint32_t transient_permille,
+                     uint8_t *out, orc_celt2_side *truth);
+
 /* SYNTH-CELT/1 packet generator on the oracle's own range encoder (same seeded draws as opn_synth_packet). */
 int orc_synth_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes,
                      uint32_t transient_permille, uint8_t *out);

@@ -81,6 +81,47 @@ static void decode_symbols(orc_dec *d, int lm, int channels, orc_synth_side *sid
     side->tell_frac = orc_dec_tell_frac(d);
 }
 
+/* Coefficients -> PCM, shared by SYNTH-CELT/1 and /2: Mdct::backward per channel onto the 60-sample carry (one long block
+ * or 2^LM interleaved short blocks), comb_filter_inplace from the previous frame's post-filter parameters to this
+ * frame's over the first 120 samples, interleaved output.  A lost frame keeps the previous parameters. */
+int orc_synth_finish_frame(orc_synth_state *st, const float *coef, int lm, int channels, int apply_comb, int lost, int postfilter,
+                           int period, int gain_idx, int tapset, int transient, float *pcm_out)
+{
+    int nf = 120 << lm;
+    int t1 = st->pf_period, tap1 = st->pf_tapset;
+    float g1 = st->pf_gain;
+    if (!lost) {
+        t1 = postfilter ? period : 0;
+        g1 = postfilter ? 0.09375f * (float)(gain_idx + 1) : 0.0f;
+        tap1 = postfilter ? tapset : 0;
+    }
+
+    int blocks = transient ? (1 << lm) : 1;
+    int shift = transient ? 3 : 3 - lm;
+    if (st->pos + (uint32_t)nf + 60 > ORC_SYNTH_BUF) { /* buffer full: history + tail to the front */
+        for (int c = 0; c < channels; c++)
+            memmove(st->buf[c], st->buf[c] + st->pos - HIST, sizeof(float) * (HIST + 60));
+        st->pos = HIST;
+    }
+    for (int c = 0; c < channels; c++) {
+        float *work = st->buf[c] + st->pos - HIST; /* work[HIST .. HIST+60) already holds the previous tail */
+        memset(work + HIST + 60, 0, sizeof(float) * (size_t)nf);
+        for (int b = 0; b < blocks; b++)
+            orc_mdct_backward(coef + c * nf + b, work + HIST + 120 * b * (blocks > 1), ORC_WINDOW,
+                              ORC_OVERLAP, shift, blocks);
+        if (apply_comb)
+            orc_comb_filter_inplace(work, HIST, (size_t)st->pf_period, (size_t)t1, (size_t)nf,
+                                    st->pf_gain, g1, (size_t)st->pf_tapset, (size_t)tap1, ORC_OVERLAP);
+        for (int i = 0; i < nf; i++) pcm_out[i * channels + c] = work[HIST + i];
+    }
+    st->pos += (uint32_t)nf;
+    st->pf_period = t1;
+    st->pf_gain = g1;
+    st->pf_tapset = tap1;
+    return nf;
+}
+
+
 int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm,
                            int channels, int apply_comb, orc_synth_side *side, int32_t *y_out,
                            float *coef_out, float *pcm_out)
@@ -103,37 +144,8 @@ int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t
         decode_symbols(&d, lm, channels, side, y_out, coef);
     }
 
-    int t1 = st->pf_period, tap1 = st->pf_tapset;
-    float g1 = st->pf_gain;
-    if (!lost) {
-        t1 = side->postfilter ? side->period : 0;
-        g1 = side->postfilter ? 0.09375f * (float)(side->gain_idx + 1) : 0.0f;
-        tap1 = side->postfilter ? side->tapset : 0;
-    }
-
-    int blocks = side->transient ? (1 << lm) : 1;
-    int shift = side->transient ? 3 : 3 - lm;
-    if (st->pos + (uint32_t)nf + 60 > ORC_SYNTH_BUF) { /* buffer full: history + tail to the front */
-        for (int c = 0; c < channels; c++)
-            memmove(st->buf[c], st->buf[c] + st->pos - HIST, sizeof(float) * (HIST + 60));
-        st->pos = HIST;
-    }
-    for (int c = 0; c < channels; c++) {
-        float *work = st->buf[c] + st->pos - HIST; /* work[HIST .. HIST+60) already holds the previous tail */
-        memset(work + HIST + 60, 0, sizeof(float) * (size_t)nf);
-        for (int b = 0; b < blocks; b++)
-            orc_mdct_backward(coef + c * nf + b, work + HIST + 120 * b * (blocks > 1), ORC_WINDOW,
-                              ORC_OVERLAP, shift, blocks);
-        if (apply_comb)
-            orc_comb_filter_inplace(work, HIST, (size_t)st->pf_period, (size_t)t1, (size_t)nf,
-                                    st->pf_gain, g1, (size_t)st->pf_tapset, (size_t)tap1, ORC_OVERLAP);
-        for (int i = 0; i < nf; i++) pcm_out[i * channels + c] = work[HIST + i];
-    }
-    st->pos += (uint32_t)nf;
-    st->pf_period = t1;
-    st->pf_gain = g1;
-    st->pf_tapset = tap1;
-    return nf;
+    return orc_synth_finish_frame(st, coef, lm, channels, apply_comb, lost, side->postfilter, side->period, side->gain_idx, side->tapset,
+                                  side->transient, pcm_out);
 }
 
 /* ------------------------------------------------------------------ packet generator

@@ -40,6 +40,7 @@ extern "C" int lanedec_run_script(const uint8_t *buf, uint32_t len, const Op *op
         uint32_t v = 0;
         switch (ops[i].op) {
         case OP_UINT: {
+            if (b == 1u) { v = d.uint_any(a); break; }  // the generic form (SYNTH-CELT/2: alphabets known only at run time)
             if (a <= 256u) { v = d.uint_small(a); break; }
             // the alphabet split and reciprocal of upload_tables (opn_kernels.cu)
             const uint32_t ftm1 = a - 1u;

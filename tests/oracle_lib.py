@@ -37,6 +37,21 @@ class SynthSide(C.Structure):
         ("final_rng", C.c_uint32), ("tell_frac", C.c_uint32), ("n_pulses", C.c_uint32)]
 
 
+class Celt2Side(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra",
+                                          "spread", "alloc_trim", "coded_bands", "intensity", "dual_stereo", "anti_collapse", "balance")] + [
+        (n, C.c_int32 * 21) for n in ("offsets", "pulses", "ebits", "fine_priority")] + [
+        (n, (C.c_int32 * 21) * 2) for n in ("coarse", "fine", "fine_final")] + [
+        (n, C.c_uint32) for n in ("n_parts", "n_pulses", "n_splits", "theta_sum", "final_rng", "tell_frac")]
+
+
+class Celt2Part(C.Structure):
+    _fields_ = [("base", C.c_uint16), ("n", C.c_uint8), ("k", C.c_uint8), ("index", C.c_uint32), ("gain", C.c_float)]
+
+
+CELT2_MAX_PARTS = 192
+
+
 class SynthState(C.Structure):
     _fields_ = [("buf", (C.c_float * (1024 + 8 * 960 + 60)) * 2), ("pos", C.c_uint32),
                 ("pf_period", C.c_int32), ("pf_tapset", C.c_int32), ("pf_gain", C.c_float)]
@@ -123,6 +138,9 @@ def lib():
     sig("orc_synth_state_init", None, C.POINTER(SynthState))
     sig("orc_synth_decode_frame", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int,
         C.POINTER(SynthSide), vp, vp, vp)
+    sig("orc_celt2_decode_symbols", C.c_int, vp, u32, C.c_int, C.c_int, C.POINTER(Celt2Side), vp, vp, vp)
+    sig("orc_celt2_decode_frame", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int, C.POINTER(Celt2Side), vp)
+    sig("orc_celt2_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp, C.POINTER(Celt2Side))
     sig("orc_synth_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp)
     sig("orc_synth_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("orc_synth_bench", C.c_double, vp, u32, u32, u32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32))
@@ -188,6 +206,47 @@ def synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt
     rc = lib().orc_synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt_bytes, transient_permille, n_threads, ptr(out))
     assert rc == 0, rc
     return out
+
+
+def celt2_packet(stream_id, frame_idx, lm, channels, pkt_bytes, transient_permille=0):
+    """-> (packet uint8[pkt_bytes] incl. TOC, Celt2Side truth) from the oracle's SYNTH-CELT/2 generator"""
+    out = np.zeros(pkt_bytes, np.uint8)
+    truth = Celt2Side()
+    rc = lib().orc_celt2_packet(stream_id, frame_idx, lm, channels, pkt_bytes, transient_permille, ptr(out), C.byref(truth))
+    assert rc == pkt_bytes, rc
+    return out, truth
+
+
+def celt2_decode_symbols(payload, lm, channels):
+    """-> (Celt2Side, parts array, y int32 [C*nf], coef float32 [C*nf])"""
+    payload = np.ascontiguousarray(payload, np.uint8)
+    nf = 120 << lm
+    side = Celt2Side()
+    parts = (Celt2Part * CELT2_MAX_PARTS)()
+    y = np.zeros(channels * nf, np.int32)
+    coef = np.zeros(channels * nf, np.float32)
+    rc = lib().orc_celt2_decode_symbols(ptr(payload), len(payload), lm, channels, C.byref(side), parts, ptr(y), ptr(coef))
+    assert rc == 0, rc
+    return side, parts, y, coef
+
+
+class Celt2Stream:
+    """One stream's oracle-side SYNTH-CELT/2 decoder state."""
+
+    def __init__(self, lm, channels, apply_comb=True):
+        self.lm, self.channels, self.apply_comb = lm, channels, apply_comb
+        self.state = SynthState()
+        lib().orc_synth_state_init(C.byref(self.state))
+
+    def decode(self, payload):
+        """-> (Celt2Side, pcm) or (error code, None) for a rejected frame"""
+        nf = 120 << self.lm
+        payload = np.frombuffer(bytes(payload), dtype=np.uint8).copy()
+        side = Celt2Side()
+        pcm = np.zeros(self.channels * nf, np.float32)
+        r = lib().orc_celt2_decode_frame(C.byref(self.state), ptr(payload) if len(payload) else None, len(payload), self.lm, self.channels,
+                                        int(self.apply_comb), C.byref(side), ptr(pcm))
+        return (side, pcm) if r == nf else (r, None)
 
 
 class SynthStream:

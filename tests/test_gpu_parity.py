@@ -395,6 +395,78 @@ def test_synth_symbols_garbage_and_truncated_payloads(lm, channels):
         assert np.array_equal(coef[s].reshape(-1).view(np.uint32), wc.view(np.uint32)), s
 
 
+# ------------------------------------------------------------------ SYNTH-CELT/2: allocation-driven frames (f1, first slice)
+CELT2 = dict(bitstream=opn.BITSTREAM_SYNTH_CELT_2)
+
+
+def _celt2_check(side, y, coef, payloads, lm, channels):
+    for s, payload in enumerate(payloads):
+        w, _, wy, wc = O.celt2_decode_symbols(payload, lm, channels)
+        for f in opn.CELT2_SIDE_DTYPE.names:
+            v = getattr(w, f)
+            v = np.ctypeslib.as_array(v) if hasattr(v, "__len__") else v
+            assert np.array_equal(side[s][f], v), (s, len(payload), f, side[s][f], v)
+        assert np.array_equal(y[s].reshape(-1), wy), (s, len(payload))
+        assert np.array_equal(coef[s].reshape(-1).view(np.uint32), wc.view(np.uint32)), s
+
+
+@pytest.mark.parametrize("lm,channels,pkt_bytes", [(3, 2, 160), (3, 1, 100), (2, 2, 130), (2, 1, 64), (1, 2, 100), (1, 1, 60), (0, 2, 80),
+                                                   (0, 1, 48), (3, 2, 48), (3, 2, 300)])
+def test_celt2_symbols(lm, channels, pkt_bytes):
+    """The device frame decode of SYNTH-CELT/2 (k_celt2_rangedec: band boosts, trim, compute_allocation on the mode's tables,
+    fine bits, theta splits with bitexact_cos / bitexact_log2tan, leaf sizes from the pulse cache; then the part-list
+    expansion) against the oracle: the whole side record -- allocation vector, fine bits and priorities, coded bands,
+    intensity / dual-stereo, balance, counts of leaves, pulses, splits, theta checksum, final range, tell_frac -- the
+    pulses and the coefficients, bit for bit.  Shapes (n, K) are computed per frame on the device."""
+    n = 64
+    pk = opn.celt2_fill(500, n, 2, 1, lm, channels, pkt_bytes, transient_permille=250)[0]
+    payload = np.ascontiguousarray(pk[:, 1:])
+    side, y, coef = opn.op_celt2_symbols(payload.reshape(-1), np.arange(n, dtype=np.uint32) * (pkt_bytes - 1),
+                                         np.full(n, pkt_bytes - 1, np.uint32), lm, channels)
+    _celt2_check(side, y, coef, [payload[s] for s in range(n)], lm, channels)
+    assert side["n_parts"].min() > 0 and side["n_splits"].sum() >= 0
+
+
+@pytest.mark.parametrize("lm,channels", [(3, 2), (2, 1), (0, 2)])
+def test_celt2_symbols_garbage_and_truncated_payloads(lm, channels):
+    """Random bytes and truncated payloads of 2..200 bytes: the allocation runs on whatever tell_frac the garbage produces
+    (budgets that go negative, bands that get nothing, uint saturation) and must still match the oracle exactly."""
+    rnd = np.random.default_rng(7 + lm)
+    lens = np.concatenate([np.arange(2, 201, 5), rnd.integers(2, 201, 40)]).astype(np.uint32)
+    n = len(lens)
+    offsets = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32)
+    arena = rnd.integers(0, 256, int(lens.sum()) + 8).astype(np.uint8)
+    real = opn.celt2_fill(9, n, 0, 1, lm, channels, 201, transient_permille=300)[0][:, 1:]
+    for s in range(0, n, 2):
+        arena[offsets[s]:offsets[s] + lens[s]] = real[s, :lens[s]]
+    side, y, coef = opn.op_celt2_symbols(arena, offsets, lens, lm, channels)
+    _celt2_check(side, y, coef, [arena[offsets[s]:offsets[s] + lens[s]] for s in range(n)], lm, channels)
+
+
+@pytest.mark.parametrize("lm,channels,pkt_bytes", [(3, 2, 160), (2, 1, 80), (0, 2, 80)])
+def test_celt2_batch_decode_chain(lm, channels, pkt_bytes):
+    """SYNTH-CELT/2 through the batch entry point: the frame kernel expands each stream's part list, then IMDCT, TDAC and the
+    comb post-filter as for SYNTH-CELT/1; PCM and final_range against the oracle's chained decode, with a lost packet."""
+    ns, nfr, nf = 40, 8, 120 << lm
+    packets = opn.celt2_fill(70, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=150)
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **CELT2)
+    oracle = [O.Celt2Stream(lm, channels) for _ in range(ns)]
+    offsets = np.arange(ns, dtype=np.uint32) * pkt_bytes
+    for f in range(nfr):
+        lens = np.full(ns, pkt_bytes, np.uint32)
+        if f == 3:
+            lens[5] = 0
+        pcm = np.zeros((ns, nf * channels), np.float32)
+        res = dec.decode_float(packets[f].reshape(-1), offsets, lens, pcm, nf)
+        assert np.all(res == nf)
+        rng = dec.final_ranges()
+        for s in range(ns):
+            side, want = oracle[s].decode(packets[f, s, 1:] if lens[s] else b"")
+            assert np.array_equal(pcm[s], want), (f, s)
+            assert rng[s] == (side.final_rng if lens[s] else 0)
+            assert_pcm(want, pcm[s], (f, s))
+
+
 def test_bitexact_trig_checksums():
     """bitexact_cos / bitexact_log2tan on the device against the reference's own checksums
     (src/math.rs:237-298) and, value by value, against the oracle."""

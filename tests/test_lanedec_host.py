@@ -37,7 +37,7 @@ def _script(rnd, n_ops):
         kind = int(rnd.integers(0, 5))
         if kind == 0:
             ft = int(rnd.choice([2, 3, 6, 255, 256, 257, 4066763520, 0xFFFFFFFF, int(rnd.integers(2, 2 ** int(rnd.integers(2, 33)) - 1))]))
-            ops.append((OP_UINT, ft, 0)); vals.append(int(rnd.integers(0, ft)))
+            ops.append((OP_UINT, ft, int(rnd.integers(0, 2)))); vals.append(int(rnd.integers(0, ft)))  # b = 1: LaneDec::uint_any
         elif kind == 1:
             nb = int(rnd.integers(1, 26))
             ops.append((OP_BITS, nb, 0)); vals.append(int(rnd.integers(0, 1 << nb)))

@@ -94,6 +94,14 @@ def test_pvq_u_identical():
     assert data == data_ref and len(data) == 1272
 
 
+def test_allocation_tables_identical():
+    g = _gen()
+    for name, mine in (("ALLOC_VECTORS", g.ALLOC_VECTORS), ("CACHE_INDEX", g.CACHE_INDEX), ("CACHE_BITS", g.CACHE_BITS), ("CACHE_CAPS", g.CACHE_CAPS)):
+        ref = [int(x) for x in re.findall(r"-?\d+", _block("celt/mode.rs", rf"const {name}:"))]  # _block starts after the declaration line
+        assert ref == mine, name
+    assert len(g.ALLOC_VECTORS) == 231 and len(g.CACHE_INDEX) == 105 and len(g.CACHE_BITS) == 392 and len(g.CACHE_CAPS) == 168
+
+
 def test_mode_constants_identical():
     g = _gen()
     eb = [int(s) for s in re.findall(r"\d+", _block("celt/mode.rs", r"const E_BANDS"))]
