@@ -267,35 +267,51 @@ OPN_HD int c2_compute_allocation(Coder &ec, const Celt2Tabs &T, int end, const i
 }
 
 // ---- one band of one channel: split in halves down to PVQ leaves (libopus bands.c quant_partition, mono) -------
+OPN_HD int c2_exp2_table8(int i)  // 2^(i/8) in Q14
+{
+    switch (i & 7) {
+    case 0: return 16384;
+    case 1: return 17866;
+    case 2: return 19483;
+    case 3: return 21247;
+    case 4: return 23170;
+    case 5: return 25267;
+    case 6: return 27554;
+    default: return 30048;
+    }
+}
 OPN_HD int c2_compute_qn(int N, int b, int offset, int pulse_cap)
 {
-    const int16_t exp2_table8[8] = {16384, 17866, 19483, 21247, 23170, 25267, 27554, 30048};
     const int N2 = 2 * N - 1;
     int qb = (b + N2 * offset) / N2;
     qb = c2_min(b - pulse_cap - (4 << C2_BITRES), qb);
     qb = c2_min(8 << C2_BITRES, qb);
     if (qb < (1 << C2_BITRES >> 1)) return 1;
-    const int qn = exp2_table8[qb & 7] >> (14 - (qb >> C2_BITRES));
+    const int qn = c2_exp2_table8(qb) >> (14 - (qb >> C2_BITRES));
     return (qn + 1) >> 1 << 1;
 }
 
-// Sink: put_part(base, n, k, index, gain) for every leaf that holds pulses.
+// The recursion of quant_partition is at most LM+1 splits deep; it runs on an explicit stack of frames so that the same code
+// serves the device lane and the host.  phase 0: entering, 1: first half done, 2: both done.
+struct C2Frame {
+    int base, N, b, B, LM, phase, mbits, sbits, itheta;
+    int32_t reb;
+    float gain, gmid, gside;
+};
+constexpr int C2_MAX_DEPTH = 6;
+
+// Sink: put_part(base, n, k, index, gain) for every leaf that holds pulses.  `st`: C2_MAX_DEPTH frames of scratch owned by the
+// caller and declared next to its allocation arrays.  (Declared in here, nvcc 12.9 gave the array the local-memory slot of the
+// caller's still-live fine_priority[] once everything was inlined into the kernel: the final fine-energy pass then read frame
+// images instead of priorities.  Found by the GPU parity test; the host build of the same source was right.)
 template <class Coder, class Sink>
-OPN_HD void c2_quant_band(Coder &ec, const Celt2Tabs &T, Sink &out, Celt2Side *sd, int band, int base0, int N0, int b0, int B0frame, int LM0,
+OPN_HD void c2_quant_band(Coder &ec, const Celt2Tabs &T, Sink &out, C2Frame *st, int band, int base0, int N0, int b0, int B0frame, int LM0,
                           int32_t &remaining_bits, uint32_t &n_splits, uint32_t &theta_sum)
 {
-    // The recursion of quant_partition is at most LM+1 splits deep; it runs on an explicit stack of frames so that the
-    // same code serves the device lane and the host.  phase 0: entering, 1: first half done, 2: both done.
-    struct Frame {
-        int base, N, b, B, LM, phase, mbits, sbits, itheta;
-        int32_t reb;
-        float gain, gmid, gside;
-    };
-    Frame st[6];
+    typedef C2Frame Frame;
     int sp = 0;
     st[0] = Frame{base0, N0, b0, B0frame, LM0, 0, 0, 0, 0, 0, 0.03125f, 0.f, 0.f};
     sp = 1;
-    (void)sd;
     while (sp > 0) {
         Frame &f = st[sp - 1];
         if (f.phase == 0) {
@@ -486,6 +502,7 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
                 const uint32_t v = ec.bits((uint32_t)ebits[i]);
                 if (sd) sd->fine[c][i] = (int32_t)v;
             }
+    C2Frame frames[C2_MAX_DEPTH];
     {
         const int32_t band_total = (total_bits << C2_BITRES) - anti_collapse_rsv;
         const int Bframe = transient ? M : 1;
@@ -509,7 +526,7 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
                     out.put_sign(c * nf + base, sign);
                     n_pulses += 1;
                 } else {
-                    c2_quant_band(ec, T, out, sd, i, c * nf + base, N, b / C, Bframe, LM, remaining_bits, n_splits, theta_sum);
+                    c2_quant_band(ec, T, out, frames, i, c * nf + base, N, b / C, Bframe, LM, remaining_bits, n_splits, theta_sum);
                 }
             }
             balance += pulses[i] + tell;
@@ -534,6 +551,10 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
     if (sd) {
         sd->n_splits = n_splits;
         sd->theta_sum = theta_sum;
+#ifdef OPN_C2_DEBUG
+        for (int i = 0; i < C2_NBANDS; i++) sd->offsets[i] = ebits[i] | fine_priority[i] << 8 | pulses[i] << 16;
+        sd->balance = (int32_t)total_bits - (int32_t)ec.tell();
+#endif
     }
 }
 

@@ -144,6 +144,7 @@ struct opn_batch {
     cudaStream_t stream_fr[NGROUPS] = {};
     cudaEvent_t ev_fr[NSETS][NGROUPS] = {};  // frame kernel of set p, group g finished
     cudaEvent_t ev_sw = nullptr;             // mode switch: everything enqueued on `stream` so far
+    cudaEvent_t ev_tm[NGROUPS] = {};         // timed pass: group g's launch finished
     bool fr_pending[NGROUPS] = {};           // group g >= 1 has work that `stream` has not been ordered after yet
     int fr_last_set[NGROUPS] = {};
     cudaEvent_t ev_k1[NSETS] = {};        // frame kernel(s) of set p finished on `stream` (group 0 / ungrouped): the set is free again
@@ -252,7 +253,29 @@ cudaError_t do_rangedec(opn_batch *b, const void *a)
     return b->cfg.bitstream == OPN_BITSTREAM_SYNTH_CELT_2 ? launch_celt2_rangedec(s, b->stream) : launch_synth_rangedec(s, b->stream);
 }
 cudaError_t do_expand(opn_batch *b, const void *a) { return launch_synth_expand(*static_cast<const SymbolArgs *>(a), b->stream); }
-cudaError_t do_frame(opn_batch *b, const void *a) { return launch_frame(*static_cast<const FrameArgs *>(a), b->stream); }
+bool frame_grouped(const opn_batch *b, const FrameArgs &m)
+{
+    return !b->unfused && opn_batch::NGROUPS > 1 && m.n_items >= opn_batch::GROUP_MIN_ITEMS && !m.stream_idx;
+}
+// Timed pass: the frame kernel in its product configuration -- a large bucket as NGROUPS concurrent launches -- between
+// the two events timed_launch records on `stream` (the second one is ordered after every group).
+cudaError_t do_frame(opn_batch *b, const void *a)
+{
+    FrameArgs m = *static_cast<const FrameArgs *>(a);
+    if (!frame_grouped(b, m)) return launch_frame(m, b->stream);
+    cudaError_t e = cudaEventRecord(b->ev_sw, b->stream);
+    const uint32_t n_items = m.n_items;
+    for (int g = 0; g < opn_batch::NGROUPS && e == cudaSuccess; g++) {
+        cudaStream_t st = g == 0 ? b->stream : b->stream_fr[g];
+        if (g > 0) e = cudaStreamWaitEvent(st, b->ev_sw, 0);
+        m.item0 = (uint32_t)((uint64_t)n_items * g / opn_batch::NGROUPS);
+        m.item_end = (uint32_t)((uint64_t)n_items * (g + 1) / opn_batch::NGROUPS);
+        if (e == cudaSuccess) e = launch_frame(m, st);
+        if (g > 0 && e == cudaSuccess) e = cudaEventRecord(b->ev_tm[g], st);
+        if (g > 0 && e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_tm[g], 0);
+    }
+    return e;
+}
 
 // Orders `stream` after everything the other frame groups have been given so far.
 int join_groups(opn_batch *b)
@@ -373,12 +396,13 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.final_range = b->d_final;
     m.softclip_reset = softclip_reset ? b->d_softclip : nullptr;
     m.hist_samples = b->timing ? b->d_hist_samples : nullptr;
-    const bool grouped = !b->timing && !b->unfused && opn_batch::NGROUPS > 1 && n_items >= opn_batch::GROUP_MIN_ITEMS && !d_stream_idx;
+    const bool grouped = !b->timing && frame_grouped(b, m);
     if (b->timing) {
         rc = join_groups(b);
         if (rc) return rc;
         rc = timed_launch(b, 1, do_frame, &m);
         if (rc) return rc;
+        if (frame_grouped(b, m)) b->launches[1] += opn_batch::NGROUPS - 1;
     } else if (!grouped) {
         rc = join_groups(b);  // streams of the other groups' ranges may be in this bucket
         if (rc) return rc;
@@ -530,6 +554,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
     for (int g = 1; g < opn_batch::NGROUPS && e == cudaSuccess; g++) e = cudaStreamCreateWithFlags(&b->stream_fr[g], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_sw, cudaEventDisableTiming);
+    for (int g = 1; g < opn_batch::NGROUPS && e == cudaSuccess; g++) e = cudaEventCreateWithFlags(&b->ev_tm[g], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_dn, cudaStreamNonBlocking);
@@ -573,6 +598,8 @@ void opn_batch_destroy(opn_batch *b)
             cudaStreamDestroy(b->stream_fr[g]);
         }
     if (b->ev_sw) cudaEventDestroy(b->ev_sw);
+    for (int g = 1; g < opn_batch::NGROUPS; g++)
+        if (b->ev_tm[g]) cudaEventDestroy(b->ev_tm[g]);
     for (int q = 0; q < opn_batch::NSETS; q++) {
         for (int g = 1; g < opn_batch::NGROUPS; g++)
             if (b->ev_fr[q][g]) cudaEventDestroy(b->ev_fr[q][g]);

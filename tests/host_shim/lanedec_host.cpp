@@ -24,6 +24,8 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
 }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 #include "../../opus-native_b200/csrc/rangedec.cuh"
+#include "../../opus-native_b200/csrc/celt2_lane.cuh"
+#include "../../opus-native_b200/csrc/opn_tables.h"
 
 using namespace opn;
 struct Op { uint32_t op, a, b; };
@@ -69,4 +71,29 @@ extern "C" int lanedec_run_script(const uint8_t *buf, uint32_t len, const Op *op
         out[i].rng = d.rng;
     }
     return 0;
+}
+
+// SYNTH-CELT/2 frame decode through the device's LaneCoder / LanePartSink (celt2_lane.cuh) and celt2_frame (celt2.cuh).
+extern "C" int lanedec_celt2_decode(const uint8_t *payload, uint32_t len, int lm, int channels, Celt2Side *side, Celt2Part *parts)
+{
+    static uint32_t lfl[21][LAP_N + 1], lfs[21][LAP_N + 1];
+    for (uint32_t b = 0; b < 21; b++) {
+        const uint32_t decay = 6000u + 400u * b;
+        laplace_table(((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u, decay, lfl[b], lfs[b]);
+    }
+    const Celt2Tabs T{OPN_E_BANDS, OPN_LOG_N, OPN_ALLOC_VECTORS, OPN_CACHE_BITS, OPN_CACHE_CAPS, OPN_LOG2_FRAC_TABLE, OPN_CACHE_INDEX, OPN_PVQ_U_DATA,
+                      OPN_PVQ_U_ROW};
+    std::memset(side, 0, sizeof(*side));
+    LaneCoder ec;
+    ec.lfl = lfl;
+    ec.lfs = lfs;
+    ec.d.init(payload, len);
+    LanePartSink sink{parts, 0u, 0u, 0u};
+    uint32_t flags = 0, n_pulses = 0;
+    celt2_frame(ec, T, len, lm, channels, side, sink, flags, n_pulses);
+    side->n_parts = sink.n - sink.nsign;
+    side->n_pulses = n_pulses;
+    side->final_rng = ec.d.rng;
+    side->tell_frac = ec.d.tell_frac();
+    return (int)sink.n;
 }

@@ -22,12 +22,14 @@ OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE = 0, 1, 2, 3, 4
 def shim():
     so = os.path.join(HERE, "host_shim", "liblanedec_host.so")
     src = os.path.join(HERE, "host_shim", "lanedec_host.cpp")
-    hdr = os.path.join(ROOT, "opus-native_b200", "csrc", "rangedec.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "opus-native_b200", "csrc", h) for h in ("rangedec.cuh", "celt2.cuh", "celt2_lane.cuh", "mathops.cuh", "opn_tables.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
     L = C.CDLL(so)
     L.lanedec_run_script.restype = C.c_int
     L.lanedec_run_script.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.lanedec_celt2_decode.restype = C.c_int
+    L.lanedec_celt2_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -111,3 +113,28 @@ def test_lanedec_synth_celt_1_symbol_sequence(shim):
             ops += [(OP_LAPLACE, O.lib().orc_laplace_start_freq(decay), decay)] * channels
         ops += [(OP_BITS, 2, 0)] * (21 * channels)
         _run(shim, payload, np.array(ops, O.OP_DTYPE))
+
+
+@pytest.mark.parametrize("lm,channels,pkt_bytes", [(3, 2, 160), (3, 1, 100), (2, 2, 130), (1, 1, 60), (0, 2, 80)])
+def test_celt2_frame_decode_through_the_lane_coder(shim, lm, channels, pkt_bytes):
+    """SYNTH-CELT/2: the device's decode-side coder (LaneCoder on LaneDec, celt2_lane.cuh) running celt2_frame (celt2.cuh),
+    compiled for the host, against the oracle's independent restatement: the whole side record, on generated packets and
+    on random bytes."""
+    import opus_native_b200 as opn
+    rnd = np.random.default_rng(lm * 10 + channels)
+    for s in range(24):
+        if s % 3 == 2:
+            payload = rnd.integers(0, 256, int(rnd.integers(2, 200))).astype(np.uint8)
+        else:
+            payload = O.celt2_packet(s, 1, lm, channels, pkt_bytes, 300)[0][1:]
+        buf = np.zeros(len(payload) + 12, np.uint8)
+        off = (-buf.ctypes.data) % 4 + 4 + (s & 3)
+        buf[off:off + len(payload)] = payload
+        side = np.zeros(1, opn.CELT2_SIDE_DTYPE)
+        parts = np.zeros(192 * 12, np.uint8)
+        shim.lanedec_celt2_decode(buf.ctypes.data + off, len(payload), lm, channels, side.ctypes.data, parts.ctypes.data)
+        w = O.celt2_decode_symbols(payload, lm, channels)[0]
+        for f in opn.CELT2_SIDE_DTYPE.names:
+            v = getattr(w, f)
+            v = np.ctypeslib.as_array(v) if hasattr(v, "__len__") else v
+            assert np.array_equal(side[0][f], v), (s, len(payload), f)
