@@ -159,6 +159,25 @@ template <int U, int M, int S> __device__ __forceinline__ void w_bfly4_const(flo
     r_bfly4(d[U], d[U + M], d[U + 2 * M], d[U + 3 * M], WTw<S * U>::get(), WTw<2 * S * U>::get(), WTw<3 * S * U>::get());
 }
 
+// Half of the radix-4 butterfly U of the last in-group stage (m = 8, twiddle stride 15) when a group is split over two lanes
+// (see w_imdct, pass A for one channel): this lane holds d[U] and d[8 + U].
+template <int U> __device__ __forceinline__ void w_split_bfly4(float2 *d, int h)
+{
+    const float2 wy = h ? WTw<45 * U>::get() : WTw<30 * U>::get();
+    const float2 xm = c_mul(d[U], WTw<15 * U>::get());
+    const float2 X = h ? xm : d[U];
+    const float2 Y = c_mul(d[8 + U], wy);
+    const float2 S = c_add(X, Y), D = c_sub(X, Y);
+    const float2 snd = h ? S : D;
+    float2 rcv;
+    rcv.x = __shfl_xor_sync(0x3FFFFFFFu, snd.x, 1);
+    rcv.y = __shfl_xor_sync(0x3FFFFFFFu, snd.y, 1);
+    const float2 P = h ? rcv : S;
+    const float2 Q = h ? make_float2(D.y, -D.x) : rcv;
+    d[U] = c_add(P, Q);
+    d[8 + U] = c_sub(P, Q);
+}
+
 // In-group position p (0 <= p < GS) -> q, where the group's inputs are i = r + 15 q
 // (digit reversal of kiss_fft.rs:281-336 for the factor lists :251,259,267,275; checked against the
 // generated tables in tests/test_host_logic.py::test_digit_reversal_closed_form).
@@ -229,7 +248,92 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
     static_assert(2 * (NFFT * NBLK + (NFFT * NBLK + PADG - 1) / PADG) <= CHF, "transpose buffer must fit the row");
 
     // ---------------------------------------------------------------- pass A
-    {
+    if constexpr (SHIFT == 0 && NBLK == 1 && C == 1) {
+        // One channel, TWO lanes per group (30 lanes): lane (g, h) owns the octets h and h+2 of group g, 16 elements
+        // instead of 32 -- half the registers.  The stages with m = 1 and m = 4 stay inside an octet.  The last one
+        // (radix 4, m = 8) combines element U of the four octets: lane 0 holds d0, d2, lane 1 holds d1, d3 of
+        // kiss_fft.rs:148-187.  Each lane forms S = X + Y, D = X - Y of its own pair (lane 0: X = d0, Y = d2 w2, so
+        // S = a0, D = s5; lane 1: X = d1 w1, Y = d3 w3, so S = s3, D = s4), they swap ONE complex value (lane 0 sends s5
+        // and gets s3, lane 1 the reverse) and finish: lane 0 writes a0 +- s3 (outputs 0, 2), lane 1 s5 +- (s4.y, -s4.x)
+        // (outputs 1, 3) -- again the octets h and h+2.  Same operations on the same values as one lane doing it all.
+        const bool on = lane < 30;
+        const int g = on ? lane >> 1 : 0, h = lane & 1;
+        const int j1 = g / 3, j2 = g - 3 * j1, r = j1 + 5 * j2;
+        const float *x0p = o + 2 * r + 30 * h, *x1p = o + (N2 - 1 - 2 * r) - 30 * h;
+        const float2 *tp = tpair + r + 15 * h;
+        float2 d[16];  // d[8e + pl]: position p = 8 (h + 2e) + pl of the group
+        if (on) {
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+                for (int pl = 0; pl < 8; pl++) {  // pre-rotation, mdct.rs:184-200; q = w_qmap<0>(p) = q0 + h
+                    const int q0 = 2 * e + 4 * ((pl >> 2) & 1) + 8 * (pl & 3);
+                    const float x0 = x0p[30 * q0], x1 = x1p[-30 * q0];
+                    const float2 t = tab_ld<TS>(tp + 15 * q0);
+                    d[8 * e + pl] = p_add(make_float2(x0 * t.x, x1 * t.x), make_float2(-(x1 * t.y), x0 * t.y));
+                }
+        }
+        __syncwarp();  // every coefficient is in a register: the row may be overwritten
+        if (on) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) r_bfly4_m1(d[4 * b], d[4 * b + 1], d[4 * b + 2], d[4 * b + 3]);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                r_bfly2<0>(d[8 * e + 0], d[8 * e + 4]);
+                r_bfly2<1>(d[8 * e + 1], d[8 * e + 5]);
+                r_bfly2<2>(d[8 * e + 2], d[8 * e + 6]);
+                r_bfly2<3>(d[8 * e + 3], d[8 * e + 7]);
+            }
+            w_split_bfly4<0>(d, h);
+            w_split_bfly4<1>(d, h);
+            w_split_bfly4<2>(d, h);
+            w_split_bfly4<3>(d, h);
+            w_split_bfly4<4>(d, h);
+            w_split_bfly4<5>(d, h);
+            w_split_bfly4<6>(d, h);
+            w_split_bfly4<7>(d, h);
+            float2 *xc = reinterpret_cast<float2 *>(o) + 33 * g + 8 * h;  // a + a / PADG with a = 32 g + p
+#pragma unroll
+            for (int U = 0; U < 8; U++) {
+                xc[U] = d[U];
+                xc[16 + U] = d[8 + U];
+            }
+        }
+    } else if constexpr (NBLK > 1 && C == 1) {
+        // One channel of a transient frame: the NBLK x 15 groups of four are dealt to the lanes (up to four per lane)
+        // instead of one lane holding a group of every block.
+        constexpr int NT = NBLK * 15, TPL = (NT + 31) / 32;
+        static_assert(SHIFT == 3, "short blocks are 120-bin transforms");
+        float2 d[TPL * 4];
+#pragma unroll
+        for (int i = 0; i < TPL; i++) {
+            const int t = lane + 32 * i;
+            if (t < NT) {
+                const int blk = t / 15, g = t - 15 * blk;
+                const int j1 = g / 3, j2 = g - 3 * j1, r = j1 + 5 * j2;
+#pragma unroll
+                for (int p = 0; p < 4; p++) {  // w_qmap<3>(p) = p
+                    const float x0 = o[blk + NBLK * (2 * r) + NBLK * 30 * p];
+                    const float x1 = o[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * p];
+                    const float2 tt = tab_ld<TS>(tpair + r + 15 * p);
+                    d[4 * i + p] = p_add(make_float2(x0 * tt.x, x1 * tt.x), make_float2(-(x1 * tt.y), x0 * tt.y));
+                }
+            }
+        }
+        __syncwarp();
+        float2 *xc = reinterpret_cast<float2 *>(o);
+#pragma unroll
+        for (int i = 0; i < TPL; i++) {
+            const int t = lane + 32 * i;
+            if (t < NT) {
+                const int blk = t / 15, g = t - 15 * blk;
+                r_bfly4_m1(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+                const int a = NFFT * blk + GS * g;
+#pragma unroll
+                for (int p = 0; p < 4; p++) xc[a + a / PADG + p] = d[4 * i + p];
+            }
+        }
+    } else {
         const bool on = lane < 15 * C;
         const int ch = (C == 2 && lane >= 15) ? 1 : 0;
         const int g = on ? lane - 15 * ch : 0;
