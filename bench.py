@@ -167,6 +167,129 @@ def run_reference(args):
     emit(line)
 
 
+MIX_WEIGHTS = (0.10, 0.10, 0.30, 0.50)      # 2.5 / 5 / 10 / 20 ms
+MIX_PKT_BYTES = (64, 80, 112, 160)          # the SYNTH-CELT/1 schedule's sizes per frame length (its bit demand is fixed per LM)
+
+
+def run_mix(args):
+    """--mix: BASELINE configs[4] shape, CELT part, device-resident.  Every step every stream holds a single-frame packet of
+    a frame size drawn anew (10/10/30/50 % of 2.5/5/10/20 ms), 10 % of the frames transient; the step's buckets are built on the
+    device (OPN_FLAG_MIXED_FRAMES).  The metric is the same: audio seconds decoded per wall-clock second = concurrent
+    realtime streams.  An extra line kept under profiles/, not the headline."""
+    import torch
+    import opus_native_b200 as opn
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libopusb200 has no CPU fallback")
+    pin_rank_to_cpus(local, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, K, W = args.streams, args.steps, args.warmup
+    total = K + W
+    tp = args.transient_permille if args.transient_permille else 100
+    lo, _ = opn.shard_range(n * world, rank, world)
+    rnd = np.random.default_rng(1234 + rank)
+    stride = max(MIX_PKT_BYTES)
+    arena = np.zeros((total, n, stride), np.uint8)
+    lens = np.zeros((total, n), np.int32)
+    lm_of = rnd.choice(4, size=(total, n), p=MIX_WEIGHTS)
+    cores = cpu_threads()
+    for f in range(total):
+        for lm in range(4):
+            ids = np.nonzero(lm_of[f] == lm)[0]
+            if len(ids):
+                arena[f, ids, :MIX_PKT_BYTES[lm]] = opn.synth_fill(lo + 7 * lm, len(ids), f, 1, lm, CHANNELS, MIX_PKT_BYTES[lm], tp, n_threads=cores)[0]
+                lens[f, ids] = MIX_PKT_BYTES[lm]
+    audio_s = float((120 << lm_of[W:]).sum()) / 48000.0  # decoded in the timed steps, this rank
+    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, CHANNELS, 0), device=local, bitstream=1)
+    stream = torch.cuda.ExternalStream(dec.cuda_stream, device=dev)
+    d_arena = torch.from_numpy(arena.reshape(-1)).to(dev)
+    d_off = (torch.arange(n, dtype=torch.int64, device=dev) * stride).to(torch.int32)
+    d_len = torch.from_numpy(lens).to(dev)
+    d_res = torch.zeros(n, dtype=torch.int32, device=dev)
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY | opn.FLAG_MIXED_FRAMES
+    p_arena, p_off, p_len, p_res = d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr()
+
+    host_s = [0.0]
+
+    def step(f):
+        dec.decode_float_ptrs(p_arena + f * n * stride, p_off, p_len + 4 * f * n, None, 0, NF, p_res, flags)
+
+    def timed(k0, k1):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            h0 = time.perf_counter()
+            for f in range(k0, k1):
+                step(f)
+            host_s[0] = time.perf_counter() - h0
+            dec.join()
+            e1.record()
+        dec.synchronize()
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3
+
+    for f in range(W):
+        step(f)
+    dec.synchronize()
+    assert bool((d_res.cpu().numpy() == (120 << lm_of[W - 1])).all()), "decode reported errors"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dec.stats(reset=True)
+    with sampler.region():
+        t = timed(W, total)
+    if dist is not None:
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+        aa = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(aa, op=dist.ReduceOp.SUM)
+        audio_s = float(aa.item())
+    launches = sum(dec.stats(reset=True)["launches"])
+    host_enqueue_ms = 1e3 * host_s[0] / K
+    assert bool((d_res.cpu().numpy() == (120 << lm_of[total - 1])).all())
+    dec.reset()
+    dec.enable_timing(True)
+    for f in range(W):
+        step(f)
+    dec.stats(reset=True)
+    timed(W, total)
+    st = dec.stats(reset=True)
+    dec.enable_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        emit({
+            "metric": "concurrent_realtime_48k_streams_decoded", "value": audio_s / t, "unit": "streams", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32+f32", "data": "synthetic",
+            "config": {"workload": f"{n} CELT-only stereo streams per GPU, every packet's frame size drawn 10/10/30/50 % from 2.5/5/10/20 ms "
+                                   f"({MIX_PKT_BYTES} B packets, SYNTH-CELT/1), {tp / 10:.0f} % transient frames (BASELINE configs[4] shape, CELT part); "
+                                   "device-resident, buckets built on the device (OPN_FLAG_MIXED_FRAMES)",
+                       "streams_per_gpu": n, "frames_per_step_per_gpu": n, "channels": CHANNELS, "transient_permille": tp,
+                       "mean_frame_ms": 1e3 * audio_s / (world * n * K)},
+            "detail": {"per_kernel_ms": {"k_synth_rangedec": st["ms"][0] / K, "k_frame_mix (one launch per group)": st["ms"][1] / K},
+                       "frames_per_s": world * n * K / t,
+                       "host_enqueue_ms_per_step": host_enqueue_ms},
+            "gpu_launches": int(launches), "clocks": clocks,
+        })
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -197,9 +320,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bitstream", type=int, default=1, choices=[1, 2],
                     help="1: SYNTH-CELT/1 (the headline workload), 2: SYNTH-CELT/2 (allocation-driven frames; kept next to it under profiles/)")
+    ap.add_argument("--mix", action="store_true",
+                    help="extra workload: per-packet frame sizes 2.5-20 ms with transients, device-resident (BASELINE configs[4] shape, CELT part)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     quiet_stdout()
+    if args.mix:
+        if args.impl != "b200":
+            raise SystemExit("--mix is an extra line of the b200 arm")
+        run_mix(args)
+        return
     if args.impl == "reference":
         if args.bitstream != 1:
             raise SystemExit("--impl reference times the SYNTH-CELT/1 workload (the headline); there is no CPU loop for --bitstream 2")
@@ -254,6 +384,8 @@ def main():
 
     p_arena, p_off, p_len, p_res = d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr()
 
+    host_s = [0.0]
+
     def step_resident(f):
         dec.decode_float_ptrs(p_arena + f * step_bytes, p_off, p_len, None, 0, NF, p_res, flags)
 
@@ -262,9 +394,11 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record()
+            h0 = time.perf_counter()
             for f in range(k0, k1):
                 step_resident(f)
-            dec.join()  # half of the streams' frame kernels run on an internal stream: make them ancestors of e1
+            host_s[0] = time.perf_counter() - h0  # host time to enqueue the steps (asynchronous calls)
+            dec.join()  # two thirds of the streams' frame kernels run on internal streams: make them ancestors of e1
             e1.record()
         dec.synchronize()
         barrier()
@@ -281,6 +415,7 @@ def main():
     with sampler.region():
         t_value = max_over_ranks(timed_resident(W, total))
     launches = sum(dec.stats(reset=True)["launches"])
+    host_enqueue_ms = 1e3 * host_s[0] / K
     # same K steps again with cudaEvents around every kernel launch -> per-kernel durations
     dec.reset()
     dec.enable_timing(True)
@@ -438,6 +573,7 @@ def main():
                 "per_kernel_ms": {"k_synth_rangedec": k0_ms, "k_frame_w": k1_ms, "k_synth_expand (unfused variant only)": k2_ms,
                                   "note": "second pass of the same steps, stages in order on one stream with cudaEvents around "
                                           "each; in the measured run the range decode of up to 8 later steps overlaps the frame kernel of step n"},
+                "host_enqueue_ms_per_step": host_enqueue_ms,
                 "peak_source": peak_src, "e2e_checksum": checksum, "rank_cpus": cpus,
             },
             "e2e": {"value": e2e, "unit": "streams", "h2d_bytes_per_step": step_bytes + 4 * 4 * n,

@@ -124,6 +124,12 @@ typedef struct {
                                   * PVQ/IMDCT stage of the previous one (without the flag it is ordered after everything
                                   * enqueued on opn_batch_cuda_stream) */
 #define OPN_FLAG_SUBMIT_ONLY 8u  /* host-buffer call: enqueue and return a ticket for opn_batch_wait */
+#define OPN_FLAG_MIXED_FRAMES 16u /* with DEVICE_PTRS: the streams' packets may hold frames of different sizes (2.5, 5, 10 or
+                                  * 20 ms, read from each packet's TOC on the device); frame_size is then the capacity of
+                                  * a stream's PCM row in samples per channel, as for Decoder::decode_float, and
+                                  * result_per_stream[i] the samples stream i decoded (OPN_ERR_FRAME_SIZE_TOO_SMALL if its
+                                  * frame does not fit).  A lost packet (lens[i] == 0) conceals one frame of the size of
+                                  * the stream's previous packet.  The step's buckets are built on the device. */
 
 int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out);
 void opn_batch_destroy(opn_batch *b);

@@ -15,7 +15,7 @@ from ._capi import (  # noqa: F401
     op_synth_symbols, synth_packet, synth_fill, enc_run_script, op_celt2_symbols, celt2_packet, celt2_fill, CELT2_SIDE_DTYPE,
     OP_DTYPE, OUT_DTYPE, SIDE_DTYPE,
     OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN,
-    OP_PULSES, OP_SHRINK, OP_TELL, OP_PULSES_EVENTS, FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY,
+    OP_PULSES, OP_SHRINK, OP_TELL, OP_PULSES_EVENTS, FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY, FLAG_MIXED_FRAMES,
     BITSTREAM_OPUS, BITSTREAM_SYNTH_CELT_1, BITSTREAM_SYNTH_CELT_2,
     SAMPLE_F32, SAMPLE_I16, SAMPLE_I32, SAMPLE_U16, SAMPLE_U32, SAMPLE_F64, SAMPLE_FORMAT_OF,
 )

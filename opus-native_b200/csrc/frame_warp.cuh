@@ -224,7 +224,8 @@ __host__ __device__ constexpr size_t frame_smem_bytes(int lm, int channels, size
 // MODE: where the coefficient rows come from.  FRAME_ROWS: global memory, by TMA (unfused variant); FRAME_SYNTH1: expanded from
 // the codeword indices of the static SYNTH-CELT/1 schedule; FRAME_SYNTH2: expanded from the per-frame part list of SYNTH-CELT/2.
 enum { FRAME_ROWS = 0, FRAME_SYNTH1 = 1, FRAME_SYNTH2 = 2 };
-template <int LM, int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
+// One CTA of the frame kernel: its FRAME_WARPS warps take the items first_item .. first_item + FRAME_WARPS - 1 (< item_end).
+template <int LM, int C, int MODE> __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_item, uint32_t item_end)
 {
     constexpr bool EXPAND = MODE != FRAME_ROWS;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -242,8 +243,8 @@ template <int LM, int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_
         mbar_expect_tx(tbar, H.total);
         bulk_g2s(smem + 16, g_fblob[LM][C - 1], H.total, tbar);
     }
-    const uint32_t item = A.item0 + blockIdx.x * FRAME_WARPS + warp;
-    const bool in_range = item < A.item_end;
+    const uint32_t item = first_item + warp;
+    const bool in_range = item < item_end;
     const uint32_t stream = in_range ? (A.stream_idx ? A.stream_idx[item] : item) : 0u;
     if constexpr (!EXPAND) {
         // coefficient rows -> output rows by TMA, before anything else (the row address only needs `stream`)
@@ -385,6 +386,120 @@ template <int LM, int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_
         if (A.final_range) A.final_range[stream] = lost ? 0u : hdr.y;
         if (A.softclip_reset && !lost) *reinterpret_cast<float2 *>(A.softclip_reset + 2 * (size_t)stream) = make_float2(0.f, 0.f);
     }
+}
+
+template <int LM, int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
+{
+    frame_cta<LM, C, MODE>(A, A.item0 + blockIdx.x * FRAME_WARPS, A.item_end);
+}
+
+// The frame kernel of a step whose streams have different frame sizes: one launch per group of the step's MixPlan; a
+// CTA looks up which bucket (frame size) it belongs to and runs that size's frame_cta.  The grid is the caller's upper
+// bound; CTAs past the last bucket retire at once.  Shared memory is sized for the largest frame.
+template <int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_mix(FrameArgs A)
+{
+    const MixPlan &P = *A.plan;
+    const int g = A.group;
+    const uint32_t c = blockIdx.x;
+    if (c >= P.cta0[g][4]) return;
+    const int lm = (c >= P.cta0[g][1]) + (c >= P.cta0[g][2]) + (c >= P.cta0[g][3]);
+    const uint32_t first = P.start[g][lm] + (c - P.cta0[g][lm]) * FRAME_WARPS, end = P.start[g][lm] + P.count[g][lm];
+    switch (lm) {
+    case 0: frame_cta<0, C, MODE>(A, first, end); break;
+    case 1: frame_cta<1, C, MODE>(A, first, end); break;
+    case 2: frame_cta<2, C, MODE>(A, first, end); break;
+    default: frame_cta<3, C, MODE>(A, first, end); break;
+    }
+}
+
+// ---- bucketing of a mixed-frame step (MixPlan, opn_internal.h)
+// k_mix_key: one thread per stream reads its packet's TOC (the checks a host caller makes with query_packet_*,
+// src/lib.rs:219-325), picks the bucket and takes a position in it.  Streams of a warp that fall into the same bucket
+// take their positions with one atomic.  A lost packet (len 0) conceals one frame of the stream's previous size.
+__global__ void __launch_bounds__(256) k_mix_key(MixArgs A)
+{
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    const bool on = s < A.n_streams;
+    uint32_t key = MIX_NO_ITEM;
+    int32_t err = 0;
+    if (on) {
+        const uint32_t len = A.lens[s];
+        int lm = -1;
+        if (len == 0u) {
+            const uint32_t l = A.last_lm[s];
+            // nothing decoded yet: zeros for the caller's frame size (decoder.rs:473-484); the frame kernel produces
+            // them from an empty spectrum and an empty overlap
+            lm = l != MIX_NO_ITEM ? (int)l : (A.capacity >= 960u ? 3 : A.capacity >= 480u ? 2 : A.capacity >= 240u ? 1 : 0);
+        } else {
+            const uint32_t toc = A.arena[A.offsets[s]];
+            if ((toc & 0x80u) == 0u) err = OPN_ERR_UNIMPLEMENTED;                  // SILK / hybrid
+            else if ((toc & 0x3u) != 0u) err = OPN_ERR_UNIMPLEMENTED;              // multi-frame packets: host path only
+            else if (((toc & 0x4u) ? 2 : 1) != A.channels) err = OPN_ERR_UNIMPLEMENTED;  // mono<->stereo mapping
+            else lm = (int)((toc >> 3) & 0x3u);
+        }
+        if (lm >= 0 && (120u << lm) > A.capacity) {
+            err = OPN_ERR_FRAME_SIZE_TOO_SMALL;  // decoder.rs:388-390
+            lm = -1;
+        }
+        if (lm >= 0) {
+            uint32_t g = 0u;  // group g holds the streams [floor(n g / G), floor(n (g+1) / G)), as a uniform bucket's launches do
+            if (A.n_groups > 1) {
+                const uint32_t G = (uint32_t)A.n_groups;
+                g = (uint32_t)(((uint64_t)s * G) / A.n_streams);
+                if (g + 1u < G && (uint32_t)(((uint64_t)A.n_streams * (g + 1u)) / G) <= s) g += 1u;
+            }
+            key = g * 4u + (uint32_t)lm;
+            if (len > 1u) A.last_lm[s] = (uint8_t)lm;  // len <= 1 is PLC/DTX (decoder.rs:467): the size is not taken from it
+        }
+    }
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    uint32_t rank = 0u;
+    if (key != MIX_NO_ITEM) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0u;
+        if ((int)(threadIdx.x & 31u) == leader) base = atomicAdd(&A.plan->count[key >> 2][key & 3u], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        rank = base + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31u)) - 1u));
+    }
+    if (on) {
+        A.key[s] = (uint8_t)key;
+        A.rank[s] = rank;
+        if (key == MIX_NO_ITEM && A.result) A.result[s] = err;
+    }
+}
+// k_mix_place: bucket starts from the counts (every CTA recomputes the dozen sums), then each stream's item record.
+__global__ void __launch_bounds__(256) k_mix_place(MixArgs A)
+{
+    __shared__ uint32_t s_start[MIX_GROUPS * 4];
+    if (threadIdx.x == 0) {
+        uint32_t at = 0u;
+        MixPlan &P = *A.plan;
+        for (int g = 0; g < MIX_GROUPS; g++) {
+            uint32_t cta = 0u;
+            for (int lm = 0; lm < 4; lm++) {
+                const uint32_t n = P.count[g][lm];
+                s_start[g * 4 + lm] = at;
+                if (blockIdx.x == 0) {
+                    P.start[g][lm] = at;
+                    P.cta0[g][lm] = cta;
+                }
+                at += (n + MIX_PAD - 1u) / MIX_PAD * MIX_PAD;
+                cta += (n + FRAME_WARPS - 1u) / FRAME_WARPS;
+            }
+            if (blockIdx.x == 0) P.cta0[g][4] = cta;
+        }
+        if (blockIdx.x == 0) P.items_padded = at;
+    }
+    __syncthreads();
+    const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+    if (s >= A.n_streams) return;
+    const uint32_t key = A.key[s];
+    if (key == MIX_NO_ITEM) return;
+    const uint32_t item = s_start[key] + A.rank[s];
+    A.item_offsets[item] = A.offsets[s];
+    A.item_lens[item] = A.lens[s];
+    A.item_stream[item] = s;
+    A.item_lm[item] = (uint8_t)(key & 3u);
 }
 
 // Operator-level Mdct::backward on independent rows (tests; opn_op_imdct_tdac): one warp per row.

@@ -182,6 +182,14 @@ struct opn_batch {
     } stg[2];
     int stg_next = 0;
     float *d_softclip = nullptr;
+    // mixed-frame steps (OPN_FLAG_MIXED_FRAMES), allocated on first use: the step's buckets are built on the device
+    // (k_mix_key / k_mix_place on stream_ex, in step order) into one item table + plan per buffer set
+    uint8_t *d_last_lm = nullptr, *d_mix_key = nullptr;  // [n] state: LM of the last decoded packet; scratch: bucket of the stream
+    uint32_t *d_mix_rank = nullptr;                      // [n] scratch
+    uint32_t *d_mix_items[NSETS] = {};                   // [3][mix_item_cap(n)]: offsets | lens | stream ids, by item
+    uint8_t *d_mix_lm[NSETS] = {};                       // [mix_item_cap(n)]
+    MixPlan *d_mix_plan[NSETS] = {};
+    cudaEvent_t ev_mix[NSETS] = {};                      // buckets of set p are built
     unsigned long long *d_hist_samples = nullptr;  // measurement: history samples the post-filter needed (timed passes only)
     // host mirrors of DecoderInner fields (decoder.rs:236-258), per stream
     std::vector<int32_t> last_nf, bandwidth, last_duration, have_mode;
@@ -259,9 +267,26 @@ bool frame_grouped(const opn_batch *b, const FrameArgs &m)
 }
 // Timed pass: the frame kernel in its product configuration -- a large bucket as NGROUPS concurrent launches -- between
 // the two events timed_launch records on `stream` (the second one is ordered after every group).
+// streams [group_first(g), group_first(g + 1)) of an n-stream batch are group g of G (the same cut as a uniform bucket's item ranges)
+uint32_t group_first(uint32_t n, int g, int G) { return (uint32_t)((uint64_t)n * (uint32_t)g / (uint32_t)G); }
+int mix_groups(const opn_batch *b) { return (opn_batch::NGROUPS > 1 && b->n >= opn_batch::GROUP_MIN_ITEMS) ? opn_batch::NGROUPS : 1; }
 cudaError_t do_frame(opn_batch *b, const void *a)
 {
     FrameArgs m = *static_cast<const FrameArgs *>(a);
+    if (m.plan) {  // mixed-frame step: one launch per group of the plan
+        const int G = mix_groups(b);
+        if (G == 1) return launch_frame_mix(m, b->n, b->stream);
+        cudaError_t e = cudaEventRecord(b->ev_sw, b->stream);
+        for (int g = 0; g < G && e == cudaSuccess; g++) {
+            cudaStream_t st = g == 0 ? b->stream : b->stream_fr[g];
+            if (g > 0) e = cudaStreamWaitEvent(st, b->ev_sw, 0);
+            m.group = g;
+            if (e == cudaSuccess) e = launch_frame_mix(m, group_first(b->n, g + 1, G) - group_first(b->n, g, G), st);
+            if (g > 0 && e == cudaSuccess) e = cudaEventRecord(b->ev_tm[g], st);
+            if (g > 0 && e == cudaSuccess) e = cudaStreamWaitEvent(b->stream, b->ev_tm[g], 0);
+        }
+        return e;
+    }
     if (!frame_grouped(b, m)) return launch_frame(m, b->stream);
     cudaError_t e = cudaEventRecord(b->ev_sw, b->stream);
     const uint32_t n_items = m.n_items;
@@ -435,6 +460,152 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     return OPN_OK;
 }
 
+int mix_alloc(opn_batch *b)
+{
+    if (b->d_last_lm) return OPN_OK;
+    const size_t n = b->n, cap = mix_item_cap(b->n);
+    CU(cudaMalloc(&b->d_mix_key, n));
+    CU(cudaMalloc(&b->d_mix_rank, n * sizeof(uint32_t)));
+    for (int q = 0; q < opn_batch::NSETS; q++) {
+        CU(cudaMalloc(&b->d_mix_items[q], 3 * cap * sizeof(uint32_t)));
+        CU(cudaMalloc(&b->d_mix_lm[q], cap));
+        CU(cudaMalloc(&b->d_mix_plan[q], sizeof(MixPlan)));
+        CU(cudaEventCreateWithFlags(&b->ev_mix[q], cudaEventDisableTiming));
+    }
+    uint8_t *p = nullptr;
+    CU(cudaMalloc(&p, n));
+    CU(cudaMemsetAsync(p, MIX_NO_ITEM, n, b->stream_ex));
+    b->d_last_lm = p;
+    return OPN_OK;
+}
+
+// One step whose streams may have different frame sizes (device-resident: one single-frame packet or a loss per stream).
+// The step's buckets are built on the device, so the host never learns the sizes: the range decode is ONE launch over the
+// padded item table, the frame kernel one k_frame_mix launch per group, each sized by its upper bound.
+int run_mixed(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens, size_t capacity, float *dense,
+              size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
+{
+    if (b->unfused) return OPN_ERR_UNIMPLEMENTED;  // the measurement variant has no mixed-frame kernel
+    int rc = mix_alloc(b);
+    if (rc) return rc;
+    const int p = b->set;
+    b->set = (p + 1) % opn_batch::NSETS;
+    cudaStream_t srd = b->stream_rd[p % opn_batch::NRD];
+    const uint32_t cap = mix_item_cap(b->n);
+    const int G = mix_groups(b);
+    MixArgs x{};
+    x.arena = d_arena;
+    x.offsets = d_offsets;
+    x.lens = d_lens;
+    x.n_streams = b->n;
+    x.channels = b->cfg.channels;
+    x.n_groups = G;
+    x.capacity = (uint32_t)std::min<size_t>(capacity, 1u << 20);
+    x.last_lm = b->d_last_lm;
+    x.key = b->d_mix_key;
+    x.rank = b->d_mix_rank;
+    x.plan = b->d_mix_plan[p];
+    x.item_offsets = b->d_mix_items[p];
+    x.item_lens = b->d_mix_items[p] + cap;
+    x.item_stream = b->d_mix_items[p] + 2 * (size_t)cap;
+    x.item_lm = b->d_mix_lm[p];
+    x.result = d_result;
+    SymbolArgs s{};
+    s.arena = d_arena;
+    s.offsets = x.item_offsets;
+    s.lens = x.item_lens;
+    s.stream_idx = x.item_stream;
+    s.item_lm = x.item_lm;
+    s.n_items = cap;
+    s.lm = 0;
+    s.channels = b->cfg.channels;
+    s.has_toc = 1;
+    s.hdr = b->d_hdr[p];
+    s.status = b->d_status[p];
+    s.idx = b->d_idx[p];
+    s.pkt_cap = 1280u;
+    s.parts = b->d_parts[p];
+    const bool celt2 = b->cfg.bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
+    FrameArgs m{};
+    m.idx = celt2 ? nullptr : b->d_idx[p];
+    m.parts = celt2 ? b->d_parts[p] : nullptr;
+    m.hdr = b->d_hdr[p];
+    m.status = b->d_status[p];
+    m.stream_idx = x.item_stream;
+    m.n_items = cap;
+    m.channels = b->cfg.channels;
+    m.postfilter = b->cfg.postfilter;
+    m.carry = b->d_carry;
+    m.ring = b->d_ring;
+    m.ring_pos = b->d_ring_pos;
+    m.pf = b->d_pf;
+    m.dense = dense;
+    m.dense_stride = dense_stride;
+    m.gain = b->gain;
+    m.result = d_result;
+    m.final_range = b->d_final;
+    m.softclip_reset = softclip_reset ? b->d_softclip : nullptr;
+    m.hist_samples = b->timing ? b->d_hist_samples : nullptr;
+    m.plan = b->d_mix_plan[p];
+    if (b->timing) {
+        // measurement pass: everything in order on `stream`
+        rc = join_groups(b);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(b->stream_ex));  // earlier steps' bucketing (it owns last_lm)
+        CU(launch_mix_plan(x, b->stream));
+        b->launches[2] += 2;
+        rc = timed_launch(b, 0, do_rangedec, &s);
+        if (rc) return rc;
+        rc = timed_launch(b, 1, do_frame, &m);
+        if (rc) return rc;
+        b->launches[1] += G - 1;
+    } else {
+        cudaStream_t sx = b->stream_ex;
+        if (inputs_on == 1) {
+            CU(cudaEventRecord(b->ev_in, b->stream));
+            CU(cudaStreamWaitEvent(sx, b->ev_in, 0));
+        }
+        if (b->k1_recorded[p]) {  // set p (its item table and plan included) is free again
+            CU(cudaStreamWaitEvent(sx, b->ev_k1[p], 0));
+            if (b->k1_grouped[p])
+                for (int g = 1; g < opn_batch::NGROUPS; g++) CU(cudaStreamWaitEvent(sx, b->ev_fr[p][g], 0));
+        }
+        CU(launch_mix_plan(x, sx));
+        b->launches[2] += 2;
+        CU(cudaEventRecord(b->ev_mix[p], sx));
+        CU(cudaStreamWaitEvent(srd, b->ev_mix[p], 0));
+        CU(celt2 ? launch_celt2_rangedec(s, srd) : launch_synth_rangedec(s, srd));
+        CU(cudaEventRecord(b->ev_rd[p], srd));
+        b->launches[0]++;
+        if (G == 1) {
+            rc = join_groups(b);
+            if (rc) return rc;
+            CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
+            CU(launch_frame_mix(m, b->n, b->stream));
+            b->launches[1]++;
+        } else {
+            CU(cudaEventRecord(b->ev_sw, b->stream));
+            for (int g = 0; g < G; g++) {
+                cudaStream_t st = g == 0 ? b->stream : b->stream_fr[g];
+                if (g > 0 && !b->fr_pending[g]) CU(cudaStreamWaitEvent(st, b->ev_sw, 0));
+                CU(cudaStreamWaitEvent(st, b->ev_rd[p], 0));
+                m.group = g;
+                CU(launch_frame_mix(m, group_first(b->n, g + 1, G) - group_first(b->n, g, G), st));
+                b->launches[1]++;
+                if (g > 0) {
+                    CU(cudaEventRecord(b->ev_fr[p][g], st));
+                    b->fr_pending[g] = true;
+                    b->fr_last_set[g] = p;
+                }
+            }
+        }
+    }
+    CU(cudaEventRecord(b->ev_k1[p], b->stream));
+    b->k1_recorded[p] = true;
+    b->k1_grouped[p] = !b->timing && G > 1;
+    return OPN_OK;
+}
+
 // PLC sizing of decode_native(None)/decode_frame(None), src/decoder.rs:427-441 and 467-513.
 void plc_frames(size_t frame_size, int32_t last_nf, std::vector<uint32_t> &out)
 {
@@ -527,6 +698,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     }
     int rc = select_device(device);
     if (rc) return rc;
+    if (kernels_frame_groups() != OPN_FRAME_GROUPS) return OPN_ERR_INTERNAL;  // kernels and runtime of different builds
     opn_batch *b = new (std::nothrow) opn_batch();
     if (!b) return OPN_ERR_INTERNAL;
     b->device = device;
@@ -626,6 +798,15 @@ void opn_batch_destroy(opn_batch *b)
     cudaFree(b->d_final);
     cudaFree(b->d_pf);
     cudaFree(b->d_softclip);
+    cudaFree(b->d_last_lm);
+    cudaFree(b->d_mix_key);
+    cudaFree(b->d_mix_rank);
+    for (int q = 0; q < opn_batch::NSETS; q++) {
+        cudaFree(b->d_mix_items[q]);
+        cudaFree(b->d_mix_lm[q]);
+        cudaFree(b->d_mix_plan[q]);
+        if (b->ev_mix[q]) cudaEventDestroy(b->ev_mix[q]);
+    }
     cudaFree(b->d_hist_samples);
     for (auto &g : b->stg) {
         cudaFree(g.d_arena);
@@ -663,6 +844,7 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     }
     b->set = 0;
     CU(cudaMemsetAsync(b->d_softclip, 0, n * 2 * sizeof(float), b->stream));
+    if (b->d_last_lm) CU(cudaMemsetAsync(b->d_last_lm, MIX_NO_ITEM, n, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     std::fill(b->last_nf.begin(), b->last_nf.end(), 120);
     std::fill(b->bandwidth.begin(), b->bandwidth.end(), -1);
@@ -865,15 +1047,22 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
         if (rc < 0) return rc;
         return (flags & OPN_FLAG_SUBMIT_ONLY) ? rc : OPN_OK;  // submit-only: the ticket for opn_batch_wait
     }
-    // Device-resident step: one single-frame CELT packet of exactly frame_size per stream; the TOC
-    // is validated on the device and reported per stream.  Asynchronous on the batch stream.
-    const int lm = lm_of_frame(frame_size);
-    if (lm < 0 || !arena) return OPN_ERR_BAD_ARG;
+    // Device-resident step: one single-frame CELT packet per stream; the TOC is validated on the device and reported per
+    // stream.  Asynchronous on the batch's streams.  Without OPN_FLAG_MIXED_FRAMES every packet must hold exactly
+    // frame_size samples; with it frame_size is the capacity of a stream's row, as in decode_float, and each stream
+    // decodes whatever single frame its packet holds.
+    if (!arena) return OPN_ERR_BAD_ARG;
     if (b->cfg.bitstream == OPN_BITSTREAM_OPUS) return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:47-56 is todo!()
     float *dense = (flags & OPN_FLAG_NO_PCM_COPY) ? nullptr : pcm;
-    if (dense && (pcm_stride_floats < frame_size * (size_t)C || (pcm_stride_floats & 3) ||
+    if (dense && (pcm_stride_floats < std::min<size_t>(frame_size, 960) * (size_t)C || (pcm_stride_floats & 3) ||
                   (reinterpret_cast<uintptr_t>(dense) & 15)))
         return OPN_ERR_BAD_ARG;
+    if (flags & OPN_FLAG_MIXED_FRAMES)
+        return run_mixed(b, arena, offsets, lens, frame_size, dense, pcm_stride_floats, result_per_stream,
+                         (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1, true);
+    const int lm = lm_of_frame(frame_size);
+    if (lm < 0) return OPN_ERR_BAD_ARG;
+    if (dense && pcm_stride_floats < frame_size * (size_t)C) return OPN_ERR_BAD_ARG;
     return run_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, lm, 1, 1280u, dense, pcm_stride_floats, result_per_stream,
                       (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1, true);
 }

@@ -43,6 +43,25 @@ __host__ __device__ inline uint32_t hdr_pack(uint32_t silence, uint32_t postfilt
     return silence | postfilter << 1 | transient << 2 | intra << 3 | tapset << 4 | gain_idx << 8 | octave << 12 | period << 16;
 }
 
+// ---- steps whose streams have different frame sizes (OPN_FLAG_MIXED_FRAMES): device-side bucketing
+// The streams of a batch are cut into MIX_GROUPS contiguous ranges (the frame kernel's concurrent launches: a stream stays
+// on its group's CUDA stream for life) and, inside a group, sorted by frame size.  Bucket (g, lm) owns the items
+// [start, start + count); every bucket starts on a multiple of MIX_PAD items so that a range-decode CTA never spans two
+// frame sizes.  Written by k_mix_place, read by the range decode and frame kernels of the same step.
+#ifndef OPN_FRAME_GROUPS
+#define OPN_FRAME_GROUPS 3  // a library variant must be built with the same value in the kernels and in the host runtime
+#endif
+constexpr int MIX_GROUPS = OPN_FRAME_GROUPS > 1 ? OPN_FRAME_GROUPS : 1;
+constexpr uint32_t MIX_PAD = 32u * OPN_RD_WARPS;
+constexpr uint8_t MIX_NO_ITEM = 0xFF;
+struct MixPlan {
+    uint32_t count[MIX_GROUPS][4];
+    uint32_t start[MIX_GROUPS][4];
+    uint32_t cta0[MIX_GROUPS][5];  // frame kernel: first CTA of bucket (g, lm) inside group g's launch; [4] = CTAs in use
+    uint32_t items_padded;         // items up to the end of the last bucket
+};
+__host__ __device__ constexpr uint32_t mix_item_cap(uint32_t n_streams) { return n_streams + MIX_GROUPS * 4u * MIX_PAD; }
+
 struct SymbolArgs {
     const uint8_t *arena;
     const uint32_t *offsets;     // [n_items] byte offset of the packet (or of the payload if !has_toc)
@@ -59,6 +78,7 @@ struct SymbolArgs {
     uint32_t pkt_cap;            // bytes of shared memory per warp for the packet
     struct Celt2Part *parts;     // SYNTH-CELT/2: [n_streams][CELT2_MAX_PARTS] PVQ leaves (range decode -> expansion)
     struct Celt2Side *side2;     // SYNTH-CELT/2: [n_streams] or nullptr: full side record (tests)
+    const uint8_t *item_lm;      // mixed-frame step: [n_items] LM of the item, MIX_NO_ITEM = padding (overrides lm); else nullptr
 };
 
 struct FrameArgs {
@@ -83,6 +103,23 @@ struct FrameArgs {
     uint32_t *final_range;        // [n_streams]
     float *softclip_reset;        // [n_streams][2] or nullptr: cleared for every stream that decodes a packet (decoder.rs:420-423)
     unsigned long long *hist_samples;  // measurement (or nullptr): += max(T0,T1)+2 per channel-frame the post-filter runs on
+    const MixPlan *plan;          // mixed-frame step (k_frame_mix): buckets of this step, else nullptr
+    int group;                    // mixed-frame step: which group of the plan this launch covers
+};
+
+struct MixArgs {  // k_mix_key / k_mix_place
+    const uint8_t *arena;
+    const uint32_t *offsets, *lens;  // [n_streams] the caller's arrays
+    uint32_t n_streams;
+    int channels, n_groups;          // n_groups = 1 or MIX_GROUPS
+    uint32_t capacity;               // samples per channel the caller's rows hold (frame_size argument)
+    uint8_t *last_lm;                // [n_streams] LM of the stream's last decoded packet, MIX_NO_ITEM = none yet (state)
+    uint8_t *key;                    // [n_streams] scratch: g*4 + lm, or MIX_NO_ITEM
+    uint32_t *rank;                  // [n_streams] scratch: position inside the bucket
+    MixPlan *plan;                   // zeroed before k_mix_key
+    uint32_t *item_offsets, *item_lens, *item_stream;  // [mix_item_cap] out
+    uint8_t *item_lm;                // [mix_item_cap] out, preset to MIX_NO_ITEM
+    int32_t *result;                 // [n_streams] or nullptr: OPN_ERR_* of the streams no bucket takes
 };
 
 // ---- launchers (opn_kernels.cu).  All return a cudaError_t and never synchronise.
@@ -97,6 +134,11 @@ cudaError_t launch_celt2_rangedec(const SymbolArgs &a, cudaStream_t st);  // SYN
 cudaError_t launch_celt2_expand(const SymbolArgs &a, cudaStream_t st);    // SYNTH-CELT/2 operator: part lists -> coefficient rows
 // the frame kernel: (PVQ expansion when a.coef == nullptr) + IMDCT + TDAC + comb post-filter + PCM store
 cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st);
+// mixed-frame step: bucketing (two kernels on one stream) and the frame kernel of one group (a.plan, a.group; grid sized by the
+// caller's upper bound n_streams_in_group)
+cudaError_t launch_mix_plan(const MixArgs &a, cudaStream_t st);
+int kernels_frame_groups();  // OPN_FRAME_GROUPS the kernels were built with
+cudaError_t launch_frame_mix(const FrameArgs &a, uint32_t n_streams_in_group, cudaStream_t st);
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,
                             int nblk, cudaStream_t st);
 cudaError_t launch_op_comb_inplace(float *y, size_t row_stride, int y_offset, int n, uint32_t n_rows, const int32_t *params4,

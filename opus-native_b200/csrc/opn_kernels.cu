@@ -33,9 +33,26 @@ template <int LM, int C> static cudaError_t set_carveout()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
 }
+static size_t mix_smem_bytes(int C)
+{
+    size_t m = 0;
+    for (int lm = 0; lm < 4; lm++) m = std::max(m, frame_smem_bytes(lm, C, g_fblob_bytes[lm][C - 1]));
+    return m;
+}
+template <int C> static cudaError_t set_carveout_mix()
+{
+    const int smem = (int)mix_smem_bytes(C);
+    cudaError_t e = cudaFuncSetAttribute(k_frame_mix<C, FRAME_SYNTH1>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_mix<C, FRAME_SYNTH1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_mix<C, FRAME_SYNTH2>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_mix<C, FRAME_SYNTH2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
+}
 static cudaError_t set_warp_kernel_attributes()
 {
     cudaError_t e = set_carveout<0, 1>();
+    if (e == cudaSuccess) e = set_carveout_mix<1>();
+    if (e == cudaSuccess) e = set_carveout_mix<2>();
     if (e == cudaSuccess) e = set_carveout<0, 2>();
     if (e == cudaSuccess) e = set_carveout<1, 1>();
     if (e == cudaSuccess) e = set_carveout<1, 2>();
@@ -340,6 +357,40 @@ cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st)
     case 7: return launch_frame_w<3, 2>(a, st);
     default: return cudaErrorInvalidValue;
     }
+}
+
+int kernels_frame_groups() { return OPN_FRAME_GROUPS; }
+
+cudaError_t launch_mix_plan(const MixArgs &a, cudaStream_t st)
+{
+    if (a.n_streams == 0) return cudaSuccess;
+    if (!a.plan || !a.key || !a.rank || !a.last_lm || !a.item_lm || !a.item_offsets || !a.item_lens || !a.item_stream) return cudaErrorInvalidValue;
+    if (a.n_groups != 1 && a.n_groups != MIX_GROUPS) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(a.plan, 0, sizeof(MixPlan), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.item_lm, MIX_NO_ITEM, mix_item_cap(a.n_streams), st);
+    if (e != cudaSuccess) return e;
+    const uint32_t grid = (a.n_streams + 255u) / 256u;
+    k_mix_key<<<grid, 256, 0, st>>>(a);
+    k_mix_place<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frame_mix(const FrameArgs &a, uint32_t n_streams_in_group, cudaStream_t st)
+{
+    if (n_streams_in_group == 0) return cudaSuccess;
+    if (!a.plan || a.group < 0 || a.group >= MIX_GROUPS || a.coef || (!a.idx && !a.parts) || !a.stream_idx) return cudaErrorInvalidValue;
+    const uint32_t grid = (n_streams_in_group + FRAME_WARPS - 1) / FRAME_WARPS + 4u;  // each of the four buckets rounds up
+    const size_t smem = mix_smem_bytes(a.channels);
+    if (a.channels == 2) {
+        if (a.parts) k_frame_mix<2, FRAME_SYNTH2><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+        else k_frame_mix<2, FRAME_SYNTH1><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    } else if (a.channels == 1) {
+        if (a.parts) k_frame_mix<1, FRAME_SYNTH2><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+        else k_frame_mix<1, FRAME_SYNTH1><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,

@@ -284,7 +284,13 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
     __shared__ SynthEntry s_ent[SYNTH_MAX_ENTRIES];
     __shared__ uint32_t s_lfl[21][LAP_N + 1], s_lfs[21][LAP_N + 1];  // decode_laplace states per band (laplace_table)
     const uint32_t lane = threadIdx.x;  // index inside the CTA: one packet per thread
-    const int lm = A.lm, C = A.channels;
+    const int C = A.channels;
+    int lm = A.lm;
+    if (A.item_lm) {  // mixed-frame step: buckets start on CTA boundaries, the CTA's first item tells its frame size
+        const uint32_t l = A.item_lm[blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u)];
+        if (l == MIX_NO_ITEM) return;
+        lm = (int)l;
+    }
     if (lane < 21u) {
         const uint32_t decay = 6000u + 400u * lane;
         const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;  // get_start_freq, src/range_coder/mod.rs:530-534
@@ -299,6 +305,7 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_synth_rangedec(
     __syncthreads();
     const uint32_t item = blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u) + lane;
     if (item >= A.n_items) return;
+    if (A.item_lm && A.item_lm[item] == MIX_NO_ITEM) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
     uint32_t len = A.lens[item];
     const uint8_t *src = A.arena + A.offsets[item];
@@ -547,7 +554,13 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_celt2_rangedec(
 {
     __shared__ uint32_t s_lfl[21][LAP_N + 1], s_lfs[21][LAP_N + 1];
     const uint32_t lane = threadIdx.x;
-    const int lm = A.lm, C = A.channels;
+    const int C = A.channels;
+    int lm = A.lm;
+    if (A.item_lm) {  // mixed-frame step, as in k_synth_rangedec
+        const uint32_t l = A.item_lm[blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u)];
+        if (l == MIX_NO_ITEM) return;
+        lm = (int)l;
+    }
     if (lane < 21u) {
         const uint32_t decay = 6000u + 400u * lane;
         const uint32_t fs0 = ((32768u - 33u) * (16384u - decay)) / (16384u + decay) + 1u;
@@ -556,6 +569,7 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_celt2_rangedec(
     __syncthreads();
     const uint32_t item = blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u) + lane;
     if (item >= A.n_items) return;
+    if (A.item_lm && A.item_lm[item] == MIX_NO_ITEM) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
     uint32_t len = A.lens[item];
     const uint8_t *src = A.arena + A.offsets[item];

@@ -742,6 +742,89 @@ def test_batch_device_resident_path_matches_host_path():
     assert ring_n == 2880 and ring_ptr and pos_ptr  # 3 x 960: a frame plus the 1024 + 2 samples of history before it
 
 
+@pytest.mark.parametrize("ns,channels", [(2300, 2), (300, 1)])
+def test_batch_device_resident_mixed_frame_sizes(ns, channels):
+    """OPN_FLAG_MIXED_FRAMES: a device-resident step whose streams hold frames of different sizes.  Every stream picks a
+    new frame size for every packet (2.5/5/10/20 ms, weights 10/10/30/50 %; 10 % transient frames), 3 % of the packets
+    are lost (concealed with one frame of the stream's previous size), a few carry a foreign TOC.  The buckets are built
+    on the device (k_mix_key / k_mix_place); ten steps are enqueued back to back (2300 streams: three frame-kernel groups
+    per step, 300: one) and every step's PCM, sample counts and the final ranges are compared with one oracle decoder per
+    stream, bit for bit."""
+    torch = pytest.importorskip("torch")
+    rnd = np.random.default_rng(11 + ns)
+    nsteps, stride, cap = 10, 160, 960
+    pkt_bytes = {0: 64, 1: 80, 2: 110, 3: 160}
+    oracle = [O.SynthStream(3, channels) for _ in range(ns)]
+    arena = np.zeros((nsteps, ns, stride), np.uint8)
+    lens = np.zeros((nsteps, ns), np.uint32)
+    lm_of = np.zeros((nsteps, ns), np.int64)
+    foreign = np.zeros((nsteps, ns), bool)
+    for f in range(nsteps):
+        lm_of[f] = rnd.choice([0, 1, 2, 3], size=ns, p=[0.1, 0.1, 0.3, 0.5])
+        for lm in range(4):
+            ids = np.nonzero(lm_of[f] == lm)[0]
+            if len(ids) == 0:
+                continue
+            pk = opn.synth_fill(4000 + lm, len(ids), f, 1, lm, channels, pkt_bytes[lm], transient_permille=100)[0]
+            arena[f, ids, :pkt_bytes[lm]] = pk
+            lens[f, ids] = pkt_bytes[lm]
+        if f > 0:
+            lens[f, rnd.random(ns) < 0.03] = 0
+        for s in rnd.choice(ns, 3, replace=False):  # SILK TOC, multi-frame code, wrong channel count
+            kind = int(rnd.integers(3))
+            if lens[f, s]:
+                foreign[f, s] = True
+                arena[f, s, 0] = [0x48, arena[f, s, 0] | 1, arena[f, s, 0] ^ 4][kind]
+    dev = torch.device("cuda:0")
+    d_arena = torch.from_numpy(arena.reshape(-1).copy()).to(dev)
+    d_off = torch.arange(ns, dtype=torch.int32, device=dev) * stride
+    d_len = torch.from_numpy(lens.astype(np.int32)).to(dev)
+    d_pcm = torch.zeros((nsteps, ns, cap * channels), dtype=torch.float32, device=dev)
+    d_res = torch.full((nsteps, ns), -99, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **SYNTH)
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY | opn.FLAG_MIXED_FRAMES
+    for f in range(nsteps):
+        dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * stride, d_off.data_ptr(), d_len[f].data_ptr(), d_pcm[f].data_ptr(),
+                              cap * channels, cap, d_res[f].data_ptr(), flags)
+    dec.join()
+    dec.synchronize()
+    res, got = d_res.cpu().numpy(), d_pcm.cpu().numpy()
+    last_lm = np.full(ns, -1)
+    last_rng = np.zeros(ns, np.uint32)
+    for f in range(nsteps):
+        for s in range(ns):
+            if foreign[f, s]:
+                assert res[f, s] == -6, (f, s, res[f, s])  # Unimplemented, state untouched
+                assert not got[f, s].any()
+                continue
+            if lens[f, s] == 0:
+                lm = last_lm[s] if last_lm[s] >= 0 else 3  # nothing decoded yet: zeros of the row's capacity (decoder.rs:473-484)
+                oracle[s].lm = int(lm)
+                want = oracle[s].decode(b"")[3]
+                last_rng[s] = 0
+            else:
+                lm = lm_of[f, s]
+                oracle[s].lm = int(lm)
+                side, _, _, want = oracle[s].decode(arena[f, s, 1:int(lens[f, s])])
+                last_lm[s] = lm
+                last_rng[s] = side.final_rng
+            nf = 120 << int(lm)
+            assert res[f, s] == nf, (f, s, res[f, s], nf)
+            assert np.array_equal(got[f, s, :nf * channels], want), (f, s, lm)
+            assert not got[f, s, nf * channels:].any()
+    assert np.array_equal(dec.final_ranges(), last_rng)
+    # a row too short for the stream's frame: FrameSizeTooSmall for that stream only (decoder.rs:388-390)
+    d_res2 = torch.full((ns,), -99, dtype=torch.int32, device=dev)
+    dec.decode_float_ptrs(d_arena.data_ptr(), d_off.data_ptr(), d_len[0].data_ptr(), d_pcm[0].data_ptr(), cap * channels, 240,
+                          d_res2.data_ptr(), flags)
+    dec.join()
+    dec.synchronize()
+    r2 = d_res2.cpu().numpy()
+    ok = ~foreign[0]
+    assert np.all(r2[ok & (lm_of[0] > 1)] == -5) and np.all(r2[ok & (lm_of[0] <= 1)] == (120 << lm_of[0][ok & (lm_of[0] <= 1)]))
+
+
 @pytest.mark.parametrize("postfilter", [True, False])
 def test_batch_device_resident_steps_enqueued_back_to_back(postfilter):
     """OPN_FLAG_INPUTS_READY: 14 steps are enqueued without a host wait in between, so range decode, PVQ
