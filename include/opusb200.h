@@ -208,6 +208,12 @@ int opn_op_comb_filter_inplace(int device, float *y, size_t row_stride, size_t y
 int opn_op_comb_filter(int device, float *y, const float *x, size_t row_stride, size_t offset,
                        size_t n, uint32_t n_rows, const int32_t *params4, const float *gains2,
                        size_t overlap);
+/* smooth_fade_into_in1 / smooth_fade_into_in2, src/decoder.rs:833-865 (the cross-fade decode_frame applies at a mode
+ * transition, decoder.rs:731-788): out = w^2 * in2 + (1 - w^2) * in1 over the first `overlap` samples per channel of
+ * n_rows interleaved rows, w = WINDOW[i * 48000 / fs_hz].  `out` may be in1 or in2 (the crate's two in-place forms);
+ * samples past the overlap are copied from in1. */
+int opn_op_smooth_fade(int device, const float *in1, const float *in2, float *out, size_t row_stride,
+                       size_t overlap, int channels, int32_t fs_hz, uint32_t n_rows);
 /* pcm_soft_clip, src/lib.rs:526-632: n_rows independent interleaved buffers. */
 int opn_op_pcm_soft_clip(int device, float *pcm, size_t row_stride, size_t row_len, int channels,
                          uint32_t n_rows, float *softclip_mem /* [n_rows][channels] */);

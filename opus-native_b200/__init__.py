@@ -11,7 +11,7 @@ from ._capi import (  # noqa: F401
     query_packet_bandwidth, query_packet_channel_count, query_packet_frame_count,
     query_packet_samples_per_frame, query_packet_sample_count, query_packet_codec_mode, parse_packet,
     DecoderConfiguration, Decoder, BatchDecoder, HostBuffer, host_register, host_unregister,
-    op_rangedec_script, op_imdct_tdac, op_comb_filter_inplace, op_comb_filter, op_pcm_soft_clip, op_bitexact_trig,
+    op_rangedec_script, op_imdct_tdac, op_comb_filter_inplace, op_comb_filter, op_pcm_soft_clip, op_bitexact_trig, op_smooth_fade,
     op_synth_symbols, synth_packet, synth_fill, enc_run_script, op_celt2_symbols, celt2_packet, celt2_fill, CELT2_SIDE_DTYPE,
     OP_DTYPE, OUT_DTYPE, SIDE_DTYPE,
     OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN,

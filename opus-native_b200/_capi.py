@@ -120,6 +120,7 @@ def lib():
     sig("opn_op_comb_filter_inplace", C.c_int, C.c_int, vp, sz, sz, sz, u32, vp, vp, sz)
     sig("opn_op_comb_filter", C.c_int, C.c_int, vp, vp, sz, sz, sz, u32, vp, vp, sz)
     sig("opn_op_pcm_soft_clip", C.c_int, C.c_int, vp, sz, sz, C.c_int, u32, vp)
+    sig("opn_op_smooth_fade", C.c_int, C.c_int, vp, vp, vp, sz, sz, C.c_int, C.c_int32, u32)
     sig("opn_op_synth_symbols", C.c_int, C.c_int, vp, vp, vp, u32, C.c_int, C.c_int, vp, vp, vp)
     sig("opn_op_celt2_symbols", C.c_int, C.c_int, vp, vp, vp, u32, C.c_int, C.c_int, vp, vp, vp)
     sig("opn_celt2_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp, vp)
@@ -430,6 +431,16 @@ def op_pcm_soft_clip(pcm, row_len, channels, mem, device=0):
     assert pcm.dtype == np.float32 and pcm.ndim == 2 and mem.dtype == np.float32 and mem.shape == (pcm.shape[0], channels)
     _chk(lib().opn_op_pcm_soft_clip(device, _p(pcm), pcm.shape[1], row_len, channels, pcm.shape[0], _p(mem)))
     return pcm
+
+
+def op_smooth_fade(in1, in2, overlap, channels, fs=48000, device=0):
+    """smooth_fade_into_in1 (src/decoder.rs:833-848) on rows of interleaved samples; returns the faded copy of in1."""
+    in1 = np.ascontiguousarray(in1, np.float32)
+    in2 = np.ascontiguousarray(in2, np.float32)
+    assert in1.ndim == 2 and in1.shape == in2.shape
+    out = np.empty_like(in1)
+    _chk(lib().opn_op_smooth_fade(device, _p(in1), _p(in2), _p(out), in1.shape[1], overlap, channels, fs, in1.shape[0]))
+    return out
 
 
 def op_bitexact_trig(x=None, isin=None, icos=None, device=0):

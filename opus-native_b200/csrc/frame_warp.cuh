@@ -402,8 +402,9 @@ template <int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_WARPS, F
     const int g = A.group;
     const uint32_t c = blockIdx.x;
     if (c >= P.cta0[g][4]) return;
-    const int lm = (c >= P.cta0[g][1]) + (c >= P.cta0[g][2]) + (c >= P.cta0[g][3]);
-    const uint32_t first = P.start[g][lm] + (c - P.cta0[g][lm]) * FRAME_WARPS, end = P.start[g][lm] + P.count[g][lm];
+    // the buckets take their CTAs longest frames first (cta0[g][j] belongs to lm = 3 - j): the short ones fill the tail
+    const int j = (c >= P.cta0[g][1]) + (c >= P.cta0[g][2]) + (c >= P.cta0[g][3]), lm = 3 - j;
+    const uint32_t first = P.start[g][lm] + (c - P.cta0[g][j]) * FRAME_WARPS, end = P.start[g][lm] + P.count[g][lm];
     switch (lm) {
     case 0: frame_cta<0, C, MODE>(A, first, end); break;
     case 1: frame_cta<1, C, MODE>(A, first, end); break;
@@ -476,12 +477,13 @@ __global__ void __launch_bounds__(256) k_mix_place(MixArgs A)
         MixPlan &P = *A.plan;
         for (int g = 0; g < MIX_GROUPS; g++) {
             uint32_t cta = 0u;
-            for (int lm = 0; lm < 4; lm++) {
+            for (int j = 0; j < 4; j++) {  // longest frames first, in the item table and in the frame kernel's CTA order
+                const int lm = 3 - j;
                 const uint32_t n = P.count[g][lm];
                 s_start[g * 4 + lm] = at;
                 if (blockIdx.x == 0) {
                     P.start[g][lm] = at;
-                    P.cta0[g][lm] = cta;
+                    P.cta0[g][j] = cta;
                 }
                 at += (n + MIX_PAD - 1u) / MIX_PAD * MIX_PAD;
                 cta += (n + FRAME_WARPS - 1u) / FRAME_WARPS;

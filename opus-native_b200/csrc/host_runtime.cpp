@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost a predicted branch unless a profiler has attached
+
 #include "opn_internal.h"
 #include "celt2.cuh"
 
@@ -201,6 +203,14 @@ struct opn_batch {
 
 namespace {
 
+// NVTX range for the host-side stages of a call (visible in Nsight Systems timelines next to the kernels)
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+    Range(const Range &) = delete;
+    Range &operator=(const Range &) = delete;
+};
+
 int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes, size_t n_items, size_t dense_floats, size_t conv_esize)
 {
     if (!g.done) CU(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
@@ -335,6 +345,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
                const uint32_t *d_stream_idx, const uint32_t *d_dense_off, uint32_t n_items, int lm, int has_toc,
                uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
 {
+    Range nv("opn: step (range decode + frame kernel)");
     const int p = b->set;
     b->set = (p + 1) % opn_batch::NSETS;
     cudaStream_t srd = b->stream_rd[p % opn_batch::NRD];
@@ -486,6 +497,7 @@ int run_mixed(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, c
               size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
 {
     if (b->unfused) return OPN_ERR_UNIMPLEMENTED;  // the measurement variant has no mixed-frame kernel
+    Range nv("opn: mixed-frame step (bucketing + range decode + frame kernel)");
     int rc = mix_alloc(b);
     if (rc) return rc;
     const int p = b->set;
@@ -711,7 +723,17 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     // All pipeline streams have the same priority (measured in round 1, tools/experiments/priorities.sh: raising the
     // entropy streams gave slow stretches, raising the frame stream serialised the pipeline).
-    for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++) e = cudaStreamCreateWithFlags(&b->stream_rd[q], cudaStreamNonBlocking);
+    {
+        // Range-decode streams run at the highest priority, so that their few CTAs are placed first whenever a frame-kernel
+        // CTA retires (OPN_RD_PRIORITY=0 in the environment turns it off).  Measured: SYNTH-CELT/1 44.3 us per step either
+        // way, SYNTH-CELT/2 125 -> 116 us.
+        const char *pr = std::getenv("OPN_RD_PRIORITY");
+        const bool high = !(pr && pr[0] == '0');
+        int lo_p = 0, hi_p = 0;
+        if (high) cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++)
+            e = cudaStreamCreateWithPriority(&b->stream_rd[q], cudaStreamNonBlocking, high ? hi_p : 0);
+    }
     for (int q = 0; q < opn_batch::NSETS && e == cudaSuccess; q++) {
         e = cudaEventCreateWithFlags(&b->ev_rd[q], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_ex[q], cudaEventDisableTiming);
@@ -861,6 +883,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                              size_t pcm_stride, size_t frame_size, int32_t *results, uint32_t flags,
                              void *pcm_conv = nullptr, int sample_format = OPN_SAMPLE_F32)
 {
+    Range nv_call("opn: host-buffer call (parse, upload, decode, download)");
     const uint32_t n = b->n;
     const int C = b->cfg.channels;
     // pre-pass: bytes to upload and an upper bound of the number of frames (items)
@@ -898,6 +921,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
     size_t kbase = 0;  // items of earlier chunks
     for (uint32_t ch = 0; ch < n_chunks; ch++) {
         const uint32_t s0 = (uint32_t)((uint64_t)n * ch / n_chunks), s1 = (uint32_t)((uint64_t)n * (ch + 1) / n_chunks);
+        Range nv_chunk("opn: chunk (host parse -> enqueue)");
         items.clear();
         bool any_gap = false;  // some stream of the chunk leaves part of its dense row unwritten
         uint32_t max_len = 8;
@@ -1479,6 +1503,26 @@ int opn_op_pcm_soft_clip(int device, float *pcm, size_t row_stride, size_t row_l
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(pcm, dP.p, (size_t)n_rows * row_stride * 4, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(softclip_mem, dM.p, (size_t)n_rows * channels * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+int opn_op_smooth_fade(int device, const float *in1, const float *in2, float *out, size_t row_stride, size_t overlap, int channels,
+                       int32_t fs_hz, uint32_t n_rows)
+{
+    if (!in1 || !in2 || !out || n_rows == 0 || channels < 1 || channels > 2 || overlap * (size_t)channels > row_stride) return OPN_ERR_BAD_ARG;
+    if (fs_hz <= 0 || 48000 % fs_hz != 0 || (overlap > 0 && (overlap - 1) * (size_t)(48000 / fs_hz) >= 120)) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n_rows * row_stride * 4;
+    DevBuf d1, d2;
+    CU(d1.alloc(bytes));
+    CU(d2.alloc(bytes));
+    CU(cudaMemcpy(d1.p, in1, bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d2.p, in2, bytes, cudaMemcpyHostToDevice));
+    // the result goes into in1's copy (smooth_fade_into_in1); the caller's `out` may be either input or a third buffer
+    CU(launch_op_smooth_fade(d1.as<float>(), d2.as<float>(), d1.as<float>(), row_stride, (int)overlap, channels, fs_hz, n_rows, nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, d1.p, bytes, cudaMemcpyDeviceToHost));
     return OPN_OK;
 }
 

@@ -57,7 +57,7 @@ constexpr uint8_t MIX_NO_ITEM = 0xFF;
 struct MixPlan {
     uint32_t count[MIX_GROUPS][4];
     uint32_t start[MIX_GROUPS][4];
-    uint32_t cta0[MIX_GROUPS][5];  // frame kernel: first CTA of bucket (g, lm) inside group g's launch; [4] = CTAs in use
+    uint32_t cta0[MIX_GROUPS][5];  // frame kernel: first CTA of group g's j-th bucket (lm = 3 - j: longest frames first); [4] = CTAs in use
     uint32_t items_padded;         // items up to the end of the last bucket
 };
 __host__ __device__ constexpr uint32_t mix_item_cap(uint32_t n_streams) { return n_streams + MIX_GROUPS * 4u * MIX_PAD; }
@@ -137,6 +137,8 @@ cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st);
 // mixed-frame step: bucketing (two kernels on one stream) and the frame kernel of one group (a.plan, a.group; grid sized by the
 // caller's upper bound n_streams_in_group)
 cudaError_t launch_mix_plan(const MixArgs &a, cudaStream_t st);
+cudaError_t launch_op_smooth_fade(const float *in1, const float *in2, float *out, size_t row_stride, int overlap, int channels, int fs,
+                                  uint32_t n_rows, cudaStream_t st);
 int kernels_frame_groups();  // OPN_FRAME_GROUPS the kernels were built with
 cudaError_t launch_frame_mix(const FrameArgs &a, uint32_t n_streams_in_group, cudaStream_t st);
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,

@@ -323,8 +323,7 @@ cudaError_t launch_celt2_rangedec(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
     if (!a.parts || !a.hdr) return cudaErrorInvalidValue;
-    constexpr uint32_t per_cta = RANGEDEC_WARPS_PER_CTA * 32u;
-    k_celt2_rangedec<<<(a.n_items + per_cta - 1u) / per_cta, per_cta, 0, st>>>(a);
+    k_celt2_rangedec<<<(a.n_items + C2_RD_ITEMS_PER_CTA - 1u) / C2_RD_ITEMS_PER_CTA, RANGEDEC_WARPS_PER_CTA * 32u, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -485,6 +484,16 @@ cudaError_t launch_op_soft_clip(float *pcm, size_t row_stride, size_t row_len, i
     if (n_rows == 0 || channels <= 0) return cudaSuccess;
     const uint32_t total = n_rows * (uint32_t)channels;
     k_op_soft_clip<<<(total + 63) / 64, 64, 0, st>>>(pcm, row_stride, row_len, channels, n_rows, mem);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_op_smooth_fade(const float *in1, const float *in2, float *out, size_t row_stride, int overlap, int channels, int fs,
+                                  uint32_t n_rows, cudaStream_t st)
+{
+    if (n_rows == 0 || overlap <= 0) return cudaSuccess;
+    if (channels < 1 || fs <= 0 || 48000 % fs != 0 || (overlap - 1) * (48000 / fs) >= 120) return cudaErrorInvalidValue;
+    const dim3 grid((uint32_t)(overlap * channels + 127) / 128, n_rows);
+    k_op_smooth_fade<<<grid, 128, 0, st>>>(in1, in2, out, row_stride, overlap, channels, 48000 / fs);
     return cudaGetLastError();
 }
 

@@ -152,4 +152,18 @@ k_softclip_convert(const float *__restrict__ dense, size_t dense_stride, const i
     }
 }
 
+// smooth_fade_into_in1 / smooth_fade_into_in2, src/decoder.rs:833-865: the cross-fade of a mode transition,
+// out = w^2 * in2 + (1 - w^2) * in1 over the first `overlap` samples of interleaved rows, w = WINDOW[i * 48000 / fs].
+// `out` may be in1 or in2 (the crate's two in-place forms).  One thread per sample of a row, one row per blockIdx.y.
+__global__ void __launch_bounds__(128) k_op_smooth_fade(const float *in1, const float *in2, float *out, size_t row_stride, int overlap,
+                                                         int channels, int inc)
+{
+    const int j = blockIdx.x * 128 + threadIdx.x;  // interleaved index: sample i = j / channels
+    if (j >= overlap * channels) return;
+    const size_t at = (size_t)blockIdx.y * row_stride + (size_t)j;
+    const float wv = g_tab.window[(j / channels) * inc];
+    const float w = wv * wv;
+    out[at] = (w * in2[at]) + ((1.0f - w) * in1[at]);
+}
+
 }  // namespace opn

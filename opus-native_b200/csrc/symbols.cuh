@@ -550,14 +550,27 @@ __device__ __forceinline__ Celt2Tabs device_celt2_tabs()
                      g_tab.pvq_u_data, g_tab.pvq_u_row};
 }
 
-__global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_celt2_rangedec(SymbolArgs A)
+// The frame logic of SYNTH-CELT/2 branches on the packet's content at every band (allocation searches, split recursion): the
+// lanes of a warp each follow their own path and the warp executes the union of them.  C2_RD_LANES packets per warp
+// (lanes 0 .. C2_RD_LANES-1; the others idle) trades idle lanes -- the kernel is latency-bound on a few hundred warps, the
+// SMs have the room -- for a shorter union.  128 registers (16 warps per SM) so that its warps fit beside resident frame-kernel CTAs.
+#ifndef OPN_C2_RD_MIN_CTAS
+#define OPN_C2_RD_MIN_CTAS 16
+#endif
+#ifndef OPN_C2_RD_LANES
+#define OPN_C2_RD_LANES 32
+#endif
+constexpr uint32_t C2_RD_LANES = OPN_C2_RD_LANES;
+constexpr uint32_t C2_RD_ITEMS_PER_CTA = RANGEDEC_WARPS_PER_CTA * C2_RD_LANES;
+static_assert(32u % C2_RD_LANES == 0u, "a mixed-frame bucket starts on a multiple of MIX_PAD items: a CTA must not span two");
+__global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32, OPN_C2_RD_MIN_CTAS) k_celt2_rangedec(SymbolArgs A)
 {
     __shared__ uint32_t s_lfl[21][LAP_N + 1], s_lfs[21][LAP_N + 1];
     const uint32_t lane = threadIdx.x;
     const int C = A.channels;
     int lm = A.lm;
     if (A.item_lm) {  // mixed-frame step, as in k_synth_rangedec
-        const uint32_t l = A.item_lm[blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u)];
+        const uint32_t l = A.item_lm[blockIdx.x * C2_RD_ITEMS_PER_CTA];
         if (l == MIX_NO_ITEM) return;
         lm = (int)l;
     }
@@ -567,7 +580,8 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32) k_celt2_rangedec(
         laplace_table(fs0, decay, s_lfl[lane], s_lfs[lane]);
     }
     __syncthreads();
-    const uint32_t item = blockIdx.x * (RANGEDEC_WARPS_PER_CTA * 32u) + lane;
+    if ((lane & 31u) >= C2_RD_LANES) return;
+    const uint32_t item = blockIdx.x * C2_RD_ITEMS_PER_CTA + (lane >> 5) * C2_RD_LANES + (lane & 31u);
     if (item >= A.n_items) return;
     if (A.item_lm && A.item_lm[item] == MIX_NO_ITEM) return;
     const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;

@@ -467,6 +467,26 @@ def test_celt2_batch_decode_chain(lm, channels, pkt_bytes):
             assert_pcm(want, pcm[s], (f, s))
 
 
+@pytest.mark.parametrize("channels,fs", [(1, 48000), (2, 48000), (2, 24000), (1, 16000), (2, 8000)])
+def test_smooth_fade(channels, fs):
+    """smooth_fade_into_in1 / _in2 (decoder.rs:833-865), the cross-fade of a mode transition: rows of interleaved samples
+    against orc_smooth_fade, bit for bit; overlap = 2.5 ms at the decoder's rate (decoder.rs:731-788), samples after it
+    untouched."""
+    rnd = np.random.default_rng(channels * 7 + fs)
+    rows, overlap = 37, fs // 400
+    n = overlap * channels + 11
+    in1 = (rnd.standard_normal((rows, n)) * 0.7).astype(np.float32)
+    in2 = (rnd.standard_normal((rows, n)) * 0.7).astype(np.float32)
+    got = opn.op_smooth_fade(in1, in2, overlap, channels, fs)
+    want = in1.copy()
+    for r in range(rows):
+        O.lib().orc_smooth_fade(O.ptr(in1[r]), O.ptr(in2[r]), O.ptr(want[r]), overlap, channels, fs)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[:, overlap * channels:], in1[:, overlap * channels:])
+    with pytest.raises(opn.OpusError):
+        opn.op_smooth_fade(in1, in2, overlap, channels, 44100)
+
+
 def test_bitexact_trig_checksums():
     """bitexact_cos / bitexact_log2tan on the device against the reference's own checksums
     (src/math.rs:237-298) and, value by value, against the oracle."""
