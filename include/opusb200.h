@@ -242,6 +242,7 @@ typedef struct {
     int32_t spread, alloc_trim, coded_bands, intensity, dual_stereo, anti_collapse, balance;
     int32_t offsets[21], pulses[21], ebits[21], fine_priority[21]; /* band boosts; compute_allocation's outputs */
     int32_t coarse[2][21], fine[2][21], fine_final[2][21];
+    int32_t energy_q9[2][21]; /* band energy = log2 of the band's gain, in 1/512: coarse + fine + final refinement */
     uint32_t n_parts, n_pulses, n_splits, theta_sum;
     uint32_t final_rng, tell_frac;
 } opn_celt2_side;

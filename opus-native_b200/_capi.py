@@ -26,7 +26,7 @@ SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "
 CELT2_SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra",
                                                   "spread", "alloc_trim", "coded_bands", "intensity", "dual_stereo", "anti_collapse", "balance")]
                             + [(n, "<i4", (21,)) for n in ("offsets", "pulses", "ebits", "fine_priority")]
-                            + [(n, "<i4", (2, 21)) for n in ("coarse", "fine", "fine_final")]
+                            + [(n, "<i4", (2, 21)) for n in ("coarse", "fine", "fine_final", "energy_q9")]
                             + [(n, "<u4") for n in ("n_parts", "n_pulses", "n_splits", "theta_sum", "final_rng", "tell_frac")])
 
 _ERR_NAMES = {-1: "BadArguments", -2: "BufferToSmall", -3: "InternalError", -4: "InvalidPacket",

@@ -32,12 +32,34 @@ struct Celt2Tabs {  // device: g_tab members; host: the OPN_* tables of opn_tabl
     const uint16_t *pvq_row;  // row offsets (pvc.rs:301-303)
 };
 
-struct Celt2Part {  // one PVQ leaf: coefficients [base, base+n) of the channel-major frame = cwrsi(n, k, index) * gain / sqrt(yy)
+// One PVQ leaf: coefficients [pos, pos+n) of the channel-major frame = (cwrsi(n, k, index) * (gain / sqrt(yy))) * band gain,
+// pos = base & C2_POS_MASK, band = base >> C2_BAND_SHIFT (the band gain is 2^(energy_q9[channel][band] / 512), c2_band_gain).
+constexpr int C2_BAND_SHIFT = 11, C2_POS_MASK = (1 << C2_BAND_SHIFT) - 1;
+struct Celt2Part {
     uint16_t base;
     uint8_t n, k;
     uint32_t index;
     float gain;
 };
+
+// Band energies (the unquant_coarse/fine/finalise steps of RFC 6716 4.3.2, without inter-frame prediction and mean
+// removal -- those tables are not in the reference): everything in Q9 (1/512 of a doubling), exact integers.
+//   coarse value q           -> clamp(q, -6, 2) * 512
+//   fine value v of fq bits  -> ((v + 1/2) 2^-fq - 1/2) * 512 = ((2v + 1) << (8 - fq)) - 256          (fq <= 8)
+//   final bit v after fq bits-> ((v - 1/2) 2^-(fq+1)) * 512   = (2v - 1) << (7 - fq)                   (fq <= 7)
+// 2^(e / 512) for a band energy e in Q9: table value of the fraction times an exact power of two (|e >> 9| <= 8)
+OPN_HD float c2_band_gain(const float *exp2_q9, int e)
+{
+    union {
+        uint32_t u;
+        float f;
+    } two;
+    two.u = (uint32_t)(127 + (e >> 9)) << 23;
+    return exp2_q9[e & 511] * two.f;
+}
+OPN_HD int c2_energy_coarse_q9(int32_t q) { return (q < -6 ? -6 : q > 2 ? 2 : q) * 512; }
+OPN_HD int c2_energy_fine_q9(uint32_t v, int fq) { return (int)(((2u * v + 1u) << (8 - fq))) - 256; }
+OPN_HD int c2_energy_final_q9(uint32_t v, int fq) { return (2 * (int)v - 1) * (1 << (7 - fq)); }
 
 OPN_HD int c2_min(int a, int b) { return a < b ? a : b; }
 OPN_HD int c2_max(int a, int b) { return a > b ? a : b; }
@@ -76,6 +98,7 @@ struct Celt2Side {
     int32_t spread, alloc_trim, coded_bands, intensity, dual_stereo, anti_collapse, balance;
     int32_t offsets[21], pulses[21], ebits[21], fine_priority[21];
     int32_t coarse[2][21], fine[2][21], fine_final[2][21];
+    int32_t energy_q9[2][21];  // band energy (log2 of the band's gain) in 1/512: coarse + fine + final refinement
     uint32_t n_parts, n_pulses, n_splits, theta_sum;
     uint32_t final_rng, tell_frac;
 };
@@ -377,7 +400,7 @@ OPN_HD void c2_quant_band(Coder &ec, const Celt2Tabs &T, Sink &out, C2Frame *st,
                 if (q != 0) {
                     const uint32_t K = c2_get_pulses((uint32_t)q);
                     const uint32_t index = ec.pulses_index(c2_pvq_v(T, (uint32_t)f.N, K));  // decode_pulses' decode_uint (pvc.rs:156-160)
-                    out.put_part(f.base, f.N, (int)K, index, f.gain);
+                    out.put_part(f.base | band << C2_BAND_SHIFT, f.N, (int)K, index, f.gain);
                 }
                 sp--;
             }
@@ -403,7 +426,8 @@ OPN_HD void c2_quant_band(Coder &ec, const Celt2Tabs &T, Sink &out, C2Frame *st,
 
 // One frame.  `len` = payload bytes.  Coder: tell(), tell_frac(), final_rng(), bit_logp(logp, p1_permille),
 // icdf(tab, ftb, n_sym), uint_(ft), bits(n), laplace(band), theta_tri(qn), pulses_index(ft), transient_permille().
-// Sink: put_part(base, n, k, index, gain), put_sign(base, sign).  sd may be null (device batch path).
+// Sink: put_part(base | band << C2_BAND_SHIFT, n, k, index, gain), put_sign(base | band << C2_BAND_SHIFT, sign),
+// energy_set / energy_add / energy (c, band, Q9).  sd may be null (device batch path).
 template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt2Tabs &T, uint32_t len, int LM, int C, Celt2Side *sd, Sink &out,
                                                            uint32_t &hdr_flags, uint32_t &n_pulses_out)
 {
@@ -445,6 +469,7 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
         for (int c = 0; c < C; c++) {
             const int32_t v = ec.laplace(b);
             if (sd) sd->coarse[c][b] = v;
+            out.energy_set(c, b, c2_energy_coarse_q9(v));
         }
     const uint32_t spread = ec.icdf(spread_icdf, 5, 4);
     if (sd) sd->spread = (int32_t)spread;
@@ -501,6 +526,7 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
             for (int c = 0; c < C; c++) {
                 const uint32_t v = ec.bits((uint32_t)ebits[i]);
                 if (sd) sd->fine[c][i] = (int32_t)v;
+                out.energy_add(c, i, c2_energy_fine_q9(v, ebits[i]));
             }
     C2Frame frames[C2_MAX_DEPTH];
     {
@@ -523,7 +549,7 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
                         sign = ec.bits(1);
                         remaining_bits -= 1 << C2_BITRES;
                     }
-                    out.put_sign(c * nf + base, sign);
+                    out.put_sign((c * nf + base) | i << C2_BAND_SHIFT, sign);
                     n_pulses += 1;
                 } else {
                     c2_quant_band(ec, T, out, frames, i, c * nf + base, N, b / C, Bframe, LM, remaining_bits, n_splits, theta_sum);
@@ -543,12 +569,15 @@ template <class Coder, class Sink> OPN_HD void celt2_frame(Coder &ec, const Celt
                 for (int c = 0; c < C; c++) {
                     const uint32_t v = ec.bits(1);
                     if (sd) sd->fine_final[c][i] = 1 + (int32_t)v;
+                    out.energy_add(c, i, c2_energy_final_q9(v, ebits[i]));
                     bits_left--;
                 }
             }
     }
     n_pulses_out = n_pulses + out.pulses();
     if (sd) {
+        for (int c = 0; c < C; c++)
+            for (int i = 0; i < C2_NBANDS; i++) sd->energy_q9[c][i] = out.energy(c, i);
         sd->n_splits = n_splits;
         sd->theta_sum = theta_sum;
 #ifdef OPN_C2_DEBUG

@@ -42,6 +42,11 @@ struct LaneCoder {  // the Coder of celt2_frame on top of LaneDec
 struct LanePartSink {
     Celt2Part *parts;
     uint32_t n, np, nsign;
+    int16_t *e9;         // band energies of this packet, Q9: e9[(c * 21 + band) * e9_stride] (shared memory, one column per lane)
+    uint32_t e9_stride;
+    __device__ __forceinline__ void energy_set(int c, int band, int v) { e9[(uint32_t)(c * 21 + band) * e9_stride] = (int16_t)v; }
+    __device__ __forceinline__ void energy_add(int c, int band, int v) { e9[(uint32_t)(c * 21 + band) * e9_stride] += (int16_t)v; }
+    __device__ __forceinline__ int energy(int c, int band) const { return e9[(uint32_t)(c * 21 + band) * e9_stride]; }
     __device__ __forceinline__ void put_part(int base, int nn, int k, uint32_t index, float gain)
     {
         if (n < (uint32_t)CELT2_MAX_PARTS) parts[n] = Celt2Part{(uint16_t)base, (uint8_t)nn, (uint8_t)k, index, gain};

@@ -307,7 +307,7 @@ template <int LM, int C, int MODE> __device__ __forceinline__ void frame_cta(con
         if (!lost && !(hdr_x & 1u)) {
             // part shapes are only known per frame: the walk uses the full PVQ tables in global memory (L1/L2 resident)
             const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
-            w_expand2<C>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, o, CHF, nullptr);
+            w_expand2<C>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, A.bande + (size_t)stream * 42, o, CHF, nullptr);
         }
         __syncwarp();
     } else {

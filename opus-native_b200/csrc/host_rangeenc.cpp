@@ -416,6 +416,10 @@ struct GenCoder {
 };
 struct CountSink {
     uint32_t n = 0, np = 0;
+    int e9[2][21] = {};
+    void energy_set(int c, int band, int v) { e9[c][band] = v; }
+    void energy_add(int c, int band, int v) { e9[c][band] += v; }
+    int energy(int c, int band) const { return e9[c][band]; }
     void put_part(int, int, int k, uint32_t, float) { n++; np += (uint32_t)k; }
     uint32_t nsign = 0;
     void put_sign(int, uint32_t) { nsign++; }  // one-bin bands are not PVQ leaves, but the decoder's list holds them too

@@ -167,6 +167,7 @@ struct opn_batch {
     uint4 *d_hdr[NSETS] = {};
     int32_t *d_status[NSETS] = {};
     Celt2Part *d_parts[NSETS] = {};  // SYNTH-CELT/2 batches only: PVQ leaves per stream
+    int16_t *d_bande[NSETS] = {};    // SYNTH-CELT/2 batches only: band energies per stream, Q9 [2][21]
     // host-path staging (device + pinned host)
     // Two staging slots, so a host-buffer call can be submitted while the previous one is still downloading.
     struct Staging {
@@ -366,6 +367,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.idx = b->d_idx[p];
     s.pkt_cap = pkt_cap;
     s.parts = b->d_parts[p];
+    s.bande = b->d_bande[p];
     s.side2 = nullptr;
     const bool celt2 = b->cfg.bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
     int rc;
@@ -411,6 +413,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.coef = b->unfused ? b->d_coef[p] : nullptr;
     m.idx = celt2 ? nullptr : b->d_idx[p];
     m.parts = celt2 ? b->d_parts[p] : nullptr;
+    m.bande = b->d_bande[p];
     m.hdr = b->d_hdr[p];
     m.status = b->d_status[p];
     m.stream_idx = d_stream_idx;
@@ -537,10 +540,12 @@ int run_mixed(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, c
     s.idx = b->d_idx[p];
     s.pkt_cap = 1280u;
     s.parts = b->d_parts[p];
+    s.bande = b->d_bande[p];
     const bool celt2 = b->cfg.bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
     FrameArgs m{};
     m.idx = celt2 ? nullptr : b->d_idx[p];
     m.parts = celt2 ? b->d_parts[p] : nullptr;
+    m.bande = b->d_bande[p];
     m.hdr = b->d_hdr[p];
     m.status = b->d_status[p];
     m.stream_idx = x.item_stream;
@@ -743,6 +748,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         if (e == cudaSuccess && b->unfused) e = cudaMalloc(&b->d_coef[q], n * C * 960 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_hdr[q], n * sizeof(uint4));
         if (e == cudaSuccess && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_parts[q], n * CELT2_MAX_PARTS * sizeof(Celt2Part));
+        if (e == cudaSuccess && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_bande[q], n * 42 * sizeof(int16_t));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
@@ -804,6 +810,7 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(b->d_coef[q]);
         cudaFree(b->d_hdr[q]);
         cudaFree(b->d_parts[q]);
+        cudaFree(b->d_bande[q]);
         cudaFree(b->d_status[q]);
     }
     if (b->ev_in) cudaEventDestroy(b->ev_in);
@@ -1610,7 +1617,8 @@ int opn_op_celt2_symbols(int device, const uint8_t *arena, const uint32_t *offse
     size_t arena_end = 0;
     for (uint32_t i = 0; i < n_packets; i++) arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
     const size_t row = (size_t)channels * (120u << lm);
-    DevBuf dA, dO, dL, dS, dSt, dY, dC, dH, dP;
+    DevBuf dA, dO, dL, dS, dSt, dY, dC, dH, dP, dE;
+    CU(dE.alloc((size_t)n_packets * 42 * sizeof(int16_t)));
     CU(dA.alloc(arena_end + 8));
     CU(dO.alloc(n_packets * 4));
     CU(dL.alloc(n_packets * 4));
@@ -1639,6 +1647,7 @@ int opn_op_celt2_symbols(int device, const uint8_t *arena, const uint32_t *offse
     s.y_out = dY.as<int32_t>();
     s.parts = dP.as<Celt2Part>();
     s.side2 = dS.as<Celt2Side>();
+    s.bande = dE.as<int16_t>();
     CU(launch_celt2_rangedec(s, nullptr));
     CU(launch_celt2_expand(s, nullptr));
     CU(cudaDeviceSynchronize());

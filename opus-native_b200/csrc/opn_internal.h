@@ -78,6 +78,7 @@ struct SymbolArgs {
     uint32_t pkt_cap;            // bytes of shared memory per warp for the packet
     struct Celt2Part *parts;     // SYNTH-CELT/2: [n_streams][CELT2_MAX_PARTS] PVQ leaves (range decode -> expansion)
     struct Celt2Side *side2;     // SYNTH-CELT/2: [n_streams] or nullptr: full side record (tests)
+    int16_t *bande;              // SYNTH-CELT/2: [n_streams][2][21] band energies in Q9 (range decode -> expansion) or nullptr
     const uint8_t *item_lm;      // mixed-frame step: [n_items] LM of the item, MIX_NO_ITEM = padding (overrides lm); else nullptr
 };
 
@@ -103,6 +104,7 @@ struct FrameArgs {
     uint32_t *final_range;        // [n_streams]
     float *softclip_reset;        // [n_streams][2] or nullptr: cleared for every stream that decodes a packet (decoder.rs:420-423)
     unsigned long long *hist_samples;  // measurement (or nullptr): += max(T0,T1)+2 per channel-frame the post-filter runs on
+    const int16_t *bande;         // SYNTH-CELT/2: [n_streams][2][21] band energies in Q9 (range decode output)
     const MixPlan *plan;          // mixed-frame step (k_frame_mix): buckets of this step, else nullptr
     int group;                    // mixed-frame step: which group of the plan this launch covers
 };

@@ -264,6 +264,8 @@ cudaError_t upload_tables(int device)
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_fblob, blobs, sizeof(blobs));
     if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(g_exp2_q9, OPN_EXP2_Q9, sizeof(float) * 512);
+    if (e != cudaSuccess) return e;
     e = set_warp_kernel_attributes();
     if (e != cudaSuccess) return e;
     // kernel 1 needs more than the 48 KB default only if ever re-tiled; set the limits once here
@@ -322,7 +324,7 @@ cudaError_t launch_synth_expand(const SymbolArgs &a, cudaStream_t st)
 cudaError_t launch_celt2_rangedec(const SymbolArgs &a, cudaStream_t st)
 {
     if (a.n_items == 0) return cudaSuccess;
-    if (!a.parts || !a.hdr) return cudaErrorInvalidValue;
+    if (!a.parts || !a.hdr || !a.bande) return cudaErrorInvalidValue;
     k_celt2_rangedec<<<(a.n_items + C2_RD_ITEMS_PER_CTA - 1u) / C2_RD_ITEMS_PER_CTA, RANGEDEC_WARPS_PER_CTA * 32u, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -566,6 +566,7 @@ static_assert(32u % C2_RD_LANES == 0u, "a mixed-frame bucket starts on a multipl
 __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32, OPN_C2_RD_MIN_CTAS) k_celt2_rangedec(SymbolArgs A)
 {
     __shared__ uint32_t s_lfl[21][LAP_N + 1], s_lfs[21][LAP_N + 1];
+    __shared__ int16_t s_e9[2 * 21][RANGEDEC_WARPS_PER_CTA * 32];  // band energies, one column per packet
     const uint32_t lane = threadIdx.x;
     const int C = A.channels;
     int lm = A.lm;
@@ -612,9 +613,14 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32, OPN_C2_RD_MIN_CTA
     ec.lfl = s_lfl;
     ec.lfs = s_lfs;
     ec.d.init(src, len);
-    LanePartSink sink{A.parts + (size_t)stream * CELT2_MAX_PARTS, 0u, 0u, 0u};
+    LanePartSink sink{A.parts + (size_t)stream * CELT2_MAX_PARTS, 0u, 0u, 0u, &s_e9[0][lane], RANGEDEC_WARPS_PER_CTA * 32u};
+    for (int i = 0; i < 2 * 21; i++) s_e9[i][lane] = 0;
     uint32_t flags = 0u, n_pulses = 0u;
     celt2_frame(ec, device_celt2_tabs(), len, lm, C, sd, sink, flags, n_pulses);
+    if (A.bande) {
+        uint32_t *be = reinterpret_cast<uint32_t *>(A.bande + (size_t)stream * 42);
+        for (int i = 0; i < 21; i++) be[i] = (uint32_t)(uint16_t)s_e9[2 * i][lane] | (uint32_t)(uint16_t)s_e9[2 * i + 1][lane] << 16;
+    }
     const uint32_t tf = ec.d.tell_frac();
     if (sd) {
         sd->n_parts = sink.n - sink.nsign;  // PVQ leaves (the list also holds the one-bin bands)
@@ -630,18 +636,22 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32, OPN_C2_RD_MIN_CTA
 // Expansion of a SYNTH-CELT/2 part list by one warp: the leaves are dealt to the lanes round-robin; a lane walks its leaf
 // with cwrsi_events (any (n, K): the walk itself falls back where its 32-bit sums could wrap), writes the pulses as
 // floats and scales the leaf by gain / sqrt(yy) once the norm is known.  `rows` must be zero on entry.
+// `bande`: the packet's band energies (Q9, [2][21]).  denormalise_bands: the decoded band has unit norm (times the split
+// gains), its energy gives it its level -- every coefficient of band b, channel c is then multiplied by 2^(bande[c][b]/512).
 template <int C>
 __device__ __forceinline__ void w_expand2(const ExpandTables &T, int lm, uint32_t lane, const Celt2Part *__restrict__ parts, uint32_t n_parts,
-                                          float *rows, int chs, int32_t *__restrict__ y_out)
+                                          const int16_t *__restrict__ bande, float *rows, int chs, int32_t *__restrict__ y_out)
 {
     const int nf = 120 << lm;
     for (uint32_t p = lane; p < n_parts; p += 32u) {
         const Celt2Part P = parts[p];
-        const uint32_t ch = P.base >= (uint32_t)nf ? 1u : 0u;
-        float *dst = rows + P.base + ch * (uint32_t)(chs - nf);
-        int32_t *yo = y_out ? y_out + P.base : nullptr;
+        const uint32_t pos = P.base & (uint32_t)C2_POS_MASK, band = P.base >> C2_BAND_SHIFT;
+        const uint32_t ch = pos >= (uint32_t)nf ? 1u : 0u;
+        float *dst = rows + pos + ch * (uint32_t)(chs - nf);
+        int32_t *yo = y_out ? y_out + pos : nullptr;
+        const float bg = c2_band_gain(g_exp2_q9, (int)bande[ch * 21u + band]);
         if (P.n == 1u) {  // sign-only band
-            dst[0] = P.index ? -P.gain : P.gain;
+            dst[0] = (P.index ? -P.gain : P.gain) * bg;
             if (yo) yo[0] = P.index ? -1 : 1;
             continue;
         }
@@ -652,7 +662,7 @@ __device__ __forceinline__ void w_expand2(const ExpandTables &T, int lm, uint32_
         const float g = P.gain / sqrtf((float)yy);
         for (uint32_t j = 0; j < P.n; j++) {
             const float v = dst[j];
-            if (v != 0.0f) dst[j] = v * g;
+            if (v != 0.0f) dst[j] = (v * g) * bg;  // normalised coefficient, then the band's gain
         }
     }
 }
@@ -678,8 +688,8 @@ __global__ void __launch_bounds__(128) k_celt2_expand(SymbolArgs A)
     __syncwarp();
     if (status == ITEM_OK && !(hdr.x & 1u)) {
         const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
-        if (C == 2) w_expand2<2>(T, lm, lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, hdr.w, rows, nf, yo);
-        else w_expand2<1>(T, lm, lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, hdr.w, rows, nf, yo);
+        if (C == 2) w_expand2<2>(T, lm, lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, hdr.w, A.bande + (size_t)stream * 42, rows, nf, yo);
+        else w_expand2<1>(T, lm, lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, hdr.w, A.bande + (size_t)stream * 42, rows, nf, yo);
     }
     __syncwarp();
     if (A.coef) {

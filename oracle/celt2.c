@@ -355,6 +355,7 @@ typedef struct {
     orc_celt2_side *side;
     orc_celt2_part *parts;
     float *coef;   /* channel's row */
+    float *coef0;  /* channel 0's row (the part list records positions in the channel-major frame) */
     int32_t *y_out;
 } band_ctx;
 
@@ -458,7 +459,7 @@ static void quant_partition(band_ctx *ctx, int base, int N, int b, int B, int LM
     orc_celt2_side *sd = ctx->side;
     if (sd->n_parts < ORC_CELT2_MAX_PARTS) {
         orc_celt2_part *p = &ctx->parts[sd->n_parts];
-        p->base = (uint16_t)base;
+        p->base = (uint16_t)((base + (int)(ctx->coef - ctx->coef0)) | ctx->band << 11);
         p->n = (uint8_t)N;
         p->k = (uint8_t)K;
         p->index = index;
@@ -547,6 +548,7 @@ static int celt2_frame(coder *ec, uint32_t len, int LM, int C, orc_celt2_side *s
         ctx.transient_blocks = sd->transient ? M : 1;
         ctx.side = sd;
         ctx.parts = parts;
+        ctx.coef0 = coef;
         const int32_t band_total = (total_bits << BITRES) - anti_collapse_rsv;
         for (int i = 0; i < end; i++) {
             int32_t tell = (int32_t)c_tell_frac(ec);
@@ -594,6 +596,19 @@ static int celt2_frame(coder *ec, uint32_t len, int LM, int C, orc_celt2_side *s
                 }
             }
     }
+    /* band energies (unquant_coarse_energy without prediction, unquant_fine_energy, unquant_energy_finalise; RFC 6716 4.3.2)
+     * in 1/512 of a doubling, then denormalise_bands: every coefficient of the band times 2^energy */
+    for (int c = 0; c < C; c++)
+        for (int i = 0; i < end; i++) {
+            int q = sd->coarse[c][i];
+            int e = (q < -6 ? -6 : q > 2 ? 2 : q) * 512;
+            if (ebits[i] > 0) e += (int)((2u * (uint32_t)sd->fine[c][i] + 1u) << (8 - ebits[i])) - 256; /* (v + 1/2) 2^-fq - 1/2 */
+            if (sd->fine_final[c][i]) e += (2 * (sd->fine_final[c][i] - 1) - 1) * (1 << (7 - ebits[i]));   /* (v - 1/2) 2^-(fq+1) */
+            sd->energy_q9[c][i] = e;
+            const int fr = e & 511, ex = (e - fr) / 512;
+            const float g = ORC_EXP2_Q9[fr] * ldexpf(1.0f, ex);
+            for (int j = ORC_E_BANDS[i] << LM; j < ORC_E_BANDS[i + 1] << LM; j++) coef[c * nf + j] *= g;
+        }
 done:
     sd->tell_frac = c_tell_frac(ec);
     sd->final_rng = ec->d ? ec->d->rng : ec->e->rng;

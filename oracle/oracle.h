@@ -169,10 +169,13 @@ typedef struct {
     int32_t spread, alloc_trim, coded_bands, intensity, dual_stereo, anti_collapse, balance;
     int32_t offsets[21], pulses[21], ebits[21], fine_priority[21];
     int32_t coarse[2][21], fine[2][21], fine_final[2][21];
+    int32_t energy_q9[2][21]; /* band energy (log2 of the band's gain) in 1/512 */
     uint32_t n_parts, n_pulses, n_splits, theta_sum;
     uint32_t final_rng, tell_frac;
 } orc_celt2_side;
-typedef struct { /* one PVQ leaf: coefficients [base, base+n) of the channel-major frame = cwrsi(n, k, index) * gain / sqrt(yy) */
+/* one PVQ leaf: normalised coefficients [pos, pos+n) of the channel-major frame = cwrsi(n, k, index) * gain / sqrt(yy);
+ * base = pos | band << 11 */
+typedef struct {
     uint16_t base;
     uint8_t n, k;
     uint32_t index;

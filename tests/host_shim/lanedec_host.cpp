@@ -88,7 +88,8 @@ extern "C" int lanedec_celt2_decode(const uint8_t *payload, uint32_t len, int lm
     ec.lfl = lfl;
     ec.lfs = lfs;
     ec.d.init(payload, len);
-    LanePartSink sink{parts, 0u, 0u, 0u};
+    int16_t e9[2 * 21] = {};
+    LanePartSink sink{parts, 0u, 0u, 0u, e9, 1u};
     uint32_t flags = 0, n_pulses = 0;
     celt2_frame(ec, T, len, lm, channels, side, sink, flags, n_pulses);
     side->n_parts = sink.n - sink.nsign;

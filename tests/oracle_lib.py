@@ -41,7 +41,7 @@ class Celt2Side(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("silence", "postfilter", "octave", "period", "gain_idx", "tapset", "transient", "intra",
                                           "spread", "alloc_trim", "coded_bands", "intensity", "dual_stereo", "anti_collapse", "balance")] + [
         (n, C.c_int32 * 21) for n in ("offsets", "pulses", "ebits", "fine_priority")] + [
-        (n, (C.c_int32 * 21) * 2) for n in ("coarse", "fine", "fine_final")] + [
+        (n, (C.c_int32 * 21) * 2) for n in ("coarse", "fine", "fine_final", "energy_q9")] + [
         (n, C.c_uint32) for n in ("n_parts", "n_pulses", "n_splits", "theta_sum", "final_rng", "tell_frac")]
 
 

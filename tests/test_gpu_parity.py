@@ -762,8 +762,8 @@ def test_batch_device_resident_path_matches_host_path():
     assert ring_n == 2880 and ring_ptr and pos_ptr  # 3 x 960: a frame plus the 1024 + 2 samples of history before it
 
 
-@pytest.mark.parametrize("ns,channels", [(2300, 2), (300, 1)])
-def test_batch_device_resident_mixed_frame_sizes(ns, channels):
+@pytest.mark.parametrize("ns,channels,bitstream", [(2300, 2, 1), (300, 1, 1), (500, 2, 2)])
+def test_batch_device_resident_mixed_frame_sizes(ns, channels, bitstream):
     """OPN_FLAG_MIXED_FRAMES: a device-resident step whose streams hold frames of different sizes.  Every stream picks a
     new frame size for every packet (2.5/5/10/20 ms, weights 10/10/30/50 %; 10 % transient frames), 3 % of the packets
     are lost (concealed with one frame of the stream's previous size), a few carry a foreign TOC.  The buckets are built
@@ -774,7 +774,17 @@ def test_batch_device_resident_mixed_frame_sizes(ns, channels):
     rnd = np.random.default_rng(11 + ns)
     nsteps, stride, cap = 10, 160, 960
     pkt_bytes = {0: 64, 1: 80, 2: 110, 3: 160}
-    oracle = [O.SynthStream(3, channels) for _ in range(ns)]
+    fill = opn.synth_fill if bitstream == 1 else opn.celt2_fill
+    oracle = [(O.SynthStream if bitstream == 1 else O.Celt2Stream)(3, channels) for _ in range(ns)]
+
+    def oracle_decode(s, payload):  # -> (final_rng, pcm)
+        if bitstream == 1:
+            side, _, _, pcm = oracle[s].decode(payload)
+        else:
+            side, pcm = oracle[s].decode(payload)
+            assert pcm is not None
+        return side.final_rng, pcm
+
     arena = np.zeros((nsteps, ns, stride), np.uint8)
     lens = np.zeros((nsteps, ns), np.uint32)
     lm_of = np.zeros((nsteps, ns), np.int64)
@@ -785,7 +795,7 @@ def test_batch_device_resident_mixed_frame_sizes(ns, channels):
             ids = np.nonzero(lm_of[f] == lm)[0]
             if len(ids) == 0:
                 continue
-            pk = opn.synth_fill(4000 + lm, len(ids), f, 1, lm, channels, pkt_bytes[lm], transient_permille=100)[0]
+            pk = fill(4000 + lm, len(ids), f, 1, lm, channels, pkt_bytes[lm], transient_permille=100)[0]
             arena[f, ids, :pkt_bytes[lm]] = pk
             lens[f, ids] = pkt_bytes[lm]
         if f > 0:
@@ -802,7 +812,7 @@ def test_batch_device_resident_mixed_frame_sizes(ns, channels):
     d_pcm = torch.zeros((nsteps, ns, cap * channels), dtype=torch.float32, device=dev)
     d_res = torch.full((nsteps, ns), -99, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
-    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **SYNTH)
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **(SYNTH if bitstream == 1 else CELT2))
     flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY | opn.FLAG_MIXED_FRAMES
     for f in range(nsteps):
         dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * stride, d_off.data_ptr(), d_len[f].data_ptr(), d_pcm[f].data_ptr(),
@@ -821,14 +831,13 @@ def test_batch_device_resident_mixed_frame_sizes(ns, channels):
             if lens[f, s] == 0:
                 lm = last_lm[s] if last_lm[s] >= 0 else 3  # nothing decoded yet: zeros of the row's capacity (decoder.rs:473-484)
                 oracle[s].lm = int(lm)
-                want = oracle[s].decode(b"")[3]
+                _, want = oracle_decode(s, b"")
                 last_rng[s] = 0
             else:
                 lm = lm_of[f, s]
                 oracle[s].lm = int(lm)
-                side, _, _, want = oracle[s].decode(arena[f, s, 1:int(lens[f, s])])
+                last_rng[s], want = oracle_decode(s, arena[f, s, 1:int(lens[f, s])])
                 last_lm[s] = lm
-                last_rng[s] = side.final_rng
             nf = 120 << int(lm)
             assert res[f, s] == nf, (f, s, res[f, s], nf)
             assert np.array_equal(got[f, s, :nf * channels], want), (f, s, lm)

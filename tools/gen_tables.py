@@ -323,6 +323,9 @@ def emit(path, prefix, guard):
         w("  {" + ", ".join("{%d,%d,%d}" % t for t in row) + "},")
     w("};\n")
     arr("float", "COMB_GAINS", [f32(g / 32768.0) for g in COMB_GAINS_Q15], fhex, 3)
+    w("/* 2^(j/512), j = 0..511, rounded to f32: the fractional part of a band energy (SYNTH-CELT/2 denormalisation); */")
+    w("/* the crate's fast_exp2 (src/math.rs:17-19) goes through libm's exp, which no two platforms round alike */")
+    arr("float", "EXP2_Q9", [f32(2.0 ** (j / 512.0)) for j in range(512)], fhex, 6)
     w(f"#endif /* {guard} */")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
