@@ -113,7 +113,8 @@ typedef struct {
 /* OPN_BITSTREAM_SYNTH_CELT_2: the allocation-driven layout of DESIGN.md section 3b -- band boosts, allocation trim,
  * compute_allocation from the mode's tables (src/celt/mode.rs:13-28, 70-111) driven by the running tell_frac, fine-energy
  * bits, and per band a theta split (bitexact_cos / bitexact_log2tan, src/math.rs:51-75) down to PVQ leaves whose (n, K) are
- * computed per frame on the device.  A slice of a real CELT frame (no tf, spreading, folding, joint stereo, energies):
+ * computed per frame on the device; the band energies (coarse + fine + final bits) scale the decoded bands
+ * (denormalise_bands).  A slice of a real CELT frame (no tf, spreading, folding, joint stereo, energy prediction):
  * closer to RFC 6716 section 4.3 than SYNTH-CELT/1, still NOT Opus-interoperable, and parity-unpinned like it. */
 #define OPN_BITSTREAM_SYNTH_CELT_2 2
 
@@ -137,7 +138,11 @@ int opn_batch_reset(opn_batch *b);
 /* One packet per stream (lens[i] == 0: lost).  Every stream i decodes packet
  * arena[offsets[i] .. offsets[i]+lens[i]) into pcm[i*pcm_stride_floats ..] (interleaved).
  * result_per_stream[i] = samples per channel or a negative error for that stream only: a bad
- * packet never poisons its neighbours.  Semantics per stream = Decoder::decode_float. */
+ * packet never poisons its neighbours.  Semantics per stream = Decoder::decode_float.
+ * Host-buffer calls take any mix of frame sizes, multi-frame packets and packets whose channel count differs from the
+ * batch's (stream_channels, decoder.rs:332: a mono packet fills both channels of a stereo decoder, a stereo packet is
+ * averaged into a mono decoder).  Device-resident calls (OPN_FLAG_DEVICE_PTRS) take single-frame packets of the batch's
+ * channel count: all of frame_size samples, or of any size with OPN_FLAG_MIXED_FRAMES. */
 int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *offsets,
                            const uint32_t *lens, float *pcm, size_t pcm_stride_floats,
                            size_t frame_size, int32_t *result_per_stream, uint32_t flags);

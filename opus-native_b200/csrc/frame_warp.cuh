@@ -225,23 +225,31 @@ __host__ __device__ constexpr size_t frame_smem_bytes(int lm, int channels, size
 // the codeword indices of the static SYNTH-CELT/1 schedule; FRAME_SYNTH2: expanded from the per-frame part list of SYNTH-CELT/2.
 enum { FRAME_ROWS = 0, FRAME_SYNTH1 = 1, FRAME_SYNTH2 = 2 };
 // One CTA of the frame kernel: its FRAME_WARPS warps take the items first_item .. first_item + FRAME_WARPS - 1 (< item_end).
-template <int LM, int C, int MODE> __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_item, uint32_t item_end)
+// CS: channels of the PACKETS (the crate's stream_channels, decoder.rs:332,376,395), C: channels of the decoder.  They
+// differ when a mono packet reaches a stereo decoder or the reverse; the frame is then expanded with the packet's layout
+// into max(C, CS) rows and mapped onto the decoder's channels before the transform, as libopus' celt_synthesis does:
+// mono -> stereo copies the spectrum (each output channel keeps its own overlap and post-filter history), stereo ->
+// mono averages the two spectra, 0.5 * (l + r).
+template <int LM, int C, int MODE, int CS = C>
+__device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_item, uint32_t item_end)
 {
     constexpr bool EXPAND = MODE != FRAME_ROWS;
+    constexpr int R = C > CS ? C : CS;  // rows of shared memory per stream
+    static_assert(EXPAND || CS == C, "coefficient rows from memory are the decoder's channels already");
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int NF = 120 << LM;
     constexpr int CHF = w_ch_floats(LM);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t *tbar = reinterpret_cast<uint64_t *>(smem);
     const uint8_t *blob = smem + 16;
-    const FBlobHdr H = g_tab.fblob_hdr[LM][C - 1];
-    float *o = reinterpret_cast<float *>(smem + 16 + H.total + (size_t)warp * frame_warp_bytes(LM, C));
-    uint64_t *bar = reinterpret_cast<uint64_t *>(o + C * CHF);  // this warp's barrier (coefficient rows by TMA, unfused variant)
+    const FBlobHdr H = g_tab.fblob_hdr[LM][CS - 1];  // the schedule's tables are the packet layout's; the transform's are the same in both
+    float *o = reinterpret_cast<float *>(smem + 16 + H.total + (size_t)warp * frame_warp_bytes(LM, R));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(o + R * CHF);  // this warp's barrier (coefficient rows by TMA, unfused variant)
 
     if (threadIdx.x == 0) {
         mbar_init(tbar, 1);
         mbar_expect_tx(tbar, H.total);
-        bulk_g2s(smem + 16, g_fblob[LM][C - 1], H.total, tbar);
+        bulk_g2s(smem + 16, g_fblob[LM][CS - 1], H.total, tbar);
     }
     const uint32_t item = first_item + warp;
     const bool in_range = item < item_end;
@@ -279,7 +287,7 @@ template <int LM, int C, int MODE> __device__ __forceinline__ void frame_cta(con
     if constexpr (EXPAND) {
         // the coefficient rows start out zero: w_expand only writes the pulses
 #pragma unroll
-        for (int c = 0; c < C; c++)
+        for (int c = 0; c < R; c++)
             for (int i = lane; i < NF / 4; i += 32) reinterpret_cast<float4 *>(o + c * CHF)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();  // the table barrier is initialised
@@ -300,18 +308,28 @@ template <int LM, int C, int MODE> __device__ __forceinline__ void frame_cta(con
             const ExpandTables T{reinterpret_cast<const uint32_t *>(blob + H.pvq_u), reinterpret_cast<const uint2 *>(blob + H.pvq_cw),
                                  reinterpret_cast<const uint16_t *>(blob + H.pvq_row), blob + H.pvq_nmax,
                                  reinterpret_cast<const SynthEntry *>(blob + H.ent), blob + H.slots, (int)H.n_slots};
-            w_expand<C>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr);
+            w_expand<CS>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr);
         }
         __syncwarp();
     } else if constexpr (MODE == FRAME_SYNTH2) {
         if (!lost && !(hdr_x & 1u)) {
             // part shapes are only known per frame: the walk uses the full PVQ tables in global memory (L1/L2 resident)
             const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
-            w_expand2<C>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, A.bande + (size_t)stream * 42, o, CHF, nullptr);
+            w_expand2<CS>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, A.bande + (size_t)stream * 42, o, CHF, nullptr);
         }
         __syncwarp();
     } else {
         mbar_wait(bar, 0);
+    }
+    if constexpr (CS == 1 && C == 2) {  // mono packet, stereo decoder: both channels transform the same spectrum
+        for (int i = lane; i < NF / 4; i += 32) reinterpret_cast<float4 *>(o + CHF)[i] = reinterpret_cast<const float4 *>(o)[i];
+        __syncwarp();
+    } else if constexpr (CS == 2 && C == 1) {  // stereo packet, mono decoder: 0.5 * (l + r)
+        for (int i = lane; i < NF / 4; i += 32) {
+            const float4 a = reinterpret_cast<const float4 *>(o)[i], b = reinterpret_cast<const float4 *>(o + CHF)[i];
+            reinterpret_cast<float4 *>(o)[i] = make_float4(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z), 0.5f * (a.w + b.w));
+        }
+        __syncwarp();
     }
     if constexpr (LM > 0) {
         if ((hdr_x >> 2) & 1u) w_imdct<3, (1 << LM), C, true>(o, lane, carry, t_short, t_tw, t_win);
@@ -388,9 +406,9 @@ template <int LM, int C, int MODE> __device__ __forceinline__ void frame_cta(con
     }
 }
 
-template <int LM, int C, int MODE> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
+template <int LM, int C, int MODE, int CS = C> __global__ void __launch_bounds__(32 * FRAME_WARPS, FRAME_CTAS) k_frame_w(FrameArgs A)
 {
-    frame_cta<LM, C, MODE>(A, A.item0 + blockIdx.x * FRAME_WARPS, A.item_end);
+    frame_cta<LM, C, MODE, CS>(A, A.item0 + blockIdx.x * FRAME_WARPS, A.item_end);
 }
 
 // The frame kernel of a step whose streams have different frame sizes: one launch per group of the step's MixPlan; a

@@ -109,6 +109,7 @@ struct EventRing {
 struct Item {
     uint32_t stream, offset, len, dense_off;
     int lm, wave;
+    int cs;  // channels of the packet (stream_channels, decoder.rs:332); concealed frames: the decoder's
 };
 
 }  // namespace
@@ -344,9 +345,12 @@ int sync_pipeline(opn_batch *b)
 // softclip_reset: a float call clears the soft-clip memory of every stream that decodes a packet (decoder.rs:420-423).
 int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens,
                const uint32_t *d_stream_idx, const uint32_t *d_dense_off, uint32_t n_items, int lm, int has_toc,
-               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
+               uint32_t pkt_cap, float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset,
+               int stream_channels = 0)
 {
     Range nv("opn: step (range decode + frame kernel)");
+    if (stream_channels == 0) stream_channels = b->cfg.channels;
+    if (stream_channels != b->cfg.channels && b->unfused) return OPN_ERR_UNIMPLEMENTED;  // the measurement variant maps nothing
     const int p = b->set;
     b->set = (p + 1) % opn_batch::NSETS;
     cudaStream_t srd = b->stream_rd[p % opn_batch::NRD];
@@ -357,7 +361,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     s.stream_idx = d_stream_idx;
     s.n_items = n_items;
     s.lm = lm;
-    s.channels = b->cfg.channels;
+    s.channels = stream_channels;  // the range decode follows the packets' layout
     s.has_toc = has_toc;
     s.side = nullptr;
     s.hdr = b->d_hdr[p];
@@ -423,6 +427,7 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     m.item_end = n_items;
     m.lm = lm;
     m.channels = b->cfg.channels;
+    m.stream_channels = stream_channels;
     m.postfilter = b->cfg.postfilter;
     m.carry = b->d_carry;
     m.ring = b->d_ring;
@@ -946,7 +951,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 uint32_t at = 0;
                 int w = 0;
                 for (uint32_t a : plc) {
-                    items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++});
+                    items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++, C});
                     at += a;
                 }
                 res[i] = (int32_t)frame_size;
@@ -969,17 +974,19 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 any_gap = true;
                 continue;
             }
-            if (mode != OPN_MODE_CELT || opn_packet_channels(pkt) != C || b->cfg.bitstream == OPN_BITSTREAM_OPUS) {
-                // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); mono<->stereo
-                // mapping lives in the stubbed CeltDecoder; CeltDecoder::decode itself is todo!() (celt/decoder.rs:47-56):
-                // CELT frames decode only when the batch was created for the SYNTH-CELT/1 layout.
+            if (mode != OPN_MODE_CELT || b->cfg.bitstream == OPN_BITSTREAM_OPUS) {
+                // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); CeltDecoder::decode itself
+                // is todo!() (celt/decoder.rs:47-56): CELT frames decode only when the batch was created for one of the
+                // SYNTH-CELT layouts.  A packet whose channel count differs from the decoder's is decoded with its own
+                // layout and mapped in the frame kernel (stream_channels, decoder.rs:332,376,395).
                 res[i] = OPN_ERR_UNIMPLEMENTED;
                 any_gap = true;
                 continue;
             }
             const int lm = lm_of_frame((size_t)pfs);
+            const int cs = opn_packet_channels(pkt);
             for (int w = 0; w < count; w++) {
-                items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), lm, w});
+                items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), lm, w, cs});
                 max_len = std::max(max_len, sz[w]);
             }
             if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
@@ -993,9 +1000,9 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         if (want_pcm && any_gap)
             CU(cudaMemsetAsync(g.d_dense + (size_t)s0 * g.dense_cap, 0, (size_t)(s1 - s0) * g.dense_cap * sizeof(float), b->stream));
         if (!items.empty()) {
-            // order: wave-major, then frame size, so each (wave, lm) bucket is contiguous
+            // order: wave-major, then frame size, then the packets' channel count, so each bucket is contiguous
             std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) {
-                return x.wave != y.wave ? x.wave < y.wave : x.lm < y.lm;
+                return x.wave != y.wave ? x.wave < y.wave : x.lm != y.lm ? x.lm < y.lm : x.cs < y.cs;
             });
             // one upload per chunk: [offsets | lens | stream ids | dense offsets], each cnt words, at 4*kbase
             const size_t cnt = items.size();
@@ -1011,9 +1018,10 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             size_t k0 = 0;
             while (k0 < cnt) {
                 size_t k1 = k0;
-                while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm) k1++;
+                while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm && items[k1].cs == items[k0].cs) k1++;
                 rc = run_bucket(b, g.d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
-                                items[k0].lm, 0, pkt_cap, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2, pcm_conv == nullptr);
+                                items[k0].lm, 0, pkt_cap, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2, pcm_conv == nullptr,
+                                items[k0].cs);
                 if (rc) return rc;
                 k0 = k1;
             }

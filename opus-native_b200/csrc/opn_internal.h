@@ -92,6 +92,7 @@ struct FrameArgs {
     uint32_t n_items;             // items of the bucket
     uint32_t item0, item_end;     // this launch covers items [item0, item_end) of them (a bucket may be cut into groups)
     int lm, channels, postfilter;
+    int stream_channels;          // channels of the packets (decoder.rs:332 stream_channels); 0 = the decoder's
     float *carry;                 // [n_streams][C][60]
     float *ring;                  // [n_streams][RING_SAMPLES][C]
     uint32_t *ring_pos;           // [n_streams]

@@ -287,6 +287,17 @@ template <int LM, int C> static cudaError_t launch_frame_w(const FrameArgs &a, c
     return cudaGetLastError();
 }
 
+// packets of CS channels into a decoder of C != CS channels (mono <-> stereo mapping inside the frame kernel)
+template <int LM, int C, int CS> static cudaError_t launch_frame_cross(const FrameArgs &a, cudaStream_t st)
+{
+    if (a.coef) return cudaErrorInvalidValue;
+    const size_t smem = frame_smem_bytes(LM, 2, g_fblob_bytes[LM][CS - 1]);
+    const uint32_t grid = (a.item_end - a.item0 + FRAME_WARPS - 1) / FRAME_WARPS;
+    if (a.parts) k_frame_w<LM, C, FRAME_SYNTH2, CS><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    else k_frame_w<LM, C, FRAME_SYNTH1, CS><<<grid, 32 * FRAME_WARPS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 static size_t symbols_smem(uint32_t pkt_cap)
 {
     return 3 * PVQ_TABLE_WORDS * 4 + 32 + 16 + (size_t)SYM_WARPS_PER_CTA * Y_STAGE * 4 + (size_t)SYM_WARPS_PER_CTA * pkt_cap;
@@ -347,6 +358,19 @@ cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st)
 {
     if (a.item_end <= a.item0) return cudaSuccess;
     if (!a.coef && !a.idx && !a.parts) return cudaErrorInvalidValue;
+    if (a.stream_channels != 0 && a.stream_channels != a.channels) {
+        switch (a.lm * 2 + (a.channels - 1)) {
+        case 0: return launch_frame_cross<0, 1, 2>(a, st);
+        case 1: return launch_frame_cross<0, 2, 1>(a, st);
+        case 2: return launch_frame_cross<1, 1, 2>(a, st);
+        case 3: return launch_frame_cross<1, 2, 1>(a, st);
+        case 4: return launch_frame_cross<2, 1, 2>(a, st);
+        case 5: return launch_frame_cross<2, 2, 1>(a, st);
+        case 6: return launch_frame_cross<3, 1, 2>(a, st);
+        case 7: return launch_frame_cross<3, 2, 1>(a, st);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (a.lm * 2 + (a.channels - 1)) {
     case 0: return launch_frame_w<0, 1>(a, st);
     case 1: return launch_frame_w<0, 2>(a, st);

@@ -654,6 +654,27 @@ int orc_celt2_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t
                                   side->transient, pcm_out);
 }
 
+/* The same with a packet of stream_channels channels in a decoder of `channels` channels (orc_map_channels, oracle/synth.c). */
+int orc_celt2_decode_frame_mapped(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm, int stream_channels, int channels,
+                                  int apply_comb, orc_celt2_side *side, float *pcm_out)
+{
+    if (lm < 0 || lm > 3 || channels < 1 || channels > 2 || stream_channels < 1 || stream_channels > 2) return ORC_ERR_BAD_ARG;
+    float coef[2 * 960];
+    orc_celt2_side local;
+    if (!side) side = &local;
+    const int lost = len <= 1;
+    memset(coef, 0, sizeof(coef));
+    if (lost) {
+        memset(side, 0, sizeof(*side));
+    } else {
+        int rc = orc_celt2_decode_symbols(payload, len, lm, stream_channels, side, NULL, NULL, coef);
+        if (rc) return rc;
+        orc_map_channels(coef, 120 << lm, stream_channels, channels);
+    }
+    return orc_synth_finish_frame(st, coef, lm, channels, apply_comb, lost, side->postfilter, side->period, side->gain_idx, side->tapset,
+                                  side->transient, pcm_out);
+}
+
 /* TOC + SYNTH-CELT/2 payload of exactly pkt_bytes, symbol values drawn from splitmix64(stream, frame). */
 int orc_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes, uint32_t transient_permille,
                      uint8_t *out, orc_celt2_side *truth)

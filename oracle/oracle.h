@@ -162,6 +162,11 @@ int orc_synth_finish_frame(orc_synth_state *st, const float *coef, int lm, int c
 int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm,
                            int channels, int apply_comb, orc_synth_side *side, int32_t *y_out,
                            float *coef_out, float *pcm_out);
+/* A packet of stream_channels channels in a decoder of `channels` channels: mono -> stereo copies the spectrum, stereo -> mono
+ * averages it (stream_channels, src/decoder.rs:332,376,395; mapping restated from libopus' celt_synthesis). */
+void orc_map_channels(float *coef, int nf, int stream_channels, int channels);
+int orc_synth_decode_frame_mapped(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm, int stream_channels, int channels,
+                                  int apply_comb, orc_synth_side *side, float *pcm_out);
 /* ---- SYNTH-CELT/2 (oracle/celt2.c): allocation-driven CELT frame decode, PARITY UNPINNED (no reference code exists) ---- */
 #define ORC_CELT2_MAX_PARTS 192
 typedef struct {
@@ -186,6 +191,8 @@ int orc_celt2_decode_symbols(const uint8_t *payload, uint32_t len, int lm, int c
                              int32_t *y_out, float *coef_out);
 int orc_celt2_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm, int channels, int apply_comb,
                            orc_celt2_side *side, float *pcm_out);
+int orc_celt2_decode_frame_mapped(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm, int stream_channels, int channels,
+                                  int apply_comb, orc_celt2_side *side, float *pcm_out);
 int orc_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes, uint32_t transient_permille,
                      uint8_t *out, orc_celt2_side *truth);
 

@@ -148,6 +148,41 @@ int orc_synth_decode_frame(orc_synth_state *st, const uint8_t *payload, uint32_t
                                   side->transient, pcm_out);
 }
 
+/* A packet of `stream_channels` channels in a decoder of `channels` channels (stream_channels, src/decoder.rs:332,376,395; the
+ * mapping itself belongs to the stubbed CeltDecoder and is restated from libopus' celt_synthesis): mono -> stereo transforms
+ * the same spectrum into both channels (each keeps its own overlap and post-filter history), stereo -> mono transforms the
+ * average 0.5 * (l + r).  coef: [max(stream_channels, channels)][nf], channel-major, mapped in place. */
+void orc_map_channels(float *coef, int nf, int stream_channels, int channels)
+{
+    if (stream_channels == 1 && channels == 2) {
+        memcpy(coef + nf, coef, sizeof(float) * (size_t)nf);
+    } else if (stream_channels == 2 && channels == 1) {
+        for (int i = 0; i < nf; i++) coef[i] = 0.5f * (coef[i] + coef[nf + i]);
+    }
+}
+
+int orc_synth_decode_frame_mapped(orc_synth_state *st, const uint8_t *payload, uint32_t len, int lm, int stream_channels, int channels,
+                                  int apply_comb, orc_synth_side *side, float *pcm_out)
+{
+    if (lm < 0 || lm > 3 || channels < 1 || channels > 2 || stream_channels < 1 || stream_channels > 2) return ORC_ERR_BAD_ARG;
+    int nf = 120 << lm;
+    float coef[2 * 960];
+    orc_synth_side side_local;
+    if (!side) side = &side_local;
+    int lost = len <= 1;
+    memset(coef, 0, sizeof(coef));
+    if (lost) {
+        memset(side, 0, sizeof(*side));
+    } else {
+        orc_dec d;
+        orc_dec_init(&d, payload, len);
+        decode_symbols(&d, lm, stream_channels, side, NULL, coef);
+        orc_map_channels(coef, nf, stream_channels, channels);
+    }
+    return orc_synth_finish_frame(st, coef, lm, channels, apply_comb, lost, side->postfilter, side->period, side->gain_idx, side->tapset,
+                                  side->transient, pcm_out);
+}
+
 /* ------------------------------------------------------------------ packet generator
  * SYNTH-CELT/1 packets for the reference arm of bench.py (so that it never loads the product library) and for
  * cross-checking the product's generator: the same splitmix64 stream and draw order as opn_synth_packet

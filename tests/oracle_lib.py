@@ -140,6 +140,8 @@ def lib():
         C.POINTER(SynthSide), vp, vp, vp)
     sig("orc_celt2_decode_symbols", C.c_int, vp, u32, C.c_int, C.c_int, C.POINTER(Celt2Side), vp, vp, vp)
     sig("orc_celt2_decode_frame", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int, C.POINTER(Celt2Side), vp)
+    sig("orc_celt2_decode_frame_mapped", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Celt2Side), vp)
+    sig("orc_synth_decode_frame_mapped", C.c_int, C.POINTER(SynthState), vp, u32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SynthSide), vp)
     sig("orc_celt2_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp, C.POINTER(Celt2Side))
     sig("orc_synth_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp)
     sig("orc_synth_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
@@ -247,6 +249,28 @@ class Celt2Stream:
         r = lib().orc_celt2_decode_frame(C.byref(self.state), ptr(payload) if len(payload) else None, len(payload), self.lm, self.channels,
                                         int(self.apply_comb), C.byref(side), ptr(pcm))
         return (side, pcm) if r == nf else (r, None)
+
+
+class MappedStream:
+    """One decoder of `channels` channels fed packets of either channel count (stream_channels, decoder.rs:332): oracle side,
+    SYNTH-CELT/1 (bitstream 1) or /2."""
+
+    def __init__(self, channels, bitstream=1, apply_comb=True):
+        self.channels, self.bitstream, self.apply_comb = channels, bitstream, apply_comb
+        self.state = SynthState()
+        lib().orc_synth_state_init(C.byref(self.state))
+
+    def decode(self, payload, lm, stream_channels):
+        """-> (final_rng, pcm [nf*channels])"""
+        nf = 120 << lm
+        payload = np.frombuffer(bytes(payload), dtype=np.uint8).copy()
+        pcm = np.zeros(self.channels * nf, np.float32)
+        side = SynthSide() if self.bitstream == 1 else Celt2Side()
+        fn = lib().orc_synth_decode_frame_mapped if self.bitstream == 1 else lib().orc_celt2_decode_frame_mapped
+        r = fn(C.byref(self.state), ptr(payload) if len(payload) else None, len(payload), lm, stream_channels, self.channels,
+               int(self.apply_comb), C.byref(side), ptr(pcm))
+        assert r == nf, r
+        return side.final_rng, pcm
 
 
 class SynthStream:

@@ -638,7 +638,11 @@ def test_batch_lost_invalid_and_foreign_packets_do_not_poison_neighbours():
                 want[s] = oracle[s].decode(arena[s, 1:])[3]
             elif k == "lost":
                 want[s] = oracle[s].decode(b"")[3]
-            elif k == "silk" or k == "mono":
+            elif k == "mono":  # decoded with the mono layout and copied to both channels (stream_channels, decoder.rs:332)
+                ms = O.MappedStream(channels, 1)
+                ms.state = oracle[s].state
+                want[s] = ms.decode(arena[s, 1:], lm, 1)[1]
+            elif k == "silk":
                 expect[s] = -6
             elif k == "invalid":
                 expect[s] = -4
@@ -760,6 +764,69 @@ def test_batch_device_resident_path_matches_host_path():
     # ring view: the last frame of stream 0 sits just before ring_pos
     ring_ptr, ring_n, pos_ptr = dec.ring()
     assert ring_n == 2880 and ring_ptr and pos_ptr  # 3 x 960: a frame plus the 1024 + 2 samples of history before it
+
+
+@pytest.mark.parametrize("channels,bitstream", [(2, 1), (1, 1), (2, 2), (1, 2)])
+def test_batch_packets_of_either_channel_count(channels, bitstream):
+    """stream_channels (decoder.rs:332,376,395): a decoder of `channels` channels takes mono and stereo packets, switching
+    per packet.  The packet is decoded with its own layout and mapped in the frame kernel -- mono -> stereo transforms the
+    same spectrum into both channels (each with its own overlap and post-filter history), stereo -> mono transforms
+    0.5 * (l + r) -- against the oracle's mapped decode, bit for bit; frame sizes mixed as well, some packets lost."""
+    rnd = np.random.default_rng(31 * channels + bitstream)
+    ns, ncalls, stride = 260, 9, 160
+    pkt_bytes = {0: 64, 1: 80, 2: 110, 3: 160}
+    fill = opn.synth_fill if bitstream == 1 else opn.celt2_fill
+    oracle = [O.MappedStream(channels, bitstream) for _ in range(ns)]
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **(SYNTH if bitstream == 1 else CELT2))
+    last_lm = np.full(ns, 3)
+    exact = True
+    for f in range(ncalls):
+        lm_of = rnd.choice([0, 1, 2, 3], size=ns, p=[0.1, 0.1, 0.3, 0.5])
+        cs_of = rnd.choice([1, 2], size=ns)
+        arena = np.zeros((ns, stride), np.uint8)
+        lens = np.zeros(ns, np.uint32)
+        for lm in range(4):
+            for cs in (1, 2):
+                ids = np.nonzero((lm_of == lm) & (cs_of == cs))[0]
+                if len(ids):
+                    arena[ids, :pkt_bytes[lm]] = fill(700 + 10 * lm + cs, len(ids), f, 1, lm, cs, pkt_bytes[lm], transient_permille=100)[0]
+                    lens[ids] = pkt_bytes[lm]
+        if f > 0:
+            lens[rnd.random(ns) < 0.04] = 0
+        pcm = np.zeros((ns, 960 * channels), np.float32)
+        res = dec.decode_float(arena.reshape(-1), np.arange(ns, dtype=np.uint32) * stride, lens, pcm, 960)
+        rng = dec.final_ranges()
+        for s in range(ns):
+            if lens[s] == 0:
+                nf = 120 << int(last_lm[s])
+                assert res[s] == 960
+                want = np.concatenate([oracle[s].decode(b"", int(last_lm[s]), channels)[1] for _ in range(960 // nf)])
+                got = pcm[s]
+            else:
+                nf = 120 << int(lm_of[s])
+                assert res[s] == nf, (f, s, res[s])
+                fr, want = oracle[s].decode(arena[s, 1:int(lens[s])], int(lm_of[s]), int(cs_of[s]))
+                assert rng[s] == fr
+                got = pcm[s, :nf * channels]
+                last_lm[s] = lm_of[s]
+            assert_pcm(want, got, (f, s))
+            exact &= np.array_equal(want, got)
+    assert exact, "PCM within tolerance but not bit-identical to the oracle"
+
+
+def test_decoder_api_mono_packet_into_stereo_decoder():
+    """Decoder::decode_float (decoder.rs:216-232) on a stereo decoder fed a mono packet: both output channels carry the
+    packet's one channel (their histories were equal), and the call returns the packet's frame size."""
+    dec = opn.Decoder(opn.DecoderConfiguration(48000, 2, 0), bitstream=opn.BITSTREAM_SYNTH_CELT_1)
+    ora = O.MappedStream(2, 1)
+    for f in range(4):
+        pk = opn.synth_fill(5, 1, f, 1, 3, 1, 100)[0, 0]
+        out = np.zeros(960 * 2, np.float32)
+        n = dec.decode_float(pk, out, 960)
+        assert n == 960
+        _, want = ora.decode(pk[1:], 3, 1)
+        assert np.array_equal(out, want)
+        assert np.array_equal(out[0::2], out[1::2]) and np.abs(out).max() > 0
 
 
 @pytest.mark.parametrize("ns,channels,bitstream", [(2300, 2, 1), (300, 1, 1), (500, 2, 2)])
