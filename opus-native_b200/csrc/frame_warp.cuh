@@ -303,19 +303,21 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
     const float2 *t_tw = reinterpret_cast<const float2 *>(blob + H.tw);
     const float *t_win = reinterpret_cast<const float *>(blob + H.win), *t_winsq = reinterpret_cast<const float *>(blob + H.win_sq);
     const bool lost = status == ITEM_LOST;
+    // a transient frame's coefficients go to block-major positions (w_imdct's BM), a long frame's stay where they are
+    const int lmt = (LM > 0 && ((hdr_x >> 2) & 1u)) ? LM : 0;
     if constexpr (MODE == FRAME_SYNTH1) {
         if (!lost && !(hdr_x & 1u)) {  // not silence
             const ExpandTables T{reinterpret_cast<const uint32_t *>(blob + H.pvq_u), reinterpret_cast<const uint2 *>(blob + H.pvq_cw),
                                  reinterpret_cast<const uint16_t *>(blob + H.pvq_row), blob + H.pvq_nmax,
                                  reinterpret_cast<const SynthEntry *>(blob + H.ent), blob + H.slots, (int)H.n_slots};
-            w_expand<CS>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr);
+            w_expand<CS>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr, lmt);
         }
         __syncwarp();
     } else if constexpr (MODE == FRAME_SYNTH2) {
         if (!lost && !(hdr_x & 1u)) {
             // part shapes are only known per frame: the walk uses the full PVQ tables in global memory (L1/L2 resident)
             const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
-            w_expand2<CS>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, A.bande + (size_t)stream * 42, o, CHF, nullptr);
+            w_expand2<CS>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, A.bande + (size_t)stream * 42, o, CHF, nullptr, lmt);
         }
         __syncwarp();
     } else {
@@ -332,7 +334,7 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
         __syncwarp();
     }
     if constexpr (LM > 0) {
-        if ((hdr_x >> 2) & 1u) w_imdct<3, (1 << LM), C, true>(o, lane, carry, t_short, t_tw, t_win);
+        if ((hdr_x >> 2) & 1u) w_imdct<3, (1 << LM), C, true, EXPAND>(o, lane, carry, t_short, t_tw, t_win);  // expanded rows are block-major
         else w_imdct<3 - LM, 1, C, true>(o, lane, carry, t_long, t_tw, t_win);
     } else {
         w_imdct<3, 1, C, true>(o, lane, carry, t_long, t_tw, t_win);

@@ -233,10 +233,15 @@ template <bool TS, class T> __device__ __forceinline__ T tab_ld(const T *p)
     if constexpr (TS) return *p;
     else return __ldg(p);
 }
-template <int SHIFT, int NBLK, int C, bool TS = false>
+// BM: the coefficients of a transient frame arrive block-major (bin k of short block b at b * N2 + k) instead of
+// interleaved (b + NBLK * k, the bitstream's order).  The frame kernel's expansion writes them that way: pass A reads bin
+// 2r + 30q of every block, which in the interleaved layout is a stride of 16 words between lanes -- two banks for fifteen
+// lanes -- and in the block-major one a stride of two.
+template <int SHIFT, int NBLK, int C, bool TS = false, bool BM = false>
 __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const float2 *tpair, const float2 *tw, const float *win)
 {
     constexpr int GS = 32 >> SHIFT, N2 = 960 >> SHIFT;
+    auto cin = [](int blk, int k) { return BM ? blk * N2 + k : blk + NBLK * k; };  // where input bin k of block blk lives
     constexpr int NF = N2 * NBLK, E = GS * NBLK;
     constexpr int CHF = NF + 60;
     // Transpose buffer (aliases the row): element `a` (= position inside the transform, plus 60 per
@@ -313,8 +318,8 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
                 const int j1 = g / 3, j2 = g - 3 * j1, r = j1 + 5 * j2;
 #pragma unroll
                 for (int p = 0; p < 4; p++) {  // w_qmap<3>(p) = p
-                    const float x0 = o[blk + NBLK * (2 * r) + NBLK * 30 * p];
-                    const float x1 = o[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * p];
+                    const float x0 = o[cin(blk, 2 * r + 30 * p)];
+                    const float x1 = o[cin(blk, N2 - 1 - 2 * r - 30 * p)];
                     const float2 tt = tab_ld<TS>(tpair + r + 15 * p);
                     d[4 * i + p] = p_add(make_float2(x0 * tt.x, x1 * tt.x), make_float2(-(x1 * tt.y), x0 * tt.y));
                 }
@@ -347,8 +352,8 @@ __device__ __forceinline__ void w_imdct(float *o, int lane, float4 carry, const 
 #pragma unroll
                 for (int p = 0; p < GS; p++) {  // pre-rotation, mdct.rs:184-200
                     const int q = w_qmap<SHIFT>(p);
-                    const float x0 = x[blk + NBLK * (2 * r) + NBLK * 30 * q];
-                    const float x1 = x[blk + NBLK * (N2 - 1 - 2 * r) - NBLK * 30 * q];
+                    const float x0 = x[cin(blk, 2 * r + 30 * q)];
+                    const float x1 = x[cin(blk, N2 - 1 - 2 * r - 30 * q)];
                     const float2 t = tab_ld<TS>(tp + 15 * q);  // (trig[i], trig[n4 + i])
                     // re = (x1 t.x) + (x0 t.y), im = (x0 t.x) - (x1 t.y); the element is (im, re)
                     d[blk * GS + p] = p_add(make_float2(x0 * t.x, x1 * t.x), make_float2(-(x1 * t.y), x0 * t.y));

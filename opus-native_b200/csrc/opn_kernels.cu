@@ -33,6 +33,15 @@ template <int LM, int C> static cudaError_t set_carveout()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
 }
+template <int LM, int C, int CS> static cudaError_t set_carveout_cross()
+{
+    const int smem = (int)frame_smem_bytes(LM, 2, g_fblob_bytes[LM][CS - 1]);
+    cudaError_t e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH1, CS>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH1, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH2, CS>, cudaFuncAttributePreferredSharedMemoryCarveout, W_CARVEOUT_PCT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_frame_w<LM, C, FRAME_SYNTH2, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
+}
 static size_t mix_smem_bytes(int C)
 {
     size_t m = 0;
@@ -51,6 +60,14 @@ template <int C> static cudaError_t set_carveout_mix()
 static cudaError_t set_warp_kernel_attributes()
 {
     cudaError_t e = set_carveout<0, 1>();
+    if (e == cudaSuccess) e = set_carveout_cross<0, 1, 2>();
+    if (e == cudaSuccess) e = set_carveout_cross<0, 2, 1>();
+    if (e == cudaSuccess) e = set_carveout_cross<1, 1, 2>();
+    if (e == cudaSuccess) e = set_carveout_cross<1, 2, 1>();
+    if (e == cudaSuccess) e = set_carveout_cross<2, 1, 2>();
+    if (e == cudaSuccess) e = set_carveout_cross<2, 2, 1>();
+    if (e == cudaSuccess) e = set_carveout_cross<3, 1, 2>();
+    if (e == cudaSuccess) e = set_carveout_cross<3, 2, 1>();
     if (e == cudaSuccess) e = set_carveout_mix<1>();
     if (e == cudaSuccess) e = set_carveout_mix<2>();
     if (e == cudaSuccess) e = set_carveout<0, 2>();

@@ -425,9 +425,12 @@ struct ExpandTables {
     const uint8_t *slots;   // [n_slots][32]: lane -> entry, 0xFF = none
     int n_slots;
 };
+// lmt > 0: the frame is transient with 2^lmt short blocks and the rows are wanted block-major (bin j of a channel at
+// (j mod 2^lmt) * (nf >> lmt) + (j >> lmt), see w_imdct); 0: bins stay in the bitstream's order.  y_out is never remapped.
+__device__ __forceinline__ uint32_t block_major(uint32_t j, int lmt, int nf) { return (j & ((1u << lmt) - 1u)) * (uint32_t)(nf >> lmt) + (j >> lmt); }
 template <int C>
 __device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t lane, const uint32_t *__restrict__ idx, float *rows, int chs,
-                                         int32_t *__restrict__ y_out)
+                                         int32_t *__restrict__ y_out, int lmt = 0)
 {
     const int nf = 120 << lm;
     const int nslots = T.n_slots;
@@ -470,13 +473,14 @@ __device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t
         if (has) {
             const float gain = 0.03125f / sqrtf((float)yy);
             const uint32_t ch = E.base >= (uint32_t)nf ? 1u : 0u;
-            float *dst = rows + E.base + ch * (uint32_t)(chs - nf);
+            const uint32_t bin0 = E.base - ch * (uint32_t)nf;  // first bin of the part inside its channel
+            float *dst = rows + ch * (uint32_t)chs;
 #pragma unroll
             for (uint32_t j = 0; j < 6u; j++) {
                 if (j < cnt) {
                     const uint32_t r = (uint32_t)(rec >> (10u * j)) & 1023u;
                     const int32_t val = ((int32_t)(r << 28)) >> 28;
-                    dst[r >> 4] = (float)val * gain;
+                    dst[block_major(bin0 + (r >> 4), lmt, nf)] = (float)val * gain;
                     if (y_out) y_out[E.base + (r >> 4)] = val;
                 }
             }
@@ -640,29 +644,31 @@ __global__ void __launch_bounds__(RANGEDEC_WARPS_PER_CTA * 32, OPN_C2_RD_MIN_CTA
 // gains), its energy gives it its level -- every coefficient of band b, channel c is then multiplied by 2^(bande[c][b]/512).
 template <int C>
 __device__ __forceinline__ void w_expand2(const ExpandTables &T, int lm, uint32_t lane, const Celt2Part *__restrict__ parts, uint32_t n_parts,
-                                          const int16_t *__restrict__ bande, float *rows, int chs, int32_t *__restrict__ y_out)
+                                          const int16_t *__restrict__ bande, float *rows, int chs, int32_t *__restrict__ y_out, int lmt = 0)
 {
     const int nf = 120 << lm;
     for (uint32_t p = lane; p < n_parts; p += 32u) {
         const Celt2Part P = parts[p];
         const uint32_t pos = P.base & (uint32_t)C2_POS_MASK, band = P.base >> C2_BAND_SHIFT;
         const uint32_t ch = pos >= (uint32_t)nf ? 1u : 0u;
-        float *dst = rows + pos + ch * (uint32_t)(chs - nf);
+        const uint32_t bin0 = pos - ch * (uint32_t)nf;  // first bin of the leaf inside its channel
+        float *dst = rows + ch * (uint32_t)chs;         // bin j of the channel lives at dst[block_major(j)]
         int32_t *yo = y_out ? y_out + pos : nullptr;
         const float bg = c2_band_gain(g_exp2_q9, (int)bande[ch * 21u + band]);
         if (P.n == 1u) {  // sign-only band
-            dst[0] = (P.index ? -P.gain : P.gain) * bg;
+            dst[block_major(bin0, lmt, nf)] = (P.index ? -P.gain : P.gain) * bg;
             if (yo) yo[0] = P.index ? -1 : 1;
             continue;
         }
         const int32_t yy = cwrsi_events(T.U, T.CW, T.row, T.nmax, (uint32_t)P.n, (uint32_t)P.k, P.index, [&](uint32_t at, int32_t val) {
-            dst[at] = (float)val;
+            dst[block_major(bin0 + at, lmt, nf)] = (float)val;
             if (yo) yo[at] = val;
         });
         const float g = P.gain / sqrtf((float)yy);
         for (uint32_t j = 0; j < P.n; j++) {
-            const float v = dst[j];
-            if (v != 0.0f) dst[j] = (v * g) * bg;  // normalised coefficient, then the band's gain
+            float *q = dst + block_major(bin0 + j, lmt, nf);
+            const float v = *q;
+            if (v != 0.0f) *q = (v * g) * bg;  // normalised coefficient, then the band's gain
         }
     }
 }
