@@ -6,6 +6,7 @@
 //                       flags, post-filter parameters, Laplace coarse energies, raw fine bits,
 //                       PVQ pulse vectors -> unit-norm coefficients for the IMDCT kernel.
 #pragma once
+#include <type_traits>
 #include "opn_device.cuh"
 #include "opn_internal.h"
 #include "rangedec.cuh"
@@ -475,15 +476,20 @@ __device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t
             const uint32_t ch = E.base >= (uint32_t)nf ? 1u : 0u;
             const uint32_t bin0 = E.base - ch * (uint32_t)nf;  // first bin of the part inside its channel
             float *dst = rows + ch * (uint32_t)chs;
+            auto store = [&](auto remap) {  // the frame is all long or all short blocks: one uniform branch, two plain loops
 #pragma unroll
-            for (uint32_t j = 0; j < 6u; j++) {
-                if (j < cnt) {
-                    const uint32_t r = (uint32_t)(rec >> (10u * j)) & 1023u;
-                    const int32_t val = ((int32_t)(r << 28)) >> 28;
-                    dst[block_major(bin0 + (r >> 4), lmt, nf)] = (float)val * gain;
-                    if (y_out) y_out[E.base + (r >> 4)] = val;
+                for (uint32_t j = 0; j < 6u; j++) {
+                    if (j < cnt) {
+                        const uint32_t r = (uint32_t)(rec >> (10u * j)) & 1023u;
+                        const int32_t val = ((int32_t)(r << 28)) >> 28;
+                        const uint32_t at = bin0 + (r >> 4);
+                        dst[decltype(remap)::value ? block_major(at, lmt, nf) : at] = (float)val * gain;
+                        if (y_out) y_out[E.base + (r >> 4)] = val;
+                    }
                 }
-            }
+            };
+            if (lmt) store(std::true_type{});
+            else store(std::false_type{});
         }
     }
 }
