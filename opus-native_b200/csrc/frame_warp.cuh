@@ -215,7 +215,9 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 #define OPN_FRAME_CTAS 4
 #endif
 constexpr int FRAME_WARPS = OPN_FRAME_WARPS, FRAME_CTAS = OPN_FRAME_CTAS;
-__host__ __device__ constexpr size_t frame_warp_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16; }
+// per warp: the rows, 16 bytes for an mbarrier (coefficient rows by TMA) and a 48-byte stash (frame header, previous
+// post-filter parameters, ring position: read once in the prologue, used again after the transform)
+__host__ __device__ constexpr size_t frame_warp_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16 + 48; }
 __host__ __device__ constexpr size_t frame_smem_bytes(int lm, int channels, size_t blob_bytes)
 {
     return 16 + blob_bytes + (size_t)FRAME_WARPS * frame_warp_bytes(lm, channels);
@@ -245,6 +247,7 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
     const FBlobHdr H = g_tab.fblob_hdr[LM][CS - 1];  // the schedule's tables are the packet layout's; the transform's are the same in both
     float *o = reinterpret_cast<float *>(smem + 16 + H.total + (size_t)warp * frame_warp_bytes(LM, R));
     uint64_t *bar = reinterpret_cast<uint64_t *>(o + R * CHF);  // this warp's barrier (coefficient rows by TMA, unfused variant)
+    uint4 *stash = reinterpret_cast<uint4 *>(o + R * CHF + 4);  // [0] frame header, [1] previous PfState, [2].x ring position
 
     if (threadIdx.x == 0) {
         mbar_init(tbar, 1);
@@ -266,7 +269,30 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
     // What the transform needs is loaded now; the rest of the post-filter state is read after the transform, so that it
     // does not occupy registers across it (its cache lines are already here by then).
     const int32_t status = in_range ? A.status[stream] : -1;
-    const uint32_t hdr_x = in_range ? A.hdr[stream].x : 0u;
+    // Lanes 0-2 fetch the frame header, the previous post-filter parameters and the ring position (one round trip through
+    // L2, together with everything else the prologue asks for) and park them in shared memory for the post-filter.
+    {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (in_range) {
+            if (lane == 0) v = A.hdr[stream];
+            else if (lane == 1) v = *reinterpret_cast<const uint4 *>(A.pf + stream);
+            else if (lane == 2) v.x = A.ring_pos[stream];
+        }
+        if (lane < 3) stash[lane] = v;
+    }
+    __syncwarp();
+    const uint32_t hdr_x = stash[0].x;
+    // SYNTH-CELT/1: the stream's codeword indices, three coalesced words per lane, requested with the rest of the prologue;
+    // a lane later picks its parts' indices out of them with shuffles (the dealing table is in the blob, still in flight)
+    [[maybe_unused]] uint32_t ix0 = 0u, ix1 = 0u, ix2 = 0u;
+    if constexpr (MODE == FRAME_SYNTH1) {
+        if (in_range) {
+            const uint32_t *ip = A.idx + (size_t)stream * SYNTH_MAX_ENTRIES;
+            ix0 = __ldg(ip + lane);
+            ix1 = __ldg(ip + 32 + lane);
+            if (lane < SYNTH_MAX_ENTRIES - 64) ix2 = __ldg(ip + 64 + lane);
+        }
+    }
     float *carry_g = A.carry + (size_t)stream * C * 60;
     float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_range && lane < 15 * C) carry = *reinterpret_cast<const float4 *>(carry_g + 4 * lane);  // [C][60] = 15 float4 per channel
@@ -274,8 +300,8 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
     if (in_range && status >= 0 && A.postfilter) {
         // The post-filter will read the last max(T_old, T_new)+2 samples before this frame from the ring: ask for those
         // lines now (HBM -> L2), a whole transform ahead of their use.
-        const int t_old = A.pf[stream].period, t_new = (hdr_x >> 1) & 1u ? (int)(hdr_x >> 16) : 0;
-        const int pos0 = (int)A.ring_pos[stream];
+        const int t_old = (int)stash[1].x, t_new = (hdr_x >> 1) & 1u ? (int)(hdr_x >> 16) : 0;
+        const int pos0 = (int)stash[2].x;
         const int need = max(max(t_old, t_new), 15) + 2;
         for (int l = lane * (128 / (4 * C)); l < need + 128 / (4 * C); l += 32 * (128 / (4 * C))) {  // one 128-byte line per lane and round
             int j = pos0 - need + l;
@@ -310,14 +336,18 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
             const ExpandTables T{reinterpret_cast<const uint32_t *>(blob + H.pvq_u), reinterpret_cast<const uint2 *>(blob + H.pvq_cw),
                                  reinterpret_cast<const uint16_t *>(blob + H.pvq_row), blob + H.pvq_nmax,
                                  reinterpret_cast<const SynthEntry *>(blob + H.ent), blob + H.slots, (int)H.n_slots};
-            w_expand<CS>(T, LM, (uint32_t)lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, o, CHF, nullptr, lmt);
+            w_expand<CS>(T, LM, (uint32_t)lane, [&](uint32_t e) {  // every lane calls it: e = 0xFF for "no part"
+                const int src = (int)(e & 31u);
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, ix0, src), b2 = __shfl_sync(0xFFFFFFFFu, ix1, src), c2 = __shfl_sync(0xFFFFFFFFu, ix2, src);
+                return e == 0xFFu ? 0u : e < 32u ? a : e < 64u ? b2 : c2;
+            }, o, CHF, nullptr, lmt);
         }
         __syncwarp();
     } else if constexpr (MODE == FRAME_SYNTH2) {
         if (!lost && !(hdr_x & 1u)) {
             // part shapes are only known per frame: the walk uses the full PVQ tables in global memory (L1/L2 resident)
             const ExpandTables T{g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, nullptr, nullptr, 0};
-            w_expand2<CS>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, A.hdr[stream].w, A.bande + (size_t)stream * 42, o, CHF, nullptr, lmt);
+            w_expand2<CS>(T, LM, (uint32_t)lane, A.parts + (size_t)stream * CELT2_MAX_PARTS, stash[0].w, A.bande + (size_t)stream * 42, o, CHF, nullptr, lmt);
         }
         __syncwarp();
     } else {
@@ -341,9 +371,16 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
     }
 
     // post-filter parameters: previous frame -> this frame
-    const uint4 hdr = A.hdr[stream];
-    const PfState old = A.pf[stream];
-    const uint32_t pos = A.ring_pos[stream];
+    const uint4 hdr = stash[0];
+    PfState old;
+    {
+        const uint4 q = stash[1];
+        old.period = (int32_t)q.x;
+        old.tapset = (int32_t)q.y;
+        old.gain = __uint_as_float(q.z);
+        old.pad = 0;
+    }
+    const uint32_t pos = stash[2].x;
     const int s_on = (hdr.x >> 1) & 1u, s_tapset = (hdr.x >> 4) & 15u, s_gain = (hdr.x >> 8) & 15u, s_period = hdr.x >> 16;
     int t1 = old.period, tap1 = old.tapset;
     float g1 = old.gain;

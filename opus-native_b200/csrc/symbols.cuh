@@ -429,8 +429,9 @@ struct ExpandTables {
 // lmt > 0: the frame is transient with 2^lmt short blocks and the rows are wanted block-major (bin j of a channel at
 // (j mod 2^lmt) * (nf >> lmt) + (j >> lmt), see w_imdct); 0: bins stay in the bitstream's order.  y_out is never remapped.
 __device__ __forceinline__ uint32_t block_major(uint32_t j, int lmt, int nf) { return (j & ((1u << lmt) - 1u)) * (uint32_t)(nf >> lmt) + (j >> lmt); }
-template <int C>
-__device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t lane, const uint32_t *__restrict__ idx, float *rows, int chs,
+// get_idx(e): the codeword index of part e (0xFF: none); called by every lane of the warp for every slot.
+template <int C, class IdxFn>
+__device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t lane, IdxFn get_idx, float *rows, int chs,
                                          int32_t *__restrict__ y_out, int lmt = 0)
 {
     const int nf = 120 << lm;
@@ -440,7 +441,7 @@ __device__ __forceinline__ void w_expand(const ExpandTables &T, int lm, uint32_t
 #pragma unroll
     for (int slot = 0; slot < SYNTH_SLOTS; slot++) {
         ee[slot] = slot < nslots ? T.slots[slot * 32 + lane] : 0xFFu;
-        ii[slot] = ee[slot] != 0xFFu ? __ldg(idx + ee[slot]) : 0u;
+        ii[slot] = get_idx(ee[slot]);
     }
 #pragma unroll 1
     for (int slot = 0; slot < nslots; slot++) {
@@ -542,8 +543,10 @@ __global__ void __launch_bounds__(EXPAND_WARPS_PER_CTA * 32) k_synth_expand(Symb
     __syncwarp();
     if (!zero_frame) {
         const ExpandTables T{s_pvq, s_cw, s_row, s_nmax, s_ent, &g_tab.synth_slot_entries[lm][C - 1][0][0], g_tab.synth_n_slots[lm][C - 1]};
-        if (C == 2) w_expand<2>(T, lm, lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, s_rows, nf, yo);
-        else w_expand<1>(T, lm, lane, A.idx + (size_t)stream * SYNTH_MAX_ENTRIES, s_rows, nf, yo);
+        const uint32_t *ip = A.idx + (size_t)stream * SYNTH_MAX_ENTRIES;
+        auto get_idx = [&](uint32_t e) { return e != 0xFFu ? __ldg(ip + e) : 0u; };
+        if (C == 2) w_expand<2>(T, lm, lane, get_idx, s_rows, nf, yo);
+        else w_expand<1>(T, lm, lane, get_idx, s_rows, nf, yo);
     }
     __syncwarp();
     if (coef4)

@@ -919,6 +919,19 @@ def test_batch_device_resident_mixed_frame_sizes(ns, channels, bitstream):
     r2 = d_res2.cpu().numpy()
     ok = ~foreign[0]
     assert np.all(r2[ok & (lm_of[0] > 1)] == -5) and np.all(r2[ok & (lm_of[0] <= 1)] == (120 << lm_of[0][ok & (lm_of[0] <= 1)]))
+    # after a reset nothing has been decoded: a step of losses only gives zeros of the row's capacity (decoder.rs:473-484),
+    # and every bucket but one is empty
+    dec.reset()
+    d_zero = torch.zeros(ns, dtype=torch.int32, device=dev)
+    for cap2 in (960, 240):
+        d_pcm[0].fill_(7.0)
+        dec.decode_float_ptrs(d_arena.data_ptr(), d_off.data_ptr(), d_zero.data_ptr(), d_pcm[0].data_ptr(), cap * channels, cap2,
+                              d_res2.data_ptr(), flags)
+        dec.join()
+        dec.synchronize()
+        assert np.all(d_res2.cpu().numpy() == cap2)
+        out = d_pcm[0].cpu().numpy()
+        assert not out[:, :cap2 * channels].any() and np.all(out[:, cap2 * channels:] == 7.0)
 
 
 @pytest.mark.parametrize("postfilter", [True, False])
