@@ -215,6 +215,10 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 #define OPN_FRAME_CTAS 4
 #endif
 constexpr int FRAME_WARPS = OPN_FRAME_WARPS, FRAME_CTAS = OPN_FRAME_CTAS;
+#ifndef OPN_STORE_UNROLL
+#define OPN_STORE_UNROLL 3  // 15 (the whole loop) measured 1-2 % slower per step: the kernel is sensitive to its code size
+#endif
+constexpr int STORE_UNROLL = OPN_STORE_UNROLL;  // iterations of the PCM store loop in flight
 // per warp: the rows, 16 bytes for an mbarrier (coefficient rows by TMA) and a 48-byte stash (frame header, previous
 // post-filter parameters, ring position: read once in the prologue, used again after the transform)
 __host__ __device__ constexpr size_t frame_warp_bytes(int lm, int channels) { return (size_t)channels * w_ch_floats(lm) * 4 + 16 + 48; }
@@ -414,7 +418,7 @@ __device__ __forceinline__ void frame_cta(const FrameArgs &A, uint32_t first_ite
     const int wrap_at = (int)(RING_SAMPLES - pos) / SPV;  // first float4 that lands at the ring start
     float4 *r0 = reinterpret_cast<float4 *>(ring + (size_t)pos * C);
     float4 *r1 = reinterpret_cast<float4 *>(ring) - wrap_at;
-#pragma unroll
+#pragma unroll STORE_UNROLL
     for (int i = lane; i < VEC; i += 32) {
         float4 v;
         if (C == 2) {
