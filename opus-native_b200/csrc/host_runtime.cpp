@@ -734,11 +734,13 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     // All pipeline streams have the same priority (measured in round 1, tools/experiments/priorities.sh: raising the
     // entropy streams gave slow stretches, raising the frame stream serialised the pipeline).
     {
-        // Range-decode streams run at the highest priority, so that their few CTAs are placed first whenever a frame-kernel
-        // CTA retires (OPN_RD_PRIORITY=0 in the environment turns it off).  Measured: SYNTH-CELT/1 44.3 us per step either
-        // way, SYNTH-CELT/2 125 -> 116 us.
+        // SYNTH-CELT/2: the range decode is the long pole (333 us per launch, 128 registers per thread): its streams run at
+        // the highest priority, so that its CTAs are placed first whenever a frame-kernel CTA retires (125 -> 116 us per
+        // step).  SYNTH-CELT/1: no difference in steady state (44.3 us either way), but a short burst loses 2-3 us per step
+        // (20 steps after a drained pipeline: 47.9-49.2 us at equal priority, 50.2-52.5 with the range decodes of eight
+        // steps placed ahead of the first frame kernels), so those keep the default.  OPN_RD_PRIORITY=0/1 overrides.
         const char *pr = std::getenv("OPN_RD_PRIORITY");
-        const bool high = !(pr && pr[0] == '0');
+        const bool high = pr ? pr[0] == '1' : cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
         int lo_p = 0, hi_p = 0;
         if (high) cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
         for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++)
