@@ -1370,6 +1370,36 @@ def test_config2_full_size_properties():
     assert 0.01 < rms < 1.0  # the 1e-5 bar is applied on +-1-scale PCM
 
 
+def test_config2_full_size_device_resident_grouped_pipeline():
+    """The benchmark's own path at its own size: 4096 stereo streams, device-resident packets, six steps enqueued back to back
+    (range decode up to eight steps ahead, the frame kernel of every step as three concurrent launches on three streams).
+    Every step's PCM of ALL streams against the multithreaded oracle decoding the same chain, bit for bit."""
+    torch = pytest.importorskip("torch")
+    ns, nfr, lm, channels, pkt_bytes, nf = 4096, 6, 3, 2, 160, 960
+    packets = opn.synth_fill(9, ns, 0, nfr, lm, channels, pkt_bytes, transient_permille=100)
+    dev = torch.device("cuda:0")
+    d_arena = torch.from_numpy(packets.reshape(-1).copy()).to(dev)
+    d_off = torch.arange(ns, dtype=torch.int32, device=dev) * pkt_bytes
+    d_len = torch.full((ns,), pkt_bytes, dtype=torch.int32, device=dev)
+    d_pcm = torch.zeros((nfr, ns, nf * channels), dtype=torch.float32, device=dev)
+    d_res = torch.zeros((nfr, ns), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    dec = opn.BatchDecoder(ns, **SYNTH)
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_INPUTS_READY
+    for f in range(nfr):
+        dec.decode_float_ptrs(d_arena.data_ptr() + f * ns * pkt_bytes, d_off.data_ptr(), d_len.data_ptr(), d_pcm[f].data_ptr(),
+                              nf * channels, nf, d_res[f].data_ptr(), flags)
+    dec.join()
+    dec.synchronize()
+    assert np.all(d_res.cpu().numpy() == nf)
+    got = d_pcm.cpu().numpy()
+    want = np.zeros((ns, nf * channels), np.float32)
+    x = C.c_uint32(0)
+    for k in range(1, nfr + 1):  # the oracle's chained decode of the first k frames leaves frame k's PCM
+        O.lib().orc_synth_bench(O.ptr(packets[:k]), ns, k, pkt_bytes, lm, channels, 1, os.cpu_count() or 1, O.ptr(want), C.byref(x))
+        assert np.array_equal(got[k - 1], want), k
+
+
 def test_cpp_mirror_example_single_equals_batch():
     """examples/decode_batch.cpp through include/opusb200.hpp: BatchDecoder with two calls in flight and a
     single-stream Decoder agree bit for bit on stream 0, from compiled host code (no Python in the path)."""
