@@ -118,6 +118,14 @@ typedef struct {
  * closer to RFC 6716 section 4.3 than SYNTH-CELT/1, still NOT Opus-interoperable, and parity-unpinned like it. */
 #define OPN_BITSTREAM_SYNTH_CELT_2 2
 
+/* OPN_BITSTREAM_SYNTH_SILK_1 (a bit, OR-ed onto one of the values above): SILK-only frames (TOC configs 0..11, 10 or 20 ms) decode
+ * with the synthetic layout of DESIGN.md section 3c -- range-coded side information and PVQ shell blocks around long-term
+ * prediction, the integer LPC synthesis recursion and a polyphase resampler to 48 kHz -- instead of reporting
+ * OPN_ERR_UNIMPLEMENTED.  SilkDecoder::decode is unimplemented!() in the crate (src/silk/decoder.rs:71-80): the layout is this
+ * library's own, NOT Opus-interoperable, parity-unpinned.  Hybrid frames and 40/60 ms SILK frames stay unimplemented. */
+#define OPN_BITSTREAM_SYNTH_SILK_1 0x100
+#define OPN_BITSTREAM_CELT_MASK 0xFF
+
 #define OPN_FLAG_DEVICE_PTRS 1u  /* arena/offsets/lens/pcm/results are device pointers; call is asynchronous */
 #define OPN_FLAG_NO_PCM_COPY 2u  /* leave PCM in the device ring only (read it with opn_batch_ring) */
 #define OPN_FLAG_INPUTS_READY 4u /* with DEVICE_PTRS: arena/offsets/lens are already complete in device memory and stay
@@ -131,6 +139,10 @@ typedef struct {
                                   * result_per_stream[i] the samples stream i decoded (OPN_ERR_FRAME_SIZE_TOO_SMALL if its
                                   * frame does not fit).  A lost packet (lens[i] == 0) conceals one frame of the size of
                                   * the stream's previous packet.  The step's buckets are built on the device. */
+
+#define OPN_FLAG_SILK_FRAMES 32u  /* with DEVICE_PTRS: every packet of the step is a single SILK-only frame of frame_size samples
+                                  * (480 or 960 at 48 kHz) of the batch's channel count; the bandwidth (NB/MB/WB) is read from each
+                                  * packet's TOC on the device.  Needs OPN_BITSTREAM_SYNTH_SILK_1. */
 
 int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out);
 void opn_batch_destroy(opn_batch *b);
@@ -260,6 +272,29 @@ int opn_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channel
                      uint32_t transient_permille, uint8_t *out, opn_celt2_side *truth);
 int opn_celt2_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,
                    uint32_t pkt_bytes, uint32_t transient_permille, int n_threads, uint8_t *out);
+
+/* ---- SYNTH-SILK/1 frames -------------------------------------------------------------------- */
+typedef struct {
+    int32_t type, gidx[4], rc_idx[16], lag[4], ltp_idx[4], seed;
+    int32_t pulses[20];
+    uint32_t index[20];
+} opn_silk_chan_side;
+typedef struct {
+    opn_silk_chan_side ch[2];
+    uint32_t final_rng, tell_frac;
+} opn_silk_side;
+/* One SILK-only packet (TOC included) per row, each decoded by a fresh decoder of `channels` output channels; every packet
+ * must hold one frame of frame_size samples (480 or 960) and `stream_channels` coded channels.  side_out [n_packets], exc_out
+ * [n_packets][2][320] (excitation after long-term prediction, Q14, per coded channel), out16 [n_packets][2][320] (internal-rate
+ * samples per output channel), pcm_out [n_packets][frame_size*channels], result [n_packets]; any output may be NULL. */
+int opn_op_silk_frames(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                       int stream_channels, int channels, size_t frame_size, opn_silk_side *side_out, int32_t *exc_out, int16_t *out16,
+                       float *pcm_out, int32_t *result);
+/* Generator (host): one packet of exactly pkt_bytes (TOC + SYNTH-SILK/1 payload) / a [frame][stream][pkt_bytes] block.
+ * bandwidth 0 NB (8 kHz), 1 MB (12 kHz), 2 WB (16 kHz); frame_ms 10 or 20. */
+int opn_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out);
+int opn_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
+                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out);
 
 /* ---- synthetic stream generator (host; uses the library's own range ENCODER) --------- */
 /* Writes one packet of exactly pkt_bytes (TOC + SYNTH-CELT/1 payload) for (stream_id, frame).

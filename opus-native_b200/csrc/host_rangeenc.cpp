@@ -478,6 +478,80 @@ int opn_celt2_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_fra
     return OPN_OK;
 }
 
+// SYNTH-SILK/1 packet generator: same seeded draws as the oracle's independent orc_silk_packet.
+static int silk_packet_attempt(uint64_t stream_id, uint64_t frame_idx, uint32_t attempt, int bandwidth, int frame_ms, int channels,
+                               uint32_t pkt_bytes, uint8_t *out)
+{
+    // TOC: SILK-only, config = 4 * bandwidth + (10 ms: 0, 20 ms: 1), stereo flag, code 0 (lib.rs:219-325)
+    out[0] = (uint8_t)(((bandwidth * 4 + (frame_ms == 20 ? 1 : 0)) << 3) | (channels == 2 ? 0x4 : 0));
+    SplitMix64 rng{77ull + 1000003ull * stream_id + 0xD1B54A32D192ED03ull * frame_idx + 0x2545F4914F6CDD1Dull * attempt};
+    const int fs_khz = bandwidth == 0 ? 8 : bandwidth == 1 ? 12 : 16, nb_subfr = frame_ms / 5, order = fs_khz == 16 ? 16 : 10;
+    const int nblk = (nb_subfr * 5 * fs_khz + 15) / 16;
+    RangeEncoder enc(out + 1, pkt_bytes - 1);
+    for (int c = 0; c < channels; c++) {
+        const uint32_t t8 = rng.below(8), type = t8 == 0 ? 0u : t8 < 3 ? 1u : 2u;
+        enc.icdf(type, OPN_SILK_TYPE_ICDF, 8);
+        enc.uint(16 + rng.below(36), 64);
+        for (int f = 1; f < nb_subfr; f++) enc.icdf(3 + rng.below(3), OPN_SILK_DELTA_GAIN_ICDF, 8);
+        for (int k = 0; k < order; k++) {
+            const uint32_t half = k < 2 ? 16 : 8;
+            const uint32_t a = rng.below(half + 1), b = rng.below(half);
+            enc.bits(a + b, k < 2 ? 5 : 4);
+        }
+        if (type == 2) {
+            enc.uint(rng.below((uint32_t)(16 * fs_khz + 1)), (uint32_t)(16 * fs_khz + 1));
+            for (int f = 0; f < nb_subfr; f++) enc.icdf(rng.below(4), OPN_SILK_CONTOUR_ICDF, 8);
+            for (int f = 0; f < nb_subfr; f++) enc.icdf(rng.below(8), OPN_SILK_LTP_ICDF, 8);
+        }
+        enc.bits(rng.below(4), 2);
+        for (int b = 0; b < nblk; b++) {
+            const uint32_t k1 = rng.below(9), k2 = rng.below(9), k = k1 < k2 ? k1 : k2;
+            enc.icdf(k, OPN_SILK_PULSES_ICDF + (type != 0 ? 9 : 0), 8);
+            if (k) {
+                const uint32_t v = pvq_v(16, k);
+                enc.uint(rng.below(v), v);
+            }
+        }
+    }
+    if (enc.error()) return enc.error();
+    if (enc.tell() > 8u * (pkt_bytes - 1u)) return OPN_ERR_BUFFER_TOO_SMALL;
+    enc.done();
+    return enc.error() ? enc.error() : (int)pkt_bytes;
+}
+
+int opn_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out)
+{
+    if (!out || bandwidth < 0 || bandwidth > 2 || (frame_ms != 10 && frame_ms != 20) || channels < 1 || channels > 2 || pkt_bytes < 3 ||
+        pkt_bytes > 1276)
+        return OPN_ERR_BAD_ARG;
+    int rc = OPN_ERR_BUFFER_TOO_SMALL;
+    for (uint32_t attempt = 0; attempt < 16 && rc == OPN_ERR_BUFFER_TOO_SMALL; attempt++)
+        rc = silk_packet_attempt(stream_id, frame_idx, attempt, bandwidth, frame_ms, channels, pkt_bytes, out);
+    return rc;
+}
+
+int opn_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
+                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out)
+{
+    if (!out || n_streams == 0 || n_frames == 0) return OPN_ERR_BAD_ARG;
+    if (n_threads < 1) n_threads = 1;
+    std::vector<int> rc((size_t)n_threads, 0);
+    std::vector<std::thread> pool;
+    const uint64_t total = (uint64_t)n_streams * n_frames;
+    for (int th = 0; th < n_threads; th++)
+        pool.emplace_back([&, th]() {
+            for (uint64_t w = total * th / n_threads; w < total * (th + 1) / n_threads; w++) {
+                int r = opn_silk_packet(first_stream + w % n_streams, first_frame + w / n_streams, bandwidth, frame_ms, channels, pkt_bytes,
+                                        out + w * pkt_bytes);
+                if (r < 0) rc[th] = r;
+            }
+        });
+    for (auto &t : pool) t.join();
+    for (int r : rc)
+        if (r < 0) return r;
+    return OPN_OK;
+}
+
 int opn_synth_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int lm, int channels,
                    uint32_t pkt_bytes, uint32_t transient_permille, int n_threads, uint8_t *out)
 {

@@ -194,6 +194,11 @@ struct opn_batch {
     uint8_t *d_mix_lm[NSETS] = {};                       // [mix_item_cap(n)]
     MixPlan *d_mix_plan[NSETS] = {};
     cudaEvent_t ev_mix[NSETS] = {};                      // buckets of set p are built
+    // SYNTH-SILK/1 (OPN_BITSTREAM_SYNTH_SILK_1): per-stream filter state and one record set per range decode in flight
+    bool silk = false;
+    SilkState d_silk{};
+    SilkRec *d_silk_rec[NSETS] = {};
+    std::vector<uint8_t> silk_cs;  // host mirror: coded channels of the stream's last SILK frame (0 = none)
     unsigned long long *d_hist_samples = nullptr;  // measurement: history samples the post-filter needed (timed passes only)
     // host mirrors of DecoderInner fields (decoder.rs:236-258), per stream
     std::vector<int32_t> last_nf, bandwidth, last_duration, have_mode;
@@ -479,6 +484,82 @@ int run_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, 
     return OPN_OK;
 }
 
+cudaError_t do_silk_rangedec(opn_batch *b, const void *a) { return launch_silk_rangedec(*static_cast<const SilkArgs *>(a), b->stream); }
+cudaError_t do_silk_frame(opn_batch *b, const void *a) { return launch_silk_frame(*static_cast<const SilkArgs *>(a), b->stream); }
+
+// One bucket of SILK-only frames (SYNTH-SILK/1) of one duration and one coded channel count: the range decode on an entropy
+// stream (it may run ahead like the CELT one), the frame kernel on the batch stream (it owns the streams' filter state and
+// the PCM ring).  bandwidth < 0: read from each packet's TOC (has_toc).
+int run_silk_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens, const uint32_t *d_stream_idx,
+                    const uint32_t *d_dense_off, uint32_t n_items, int frame_ms, int has_toc, int bandwidth, int stream_channels,
+                    float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
+{
+    Range nv("opn: SILK step (range decode + frame kernel)");
+    if (!b->silk) return OPN_ERR_UNIMPLEMENTED;  // silk/decoder.rs:79
+    const int p = b->set;
+    b->set = (p + 1) % opn_batch::NSETS;
+    cudaStream_t srd = b->stream_rd[p % opn_batch::NRD];
+    SilkArgs a{};
+    a.arena = d_arena;
+    a.offsets = d_offsets;
+    a.lens = d_lens;
+    a.stream_idx = d_stream_idx;
+    a.n_items = n_items;
+    a.frame_ms = frame_ms;
+    a.stream_channels = stream_channels;
+    a.channels = b->cfg.channels;
+    a.has_toc = has_toc;
+    a.bandwidth = bandwidth;
+    a.rec = b->d_silk_rec[p];
+    a.hdr = b->d_hdr[p];
+    a.status = b->d_status[p];
+    a.st = b->d_silk;
+    a.ring = b->d_ring;
+    a.ring_pos = b->d_ring_pos;
+    a.dense = dense;
+    a.dense_stride = dense_stride;
+    a.dense_off = d_dense_off;
+    a.gain = b->gain;
+    a.result = d_result;
+    a.final_range = b->d_final;
+    a.softclip_reset = softclip_reset ? b->d_softclip : nullptr;
+    int rc = join_groups(b);  // CELT frame kernels of these streams may still run on the group streams
+    if (rc) return rc;
+    if (b->timing) {
+        if (inputs_on == 2) {
+            CU(cudaEventRecord(b->ev_in, b->stream_up));
+            CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
+        }
+        rc = timed_launch(b, 0, do_silk_rangedec, &a);
+        if (rc) return rc;
+        rc = timed_launch(b, 1, do_silk_frame, &a);
+        if (rc) return rc;
+    } else {
+        if (inputs_on == 1) {
+            CU(cudaEventRecord(b->ev_in, b->stream));
+            CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
+        } else if (inputs_on == 2) {
+            CU(cudaEventRecord(b->ev_in, b->stream_up));
+            CU(cudaStreamWaitEvent(srd, b->ev_in, 0));
+        }
+        if (b->k1_recorded[p]) {  // set p is free again
+            CU(cudaStreamWaitEvent(srd, b->ev_k1[p], 0));
+            if (b->k1_grouped[p])
+                for (int g = 1; g < opn_batch::NGROUPS; g++) CU(cudaStreamWaitEvent(srd, b->ev_fr[p][g], 0));
+        }
+        CU(launch_silk_rangedec(a, srd));
+        CU(cudaEventRecord(b->ev_rd[p], srd));
+        b->launches[0]++;
+        CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
+        CU(launch_silk_frame(a, b->stream));
+        b->launches[1]++;
+    }
+    CU(cudaEventRecord(b->ev_k1[p], b->stream));
+    b->k1_recorded[p] = true;
+    b->k1_grouped[p] = false;
+    return OPN_OK;
+}
+
 int mix_alloc(opn_batch *b)
 {
     if (b->d_last_lm) return OPN_OK;
@@ -711,7 +792,9 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
 {
     if (!out || !cfg || n_streams == 0) return OPN_ERR_BAD_ARG;
     if (cfg->channels < 1 || cfg->channels > 2) return OPN_ERR_BAD_ARG;
-    if (cfg->bitstream != OPN_BITSTREAM_OPUS && cfg->bitstream != OPN_BITSTREAM_SYNTH_CELT_1 && cfg->bitstream != OPN_BITSTREAM_SYNTH_CELT_2)
+    if (cfg->bitstream & ~(OPN_BITSTREAM_CELT_MASK | OPN_BITSTREAM_SYNTH_SILK_1)) return OPN_ERR_BAD_ARG;
+    const int32_t celt_bitstream = cfg->bitstream & OPN_BITSTREAM_CELT_MASK;
+    if (celt_bitstream != OPN_BITSTREAM_OPUS && celt_bitstream != OPN_BITSTREAM_SYNTH_CELT_1 && celt_bitstream != OPN_BITSTREAM_SYNTH_CELT_2)
         return OPN_ERR_BAD_ARG;
     switch (cfg->fs_hz) {
     case 48000: break;
@@ -726,9 +809,11 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->device = device;
     b->n = n_streams;
     b->cfg = *cfg;
+    b->cfg.bitstream = celt_bitstream;  // how CELT frames are laid out; the SILK opt-in is b->silk
+    b->silk = (cfg->bitstream & OPN_BITSTREAM_SYNTH_SILK_1) != 0;
     b->gain = host_gain_from_q8(cfg->gain_q8);
     const char *uf = std::getenv("OPN_UNFUSED_EXPAND");
-    b->unfused = uf && uf[0] == '1' && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_1;
+    b->unfused = uf && uf[0] == '1' && celt_bitstream == OPN_BITSTREAM_SYNTH_CELT_1;
     const size_t n = n_streams, C = (size_t)cfg->channels;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     // All pipeline streams have the same priority (measured in round 1, tools/experiments/priorities.sh: raising the
@@ -740,7 +825,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         // (20 steps after a drained pipeline: 47.9-49.2 us at equal priority, 50.2-52.5 with the range decodes of eight
         // steps placed ahead of the first frame kernels), so those keep the default.  OPN_RD_PRIORITY=0/1 overrides.
         const char *pr = std::getenv("OPN_RD_PRIORITY");
-        const bool high = pr ? pr[0] == '1' : cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
+        const bool high = pr ? pr[0] == '1' : celt_bitstream == OPN_BITSTREAM_SYNTH_CELT_2;
         int lo_p = 0, hi_p = 0;
         if (high) cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
         for (int q = 0; q < opn_batch::NRD && e == cudaSuccess; q++)
@@ -754,8 +839,9 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
         if (e == cudaSuccess) e = cudaMalloc(&b->d_idx[q], n * 72 * sizeof(uint32_t));
         if (e == cudaSuccess && b->unfused) e = cudaMalloc(&b->d_coef[q], n * C * 960 * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_hdr[q], n * sizeof(uint4));
-        if (e == cudaSuccess && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_parts[q], n * CELT2_MAX_PARTS * sizeof(Celt2Part));
-        if (e == cudaSuccess && cfg->bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_bande[q], n * 42 * sizeof(int16_t));
+        if (e == cudaSuccess && celt_bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_parts[q], n * CELT2_MAX_PARTS * sizeof(Celt2Part));
+        if (e == cudaSuccess && b->silk) e = cudaMalloc(&b->d_silk_rec[q], n * 2 * sizeof(SilkRec));
+        if (e == cudaSuccess && celt_bitstream == OPN_BITSTREAM_SYNTH_CELT_2) e = cudaMalloc(&b->d_bande[q], n * 42 * sizeof(int16_t));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_status[q], n * sizeof(int32_t));
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream_ex, cudaStreamNonBlocking);
@@ -772,6 +858,14 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     if (e == cudaSuccess) e = cudaMalloc(&b->d_final, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_pf, n * sizeof(PfState));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_softclip, n * 2 * sizeof(float));
+    if (b->silk) {
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_silk.slpc, n * 2 * 16 * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_silk.hist, n * 2 * SILK_HIST * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_silk.a_q12, n * 2 * 16 * sizeof(int16_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_silk.gain, n * 2 * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_silk.rs, n * 2 * 8 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_silk.fs, n * 2);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&b->d_hist_samples, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(b->d_hist_samples, 0, sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -782,6 +876,7 @@ int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_
     b->bandwidth.assign(n, -1);
     b->last_duration.assign(n, -1);
     b->have_mode.assign(n, 0);
+    b->silk_cs.assign(n, 0);
     *out = b;
     rc = opn_batch_reset(b);
     if (rc) {
@@ -819,7 +914,14 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(b->d_parts[q]);
         cudaFree(b->d_bande[q]);
         cudaFree(b->d_status[q]);
+        cudaFree(b->d_silk_rec[q]);
     }
+    cudaFree(b->d_silk.slpc);
+    cudaFree(b->d_silk.hist);
+    cudaFree(b->d_silk.a_q12);
+    cudaFree(b->d_silk.gain);
+    cudaFree(b->d_silk.rs);
+    cudaFree(b->d_silk.fs);
     if (b->ev_in) cudaEventDestroy(b->ev_in);
     for (int q = 0; q < opn_batch::MAX_CHUNKS; q++)
         if (b->ev_chunk[q]) cudaEventDestroy(b->ev_chunk[q]);
@@ -881,11 +983,20 @@ int opn_batch_reset(opn_batch *b)  // DecoderInner::reset, decoder.rs:286-303, f
     b->set = 0;
     CU(cudaMemsetAsync(b->d_softclip, 0, n * 2 * sizeof(float), b->stream));
     if (b->d_last_lm) CU(cudaMemsetAsync(b->d_last_lm, MIX_NO_ITEM, n, b->stream));
+    if (b->silk) {
+        CU(cudaMemsetAsync(b->d_silk.slpc, 0, n * 2 * 16 * sizeof(int32_t), b->stream));
+        CU(cudaMemsetAsync(b->d_silk.hist, 0, n * 2 * SILK_HIST * sizeof(int32_t), b->stream));
+        CU(cudaMemsetAsync(b->d_silk.a_q12, 0, n * 2 * 16 * sizeof(int16_t), b->stream));
+        CU(cudaMemsetAsync(b->d_silk.gain, 0, n * 2 * sizeof(int32_t), b->stream));
+        CU(cudaMemsetAsync(b->d_silk.rs, 0, n * 2 * 8 * sizeof(float), b->stream));
+        CU(cudaMemsetAsync(b->d_silk.fs, 0, n * 2, b->stream));
+    }
     CU(cudaStreamSynchronize(b->stream));
     std::fill(b->last_nf.begin(), b->last_nf.end(), 120);
     std::fill(b->bandwidth.begin(), b->bandwidth.end(), -1);
     std::fill(b->last_duration.begin(), b->last_duration.end(), -1);
     std::fill(b->have_mode.begin(), b->have_mode.end(), 0);
+    std::fill(b->silk_cs.begin(), b->silk_cs.end(), 0);
     return OPN_OK;
 }
 
@@ -932,11 +1043,14 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
     items.reserve(items_ub / n_chunks + 64);
     std::vector<int32_t> res(n, 0);
     std::vector<uint32_t> plc;
+    std::vector<uint32_t> silk_resets, celt_resets;  // streams whose codec mode changes in this chunk
     size_t kbase = 0;  // items of earlier chunks
     for (uint32_t ch = 0; ch < n_chunks; ch++) {
         const uint32_t s0 = (uint32_t)((uint64_t)n * ch / n_chunks), s1 = (uint32_t)((uint64_t)n * (ch + 1) / n_chunks);
         Range nv_chunk("opn: chunk (host parse -> enqueue)");
         items.clear();
+        silk_resets.clear();
+        celt_resets.clear();
         bool any_gap = false;  // some stream of the chunk leaves part of its dense row unwritten
         uint32_t max_len = 8;
         for (uint32_t i = s0; i < s1; i++) {
@@ -952,6 +1066,23 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 plc_frames(frame_size, b->last_nf[i], plc);
                 uint32_t at = 0;
                 int w = 0;
+                if (b->have_mode[i] == 1 + OPN_MODE_SILK) {
+                    // the stream's last packet was SILK: concealed by the SILK path (10 and 20 ms frames only)
+                    bool ok = b->silk;
+                    for (uint32_t a : plc) ok = ok && (a == 480 || a == 960);
+                    if (!ok) {
+                        res[i] = OPN_ERR_UNIMPLEMENTED;
+                        any_gap = true;
+                        continue;
+                    }
+                    for (uint32_t a : plc) {
+                        items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, 8 + (a == 960 ? 1 : 0), w++, (int)b->silk_cs[i]});
+                        at += a;
+                    }
+                    res[i] = (int32_t)frame_size;
+                    b->last_duration[i] = (int32_t)frame_size;
+                    continue;
+                }
                 for (uint32_t a : plc) {
                     items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++, C});
                     at += a;
@@ -976,6 +1107,24 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 any_gap = true;
                 continue;
             }
+            if (mode == OPN_MODE_SILK && b->silk && (pfs == 480 || pfs == 960) && opn_packet_bandwidth(pkt) <= OPN_BW_WIDE) {
+                // SYNTH-SILK/1: bucket code 8 + 2 * bandwidth + (20 ms)
+                const int code = 8 + 2 * opn_packet_bandwidth(pkt) + (pfs == 960 ? 1 : 0);
+                const int cs = opn_packet_channels(pkt);
+                for (int w = 0; w < count; w++) {
+                    items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), code, w, cs});
+                    max_len = std::max(max_len, sz[w]);
+                }
+                if (b->have_mode[i] == 1 + OPN_MODE_CELT) silk_resets.push_back(i);  // decoder.rs:555-557: silk_dec.reset()
+                if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
+                res[i] = count * pfs;
+                b->have_mode[i] = 1 + OPN_MODE_SILK;
+                b->silk_cs[i] = (uint8_t)cs;
+                b->last_nf[i] = pfs;
+                b->bandwidth[i] = opn_packet_bandwidth(pkt);
+                b->last_duration[i] = count * pfs;
+                continue;
+            }
             if (mode != OPN_MODE_CELT || b->cfg.bitstream == OPN_BITSTREAM_OPUS) {
                 // SilkDecoder::decode is unimplemented!() in the reference (silk/decoder.rs:79); CeltDecoder::decode itself
                 // is todo!() (celt/decoder.rs:47-56): CELT frames decode only when the batch was created for one of the
@@ -992,8 +1141,9 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 max_len = std::max(max_len, sz[w]);
             }
             if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
+            if (b->have_mode[i] == 1 + OPN_MODE_SILK) celt_resets.push_back(i);  // decoder.rs:703-705: celt_dec.reset() on a mode change
             res[i] = count * pfs;
-            b->have_mode[i] = 1;
+            b->have_mode[i] = 1 + OPN_MODE_CELT;
             b->last_nf[i] = pfs;
             b->bandwidth[i] = opn_packet_bandwidth(pkt);
             b->last_duration[i] = count * pfs;
@@ -1016,11 +1166,29 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 hi[3 * cnt + k] = items[k].dense_off;
             }
             CU(cudaMemcpyAsync(di, hi, 4 * cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream_up));
+            // mode changes: the decoder that takes over starts from rest (ordered before this chunk's range decodes, which
+            // wait for stream_up; the stream's earlier frames ran in earlier calls)
+            for (uint32_t i : silk_resets) CU(cudaMemsetAsync(b->d_silk.fs + 2 * (size_t)i, 0, 2, b->stream_up));
+            for (uint32_t i : celt_resets) {
+                CU(cudaMemsetAsync(b->d_carry + (size_t)i * C * 60, 0, (size_t)C * 60 * sizeof(float), b->stream_up));
+                CU(cudaMemsetAsync(b->d_pf + i, 0, sizeof(PfState), b->stream_up));
+                // CeltDecoder::reset clears its decode memory: the post-filter must not see SILK output as history
+                CU(cudaMemsetAsync(b->d_ring + (size_t)i * C * RING_SAMPLES, 0, (size_t)C * RING_SAMPLES * sizeof(float), b->stream_up));
+            }
             const uint32_t pkt_cap = (max_len + 15u) & ~15u;
             size_t k0 = 0;
             while (k0 < cnt) {
                 size_t k1 = k0;
                 while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm && items[k1].cs == items[k0].cs) k1++;
+                if (items[k0].lm >= 8) {
+                    const int code = items[k0].lm - 8;
+                    rc = run_silk_bucket(b, g.d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
+                                         (code & 1) ? 20 : 10, 0, code >> 1, items[k0].cs, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2,
+                                         pcm_conv == nullptr);
+                    if (rc) return rc;
+                    k0 = k1;
+                    continue;
+                }
                 rc = run_bucket(b, g.d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
                                 items[k0].lm, 0, pkt_cap, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2, pcm_conv == nullptr,
                                 items[k0].cs);
@@ -1093,11 +1261,17 @@ int opn_batch_decode_float(opn_batch *b, const uint8_t *arena, const uint32_t *o
     // frame_size samples; with it frame_size is the capacity of a stream's row, as in decode_float, and each stream
     // decodes whatever single frame its packet holds.
     if (!arena) return OPN_ERR_BAD_ARG;
-    if (b->cfg.bitstream == OPN_BITSTREAM_OPUS) return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:47-56 is todo!()
+    if (b->cfg.bitstream == OPN_BITSTREAM_OPUS && !(flags & OPN_FLAG_SILK_FRAMES)) return OPN_ERR_UNIMPLEMENTED;  // celt/decoder.rs:47-56 is todo!()
     float *dense = (flags & OPN_FLAG_NO_PCM_COPY) ? nullptr : pcm;
     if (dense && (pcm_stride_floats < std::min<size_t>(frame_size, 960) * (size_t)C || (pcm_stride_floats & 3) ||
                   (reinterpret_cast<uintptr_t>(dense) & 15)))
         return OPN_ERR_BAD_ARG;
+    if (flags & OPN_FLAG_SILK_FRAMES) {
+        if (!b->silk || (flags & OPN_FLAG_MIXED_FRAMES) || (frame_size != 480 && frame_size != 960)) return OPN_ERR_BAD_ARG;
+        if (dense && pcm_stride_floats < frame_size * (size_t)C) return OPN_ERR_BAD_ARG;
+        return run_silk_bucket(b, arena, offsets, lens, nullptr, nullptr, b->n, frame_size == 960 ? 20 : 10, 1, -1, C, dense, pcm_stride_floats,
+                               result_per_stream, (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1, true);
+    }
     if (flags & OPN_FLAG_MIXED_FRAMES)
         return run_mixed(b, arena, offsets, lens, frame_size, dense, pcm_stride_floats, result_per_stream,
                          (flags & OPN_FLAG_INPUTS_READY) ? 0 : 1, true);
@@ -1664,6 +1838,90 @@ int opn_op_celt2_symbols(int device, const uint8_t *arena, const uint32_t *offse
     if (side_out) CU(cudaMemcpy(side_out, dS.p, (size_t)n_packets * sizeof(Celt2Side), cudaMemcpyDeviceToHost));
     if (y_out) CU(cudaMemcpy(y_out, dY.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
     if (coef_out) CU(cudaMemcpy(coef_out, dC.p, (size_t)n_packets * row * 4, cudaMemcpyDeviceToHost));
+    return OPN_OK;
+}
+
+// SYNTH-SILK/1 operator: every packet is decoded by a fresh decoder (zero state) through the product's two kernels.
+int opn_op_silk_frames(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
+                       int stream_channels, int channels, size_t frame_size, opn_silk_side *side_out, int32_t *exc_out, int16_t *out16,
+                       float *pcm_out, int32_t *result)
+{
+    if (!arena || !offsets || !lens || n_packets == 0 || channels < 1 || channels > 2 || stream_channels < 1 || stream_channels > 2)
+        return OPN_ERR_BAD_ARG;
+    if (frame_size != 480 && frame_size != 960) return OPN_ERR_BAD_ARG;
+    int rc = select_device(device);
+    if (rc) return rc;
+    size_t arena_end = 0;
+    for (uint32_t i = 0; i < n_packets; i++) arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
+    const size_t n = n_packets, row = frame_size * (size_t)channels;
+    DevBuf dA, dO, dL, dS, dSt, dH, dR, dX, dY, dP, dRes, dRing, dPos, dFin;
+    DevBuf sL, sH, sA, sG, sR, sF;
+    CU(dA.alloc(arena_end + 8));
+    CU(dO.alloc(n * 4));
+    CU(dL.alloc(n * 4));
+    CU(dS.alloc(n * sizeof(opn_silk_side)));
+    CU(dSt.alloc(n * 4));
+    CU(dH.alloc(n * sizeof(uint4)));
+    CU(dR.alloc(n * 2 * sizeof(SilkRec)));
+    CU(dX.alloc(n * 2 * SILK_MAX_FRAME * 4));
+    CU(dY.alloc(n * 2 * SILK_MAX_FRAME * 2));
+    CU(dP.alloc(n * row * 4));
+    CU(dRes.alloc(n * 4));
+    CU(dRing.alloc(n * (size_t)channels * RING_SAMPLES * 4));
+    CU(dPos.alloc(n * 4));
+    CU(dFin.alloc(n * 4));
+    CU(sL.alloc(n * 2 * 16 * 4));
+    CU(sH.alloc(n * 2 * SILK_HIST * 4));
+    CU(sA.alloc(n * 2 * 16 * 2));
+    CU(sG.alloc(n * 2 * 4));
+    CU(sR.alloc(n * 2 * 8 * 4));
+    CU(sF.alloc(n * 2));
+    CU(cudaMemcpy(dA.p, arena, arena_end, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dO.p, offsets, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dL.p, lens, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dS.p, 0, n * sizeof(opn_silk_side)));
+    CU(cudaMemset(dX.p, 0, n * 2 * SILK_MAX_FRAME * 4));
+    CU(cudaMemset(dY.p, 0, n * 2 * SILK_MAX_FRAME * 2));
+    CU(cudaMemset(dP.p, 0, n * row * 4));
+    CU(cudaMemset(dPos.p, 0, n * 4));
+    CU(cudaMemset(sL.p, 0, n * 2 * 16 * 4));
+    CU(cudaMemset(sH.p, 0, n * 2 * SILK_HIST * 4));
+    CU(cudaMemset(sA.p, 0, n * 2 * 16 * 2));
+    CU(cudaMemset(sG.p, 0, n * 2 * 4));
+    CU(cudaMemset(sR.p, 0, n * 2 * 8 * 4));
+    CU(cudaMemset(sF.p, 0, n * 2));
+    SilkArgs a{};
+    a.arena = dA.as<uint8_t>();
+    a.offsets = dO.as<uint32_t>();
+    a.lens = dL.as<uint32_t>();
+    a.n_items = n_packets;
+    a.frame_ms = frame_size == 960 ? 20 : 10;
+    a.stream_channels = stream_channels;
+    a.channels = channels;
+    a.has_toc = 1;
+    a.bandwidth = -1;
+    a.rec = dR.as<SilkRec>();
+    a.hdr = dH.as<uint4>();
+    a.status = dSt.as<int32_t>();
+    a.st = SilkState{sL.as<int32_t>(), sH.as<int32_t>(), sA.as<int16_t>(), sG.as<int32_t>(), sR.as<float>(), sF.as<uint8_t>()};
+    a.ring = dRing.as<float>();
+    a.ring_pos = dPos.as<uint32_t>();
+    a.dense = dP.as<float>();
+    a.dense_stride = row;
+    a.gain = 1.0f;
+    a.result = dRes.as<int32_t>();
+    a.final_range = dFin.as<uint32_t>();
+    a.side = dS.as<opn_silk_side>();
+    a.exc_out = dX.as<int32_t>();
+    a.out16 = dY.as<int16_t>();
+    CU(launch_silk_rangedec(a, nullptr));
+    CU(launch_silk_frame(a, nullptr));
+    CU(cudaDeviceSynchronize());
+    if (side_out) CU(cudaMemcpy(side_out, dS.p, n * sizeof(opn_silk_side), cudaMemcpyDeviceToHost));
+    if (exc_out) CU(cudaMemcpy(exc_out, dX.p, n * 2 * SILK_MAX_FRAME * 4, cudaMemcpyDeviceToHost));
+    if (out16) CU(cudaMemcpy(out16, dY.p, n * 2 * SILK_MAX_FRAME * 2, cudaMemcpyDeviceToHost));
+    if (pcm_out) CU(cudaMemcpy(pcm_out, dP.p, n * row * 4, cudaMemcpyDeviceToHost));
+    if (result) CU(cudaMemcpy(result, dRes.p, n * 4, cudaMemcpyDeviceToHost));
     return OPN_OK;
 }
 

@@ -125,6 +125,62 @@ struct MixArgs {  // k_mix_key / k_mix_place
     int32_t *result;                 // [n_streams] or nullptr: OPN_ERR_* of the streams no bucket takes
 };
 
+// ---- SYNTH-SILK/1 (silk.cuh)
+constexpr int SILK_MAX_FRAME = 320;  // 20 ms at 16 kHz
+constexpr int SILK_HIST = 320;       // excitation history of the long-term predictor
+constexpr int SILK_ROWS = 32;        // coded channels per CTA
+constexpr int SILK_WARPS = 8;
+constexpr int SILK_RS = 33;          // row stride of the transposed rows (words)
+
+// range decode -> frame kernel, one per coded channel
+struct alignas(16) SilkRec {
+    uint32_t index[20];
+    uint16_t lag[4];
+    uint8_t pulses[20];
+    uint8_t rc[16];
+    uint8_t gidx[4], ltp[4];
+    uint8_t type, seed, pad[2];
+    uint32_t pad2[2];
+};
+static_assert(sizeof(SilkRec) == 144, "SilkRec layout");
+
+struct SilkState {  // per stream (structure of arrays, device)
+    int32_t *slpc;   // [n][2][16]  sLPC_Q14 of the last 16 samples, [15] newest
+    int32_t *hist;   // [n][2][SILK_HIST] excitation after long-term prediction, newest last
+    int16_t *a_q12;  // [n][2][16]
+    int32_t *gain;   // [n][2]
+    float *rs;       // [n][2][8] resampler history per output channel: rs[j] = x[-1-j]
+    uint8_t *fs;     // [n][2]: internal rate of the previous SILK frame in kHz (0 = none), its coded channels
+};
+
+struct SilkArgs {
+    const uint8_t *arena;
+    const uint32_t *offsets, *lens, *stream_idx;  // per item; stream_idx may be nullptr
+    uint32_t n_items;
+    int frame_ms;          // 10 or 20: every item of the launch
+    int stream_channels;   // coded channels of every item
+    int channels;          // the decoder's
+    int has_toc;           // 1: offsets point at the TOC (device-resident steps); 0: at the frame payload, bandwidth below
+    int bandwidth;         // host path: 0 NB, 1 MB, 2 WB of every item
+    SilkRec *rec;          // [n_streams][2]
+    uint4 *hdr;            // [n_streams] .x = fs_khz of the frame, .y final range, .z tell_frac
+    int32_t *status;       // [n_streams]
+    SilkState st;
+    float *ring;           // [n_streams][RING_SAMPLES][C]
+    uint32_t *ring_pos;
+    float *dense;          // rows of dense_stride floats or nullptr
+    size_t dense_stride;
+    const uint32_t *dense_off;
+    float gain;
+    int32_t *result;
+    uint32_t *final_range;
+    float *softclip_reset;
+    // operator entry / tests (indexed by stream)
+    opn_silk_side *side;   // or nullptr
+    int32_t *exc_out;      // [n_streams][2][SILK_MAX_FRAME] or nullptr
+    int16_t *out16;        // [n_streams][2][SILK_MAX_FRAME] or nullptr
+};
+
 // ---- launchers (opn_kernels.cu).  All return a cudaError_t and never synchronise.
 cudaError_t upload_tables(int device);  // idempotent per device
 cudaError_t launch_rangedec_script(const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
@@ -142,6 +198,8 @@ cudaError_t launch_frame(const FrameArgs &a, cudaStream_t st);
 cudaError_t launch_mix_plan(const MixArgs &a, cudaStream_t st);
 cudaError_t launch_op_smooth_fade(const float *in1, const float *in2, float *out, size_t row_stride, int overlap, int channels, int fs,
                                   uint32_t n_rows, cudaStream_t st);
+cudaError_t launch_silk_rangedec(const SilkArgs &a, cudaStream_t st);  // one lane per packet -> one record per coded channel
+cudaError_t launch_silk_frame(const SilkArgs &a, cudaStream_t st);     // excitation + LTP + LPC synthesis + resampler + PCM store
 int kernels_frame_groups();  // OPN_FRAME_GROUPS the kernels were built with
 cudaError_t launch_frame_mix(const FrameArgs &a, uint32_t n_streams_in_group, cudaStream_t st);
 cudaError_t launch_op_imdct(const float *in, size_t in_stride, float *out, size_t out_stride, uint32_t n_rows, int shift,

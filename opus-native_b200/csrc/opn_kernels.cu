@@ -11,6 +11,7 @@
 #include "opn_tables.h"
 #include "softclip.cuh"
 #include "symbols.cuh"
+#include "silk.cuh"
 
 namespace opn {
 
@@ -282,6 +283,25 @@ cudaError_t upload_tables(int device)
     e = cudaMemcpyToSymbol(g_fblob, blobs, sizeof(blobs));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(g_exp2_q9, OPN_EXP2_Q9, sizeof(float) * 512);
+    if (e == cudaSuccess) {
+        static SilkTables sk;
+        std::memset(&sk, 0, sizeof(sk));
+        for (int i = 0; i < 64; i++) sk.gain_q10[i] = OPN_SILK_GAIN_Q10[i];
+        for (int i = 0; i < 40; i++) sk.ltp_q14[i] = OPN_SILK_LTP_Q14[i];
+        for (int i = 0; i < 3; i++) sk.type_icdf[i] = OPN_SILK_TYPE_ICDF[i];
+        for (int i = 0; i < 9; i++) sk.delta_icdf[i] = OPN_SILK_DELTA_GAIN_ICDF[i];
+        for (int i = 0; i < 4; i++) sk.contour_icdf[i] = OPN_SILK_CONTOUR_ICDF[i];
+        for (int i = 0; i < 8; i++) sk.ltp_icdf[i] = OPN_SILK_LTP_ICDF[i];
+        for (int i = 0; i < 18; i++) sk.pulses_icdf[i] = OPN_SILK_PULSES_ICDF[i];
+        for (int i = 0; i < 48; i++) sk.up[0][i] = OPN_SILK_UP6[i];
+        for (int i = 0; i < 32; i++) sk.up[1][i] = OPN_SILK_UP4[i];
+        for (int i = 0; i < 24; i++) sk.up[2][i] = OPN_SILK_UP3[i];
+        e = cudaMemcpyToSymbol(g_silk, &sk, sizeof(sk));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());
+    }
     if (e != cudaSuccess) return e;
     e = set_warp_kernel_attributes();
     if (e != cudaSuccess) return e;
@@ -537,6 +557,27 @@ cudaError_t launch_op_smooth_fade(const float *in1, const float *in2, float *out
     if (channels < 1 || fs <= 0 || 48000 % fs != 0 || (overlap - 1) * (48000 / fs) >= 120) return cudaErrorInvalidValue;
     const dim3 grid((uint32_t)(overlap * channels + 127) / 128, n_rows);
     k_op_smooth_fade<<<grid, 128, 0, st>>>(in1, in2, out, row_stride, overlap, channels, 48000 / fs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_silk_rangedec(const SilkArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    k_silk_rangedec<<<(a.n_items + 31u) / 32u, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_silk_frame(const SilkArgs &a, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    const int cs = a.stream_channels, c = a.channels;
+    if (cs < 1 || cs > 2 || c < 1 || c > 2 || (a.frame_ms != 10 && a.frame_ms != 20)) return cudaErrorInvalidValue;
+    const uint32_t items_per_cta = (uint32_t)(SILK_ROWS / cs), grid = (a.n_items + items_per_cta - 1u) / items_per_cta;
+    const size_t smem = silk_frame_smem();
+    if (cs == 1 && c == 1) k_silk_frame<1, 1><<<grid, 32 * SILK_WARPS, smem, st>>>(a);
+    else if (cs == 1) k_silk_frame<1, 2><<<grid, 32 * SILK_WARPS, smem, st>>>(a);
+    else if (c == 1) k_silk_frame<2, 1><<<grid, 32 * SILK_WARPS, smem, st>>>(a);
+    else k_silk_frame<2, 2><<<grid, 32 * SILK_WARPS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,454 @@
+// silk.cuh -- SYNTH-SILK/1 frames on the device: north_star's src/silk part -- "LPC synthesis across
+// streams and the polyphase resampler to 48 kHz".  The reference's SilkDecoder::decode is unimplemented!()
+// (src/silk/decoder.rs:71-80; caller src/decoder.rs:552-624, merge src/decoder.rs:722-729), so the frame layout is this
+// repo's own (oracle/silk.c states it; parity unpinned): range-coder operations the crate implements around long-term
+// prediction, the integer short-term synthesis recursion of SURVEY.md appendix B and a polyphase interpolator.
+//
+// One step = two launches, like the CELT path:
+//   k_silk_rangedec   one LANE per packet (LaneDec): symbols -> one 144-byte record per coded channel
+//   k_silk_frame      one CTA per 32 coded channels ("rows"; a stereo packet is two rows), 8 warps, three phases:
+//     A  warp per row:  PVQ shell blocks -> excitation (one lane per 16-sample block, cwrsi_events), sign dither, long-term
+//                       prediction in spans of lag-2 samples (a sample's taps lie at least lag-2 samples back), reflection
+//                       coefficients -> A_Q12 with one lane per coefficient; rows land TRANSPOSED in shared memory
+//                       ([sample][row], row stride 33 words: conflict-free for both access patterns)
+//     B  lane per row:  the LPC recursion is strictly serial per channel (sat32 makes it non-linear: no scan), so it runs
+//                       ACROSS streams: 32 channels per warp, the 16-sample window and the 16 coefficients in registers
+//     C  warp per item: mid/side -> left/right, polyphase interpolation to 48 kHz, x 1/32768, coalesced stores into the PCM
+//                       ring and the dense rows
+#pragma once
+#include "opn_device.cuh"
+#include "rangedec.cuh"
+#include "symbols.cuh"
+
+namespace opn {
+
+struct SilkTables {
+    int32_t gain_q10[64];
+    int16_t ltp_q14[40];
+    uint8_t type_icdf[4], delta_icdf[12], contour_icdf[4], ltp_icdf[8], pulses_icdf[20];
+    float up[3][48];  // [0] x6 (8 kHz), [1] x4 (12 kHz), [2] x3 (16 kHz): [phase][tap]
+};
+__device__ SilkTables g_silk;
+
+__device__ __forceinline__ int32_t silk_smulwb(int32_t a, int32_t b16) { return (int32_t)(((int64_t)a * (int64_t)b16) >> 16); }
+__device__ __forceinline__ int32_t silk_smulww(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * (int64_t)b) >> 16); }
+__device__ __forceinline__ int32_t silk_sat16(int32_t x) { return max(-32768, min(32767, x)); }
+
+// ------------------------------------------------------------------------------------------------- range decode
+__global__ void __launch_bounds__(32) k_silk_rangedec(SilkArgs A)
+{
+    __shared__ uint8_t s_icdf[48];  // type 0..3 | delta 4..15 | contour 16..19 | ltp 20..27 | pulses 28..47
+    const uint32_t lane = threadIdx.x;
+    if (lane < 4u) s_icdf[lane] = g_silk.type_icdf[lane];
+    if (lane < 12u) s_icdf[4u + lane] = g_silk.delta_icdf[lane];
+    if (lane < 4u) s_icdf[16u + lane] = g_silk.contour_icdf[lane];
+    if (lane < 8u) s_icdf[20u + lane] = g_silk.ltp_icdf[lane];
+    if (lane < 20u) s_icdf[28u + lane] = g_silk.pulses_icdf[lane];
+    __syncwarp();
+    const uint32_t item = blockIdx.x * 32u + lane;
+    if (item >= A.n_items) return;
+    const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+    uint32_t len = A.lens[item];
+    const uint8_t *src = A.arena + A.offsets[item];
+    int32_t status = len == 0u ? ITEM_LOST : ITEM_OK;
+    int bandwidth = A.bandwidth;
+    if (A.has_toc && len > 0u) {
+        // what a host caller checks with query_packet_* (src/lib.rs:219-325) before decode_frame
+        const uint32_t toc = __ldg(src), config = toc >> 3;
+        if (config >= 12u) status = OPN_ERR_UNIMPLEMENTED;                                  // hybrid / CELT: not this launch
+        else if ((toc & 0x3u) != 0u) status = OPN_ERR_UNIMPLEMENTED;                        // multi-frame: host path only
+        else if ((config & 3u) > 1u) status = OPN_ERR_UNIMPLEMENTED;                        // 40 / 60 ms: several SILK frames
+        else if ((int)((config & 3u) ? 20 : 10) != A.frame_ms) status = OPN_ERR_FRAME_SIZE_TOO_SMALL;
+        else if (((toc & 0x4u) ? 2 : 1) != A.stream_channels) status = OPN_ERR_UNIMPLEMENTED;
+        bandwidth = (int)(config >> 2);
+        src += 1;
+        len -= 1u;
+    }
+    if (status == ITEM_OK && len <= 1u) status = ITEM_LOST;  // decoder.rs:467
+    A.status[stream] = status;
+    if (status != ITEM_OK) {
+        if (status == ITEM_LOST) A.hdr[stream] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int fs_khz = bandwidth == 0 ? 8 : bandwidth == 1 ? 12 : 16;
+    const int nb_subfr = A.frame_ms / 5, order = fs_khz == 16 ? 16 : 10, nblk = (nb_subfr * 5 * fs_khz + 15) / 16;
+    const int min_lag = 2 * fs_khz, max_lag = 18 * fs_khz;
+    const PvqTable T{g_tab.pvq_u_data, g_tab.pvq_u_row};
+    LaneDec d;
+    d.init(src, len);
+    for (int c = 0; c < A.stream_channels; c++) {
+        SilkRec *r = A.rec + (size_t)stream * 2 + c;
+        opn_silk_chan_side *sd = A.side ? &A.side[stream].ch[c] : nullptr;
+        const uint32_t type = d.icdf(s_icdf, 8u);
+        uint32_t g = d.uint_small(64u);
+        r->type = (uint8_t)type;
+        r->gidx[0] = (uint8_t)g;
+        if (sd) {
+            sd->type = (int32_t)type;
+            sd->gidx[0] = (int32_t)g;
+        }
+        for (int f = 1; f < 4; f++) {
+            if (f < nb_subfr) {
+                const int v = (int)g + (int)d.icdf(s_icdf + 4, 8u) - 4;
+                g = (uint32_t)max(0, min(63, v));
+            }
+            r->gidx[f] = (uint8_t)g;
+            if (sd) sd->gidx[f] = f < nb_subfr ? (int32_t)g : 0;
+        }
+        for (int k = 0; k < 16; k++) {
+            const uint32_t v = k < order ? d.bits(k < 2 ? 5u : 4u) : 0u;
+            r->rc[k] = (uint8_t)v;
+            if (sd) sd->rc_idx[k] = (int32_t)v;
+        }
+        if (type == 2u) {
+            const int lag0 = min_lag + (int)d.uint_any((uint32_t)(max_lag - min_lag + 1));
+            for (int f = 0; f < 4; f++) {
+                int l = 0;
+                if (f < nb_subfr) l = max(min_lag, min(max_lag, lag0 + (int)d.icdf(s_icdf + 16, 8u) - 1));
+                r->lag[f] = (uint16_t)l;
+                if (sd) sd->lag[f] = l;
+            }
+            for (int f = 0; f < 4; f++) {
+                const uint32_t v = f < nb_subfr ? d.icdf(s_icdf + 20, 8u) : 0u;
+                r->ltp[f] = (uint8_t)v;
+                if (sd) sd->ltp_idx[f] = (int32_t)v;
+            }
+        } else {
+            for (int f = 0; f < 4; f++) {
+                r->lag[f] = 0;
+                r->ltp[f] = 0;
+                if (sd) sd->lag[f] = sd->ltp_idx[f] = 0;
+            }
+        }
+        const uint32_t seed = d.bits(2u);
+        r->seed = (uint8_t)seed;
+        if (sd) sd->seed = (int32_t)seed;
+        const uint8_t *pt = s_icdf + 28 + (type != 0u ? 9 : 0);
+        for (int b = 0; b < 20; b++) {
+            uint32_t k = 0u, idx = 0u;
+            if (b < nblk) {
+                k = d.icdf(pt, 8u);
+                if (k) idx = d.uint_any(T.v(16u, k));
+            }
+            r->pulses[b] = (uint8_t)k;
+            r->index[b] = idx;
+            if (sd) {
+                sd->pulses[b] = (int32_t)k;
+                sd->index[b] = idx;
+            }
+        }
+    }
+    const uint32_t tf = d.tell_frac();
+    if (A.side) {
+        A.side[stream].final_rng = d.rng;
+        A.side[stream].tell_frac = tf;
+    }
+    A.hdr[stream] = make_uint4((uint32_t)fs_khz, d.rng, tf, 0u);
+}
+
+// ------------------------------------------------------------------------------------------------- frame kernel
+// t / up and t % up for up in {3, 4, 6} without a runtime division
+__device__ __forceinline__ void silk_divmod(int t, int up, int &q, int &r)
+{
+    q = up == 3 ? t / 3 : up == 4 ? t >> 2 : t / 6;
+    r = t - q * up;
+}
+
+constexpr size_t silk_frame_smem() { return (size_t)(SILK_MAX_FRAME * SILK_RS + 16 * SILK_RS + 16 * SILK_RS + 4 * SILK_RS) * 4 + 8 * SILK_ROWS; }
+
+template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_silk_frame(SilkArgs A)
+{
+    extern __shared__ __align__(16) uint8_t silk_smem[];
+    int32_t *s_res = reinterpret_cast<int32_t *>(silk_smem);  // [SILK_MAX_FRAME][SILK_RS]: excitation, then internal-rate samples
+    int32_t *s_a = s_res + SILK_MAX_FRAME * SILK_RS;          // [16][SILK_RS] A_Q12
+    int32_t *s_lpc = s_a + 16 * SILK_RS;                      // [16][SILK_RS] sLPC_Q14 window, [15] newest
+    int32_t *s_gain = s_lpc + 16 * SILK_RS;                   // [4][SILK_RS]
+    // per row: [0] fs_khz (0 = the row does nothing), [1] lost, [2] state was reset, [3] silent (lost before any frame)
+    uint8_t *s_meta = reinterpret_cast<uint8_t *>(s_gain + 4 * SILK_RS);  // [SILK_ROWS][8]
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    constexpr uint32_t ITEMS = SILK_ROWS / CS;
+    const uint32_t item0 = blockIdx.x * ITEMS;
+    const int nb_subfr = A.frame_ms / 5;
+
+    // ---- phase A: one warp per row
+    for (uint32_t row = warp; row < (uint32_t)SILK_ROWS; row += SILK_WARPS) {
+        const uint32_t item = item0 + row / CS, c = row % CS;
+        uint8_t *meta = s_meta + row * 8;
+        if (item >= A.n_items) {
+            if (lane == 0) meta[0] = 0;
+            continue;
+        }
+        const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+        const int32_t status = A.status[stream];
+        const uint32_t fs_prev = A.st.fs[2 * stream], cs_prev = A.st.fs[2 * stream + 1];
+        const bool lost = status == ITEM_LOST;
+        int fs_khz = lost ? (int)fs_prev : (int)A.hdr[stream].x;
+        const bool silent = status < 0 || (lost && (fs_prev == 0u || c >= cs_prev));  // errors and losses before any frame: no work
+        const bool reset = !lost && (uint32_t)fs_khz != fs_prev;
+        if (lane == 0) {
+            meta[0] = silent ? 0 : (uint8_t)fs_khz;
+            meta[1] = lost;
+            meta[2] = reset;
+            meta[3] = status < 0 ? 2 : (lost && fs_prev == 0u) ? 1 : 0;
+        }
+        if (silent) continue;
+        const int order = fs_khz == 16 ? 16 : 10, sub = 5 * fs_khz, L = nb_subfr * sub, nblk = (L + 15) / 16;
+        const size_t chs = (size_t)stream * 2 + c;
+        int32_t *hist = A.st.hist + chs * SILK_HIST;
+        int32_t *res = s_res + row;  // sample i at res[i * SILK_RS]
+        // previous window of the LPC recursion, coefficient and gain state
+        if (lane < 16u) s_lpc[lane * SILK_RS + row] = reset ? 0 : A.st.slpc[chs * 16 + lane];
+        if (lost) {
+            for (int i = (int)lane; i < L; i += 32) res[i * SILK_RS] = 0;
+            if (lane < 16u) s_a[lane * SILK_RS + row] = (int32_t)A.st.a_q12[chs * 16 + lane];
+            if (lane < 4u) s_gain[lane * SILK_RS + row] = A.st.gain[chs];
+        } else {
+            const SilkRec *r = A.rec + chs;
+            const uint32_t type = r->type, seed = r->seed;
+            // excitation: lane b expands shell block b
+            if ((int)lane < nblk) {
+                const uint32_t k = r->pulses[lane], idx = r->index[lane];
+                uint64_t lo = 0ull, hi = 0ull;  // y[j] as a signed byte, j < 8 in lo, the rest in hi
+                if (k) {
+                    cwrsi_events(g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, 16u, k, idx, [&](uint32_t pos, int32_t val) {
+                        const uint64_t v = (uint64_t)(uint8_t)(int8_t)val << (8u * (pos & 7u));
+                        if (pos < 8u) lo |= v;
+                        else hi |= v;
+                    });
+                }
+                const int32_t offs = type == 1u ? (100 << 4) : (32 << 4);
+                uint32_t rr = (seed + 1u) * 2654435761u + lane * 2246822519u;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int32_t y = (int32_t)(int8_t)(uint8_t)((j < 8 ? lo : hi) >> (8 * (j & 7)));
+                    int32_t e = y * 16384;
+                    e += y > 0 ? -(80 << 4) : y < 0 ? (80 << 4) : 0;
+                    e += offs;
+                    rr = rr * 196314165u + 907633515u;
+                    if (rr & 0x80000000u) e = -e;
+                    rr += (uint32_t)y;
+                    const int i = 16 * (int)lane + j;
+                    if (i < L) res[i * SILK_RS] = e;
+                }
+            }
+            __syncwarp();
+            if (type == 2u) {
+                // long-term prediction: pres[i] = exc[i] + ((2 + sum_k smulwb(pres[i - lag + 2 - k], B[k])) << 2); the newest tap lies
+                // lag - 2 samples back, so spans of min(32, lag - 2) samples are independent
+                for (int f = 0; f < nb_subfr; f++) {
+                    const int lag = (int)r->lag[f];
+                    const int16_t *B = g_silk.ltp_q14 + 5 * r->ltp[f];
+                    const int32_t b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4];
+                    const int span = min(32, lag - 2), end = (f + 1) * sub;
+                    for (int i0 = f * sub; i0 < end; i0 += span) {
+                        const int i = i0 + (int)lane;
+                        if ((int)lane < span && i < end) {
+                            const int top = i - lag + 2;  // index of tap 0; taps run downwards
+                            int32_t pred = 2;
+                            const int32_t bk[5] = {b0, b1, b2, b3, b4};
+#pragma unroll
+                            for (int k = 0; k < 5; k++) {
+                                const int q = top - k;
+                                const int32_t v = q >= 0 ? res[q * SILK_RS] : (reset ? 0 : hist[SILK_HIST + q]);
+                                pred += silk_smulwb(v, bk[k]);
+                            }
+                            res[i * SILK_RS] += (int32_t)((uint32_t)pred << 2);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // reflection coefficients -> A_Q12: lane n holds c[n] (Q24); step k adds rc_k * c[k-1-n] to every n < k at once
+            {
+                int32_t cn = 0;
+                for (int k = 0; k < order; k++) {
+                    const int32_t idx = (int32_t)r->rc[k];
+                    const int32_t rc = k < 2 ? (idx - 16) * 3600 : (idx - 8) * (k < 6 ? 4800 : 2400);
+                    const int32_t partner = __shfl_sync(0xffffffffu, cn, (k - 1 - (int)lane) & 31);
+                    if ((int)lane < k) cn += silk_smulww(partner, rc);
+                    else if ((int)lane == k) cn = rc * 256;
+                }
+                if (lane < 16u) {
+                    const int32_t x = (int)lane < order ? (int32_t)(0u - (uint32_t)cn) : 0;
+                    s_a[lane * SILK_RS + row] = silk_sat16(((x >> 11) + 1) >> 1);
+                }
+                if (lane < 4u) s_gain[lane * SILK_RS + row] = g_silk.gain_q10[r->gidx[min((int)lane, nb_subfr - 1)]];
+            }
+        }
+        __syncwarp();
+        if (A.exc_out)
+            for (int i = (int)lane; i < L; i += 32) A.exc_out[chs * SILK_MAX_FRAME + i] = res[i * SILK_RS];
+        // excitation history: the last SILK_HIST samples of (old history ++ this frame)
+        {
+            int32_t keep[8];  // old samples that stay (L < SILK_HIST): read before anything is overwritten
+            const int stay = SILK_HIST - L;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int j = (int)lane + 32 * u;
+                keep[u] = (j < stay && !reset) ? hist[j + L] : 0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int j = (int)lane + 32 * u;
+                if (j < stay) hist[j] = keep[u];
+            }
+            for (int j = max(stay, 0) + (int)lane; j < SILK_HIST; j += 32) hist[j] = res[(j - stay) * SILK_RS];
+        }
+        if (reset && CS == 1) {  // a mono frame at a new rate: the second channel's filters start from rest as well
+            for (int j = (int)lane; j < SILK_HIST; j += 32) hist[SILK_HIST + j] = 0;
+            if (lane < 16u) {
+                A.st.slpc[(chs + 1) * 16 + lane] = 0;
+                A.st.a_q12[(chs + 1) * 16 + lane] = 0;
+            }
+            if (lane == 0) A.st.gain[chs + 1] = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: warp 0, one lane per row.  SURVEY.md appendix B:
+    //   pred_Q10 = order/2 + sum_k smulwb(sLPC_Q14[i-1-k], A_Q12[k]); sLPC_Q14[i] = sat32(res_Q14[i] + (pred_Q10 << 4));
+    //   out[i] = sat16(rshift_round(smulww(sLPC_Q14[i], gain_Q10), 8))
+    if (warp == 0) {
+        const uint32_t row = lane;
+        const int fs_khz = s_meta[row * 8];
+        const int sub = 5 * fs_khz, L = nb_subfr * sub;
+        int Lmax = L;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, o));
+        int32_t a[16], s[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            a[k] = s_a[k * SILK_RS + row];
+            s[k] = s_lpc[k * SILK_RS + row];  // s[15] = sLPC[-1]; sample i lives in s[i & 15]
+        }
+        const int32_t rnd = fs_khz == 16 ? 8 : 5;
+        const int32_t g0 = s_gain[row], g1 = s_gain[SILK_RS + row], g2 = s_gain[2 * SILK_RS + row], g3 = s_gain[3 * SILK_RS + row];
+        for (int i0 = 0; i0 < Lmax; i0 += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int i = i0 + u;
+                if (i < L) {
+                    int32_t pred = rnd;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) pred += silk_smulwb(s[(u - 1 - k) & 15], a[k]);
+                    const int64_t v = (int64_t)s_res[i * SILK_RS + row] + (int64_t)pred * 16;
+                    const int32_t v32 = v > 2147483647ll ? 2147483647 : v < -2147483648ll ? (int32_t)0x80000000 : (int32_t)v;
+                    s[u] = v32;
+                    const int f = i / sub;
+                    const int32_t w = silk_smulww(v32, f == 0 ? g0 : f == 1 ? g1 : f == 2 ? g2 : g3);
+                    s_res[i * SILK_RS + row] = silk_sat16(((w >> 7) + 1) >> 1);
+                }
+            }
+        }
+        if (fs_khz) {
+            const uint32_t item = item0 + row / CS, c = row % CS;
+            const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+            const size_t chs = (size_t)stream * 2 + c;
+            // the window is a ring indexed by i & 15: after L samples (L is a multiple of 8, not always of 16) the newest
+            // is s[(L - 1) & 15]
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                // slpc[15 - k] = sLPC[L - 1 - k] = s[(L - 1 - k) & 15]
+                int32_t v = s[0];
+#pragma unroll
+                for (int q = 1; q < 16; q++) v = ((L - 1 - k) & 15) == q ? s[q] : v;
+                A.st.slpc[chs * 16 + 15 - k] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) A.st.a_q12[chs * 16 + k] = (int16_t)a[k];
+            A.st.gain[chs] = nb_subfr == 4 ? g3 : g1;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: one warp per item
+    for (uint32_t it = warp; it < ITEMS; it += SILK_WARPS) {
+        const uint32_t item = item0 + it;
+        if (item >= A.n_items) continue;
+        const uint32_t row0 = it * CS;
+        const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+        const int n48 = A.frame_ms * 48;
+        const uint32_t flag = s_meta[row0 * 8 + 3];
+        const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
+        float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
+        if (flag == 2u) {  // rejected packet: state untouched, the error is the result
+            if (lane == 0 && A.result) A.result[stream] = A.status[stream];
+            continue;
+        }
+        if (flag == 1u) {  // lost before anything was decoded: silence, state untouched
+            if (dense)
+                for (int t = (int)lane; t < n48 * C; t += 32) dense[t] = 0.0f;
+            if (lane == 0) {
+                if (A.result) A.result[stream] = n48;
+                if (A.final_range) A.final_range[stream] = 0u;
+            }
+            continue;
+        }
+        const int fs_khz = s_meta[row0 * 8];
+        const bool lost = s_meta[row0 * 8 + 1], reset = s_meta[row0 * 8 + 2];
+        const int L = nb_subfr * 5 * fs_khz, up = 48 / fs_khz;
+        const float *h = g_silk.up[up == 6 ? 0 : up == 4 ? 1 : 2];
+        const uint32_t pos = A.ring_pos[stream];
+        float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
+        float *rs = A.st.rs + (size_t)stream * 16;
+        // internal-rate sample i of output channel c (decoder.rs:332 stream_channels -> channels)
+        auto sample = [&](int i, int c) -> float {
+            if (i < 0) return reset ? 0.0f : rs[c * 8 + (-1 - i)];
+            const int32_t m = s_res[i * SILK_RS + row0];
+            if (CS == 2 && C == 2) {
+                const int32_t sd = s_res[i * SILK_RS + row0 + 1];
+                return (float)silk_sat16(c == 0 ? m + sd : m - sd);
+            }
+            return (float)m;
+        };
+        float hist_new[2] = {0.0f, 0.0f};  // lane j < 7 keeps x[L-1-j] of both channels
+        if (lane < 7u) {
+#pragma unroll
+            for (int c = 0; c < C; c++) hist_new[c] = sample(L - 1 - (int)lane, c);
+        }
+        for (int t = (int)lane; t < n48; t += 32) {
+            int i, p;
+            silk_divmod(t, up, i, p);
+            float out[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                float acc = h[8 * p] * sample(i, c);
+#pragma unroll
+                for (int j = 1; j < 8; j++) acc = acc + h[8 * p + j] * sample(i - j, c);
+                out[c] = 0.0f + (1.0f / 32768.0f) * acc;  // decoder.rs:722-729 onto a zero CELT contribution
+            }
+            uint32_t rp = pos + (uint32_t)t;
+            if (rp >= (uint32_t)RING_SAMPLES) rp -= RING_SAMPLES;
+            if (C == 2) {
+                *reinterpret_cast<float2 *>(ring + (size_t)rp * 2) = make_float2(out[0], out[1]);
+                if (dense) *reinterpret_cast<float2 *>(dense + (size_t)t * 2) = make_float2(out[0] * A.gain, out[C - 1] * A.gain);
+            } else {
+                ring[rp] = out[0];
+                if (dense) dense[t] = out[0] * A.gain;
+            }
+        }
+        __syncwarp();
+        if (lane < 7u) {
+#pragma unroll
+            for (int c = 0; c < C; c++) rs[c * 8 + lane] = hist_new[c];
+        }
+        if (lane == 0) {
+            uint32_t np = pos + (uint32_t)n48;
+            if (np >= (uint32_t)RING_SAMPLES) np -= RING_SAMPLES;
+            A.ring_pos[stream] = np;
+            if (!lost) {
+                A.st.fs[2 * stream] = (uint8_t)fs_khz;
+                A.st.fs[2 * stream + 1] = (uint8_t)CS;
+            }
+            if (A.result) A.result[stream] = n48;
+            if (A.final_range) A.final_range[stream] = lost ? 0u : A.hdr[stream].y;
+            if (A.softclip_reset && !lost) *reinterpret_cast<float2 *>(A.softclip_reset + 2 * (size_t)stream) = make_float2(0.f, 0.f);
+        }
+        if (A.out16)
+            for (int i = (int)lane; i < L; i += 32)
+                for (int c = 0; c < C; c++) A.out16[((size_t)stream * 2 + c) * SILK_MAX_FRAME + i] = (int16_t)sample(i, c);
+    }
+}
+
+}  // namespace opn

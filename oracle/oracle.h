@@ -196,6 +196,41 @@ int orc_celt2_decode_frame_mapped(orc_synth_state *st, const uint8_t *payload, u
 int orc_celt2_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes, uint32_t transient_permille,
                      uint8_t *out, orc_celt2_side *truth);
 
+/* ---- SYNTH-SILK/1 (oracle/silk.c): SILK-only frames, PARITY UNPINNED (src/silk/decoder.rs:71-80 is unimplemented!()) ---- */
+#define ORC_SILK_MAX_FRAME 320 /* 20 ms at 16 kHz */
+#define ORC_SILK_HIST 320      /* excitation history of the long-term predictor (>= 18 ms + 2 samples) */
+typedef struct {
+    int32_t type, gidx[4], rc_idx[16], lag[4], ltp_idx[4], seed;
+    int32_t pulses[20];
+    uint32_t index[20];
+} orc_silk_chan_side;
+typedef struct {
+    orc_silk_chan_side ch[2];
+    uint32_t final_rng, tell_frac;
+} orc_silk_side;
+typedef struct {
+    int32_t slpc[16];            /* sLPC_Q14 of the last 16 samples, [15] = newest */
+    int32_t hist[ORC_SILK_HIST]; /* excitation after long-term prediction, [ORC_SILK_HIST-1] = newest */
+    int16_t a_q12[16];
+    int32_t gain_q10;
+} orc_silk_chan;
+typedef struct {
+    orc_silk_chan ch[2];
+    float rs[2][8];              /* resampler history per output channel: rs[c][j] = x[-1-j] */
+    int32_t fs_khz, stream_channels;
+} orc_silk_state;
+void orc_silk_state_init(orc_silk_state *st);
+/* payload = frame bytes after the TOC; bandwidth 0 NB / 1 MB / 2 WB; frame_ms 10 or 20.  exc_out: [2][ORC_SILK_MAX_FRAME]
+ * excitation after long-term prediction (Q14) or NULL; out16: [2][ORC_SILK_MAX_FRAME] internal-rate samples per OUTPUT channel
+ * or NULL; pcm_out: interleaved frame_ms*48*channels floats.  Returns samples per channel at 48 kHz. */
+int orc_silk_decode_frame(orc_silk_state *st, const uint8_t *payload, uint32_t len, int bandwidth, int frame_ms, int stream_channels,
+                          int channels, int lost, orc_silk_side *side, int32_t *exc_out, int16_t *out16, float *pcm_out);
+int orc_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out);
+int orc_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
+                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out);
+double orc_silk_bench(const uint8_t *packets, uint32_t n_streams, uint32_t n_frames, uint32_t pkt_bytes, int bandwidth, int frame_ms,
+                      int channels, int n_threads, float *pcm_last, uint32_t *final_rng_xor);
+
 /* SYNTH-CELT/1 packet generator on the oracle's own range encoder (same seeded draws as opn_synth_packet). */
 int orc_synth_packet(uint64_t stream_id, uint64_t frame_idx, int lm, int channels, uint32_t pkt_bytes,
                      uint32_t transient_permille, uint8_t *out);

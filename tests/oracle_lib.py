@@ -57,6 +57,26 @@ class SynthState(C.Structure):
                 ("pf_period", C.c_int32), ("pf_tapset", C.c_int32), ("pf_gain", C.c_float)]
 
 
+class SilkChanSide(C.Structure):
+    _fields_ = [("type", C.c_int32), ("gidx", C.c_int32 * 4), ("rc_idx", C.c_int32 * 16), ("lag", C.c_int32 * 4), ("ltp_idx", C.c_int32 * 4),
+                ("seed", C.c_int32), ("pulses", C.c_int32 * 20), ("index", C.c_uint32 * 20)]
+
+
+class SilkSide(C.Structure):
+    _fields_ = [("ch", SilkChanSide * 2), ("final_rng", C.c_uint32), ("tell_frac", C.c_uint32)]
+
+
+SILK_MAX_FRAME = 320
+
+
+class SilkChan(C.Structure):
+    _fields_ = [("slpc", C.c_int32 * 16), ("hist", C.c_int32 * 320), ("a_q12", C.c_int16 * 16), ("gain_q10", C.c_int32)]
+
+
+class SilkState(C.Structure):
+    _fields_ = [("ch", SilkChan * 2), ("rs", (C.c_float * 8) * 2), ("fs_khz", C.c_int32), ("stream_channels", C.c_int32)]
+
+
 OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL = range(10)
 OP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4")])
 OUT_DTYPE = np.dtype([("value", "<u4"), ("tell_frac", "<u4"), ("rng", "<u4")])
@@ -146,6 +166,12 @@ def lib():
     sig("orc_synth_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp)
     sig("orc_synth_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("orc_synth_bench", C.c_double, vp, u32, u32, u32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32))
+    sig("orc_silk_state_init", None, C.POINTER(SilkState))
+    sig("orc_silk_decode_frame", C.c_int, C.POINTER(SilkState), vp, u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SilkSide),
+        vp, vp, vp)
+    sig("orc_silk_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, u32, vp)
+    sig("orc_silk_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, C.c_int, u32, C.c_int, vp)
+    sig("orc_silk_bench", C.c_double, vp, u32, u32, u32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32))
     _lib = L
     return L
 
@@ -292,3 +318,32 @@ class SynthStream:
                                         self.channels, int(self.apply_comb), C.byref(side), ptr(y), ptr(coef), ptr(pcm))
         assert r == nf
         return side, y, coef, pcm
+
+
+def silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads=1):
+    """-> uint8 [n_frames, n_streams, pkt_bytes]: SYNTH-SILK/1 packets (TOC included) from the oracle's generator"""
+    out = np.zeros((n_frames, n_streams, pkt_bytes), np.uint8)
+    rc = lib().orc_silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads, ptr(out))
+    assert rc == 0, rc
+    return out
+
+
+class SilkStream:
+    """One decoder's oracle-side SYNTH-SILK/1 state (decoder of `channels` output channels)."""
+
+    def __init__(self, channels):
+        self.channels = channels
+        self.state = SilkState()
+        lib().orc_silk_state_init(C.byref(self.state))
+
+    def decode(self, payload, bandwidth, frame_ms, stream_channels, lost=False):
+        """-> (SilkSide, exc int32 [2, 320], out16 int16 [2, 320], pcm float32 [frame_ms*48*channels])"""
+        payload = np.frombuffer(bytes(payload), dtype=np.uint8).copy()
+        side = SilkSide()
+        exc = np.zeros((2, SILK_MAX_FRAME), np.int32)
+        out16 = np.zeros((2, SILK_MAX_FRAME), np.int16)
+        pcm = np.zeros(frame_ms * 48 * self.channels, np.float32)
+        r = lib().orc_silk_decode_frame(C.byref(self.state), ptr(payload) if len(payload) else None, len(payload), bandwidth, frame_ms,
+                                       stream_channels, self.channels, int(lost), C.byref(side), ptr(exc), ptr(out16), ptr(pcm))
+        assert r == frame_ms * 48, r
+        return side, exc, out16, pcm

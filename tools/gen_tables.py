@@ -267,6 +267,51 @@ def synth_schedule():
     return sched
 
 
+def silk_up_filter(L, taps=8, beta=8.0):
+    """Polyphase interpolator by L: phase p, tap j weighs input x[i - j] for output L*i + p."""
+    n = L * taps
+    centre = (n - 1) / 2.0
+    def i0(x):  # modified Bessel function of the first kind, order 0
+        t, term, k = 1.0, 1.0, 1
+        while term > 1e-18 * t:
+            term *= (x / (2.0 * k)) ** 2
+            t += term
+            k += 1
+        return t
+    proto = []
+    for m in range(n):
+        x = (m - centre) / L                      # in input samples
+        s = 1.0 if x == 0 else math.sin(math.pi * 0.9 * x) / (math.pi * 0.9 * x)
+        r = 2.0 * m / (n - 1) - 1.0
+        proto.append(0.9 * s * i0(beta * math.sqrt(max(0.0, 1.0 - r * r))) / i0(beta))
+    phases = []
+    for p in range(L):
+        ph = [proto[p + L * j] for j in range(taps)]
+        g = sum(ph)
+        phases.append([v / g for v in ph])
+    return phases
+
+
+def silk_ltp_filters():
+    """SYNTH-SILK/1 long-term predictor codebook: 8 symmetric 5-tap filters in Q14, total gain 0.20 .. 0.76."""
+    out = []
+    for f in range(8):
+        g = 0.2 + 0.08 * f
+        w0 = 0.5 + 0.05 * f
+        w1 = (1.0 - w0) / 2.0 * 0.8
+        w2 = (1.0 - w0) / 2.0 * 0.2
+        out += [int(round(16384.0 * g * w)) for w in (w2, w1, w0, w1, w2)]
+    return out
+
+
+SILK_TYPE_ICDF = [230, 154, 0]                                # frame type: 0 inactive, 1 unvoiced, 2 voiced
+SILK_DELTA_GAIN_ICDF = [250, 240, 220, 180, 76, 36, 16, 6, 0]  # gain index step - 4, subframes 1..3
+SILK_CONTOUR_ICDF = [200, 60, 20, 0]                          # pitch lag of a subframe - frame lag + 1
+SILK_LTP_ICDF = [224, 192, 160, 128, 96, 64, 32, 0]           # LTP filter of a subframe
+SILK_PULSES_ICDF = [120, 60, 30, 14, 6, 3, 2, 1, 0,           # pulses K of a 16-sample shell block, inactive frames
+                    200, 130, 80, 45, 25, 12, 5, 2, 0]        # ... active frames
+
+
 def fhex(x: float) -> str:
     if x == 0.0:
         return "-0.0f" if math.copysign(1, x) < 0 else "0.0f"
@@ -323,6 +368,20 @@ def emit(path, prefix, guard):
         w("  {" + ", ".join("{%d,%d,%d}" % t for t in row) + "},")
     w("};\n")
     arr("float", "COMB_GAINS", [f32(g / 32768.0) for g in COMB_GAINS_Q15], fhex, 3)
+    # SILK output resampler (RFC 6716 4.2.9: not normative, "any resampler"): polyphase windowed-sinc interpolators from the
+    # internal rates 8/12/16/24 kHz to 48 kHz.  Factor L, 8 taps per phase, prototype = sinc at 0.45 fs_in x Kaiser(beta 8),
+    # each phase normalised to unity DC gain.  Stored [L][8]: out[L i + p] = sum_j h[p][j] x[i - j].
+    for up in (2, 3, 4, 6):
+        w(f"/* {48 // up} kHz -> 48 kHz: {up} phases x 8 taps */")
+        arr("float", f"SILK_UP{up}", [f32(v) for ph in silk_up_filter(up) for v in ph], fhex, 8)
+    w("/* SYNTH-SILK/1 (DESIGN.md 3c): subframe gain 2^(1 + i*11/63) in Q10; LTP codebook [8][5] in Q14; symbol models */")
+    arr("int32_t", "SILK_GAIN_Q10", [int(round(1024.0 * 2.0 ** (1.0 + i * 11.0 / 63.0))) for i in range(64)], str, 8)
+    arr("int16_t", "SILK_LTP_Q14", silk_ltp_filters(), str, 5)
+    arr("uint8_t", "SILK_TYPE_ICDF", SILK_TYPE_ICDF, str, 16)
+    arr("uint8_t", "SILK_DELTA_GAIN_ICDF", SILK_DELTA_GAIN_ICDF, str, 16)
+    arr("uint8_t", "SILK_CONTOUR_ICDF", SILK_CONTOUR_ICDF, str, 16)
+    arr("uint8_t", "SILK_LTP_ICDF", SILK_LTP_ICDF, str, 16)
+    arr("uint8_t", "SILK_PULSES_ICDF", SILK_PULSES_ICDF, str, 9)
     w("/* 2^(j/512), j = 0..511, rounded to f32: the fractional part of a band energy (SYNTH-CELT/2 denormalisation); */")
     w("/* the crate's fast_exp2 (src/math.rs:17-19) goes through libm's exp, which no two platforms round alike */")
     arr("float", "EXP2_Q9", [f32(2.0 ** (j / 512.0)) for j in range(512)], fhex, 6)
