@@ -290,6 +290,170 @@ def run_mix(args):
         dist.destroy_process_group()
 
 
+SILK_PKT_BYTES = 80   # SILK wideband mono 20 ms at 32 kbps (TOC + SYNTH-SILK/1 payload)
+
+
+def run_silk(args):
+    """--silk: BASELINE configs[2], "16384 SILK-only wideband 16 kHz 20 ms streams: LPC synthesis + resample to 48 kHz on 1
+    B200" (SYNTH-SILK/1; mono, 80-byte packets).  Device-resident steps for `value`, the host-buffer
+    call for `e2e`, the oracle's CPU loop on a bounded sample for `cpu_baseline`.  An extra line kept under profiles/."""
+    import torch
+    import opus_native_b200 as opn
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libopusb200 has no CPU fallback")
+    pin_rank_to_cpus(local, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, K, W = args.streams, args.steps, args.warmup
+    total = K + W
+    nb, n48, ch = SILK_PKT_BYTES, 960, 1
+    lo, _ = opn.shard_range(n * world, rank, world)
+    cores = cpu_threads()
+    packets = opn.silk_fill(lo, n, 0, total, 2, 20, ch, nb, n_threads=cores)
+    bits = opn.BITSTREAM_SYNTH_CELT_1 | opn.BITSTREAM_SYNTH_SILK_1
+    dec = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, ch, 0), device=local, bitstream=bits)
+    stream = torch.cuda.ExternalStream(dec.cuda_stream, device=dev)
+    d_arena = torch.from_numpy(packets.reshape(-1)).to(dev)
+    d_off = (torch.arange(n, dtype=torch.int64, device=dev) * nb).to(torch.int32)
+    d_len = torch.full((n,), nb, dtype=torch.int32, device=dev)
+    d_res = torch.zeros(n, dtype=torch.int32, device=dev)
+    flags = opn.FLAG_DEVICE_PTRS | opn.FLAG_NO_PCM_COPY | opn.FLAG_INPUTS_READY | opn.FLAG_SILK_FRAMES
+    p_arena, p_off, p_len, p_res = d_arena.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr()
+    host_s = [0.0]
+
+    def step(f):
+        dec.decode_float_ptrs(p_arena + f * n * nb, p_off, p_len, None, 0, n48, p_res, flags)
+
+    def timed(k0, k1):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            h0 = time.perf_counter()
+            for f in range(k0, k1):
+                step(f)
+            host_s[0] = time.perf_counter() - h0
+            dec.join()
+            e1.record()
+        dec.synchronize()
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3
+
+    for f in range(W):
+        step(f)
+    dec.synchronize()
+    assert int((d_res != n48).sum().item()) == 0, "decode reported errors"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dec.stats(reset=True)
+    with sampler.region():
+        t = max_over_ranks(timed(W, total))
+    launches = sum(dec.stats(reset=True)["launches"])
+    host_enqueue_ms = 1e3 * host_s[0] / K
+    dec.reset()
+    dec.enable_timing(True)
+    for f in range(W):
+        step(f)
+    dec.stats(reset=True)
+    with sampler.region():
+        timed(W, total)
+    st = dec.stats(reset=True)
+    dec.enable_timing(False)
+    k0_ms, k1_ms = st["ms"][0] / K, st["ms"][1] / K
+
+    # end to end: pinned host packets in, pinned host PCM out, two calls in flight
+    dec2 = opn.BatchDecoder(n, opn.DecoderConfiguration(48000, ch, 0), device=local, bitstream=bits)
+    h_arena = torch.from_numpy(packets.reshape(-1)).pin_memory()
+    h_pcm = [torch.zeros((n, n48 * ch), dtype=torch.float32).pin_memory() for _ in range(2)]
+    a_np, p_np = h_arena.numpy(), [x.numpy() for x in h_pcm]
+    offs = (np.arange(n, dtype=np.uint32) * nb)
+    lens = np.full(n, nb, np.uint32)
+    res = [np.zeros(n, np.int32) for _ in range(2)]
+
+    def run_e2e(k0, k1):
+        probe, ticket = 0.0, None
+        for f in range(k0, k1):
+            q = f & 1
+            tk = dec2.decode_float_ptrs(a_np.ctypes.data + f * n * nb, offs.ctypes.data, lens.ctypes.data, p_np[q].ctypes.data, n48 * ch, n48,
+                                        res[q].ctypes.data, opn.FLAG_SUBMIT_ONLY)
+            if ticket is not None:
+                dec2.wait(ticket)
+                probe += float(p_np[(f - 1) & 1][0, 0]) + float(p_np[(f - 1) & 1][-1, -1])
+            ticket = tk
+        dec2.wait(ticket)
+        return probe + float(p_np[(k1 - 1) & 1][0, 0]) + float(p_np[(k1 - 1) & 1][-1, -1])
+
+    Ke = min(K, 50)
+    run_e2e(0, W)
+    barrier()
+    with sampler.region():
+        h0 = time.perf_counter()
+        checksum = run_e2e(W, W + Ke)
+        t_e2e = max_over_ranks(time.perf_counter() - h0)
+    assert all(int((r != n48).sum()) == 0 for r in res)
+    clocks = sampler.stop() if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        ns, nfr = min(n, 2048), min(total, 25)
+        x = ctypes.c_uint32(0)
+        sample = np.ascontiguousarray(packets[:nfr, :ns])
+        tc = O.lib().orc_silk_bench(O.ptr(sample), ns, nfr, nb, 2, 20, ch, cores, None, ctypes.byref(x))
+        cpu = {"value": ns * nfr / tc * FRAME_S, "unit": "streams", "cores": cores, "kind": "port",
+               "sample": f"{nfr} chained frames x {ns} streams of the same packets, C oracle (oracle/silk.c), one thread per core, {tc:.2f} s wall"}
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        chan_frames = n * ch
+        # per channel-frame: 3840 B of PCM out, the 144-byte side record in, the filter state in and out (sLPC 64, A_Q12 32,
+        # gain 4, resampler 32), the excitation history read by the long-term predictor and written back (1280 each)
+        algo = chan_frames * (3840 + 144 + 2 * 132 + 2 * 1280)
+        emit({
+            "metric": "concurrent_realtime_48k_streams_decoded", "value": world * n * K / t * FRAME_S, "unit": "streams", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i32+f32", "data": "synthetic",
+            "config": {"workload": f"{n} SILK-only wideband (16 kHz internal) 20 ms mono streams per GPU (BASELINE configs[2]; SYNTH-SILK/1, "
+                                   f"{nb} B packets): range decode + PVQ shell blocks + long-term prediction + integer LPC synthesis + "
+                                   "polyphase resampler to 48 kHz",
+                       "streams_per_gpu": n, "frames_per_step_per_gpu": n, "packet_bytes": nb, "frame_ms": 20, "channels": ch},
+            "detail": {"cache": f"{total} distinct packet sets resident in HBM, each read once; every step writes {n * 3840 / 1e6:.1f} MB of PCM",
+                       "per_kernel_ms": {"k_silk_rangedec": k0_ms, "k_silk_frame": k1_ms}, "host_enqueue_ms_per_step": host_enqueue_ms,
+                       "e2e_checksum": checksum, "peak_source": peak_src},
+            "e2e": {"value": world * n * Ke / t_e2e * FRAME_S, "unit": "streams", "h2d_bytes_per_step": n * nb + 4 * 4 * n,
+                    "d2h_bytes_per_step": n * n48 * ch * 4, "ms_per_step": 1e3 * t_e2e / Ke, "steps": Ke},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_silk_frame<1,1> (excitation + LTP + LPC synthesis across streams + resampler + PCM store)",
+                         "achieved": algo / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / (k1_ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": algo,
+                         "bytes_note": "per channel-frame: 3840 B PCM + 144 B side record + 2 x 132 B filter state + 2 x 1280 B excitation history"},
+            "cpu_baseline": cpu, "clocks": clocks,
+        })
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -322,9 +486,18 @@ def main():
                     help="1: SYNTH-CELT/1 (the headline workload), 2: SYNTH-CELT/2 (allocation-driven frames; kept next to it under profiles/)")
     ap.add_argument("--mix", action="store_true",
                     help="extra workload: per-packet frame sizes 2.5-20 ms with transients, device-resident (BASELINE configs[4] shape, CELT part)")
+    ap.add_argument("--silk", action="store_true",
+                    help="extra workload: BASELINE configs[2], SILK-only wideband 20 ms mono streams (SYNTH-SILK/1), default 16384 streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     quiet_stdout()
+    if args.silk:
+        if args.impl != "b200":
+            raise SystemExit("--silk is an extra line of the b200 arm")
+        if args.streams == 4096:
+            args.streams = 16384
+        run_silk(args)
+        return
     if args.mix:
         if args.impl != "b200":
             raise SystemExit("--mix is an extra line of the b200 arm")

@@ -293,10 +293,13 @@ cudaError_t upload_tables(int device)
         for (int i = 0; i < 4; i++) sk.contour_icdf[i] = OPN_SILK_CONTOUR_ICDF[i];
         for (int i = 0; i < 8; i++) sk.ltp_icdf[i] = OPN_SILK_LTP_ICDF[i];
         for (int i = 0; i < 18; i++) sk.pulses_icdf[i] = OPN_SILK_PULSES_ICDF[i];
-        for (int i = 0; i < 48; i++) sk.up[0][i] = OPN_SILK_UP6[i];
-        for (int i = 0; i < 32; i++) sk.up[1][i] = OPN_SILK_UP4[i];
-        for (int i = 0; i < 24; i++) sk.up[2][i] = OPN_SILK_UP3[i];
+        static float up[3][48];
+        std::memset(up, 0, sizeof(up));
+        for (int i = 0; i < 48; i++) up[0][i] = OPN_SILK_UP6[i];
+        for (int i = 0; i < 32; i++) up[1][i] = OPN_SILK_UP4[i];
+        for (int i = 0; i < 24; i++) up[2][i] = OPN_SILK_UP3[i];
         e = cudaMemcpyToSymbol(g_silk, &sk, sizeof(sk));
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_silk_up, up, sizeof(up));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_silk_frame<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)silk_frame_smem());

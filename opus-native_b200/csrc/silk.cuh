@@ -26,11 +26,15 @@ struct SilkTables {
     int32_t gain_q10[64];
     int16_t ltp_q14[40];
     uint8_t type_icdf[4], delta_icdf[12], contour_icdf[4], ltp_icdf[8], pulses_icdf[20];
-    float up[3][48];  // [0] x6 (8 kHz), [1] x4 (12 kHz), [2] x3 (16 kHz): [phase][tap]
 };
 __device__ SilkTables g_silk;
+// resampler taps [0] x6 (8 kHz), [1] x4 (12 kHz), [2] x3 (16 kHz), [phase][tap]: constant memory, so that the fully unrolled
+// interpolation reads them as instruction operands
+__constant__ float c_silk_up[3][48];
 
 __device__ __forceinline__ int32_t silk_smulwb(int32_t a, int32_t b16) { return (int32_t)(((int64_t)a * (int64_t)b16) >> 16); }
+// the same with the 16-bit factor pre-shifted: (a * (b << 16)) >> 32 == (a * b) >> 16, one IMAD.HI
+__device__ __forceinline__ int32_t silk_smulwb_sh(int32_t a, int32_t b16_shl16) { return __mulhi(a, b16_shl16); }
 __device__ __forceinline__ int32_t silk_smulww(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * (int64_t)b) >> 16); }
 __device__ __forceinline__ int32_t silk_sat16(int32_t x) { return max(-32768, min(32767, x)); }
 
@@ -154,12 +158,57 @@ __device__ __forceinline__ void silk_divmod(int t, int up, int &q, int &r)
     r = t - q * up;
 }
 
-constexpr size_t silk_frame_smem() { return (size_t)(SILK_MAX_FRAME * SILK_RS + 16 * SILK_RS + 16 * SILK_RS + 4 * SILK_RS) * 4 + 8 * SILK_ROWS; }
+constexpr int SILK_LEAD = 8;  // rows before sample 0: the resampler's history (x[-7..-1]) sits in front of the frame
+constexpr size_t silk_frame_smem() { return (size_t)((SILK_MAX_FRAME + SILK_LEAD) * SILK_RS + 16 * SILK_RS + 16 * SILK_RS + 4 * SILK_RS) * 4 + 8 * SILK_ROWS; }
+
+// Polyphase interpolation by UP of one item's NCH channels (x[i * SILK_RS + c], floats, history at i = -7..-1) and the PCM
+// stores: y[UP i + p] = sum_j h[p][j] x[i - j] summed in tap order, then the merge of decoder.rs:722-729 onto a zero CELT part.
+// One lane per INPUT sample: its eight-sample window is loaded once for the UP outputs it produces.
+template <int UP, int NCH, int C>
+__device__ __forceinline__ void silk_resample_store(const float *x, int L, uint32_t lane, float *ring, uint32_t pos, float *dense, float gain,
+                                                    const float *rs1 /* C == 2 from one channel: history of output channel 1 */)
+{
+    constexpr int T = UP == 6 ? 0 : UP == 4 ? 1 : 2;
+    for (int i0 = 0; i0 < L; i0 += 32) {
+        const int i = i0 + (int)lane;
+        if (i >= L) continue;
+        float xv[2][8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            xv[0][j] = x[(i - j) * SILK_RS];
+            xv[1][j] = NCH == 2 ? x[(i - j) * SILK_RS + 1] : xv[0][j];
+            if (NCH == 1 && C == 2 && rs1 && i - j < 0) xv[1][j] = rs1[-1 - (i - j)];
+        }
+#pragma unroll
+        for (int p = 0; p < UP; p++) {
+            float o[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if (c == 1 && C == 1) continue;
+                float acc = c_silk_up[T][8 * p] * xv[c][0];
+#pragma unroll
+                for (int j = 1; j < 8; j++) acc = acc + c_silk_up[T][8 * p + j] * xv[c][j];
+                o[c] = 0.0f + (1.0f / 32768.0f) * acc;
+            }
+            const int t = UP * i + p;
+            uint32_t rp = pos + (uint32_t)t;
+            if (rp >= (uint32_t)RING_SAMPLES) rp -= RING_SAMPLES;
+            if (C == 2) {
+                *reinterpret_cast<float2 *>(ring + (size_t)rp * 2) = make_float2(o[0], o[1]);
+                if (dense) *reinterpret_cast<float2 *>(dense + (size_t)t * 2) = make_float2(o[0] * gain, o[1] * gain);
+            } else {
+                ring[rp] = o[0];
+                if (dense) dense[t] = o[0] * gain;
+            }
+        }
+    }
+}
 
 template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_silk_frame(SilkArgs A)
 {
     extern __shared__ __align__(16) uint8_t silk_smem[];
-    int32_t *s_res = reinterpret_cast<int32_t *>(silk_smem);  // [SILK_MAX_FRAME][SILK_RS]: excitation, then internal-rate samples
+    // [SILK_LEAD + SILK_MAX_FRAME][SILK_RS]: excitation, then internal-rate samples (as floats); s_res points at sample 0
+    int32_t *s_res = reinterpret_cast<int32_t *>(silk_smem) + SILK_LEAD * SILK_RS;
     int32_t *s_a = s_res + SILK_MAX_FRAME * SILK_RS;          // [16][SILK_RS] A_Q12
     int32_t *s_lpc = s_a + 16 * SILK_RS;                      // [16][SILK_RS] sLPC_Q14 window, [15] newest
     int32_t *s_gain = s_lpc + 16 * SILK_RS;                   // [4][SILK_RS]
@@ -238,7 +287,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
                 for (int f = 0; f < nb_subfr; f++) {
                     const int lag = (int)r->lag[f];
                     const int16_t *B = g_silk.ltp_q14 + 5 * r->ltp[f];
-                    const int32_t b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4];
+                    const int32_t b0 = (int32_t)B[0] << 16, b1 = (int32_t)B[1] << 16, b2 = (int32_t)B[2] << 16, b3 = (int32_t)B[3] << 16, b4 = (int32_t)B[4] << 16;
                     const int span = min(32, lag - 2), end = (f + 1) * sub;
                     for (int i0 = f * sub; i0 < end; i0 += span) {
                         const int i = i0 + (int)lane;
@@ -250,7 +299,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
                             for (int k = 0; k < 5; k++) {
                                 const int q = top - k;
                                 const int32_t v = q >= 0 ? res[q * SILK_RS] : (reset ? 0 : hist[SILK_HIST + q]);
-                                pred += silk_smulwb(v, bk[k]);
+                                pred += silk_smulwb_sh(v, bk[k]);
                             }
                             res[i * SILK_RS] += (int32_t)((uint32_t)pred << 2);
                         }
@@ -306,38 +355,44 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
     }
     __syncthreads();
 
-    // ---- phase B: warp 0, one lane per row.  SURVEY.md appendix B:
+    // ---- phase B: one warp, one lane per row (the warp differs from CTA to CTA so that the CTAs of an SM put theirs on
+    // different schedulers).  SURVEY.md appendix B:
     //   pred_Q10 = order/2 + sum_k smulwb(sLPC_Q14[i-1-k], A_Q12[k]); sLPC_Q14[i] = sat32(res_Q14[i] + (pred_Q10 << 4));
     //   out[i] = sat16(rshift_round(smulww(sLPC_Q14[i], gain_Q10), 8))
-    if (warp == 0) {
+    if (warp == (blockIdx.x & (SILK_WARPS - 1))) {
         const uint32_t row = lane;
         const int fs_khz = s_meta[row * 8];
         const int sub = 5 * fs_khz, L = nb_subfr * sub;
         int Lmax = L;
 #pragma unroll
         for (int o = 16; o; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, o));
-        int32_t a[16], s[16];
+        int32_t a[16], s[16];  // a: A_Q12 << 16 (smulwb is then one multiply-high)
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            a[k] = s_a[k * SILK_RS + row];
+            a[k] = s_a[k * SILK_RS + row] << 16;
             s[k] = s_lpc[k * SILK_RS + row];  // s[15] = sLPC[-1]; sample i lives in s[i & 15]
         }
         const int32_t rnd = fs_khz == 16 ? 8 : 5;
         const int32_t g0 = s_gain[row], g1 = s_gain[SILK_RS + row], g2 = s_gain[2 * SILK_RS + row], g3 = s_gain[3 * SILK_RS + row];
+        const int e1 = sub, e2 = 2 * sub, e3 = 3 * sub;
         for (int i0 = 0; i0 < Lmax; i0 += 16) {
 #pragma unroll
             for (int u = 0; u < 16; u++) {
                 const int i = i0 + u;
                 if (i < L) {
-                    int32_t pred = rnd;
+                    // the taps on older samples first: only the last product waits for the previous sample
+                    int32_t pa = rnd, pb = 0;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) pred += silk_smulwb(s[(u - 1 - k) & 15], a[k]);
+                    for (int k = 15; k >= 0; k -= 2) {
+                        pa += silk_smulwb_sh(s[(u - 1 - k) & 15], a[k]);
+                        pb += silk_smulwb_sh(s[(u - k) & 15], a[k - 1]);
+                    }
+                    const int32_t pred = pa + pb;
                     const int64_t v = (int64_t)s_res[i * SILK_RS + row] + (int64_t)pred * 16;
                     const int32_t v32 = v > 2147483647ll ? 2147483647 : v < -2147483648ll ? (int32_t)0x80000000 : (int32_t)v;
                     s[u] = v32;
-                    const int f = i / sub;
-                    const int32_t w = silk_smulww(v32, f == 0 ? g0 : f == 1 ? g1 : f == 2 ? g2 : g3);
-                    s_res[i * SILK_RS + row] = silk_sat16(((w >> 7) + 1) >> 1);
+                    const int32_t w = silk_smulww(v32, i < e1 ? g0 : i < e2 ? g1 : i < e3 ? g2 : g3);
+                    s_res[i * SILK_RS + row] = __float_as_int((float)silk_sat16(((w >> 7) + 1) >> 1));  // exact: |x| <= 2^15
                 }
             }
         }
@@ -356,7 +411,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
                 A.st.slpc[chs * 16 + 15 - k] = v;
             }
 #pragma unroll
-            for (int k = 0; k < 16; k++) A.st.a_q12[chs * 16 + k] = (int16_t)a[k];
+            for (int k = 0; k < 16; k++) A.st.a_q12[chs * 16 + k] = (int16_t)(a[k] >> 16);
             A.st.gain[chs] = nb_subfr == 4 ? g3 : g1;
         }
     }
@@ -388,50 +443,37 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
         const int fs_khz = s_meta[row0 * 8];
         const bool lost = s_meta[row0 * 8 + 1], reset = s_meta[row0 * 8 + 2];
         const int L = nb_subfr * 5 * fs_khz, up = 48 / fs_khz;
-        const float *h = g_silk.up[up == 6 ? 0 : up == 4 ? 1 : 2];
         const uint32_t pos = A.ring_pos[stream];
         float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
         float *rs = A.st.rs + (size_t)stream * 16;
-        // internal-rate sample i of output channel c (decoder.rs:332 stream_channels -> channels)
-        auto sample = [&](int i, int c) -> float {
-            if (i < 0) return reset ? 0.0f : rs[c * 8 + (-1 - i)];
-            const int32_t m = s_res[i * SILK_RS + row0];
-            if (CS == 2 && C == 2) {
-                const int32_t sd = s_res[i * SILK_RS + row0 + 1];
-                return (float)silk_sat16(c == 0 ? m + sd : m - sd);
+        float *x = reinterpret_cast<float *>(s_res) + row0;  // sample i of coded channel c at x[i * SILK_RS + c]
+        constexpr int NCH = (CS == 2 && C == 2) ? 2 : 1;      // channels that go through the interpolator
+        // stream_channels -> channels (decoder.rs:332): mid/side -> left/right in place; a mono packet feeds both outputs; a mono
+        // decoder takes the mid channel of a stereo packet
+        if (NCH == 2) {
+            for (int i = (int)lane; i < L; i += 32) {
+                const float m = x[i * SILK_RS], sd = x[i * SILK_RS + 1];
+                x[i * SILK_RS] = fminf(fmaxf(m + sd, -32768.0f), 32767.0f);  // sat16 of an exact integer sum
+                x[i * SILK_RS + 1] = fminf(fmaxf(m - sd, -32768.0f), 32767.0f);
             }
-            return (float)m;
-        };
-        float hist_new[2] = {0.0f, 0.0f};  // lane j < 7 keeps x[L-1-j] of both channels
-        if (lane < 7u) {
-#pragma unroll
-            for (int c = 0; c < C; c++) hist_new[c] = sample(L - 1 - (int)lane, c);
         }
-        for (int t = (int)lane; t < n48; t += 32) {
-            int i, p;
-            silk_divmod(t, up, i, p);
-            float out[C];
+        if (lane < 7u) {  // resampler history in front of the frame: x[-1-j] = rs[c][j]
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                float acc = h[8 * p] * sample(i, c);
+            for (int c = 0; c < NCH; c++) x[-(1 + (int)lane) * SILK_RS + c] = reset ? 0.0f : rs[c * 8 + lane];
+        }
+        float rs1[8];  // a mono packet in a stereo decoder: output channel 1 keeps its own history (it differs after a stereo packet)
+        if (NCH == 1 && C == 2) {
 #pragma unroll
-                for (int j = 1; j < 8; j++) acc = acc + h[8 * p + j] * sample(i - j, c);
-                out[c] = 0.0f + (1.0f / 32768.0f) * acc;  // decoder.rs:722-729 onto a zero CELT contribution
-            }
-            uint32_t rp = pos + (uint32_t)t;
-            if (rp >= (uint32_t)RING_SAMPLES) rp -= RING_SAMPLES;
-            if (C == 2) {
-                *reinterpret_cast<float2 *>(ring + (size_t)rp * 2) = make_float2(out[0], out[1]);
-                if (dense) *reinterpret_cast<float2 *>(dense + (size_t)t * 2) = make_float2(out[0] * A.gain, out[C - 1] * A.gain);
-            } else {
-                ring[rp] = out[0];
-                if (dense) dense[t] = out[0] * A.gain;
-            }
+            for (int j = 0; j < 8; j++) rs1[j] = (reset || j == 7) ? 0.0f : rs[8 + j];
         }
         __syncwarp();
+        const float *r1 = (NCH == 1 && C == 2) ? rs1 : nullptr;
+        if (up == 3) silk_resample_store<3, NCH, C>(x, L, lane, ring, pos, dense, A.gain, r1);
+        else if (up == 4) silk_resample_store<4, NCH, C>(x, L, lane, ring, pos, dense, A.gain, r1);
+        else silk_resample_store<6, NCH, C>(x, L, lane, ring, pos, dense, A.gain, r1);
         if (lane < 7u) {
 #pragma unroll
-            for (int c = 0; c < C; c++) rs[c * 8 + lane] = hist_new[c];
+            for (int c = 0; c < C; c++) rs[c * 8 + lane] = x[(L - 1 - (int)lane) * SILK_RS + (NCH == 2 ? c : 0)];
         }
         if (lane == 0) {
             uint32_t np = pos + (uint32_t)n48;
@@ -447,7 +489,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
         }
         if (A.out16)
             for (int i = (int)lane; i < L; i += 32)
-                for (int c = 0; c < C; c++) A.out16[((size_t)stream * 2 + c) * SILK_MAX_FRAME + i] = (int16_t)sample(i, c);
+                for (int c = 0; c < C; c++) A.out16[((size_t)stream * 2 + c) * SILK_MAX_FRAME + i] = (int16_t)x[i * SILK_RS + (NCH == 2 ? c : 0)];
     }
 }
 
