@@ -179,6 +179,7 @@ struct SilkArgs {
     opn_silk_side *side;   // or nullptr
     int32_t *exc_out;      // [n_streams][2][SILK_MAX_FRAME] or nullptr
     int16_t *out16;        // [n_streams][2][SILK_MAX_FRAME] or nullptr
+    unsigned long long *phase_clk;  // measurement (OPN_SILK_CLK=1): [3] cycles in phases A, B, C summed over CTAs, [3] = CTAs; else nullptr
 };
 
 // ---- launchers (opn_kernels.cu).  All return a cudaError_t and never synchronise.

@@ -1,5 +1,7 @@
 // opn_kernels.cu -- the single CUDA translation unit of libopusb200 (sm_100a, -fmad=false).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -570,9 +572,24 @@ cudaError_t launch_silk_rangedec(const SilkArgs &a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_silk_frame(const SilkArgs &a, cudaStream_t st)
+cudaError_t launch_silk_frame(const SilkArgs &a0, cudaStream_t st)
 {
-    if (a.n_items == 0) return cudaSuccess;
+    if (a0.n_items == 0) return cudaSuccess;
+    SilkArgs a = a0;
+    static unsigned long long *clk = [] {  // OPN_SILK_CLK=1: per-phase cycle counters, printed when the process exits
+        unsigned long long *p = nullptr;
+        const char *e = std::getenv("OPN_SILK_CLK");
+        if (e && e[0] == '1' && cudaMallocManaged(&p, 4 * sizeof(unsigned long long)) == cudaSuccess) {
+            std::memset(p, 0, 4 * sizeof(unsigned long long));
+            static unsigned long long *keep = p;
+            std::atexit([] {
+                if (keep[3]) fprintf(stderr, "k_silk_frame cycles per CTA: A %.0f  B %.0f  C %.0f  (%llu CTAs)\n", (double)keep[0] / keep[3],
+                                     (double)keep[1] / keep[3], (double)keep[2] / keep[3], keep[3]);
+            });
+        }
+        return p;
+    }();
+    a.phase_clk = clk;
     const int cs = a.stream_channels, c = a.channels;
     if (cs < 1 || cs > 2 || c < 1 || c > 2 || (a.frame_ms != 10 && a.frame_ms != 20)) return cudaErrorInvalidValue;
     const uint32_t items_per_cta = (uint32_t)(SILK_ROWS / cs), grid = (a.n_items + items_per_cta - 1u) / items_per_cta;

@@ -215,6 +215,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
     // per row: [0] fs_khz (0 = the row does nothing), [1] lost, [2] state was reset, [3] silent (lost before any frame)
     uint8_t *s_meta = reinterpret_cast<uint8_t *>(s_gain + 4 * SILK_RS);  // [SILK_ROWS][8]
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const long long clk0 = A.phase_clk ? clock64() : 0;
     constexpr uint32_t ITEMS = SILK_ROWS / CS;
     const uint32_t item0 = blockIdx.x * ITEMS;
     const int nb_subfr = A.frame_ms / 5;
@@ -249,7 +250,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
         if (lane < 16u) s_lpc[lane * SILK_RS + row] = reset ? 0 : A.st.slpc[chs * 16 + lane];
         if (lost) {
             for (int i = (int)lane; i < L; i += 32) res[i * SILK_RS] = 0;
-            if (lane < 16u) s_a[lane * SILK_RS + row] = (int32_t)A.st.a_q12[chs * 16 + lane];
+            if (lane < 16u) s_a[lane * SILK_RS + row] = (int32_t)A.st.a_q12[chs * 16 + lane] << 16;
             if (lane < 4u) s_gain[lane * SILK_RS + row] = A.st.gain[chs];
         } else {
             const SilkRec *r = A.rec + chs;
@@ -319,7 +320,9 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
                 }
                 if (lane < 16u) {
                     const int32_t x = (int)lane < order ? (int32_t)(0u - (uint32_t)cn) : 0;
-                    s_a[lane * SILK_RS + row] = silk_sat16(((x >> 11) + 1) >> 1);
+                    const int32_t aq = silk_sat16(((x >> 11) + 1) >> 1);
+                    s_a[lane * SILK_RS + row] = aq << 16;  // pre-shifted: smulwb becomes one multiply-high in phase B
+                    A.st.a_q12[chs * 16 + lane] = (int16_t)aq;
                 }
                 if (lane < 4u) s_gain[lane * SILK_RS + row] = g_silk.gain_q10[r->gidx[min((int)lane, nb_subfr - 1)]];
             }
@@ -355,68 +358,70 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
     }
     __syncthreads();
 
-    // ---- phase B: one warp, one lane per row (the warp differs from CTA to CTA so that the CTAs of an SM put theirs on
-    // different schedulers).  SURVEY.md appendix B:
+    // ---- phase B: warp 0, one lane per row (the hardware spreads the warp slots of co-resident CTAs over the four schedulers: picking
+    // the warp by hardware slot measured the same, picking it by blockIdx measured 5-25 % slower).  SURVEY.md appendix B:
     //   pred_Q10 = order/2 + sum_k smulwb(sLPC_Q14[i-1-k], A_Q12[k]); sLPC_Q14[i] = sat32(res_Q14[i] + (pred_Q10 << 4));
     //   out[i] = sat16(rshift_round(smulww(sLPC_Q14[i], gain_Q10), 8))
-    if (warp == (blockIdx.x & (SILK_WARPS - 1))) {
+    const long long clk1 = A.phase_clk ? clock64() : 0;
+    if (warp == 0) {
         const uint32_t row = lane;
         const int fs_khz = s_meta[row * 8];
         const int sub = 5 * fs_khz, L = nb_subfr * sub;
         int Lmax = L;
 #pragma unroll
         for (int o = 16; o; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, o));
-        int32_t a[16], s[16];  // a: A_Q12 << 16 (smulwb is then one multiply-high)
+        // a: A_Q12 << 16 (smulwb is then one multiply-high).  s[0..15]: the window sLPC[i0-16 .. i0-1], oldest first; four samples
+        // per iteration land in s[16..19], then the window slides by four.  (Sixteen samples per iteration with the window as a
+        // ring needed no moves but made the loop 11 KB of code: the four co-resident CTAs' serial warps then ran 25 % slower on
+        // four schedulers than on one -- instruction fetch, not arithmetic, was the limit.)
+        int32_t a[16], s[20];
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            a[k] = s_a[k * SILK_RS + row] << 16;
-            s[k] = s_lpc[k * SILK_RS + row];  // s[15] = sLPC[-1]; sample i lives in s[i & 15]
+            a[k] = s_a[k * SILK_RS + row];
+            s[k] = s_lpc[k * SILK_RS + row];
         }
         const int32_t rnd = fs_khz == 16 ? 8 : 5;
         const int32_t g0 = s_gain[row], g1 = s_gain[SILK_RS + row], g2 = s_gain[2 * SILK_RS + row], g3 = s_gain[3 * SILK_RS + row];
         const int e1 = sub, e2 = 2 * sub, e3 = 3 * sub;
-        for (int i0 = 0; i0 < Lmax; i0 += 16) {
+        int32_t *rp = s_res + row;
+#pragma unroll 1
+        for (int i0 = 0; i0 < Lmax; i0 += 4) {
+            const bool act = i0 < L;  // L is a multiple of 8: rows of a shorter frame (mixed bandwidths in one CTA) idle through the tail
+            const int32_t g = i0 < e1 ? g0 : i0 < e2 ? g1 : i0 < e3 ? g2 : g3;  // subframes are multiples of 8 samples too
 #pragma unroll
-            for (int u = 0; u < 16; u++) {
+            for (int u = 0; u < 4; u++) {
                 const int i = i0 + u;
-                if (i < L) {
-                    // the taps on older samples first: only the last product waits for the previous sample
-                    int32_t pa = rnd, pb = 0;
+                // four partial sums; the tap on the previous sample comes last, so that only one product and one sum wait for it
+                int32_t p0 = rnd, p1 = 0, p2 = 0, p3 = 0;
 #pragma unroll
-                    for (int k = 15; k >= 0; k -= 2) {
-                        pa += silk_smulwb_sh(s[(u - 1 - k) & 15], a[k]);
-                        pb += silk_smulwb_sh(s[(u - k) & 15], a[k - 1]);
-                    }
-                    const int32_t pred = pa + pb;
-                    const int64_t v = (int64_t)s_res[i * SILK_RS + row] + (int64_t)pred * 16;
-                    const int32_t v32 = v > 2147483647ll ? 2147483647 : v < -2147483648ll ? (int32_t)0x80000000 : (int32_t)v;
-                    s[u] = v32;
-                    const int32_t w = silk_smulww(v32, i < e1 ? g0 : i < e2 ? g1 : i < e3 ? g2 : g3);
-                    s_res[i * SILK_RS + row] = __float_as_int((float)silk_sat16(((w >> 7) + 1) >> 1));  // exact: |x| <= 2^15
+                for (int k = 15; k >= 3; k -= 4) {
+                    p0 += silk_smulwb_sh(s[15 + u - k], a[k]);
+                    p1 += silk_smulwb_sh(s[16 + u - k], a[k - 1]);
+                    p2 += silk_smulwb_sh(s[17 + u - k], a[k - 2]);
+                    p3 += silk_smulwb_sh(s[18 + u - k], a[k - 3]);
                 }
+                const int32_t pred = (p0 + p1) + (p2 + p3);
+                const int64_t v = (int64_t)rp[i * SILK_RS] + (int64_t)pred * 16;
+                const int32_t v32 = v > 2147483647ll ? 2147483647 : v < -2147483648ll ? (int32_t)0x80000000 : (int32_t)v;
+                s[16 + u] = v32;
+                const int32_t w = silk_smulww(v32, g);
+                if (act) rp[i * SILK_RS] = __float_as_int((float)silk_sat16(((w >> 7) + 1) >> 1));  // exact: |x| <= 2^15
             }
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[k] = act ? s[k + 4] : s[k];
         }
         if (fs_khz) {
             const uint32_t item = item0 + row / CS, c = row % CS;
             const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
             const size_t chs = (size_t)stream * 2 + c;
-            // the window is a ring indexed by i & 15: after L samples (L is a multiple of 8, not always of 16) the newest
-            // is s[(L - 1) & 15]
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                // slpc[15 - k] = sLPC[L - 1 - k] = s[(L - 1 - k) & 15]
-                int32_t v = s[0];
-#pragma unroll
-                for (int q = 1; q < 16; q++) v = ((L - 1 - k) & 15) == q ? s[q] : v;
-                A.st.slpc[chs * 16 + 15 - k] = v;
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++) A.st.a_q12[chs * 16 + k] = (int16_t)(a[k] >> 16);
+            for (int k = 0; k < 16; k++) A.st.slpc[chs * 16 + k] = s[k];
             A.st.gain[chs] = nb_subfr == 4 ? g3 : g1;
         }
     }
     __syncthreads();
 
+    const long long clk2 = A.phase_clk ? clock64() : 0;
     // ---- phase C: one warp per item
     for (uint32_t it = warp; it < ITEMS; it += SILK_WARPS) {
         const uint32_t item = item0 + it;
@@ -490,6 +495,16 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
         if (A.out16)
             for (int i = (int)lane; i < L; i += 32)
                 for (int c = 0; c < C; c++) A.out16[((size_t)stream * 2 + c) * SILK_MAX_FRAME + i] = (int16_t)x[i * SILK_RS + (NCH == 2 ? c : 0)];
+    }
+    if (A.phase_clk) {  // measurement only (OPN_SILK_CLK=1): cycles per phase summed over the CTAs
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long clk3 = clock64();
+            atomicAdd(A.phase_clk + 0, (unsigned long long)(clk1 - clk0));
+            atomicAdd(A.phase_clk + 1, (unsigned long long)(clk2 - clk1));
+            atomicAdd(A.phase_clk + 2, (unsigned long long)(clk3 - clk2));
+            atomicAdd(A.phase_clk + 3, 1ull);
+        }
     }
 }
 
