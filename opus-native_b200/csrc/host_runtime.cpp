@@ -523,7 +523,11 @@ int run_silk_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offs
     a.result = d_result;
     a.final_range = b->d_final;
     a.softclip_reset = softclip_reset ? b->d_softclip : nullptr;
-    int rc = join_groups(b);  // CELT frame kernels of these streams may still run on the group streams
+    // a large device-resident bucket (item k = stream k) runs as NGROUPS concurrent launches, group g on the stream that owns
+    // streams [n g / G, n (g+1) / G) -- the same cut as the CELT frame kernel's, so a stream's frames stay in order whatever it sends
+    const bool grouped = !b->timing && opn_batch::NGROUPS > 1 && !d_stream_idx && n_items == b->n && n_items >= opn_batch::GROUP_MIN_ITEMS;
+    int rc = OPN_OK;
+    if (!grouped) rc = join_groups(b);  // frame kernels of these streams may still run on the group streams
     if (rc) return rc;
     if (b->timing) {
         if (inputs_on == 2) {
@@ -550,13 +554,33 @@ int run_silk_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offs
         CU(launch_silk_rangedec(a, srd));
         CU(cudaEventRecord(b->ev_rd[p], srd));
         b->launches[0]++;
-        CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
-        CU(launch_silk_frame(a, b->stream));
-        b->launches[1]++;
+        if (!grouped) {
+            CU(cudaStreamWaitEvent(b->stream, b->ev_rd[p], 0));
+            CU(launch_silk_frame(a, b->stream));
+            b->launches[1]++;
+        } else {
+            // like the CELT frame kernel: contiguous thirds of the streams on three CUDA streams, each after its own previous
+            // frames.  The serial LPC phase of one group's CTAs then overlaps the parallel phases of the others'.
+            CU(cudaEventRecord(b->ev_sw, b->stream));
+            for (int g = 0; g < opn_batch::NGROUPS; g++) {
+                cudaStream_t st = g == 0 ? b->stream : b->stream_fr[g];
+                if (g > 0 && !b->fr_pending[g]) CU(cudaStreamWaitEvent(st, b->ev_sw, 0));
+                CU(cudaStreamWaitEvent(st, b->ev_rd[p], 0));
+                a.item0 = group_first(n_items, g, opn_batch::NGROUPS);
+                a.item_end = group_first(n_items, g + 1, opn_batch::NGROUPS);
+                CU(launch_silk_frame(a, st));
+                b->launches[1]++;
+                if (g > 0) {
+                    CU(cudaEventRecord(b->ev_fr[p][g], st));
+                    b->fr_pending[g] = true;
+                    b->fr_last_set[g] = p;
+                }
+            }
+        }
     }
     CU(cudaEventRecord(b->ev_k1[p], b->stream));
     b->k1_recorded[p] = true;
-    b->k1_grouped[p] = false;
+    b->k1_grouped[p] = grouped;
     return OPN_OK;
 }
 

@@ -157,6 +157,7 @@ struct SilkArgs {
     const uint8_t *arena;
     const uint32_t *offsets, *lens, *stream_idx;  // per item; stream_idx may be nullptr
     uint32_t n_items;
+    uint32_t item0, item_end;  // frame kernel: this launch covers items [item0, item_end) (a large bucket is cut into groups); 0, 0 = all
     int frame_ms;          // 10 or 20: every item of the launch
     int stream_channels;   // coded channels of every item
     int channels;          // the decoder's

@@ -592,7 +592,9 @@ cudaError_t launch_silk_frame(const SilkArgs &a0, cudaStream_t st)
     a.phase_clk = clk;
     const int cs = a.stream_channels, c = a.channels;
     if (cs < 1 || cs > 2 || c < 1 || c > 2 || (a.frame_ms != 10 && a.frame_ms != 20)) return cudaErrorInvalidValue;
-    const uint32_t items_per_cta = (uint32_t)(SILK_ROWS / cs), grid = (a.n_items + items_per_cta - 1u) / items_per_cta;
+    if (a.item_end == 0) a.item_end = a.n_items;
+    if (a.item_end <= a.item0) return cudaSuccess;
+    const uint32_t items_per_cta = (uint32_t)(SILK_ROWS / cs), grid = (a.item_end - a.item0 + items_per_cta - 1u) / items_per_cta;
     const size_t smem = silk_frame_smem();
     if (cs == 1 && c == 1) k_silk_frame<1, 1><<<grid, 32 * SILK_WARPS, smem, st>>>(a);
     else if (cs == 1) k_silk_frame<1, 2><<<grid, 32 * SILK_WARPS, smem, st>>>(a);

@@ -34,7 +34,11 @@ __constant__ float c_silk_up[3][48];
 
 __device__ __forceinline__ int32_t silk_smulwb(int32_t a, int32_t b16) { return (int32_t)(((int64_t)a * (int64_t)b16) >> 16); }
 // the same with the 16-bit factor pre-shifted: (a * (b << 16)) >> 32 == (a * b) >> 16, one IMAD.HI
+#ifdef OPN_SILK_EXP_FAKE_MUL  // timing experiment only (wrong results): what the multiply-high costs
+__device__ __forceinline__ int32_t silk_smulwb_sh(int32_t a, int32_t b16_shl16) { return a * b16_shl16; }
+#else
 __device__ __forceinline__ int32_t silk_smulwb_sh(int32_t a, int32_t b16_shl16) { return __mulhi(a, b16_shl16); }
+#endif
 __device__ __forceinline__ int32_t silk_smulww(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * (int64_t)b) >> 16); }
 __device__ __forceinline__ int32_t silk_sat16(int32_t x) { return max(-32768, min(32767, x)); }
 
@@ -217,14 +221,14 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const long long clk0 = A.phase_clk ? clock64() : 0;
     constexpr uint32_t ITEMS = SILK_ROWS / CS;
-    const uint32_t item0 = blockIdx.x * ITEMS;
+    const uint32_t item0 = A.item0 + blockIdx.x * ITEMS;
     const int nb_subfr = A.frame_ms / 5;
 
     // ---- phase A: one warp per row
     for (uint32_t row = warp; row < (uint32_t)SILK_ROWS; row += SILK_WARPS) {
         const uint32_t item = item0 + row / CS, c = row % CS;
         uint8_t *meta = s_meta + row * 8;
-        if (item >= A.n_items) {
+        if (item >= A.item_end) {
             if (lane == 0) meta[0] = 0;
             continue;
         }
@@ -425,7 +429,7 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
     // ---- phase C: one warp per item
     for (uint32_t it = warp; it < ITEMS; it += SILK_WARPS) {
         const uint32_t item = item0 + it;
-        if (item >= A.n_items) continue;
+        if (item >= A.item_end) continue;
         const uint32_t row0 = it * CS;
         const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
         const int n48 = A.frame_ms * 48;

@@ -197,7 +197,7 @@ def test_silk_decoder_api_single_stream():
         assert np.array_equal(want, pcm), f
 
 
-@pytest.mark.parametrize("ns,channels,ms", [(700, 1, 20), (130, 2, 20), (90, 2, 10)])
+@pytest.mark.parametrize("ns,channels,ms", [(2300, 1, 20), (130, 2, 20), (90, 2, 10)])
 def test_silk_device_resident_steps_enqueued_back_to_back(ns, channels, ms):
     """OPN_FLAG_SILK_FRAMES with device pointers: ten steps enqueued without a host wait (the range decode of later steps runs
     ahead on its own streams, the frame kernel owns the filter state in step order), bandwidths mixed across the streams and
