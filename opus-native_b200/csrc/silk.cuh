@@ -388,10 +388,8 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
         const int32_t g0 = s_gain[row], g1 = s_gain[SILK_RS + row], g2 = s_gain[2 * SILK_RS + row], g3 = s_gain[3 * SILK_RS + row];
         const int e1 = sub, e2 = 2 * sub, e3 = 3 * sub;
         int32_t *rp = s_res + row;
-#pragma unroll 1
-        for (int i0 = 0; i0 < Lmax; i0 += 4) {
-            const bool act = i0 < L;  // L is a multiple of 8: rows of a shorter frame (mixed bandwidths in one CTA) idle through the tail
-            const int32_t g = i0 < e1 ? g0 : i0 < e2 ? g1 : i0 < e3 ? g2 : g3;  // subframes are multiples of 8 samples too
+        // one sample of the recursion; the window slides after every four
+        auto lpc4 = [&](int i0, int32_t g, bool act) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int i = i0 + u;
@@ -405,14 +403,31 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
                     p3 += silk_smulwb_sh(s[18 + u - k], a[k - 3]);
                 }
                 const int32_t pred = (p0 + p1) + (p2 + p3);
-                const int64_t v = (int64_t)rp[i * SILK_RS] + (int64_t)pred * 16;
-                const int32_t v32 = v > 2147483647ll ? 2147483647 : v < -2147483648ll ? (int32_t)0x80000000 : (int32_t)v;
+                const int64_t v = (int64_t)pred * 16 + (int64_t)rp[i * SILK_RS];          // one IMAD.WIDE
+                const int32_t lo = (int32_t)v, hi = (int32_t)(v >> 32);
+                const int32_t v32 = hi == (lo >> 31) ? lo : (0x7fffffff ^ (hi >> 31));      // sat32
                 s[16 + u] = v32;
-                const int32_t w = silk_smulww(v32, g);
-                if (act) rp[i * SILK_RS] = __float_as_int((float)silk_sat16(((w >> 7) + 1) >> 1));  // exact: |x| <= 2^15
+                const int64_t wg = (int64_t)v32 * (int64_t)g;                               // smulww: one IMAD.WIDE and a funnel shift
+                const int32_t w = (int32_t)__funnelshift_r((uint32_t)wg, (uint32_t)(wg >> 32), 16);
+                const int32_t o = __float_as_int((float)silk_sat16(((w >> 7) + 1) >> 1));  // exact: |x| <= 2^15
+                if (act) rp[i * SILK_RS] = o;
             }
+        };
+        if (__all_sync(0xffffffffu, L == Lmax)) {  // every row of the CTA has the same frame length (the usual case): no predication
+#pragma unroll 1
+            for (int i0 = 0; i0 < L; i0 += 4) {
+                lpc4(i0, i0 < e1 ? g0 : i0 < e2 ? g1 : i0 < e3 ? g2 : g3, true);  // subframes are multiples of 8 samples
 #pragma unroll
-            for (int k = 0; k < 16; k++) s[k] = act ? s[k + 4] : s[k];
+                for (int k = 0; k < 16; k++) s[k] = s[k + 4];
+            }
+        } else {  // mixed bandwidths in one CTA: rows of a shorter frame idle through the tail (L is a multiple of 8)
+#pragma unroll 1
+            for (int i0 = 0; i0 < Lmax; i0 += 4) {
+                const bool act = i0 < L;
+                lpc4(i0, i0 < e1 ? g0 : i0 < e2 ? g1 : i0 < e3 ? g2 : g3, act);
+#pragma unroll
+                for (int k = 0; k < 16; k++) s[k] = act ? s[k + 4] : s[k];
+            }
         }
         if (fs_khz) {
             const uint32_t item = item0 + row / CS, c = row % CS;
