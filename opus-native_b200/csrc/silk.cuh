@@ -208,7 +208,7 @@ __device__ __forceinline__ void silk_resample_store(const float *x, int L, uint3
     }
 }
 
-template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_silk_frame(SilkArgs A)
+template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS, 4) k_silk_frame(SilkArgs A)
 {
     extern __shared__ __align__(16) uint8_t silk_smem[];
     // [SILK_LEAD + SILK_MAX_FRAME][SILK_RS]: excitation, then internal-rate samples (as floats); s_res points at sample 0
@@ -224,67 +224,87 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS) k_si
     const uint32_t item0 = A.item0 + blockIdx.x * ITEMS;
     const int nb_subfr = A.frame_ms / 5;
 
-    // ---- phase A: one warp per row
-    for (uint32_t row = warp; row < (uint32_t)SILK_ROWS; row += SILK_WARPS) {
-        const uint32_t item = item0 + row / CS, c = row % CS;
+    // ---- phase A0: one thread per row: what the row is (frame parameters, where its state lives)
+    __shared__ uint32_t s_chs[SILK_ROWS];  // stream * 2 + coded channel
+    if (threadIdx.x < (uint32_t)SILK_ROWS) {
+        const uint32_t row = threadIdx.x, item = item0 + row / CS, c = row % CS;
         uint8_t *meta = s_meta + row * 8;
-        if (item >= A.item_end) {
-            if (lane == 0) meta[0] = 0;
-            continue;
-        }
-        const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-        const int32_t status = A.status[stream];
-        const uint32_t fs_prev = A.st.fs[2 * stream], cs_prev = A.st.fs[2 * stream + 1];
-        const bool lost = status == ITEM_LOST;
-        int fs_khz = lost ? (int)fs_prev : (int)A.hdr[stream].x;
-        const bool silent = status < 0 || (lost && (fs_prev == 0u || c >= cs_prev));  // errors and losses before any frame: no work
-        const bool reset = !lost && (uint32_t)fs_khz != fs_prev;
-        if (lane == 0) {
+        meta[0] = 0;
+        meta[3] = 3;  // no item
+        if (item < A.item_end) {
+            const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+            const int32_t status = A.status[stream];
+            const uint32_t fs_prev = A.st.fs[2 * stream], cs_prev = A.st.fs[2 * stream + 1];
+            const bool lost = status == ITEM_LOST;
+            const uint32_t fs_khz = lost ? fs_prev : A.hdr[stream].x;
+            const bool silent = status < 0 || (lost && (fs_prev == 0u || c >= cs_prev));  // errors and losses before any frame: no work
             meta[0] = silent ? 0 : (uint8_t)fs_khz;
             meta[1] = lost;
-            meta[2] = reset;
+            meta[2] = !lost && fs_khz != fs_prev;  // first frame or a new internal rate: every filter starts from rest
             meta[3] = status < 0 ? 2 : (lost && fs_prev == 0u) ? 1 : 0;
+            s_chs[row] = stream * 2u + c;
         }
-        if (silent) continue;
-        const int order = fs_khz == 16 ? 16 : 10, sub = 5 * fs_khz, L = nb_subfr * sub, nblk = (L + 15) / 16;
-        const size_t chs = (size_t)stream * 2 + c;
+    }
+    __syncthreads();
+
+    // ---- phase A1: excitation, one LANE per 16-sample shell block: task (row, b), the rows of a warp's 32 tasks all different
+    // (conflict-free stores into the transposed rows); the codeword walk is the product's cwrsi_events (pvc.rs:182-284)
+    for (uint32_t t = threadIdx.x; t < (uint32_t)SILK_ROWS * 20u; t += 32u * SILK_WARPS) {
+        const uint32_t row = t & 31u, blk = t >> 5;
+        const int fs_khz = s_meta[row * 8];
+        const int L = nb_subfr * 5 * fs_khz;
+        if (16 * (int)blk >= L) continue;  // also rows that do nothing (fs_khz == 0)
+        int32_t *res = s_res + row;
+        if (s_meta[row * 8 + 1]) {  // lost: no excitation
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (16 * (int)blk + j < L) res[(16 * blk + j) * SILK_RS] = 0;
+            continue;
+        }
+        const SilkRec *r = A.rec + s_chs[row];
+        const uint32_t type = r->type, seed = r->seed, k = r->pulses[blk], idx = r->index[blk];
+        uint64_t lo = 0ull, hi = 0ull;  // y[j] as a signed byte, j < 8 in lo, the rest in hi
+        if (k) {
+            cwrsi_events(g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, 16u, k, idx, [&](uint32_t pos, int32_t val) {
+                const uint64_t v = (uint64_t)(uint8_t)(int8_t)val << (8u * (pos & 7u));
+                if (pos < 8u) lo |= v;
+                else hi |= v;
+            });
+        }
+        const int32_t offs = type == 1u ? (100 << 4) : (32 << 4);
+        uint32_t rr = (seed + 1u) * 2654435761u + blk * 2246822519u;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int32_t y = (int32_t)(int8_t)(uint8_t)((j < 8 ? lo : hi) >> (8 * (j & 7)));
+            int32_t e = y * 16384;
+            e += y > 0 ? -(80 << 4) : y < 0 ? (80 << 4) : 0;
+            e += offs;
+            rr = rr * 196314165u + 907633515u;
+            if (rr & 0x80000000u) e = -e;
+            rr += (uint32_t)y;
+            const int i = 16 * (int)blk + j;
+            if (i < L) res[i * SILK_RS] = e;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase A2: one warp per row: long-term prediction, filter coefficients, state
+    for (uint32_t row = warp; row < (uint32_t)SILK_ROWS; row += SILK_WARPS) {
+        const int fs_khz = s_meta[row * 8];
+        if (fs_khz == 0) continue;
+        const bool lost = s_meta[row * 8 + 1], reset = s_meta[row * 8 + 2];
+        const int order = fs_khz == 16 ? 16 : 10, sub = 5 * fs_khz, L = nb_subfr * sub;
+        const size_t chs = s_chs[row];
         int32_t *hist = A.st.hist + chs * SILK_HIST;
         int32_t *res = s_res + row;  // sample i at res[i * SILK_RS]
         // previous window of the LPC recursion, coefficient and gain state
         if (lane < 16u) s_lpc[lane * SILK_RS + row] = reset ? 0 : A.st.slpc[chs * 16 + lane];
         if (lost) {
-            for (int i = (int)lane; i < L; i += 32) res[i * SILK_RS] = 0;
             if (lane < 16u) s_a[lane * SILK_RS + row] = (int32_t)A.st.a_q12[chs * 16 + lane] << 16;
             if (lane < 4u) s_gain[lane * SILK_RS + row] = A.st.gain[chs];
         } else {
             const SilkRec *r = A.rec + chs;
-            const uint32_t type = r->type, seed = r->seed;
-            // excitation: lane b expands shell block b
-            if ((int)lane < nblk) {
-                const uint32_t k = r->pulses[lane], idx = r->index[lane];
-                uint64_t lo = 0ull, hi = 0ull;  // y[j] as a signed byte, j < 8 in lo, the rest in hi
-                if (k) {
-                    cwrsi_events(g_tab.pvq_u_data, g_tab.pvq_cw_data, g_tab.pvq_u_row, g_tab.pvq_ev_nmax, 16u, k, idx, [&](uint32_t pos, int32_t val) {
-                        const uint64_t v = (uint64_t)(uint8_t)(int8_t)val << (8u * (pos & 7u));
-                        if (pos < 8u) lo |= v;
-                        else hi |= v;
-                    });
-                }
-                const int32_t offs = type == 1u ? (100 << 4) : (32 << 4);
-                uint32_t rr = (seed + 1u) * 2654435761u + lane * 2246822519u;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int32_t y = (int32_t)(int8_t)(uint8_t)((j < 8 ? lo : hi) >> (8 * (j & 7)));
-                    int32_t e = y * 16384;
-                    e += y > 0 ? -(80 << 4) : y < 0 ? (80 << 4) : 0;
-                    e += offs;
-                    rr = rr * 196314165u + 907633515u;
-                    if (rr & 0x80000000u) e = -e;
-                    rr += (uint32_t)y;
-                    const int i = 16 * (int)lane + j;
-                    if (i < L) res[i * SILK_RS] = e;
-                }
-            }
+            const uint32_t type = r->type;
             __syncwarp();
             if (type == 2u) {
                 // long-term prediction: pres[i] = exc[i] + ((2 + sum_k smulwb(pres[i - lag + 2 - k], B[k])) << 2); the newest tap lies
