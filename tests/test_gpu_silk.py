@@ -232,3 +232,27 @@ def test_silk_device_resident_steps_enqueued_back_to_back(ns, channels, ms):
     for f in range(nfr):
         assert np.array_equal(got[f], want[f]), f
     assert np.array_equal(dec.final_ranges(), want_rng[nfr - 1])
+
+
+def test_silk_decode_i16_matches_oracle():
+    """Decoder::decode::<i16> on SILK streams: the frame kernel's dense rows go through the device-side pcm_soft_clip (per-stream
+    memory) and Sample::from_f32.  Unit gain on purpose: the crate's soft clip treats the last sample of a frame without peaks as
+    one (lib.rs:526-632, `pos == frame_size` can never hold), which leaves coefficients of 1e3..1e7 in its memory for quiet
+    signals like these -- a one-ulp difference in a gain factor would be amplified past an LSB, bit-identical input is not."""
+    ns, nfr, nb, channels = 40, 4, 170, 2
+    packets = opn.silk_fill(60, ns, 0, nfr, 2, 20, channels, nb)
+    batch = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    oracle = [(O.SilkStream(channels), np.zeros(2, np.float32)) for _ in range(ns)]
+    offs = (np.arange(ns) * nb).astype(np.uint32)
+    lens = np.full(ns, nb, np.uint32)
+    for f in range(nfr):
+        out = np.zeros((ns, 960 * channels), np.int16)
+        res, _ = batch.decode_i16(packets[f].reshape(-1), offs, lens, out, 960)
+        assert np.all(res == 960)
+        for s in range(ns):
+            st, mem = oracle[s]
+            w = st.decode(packets[f, s, 1:], 2, 20, channels)[3].copy()
+            O.lib().orc_pcm_soft_clip(O.ptr(w), 960, channels, O.ptr(mem), 2)
+            w16 = np.clip(w * np.float32(32768.0), -32768.0, 32767.0).astype(np.int16)
+            assert np.abs(out[s].astype(np.int32) - w16.astype(np.int32)).max() <= 1, (f, s)
+    assert np.abs(out).max() > 1000
