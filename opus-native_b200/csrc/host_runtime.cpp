@@ -181,6 +181,7 @@ struct opn_batch {
         void *d_conv = nullptr;        // converted rows (decode::<S> calls), conv_cap samples of conv_esize bytes per stream
         size_t conv_cap = 0, conv_esize = 0;
         int32_t *d_cliplen = nullptr, *h_cliplen = nullptr;  // [n] soft-clip slice length per stream
+        uint32_t *d_trans = nullptr, *h_trans = nullptr;       // [n] streams that switch from CELT to SILK in this call
         cudaEvent_t done = nullptr;    // everything that uses this slot has finished (incl. the PCM download)
         bool pending = false;
     } stg[2];
@@ -976,6 +977,8 @@ void opn_batch_destroy(opn_batch *b)
         cudaFree(g.d_dense);
         cudaFree(g.d_conv);
         cudaFree(g.d_cliplen);
+        cudaFree(g.d_trans);
+        if (g.h_trans) cudaFreeHost(g.h_trans);
         if (g.h_cliplen) cudaFreeHost(g.h_cliplen);
         if (g.h_items) cudaFreeHost(g.h_items);
         if (g.done) cudaEventDestroy(g.done);
@@ -1044,9 +1047,11 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         }
         arena_end = std::max(arena_end, (size_t)offsets[i] + lens[i]);
         const int fc = opn_packet_frame_count(arena + offsets[i], lens[i]);
-        items_ub += fc > 0 ? (size_t)fc : 1;
+        items_ub += (fc > 0 ? (size_t)fc : 1) + (b->silk ? 1 : 0);  // + the concealed frame of a CELT -> SILK transition
     }
-    const size_t dense_stride = (frame_size * (size_t)C + 3) & ~(size_t)3;
+    // a SILK-capable batch keeps 5 ms behind every dense row: the transition buffer of a CELT -> SILK switch (decoder.rs:519-543)
+    const size_t row_floats = (frame_size * (size_t)C + 3) & ~(size_t)3;
+    const size_t dense_stride = row_floats + (b->silk ? 240 * (size_t)C : 0);
     const int slot = b->stg_next;
     b->stg_next ^= 1;
     opn_batch::Staging &g = b->stg[slot];
@@ -1139,7 +1144,11 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                     items.push_back(Item{i, offsets[i] + fr[w], sz[w], (uint32_t)(w * pfs * C), code, w, cs});
                     max_len = std::max(max_len, sz[w]);
                 }
-                if (b->have_mode[i] == 1 + OPN_MODE_CELT) silk_resets.push_back(i);  // decoder.rs:555-557: silk_dec.reset()
+                if (b->have_mode[i] == 1 + OPN_MODE_CELT) {
+                    silk_resets.push_back(i);  // decoder.rs:555-557: silk_dec.reset()
+                    // decoder.rs:519-543, 674-676: the CELT decoder conceals 5 ms into the transition buffer (the tail of the row)
+                    items.push_back(Item{i, 0u, 0u, (uint32_t)row_floats, 1, -1, C});
+                }
                 if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
                 res[i] = count * pfs;
                 b->have_mode[i] = 1 + OPN_MODE_SILK;
@@ -1220,6 +1229,18 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 k0 = k1;
             }
             kbase += items.size();
+            if (want_pcm && !silk_resets.empty()) {
+                // decoder.rs:765-788: first 2.5 ms = the concealed CELT audio, next 2.5 ms = smooth_fade_into_in2(transition, samples)
+                if (!g.d_trans) {
+                    CU(cudaMalloc(&g.d_trans, (size_t)b->n * sizeof(uint32_t)));
+                    CU(cudaMallocHost(&g.h_trans, (size_t)b->n * sizeof(uint32_t)));
+                }
+                std::memcpy(g.h_trans + s0, silk_resets.data(), silk_resets.size() * sizeof(uint32_t));
+                CU(cudaMemcpyAsync(g.d_trans + s0, g.h_trans + s0, silk_resets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream_up));
+                CU(cudaEventRecord(b->ev_in, b->stream_up));
+                CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
+                CU(launch_transition_fade(g.d_dense, g.dense_cap, g.d_trans + s0, (uint32_t)silk_resets.size(), (uint32_t)row_floats, C, b->stream));
+            }
         }
         if (want_pcm && pcm_conv) {
             // decode::<S>: soft clip + Sample::from_f32 on the device; for the 16-bit types half the bytes go home.

@@ -319,6 +319,15 @@ class SynthStream:
         assert r == nf
         return side, y, coef, pcm
 
+    def conceal(self, lm):
+        """One lost frame of 120 << lm samples (decode_frame(None)): -> pcm [nf * channels]"""
+        nf = 120 << lm
+        side = SynthSide()
+        pcm = np.zeros(self.channels * nf, np.float32)
+        r = lib().orc_synth_decode_frame(C.byref(self.state), None, 0, lm, self.channels, int(self.apply_comb), C.byref(side), None, None, ptr(pcm))
+        assert r == nf
+        return pcm
+
 
 def silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads=1):
     """-> uint8 [n_frames, n_streams, pkt_bytes]: SYNTH-SILK/1 packets (TOC included) from the oracle's generator"""

@@ -152,7 +152,9 @@ def test_silk_needs_the_explicit_opt_in_and_rejects_what_is_not_built():
 
 def test_silk_bandwidth_change_and_mode_changes_mid_stream():
     """One decoder fed NB, then WB (internal rate changes: every SILK filter restarts), then a CELT packet, then SILK again
-    (silk_dec.reset() after CELT, decoder.rs:555-557), then CELT again (celt_dec.reset() on a mode change, decoder.rs:703-705)."""
+    (silk_dec.reset() after CELT, decoder.rs:555-557, and the transition of decoder.rs:519-543 / 765-788: the CELT decoder conceals
+    5 ms, 2.5 ms of that open the frame, the next 2.5 ms are smooth_fade_into_in2), then CELT again (celt_dec.reset() on a mode
+    change, decoder.rs:703-705; no cross-fade without a redundancy frame)."""
     channels, nb = 2, 160
     dec = opn.BatchDecoder(3, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
     seq = [("silk", 0), ("silk", 0), ("silk", 2), ("silk", 2), ("celt", 0), ("silk", 2), ("silk", 2), ("celt", 0), ("celt", 0)]
@@ -170,9 +172,18 @@ def test_silk_bandwidth_change_and_mode_changes_mid_stream():
         assert np.all(res == 960), (f, res)
         for s in range(3):
             if kind == "silk":
-                if f > 0 and seq[f - 1][0] == "celt":
+                switch = f > 0 and seq[f - 1][0] == "celt"
+                if switch:
                     silk[s] = O.SilkStream(channels)
+                    trans = celt[s].conceal(1)  # decoder.rs:519-543, 674-676: the CELT decoder conceals 5 ms into the transition buffer
                 want = silk[s].decode(pk[s, 1:], bw, 20, channels)[3]
+                if switch:  # decoder.rs:765-778: 2.5 ms of it, then smooth_fade_into_in2 over the next 2.5 ms
+                    n = 120 * channels
+                    faded = np.zeros(n, np.float32)
+                    O.lib().orc_smooth_fade(O.ptr(trans[n:2 * n].copy()), O.ptr(want[n:2 * n].copy()), O.ptr(faded), 120, channels, 48000)
+                    want = want.copy()
+                    want[:n] = trans[:n]
+                    want[n:2 * n] = faded
             else:
                 if f > 0 and seq[f - 1][0] == "silk":
                     celt[s] = O.SynthStream(3, channels)
