@@ -446,7 +446,12 @@ def run_silk(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_silk_frame<1,1> (excitation + LTP + LPC synthesis across streams + resampler + PCM store)",
                          "achieved": algo / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / (k1_ms * 1e-3) / 1e9 / peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": algo,
+                         "traffic": 15835904.0,
+                         "traffic_source": "static: profiles/r2b_silk_frame_ncu_summary.json, 2026-10-19: ncu --set full, dram__bytes_read.sum + "
+                                           "dram__bytes_write.sum summed over the three k_silk_frame<1,1> launches of one 16384-stream step; well below "
+                                           "the algorithmic bytes because packets' records, filter state and the 62.9 MB of PCM a step writes live in the "
+                                           "126 MB L2 between launches (ncu flushes before each launch: what is left is read traffic)",
+                         "algorithmic_bytes_per_launch": algo,
                          "bytes_note": "per channel-frame: 3840 B PCM + 144 B side record + 2 x 132 B filter state + 2 x 1280 B excitation history"},
             "cpu_baseline": cpu, "clocks": clocks,
         })
