@@ -144,6 +144,11 @@ typedef struct {
                                   * (480 or 960 at 48 kHz) of the batch's channel count; the bandwidth (NB/MB/WB) is read from each
                                   * packet's TOC on the device.  Needs OPN_BITSTREAM_SYNTH_SILK_1. */
 
+#define OPN_FLAG_DECODE_FEC 64u   /* host-buffer calls: Decoder::decode(.., decode_fec = true) for every stream (decoder.rs:343-386):
+                                  * conceal frame_size minus one packet frame, then decode the packet's in-band redundant copy of the
+                                  * previous frame (SILK LBRR); CELT packets, CELT streams and rows too short for a frame conceal
+                                  * everything.  opn_decode_* take the same as their decode_fec argument. */
+
 int opn_batch_create(int device, uint32_t n_streams, const opn_config *cfg, opn_batch **out);
 void opn_batch_destroy(opn_batch *b);
 int opn_batch_reset(opn_batch *b);
@@ -282,19 +287,22 @@ typedef struct {
 typedef struct {
     opn_silk_chan_side ch[2];
     uint32_t final_rng, tell_frac;
+    int32_t lbrr; /* the packet carries a redundant copy of the previous frame (in-band FEC) */
 } opn_silk_side;
 /* One SILK-only packet (TOC included) per row, each decoded by a fresh decoder of `channels` output channels; every packet
  * must hold one frame of frame_size samples (480 or 960) and `stream_channels` coded channels.  side_out [n_packets], exc_out
  * [n_packets][2][320] (excitation after long-term prediction, Q14, per coded channel), out16 [n_packets][2][320] (internal-rate
- * samples per output channel), pcm_out [n_packets][frame_size*channels], result [n_packets]; any output may be NULL. */
+ * samples per output channel), pcm_out [n_packets][frame_size*channels], result [n_packets]; any output may be NULL.  decode_fec:
+ * decode each packet's redundant copy of the previous frame instead of its own (a packet without one conceals: silence from rest). */
 int opn_op_silk_frames(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
-                       int stream_channels, int channels, size_t frame_size, opn_silk_side *side_out, int32_t *exc_out, int16_t *out16,
-                       float *pcm_out, int32_t *result);
+                       int stream_channels, int channels, size_t frame_size, int decode_fec, opn_silk_side *side_out, int32_t *exc_out,
+                       int16_t *out16, float *pcm_out, int32_t *result);
 /* Generator (host): one packet of exactly pkt_bytes (TOC + SYNTH-SILK/1 payload) / a [frame][stream][pkt_bytes] block.
  * bandwidth 0 NB (8 kHz), 1 MB (12 kHz), 2 WB (16 kHz); frame_ms 10 or 20. */
-int opn_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out);
+int opn_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes,
+                    uint32_t lbrr_permille /* chance in 1/1000 that the packet carries an LBRR copy of the previous frame */, uint8_t *out);
 int opn_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
-                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out);
+                  int channels, uint32_t pkt_bytes, uint32_t lbrr_permille, int n_threads, uint8_t *out);
 
 /* ---- synthetic stream generator (host; uses the library's own range ENCODER) --------- */
 /* Writes one packet of exactly pkt_bytes (TOC + SYNTH-CELT/1 payload) for (stream_id, frame).

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libopusb200.so")
 
 OP_UINT, OP_BITS, OP_BIT_LOGP, OP_ICDF, OP_LAPLACE, OP_BIT_VIA_DECODE, OP_BIT_VIA_DECODE_BIN, OP_PULSES, OP_SHRINK, OP_TELL, OP_PULSES_EVENTS = range(11)
-FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY, FLAG_MIXED_FRAMES, FLAG_SILK_FRAMES = 1, 2, 4, 8, 16, 32
+FLAG_DEVICE_PTRS, FLAG_NO_PCM_COPY, FLAG_INPUTS_READY, FLAG_SUBMIT_ONLY, FLAG_MIXED_FRAMES, FLAG_SILK_FRAMES, FLAG_DECODE_FEC = 1, 2, 4, 8, 16, 32, 64
 # OPN_BITSTREAM_*: CELT frames are Unimplemented (as in the crate, whose CeltDecoder::decode is todo!()) unless the caller
 # opts in to the synthetic SYNTH-CELT/1 frame layout (not Opus-interoperable)
 BITSTREAM_OPUS, BITSTREAM_SYNTH_CELT_1, BITSTREAM_SYNTH_CELT_2 = 0, 1, 2
@@ -34,7 +34,7 @@ CELT2_SIDE_DTYPE = np.dtype([(n, "<i4") for n in ("silence", "postfilter", "octa
 
 _SILK_CH = [("type", "<i4"), ("gidx", "<i4", (4,)), ("rc_idx", "<i4", (16,)), ("lag", "<i4", (4,)), ("ltp_idx", "<i4", (4,)), ("seed", "<i4"),
             ("pulses", "<i4", (20,)), ("index", "<u4", (20,))]
-SILK_SIDE_DTYPE = np.dtype([("ch", np.dtype(_SILK_CH), (2,)), ("final_rng", "<u4"), ("tell_frac", "<u4")])
+SILK_SIDE_DTYPE = np.dtype([("ch", np.dtype(_SILK_CH), (2,)), ("final_rng", "<u4"), ("tell_frac", "<u4"), ("lbrr", "<i4")])
 
 _ERR_NAMES = {-1: "BadArguments", -2: "BufferToSmall", -3: "InternalError", -4: "InvalidPacket",
               -5: "FrameSizeTooSmall", -6: "Unimplemented", -7: "Cuda"}
@@ -136,9 +136,9 @@ def lib():
     sig("opn_celt2_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("opn_synth_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32, u32, vp, vp)
     sig("opn_synth_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp)
-    sig("opn_op_silk_frames", C.c_int, C.c_int, vp, vp, vp, u32, C.c_int, C.c_int, sz, vp, vp, vp, vp, vp)
-    sig("opn_silk_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, u32, vp)
-    sig("opn_silk_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, C.c_int, u32, C.c_int, vp)
+    sig("opn_op_silk_frames", C.c_int, C.c_int, vp, vp, vp, u32, C.c_int, C.c_int, sz, C.c_int, vp, vp, vp, vp, vp)
+    sig("opn_silk_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, u32, u32, vp)
+    sig("opn_silk_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("opn_enc_run_script", C.c_int, vp, u32, vp, vp, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32))
     _lib = L
     return L
@@ -497,17 +497,17 @@ def synth_fill(first_stream, n_streams, first_frame, n_frames, lm, channels, pkt
     return out
 
 
-def silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads=None, out=None):
+def silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads=None, out=None, lbrr_permille=0):
     """SYNTH-SILK/1 packets (TOC + payload) -> uint8 [n_frames, n_streams, pkt_bytes]; bandwidth 0 NB, 1 MB, 2 WB; frame_ms 10 or 20"""
     if out is None:
         out = np.zeros((n_frames, n_streams, pkt_bytes), np.uint8)
     assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == n_frames * n_streams * pkt_bytes
     nt = n_threads or min(os.cpu_count() or 1, 32)
-    _chk(lib().opn_silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, nt, _p(out)))
+    _chk(lib().opn_silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, lbrr_permille, nt, _p(out)))
     return out
 
 
-def op_silk_frames(arena, offsets, lens, stream_channels, channels, frame_size, device=0):
+def op_silk_frames(arena, offsets, lens, stream_channels, channels, frame_size, device=0, decode_fec=False):
     """One SILK-only packet per row, each through a fresh decoder -> (side, exc [n, 2, 320], out16 [n, 2, 320], pcm, results)"""
     arena = np.ascontiguousarray(arena, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.uint32)
@@ -518,7 +518,7 @@ def op_silk_frames(arena, offsets, lens, stream_channels, channels, frame_size, 
     out16 = np.zeros((n, 2, SILK_MAX_FRAME), np.int16)
     pcm = np.zeros((n, frame_size * channels), np.float32)
     res = np.zeros(n, np.int32)
-    _chk(lib().opn_op_silk_frames(device, _p(arena), _p(offsets), _p(lens), n, stream_channels, channels, frame_size, _p(side), _p(exc),
+    _chk(lib().opn_op_silk_frames(device, _p(arena), _p(offsets), _p(lens), n, stream_channels, channels, frame_size, int(decode_fec), _p(side), _p(exc),
                                   _p(out16), _p(pcm), _p(res)))
     return side, exc, out16, pcm, res
 

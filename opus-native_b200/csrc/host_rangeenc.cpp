@@ -479,15 +479,10 @@ int opn_celt2_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_fra
 }
 
 // SYNTH-SILK/1 packet generator: same seeded draws as the oracle's independent orc_silk_packet.
-static int silk_packet_attempt(uint64_t stream_id, uint64_t frame_idx, uint32_t attempt, int bandwidth, int frame_ms, int channels,
-                               uint32_t pkt_bytes, uint8_t *out)
+// One block of symbols = all coded channels of one frame (the regular frame, or the LBRR copy of the previous one).
+static void silk_encode_block(RangeEncoder &enc, SplitMix64 &rng, int fs_khz, int nb_subfr, int channels)
 {
-    // TOC: SILK-only, config = 4 * bandwidth + (10 ms: 0, 20 ms: 1), stereo flag, code 0 (lib.rs:219-325)
-    out[0] = (uint8_t)(((bandwidth * 4 + (frame_ms == 20 ? 1 : 0)) << 3) | (channels == 2 ? 0x4 : 0));
-    SplitMix64 rng{77ull + 1000003ull * stream_id + 0xD1B54A32D192ED03ull * frame_idx + 0x2545F4914F6CDD1Dull * attempt};
-    const int fs_khz = bandwidth == 0 ? 8 : bandwidth == 1 ? 12 : 16, nb_subfr = frame_ms / 5, order = fs_khz == 16 ? 16 : 10;
-    const int nblk = (nb_subfr * 5 * fs_khz + 15) / 16;
-    RangeEncoder enc(out + 1, pkt_bytes - 1);
+    const int order = fs_khz == 16 ? 16 : 10, nblk = (nb_subfr * 5 * fs_khz + 15) / 16;
     for (int c = 0; c < channels; c++) {
         const uint32_t t8 = rng.below(8), type = t8 == 0 ? 0u : t8 < 3 ? 1u : 2u;
         enc.icdf(type, OPN_SILK_TYPE_ICDF, 8);
@@ -513,25 +508,40 @@ static int silk_packet_attempt(uint64_t stream_id, uint64_t frame_idx, uint32_t 
             }
         }
     }
+}
+
+static int silk_packet_attempt(uint64_t stream_id, uint64_t frame_idx, uint32_t attempt, int bandwidth, int frame_ms, int channels,
+                               uint32_t pkt_bytes, uint32_t lbrr_permille, uint8_t *out)
+{
+    // TOC: SILK-only, config = 4 * bandwidth + (10 ms: 0, 20 ms: 1), stereo flag, code 0 (lib.rs:219-325)
+    out[0] = (uint8_t)(((bandwidth * 4 + (frame_ms == 20 ? 1 : 0)) << 3) | (channels == 2 ? 0x4 : 0));
+    SplitMix64 rng{77ull + 1000003ull * stream_id + 0xD1B54A32D192ED03ull * frame_idx + 0x2545F4914F6CDD1Dull * attempt};
+    const int fs_khz = bandwidth == 0 ? 8 : bandwidth == 1 ? 12 : 16, nb_subfr = frame_ms / 5;
+    RangeEncoder enc(out + 1, pkt_bytes - 1);
+    const uint32_t lbrr = rng.below(1000) < lbrr_permille ? 1u : 0u;
+    enc.bit_logp(lbrr, 1);
+    if (lbrr) silk_encode_block(enc, rng, fs_khz, nb_subfr, channels);  // the redundant copy of the previous frame: its own draws
+    silk_encode_block(enc, rng, fs_khz, nb_subfr, channels);
     if (enc.error()) return enc.error();
     if (enc.tell() > 8u * (pkt_bytes - 1u)) return OPN_ERR_BUFFER_TOO_SMALL;
     enc.done();
     return enc.error() ? enc.error() : (int)pkt_bytes;
 }
 
-int opn_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out)
+int opn_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes,
+                    uint32_t lbrr_permille, uint8_t *out)
 {
     if (!out || bandwidth < 0 || bandwidth > 2 || (frame_ms != 10 && frame_ms != 20) || channels < 1 || channels > 2 || pkt_bytes < 3 ||
         pkt_bytes > 1276)
         return OPN_ERR_BAD_ARG;
     int rc = OPN_ERR_BUFFER_TOO_SMALL;
     for (uint32_t attempt = 0; attempt < 16 && rc == OPN_ERR_BUFFER_TOO_SMALL; attempt++)
-        rc = silk_packet_attempt(stream_id, frame_idx, attempt, bandwidth, frame_ms, channels, pkt_bytes, out);
+        rc = silk_packet_attempt(stream_id, frame_idx, attempt, bandwidth, frame_ms, channels, pkt_bytes, lbrr_permille, out);
     return rc;
 }
 
 int opn_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
-                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out)
+                  int channels, uint32_t pkt_bytes, uint32_t lbrr_permille, int n_threads, uint8_t *out)
 {
     if (!out || n_streams == 0 || n_frames == 0) return OPN_ERR_BAD_ARG;
     if (n_threads < 1) n_threads = 1;
@@ -542,7 +552,7 @@ int opn_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_fram
         pool.emplace_back([&, th]() {
             for (uint64_t w = total * th / n_threads; w < total * (th + 1) / n_threads; w++) {
                 int r = opn_silk_packet(first_stream + w % n_streams, first_frame + w / n_streams, bandwidth, frame_ms, channels, pkt_bytes,
-                                        out + w * pkt_bytes);
+                                        lbrr_permille, out + w * pkt_bytes);
                 if (r < 0) rc[th] = r;
             }
         });

@@ -493,7 +493,7 @@ cudaError_t do_silk_frame(opn_batch *b, const void *a) { return launch_silk_fram
 // the PCM ring).  bandwidth < 0: read from each packet's TOC (has_toc).
 int run_silk_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offsets, const uint32_t *d_lens, const uint32_t *d_stream_idx,
                     const uint32_t *d_dense_off, uint32_t n_items, int frame_ms, int has_toc, int bandwidth, int stream_channels,
-                    float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset)
+                    float *dense, size_t dense_stride, int32_t *d_result, int inputs_on, bool softclip_reset, int fec = 0)
 {
     Range nv("opn: SILK step (range decode + frame kernel)");
     if (!b->silk) return OPN_ERR_UNIMPLEMENTED;  // silk/decoder.rs:79
@@ -511,6 +511,7 @@ int run_silk_bucket(opn_batch *b, const uint8_t *d_arena, const uint32_t *d_offs
     a.channels = b->cfg.channels;
     a.has_toc = has_toc;
     a.bandwidth = bandwidth;
+    a.fec = fec;
     a.rec = b->d_silk_rec[p];
     a.hdr = b->d_hdr[p];
     a.status = b->d_status[p];
@@ -1084,40 +1085,37 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         uint32_t max_len = 8;
         for (uint32_t i = s0; i < s1; i++) {
             const uint32_t len = lens[i];
-            if (len == 0) {  // lost packet: decode_native(None), decoder.rs:427-441
-                if (!b->have_mode[i]) {  // decoder.rs:478-487: nothing decoded yet -> zeros, state untouched
-                    res[i] = (int32_t)frame_size;
-                    any_gap = true;
-                    b->last_duration[i] = (int32_t)frame_size;
-                    continue;
-                }
+            // decode_native(None, n) (decoder.rs:427-441): conceal n samples from sample `at0` of the row; the concealed frames take
+            // waves w0, w0+1, ...  Returns the number of frames pushed, -1 when nothing was decoded yet (zeros, state untouched,
+            // decoder.rs:478-487), -2 when this kind of concealment is not built.
+            auto conceal = [&](uint32_t i, size_t n_samples, uint32_t at0, int w0) -> int {
+                if (!b->have_mode[i]) return -1;
                 plc.clear();
-                plc_frames(frame_size, b->last_nf[i], plc);
-                uint32_t at = 0;
-                int w = 0;
+                plc_frames(n_samples, b->last_nf[i], plc);
+                uint32_t at = at0;
+                int w = w0;
                 if (b->have_mode[i] == 1 + OPN_MODE_SILK) {
                     // the stream's last packet was SILK: concealed by the SILK path (10 and 20 ms frames only)
                     bool ok = b->silk;
                     for (uint32_t a : plc) ok = ok && (a == 480 || a == 960);
-                    if (!ok) {
-                        res[i] = OPN_ERR_UNIMPLEMENTED;
-                        any_gap = true;
-                        continue;
-                    }
+                    if (!ok) return -2;
                     for (uint32_t a : plc) {
                         items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, 8 + (a == 960 ? 1 : 0), w++, (int)b->silk_cs[i]});
                         at += a;
                     }
-                    res[i] = (int32_t)frame_size;
-                    b->last_duration[i] = (int32_t)frame_size;
-                    continue;
+                } else {
+                    for (uint32_t a : plc) {
+                        items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++, C});
+                        at += a;
+                    }
                 }
-                for (uint32_t a : plc) {
-                    items.push_back(Item{i, 0u, 0u, at * (uint32_t)C, lm_of_frame(a), w++, C});
-                    at += a;
-                }
-                res[i] = (int32_t)frame_size;
-                b->last_duration[i] = (int32_t)frame_size;
+                return w - w0;
+            };
+            if (len == 0) {  // lost packet
+                const int k = conceal(i, frame_size, 0u, 0);
+                if (k < 0) any_gap = true;
+                res[i] = k == -2 ? OPN_ERR_UNIMPLEMENTED : (int32_t)frame_size;
+                if (k != -2) b->last_duration[i] = (int32_t)frame_size;
                 continue;
             }
             const uint8_t *pkt = arena + offsets[i];
@@ -1129,6 +1127,46 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
             if (count < 0) {
                 res[i] = count;
                 any_gap = true;
+                continue;
+            }
+            if (flags & OPN_FLAG_DECODE_FEC) {  // decode_native(Some(packet), decode_fec = true), decoder.rs:343-386
+                // no FEC can be present in a CELT packet or for a CELT stream, nor fit a row shorter than a packet frame: conceal it all
+                if (frame_size < (size_t)pfs || mode == OPN_MODE_CELT || b->have_mode[i] == 1 + OPN_MODE_CELT) {
+                    const int k = conceal(i, frame_size, 0u, 0);
+                    if (k < 0) any_gap = true;
+                    res[i] = k == -2 ? OPN_ERR_UNIMPLEMENTED : (int32_t)frame_size;
+                    if (k != -2) b->last_duration[i] = (int32_t)frame_size;
+                    continue;
+                }
+                if (mode != OPN_MODE_SILK || !b->silk || (pfs != 480 && pfs != 960) || opn_packet_bandwidth(pkt) > OPN_BW_WIDE) {
+                    res[i] = OPN_ERR_UNIMPLEMENTED;  // hybrid frames, 40 / 60 ms SILK frames
+                    any_gap = true;
+                    continue;
+                }
+                // conceal everything but the one frame the packet may hold a redundant copy of, then decode that copy
+                int k = 0;
+                if (frame_size > (size_t)pfs) {
+                    k = conceal(i, frame_size - (size_t)pfs, 0u, 0);
+                    if (k == -2) {
+                        res[i] = OPN_ERR_UNIMPLEMENTED;
+                        any_gap = true;
+                        continue;
+                    }
+                    if (k < 0) {
+                        any_gap = true;
+                        k = 0;
+                    }
+                }
+                const int cs = opn_packet_channels(pkt);
+                const int code = 8 + 2 * opn_packet_bandwidth(pkt) + (pfs == 960 ? 1 : 0) + 16;  // + 16: the redundant copy
+                items.push_back(Item{i, offsets[i] + fr[0], sz[0], (uint32_t)((frame_size - (size_t)pfs) * C), code, k, cs});
+                max_len = std::max(max_len, sz[0]);
+                res[i] = (int32_t)frame_size;
+                b->have_mode[i] = 1 + OPN_MODE_SILK;
+                b->silk_cs[i] = (uint8_t)cs;
+                b->last_nf[i] = pfs;
+                b->bandwidth[i] = opn_packet_bandwidth(pkt);
+                b->last_duration[i] = (int32_t)frame_size;
                 continue;
             }
             if ((size_t)count * (size_t)pfs > frame_size) {  // decoder.rs:388-390
@@ -1214,10 +1252,10 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 size_t k1 = k0;
                 while (k1 < cnt && items[k1].wave == items[k0].wave && items[k1].lm == items[k0].lm && items[k1].cs == items[k0].cs) k1++;
                 if (items[k0].lm >= 8) {
-                    const int code = items[k0].lm - 8;
+                    const int fec = (items[k0].lm - 8) >> 4, code = (items[k0].lm - 8) & 15;
                     rc = run_silk_bucket(b, g.d_arena, di + k0, di + cnt + k0, di + 2 * cnt + k0, di + 3 * cnt + k0, (uint32_t)(k1 - k0),
                                          (code & 1) ? 20 : 10, 0, code >> 1, items[k0].cs, want_pcm ? g.d_dense : nullptr, g.dense_cap, nullptr, 2,
-                                         pcm_conv == nullptr);
+                                         pcm_conv == nullptr, fec);
                     if (rc) return rc;
                     k0 = k1;
                     continue;
@@ -1521,16 +1559,13 @@ static int decoder_decode(opn_decoder *d, const uint8_t *packet, size_t len, flo
     if (packet && len == 0) return OPN_ERR_BAD_ARG;                                           // decoder.rs:323-325
     if (packet && len > 0xFFFFFFFFull) return OPN_ERR_BAD_ARG;
     uint32_t off = 0, l = packet ? (uint32_t)len : 0u;
-    if (packet && decode_fec) {
-        // decoder.rs:343-350: FEC only exists in SILK frames; for a CELT-only packet (or decoder) the
-        // reference conceals the whole gap instead.  SILK/hybrid FEC needs the stubbed SilkDecoder.
-        if (opn_packet_mode(packet) != OPN_MODE_CELT && d->batch->have_mode[0] == 0) return OPN_ERR_UNIMPLEMENTED;
-        l = 0;
-    }
+    // decoder.rs:343-386: FEC only exists in SILK frames; for a CELT-only packet (or stream) the reference conceals the whole gap
+    // instead, otherwise it conceals all but one packet frame and decodes the packet's redundant copy of the previous frame:
+    // batch_decode_host does both under OPN_FLAG_DECODE_FEC
     static const uint8_t dummy = 0;
     int32_t res = 0;
     int rc = batch_decode_host(d->batch, packet ? packet : &dummy, &off, &l, pcm, frame_size * (size_t)d->channels, frame_size,
-                               &res, 0, pcm_conv, sample_format);
+                               &res, (packet && decode_fec) ? OPN_FLAG_DECODE_FEC : 0u, pcm_conv, sample_format);
     if (rc < 0) return rc;
     if (res >= 0) {
         uint32_t fr = 0;
@@ -1888,8 +1923,8 @@ int opn_op_celt2_symbols(int device, const uint8_t *arena, const uint32_t *offse
 
 // SYNTH-SILK/1 operator: every packet is decoded by a fresh decoder (zero state) through the product's two kernels.
 int opn_op_silk_frames(int device, const uint8_t *arena, const uint32_t *offsets, const uint32_t *lens, uint32_t n_packets,
-                       int stream_channels, int channels, size_t frame_size, opn_silk_side *side_out, int32_t *exc_out, int16_t *out16,
-                       float *pcm_out, int32_t *result)
+                       int stream_channels, int channels, size_t frame_size, int decode_fec, opn_silk_side *side_out, int32_t *exc_out,
+                       int16_t *out16, float *pcm_out, int32_t *result)
 {
     if (!arena || !offsets || !lens || n_packets == 0 || channels < 1 || channels > 2 || stream_channels < 1 || stream_channels > 2)
         return OPN_ERR_BAD_ARG;
@@ -1945,6 +1980,7 @@ int opn_op_silk_frames(int device, const uint8_t *arena, const uint32_t *offsets
     a.channels = channels;
     a.has_toc = 1;
     a.bandwidth = -1;
+    a.fec = decode_fec ? 1 : 0;
     a.rec = dR.as<SilkRec>();
     a.hdr = dH.as<uint4>();
     a.status = dSt.as<int32_t>();

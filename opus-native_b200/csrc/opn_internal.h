@@ -163,6 +163,7 @@ struct SilkArgs {
     int channels;          // the decoder's
     int has_toc;           // 1: offsets point at the TOC (device-resident steps); 0: at the frame payload, bandwidth below
     int bandwidth;         // host path: 0 NB, 1 MB, 2 WB of every item
+    int fec;               // LostFlag::DecodeFec: decode each packet's redundant copy of the previous frame (none: conceal)
     SilkRec *rec;          // [n_streams][2]
     uint4 *hdr;            // [n_streams] .x = fs_khz of the frame, .y final range, .z tell_frac
     int32_t *status;       // [n_streams]

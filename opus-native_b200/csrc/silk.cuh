@@ -84,6 +84,18 @@ __global__ void __launch_bounds__(32) k_silk_rangedec(SilkArgs A)
     const PvqTable T{g_tab.pvq_u_data, g_tab.pvq_u_row};
     LaneDec d;
     d.init(src, len);
+    // lbrr: a redundant copy of the PREVIOUS frame (same syntax) comes before the regular frame -- the in-band FEC behind
+    // Decoder::decode(.., decode_fec = true) (decoder.rs:343-386; LostFlag::DecodeFec, silk/decoder.rs:6-14).  Decoding the regular frame
+    // walks through the copy first (its values are overwritten by the second pass); decoding the copy stops after it.
+    const uint32_t lbrr = d.bit_logp(1u);
+    if (A.fec && !lbrr) {  // FEC asked of a packet that has none: conceal
+        A.status[stream] = ITEM_LOST;
+        A.hdr[stream] = make_uint4(0u, 0u, 0u, 0u);
+        if (A.side) A.side[stream].lbrr = 0;
+        return;
+    }
+    const int npass = (!A.fec && lbrr) ? 2 : 1;
+    for (int pass = 0; pass < npass; pass++)
     for (int c = 0; c < A.stream_channels; c++) {
         SilkRec *r = A.rec + (size_t)stream * 2 + c;
         opn_silk_chan_side *sd = A.side ? &A.side[stream].ch[c] : nullptr;
@@ -150,6 +162,7 @@ __global__ void __launch_bounds__(32) k_silk_rangedec(SilkArgs A)
     if (A.side) {
         A.side[stream].final_rng = d.rng;
         A.side[stream].tell_frac = tf;
+        A.side[stream].lbrr = (int32_t)lbrr;
     }
     A.hdr[stream] = make_uint4((uint32_t)fs_khz, d.rng, tf, 0u);
 }

@@ -207,6 +207,7 @@ typedef struct {
 typedef struct {
     orc_silk_chan_side ch[2];
     uint32_t final_rng, tell_frac;
+    int32_t lbrr; /* the packet carries a redundant copy of the previous frame */
 } orc_silk_side;
 typedef struct {
     int32_t slpc[16];            /* sLPC_Q14 of the last 16 samples, [15] = newest */
@@ -222,12 +223,14 @@ typedef struct {
 void orc_silk_state_init(orc_silk_state *st);
 /* payload = frame bytes after the TOC; bandwidth 0 NB / 1 MB / 2 WB; frame_ms 10 or 20.  exc_out: [2][ORC_SILK_MAX_FRAME]
  * excitation after long-term prediction (Q14) or NULL; out16: [2][ORC_SILK_MAX_FRAME] internal-rate samples per OUTPUT channel
- * or NULL; pcm_out: interleaved frame_ms*48*channels floats.  Returns samples per channel at 48 kHz. */
+ * or NULL; pcm_out: interleaved frame_ms*48*channels floats.  lost: 0 decode the packet's frame, 1 conceal, 2 decode the packet's
+ * redundant copy of the previous frame (LostFlag::DecodeFec; conceals when the packet has none).  Returns samples per channel at 48 kHz. */
 int orc_silk_decode_frame(orc_silk_state *st, const uint8_t *payload, uint32_t len, int bandwidth, int frame_ms, int stream_channels,
                           int channels, int lost, orc_silk_side *side, int32_t *exc_out, int16_t *out16, float *pcm_out);
-int orc_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out);
+int orc_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes,
+                    uint32_t lbrr_permille, uint8_t *out);
 int orc_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
-                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out);
+                  int channels, uint32_t pkt_bytes, uint32_t lbrr_permille, int n_threads, uint8_t *out);
 double orc_silk_bench(const uint8_t *packets, uint32_t n_streams, uint32_t n_frames, uint32_t pkt_bytes, int bandwidth, int frame_ms,
                       int channels, int n_threads, float *pcm_last, uint32_t *final_rng_xor);
 

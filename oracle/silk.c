@@ -10,6 +10,7 @@
  * resampler to 48 kHz.  NOT interoperable with Opus.  This file defines the truth the CUDA path is compared with: every
  * integer (symbols, excitation, internal-rate samples) bit for bit, the float PCM within north_star's 1e-5.
  *
+ * lbrr = bit_logp(1) opens the packet: 1 = a redundant copy of the previous frame (same syntax) precedes the regular frame.
  * Per coded channel (the channels of a stereo packet follow each other in the payload):
  *   type      = icdf(TYPE, 8)                          0 inactive, 1 unvoiced, 2 voiced
  *   gidx[0]   = uint(64); gidx[s] = clamp(gidx[s-1] + icdf(DELTA, 8) - 4, 0, 63)      gain_Q10 = GAIN_Q10[gidx]
@@ -36,8 +37,8 @@ void orc_silk_state_init(orc_silk_state *st) { memset(st, 0, sizeof(*st)); }
 
 static int silk_fs_khz(int bandwidth) { return bandwidth == 0 ? 8 : bandwidth == 1 ? 12 : 16; }
 
-/* symbols of one frame (all coded channels) */
-static void silk_decode_symbols(orc_dec *d, int fs_khz, int nb_subfr, int stream_channels, orc_silk_side *side)
+/* one block of symbols: all coded channels of one frame (the regular frame of a packet, or its LBRR copy of the previous one) */
+static void silk_decode_block(orc_dec *d, int fs_khz, int nb_subfr, int stream_channels, orc_silk_side *side)
 {
     const int order = fs_khz == 16 ? 16 : 10, L = nb_subfr * 5 * fs_khz, nblk = (L + 15) / 16;
     const int min_lag = 2 * fs_khz, max_lag = 18 * fs_khz;
@@ -65,8 +66,29 @@ static void silk_decode_symbols(orc_dec *d, int fs_khz, int nb_subfr, int stream
             s->index[b] = k ? orc_dec_uint(d, orc_pvq_v(16, k)) : 0u;
         }
     }
+}
+
+/* A packet starts with lbrr = bit_logp(1); when set, a low-bit-rate redundant copy of the PREVIOUS frame (same syntax) comes before
+ * the regular frame -- the in-band FEC that Decoder::decode(.., decode_fec = true) asks for (src/decoder.rs:343-386, LostFlag::DecodeFec
+ * in src/silk/decoder.rs:6-14).  fec: decode the redundant block instead of the regular frame; returns 0 when the packet has none. */
+static int silk_decode_symbols(orc_dec *d, int fs_khz, int nb_subfr, int stream_channels, int fec, orc_silk_side *side)
+{
+    const int lbrr = orc_dec_bit_logp(d, 1);
+    int have = 1;
+    if (fec) {
+        if (lbrr) silk_decode_block(d, fs_khz, nb_subfr, stream_channels, side);
+        else have = 0;
+    } else {
+        if (lbrr) {
+            orc_silk_side skip;
+            silk_decode_block(d, fs_khz, nb_subfr, stream_channels, &skip);
+        }
+        silk_decode_block(d, fs_khz, nb_subfr, stream_channels, side);
+    }
+    side->lbrr = lbrr;
     side->final_rng = d->rng;
     side->tell_frac = orc_dec_tell_frac(d);
+    return have;
 }
 
 /* reflection coefficients -> prediction coefficients: the step-up recursion A_k(z) = A_{k-1}(z) + rc_k z^-k A_{k-1}(1/z) on
@@ -164,12 +186,20 @@ int orc_silk_decode_frame(orc_silk_state *st, const uint8_t *payload, uint32_t l
 {
     if (!st || !pcm_out || channels < 1 || channels > 2 || stream_channels < 1 || stream_channels > 2) return ORC_ERR_BAD_ARG;
     if (frame_ms != 10 && frame_ms != 20) return ORC_ERR_BAD_ARG;
+    const int fec = lost == 2; /* LostFlag::DecodeFec: the packet's redundant copy of the previous frame */
+    if (fec) lost = 0;
     if (!lost && (bandwidth < 0 || bandwidth > 2)) return ORC_ERR_INVALID_PACKET; /* decoder.rs:566-585: SILK stops at wideband */
     if (!lost && (!payload || len <= 1)) lost = 1;                                /* decoder.rs:467 */
     const int n48 = frame_ms * 48;
     orc_silk_side local;
     if (!side) side = &local;
     memset(side, 0, sizeof(*side));
+    if (!lost) { /* the symbols need nothing of the decoder's state */
+        orc_dec d;
+        orc_dec_init(&d, payload, len);
+        if (!silk_decode_symbols(&d, silk_fs_khz(bandwidth), frame_ms / 5, stream_channels, fec, side)) lost = 1; /* FEC asked of a
+                                                                                 packet without a redundant copy: conceal */
+    }
     if (lost && st->fs_khz == 0) { /* nothing decoded yet: silence, state untouched */
         memset(pcm_out, 0, sizeof(float) * (size_t)n48 * (size_t)channels);
         return n48;
@@ -182,11 +212,6 @@ int orc_silk_decode_frame(orc_silk_state *st, const uint8_t *payload, uint32_t l
         st->fs_khz = fs_khz;
     }
     st->stream_channels = stream_channels;
-    if (!lost) {
-        orc_dec d;
-        orc_dec_init(&d, payload, len);
-        silk_decode_symbols(&d, fs_khz, nb_subfr, stream_channels, side);
-    }
     int32_t out[2][ORC_SILK_MAX_FRAME];
     for (int c = 0; c < stream_channels; c++)
         silk_channel(&st->ch[c], &side->ch[c], fs_khz, nb_subfr, lost, exc_out ? exc_out + c * ORC_SILK_MAX_FRAME : NULL, out[c]);
@@ -231,61 +256,72 @@ static uint64_t sm_next(smix *r)
 }
 static uint32_t sm_below(smix *r, uint32_t n) { return (uint32_t)(((sm_next(r) >> 32) * (uint64_t)n) >> 32); }
 
+static void silk_encode_block(orc_enc *pe, smix *prng, int fs_khz, int nb_subfr, int channels);
+
 static int silk_packet_attempt(uint64_t stream_id, uint64_t frame_idx, uint32_t attempt, int bandwidth, int frame_ms, int channels,
-                               uint32_t pkt_bytes, uint8_t *out)
+                               uint32_t pkt_bytes, uint32_t lbrr_permille, uint8_t *out)
 {
     /* TOC: SILK-only, config = 4 bandwidth + (10 ms: 0, 20 ms: 1), stereo flag, code 0 (src/lib.rs:219-325) */
     out[0] = (uint8_t)(((bandwidth * 4 + (frame_ms == 20 ? 1 : 0)) << 3) | (channels == 2 ? 0x4 : 0));
     smix rng = {77ull + 1000003ull * stream_id + 0xD1B54A32D192ED03ull * frame_idx + 0x2545F4914F6CDD1Dull * attempt};
-    const int fs_khz = silk_fs_khz(bandwidth), nb_subfr = frame_ms / 5, order = fs_khz == 16 ? 16 : 10;
-    const int L = nb_subfr * 5 * fs_khz, nblk = (L + 15) / 16;
+    const int fs_khz = silk_fs_khz(bandwidth), nb_subfr = frame_ms / 5;
     orc_enc e;
     orc_enc_init(&e, out + 1, pkt_bytes - 1);
-    for (int c = 0; c < channels; c++) {
-        const uint32_t t8 = sm_below(&rng, 8), type = t8 == 0 ? 0u : t8 < 3 ? 1u : 2u;
-        orc_enc_icdf(&e, type, ORC_SILK_TYPE_ICDF, 8);
-        orc_enc_uint(&e, 16 + sm_below(&rng, 36), 64);
-        for (int f = 1; f < nb_subfr; f++) orc_enc_icdf(&e, 3 + sm_below(&rng, 3), ORC_SILK_DELTA_GAIN_ICDF, 8);
-        for (int k = 0; k < order; k++) {
-            const uint32_t half = k < 2 ? 16 : 8;
-            const uint32_t a = sm_below(&rng, half + 1), b = sm_below(&rng, half); /* triangular around the middle */
-            orc_enc_bits(&e, a + b, k < 2 ? 5 : 4);
-        }
-        if (type == 2) {
-            orc_enc_uint(&e, sm_below(&rng, (uint32_t)(16 * fs_khz + 1)), (uint32_t)(16 * fs_khz + 1));
-            for (int f = 0; f < nb_subfr; f++) orc_enc_icdf(&e, sm_below(&rng, 4), ORC_SILK_CONTOUR_ICDF, 8);
-            for (int f = 0; f < nb_subfr; f++) orc_enc_icdf(&e, sm_below(&rng, 8), ORC_SILK_LTP_ICDF, 8);
-        }
-        orc_enc_bits(&e, sm_below(&rng, 4), 2);
-        for (int b = 0; b < nblk; b++) {
-            uint32_t k1 = sm_below(&rng, 9), k2 = sm_below(&rng, 9), k = k1 < k2 ? k1 : k2;
-            orc_enc_icdf(&e, k, ORC_SILK_PULSES_ICDF + (type != 0 ? 9 : 0), 8);
-            if (k) {
-                uint32_t v = orc_pvq_v(16, k);
-                orc_enc_uint(&e, sm_below(&rng, v), v); /* a uniform codeword index == encode_pulses(cwrsi(index)) */
-            }
-        }
-    }
+    const uint32_t lbrr = sm_below(&rng, 1000) < lbrr_permille ? 1u : 0u;
+    orc_enc_bit_logp(&e, lbrr, 1);
+    if (lbrr) silk_encode_block(&e, &rng, fs_khz, nb_subfr, channels); /* the redundant copy of the previous frame: its own draws */
+    silk_encode_block(&e, &rng, fs_khz, nb_subfr, channels);
     if (e.error) return e.error;
     if (orc_enc_tell(&e) > 8u * (pkt_bytes - 1u)) return ORC_ERR_BUFFER_TOO_SMALL;
     orc_enc_done(&e);
     return e.error ? e.error : (int)pkt_bytes;
 }
 
-int orc_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes, uint8_t *out)
+static void silk_encode_block(orc_enc *pe, smix *prng, int fs_khz, int nb_subfr, int channels)
+{
+    const int order = fs_khz == 16 ? 16 : 10, L = nb_subfr * 5 * fs_khz, nblk = (L + 15) / 16;
+    for (int c = 0; c < channels; c++) {
+        const uint32_t t8 = sm_below(prng, 8), type = t8 == 0 ? 0u : t8 < 3 ? 1u : 2u;
+        orc_enc_icdf(pe, type, ORC_SILK_TYPE_ICDF, 8);
+        orc_enc_uint(pe, 16 + sm_below(prng, 36), 64);
+        for (int f = 1; f < nb_subfr; f++) orc_enc_icdf(pe, 3 + sm_below(prng, 3), ORC_SILK_DELTA_GAIN_ICDF, 8);
+        for (int k = 0; k < order; k++) {
+            const uint32_t half = k < 2 ? 16 : 8;
+            const uint32_t a = sm_below(prng, half + 1), b = sm_below(prng, half); /* triangular around the middle */
+            orc_enc_bits(pe, a + b, k < 2 ? 5 : 4);
+        }
+        if (type == 2) {
+            orc_enc_uint(pe, sm_below(prng, (uint32_t)(16 * fs_khz + 1)), (uint32_t)(16 * fs_khz + 1));
+            for (int f = 0; f < nb_subfr; f++) orc_enc_icdf(pe, sm_below(prng, 4), ORC_SILK_CONTOUR_ICDF, 8);
+            for (int f = 0; f < nb_subfr; f++) orc_enc_icdf(pe, sm_below(prng, 8), ORC_SILK_LTP_ICDF, 8);
+        }
+        orc_enc_bits(pe, sm_below(prng, 4), 2);
+        for (int b = 0; b < nblk; b++) {
+            uint32_t k1 = sm_below(prng, 9), k2 = sm_below(prng, 9), k = k1 < k2 ? k1 : k2;
+            orc_enc_icdf(pe, k, ORC_SILK_PULSES_ICDF + (type != 0 ? 9 : 0), 8);
+            if (k) {
+                uint32_t v = orc_pvq_v(16, k);
+                orc_enc_uint(pe, sm_below(prng, v), v); /* a uniform codeword index == encode_pulses(cwrsi(index)) */
+            }
+        }
+    }
+}
+
+int orc_silk_packet(uint64_t stream_id, uint64_t frame_idx, int bandwidth, int frame_ms, int channels, uint32_t pkt_bytes,
+                    uint32_t lbrr_permille, uint8_t *out)
 {
     if (!out || bandwidth < 0 || bandwidth > 2 || (frame_ms != 10 && frame_ms != 20) || channels < 1 || channels > 2 || pkt_bytes < 3 ||
         pkt_bytes > 1276)
         return ORC_ERR_BAD_ARG;
     int rc = ORC_ERR_BUFFER_TOO_SMALL; /* a draw that overruns the byte budget is redrawn from the next sub-seed */
     for (uint32_t attempt = 0; attempt < 16 && rc == ORC_ERR_BUFFER_TOO_SMALL; attempt++)
-        rc = silk_packet_attempt(stream_id, frame_idx, attempt, bandwidth, frame_ms, channels, pkt_bytes, out);
+        rc = silk_packet_attempt(stream_id, frame_idx, attempt, bandwidth, frame_ms, channels, pkt_bytes, lbrr_permille, out);
     return rc;
 }
 
 typedef struct {
     uint64_t first_stream, first_frame, w0, w1;
-    uint32_t n_streams, pkt_bytes;
+    uint32_t n_streams, pkt_bytes, lbrr_permille;
     int bandwidth, frame_ms, channels, rc;
     uint8_t *out;
 } sfill_job;
@@ -295,7 +331,7 @@ static void *sfill_thread(void *arg)
     sfill_job *j = (sfill_job *)arg;
     for (uint64_t w = j->w0; w < j->w1; w++) {
         int r = orc_silk_packet(j->first_stream + w % j->n_streams, j->first_frame + w / j->n_streams, j->bandwidth, j->frame_ms,
-                                j->channels, j->pkt_bytes, j->out + w * j->pkt_bytes);
+                                j->channels, j->pkt_bytes, j->lbrr_permille, j->out + w * j->pkt_bytes);
         if (r < 0) j->rc = r;
     }
     return NULL;
@@ -303,7 +339,7 @@ static void *sfill_thread(void *arg)
 
 /* layout [frame][stream][pkt_bytes] */
 int orc_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_frame, uint32_t n_frames, int bandwidth, int frame_ms,
-                  int channels, uint32_t pkt_bytes, int n_threads, uint8_t *out)
+                  int channels, uint32_t pkt_bytes, uint32_t lbrr_permille, int n_threads, uint8_t *out)
 {
     if (!out || n_streams == 0 || n_frames == 0) return ORC_ERR_BAD_ARG;
     if (n_threads < 1) n_threads = 1;
@@ -314,7 +350,7 @@ int orc_silk_fill(uint64_t first_stream, uint32_t n_streams, uint64_t first_fram
         sfill_job *j = &jobs[t];
         j->first_stream = first_stream; j->first_frame = first_frame;
         j->w0 = total * (uint64_t)t / (uint64_t)n_threads; j->w1 = total * (uint64_t)(t + 1) / (uint64_t)n_threads;
-        j->n_streams = n_streams; j->pkt_bytes = pkt_bytes;
+        j->n_streams = n_streams; j->pkt_bytes = pkt_bytes; j->lbrr_permille = lbrr_permille;
         j->bandwidth = bandwidth; j->frame_ms = frame_ms; j->channels = channels; j->out = out;
         pthread_create(&th[t], NULL, sfill_thread, j);
     }

@@ -63,7 +63,7 @@ class SilkChanSide(C.Structure):
 
 
 class SilkSide(C.Structure):
-    _fields_ = [("ch", SilkChanSide * 2), ("final_rng", C.c_uint32), ("tell_frac", C.c_uint32)]
+    _fields_ = [("ch", SilkChanSide * 2), ("final_rng", C.c_uint32), ("tell_frac", C.c_uint32), ("lbrr", C.c_int32)]
 
 
 SILK_MAX_FRAME = 320
@@ -169,8 +169,8 @@ def lib():
     sig("orc_silk_state_init", None, C.POINTER(SilkState))
     sig("orc_silk_decode_frame", C.c_int, C.POINTER(SilkState), vp, u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SilkSide),
         vp, vp, vp)
-    sig("orc_silk_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, u32, vp)
-    sig("orc_silk_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, C.c_int, u32, C.c_int, vp)
+    sig("orc_silk_packet", C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, u32, u32, vp)
+    sig("orc_silk_fill", C.c_int, C.c_uint64, u32, C.c_uint64, u32, C.c_int, C.c_int, C.c_int, u32, u32, C.c_int, vp)
     sig("orc_silk_bench", C.c_double, vp, u32, u32, u32, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(u32))
     _lib = L
     return L
@@ -329,10 +329,10 @@ class SynthStream:
         return pcm
 
 
-def silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads=1):
+def silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads=1, lbrr_permille=0):
     """-> uint8 [n_frames, n_streams, pkt_bytes]: SYNTH-SILK/1 packets (TOC included) from the oracle's generator"""
     out = np.zeros((n_frames, n_streams, pkt_bytes), np.uint8)
-    rc = lib().orc_silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, n_threads, ptr(out))
+    rc = lib().orc_silk_fill(first_stream, n_streams, first_frame, n_frames, bandwidth, frame_ms, channels, pkt_bytes, lbrr_permille, n_threads, ptr(out))
     assert rc == 0, rc
     return out
 
@@ -345,14 +345,15 @@ class SilkStream:
         self.state = SilkState()
         lib().orc_silk_state_init(C.byref(self.state))
 
-    def decode(self, payload, bandwidth, frame_ms, stream_channels, lost=False):
-        """-> (SilkSide, exc int32 [2, 320], out16 int16 [2, 320], pcm float32 [frame_ms*48*channels])"""
+    def decode(self, payload, bandwidth, frame_ms, stream_channels, lost=False, fec=False):
+        """-> (SilkSide, exc int32 [2, 320], out16 int16 [2, 320], pcm float32 [frame_ms*48*channels]); fec: the packet's redundant
+        copy of the previous frame (LostFlag::DecodeFec)"""
         payload = np.frombuffer(bytes(payload), dtype=np.uint8).copy()
         side = SilkSide()
         exc = np.zeros((2, SILK_MAX_FRAME), np.int32)
         out16 = np.zeros((2, SILK_MAX_FRAME), np.int16)
         pcm = np.zeros(frame_ms * 48 * self.channels, np.float32)
         r = lib().orc_silk_decode_frame(C.byref(self.state), ptr(payload) if len(payload) else None, len(payload), bandwidth, frame_ms,
-                                       stream_channels, self.channels, int(lost), C.byref(side), ptr(exc), ptr(out16), ptr(pcm))
+                                       stream_channels, self.channels, 2 if fec else int(lost), C.byref(side), ptr(exc), ptr(out16), ptr(pcm))
         assert r == frame_ms * 48, r
         return side, exc, out16, pcm

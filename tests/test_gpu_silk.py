@@ -267,3 +267,75 @@ def test_silk_decode_i16_matches_oracle():
             w16 = np.clip(w * np.float32(32768.0), -32768.0, 32767.0).astype(np.int16)
             assert np.abs(out[s].astype(np.int32) - w16.astype(np.int32)).max() <= 1, (f, s)
     assert np.abs(out).max() > 1000
+
+
+@pytest.mark.parametrize("bw,ms,cs,pkt_bytes", [(2, 20, 1, 170), (2, 20, 2, 330), (0, 10, 1, 90)])
+def test_silk_lbrr_packets_and_fec_decode_match_oracle(bw, ms, cs, pkt_bytes):
+    """Packets with and without the in-band redundant copy of the previous frame (LBRR): the regular decode walks through the
+    copy, decode_fec decodes the copy instead (LostFlag::DecodeFec) and conceals when the packet has none -- symbols, excitation,
+    internal-rate samples and PCM against the oracle."""
+    n = 64
+    packets = opn.silk_fill(21, n, 0, 1, bw, ms, cs, pkt_bytes, lbrr_permille=500)[0]
+    assert np.array_equal(packets, O.silk_fill(21, n, 0, 1, bw, ms, cs, pkt_bytes, lbrr_permille=500)[0])
+    _check_frames(packets, bw, ms, cs, cs)
+    fs, nb_subfr = FS_KHZ[bw], ms // 5
+    L = nb_subfr * 5 * fs
+    offs = (np.arange(n) * pkt_bytes).astype(np.uint32)
+    lens = np.full(n, pkt_bytes, np.uint32)
+    side, exc, out16, pcm, res = opn.op_silk_frames(packets.reshape(-1), offs, lens, cs, cs, ms * 48, decode_fec=True)
+    assert np.all(res == ms * 48)
+    with_copy = 0
+    for i in range(n):
+        w_side, w_exc, w_out16, w_pcm = O.SilkStream(cs).decode(packets[i, 1:], bw, ms, cs, fec=True)
+        with_copy += w_side.lbrr
+        assert side[i]["lbrr"] == w_side.lbrr
+        if w_side.lbrr:
+            _side_equal(side[i], w_side, cs, nb_subfr, 16 if fs == 16 else 10, (L + 15) // 16, f"fec {i}")
+            assert np.array_equal(exc[i, :cs, :L], w_exc[:cs, :L]), i
+        assert np.array_equal(out16[i, :cs, :L], w_out16[:cs, :L]), i
+        assert np.array_equal(pcm[i], w_pcm), i
+    assert 10 < with_copy < n - 10
+
+
+def test_silk_fec_recovers_a_lost_packet_on_the_batch_path_and_the_decoder_api():
+    """The use decode_fec exists for (decoder.rs:343-386): packet 3 never arrives; the caller decodes packet 4 with decode_fec (the
+    redundant copy of frame 3, or concealment where packet 4 has none), then packet 4 normally.  Host-buffer batch call with
+    OPN_FLAG_DECODE_FEC and the single-stream Decoder::decode_float(.., decode_fec = true), the latter also with a row of two packet
+    frames (one concealed, then the copy), against the oracle doing the same."""
+    ns, nfr, nb, channels = 90, 6, 170, 1
+    packets = opn.silk_fill(300, ns, 0, nfr, 2, 20, channels, nb, lbrr_permille=700)
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    oracle = [O.SilkStream(channels) for _ in range(ns)]
+    offs = (np.arange(ns) * nb).astype(np.uint32)
+    lens = np.full(ns, nb, np.uint32)
+    pcm = np.zeros((ns, 960), np.float32)
+    for f in range(nfr):
+        if f == 3:
+            continue  # lost on the way
+        if f == 4:
+            res = dec.decode_float(packets[4].reshape(-1), offs, lens, pcm, 960, flags=opn.FLAG_DECODE_FEC)
+            assert np.all(res == 960)
+            for s in range(ns):
+                assert np.array_equal(oracle[s].decode(packets[4, s, 1:], 2, 20, channels, fec=True)[3], pcm[s]), s
+        res = dec.decode_float(packets[f].reshape(-1), offs, lens, pcm, 960)
+        assert np.all(res == 960)
+        for s in range(ns):
+            assert np.array_equal(oracle[s].decode(packets[f, s, 1:], 2, 20, channels)[3], pcm[s]), (f, s)
+    # single stream, frame_size = two packet frames: 20 ms concealed, then the redundant copy
+    one = opn.Decoder(opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    st = O.SilkStream(channels)
+    pk = packets[:, 7]
+    out = np.zeros(960, np.float32)
+    for f in range(2):
+        assert one.decode_float(pk[f], out, 960) == 960
+        assert np.array_equal(st.decode(pk[f, 1:], 2, 20, channels)[3], out)
+    out2 = np.zeros(1920, np.float32)
+    assert one.decode_float(pk[4], out2, 1920, decode_fec=True) == 1920   # packets 2 and 3 lost
+    want = np.concatenate([st.decode(b"", 2, 20, channels, lost=True)[3], st.decode(pk[4, 1:], 2, 20, channels, fec=True)[3]])
+    assert np.array_equal(want, out2)
+    assert one.decode_float(pk[4], out, 960) == 960
+    assert np.array_equal(st.decode(pk[4, 1:], 2, 20, channels)[3], out)
+    # a CELT packet has no FEC: everything is concealed (decoder.rs:345-350)
+    cp = opn.synth_fill(1, 1, 0, 1, 3, channels, 100)[0, 0]
+    assert one.decode_float(cp, out, 960, decode_fec=True) == 960
+    assert np.array_equal(st.decode(b"", 2, 20, channels, lost=True)[3], out)
