@@ -167,11 +167,6 @@ __global__ void __launch_bounds__(32) k_silk_rangedec(SilkArgs A)
     A.hdr[stream] = make_uint4((uint32_t)fs_khz, d.rng, tf, 0u);
 }
 
-// named barriers (ids 1..15; 0 is __syncthreads): the producer arrives, the consumers wait
-__device__ __forceinline__ void silk_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void silk_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-constexpr int SILK_CHUNK = 64;  // samples of the recursion between two hand-overs to the resampler warps
-
 // ------------------------------------------------------------------------------------------------- frame kernel
 // t / up and t % up for up in {3, 4, 6} without a runtime division
 __device__ __forceinline__ void silk_divmod(int t, int up, int &q, int &r)
@@ -187,13 +182,13 @@ constexpr size_t silk_frame_smem() { return (size_t)((SILK_MAX_FRAME + SILK_LEAD
 // stores: y[UP i + p] = sum_j h[p][j] x[i - j] summed in tap order, then the merge of decoder.rs:722-729 onto a zero CELT part.
 // One lane per INPUT sample: its eight-sample window is loaded once for the UP outputs it produces.
 template <int UP, int NCH, int C>
-__device__ __forceinline__ void silk_resample_store(const float *x, int ibeg, int iend, uint32_t lane, float *ring, uint32_t pos, float *dense,
-                                                    float gain, const float *rs1 /* C == 2 from one channel: history of output channel 1 */)
+__device__ __forceinline__ void silk_resample_store(const float *x, int L, uint32_t lane, float *ring, uint32_t pos, float *dense, float gain,
+                                                    const float *rs1 /* C == 2 from one channel: history of output channel 1 */)
 {
     constexpr int T = UP == 6 ? 0 : UP == 4 ? 1 : 2;
-    for (int i0 = ibeg; i0 < iend; i0 += 32) {
+    for (int i0 = 0; i0 < L; i0 += 32) {
         const int i = i0 + (int)lane;
-        if (i >= iend) continue;
+        if (i >= L) continue;
         float xv[2][8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -457,10 +452,6 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS, 4) k
                 lpc4(i0, i0 < e1 ? g0 : i0 < e2 ? g1 : i0 < e3 ? g2 : g3, true);  // subframes are multiples of 8 samples
 #pragma unroll
                 for (int k = 0; k < 16; k++) s[k] = s[k + 4];
-                if (((i0 + 4) & (SILK_CHUNK - 1)) == 0 || i0 + 4 >= L) {  // a chunk is complete: the resampler warps may take it
-                    __threadfence_block();
-                    silk_bar_arrive(1 + (i0 / SILK_CHUNK), 32 * SILK_WARPS);
-                }
             }
         } else {  // mixed bandwidths in one CTA: rows of a shorter frame idle through the tail (L is a multiple of 8)
 #pragma unroll 1
@@ -469,10 +460,6 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS, 4) k
                 lpc4(i0, i0 < e1 ? g0 : i0 < e2 ? g1 : i0 < e3 ? g2 : g3, act);
 #pragma unroll
                 for (int k = 0; k < 16; k++) s[k] = act ? s[k + 4] : s[k];
-                if (((i0 + 4) & (SILK_CHUNK - 1)) == 0 || i0 + 4 >= Lmax) {
-                    __threadfence_block();
-                    silk_bar_arrive(1 + (i0 / SILK_CHUNK), 32 * SILK_WARPS);
-                }
             }
         }
         if (fs_khz) {
@@ -484,120 +471,83 @@ template <int CS, int C> __global__ void __launch_bounds__(32 * SILK_WARPS, 4) k
             A.st.gain[chs] = nb_subfr == 4 ? g3 : g1;
         }
     }
-    else {
-        // ---- phase C: warps 1..7, one warp per item, UNDER phase B: as soon as the recursion has finished a chunk of SILK_CHUNK
-        // samples for every row (named barrier 1 + chunk: warp 0 arrives, these warps wait), its samples are converted --
-        // mid/side -> left/right, polyphase interpolation, x 1/32768, stores -- while warp 0 runs the next chunk.
-        int Lmax = nb_subfr * 5 * (int)s_meta[lane * 8];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, o));
-        constexpr int NCH = (CS == 2 && C == 2) ? 2 : 1;  // channels that go through the interpolator
-        const int n48 = A.frame_ms * 48;
-        // prologue per item: results of rows that decode nothing; the resampler's history in front of the frame
-        for (uint32_t it = warp - 1; it < ITEMS; it += SILK_WARPS - 1) {
-            const uint32_t item = item0 + it;
-            if (item >= A.item_end) continue;
-            const uint32_t row0 = it * CS;
-            const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-            const uint32_t flag = s_meta[row0 * 8 + 3];
-            if (flag == 2u) {  // rejected packet: state untouched, the error is the result
-                if (lane == 0 && A.result) A.result[stream] = A.status[stream];
-                continue;
-            }
-            if (flag == 1u) {  // lost before anything was decoded: silence, state untouched
-                const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
-                float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
-                if (dense)
-                    for (int t = (int)lane; t < n48 * C; t += 32) dense[t] = 0.0f;
-                if (lane == 0) {
-                    if (A.result) A.result[stream] = n48;
-                    if (A.final_range) A.final_range[stream] = 0u;
-                }
-                continue;
-            }
-            const bool reset = s_meta[row0 * 8 + 2];
-            const float *rs = A.st.rs + (size_t)stream * 16;
-            float *x = reinterpret_cast<float *>(s_res) + row0;
-            if (lane < 7u) {  // x[-1-j] = rs[c][j]
-#pragma unroll
-                for (int c = 0; c < NCH; c++) x[-(1 + (int)lane) * SILK_RS + c] = reset ? 0.0f : rs[c * 8 + lane];
-            }
-        }
-        __syncwarp();
-        for (int lo = 0, chunk = 0; lo < Lmax; lo += SILK_CHUNK, chunk++) {
-            silk_bar_sync(1 + chunk, 32 * SILK_WARPS);
-            for (uint32_t it = warp - 1; it < ITEMS; it += SILK_WARPS - 1) {
-                const uint32_t item = item0 + it;
-                if (item >= A.item_end) continue;
-                const uint32_t row0 = it * CS;
-                if (s_meta[row0 * 8 + 3] != 0u) continue;
-                const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-                const int fs_khz = s_meta[row0 * 8];
-                const bool reset = s_meta[row0 * 8 + 2];
-                const int L = nb_subfr * 5 * fs_khz, up = 48 / fs_khz, hi = min(lo + SILK_CHUNK, L);
-                if (lo >= L) continue;
-                const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
-                float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
-                const uint32_t pos = A.ring_pos[stream];
-                float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
-                const float *rs = A.st.rs + (size_t)stream * 16;
-                float *x = reinterpret_cast<float *>(s_res) + row0;  // sample i of coded channel c at x[i * SILK_RS + c]
-                // stream_channels -> channels (decoder.rs:332): mid/side -> left/right in place; a mono packet feeds both outputs; a
-                // mono decoder takes the mid channel of a stereo packet
-                if (NCH == 2) {
-                    for (int i = lo + (int)lane; i < hi; i += 32) {
-                        const float m = x[i * SILK_RS], sd = x[i * SILK_RS + 1];
-                        x[i * SILK_RS] = fminf(fmaxf(m + sd, -32768.0f), 32767.0f);  // sat16 of an exact integer sum
-                        x[i * SILK_RS + 1] = fminf(fmaxf(m - sd, -32768.0f), 32767.0f);
-                    }
-                    __syncwarp();
-                }
-                float rs1[8];  // a mono packet in a stereo decoder: output channel 1 keeps its own history (it differs after a stereo packet)
-                if (NCH == 1 && C == 2) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) rs1[j] = (reset || j == 7 || lo != 0) ? 0.0f : rs[8 + j];
-                }
-                const float *r1 = (NCH == 1 && C == 2 && lo == 0) ? rs1 : nullptr;
-                if (up == 3) silk_resample_store<3, NCH, C>(x, lo, hi, lane, ring, pos, dense, A.gain, r1);
-                else if (up == 4) silk_resample_store<4, NCH, C>(x, lo, hi, lane, ring, pos, dense, A.gain, r1);
-                else silk_resample_store<6, NCH, C>(x, lo, hi, lane, ring, pos, dense, A.gain, r1);
-            }
-        }
-        __syncwarp();
-        // epilogue per item: resampler history, ring cursor, results
-        for (uint32_t it = warp - 1; it < ITEMS; it += SILK_WARPS - 1) {
-            const uint32_t item = item0 + it;
-            if (item >= A.item_end) continue;
-            const uint32_t row0 = it * CS;
-            if (s_meta[row0 * 8 + 3] != 0u) continue;
-            const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
-            const int fs_khz = s_meta[row0 * 8];
-            const bool lost = s_meta[row0 * 8 + 1];
-            const int L = nb_subfr * 5 * fs_khz;
-            float *rs = A.st.rs + (size_t)stream * 16;
-            const float *x = reinterpret_cast<const float *>(s_res) + row0;
-            if (lane < 7u) {
-#pragma unroll
-                for (int c = 0; c < C; c++) rs[c * 8 + lane] = x[(L - 1 - (int)lane) * SILK_RS + (NCH == 2 ? c : 0)];
-            }
-            if (lane == 0) {
-                uint32_t np = A.ring_pos[stream] + (uint32_t)n48;
-                if (np >= (uint32_t)RING_SAMPLES) np -= RING_SAMPLES;
-                A.ring_pos[stream] = np;
-                if (!lost) {
-                    A.st.fs[2 * stream] = (uint8_t)fs_khz;
-                    A.st.fs[2 * stream + 1] = (uint8_t)CS;
-                }
-                if (A.result) A.result[stream] = n48;
-                if (A.final_range) A.final_range[stream] = lost ? 0u : A.hdr[stream].y;
-                if (A.softclip_reset && !lost) *reinterpret_cast<float2 *>(A.softclip_reset + 2 * (size_t)stream) = make_float2(0.f, 0.f);
-            }
-            if (A.out16)
-                for (int i = (int)lane; i < L; i += 32)
-                    for (int c = 0; c < C; c++) A.out16[((size_t)stream * 2 + c) * SILK_MAX_FRAME + i] = (int16_t)x[i * SILK_RS + (NCH == 2 ? c : 0)];
-        }
-    }
+    __syncthreads();
+
     const long long clk2 = A.phase_clk ? clock64() : 0;
+    // ---- phase C: one warp per item
+    for (uint32_t it = warp; it < ITEMS; it += SILK_WARPS) {
+        const uint32_t item = item0 + it;
+        if (item >= A.item_end) continue;
+        const uint32_t row0 = it * CS;
+        const uint32_t stream = A.stream_idx ? A.stream_idx[item] : item;
+        const int n48 = A.frame_ms * 48;
+        const uint32_t flag = s_meta[row0 * 8 + 3];
+        const uint32_t dense_off = (A.dense && A.dense_off) ? A.dense_off[item] : 0u;
+        float *dense = A.dense ? A.dense + (size_t)stream * A.dense_stride + dense_off : nullptr;
+        if (flag == 2u) {  // rejected packet: state untouched, the error is the result
+            if (lane == 0 && A.result) A.result[stream] = A.status[stream];
+            continue;
+        }
+        if (flag == 1u) {  // lost before anything was decoded: silence, state untouched
+            if (dense)
+                for (int t = (int)lane; t < n48 * C; t += 32) dense[t] = 0.0f;
+            if (lane == 0) {
+                if (A.result) A.result[stream] = n48;
+                if (A.final_range) A.final_range[stream] = 0u;
+            }
+            continue;
+        }
+        const int fs_khz = s_meta[row0 * 8];
+        const bool lost = s_meta[row0 * 8 + 1], reset = s_meta[row0 * 8 + 2];
+        const int L = nb_subfr * 5 * fs_khz, up = 48 / fs_khz;
+        const uint32_t pos = A.ring_pos[stream];
+        float *ring = A.ring + (size_t)stream * RING_SAMPLES * C;
+        float *rs = A.st.rs + (size_t)stream * 16;
+        float *x = reinterpret_cast<float *>(s_res) + row0;  // sample i of coded channel c at x[i * SILK_RS + c]
+        constexpr int NCH = (CS == 2 && C == 2) ? 2 : 1;      // channels that go through the interpolator
+        // stream_channels -> channels (decoder.rs:332): mid/side -> left/right in place; a mono packet feeds both outputs; a mono
+        // decoder takes the mid channel of a stereo packet
+        if (NCH == 2) {
+            for (int i = (int)lane; i < L; i += 32) {
+                const float m = x[i * SILK_RS], sd = x[i * SILK_RS + 1];
+                x[i * SILK_RS] = fminf(fmaxf(m + sd, -32768.0f), 32767.0f);  // sat16 of an exact integer sum
+                x[i * SILK_RS + 1] = fminf(fmaxf(m - sd, -32768.0f), 32767.0f);
+            }
+        }
+        if (lane < 7u) {  // resampler history in front of the frame: x[-1-j] = rs[c][j]
+#pragma unroll
+            for (int c = 0; c < NCH; c++) x[-(1 + (int)lane) * SILK_RS + c] = reset ? 0.0f : rs[c * 8 + lane];
+        }
+        float rs1[8];  // a mono packet in a stereo decoder: output channel 1 keeps its own history (it differs after a stereo packet)
+        if (NCH == 1 && C == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) rs1[j] = (reset || j == 7) ? 0.0f : rs[8 + j];
+        }
+        __syncwarp();
+        const float *r1 = (NCH == 1 && C == 2) ? rs1 : nullptr;
+        if (up == 3) silk_resample_store<3, NCH, C>(x, L, lane, ring, pos, dense, A.gain, r1);
+        else if (up == 4) silk_resample_store<4, NCH, C>(x, L, lane, ring, pos, dense, A.gain, r1);
+        else silk_resample_store<6, NCH, C>(x, L, lane, ring, pos, dense, A.gain, r1);
+        if (lane < 7u) {
+#pragma unroll
+            for (int c = 0; c < C; c++) rs[c * 8 + lane] = x[(L - 1 - (int)lane) * SILK_RS + (NCH == 2 ? c : 0)];
+        }
+        if (lane == 0) {
+            uint32_t np = pos + (uint32_t)n48;
+            if (np >= (uint32_t)RING_SAMPLES) np -= RING_SAMPLES;
+            A.ring_pos[stream] = np;
+            if (!lost) {
+                A.st.fs[2 * stream] = (uint8_t)fs_khz;
+                A.st.fs[2 * stream + 1] = (uint8_t)CS;
+            }
+            if (A.result) A.result[stream] = n48;
+            if (A.final_range) A.final_range[stream] = lost ? 0u : A.hdr[stream].y;
+            if (A.softclip_reset && !lost) *reinterpret_cast<float2 *>(A.softclip_reset + 2 * (size_t)stream) = make_float2(0.f, 0.f);
+        }
+        if (A.out16)
+            for (int i = (int)lane; i < L; i += 32)
+                for (int c = 0; c < C; c++) A.out16[((size_t)stream * 2 + c) * SILK_MAX_FRAME + i] = (int16_t)x[i * SILK_RS + (NCH == 2 ? c : 0)];
+    }
     if (A.phase_clk) {  // measurement only (OPN_SILK_CLK=1): cycles per phase summed over the CTAs
         __syncthreads();
         if (threadIdx.x == 0) {
