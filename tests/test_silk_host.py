@@ -103,3 +103,23 @@ def test_oracle_channel_mapping():
     l, r = lr16[0].astype(np.int64), lr16[1].astype(np.int64)
     ok = (np.abs(l) < 32767) & (np.abs(r) < 32767)
     assert ok.sum() > 200 and np.array_equal((l + r)[ok], 2 * m[ok])
+
+
+def test_oracle_fec_decodes_the_redundant_copy():
+    """decode_fec (LostFlag::DecodeFec): the packet's leading redundant block is decoded instead of its regular frame; a packet
+    without one conceals; the regular decode of a packet with a copy walks through it and decodes what follows."""
+    with_copy = O.silk_fill(4, 1, 0, 3, 2, 20, 1, 170, lbrr_permille=1000)[:, 0]
+    without = O.silk_fill(4, 1, 0, 3, 2, 20, 1, 170, lbrr_permille=0)[:, 0]
+    a = O.SilkStream(1)
+    a.decode(with_copy[0, 1:], 2, 20, 1)
+    fec_side, _, _, fec_pcm = a.decode(with_copy[1, 1:], 2, 20, 1, fec=True)
+    reg_side, _, _, reg_pcm = a.decode(with_copy[1, 1:], 2, 20, 1)
+    assert fec_side.lbrr == 1 and reg_side.lbrr == 1
+    assert fec_side.tell_frac < reg_side.tell_frac          # the copy comes first, the regular frame after it
+    assert not np.array_equal(fec_pcm, reg_pcm) and np.abs(fec_pcm).max() > 0
+    b = O.SilkStream(1)
+    b.decode(without[0, 1:], 2, 20, 1)
+    side, _, _, pcm = b.decode(without[1, 1:], 2, 20, 1, fec=True)
+    c = O.SilkStream(1)
+    c.decode(without[0, 1:], 2, 20, 1)
+    assert side.lbrr == 0 and np.array_equal(pcm, c.decode(b"", 2, 20, 1, lost=True)[3])   # no copy: concealment
