@@ -339,3 +339,89 @@ def test_silk_fec_recovers_a_lost_packet_on_the_batch_path_and_the_decoder_api()
     cp = opn.synth_fill(1, 1, 0, 1, 3, channels, 100)[0, 0]
     assert one.decode_float(cp, out, 960, decode_fec=True) == 960
     assert np.array_equal(st.decode(b"", 2, 20, channels, lost=True)[3], out)
+
+
+def _plc_frames(frame_size, last_nf):
+    """decode_native(None): the sizes decode_frame(None) is called with (decoder.rs:427-441, 467-513)"""
+    out, done = [], 0
+    while done < frame_size:
+        a = min(frame_size - done, last_nf)
+        if a > 960:
+            a = 960
+        elif a < 960:
+            if a > 480:
+                a = 480
+            elif 240 < a < 480:
+                a = 240
+        out.append(a)
+        done += a
+    return out
+
+
+def test_random_mix_of_celt_silk_and_lost_packets_per_stream():
+    """Every stream draws, step by step, a CELT packet (10 or 20 ms), a SILK packet (NB / MB / WB, 10 or 20 ms) or a loss, with
+    a row of 20 ms per call: mode changes in both directions (resets, the CELT -> SILK cross-fade), concealment by the codec of
+    the previous packet in frames of its size, rows partly filled by 10 ms packets.  The oracle composes the same per stream."""
+    rng = np.random.default_rng(2026)
+    ns, nsteps, channels, nb = 120, 14, 2, 340
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    celt = [O.SynthStream(3, channels) for _ in range(ns)]
+    silk = [O.SilkStream(channels) for _ in range(ns)]
+    mode = [None] * ns       # "celt" / "silk": codec of the last packet
+    last_nf = [120] * ns
+    offs = (np.arange(ns) * nb).astype(np.uint32)
+    pcm = np.zeros((ns, 960 * channels), np.float32)
+    n2 = 120 * channels
+    for step in range(nsteps):
+        arena = np.zeros((ns, nb), np.uint8)
+        lens = np.zeros(ns, np.uint32)
+        kind = rng.choice(["celt", "silk", "lost"], size=ns, p=[0.4, 0.4, 0.2])
+        want = np.zeros((ns, 960 * channels), np.float32)
+        for s in range(ns):
+            if kind[s] == "lost":
+                if mode[s] is None:
+                    continue                                     # nothing decoded yet: zeros, state untouched
+                at = 0
+                for a in _plc_frames(960, last_nf[s]):
+                    if mode[s] == "celt":
+                        w = celt[s].conceal({240: 1, 480: 2, 960: 3}[a])
+                    else:
+                        w = silk[s].decode(b"", 2, a // 48, channels, lost=True)[3]
+                    want[s, at * channels:(at + a) * channels] = w
+                    at += a
+                continue
+            ms = int(rng.choice([10, 20]))
+            nf = ms * 48
+            if kind[s] == "celt":
+                lm = 2 if ms == 10 else 3
+                size = 112 if ms == 10 else 160
+                pk = opn.synth_fill(1000 + s, 1, step, 1, lm, channels, size)[0, 0]
+                if mode[s] == "silk":
+                    celt[s] = O.SynthStream(3, channels)         # decoder.rs:703-705
+                celt[s].lm = lm
+                w = celt[s].decode(pk[1:])[3]
+                mode[s] = "celt"
+            else:
+                bw = int(rng.integers(0, 3))
+                size = 170 * channels
+                pk = opn.silk_fill(1000 + s, 1, step, 1, bw, ms, channels, size, lbrr_permille=300)[0, 0]
+                switch = mode[s] == "celt"
+                if switch:
+                    silk[s] = O.SilkStream(channels)             # decoder.rs:555-557
+                    trans = celt[s].conceal(1)                   # decoder.rs:519-543
+                w = silk[s].decode(pk[1:], bw, ms, channels)[3].copy()
+                if switch:                                       # decoder.rs:765-778
+                    faded = np.zeros(n2, np.float32)
+                    O.lib().orc_smooth_fade(O.ptr(trans[n2:2 * n2].copy()), O.ptr(w[n2:2 * n2].copy()), O.ptr(faded), 120, channels, 48000)
+                    w[:n2] = trans[:n2]
+                    w[n2:2 * n2] = faded
+                mode[s] = "silk"
+            arena[s, :len(pk)] = pk
+            lens[s] = len(pk)
+            last_nf[s] = nf
+            want[s, :nf * channels] = w
+        res = dec.decode_float(arena.reshape(-1), offs, lens, pcm, 960)
+        for s in range(ns):
+            expect = 960 if kind[s] == "lost" else last_nf[s]
+            assert res[s] == expect, (step, s, kind[s], res[s])
+            assert np.array_equal(want[s], pcm[s]), (step, s, kind[s], mode[s])
