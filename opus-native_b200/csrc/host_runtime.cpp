@@ -237,7 +237,9 @@ int batch_alloc_staging(opn_batch *b, opn_batch::Staging &g, size_t arena_bytes,
     if (dense_floats > g.dense_cap) {
         if (g.d_dense) cudaFree(g.d_dense);
         g.dense_cap = dense_floats;
-        CU(cudaMalloc(&g.d_dense, (size_t)b->n * g.dense_cap * sizeof(float)));
+        // a SILK-capable batch keeps 5 ms per stream BEHIND the rows (at n * dense_cap + 240 C i): the transition buffer of a
+        // CELT -> SILK switch (decoder.rs:519-543); the rows themselves stay contiguous for the PCM download
+        CU(cudaMalloc(&g.d_dense, (size_t)b->n * (g.dense_cap + (b->silk ? 240 * (size_t)b->cfg.channels : 0)) * sizeof(float)));
     }
     if (conv_esize && (g.dense_cap > g.conv_cap || conv_esize > g.conv_esize)) {
         if (g.d_conv) cudaFree(g.d_conv);
@@ -1050,9 +1052,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
         const int fc = opn_packet_frame_count(arena + offsets[i], lens[i]);
         items_ub += (fc > 0 ? (size_t)fc : 1) + (b->silk ? 1 : 0);  // + the concealed frame of a CELT -> SILK transition
     }
-    // a SILK-capable batch keeps 5 ms behind every dense row: the transition buffer of a CELT -> SILK switch (decoder.rs:519-543)
-    const size_t row_floats = (frame_size * (size_t)C + 3) & ~(size_t)3;
-    const size_t dense_stride = row_floats + (b->silk ? 240 * (size_t)C : 0);
+    const size_t dense_stride = (frame_size * (size_t)C + 3) & ~(size_t)3;
     const int slot = b->stg_next;
     b->stg_next ^= 1;
     opn_batch::Staging &g = b->stg[slot];
@@ -1185,7 +1185,8 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 if (b->have_mode[i] == 1 + OPN_MODE_CELT) {
                     silk_resets.push_back(i);  // decoder.rs:555-557: silk_dec.reset()
                     // decoder.rs:519-543, 674-676: the CELT decoder conceals 5 ms into the transition buffer (the tail of the row)
-                    items.push_back(Item{i, 0u, 0u, (uint32_t)row_floats, 1, -1, C});
+                    // (its "row offset" reaches from the stream's row to its slot in the tail area behind all rows)
+                    items.push_back(Item{i, 0u, 0u, (uint32_t)((size_t)(n - i) * g.dense_cap + (size_t)i * 240 * C), 1, -1, C});
                 }
                 if ((size_t)count * (size_t)pfs < frame_size) any_gap = true;
                 res[i] = count * pfs;
@@ -1277,7 +1278,7 @@ static int batch_decode_host(opn_batch *b, const uint8_t *arena, const uint32_t 
                 CU(cudaMemcpyAsync(g.d_trans + s0, g.h_trans + s0, silk_resets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream_up));
                 CU(cudaEventRecord(b->ev_in, b->stream_up));
                 CU(cudaStreamWaitEvent(b->stream, b->ev_in, 0));
-                CU(launch_transition_fade(g.d_dense, g.dense_cap, g.d_trans + s0, (uint32_t)silk_resets.size(), (uint32_t)row_floats, C, b->stream));
+                CU(launch_transition_fade(g.d_dense, g.dense_cap, g.d_trans + s0, (uint32_t)silk_resets.size(), n, C, b->stream));
             }
         }
         if (want_pcm && pcm_conv) {

@@ -603,11 +603,11 @@ cudaError_t launch_silk_frame(const SilkArgs &a0, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_transition_fade(float *dense, size_t dense_stride, const uint32_t *d_streams, uint32_t n_streams, uint32_t tail_off, int channels,
+cudaError_t launch_transition_fade(float *dense, size_t dense_stride, const uint32_t *d_streams, uint32_t n_streams, uint32_t n_rows, int channels,
                                    cudaStream_t st)
 {
     if (n_streams == 0) return cudaSuccess;
-    k_transition_fade<<<n_streams, 128, 0, st>>>(dense, dense_stride, d_streams, tail_off, channels);
+    k_transition_fade<<<n_streams, 128, 0, st>>>(dense, dense_stride, d_streams, n_rows, channels);
     return cudaGetLastError();
 }
 

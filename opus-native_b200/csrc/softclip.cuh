@@ -167,13 +167,14 @@ __global__ void __launch_bounds__(128) k_op_smooth_fade(const float *in1, const 
 }
 
 // The cross-fade decode_frame applies when a stream switches from CELT to SILK (src/decoder.rs:519-543, 674-676, 765-788): the old
-// decoder conceals 5 ms into a transition buffer (here: the tail of the stream's dense row, at `tail_off` floats); the first 2.5 ms of
+// decoder conceals 5 ms into a transition buffer (here: the stream's 240 C floats behind the n_rows dense rows); the first 2.5 ms of
 // the new frame are replaced by it, the next 2.5 ms are smooth_fade_into_in2(transition, samples) = w^2 samples + (1 - w^2) transition.
 // One CTA per listed stream, f2_5 = 120 samples at 48 kHz.
-__global__ void __launch_bounds__(128) k_transition_fade(float *dense, size_t dense_stride, const uint32_t *streams, uint32_t tail_off, int channels)
+__global__ void __launch_bounds__(128) k_transition_fade(float *dense, size_t dense_stride, const uint32_t *streams, uint32_t n_rows, int channels)
 {
-    float *row = dense + (size_t)streams[blockIdx.x] * dense_stride;
-    const float *tr = row + tail_off;
+    const uint32_t stream = streams[blockIdx.x];
+    float *row = dense + (size_t)stream * dense_stride;
+    const float *tr = dense + (size_t)n_rows * dense_stride + (size_t)stream * 240 * channels;  // the tail area behind all rows
     const int n = 120 * channels;
     for (int j = (int)threadIdx.x; j < n; j += 128) {
         const float wv = g_tab.window[j / channels];
