@@ -425,3 +425,27 @@ def test_random_mix_of_celt_silk_and_lost_packets_per_stream():
             expect = 960 if kind[s] == "lost" else last_nf[s]
             assert res[s] == expect, (step, s, kind[s], res[s])
             assert np.array_equal(want[s], pcm[s]), (step, s, kind[s], mode[s])
+
+
+def test_silk_multi_frame_packets():
+    """Code-1 packets (two equal frames behind one TOC, lib.rs:345-498): decode_native runs decode_frame per frame, each frame
+    with its own range decoder; on the batch path the two frames of a stream are two items of consecutive waves."""
+    ns, channels, nb = 70, 2, 171
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    oracle = [O.SilkStream(channels) for _ in range(ns)]
+    offs = (np.arange(ns) * (2 * nb)).astype(np.uint32)
+    pcm = np.zeros((ns, 1920 * channels), np.float32)
+    for step in range(3):
+        bw = step % 3
+        single = opn.silk_fill(700, ns, 2 * step, 2, bw, 20, channels, nb, lbrr_permille=200)   # [2, ns, nb], each with its own TOC
+        arena = np.zeros((ns, 2 * nb), np.uint8)
+        arena[:, 0] = single[0, :, 0] | 1                       # code 1: two frames of equal size
+        arena[:, 1:nb] = single[0, :, 1:]
+        arena[:, nb:2 * nb - 1] = single[1, :, 1:]
+        lens = np.full(ns, 2 * nb - 1, np.uint32)
+        res = dec.decode_float(arena.reshape(-1), offs, lens, pcm, 1920)
+        assert np.all(res == 1920), res
+        for s in range(ns):
+            a = oracle[s].decode(single[0, s, 1:], bw, 20, channels)[3]
+            b = oracle[s].decode(single[1, s, 1:], bw, 20, channels)[3]
+            assert np.array_equal(np.concatenate([a, b]), pcm[s]), (step, s)
