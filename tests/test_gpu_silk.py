@@ -449,3 +449,27 @@ def test_silk_multi_frame_packets():
             a = oracle[s].decode(single[0, s, 1:], bw, 20, channels)[3]
             b = oracle[s].decode(single[1, s, 1:], bw, 20, channels)[3]
             assert np.array_equal(np.concatenate([a, b]), pcm[s]), (step, s)
+
+
+def test_silk_reset_restores_a_fresh_decoder():
+    """Decoder::reset (decoder.rs:74, 286-303) on a batch that has decoded SILK and CELT frames: every SILK filter, the excitation
+    history, the resampler history and the host mirrors (mode, last frame size) start over -- the next frames equal a fresh batch's,
+    and a loss right after the reset is silence."""
+    ns, channels, nb = 50, 1, 96
+    dec = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    offs = (np.arange(ns) * nb).astype(np.uint32)
+    lens = np.full(ns, nb, np.uint32)
+    pcm = np.zeros((ns, 960), np.float32)
+    for f in range(3):
+        dec.decode_float(opn.silk_fill(5, ns, f, 1, 2, 20, channels, nb)[0].reshape(-1), offs, lens, pcm, 960)
+    dec.reset()
+    res = dec.decode_float(np.zeros(ns * nb, np.uint8), offs, np.zeros(ns, np.uint32), pcm, 960)
+    assert np.all(res == 960) and np.all(pcm == 0)
+    fresh = opn.BatchDecoder(ns, opn.DecoderConfiguration(48000, channels, 0), **BOTH)
+    want = np.zeros((ns, 960), np.float32)
+    for f in range(3, 5):
+        pk = opn.silk_fill(5, ns, f, 1, 1, 20, channels, nb)[0].reshape(-1)
+        dec.decode_float(pk, offs, lens, pcm, 960)
+        fresh.decode_float(pk, offs, lens, want, 960)
+        assert np.array_equal(pcm, want) and np.abs(want).max() > 0
+        assert np.array_equal(dec.final_ranges(), fresh.final_ranges())
